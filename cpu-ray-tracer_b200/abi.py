@@ -1,0 +1,73 @@
+"""ctypes mirror of include/rt_b200.h (the C-ABI).  Field order and types must match the header exactly;
+tests/test_abi.py checks the struct sizes against the sizes the compiled library reports."""
+import ctypes as C
+
+import numpy as np
+
+RT_OK, RT_ERR_INVALID, RT_ERR_NO_DEVICE, RT_ERR_CUDA, RT_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
+RT_SCENE_FLAT, RT_SCENE_TLAS = 0, 1
+RT_SCENE_FLAG_COUNTERS = 1
+RT_INTEGRATOR_WHITTED, RT_INTEGRATOR_PATH = 0, 1
+RT_SEED_REFERENCE_TILE, RT_SEED_PER_PIXEL = 0, 1
+
+f3 = C.c_float * 3
+f16 = C.c_float * 16
+
+
+class rt_blas_desc(C.Structure):
+    _fields_ = [("nodes", C.c_void_p), ("node_count", C.c_uint32),
+                ("tris", C.c_void_p), ("tri_indices", C.c_void_p), ("tri_count", C.c_uint32),
+                ("T", f16), ("inv_T", f16), ("obj_idx", C.c_int32), ("mat_idx", C.c_int32)]
+
+
+class rt_material(C.Structure):
+    _fields_ = [("reflectivity", C.c_float), ("refractivity", C.c_float), ("absorption", f3),
+                ("albedo", f3), ("is_light", C.c_int32), ("texture", C.c_int32)]
+
+
+class rt_texture(C.Structure):
+    _fields_ = [("pixels", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32)]
+
+
+class rt_scene_desc(C.Structure):
+    _fields_ = [("kind", C.c_int32),
+                ("blas", C.POINTER(rt_blas_desc)), ("blas_count", C.c_uint32),
+                ("tlas_nodes", C.c_void_p), ("tlas_node_count", C.c_uint32),
+                ("obj_material", C.c_void_p), ("obj_count", C.c_uint32),
+                ("materials", C.c_void_p), ("material_count", C.c_uint32),
+                ("textures", C.POINTER(rt_texture)), ("texture_count", C.c_uint32),
+                ("skydome_texture", C.c_int32), ("floor_texture", C.c_int32),
+                ("floor_n", f3), ("floor_d", C.c_float), ("floor_invto", C.c_float),
+                ("light_T", f16), ("light_inv_T", f16), ("light_size", C.c_float),
+                ("light_color", f3), ("light_pos", f3)]
+
+
+class rt_camera(C.Structure):
+    _fields_ = [("pos", f3), ("top_left", f3), ("top_right", f3), ("bottom_left", f3)]
+
+
+class rt_render_params(C.Structure):
+    _fields_ = [("integrator", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
+                ("depth_limit", C.c_int32), ("epsilon", C.c_float), ("seed_mode", C.c_int32),
+                ("tile_begin", C.c_int32), ("tile_end", C.c_int32), ("max_frames_in_flight", C.c_int32)]
+
+
+class rt_counters(C.Structure):
+    _fields_ = [("extension_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("paths", C.c_uint64),
+                ("wavefront_iterations", C.c_uint64), ("kernel_launches", C.c_uint64)]
+
+
+# numpy record layouts of the POD arrays (same bytes as the reference's structs)
+NODE_DTYPE = np.dtype([("aabb_min", "<f4", 3), ("aabb_max", "<f4", 3), ("left_first", "<u4"), ("tri_count", "<u4")])
+TRI_DTYPE = np.dtype([("v0", "<f4", 3), ("v1", "<f4", 3), ("v2", "<f4", 3),
+                      ("n0", "<f4", 3), ("n1", "<f4", 3), ("n2", "<f4", 3),
+                      ("uv0", "<f4", 2), ("uv1", "<f4", 2), ("uv2", "<f4", 2),
+                      ("centroid", "<f4", 3), ("obj_idx", "<i4")])
+TLAS_NODE_DTYPE = np.dtype([("aabb_min", "<f4", 3), ("left_right", "<u4"), ("aabb_max", "<f4", 3), ("blas", "<u4")])
+MATERIAL_DTYPE = np.dtype([("reflectivity", "<f4"), ("refractivity", "<f4"), ("absorption", "<f4", 3),
+                           ("albedo", "<f4", 3), ("is_light", "<i4"), ("texture", "<i4")])
+RAY_DTYPE = np.dtype([("O", "<f4", 3), ("tmax", "<f4"), ("D", "<f4", 3), ("inside", "<i4")])
+HIT_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("obj_idx", "<i4"), ("tri_idx", "<i4"),
+                      ("traversed", "<i4"), ("tested", "<i4"), ("reserved", "<i4")])
+assert NODE_DTYPE.itemsize == 32 and TRI_DTYPE.itemsize == 112 and TLAS_NODE_DTYPE.itemsize == 32
+assert MATERIAL_DTYPE.itemsize == 40 and RAY_DTYPE.itemsize == 32 and HIT_DTYPE.itemsize == 32

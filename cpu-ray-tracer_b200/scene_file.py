@@ -1,0 +1,140 @@
+""".rtscene: the flattened scene the C-ABI consumes, as a chunk file (host-side data format).
+
+A flattened scene is exactly what the reference's FileScene / TLASFileScene hold after their
+constructors ran (file_scene.cpp:4-62, tlas_file_scene.cpp:4-93), in the reference's own POD layouts:
+
+    header       scalars: kind, skydome/floor texture ids, floor plane, light quad, light colour/pos
+    blas_table   per BLAS: node/tri ranges into the shared arrays, T, invT, objIdx, matIdx
+    nodes        BVHNode[]   (32 B, blas_bvh.h:13-20)       all BLAS concatenated
+    tris         Tri[]       (112 B, helper.h:6-26)
+    tri_indices  uint[]      (per-BLAS local indices)
+    tlas_nodes   TLASBVHNode[] (32 B, tlas_bvh.h:7-14)      TLAS scenes only
+    obj_material int[]       material index of object (objIdx - 2)
+    materials    rt_material[]
+    tex_table    per texture: offset into tex_pixels, width, height
+    tex_pixels   uint[]      packed 0x00RRGGBB (texture.h:31-34)
+
+File layout: "RTSCN001", u32 chunk count, u32 pad, then per chunk: char name[24], u64 nbytes, payload
+padded to 8 bytes.  A ".gz" suffix means the whole file is gzip-compressed.
+Writers: oracle/ref_build/ref_api.cpp (from the reference's own loaders) and FlatScene.save (synthetic
+scenes built by host_build.py).
+"""
+import ctypes as C
+import gzip
+import struct
+
+import numpy as np
+
+from . import abi
+
+HEADER_DTYPE = np.dtype([("kind", "<i4"), ("skydome_texture", "<i4"), ("floor_texture", "<i4"), ("reserved", "<i4"),
+                         ("floor_n", "<f4", 3), ("floor_d", "<f4"), ("floor_invto", "<f4"),
+                         ("light_T", "<f4", 16), ("light_inv_T", "<f4", 16), ("light_size", "<f4"),
+                         ("light_color", "<f4", 3), ("light_pos", "<f4", 3)])
+BLAS_TABLE_DTYPE = np.dtype([("node_offset", "<u4"), ("node_count", "<u4"), ("tri_offset", "<u4"), ("tri_count", "<u4"),
+                             ("T", "<f4", 16), ("inv_T", "<f4", 16), ("obj_idx", "<i4"), ("mat_idx", "<i4")])
+TEX_TABLE_DTYPE = np.dtype([("pixel_offset", "<u8"), ("width", "<i4"), ("height", "<i4")])
+
+_CHUNK_DTYPES = {
+    "header": HEADER_DTYPE, "blas_table": BLAS_TABLE_DTYPE, "nodes": abi.NODE_DTYPE, "tris": abi.TRI_DTYPE,
+    "tri_indices": np.dtype("<u4"), "tlas_nodes": abi.TLAS_NODE_DTYPE, "obj_material": np.dtype("<i4"),
+    "materials": abi.MATERIAL_DTYPE, "tex_table": TEX_TABLE_DTYPE, "tex_pixels": np.dtype("<u4"),
+}
+
+
+class FlatScene:
+    """Host-side container of the flattened arrays; builds the rt_scene_desc handed over the C-ABI."""
+
+    def __init__(self, chunks):
+        self.header = chunks["header"]
+        self.blas_table = chunks["blas_table"]
+        self.nodes = chunks["nodes"]
+        self.tris = chunks["tris"]
+        self.tri_indices = chunks["tri_indices"]
+        self.tlas_nodes = chunks.get("tlas_nodes", np.zeros(0, abi.TLAS_NODE_DTYPE))
+        self.obj_material = chunks["obj_material"]
+        self.materials = chunks["materials"]
+        self.tex_table = chunks["tex_table"]
+        self.tex_pixels = chunks["tex_pixels"]
+        self._keep = None
+
+    @property
+    def kind(self):
+        return int(self.header["kind"][0])
+
+    @property
+    def triangle_count(self):
+        return int(self.tris.shape[0])
+
+    @staticmethod
+    def load(path):
+        opener = gzip.open if str(path).endswith(".gz") else open
+        with opener(path, "rb") as f:
+            data = f.read()
+        if data[:8] != b"RTSCN001":
+            raise ValueError(f"{path}: not an .rtscene file")
+        (count,) = struct.unpack_from("<I", data, 8)
+        off = 16
+        chunks = {}
+        for _ in range(count):
+            name = data[off:off + 24].split(b"\0", 1)[0].decode()
+            (nbytes,) = struct.unpack_from("<Q", data, off + 24)
+            off += 32
+            dt = _CHUNK_DTYPES[name]
+            chunks[name] = np.frombuffer(data, dtype=dt, count=nbytes // dt.itemsize, offset=off).copy()
+            off += (nbytes + 7) & ~7
+        return FlatScene(chunks)
+
+    def save(self, path):
+        opener = gzip.open if str(path).endswith(".gz") else open
+        names = ["header", "blas_table", "nodes", "tris", "tri_indices", "tlas_nodes", "obj_material",
+                 "materials", "tex_table", "tex_pixels"]
+        with opener(path, "wb") as f:
+            f.write(b"RTSCN001" + struct.pack("<II", len(names), 0))
+            for name in names:
+                raw = np.ascontiguousarray(getattr(self, name)).tobytes()
+                f.write(name.encode().ljust(24, b"\0") + struct.pack("<Q", len(raw)) + raw)
+                f.write(b"\0" * (((len(raw) + 7) & ~7) - len(raw)))
+
+    def desc(self):
+        """rt_scene_desc whose pointers reference this object's numpy arrays (kept alive by self)."""
+        h = self.header[0]
+        nb = len(self.blas_table)
+        blas = (abi.rt_blas_desc * nb)()
+        for i, b in enumerate(self.blas_table):
+            blas[i].nodes = self.nodes.ctypes.data + int(b["node_offset"]) * 32
+            blas[i].node_count = int(b["node_count"])
+            blas[i].tris = self.tris.ctypes.data + int(b["tri_offset"]) * 112
+            blas[i].tri_indices = self.tri_indices.ctypes.data + int(b["tri_offset"]) * 4
+            blas[i].tri_count = int(b["tri_count"])
+            blas[i].T = abi.f16(*b["T"].tolist())
+            blas[i].inv_T = abi.f16(*b["inv_T"].tolist())
+            blas[i].obj_idx = int(b["obj_idx"])
+            blas[i].mat_idx = int(b["mat_idx"])
+        nt = len(self.tex_table)
+        tex = (abi.rt_texture * max(nt, 1))()
+        for i, t in enumerate(self.tex_table):
+            tex[i].pixels = self.tex_pixels.ctypes.data + int(t["pixel_offset"]) * 4
+            tex[i].width, tex[i].height = int(t["width"]), int(t["height"])
+        d = abi.rt_scene_desc()
+        d.kind = int(h["kind"])
+        d.blas = C.cast(blas, C.POINTER(abi.rt_blas_desc))
+        d.blas_count = nb
+        d.tlas_nodes = self.tlas_nodes.ctypes.data if len(self.tlas_nodes) else None
+        d.tlas_node_count = len(self.tlas_nodes)
+        d.obj_material = self.obj_material.ctypes.data
+        d.obj_count = len(self.obj_material)
+        d.materials = self.materials.ctypes.data
+        d.material_count = len(self.materials)
+        d.textures = C.cast(tex, C.POINTER(abi.rt_texture))
+        d.texture_count = nt
+        d.skydome_texture, d.floor_texture = int(h["skydome_texture"]), int(h["floor_texture"])
+        d.floor_n = abi.f3(*h["floor_n"].tolist())
+        d.floor_d, d.floor_invto = float(h["floor_d"]), float(h["floor_invto"])
+        d.light_T = abi.f16(*h["light_T"].tolist())
+        d.light_inv_T = abi.f16(*h["light_inv_T"].tolist())
+        d.light_size = float(h["light_size"])
+        d.light_color = abi.f3(*h["light_color"].tolist())
+        d.light_pos = abi.f3(*h["light_pos"].tolist())
+        self._keep = (blas, tex)
+        return d

@@ -1,0 +1,244 @@
+/* rt_b200.h — C-ABI of the B200-native ray core (drop-in for the hot path of willake/cpu-ray-tracer).
+ *
+ * The reference has no plugin/FFI boundary; the seam is two C++ class surfaces:
+ *   - BaseScene virtuals  FindNearest / IsOccluded / GetHitInfo / GetSkyColor / GetLightPos / GetLightColor
+ *     (infra/scene/base_scene.h:16-32, implemented by FileScene file_scene.cpp:142-214 and TLASFileScene
+ *     tlas_file_scene.cpp:173-260), and
+ *   - Renderer : TheApp    Init / Tick / Trace / Sample + public `accumulator`, `camera`, `spp`, `passes`,
+ *     `depthLimit` (2. WhittedStyle/renderer.h:41-61, 3. PathTracer/renderer.h:29-53).
+ * This header is what a binding of those two surfaces calls.  Everything is plain C: pointers, sizes,
+ * POD structs, int status codes; no exceptions cross it.  Host-side scene/OBJ/XML/image loading and
+ * the SAH/TLAS builders stay where they are in the reference; after construction the host hands the
+ * builders' own arrays over unchanged (the POD structs below have the reference's exact memory layout,
+ * so `acc.bvhNodes.data()` etc. can be passed without conversion).
+ *
+ * All rt_* entry points are implemented in CUDA for sm_100a (cpu-ray-tracer_b200/csrc); there is no CPU
+ * fallback: without a CUDA device every compute call returns RT_ERR_NO_DEVICE.
+ */
+#ifndef RT_B200_H
+#define RT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_B200_ABI_VERSION 1
+
+typedef int rt_status;
+enum {
+    RT_OK = 0,
+    RT_ERR_INVALID = -1,    /* null / inconsistent argument */
+    RT_ERR_NO_DEVICE = -2,  /* no CUDA device: the product path never falls back to the CPU */
+    RT_ERR_CUDA = -3,       /* a CUDA call failed; rt_last_error() has the text */
+    RT_ERR_UNSUPPORTED = -4
+};
+
+/* ---- flattened scene: the reference builders' own arrays ------------------------------------ */
+
+/* = Tmpl8::BVHNode, infra/blas_bvh.h:13-20 (32 bytes). tri_count > 0 => leaf, left_first = first
+ * entry in tri_indices; else left_first = index of the left child, right child = left_first + 1. */
+typedef struct rt_bvh_node {
+    float aabb_min[3];
+    float aabb_max[3];
+    uint32_t left_first;
+    uint32_t tri_count;
+} rt_bvh_node;
+
+/* = Tri, infra/helper.h:6-26 (112 bytes). */
+typedef struct rt_tri {
+    float v0[3], v1[3], v2[3];
+    float n0[3], n1[3], n2[3];
+    float uv0[2], uv1[2], uv2[2];
+    float centroid[3];
+    int32_t obj_idx;
+} rt_tri;
+
+/* = Tmpl8::TLASBVHNode, infra/tlas_bvh.h:7-14 (32 bytes). left_right == 0 => leaf holding `blas`;
+ * else children are tlas_nodes[left_right & 0xffff] and tlas_nodes[left_right >> 16]. Node 0 = root. */
+typedef struct rt_tlas_node {
+    float aabb_min[3];
+    uint32_t left_right;
+    float aabb_max[3];
+    uint32_t blas;
+} rt_tlas_node;
+
+/* One bottom-level BVH: BVH (infra/bvh.h:38-41, FileScene::acc) or BLASBVH (infra/blas_bvh.h:44-53).
+ * T / inv_T are row-major mat4::cell arrays (identity for the flat FileScene BVH).
+ * obj_idx: the BLAS' objIdx written into hits (blas_bvh.cpp:299); -1 for the flat BVH, where the hit
+ * takes tri.obj_idx instead (bvh.cpp:220). */
+typedef struct rt_blas_desc {
+    const rt_bvh_node* nodes;
+    uint32_t node_count;            /* nodesUsed */
+    const rt_tri* tris;
+    const uint32_t* tri_indices;
+    uint32_t tri_count;
+    float T[16];
+    float inv_T[16];
+    int32_t obj_idx;
+    int32_t mat_idx;
+} rt_blas_desc;
+
+/* = Tmpl8::Material (template/material.h:36-45); texture = index into rt_scene_desc.textures or -1. */
+typedef struct rt_material {
+    float reflectivity;
+    float refractivity;
+    float absorption[3];
+    float albedo[3];
+    int32_t is_light;
+    int32_t texture;
+} rt_material;
+
+/* = Tmpl8::Texture (template/texture.h:98-103): packed 0x00RRGGBB texels, row 0 first. */
+typedef struct rt_texture {
+    const uint32_t* pixels;
+    int32_t width, height;
+} rt_texture;
+
+enum { RT_SCENE_FLAT = 0 /* FileScene, USE_BVH */, RT_SCENE_TLAS = 1 /* TLASFileScene, TLAS_USE_BVH */ };
+
+typedef struct rt_scene_desc {
+    int32_t kind;
+    const rt_blas_desc* blas;       /* RT_SCENE_FLAT: exactly one */
+    uint32_t blas_count;
+    const rt_tlas_node* tlas_nodes; /* RT_SCENE_TLAS only */
+    uint32_t tlas_node_count;
+    /* material index of object (objIdx - 2): models[i]->matIdx (file_scene.cpp:207) or
+     * blas[i]->matIdx (tlas_file_scene.cpp:237-240) */
+    const int32_t* obj_material;
+    uint32_t obj_count;
+    const rt_material* materials;
+    uint32_t material_count;
+    const rt_texture* textures;
+    uint32_t texture_count;
+    int32_t skydome_texture;        /* FileScene::skydome */
+    int32_t floor_texture;          /* primitiveMaterials[1].textureDiffuse */
+    float floor_n[3];               /* Plane floor: N, d, invto (file_scene.cpp:16, primitives.h:104-106) */
+    float floor_d;
+    float floor_invto;
+    float light_T[16];              /* Quad light (file_scene.cpp:15-19, primitives.h:324-329) */
+    float light_inv_T[16];
+    float light_size;               /* half edge */
+    float light_color[3];           /* GetLightColor(): (24,24,22) */
+    float light_pos[3];             /* GetLightPos() */
+} rt_scene_desc;
+
+/* ---- rays and hits (Ray, template/ray.h:6-41, as plain records) ------------------------------ */
+
+typedef struct rt_ray {
+    float O[3];
+    float tmax;     /* Ray::t on entry (1e34f = unbounded) */
+    float D[3];
+    int32_t inside; /* Ray::inside */
+} rt_ray;
+
+typedef struct rt_hit {
+    float t;            /* Ray::t after FindNearest (tmax if nothing was hit) */
+    float u, v;         /* Ray::barycentric */
+    int32_t obj_idx;    /* -1 = miss, 0 = light quad, 1 = floor plane, >= 2 = model */
+    int32_t tri_idx;    /* Ray::triIdx (-1 unless a triangle was hit) */
+    int32_t traversed;  /* Ray::traversed / tested work counters (ray.h:38-39), only when     */
+    int32_t tested;     /* the scene was created with RT_SCENE_FLAG_COUNTERS, else 0          */
+    int32_t reserved;
+} rt_hit;
+
+typedef struct rt_scene rt_scene;       /* immutable after creation; shareable between renderers */
+typedef struct rt_renderer rt_renderer; /* owns accumulator + wavefront queues; one stream per renderer */
+
+enum { RT_SCENE_FLAG_COUNTERS = 1 };
+
+const char* rt_last_error(void);
+int rt_abi_version(void);
+int rt_device_count(void);
+
+/* Upload + re-layout for the GPU (fat BVH2 nodes, leaf-ordered float4 triangles, texel arrays).
+ * Replaces: the state FileScene/TLASFileScene hold after their constructors ran
+ * (file_scene.cpp:4-62, tlas_file_scene.cpp:4-93). */
+rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags, rt_scene** out);
+void rt_scene_destroy(rt_scene* scene);
+
+/* Batched BaseScene::FindNearest (file_scene.cpp:170-175 / tlas_file_scene.cpp:201-206):
+ * light quad, floor plane, then the BVH / TLAS.  Host buffers; H2D + kernel + D2H inside the call. */
+rt_status rt_find_nearest(rt_scene* scene, const rt_ray* rays, rt_hit* hits, size_t n);
+/* Batched BaseScene::IsOccluded (file_scene.cpp:177-187 / tlas_file_scene.cpp:208-218). */
+rt_status rt_is_occluded(rt_scene* scene, const rt_ray* rays, uint8_t* occluded, size_t n);
+/* Same, buffers already resident on the scene's device; `stream` is a cudaStream_t (NULL = default). */
+rt_status rt_find_nearest_device(rt_scene* scene, const rt_ray* d_rays, rt_hit* d_hits, size_t n, void* stream);
+rt_status rt_is_occluded_device(rt_scene* scene, const rt_ray* d_rays, uint8_t* d_occluded, size_t n, void* stream);
+
+/* ---- camera (template/camera.h) -------------------------------------------------------------- */
+
+typedef struct rt_camera {
+    float pos[3];
+    float top_left[3], top_right[3], bottom_left[3];
+} rt_camera;
+
+/* Camera::Camera() (camera.h:12-21) for a width x height screen. */
+void rt_camera_default(rt_camera* cam, int width, int height);
+/* Camera::SetCameraState (camera.h:61-73). */
+void rt_camera_look_at(rt_camera* cam, const float pos[3], const float target[3], int width, int height);
+
+/* ---- renderer (Renderer::Init / Tick / accumulator) ----------------------------------------- */
+
+enum { RT_INTEGRATOR_WHITTED = 0 /* 2. WhittedStyle */, RT_INTEGRATOR_PATH = 1 /* 3. PathTracer */ };
+enum {
+    /* the reference's RNG: one xorshift32 stream per 16x16 tile per frame, seeded
+     * InitSeed(tx + ty*W + spp*1799), carried serially through the tile's 256 pixels
+     * (3. PathTracer/renderer.cpp:117-131).  Every (tile, frame) stream is one wavefront slot. */
+    RT_SEED_REFERENCE_TILE = 0,
+    /* one independent stream per pixel per frame (not the reference's sequence; same estimator) */
+    RT_SEED_PER_PIXEL = 1
+};
+
+typedef struct rt_render_params {
+    int32_t integrator;
+    int32_t width, height;  /* SCRWIDTH / SCRHEIGHT (camera.h:4-5) */
+    int32_t depth_limit;    /* Renderer::depthLimit, reference default 5 */
+    float epsilon;          /* EPSILON, renderer.h:12, reference 0.001f */
+    int32_t seed_mode;
+    int32_t tile_begin;     /* path tracer: render tiles [tile_begin, tile_end) of the          */
+    int32_t tile_end;       /* (W/16)x(H/16) row-major tile grid; tile_end <= 0 = all tiles      */
+    int32_t max_frames_in_flight; /* wavefront width = tiles x frames in flight; 0 = library default */
+} rt_render_params;
+
+void rt_render_params_default(rt_render_params* p, int integrator, int width, int height);
+
+typedef struct rt_counters {
+    uint64_t extension_rays;  /* FindNearest queries */
+    uint64_t shadow_rays;     /* IsOccluded queries */
+    uint64_t paths;           /* primary samples */
+    uint64_t wavefront_iterations;
+    uint64_t kernel_launches;
+} rt_counters;
+
+rt_status rt_renderer_create(rt_scene* scene, const rt_render_params* params, rt_renderer** out);
+void rt_renderer_destroy(rt_renderer* r);
+/* Run on `stream` (cudaStream_t) instead of the renderer's own stream. */
+rt_status rt_renderer_set_stream(rt_renderer* r, void* stream);
+/* Accumulate into a caller-owned device buffer of width*height float4 (e.g. a torch tensor that is
+ * later reduced with NCCL) instead of the renderer's own. */
+rt_status rt_renderer_set_accumulator(rt_renderer* r, void* d_accumulator);
+rt_status rt_renderer_set_camera(rt_renderer* r, const rt_camera* cam);
+/* Renderer::ClearAccumulator (3. PathTracer/renderer.cpp:15-18). */
+rt_status rt_renderer_clear(rt_renderer* r);
+/* `count` calls of Renderer::Tick (one frame each), for the frames whose reference `spp` counter
+ * would be first_spp, first_spp + stride, ... (a fresh reference renderer starts at spp = 1 and adds
+ * `passes` = 1 per frame, 3. PathTracer/renderer.h:50, renderer.cpp:167).  Asynchronous.
+ * Whitted ignores first_spp/stride and overwrites the accumulator, as the reference does. */
+rt_status rt_renderer_render(rt_renderer* r, int first_spp, int count, int stride);
+rt_status rt_renderer_sync(rt_renderer* r);
+/* Device -> host copy of the float4 accumulator (synchronises). */
+rt_status rt_renderer_read_accumulator(rt_renderer* r, float* host_rgba);
+/* screen->pixels as the reference would display it: accumulator * scale through RGBF32_to_RGB8
+ * (template/precomp.h:325-341; scale = 1/(spp+passes) for the path tracer, 1 for Whitted). */
+rt_status rt_renderer_read_pixels(rt_renderer* r, float scale, uint32_t* host_rgb8);
+void* rt_renderer_device_accumulator(rt_renderer* r);
+rt_status rt_renderer_get_counters(rt_renderer* r, rt_counters* out);
+rt_status rt_renderer_reset_counters(rt_renderer* r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_B200_H */
