@@ -1,0 +1,300 @@
+"""Host-side mirror of the reference's Scene / Renderer surface over the C-ABI (include/rt_b200.h).
+
+Same names, argument meaning and error behaviour as the reference classes, batched:
+
+    GpuFileScene / GpuTLASFileScene   <->  FileScene / TLASFileScene  (infra/scene/*.h):
+        FindNearest, IsOccluded, GetLightPos, GetLightColor, GetTriangleCount
+    Camera                            <->  Tmpl8::Camera (template/camera.h): SetCameraState
+    GpuRenderer                       <->  Renderer : TheApp (2. WhittedStyle / 3. PathTracer renderer.h):
+        Init, Tick, ClearAccumulator, accumulator, camera, spp, passes, depthLimit
+
+There is no CPU fallback anywhere in this module: if librt_b200.so is missing or no CUDA device is
+visible the calls raise (RtError / OSError).  The C++ twin of these adapters is csrc/host/gpu_scene.h.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+from .scene_file import FlatScene
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "librt_b200.so")
+
+EXPORTS = [
+    "rt_last_error", "rt_abi_version", "rt_device_count", "rt_scene_create", "rt_scene_destroy",
+    "rt_find_nearest", "rt_is_occluded", "rt_find_nearest_device", "rt_is_occluded_device",
+    "rt_camera_default", "rt_camera_look_at", "rt_render_params_default",
+    "rt_renderer_create", "rt_renderer_destroy", "rt_renderer_set_stream", "rt_renderer_set_accumulator",
+    "rt_renderer_set_camera", "rt_renderer_clear", "rt_renderer_render", "rt_renderer_sync",
+    "rt_renderer_read_accumulator", "rt_renderer_read_pixels", "rt_renderer_device_accumulator",
+    "rt_renderer_get_counters", "rt_renderer_reset_counters",
+]
+
+
+class RtError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"rt_b200 status {status}: {msg}")
+        self.status = status
+
+
+_lib = None
+
+
+def lib():
+    """Loads the CUDA library; raises if it was not built (never substitutes a CPU path)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OSError(f"{LIB_PATH} not built: run `python __graft_entry__.py build` (nvcc, sm_100a). "
+                      "There is no CPU fallback for the ray core.")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, sz = C.c_void_p, C.c_int, C.c_size_t
+    L.rt_last_error.restype = C.c_char_p
+    L.rt_scene_create.argtypes = [C.POINTER(abi.rt_scene_desc), i32, C.c_uint32, C.POINTER(vp)]
+    L.rt_scene_destroy.argtypes = [vp]
+    L.rt_scene_destroy.restype = None
+    L.rt_find_nearest.argtypes = [vp, vp, vp, sz]
+    L.rt_is_occluded.argtypes = [vp, vp, vp, sz]
+    L.rt_find_nearest_device.argtypes = [vp, vp, vp, sz, vp]
+    L.rt_is_occluded_device.argtypes = [vp, vp, vp, sz, vp]
+    L.rt_camera_default.argtypes = [C.POINTER(abi.rt_camera), i32, i32]
+    L.rt_camera_default.restype = None
+    L.rt_camera_look_at.argtypes = [C.POINTER(abi.rt_camera), C.POINTER(C.c_float), C.POINTER(C.c_float), i32, i32]
+    L.rt_camera_look_at.restype = None
+    L.rt_render_params_default.argtypes = [C.POINTER(abi.rt_render_params), i32, i32, i32]
+    L.rt_render_params_default.restype = None
+    L.rt_renderer_create.argtypes = [vp, C.POINTER(abi.rt_render_params), C.POINTER(vp)]
+    L.rt_renderer_destroy.argtypes = [vp]
+    L.rt_renderer_destroy.restype = None
+    L.rt_renderer_set_stream.argtypes = [vp, vp]
+    L.rt_renderer_set_accumulator.argtypes = [vp, vp]
+    L.rt_renderer_set_camera.argtypes = [vp, C.POINTER(abi.rt_camera)]
+    L.rt_renderer_clear.argtypes = [vp]
+    L.rt_renderer_render.argtypes = [vp, i32, i32, i32]
+    L.rt_renderer_sync.argtypes = [vp]
+    L.rt_renderer_read_accumulator.argtypes = [vp, vp]
+    L.rt_renderer_read_pixels.argtypes = [vp, C.c_float, vp]
+    L.rt_renderer_device_accumulator.argtypes = [vp]
+    L.rt_renderer_device_accumulator.restype = vp
+    L.rt_renderer_get_counters.argtypes = [vp, C.POINTER(abi.rt_counters)]
+    L.rt_renderer_reset_counters.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def _check(status):
+    if status != abi.RT_OK:
+        raise RtError(status, lib().rt_last_error().decode(errors="replace"))
+
+
+def device_count():
+    return lib().rt_device_count()
+
+
+class Camera:
+    """Tmpl8::Camera (template/camera.h): default view (0,0,-2) -> +z, SetCameraState."""
+
+    def __init__(self, width, height):
+        self.width, self.height = width, height
+        self.c = abi.rt_camera()
+        lib().rt_camera_default(C.byref(self.c), width, height)
+
+    def SetCameraState(self, position, target):
+        p = (C.c_float * 3)(*[float(x) for x in position])
+        t = (C.c_float * 3)(*[float(x) for x in target])
+        lib().rt_camera_look_at(C.byref(self.c), p, t, self.width, self.height)
+
+    @property
+    def camPos(self):
+        return np.array(list(self.c.pos), np.float32)
+
+
+def make_rays(O, D, tmax=1e34, inside=0):
+    O = np.asarray(O, np.float32)
+    rays = np.zeros(O.shape[0], abi.RAY_DTYPE)
+    rays["O"], rays["D"], rays["tmax"], rays["inside"] = O, np.asarray(D, np.float32), tmax, inside
+    return rays
+
+
+class GpuScene:
+    """BaseScene surface (infra/scene/base_scene.h:16-32) served by the CUDA library."""
+
+    KIND = None
+
+    def __init__(self, flat: FlatScene, device=0, counters=False):
+        if isinstance(flat, (str, os.PathLike)):
+            flat = FlatScene.load(flat)
+        if self.KIND is not None and flat.kind != self.KIND:
+            raise ValueError(f"{type(self).__name__} needs a scene of kind {self.KIND}, got {flat.kind}")
+        self.flat = flat
+        self.device = device
+        self.handle = C.c_void_p()
+        desc = flat.desc()
+        _check(lib().rt_scene_create(C.byref(desc), device, abi.RT_SCENE_FLAG_COUNTERS if counters else 0, C.byref(self.handle)))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib().rt_scene_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- BaseScene ---------------------------------------------------------------------------
+    def FindNearest(self, rays):
+        """Batched FindNearest: rays = RAY_DTYPE array (host). Returns HIT_DTYPE array; miss <=> obj_idx == -1."""
+        rays = np.ascontiguousarray(rays, abi.RAY_DTYPE)
+        hits = np.empty(len(rays), abi.HIT_DTYPE)
+        _check(lib().rt_find_nearest(self.handle, rays.ctypes.data, hits.ctypes.data, len(rays)))
+        return hits
+
+    def IsOccluded(self, rays):
+        rays = np.ascontiguousarray(rays, abi.RAY_DTYPE)
+        out = np.empty(len(rays), np.uint8)
+        _check(lib().rt_is_occluded(self.handle, rays.ctypes.data, out.ctypes.data, len(rays)))
+        return out
+
+    def FindNearestDevice(self, d_rays_ptr, d_hits_ptr, n, stream=None):
+        """Buffers already in HBM (e.g. torch tensors' data_ptr()); asynchronous on `stream`."""
+        _check(lib().rt_find_nearest_device(self.handle, d_rays_ptr, d_hits_ptr, n, stream))
+
+    def IsOccludedDevice(self, d_rays_ptr, d_out_ptr, n, stream=None):
+        _check(lib().rt_is_occluded_device(self.handle, d_rays_ptr, d_out_ptr, n, stream))
+
+    def GetLightPos(self):
+        return self.flat.header["light_pos"][0].copy()
+
+    def GetLightColor(self):
+        return self.flat.header["light_color"][0].copy()
+
+    def GetTriangleCount(self):
+        return self.flat.triangle_count
+
+
+class GpuFileScene(GpuScene):
+    """FileScene with USE_BVH (infra/scene/file_scene.h): one flat SAH BVH over all triangles."""
+    KIND = abi.RT_SCENE_FLAT
+
+
+class GpuTLASFileScene(GpuScene):
+    """TLASFileScene with TLAS_USE_BVH (infra/scene/tlas_file_scene.h): TLAS over per-object BLAS."""
+    KIND = abi.RT_SCENE_TLAS
+
+
+def open_scene(path_or_flat, device=0, counters=False):
+    flat = FlatScene.load(path_or_flat) if isinstance(path_or_flat, (str, os.PathLike)) else path_or_flat
+    cls = GpuTLASFileScene if flat.kind == abi.RT_SCENE_TLAS else GpuFileScene
+    return cls(flat, device=device, counters=counters)
+
+
+class GpuRenderer:
+    """Renderer : TheApp (2. WhittedStyle/renderer.h:41-61, 3. PathTracer/renderer.h:29-53)."""
+
+    def __init__(self, scene: GpuScene, integrator, width, height, depthLimit=5, seed_mode=abi.RT_SEED_REFERENCE_TILE,
+                 tile_begin=0, tile_end=0, max_frames_in_flight=0):
+        self.scene = scene
+        self.integrator = integrator
+        self.width, self.height = width, height
+        self.depthLimit = depthLimit
+        self.camera = Camera(width, height)
+        self.spp, self.passes = 1, 1  # renderer.h:50
+        self.params = abi.rt_render_params()
+        lib().rt_render_params_default(C.byref(self.params), integrator, width, height)
+        self.params.depth_limit = depthLimit
+        self.params.seed_mode = seed_mode
+        self.params.tile_begin, self.params.tile_end = tile_begin, tile_end
+        self.params.max_frames_in_flight = max_frames_in_flight
+        self.handle = C.c_void_p()
+        self._initialised = False
+
+    def Init(self):
+        """Renderer::Init: allocate + clear the accumulator (renderer.cpp:8-13)."""
+        if self.handle:
+            lib().rt_renderer_destroy(self.handle)
+            self.handle = C.c_void_p()
+        _check(lib().rt_renderer_create(self.scene.handle, C.byref(self.params), C.byref(self.handle)))
+        self._initialised = True
+        return self
+
+    def _need(self):
+        if not self._initialised:
+            self.Init()
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib().rt_renderer_destroy(self.handle)
+            self.handle = None
+            self._initialised = False
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def ClearAccumulator(self):
+        self._need()
+        _check(lib().rt_renderer_clear(self.handle))
+
+    def set_stream(self, cuda_stream_ptr):
+        self._need()
+        _check(lib().rt_renderer_set_stream(self.handle, cuda_stream_ptr))
+
+    def set_accumulator(self, device_ptr):
+        self._need()
+        _check(lib().rt_renderer_set_accumulator(self.handle, device_ptr))
+
+    def Tick(self, deltaTime=0.0):
+        """One frame.  Path tracer: one sample per pixel with the current `spp`, then spp += passes
+        (renderer.cpp:144-168).  Whitted: overwrites the accumulator (renderer.cpp:131-157)."""
+        self.render(1)
+
+    def render(self, frames, first_spp=None, stride=1):
+        """`frames` Ticks in one call (frames run concurrently on the GPU; result = running them in order)."""
+        self._need()
+        _check(lib().rt_renderer_set_camera(self.handle, C.byref(self.camera.c)))
+        first = self.spp if first_spp is None else first_spp
+        _check(lib().rt_renderer_render(self.handle, first, frames, stride))
+        if self.integrator == abi.RT_INTEGRATOR_PATH and first_spp is None:
+            self.spp += frames * self.passes
+
+    def sync(self):
+        self._need()
+        _check(lib().rt_renderer_sync(self.handle))
+
+    @property
+    def accumulator(self):
+        self._need()
+        out = np.empty((self.height, self.width, 4), np.float32)
+        _check(lib().rt_renderer_read_accumulator(self.handle, out.ctypes.data))
+        return out
+
+    def device_accumulator(self):
+        self._need()
+        return lib().rt_renderer_device_accumulator(self.handle)
+
+    def screen_pixels(self, scale=None):
+        """screen->pixels as the reference displays them: accumulator * 1/(spp+passes) through RGBF32_to_RGB8
+        (renderer.cpp:119,127-129); note that `spp` here is the value BEFORE the last Tick's increment."""
+        self._need()
+        if scale is None:
+            scale = 1.0 if self.integrator == abi.RT_INTEGRATOR_WHITTED else 1.0 / float(self.spp)
+        out = np.empty((self.height, self.width), np.uint32)
+        _check(lib().rt_renderer_read_pixels(self.handle, scale, out.ctypes.data))
+        return out
+
+    def counters(self):
+        self._need()
+        c = abi.rt_counters()
+        _check(lib().rt_renderer_get_counters(self.handle, C.byref(c)))
+        return {k: int(getattr(c, k)) for k, _ in abi.rt_counters._fields_}
+
+    def reset_counters(self):
+        self._need()
+        _check(lib().rt_renderer_reset_counters(self.handle))

@@ -1,0 +1,49 @@
+"""Compile the CUDA library in-tree: cpu-ray-tracer_b200/librt_b200.so (sm_100a only).
+
+Flags that matter for parity ("FP discipline"): -fmad=false (no FMA contraction: the
+reference's hits are reproduced bit for bit), IEEE division / sqrt (nvcc defaults, stated explicitly),
+no --use_fast_math; host code of the same files is compiled with -ffp-contract=off.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "librt_b200.so")
+SOURCES = ["rt_scene.cu", "rt_render.cu"]
+HEADERS = ["rt_device.cuh", "rt_internal.h", os.path.join("..", "..", "include", "rt_b200.h")]
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
+              "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-shared", "-cudart", "shared"]
+
+
+def nvcc():
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if c and (os.path.isabs(c) and os.path.exists(c) or not os.path.isabs(c)):
+            return c
+    return "nvcc"
+
+
+def up_to_date():
+    if not os.path.exists(LIB):
+        return False
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return all(os.path.getmtime(d) <= t for d in deps)
+
+
+def build(force=False, verbose=False, extra=()):
+    if not force and up_to_date():
+        return LIB
+    cmd = [nvcc(), *NVCC_FLAGS, *extra, *[os.path.join(CSRC, f) for f in SOURCES], "-o", LIB]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    extra = ["-Xptxas", "-v"] if "-v" in sys.argv else []
+    print(build(force=True, verbose=True, extra=extra))

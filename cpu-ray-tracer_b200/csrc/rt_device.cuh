@@ -1,0 +1,451 @@
+// rt_device.cuh — device-side core of the B200 ray tracer: scene layout, slab / triangle tests,
+// the two-level ordered stack traversal, analytic primitives, textures and hit shading queries.
+//
+// Numerics contract (DESIGN.md "FP discipline"): this translation unit is compiled with -fmad=false,
+// IEEE division and square root, no fast-math.  Every expression keeps the reference's operation
+// order so that hits (t, u, v, objIdx, triIdx) are bit-identical to the reference's CPU code; the
+// reference lines each routine follows are cited next to it (paths relative to /root/reference).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rtb {
+
+// ------------------------------------------------------------------------------------------------
+// Device scene layout (built by rt_scene.cu from the reference-layout arrays of rt_scene_desc)
+//
+//   nodes   "fat" BVH2 nodes, 64 B = 4 x float4, one per INTERIOR node of a reference BVH / TLAS:
+//             n0 = (L.min.x, L.min.y, L.min.z, L.max.x)
+//             n1 = (L.max.y, L.max.z, R.min.x, R.min.y)
+//             n2 = (R.min.z, R.max.x, R.max.y, R.max.z)
+//             n3 = (int left_ref, int right_ref, -, -)
+//           Both child boxes travel in one 64-byte, 64-byte-aligned record (two sectors), so an
+//           interior visit costs one node fetch instead of the reference's parent + 2 children.
+//           The boxes are bit copies of the reference's, the test order is the reference's.
+//   ref     >= 0: index of a fat node.   < 0: leaf, payload = ~ref:
+//             payload == SENTINEL            stack marker: leave the current instance
+//             payload & INSTANCE_BIT         TLAS leaf: instance id = payload & ~INSTANCE_BIT
+//             otherwise                      first triangle slot of a triangle leaf
+//   tris    leaf-ordered triangles (the order of the reference's triangleIndices), 48 B = 3 x float4:
+//             t0 = (v0.xyz, int triIdx | LAST_BIT)      LAST_BIT marks the last triangle of a leaf
+//             t1 = (v1-v0, int objIdx)                  objIdx: Tri::objIdx (flat BVH only)
+//             t2 = (v2-v0, -)
+//           edge vectors are precomputed with the same fp32 subtraction the reference does per test.
+//   inst    per BLAS instance, 64 B: rows 0..2 of invT (3 x float4) + (int root_ref, int objIdx, -, -)
+//   shade   per triangle (global id = instance tri_base + triIdx), 64 B:
+//             s0 = (n0.xyz, n1.x) s1 = (n1.yz, n2.xy) s2 = (n2.z, uv0.xy, uv1.x) s3 = (uv1.y, uv2.xy, int objIdx)
+//   inst_shade per instance, 64 B: rows 0..2 of T + (int tri_base, -, -, -)
+// ------------------------------------------------------------------------------------------------
+constexpr int SENTINEL_PAYLOAD = 0x7fffffff;
+constexpr int INSTANCE_BIT = 0x40000000;
+constexpr int LAST_BIT = (int)0x80000000u;
+constexpr int STACK_SIZE = 64; // the reference's own limit: BVHNode* stack[64] (bvh.cpp:227)
+
+struct DMaterial {
+    float reflectivity, refractivity;
+    float absorption[3];
+    float albedo[3];
+    int is_light;
+    int texture;
+};
+
+struct DTexture {
+    const uint32_t* pixels;
+    int width, height;
+};
+
+struct DScene {
+    const float4* nodes;
+    const float4* tris;
+    const float4* inst;
+    const float4* shade;
+    const float4* inst_shade;
+    const int* obj_material;
+    const DMaterial* materials;
+    const DTexture* textures;
+    int root_ref;
+    int kind;          // RT_SCENE_FLAT / RT_SCENE_TLAS
+    int flat_obj_idx;  // objIdx override for the flat BVH (-1: take the triangle's)
+    int skydome_texture, floor_texture;
+    float floor_n[3], floor_d, floor_invto;
+    float light_T[16], light_inv_T[16], light_size;
+    float light_color[3], light_pos[3];
+};
+
+// ------------------------------------------------------------------------------------------------
+// float3 helpers, written so that each reference expression maps 1:1 (template/tmplmath.h)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+__device__ __forceinline__ float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 operator*(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ float3 operator*(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float3 operator*(float s, float3 a) { return f3(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ float3 operator-(float3 a) { return f3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }   // tmplmath.h:458
+__device__ __forceinline__ float3 cross(float3 a, float3 b)                                               // tmplmath.h:512
+{
+    return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ float3 normalize(float3 v) { float invLen = 1.0f / sqrtf(dot(v, v)); return v * invLen; } // :124,:480
+__device__ __forceinline__ float3 reflect(float3 i, float3 n) { return i - 2.0f * n * dot(n, i); }        // tmplmath.h:506
+__device__ __forceinline__ float3 recip(float3 d) { return f3(1 / d.x, 1 / d.y, 1 / d.z); }              // ray.h:19
+
+// std::min / std::max exactly as the host compiler evaluates them in the slab test: a NaN in the
+// FIRST operand propagates, a NaN in the second is dropped (CUDA's fminf/fmaxf drop either).
+__device__ __forceinline__ float smin(float a, float b) { return (b < a) ? b : a; }
+__device__ __forceinline__ float smax(float a, float b) { return (a < b) ? b : a; }
+// template/tmplmath.h:122-123,435
+__device__ __forceinline__ float tfminf(float a, float b) { return a < b ? a : b; }
+__device__ __forceinline__ float tfmaxf(float a, float b) { return a > b ? a : b; }
+__device__ __forceinline__ float clampf(float f, float a, float b) { return tfmaxf(a, tfminf(f, b)); }
+__device__ __forceinline__ int clampi(int f, int a, int b) { int m = f < b ? f : b; return a > m ? a : m; }
+
+#define RT_PI 3.14159265358979323846264f
+#define RT_INVPI 0.31830988618379067153777f
+#define RT_INV2PI 0.15915494309189533576888f
+
+// RNG: template/tmplmath.cpp:5-34
+__device__ __forceinline__ uint32_t wang_hash(uint32_t s)
+{
+    s = (s ^ 61) ^ (s >> 16);
+    s *= 9, s = s ^ (s >> 4);
+    s *= 0x27d4eb2d;
+    s = s ^ (s >> 15);
+    return s;
+}
+__device__ __forceinline__ uint32_t init_seed(uint32_t base) { return wang_hash((base + 1) * 17); }
+__device__ __forceinline__ float random_float(uint32_t& s)
+{
+    s ^= s << 13, s ^= s >> 17, s ^= s << 5;
+    return s * 2.3283064365387e-10f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// hit record carried through traversal (Ray::t, barycentric, objIdx, triIdx, traversed, tested)
+// ------------------------------------------------------------------------------------------------
+struct HitRec {
+    float t, u, v;
+    int obj, tri;
+    int traversed, tested;
+};
+
+// A ray needs the NaN-exact slab path iff a direction component is zero (rD = inf, so
+// (b - O) * rD can be 0 * inf) or something is non-finite.  Everything else cannot produce NaN
+// and fminf/fmaxf give the same values as std::min/max there.
+__device__ __forceinline__ bool needs_exact_slab(float3 O, float3 D)
+{
+    const bool dirOk = fabsf(D.x) > 0 && fabsf(D.y) > 0 && fabsf(D.z) > 0 && fabsf(D.x) < 3e38f && fabsf(D.y) < 3e38f && fabsf(D.z) < 3e38f;
+    const bool orgOk = fabsf(O.x) < 3e38f && fabsf(O.y) < 3e38f && fabsf(O.z) < 3e38f;
+    return !(dirOk && orgOk);
+}
+
+// slab test: bvh.cpp:181-190 = blas_bvh.cpp:259-268 = tlas_bvh.cpp:72-81.  Returns tmin or 1e30f.
+__device__ __forceinline__ float slab(float3 O, float3 rD, float rayT, bool exact,
+    float bminx, float bminy, float bminz, float bmaxx, float bmaxy, float bmaxz)
+{
+    const float tx1 = (bminx - O.x) * rD.x, tx2 = (bmaxx - O.x) * rD.x;
+    const float ty1 = (bminy - O.y) * rD.y, ty2 = (bmaxy - O.y) * rD.y;
+    const float tz1 = (bminz - O.z) * rD.z, tz2 = (bmaxz - O.z) * rD.z;
+    float tmin, tmax;
+    if (!exact)
+    {
+        tmin = fminf(tx1, tx2), tmax = fmaxf(tx1, tx2);
+        tmin = fmaxf(tmin, fminf(ty1, ty2)), tmax = fminf(tmax, fmaxf(ty1, ty2));
+        tmin = fmaxf(tmin, fminf(tz1, tz2)), tmax = fminf(tmax, fmaxf(tz1, tz2));
+    }
+    else
+    {
+        tmin = smin(tx1, tx2), tmax = smax(tx1, tx2);
+        tmin = smax(tmin, smin(ty1, ty2)), tmax = smin(tmax, smax(ty1, ty2));
+        tmin = smax(tmin, smin(tz1, tz2)), tmax = smin(tmax, smax(tz1, tz2));
+    }
+    return (tmax >= tmin && tmin < rayT && tmax > 0) ? tmin : 1e30f;
+}
+
+// Moeller-Trumbore: bvh.cpp:203-222 / blas_bvh.cpp:281-300.  Returns true when the hit was accepted.
+__device__ __forceinline__ bool intersect_tri(float3 O, float3 D, float3 v0, float3 edge1, float3 edge2,
+    float& rayT, float& outU, float& outV)
+{
+    const float3 h = cross(D, edge2);
+    const float a = dot(edge1, h);
+    if (a > -0.0001f && a < 0.0001f) return false;
+    const float f = 1 / a;
+    const float3 s = O - v0;
+    const float u = f * dot(s, h);
+    if (u < 0 || u > 1) return false;
+    const float3 q = cross(s, edge1);
+    const float v = f * dot(D, q);
+    if (v < 0 || u + v > 1) return false;
+    const float t = f * dot(edge2, q);
+    if (t > 0.0001f && t < rayT)
+    {
+        rayT = t, outU = u, outV = v;
+        return true;
+    }
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Two-level ordered traversal.
+//   closest hit: bvh.cpp:224-258 (flat), tlas_bvh.cpp:83-111 + blas_bvh.cpp:376-389 + :302-336 (TLAS).
+//   Same visiting order as the reference: near child first by slab tmin, left first on ties, far
+//   child pushed only when hit, miss sentinel 1e30f compared with ==; the root box is never tested.
+//   One stack serves both levels: entering an instance pushes SENTINEL, so that the instance's whole
+//   subtree is finished (as the reference's nested call does) before the TLAS stack continues.
+//   ANYHIT: return at the first accepted triangle (IsOccluded, file_scene.cpp:177-187: the reference
+//   runs the closest-hit traversal with t = 1e34 and only asks whether anything was hit).
+// ------------------------------------------------------------------------------------------------
+template <bool ANYHIT, bool COUNTERS>
+__device__ __forceinline__ void traverse(const DScene& s, const float3 wO, const float3 wD, HitRec& hit)
+{
+    float3 O = wO, D = wD, rD = recip(wD);
+    bool exact = needs_exact_slab(O, D);
+    int instObj = s.flat_obj_idx;
+    int stack[STACK_SIZE];
+    int sp = 0;
+    int cur = s.root_ref;
+    const float4* __restrict__ nodes = s.nodes;
+    const float4* __restrict__ tris = s.tris;
+    while (true)
+    {
+        if (cur >= 0)
+        {
+            if (COUNTERS) hit.traversed++;
+            const float4* n = nodes + 4 * (size_t)cur;
+            const float4 n0 = __ldg(n), n1 = __ldg(n + 1), n2 = __ldg(n + 2);
+            const int4 n3 = __ldg((const int4*)(n + 3));
+            float d1 = slab(O, rD, hit.t, exact, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y);
+            float d2 = slab(O, rD, hit.t, exact, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w);
+            int c1 = n3.x, c2 = n3.y;
+            if (d1 > d2) { const float tf = d1; d1 = d2; d2 = tf; const int tc = c1; c1 = c2; c2 = tc; }
+            if (d1 == 1e30f)
+            {
+                if (sp == 0) break;
+                cur = stack[--sp];
+            }
+            else
+            {
+                cur = c1;
+                if (d2 != 1e30f) stack[sp++] = c2;
+            }
+            continue;
+        }
+        const int payload = ~cur;
+        if (payload == SENTINEL_PAYLOAD)
+        {
+            // leave the instance: blas_bvh.cpp:385-388 restores O, D, rD
+            O = wO, D = wD, rD = recip(wD);
+            exact = needs_exact_slab(O, D);
+        }
+        else if (payload & INSTANCE_BIT)
+        {
+            // TLAS leaf -> BLASBVH::Intersect (blas_bvh.cpp:376-389), SSE lane-sum order of
+            // TransformPosition_SSE / TransformVector_SSE (tmplmath.cpp:170-191)
+            if (COUNTERS) hit.traversed++, hit.tested = 0;
+            const float4* I = s.inst + 4 * (size_t)(payload & ~INSTANCE_BIT);
+            const float4 r0 = __ldg(I), r1 = __ldg(I + 1), r2 = __ldg(I + 2);
+            const int4 meta = __ldg((const int4*)(I + 3));
+            O = f3((wO.x * r0.x + wO.y * r0.y) + (wO.z * r0.z + r0.w),
+                   (wO.x * r1.x + wO.y * r1.y) + (wO.z * r1.z + r1.w),
+                   (wO.x * r2.x + wO.y * r2.y) + (wO.z * r2.z + r2.w));
+            D = f3((wD.x * r0.x + wD.y * r0.y) + wD.z * r0.z,
+                   (wD.x * r1.x + wD.y * r1.y) + wD.z * r1.z,
+                   (wD.x * r2.x + wD.y * r2.y) + wD.z * r2.z);
+            rD = recip(D);
+            exact = needs_exact_slab(O, D);
+            instObj = meta.y;
+            stack[sp++] = ~SENTINEL_PAYLOAD;
+            cur = meta.x;
+            continue;
+        }
+        else
+        {
+            // triangle leaf: bvh.cpp:232-241
+            if (COUNTERS) hit.traversed++;
+            int slot = payload;
+            while (true)
+            {
+                const float4* T = tris + 3 * (size_t)slot;
+                const float4 t0 = __ldg(T), t1 = __ldg(T + 1), t2 = __ldg(T + 2);
+                const int tag = __float_as_int(t0.w);
+                if (COUNTERS) hit.tested++;
+                if (intersect_tri(O, D, f3(t0.x, t0.y, t0.z), f3(t1.x, t1.y, t1.z), f3(t2.x, t2.y, t2.z), hit.t, hit.u, hit.v))
+                {
+                    hit.tri = tag & ~LAST_BIT;
+                    hit.obj = instObj >= 0 ? instObj : __float_as_int(t1.w);
+                    if (ANYHIT) return;
+                }
+                if (tag & LAST_BIT) break;
+                slot++;
+            }
+        }
+        if (sp == 0) break;
+        cur = stack[--sp];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// analytic primitives tested for every ray before the BVH (file_scene.cpp:172-173)
+// ------------------------------------------------------------------------------------------------
+// Quad::Intersect / IsOccluded share this test: primitives.h:331-362
+__device__ __forceinline__ bool quad_test(const DScene& s, float3 O, float3 D, float rayT, float& tOut)
+{
+    const float* m = s.light_inv_T;
+    const float Oy = m[4] * O.x + m[5] * O.y + m[6] * O.z + m[7];
+    const float Dy = m[4] * D.x + m[5] * D.y + m[6] * D.z;
+    const float t = Oy / -Dy;
+    if (t < rayT && t > 0)
+    {
+        const float Ox = m[0] * O.x + m[1] * O.y + m[2] * O.z + m[3];
+        const float Oz = m[8] * O.x + m[9] * O.y + m[10] * O.z + m[11];
+        const float Dx = m[0] * D.x + m[1] * D.y + m[2] * D.z;
+        const float Dz = m[8] * D.x + m[9] * D.y + m[10] * D.z;
+        const float Ix = Ox + t * Dx, Iz = Oz + t * Dz;
+        const float size = s.light_size;
+        if (Ix > -size && Ix < size && Iz > -size && Iz < size) { tOut = t; return true; }
+    }
+    return false;
+}
+
+// BaseScene::FindNearest: file_scene.cpp:170-175 = tlas_file_scene.cpp:201-206
+template <bool COUNTERS>
+__device__ __forceinline__ void find_nearest(const DScene& s, float3 O, float3 D, float tmax, HitRec& hit)
+{
+    hit.t = tmax, hit.u = 0, hit.v = 0, hit.obj = -1, hit.tri = -1, hit.traversed = 0, hit.tested = 0;
+    float tq;
+    if (quad_test(s, O, D, hit.t, tq)) hit.t = tq, hit.obj = 0;
+    {
+        // Plane::Intersect primitives.h:107-111
+        const float3 N = f3(s.floor_n[0], s.floor_n[1], s.floor_n[2]);
+        const float t = -(dot(O, N) + s.floor_d) / (dot(D, N));
+        if (t < hit.t && t > 0) hit.t = t, hit.obj = 1;
+    }
+    traverse<false, COUNTERS>(s, O, D, hit);
+}
+
+// BaseScene::IsOccluded: file_scene.cpp:177-187 = tlas_file_scene.cpp:208-218 (SURVEY quirk Q2:
+// geometry is tested with t = 1e34, the floor never occludes, the light quad uses the real t)
+__device__ __forceinline__ bool is_occluded(const DScene& s, float3 O, float3 D, float tmax)
+{
+    float tq;
+    if (quad_test(s, O, D, tmax, tq)) return true;
+    HitRec hit;
+    hit.t = 1e34f, hit.u = 0, hit.v = 0, hit.obj = -1, hit.tri = -1, hit.traversed = 0, hit.tested = 0;
+    traverse<true, false>(s, O, D, hit);
+    return hit.obj > -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// textures, sky, hit shading queries
+// ------------------------------------------------------------------------------------------------
+// Texture::Sample: texture.h:61-96 (nearest, clamp, v flip, 0x00RRGGBB)
+__device__ __forceinline__ float3 texture_sample(const DScene& s, int tex, float u, float v)
+{
+    if (tex < 0) return f3(0, 0, 0);
+    const DTexture T = s.textures[tex];
+    if (T.width * T.height == 0) return f3(0, 0, 0);
+    u = clampf(u, 0.0f, 1.0f);
+    v = 1 - clampf(v, 0.0f, 1.0f);
+    int x = (int)(u * T.width);
+    int y = (int)(v * T.height);
+    x = clampi(x, 0, T.width - 1);
+    y = clampi(y, 0, T.height - 1);
+    const uint32_t pixel = __ldg(T.pixels + (x + y * T.width));
+    const float rgbScale = 1 / 255.0f;
+    return f3(((pixel >> 16) & 0xFF) * rgbScale, ((pixel >> 8) & 0xFF) * rgbScale, (pixel & 0xFF) * rgbScale);
+}
+
+// GetSkyColor: file_scene.cpp:142-154.  atan2f / acosf are CUDA's (<= 2 ulp from glibc's): a texel
+// can flip at a texel border, which is why radiance parity is a tolerance and hit parity is exact.
+__device__ __forceinline__ float3 sky_color(const DScene& s, float3 D)
+{
+    const float phi = atan2f(-D.z, D.x) + RT_PI;
+    const float theta = acosf(-D.y);
+    const float u = phi * RT_INV2PI;
+    const float v = theta * RT_INVPI;
+    return texture_sample(s, s.skydome_texture, u, v);
+}
+
+struct ShadeHit {
+    float3 N, albedo, absorption;
+    float reflectivity, refractivity;
+    bool isLight;
+};
+
+// GetHitInfo (file_scene.cpp:189-214 / tlas_file_scene.cpp:220-260) + Material::GetAlbedo (material.h:28-35)
+__device__ __forceinline__ void hit_info(const DScene& s, float3 D, float3 I, int obj, int tri, float bu, float bv, ShadeHit& h, float& outU, float& outV)
+{
+    h.isLight = false, h.reflectivity = 0, h.refractivity = 0, h.absorption = f3(0, 0, 0);
+    float u = 0, v = 0;
+    int tex = -1;
+    float3 matAlbedo = f3(1, 1, 1);
+    if (obj == 0)
+    {
+        h.N = f3(-s.light_T[1], -s.light_T[5], -s.light_T[9]); // Quad::GetNormal primitives.h:363-367
+        h.isLight = true;
+    }
+    else if (obj == 1)
+    {
+        h.N = f3(s.floor_n[0], s.floor_n[1], s.floor_n[2]);
+        if (s.floor_n[1] == 1) // Plane::GetUV primitives.h:116-133
+        {
+            u = I.x, v = I.z;
+            u *= s.floor_invto, v *= s.floor_invto;
+            u = u - floorf(u), v = v - floorf(v);
+        }
+        tex = s.floor_texture;
+    }
+    else
+    {
+        int triBase = 0;
+        float4 r0, r1, r2;
+        const bool tlas = s.kind == 1;
+        if (tlas)
+        {
+            const float4* IS = s.inst_shade + 4 * (size_t)(obj - 2);
+            r0 = __ldg(IS), r1 = __ldg(IS + 1), r2 = __ldg(IS + 2);
+            triBase = __float_as_int(__ldg(IS + 3).x);
+        }
+        const float4* S = s.shade + 4 * (size_t)(triBase + tri);
+        const float4 s0 = __ldg(S), s1 = __ldg(S + 1), s2 = __ldg(S + 2), s3 = __ldg(S + 3);
+        const float3 n0 = f3(s0.x, s0.y, s0.z), n1 = f3(s0.w, s1.x, s1.y), n2 = f3(s1.z, s1.w, s2.x);
+        // GetNormal bvh.cpp:290-297 / blas_bvh.cpp:391-398
+        float3 N = (1 - bu - bv) * n0 + bu * n1 + bv * n2;
+        if (tlas) // TransformVector(N, T): float4(N, 0) * M, tmplmath.cpp:155-169
+            N = f3(r0.x * N.x + r0.y * N.y + r0.z * N.z + r0.w * 0.0f,
+                   r1.x * N.x + r1.y * N.y + r1.z * N.z + r1.w * 0.0f,
+                   r2.x * N.x + r2.y * N.y + r2.z * N.z + r2.w * 0.0f);
+        h.N = normalize(N);
+        // GetUV bvh.cpp:299-305
+        const float w = 1 - bu - bv;
+        u = w * s2.y + bu * s2.w + bv * s3.y;
+        v = w * s2.z + bu * s3.x + bv * s3.z;
+        const int objIdx = tlas ? obj : __float_as_int(s3.w);
+        const DMaterial m = s.materials[s.obj_material[objIdx - 2]];
+        h.reflectivity = m.reflectivity, h.refractivity = m.refractivity;
+        h.absorption = f3(m.absorption[0], m.absorption[1], m.absorption[2]);
+        h.isLight = m.is_light != 0;
+        matAlbedo = f3(m.albedo[0], m.albedo[1], m.albedo[2]);
+        tex = m.texture;
+    }
+    if (dot(h.N, D) > 0) h.N = -h.N;
+    h.albedo = tex < 0 ? matAlbedo : texture_sample(s, tex, u, v);
+    outU = u, outV = v;
+}
+
+// Camera::GetPrimaryRay: camera.h:23-30
+struct DCamera {
+    float3 pos, topLeft, topRight, bottomLeft;
+    float invW, invH; // 1.0f / SCRWIDTH, 1.0f / SCRHEIGHT
+};
+
+__device__ __forceinline__ float3 primary_dir(const DCamera& c, float x, float y)
+{
+    const float u = x * c.invW;
+    const float v = y * c.invH;
+    const float3 P = c.topLeft + u * (c.topRight - c.topLeft) + v * (c.bottomLeft - c.topLeft);
+    return normalize(P - c.pos);
+}
+
+} // namespace rtb

@@ -1,0 +1,45 @@
+// rt_internal.h — host-side objects behind the opaque handles of include/rt_b200.h
+#pragma once
+#include <cuda_runtime.h>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/rt_b200.h"
+#include "rt_device.cuh"
+
+namespace rtb {
+
+void set_error(const std::string& msg);
+bool cuda_ok(cudaError_t e, const char* what);
+
+#define RT_CUDA(call)                                            \
+    do {                                                         \
+        if (!rtb::cuda_ok((call), #call)) return RT_ERR_CUDA;    \
+    } while (0)
+
+} // namespace rtb
+
+struct rt_scene {
+    int device = 0;
+    uint32_t flags = 0;
+    rtb::DScene d = {};
+    // owned device allocations
+    float4* nodes = nullptr;
+    float4* tris = nullptr;
+    float4* inst = nullptr;
+    float4* shade = nullptr;
+    float4* inst_shade = nullptr;
+    int* obj_material = nullptr;
+    rtb::DMaterial* materials = nullptr;
+    rtb::DTexture* textures = nullptr;
+    uint32_t* tex_pixels = nullptr;
+    size_t node_count = 0, tri_count = 0, inst_count = 0;
+    size_t bytes_geometry = 0, bytes_textures = 0;
+    // scratch for the host-buffer entry points (rt_find_nearest / rt_is_occluded)
+    std::mutex scratch_mutex;
+    void* scratch_in = nullptr;
+    void* scratch_out = nullptr;
+    size_t scratch_in_bytes = 0, scratch_out_bytes = 0;
+    cudaStream_t stream = nullptr;
+};

@@ -1,0 +1,782 @@
+// rt_render.cu — the two integrators as wavefront pipelines over SoA ray queues.
+//
+// Replaces (reference, /root/reference):
+//   path tracer  3. PathTracer/renderer.cpp: Sample :50-100, HandleMirror :20-25, HandleDielectric :27-45,
+//                ProcessTile :117-131, Tick :144-168; diffusereflection template/tmplmath.h:535-544
+//   Whitted      2. WhittedStyle/renderer.cpp: Trace :21-91, DirectIllumination :105-126, Tick :131-157
+//
+// Path tracer.  The reference carries ONE xorshift32 stream through the 256 pixels of a 16x16 tile
+// (seeded per tile per frame), so pixels of a tile are serially dependent but every (tile, frame) pair
+// is independent.  Each such pair is one wavefront *slot*: it owns one ray at a time; when its path
+// ends the shade stage splats the sample and regenerates the next pixel's primary ray from the same
+// stream.  Stages (separate kernels, persistent grid-stride, counts stay on the device):
+//   generate  first primary ray of every slot
+//   extend    closest hit for every queued slot (rt_device.cuh traverse)
+//   shade     sky / light / depth-limit termination, material evaluation, RNG, next ray, regeneration;
+//             survivors are compacted into the next queue with warp ballot/popc + one atomic per warp
+// The reference path tracer has no next-event estimation, so it has no connect stage.
+//
+// Whitted.  Rays carry (pixel, weight); shade splats sky / light / ambient terms, pushes reflection and
+// refraction rays into the next queue and one shadow ray per diffuse hit into the shadow queue;
+//   connect   any-hit occlusion kernel over the shadow queue, adds the direct term when visible.
+#include <cstdio>
+#include <cstring>
+
+#include "rt_internal.h"
+
+namespace rtb {
+
+struct PTState {
+    float4* rayO;      // O.xyz, -
+    float4* rayD;      // D.xyz, int flags = inside | depth << 8
+    float4* hit;       // t, u, v, int objIdx
+    int* hitTri;
+    uint32_t* seed;
+    int* pix;          // next pixel of the tile this slot will generate (0..256)
+    float4* weights;   // [depth_limit][slots]: throughput factor of every bounce (see k_pt_shade)
+    int* active[2];
+    int* count;        // [2]
+    unsigned long long* counters; // [0] extension rays, [1] shadow rays, [2] iterations
+    float4* accum;
+    int slots, nTiles, tilesX, tileBegin;
+    int firstSpp, stride;
+    int W, H, depthLimit, seedMode;
+    float eps;
+};
+
+__device__ __forceinline__ uint32_t pt_seed(const PTState& p, int tile, int spp)
+{
+    const int tx = tile % p.tilesX, ty = tile / p.tilesX;
+    return init_seed((uint32_t)(tx + ty * p.W + spp * 1799)); // renderer.cpp:120
+}
+
+// Generates the primary ray of pixel `pix` of the slot's tile (renderer.cpp:121-126): jitter draws
+// y first, then x (argument evaluation order of the reference build, see oracle/ref_build).
+__device__ __forceinline__ void pt_generate(const PTState& p, const DCamera& cam, int slot, int pix, uint32_t& seed, float3& D)
+{
+    const int tile = p.tileBegin + slot % p.nTiles;
+    const int tx = tile % p.tilesX, ty = tile / p.tilesX;
+    const int x = tx * 16 + (pix & 15), y = ty * 16 + (pix >> 4);
+    if (p.seedMode == RT_SEED_PER_PIXEL)
+    {
+        const int spp = p.firstSpp + (slot / p.nTiles) * p.stride;
+        seed = init_seed((uint32_t)(x + y * p.W) + (uint32_t)spp * 0x9E3779B1u);
+        if (seed == 0) seed = 0x12345678u;
+    }
+    const float jy = random_float(seed);
+    const float jx = random_float(seed);
+    D = primary_dir(cam, (float)x + jx, (float)y + jy);
+}
+
+__global__ void __launch_bounds__(256) k_pt_generate(const PTState p, const DCamera cam)
+{
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < p.slots; slot += gridDim.x * blockDim.x)
+    {
+        const int tile = p.tileBegin + slot % p.nTiles;
+        const int spp = p.firstSpp + (slot / p.nTiles) * p.stride;
+        uint32_t seed = pt_seed(p, tile, spp);
+        float3 D;
+        pt_generate(p, cam, slot, 0, seed, D);
+        p.rayO[slot] = make_float4(cam.pos.x, cam.pos.y, cam.pos.z, 0);
+        p.rayD[slot] = make_float4(D.x, D.y, D.z, __int_as_float(0));
+        p.seed[slot] = seed;
+        p.pix[slot] = 1;
+        p.active[0][slot] = slot;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.count[0] = p.slots, p.count[1] = 0;
+}
+
+__global__ void __launch_bounds__(128) k_pt_extend(const PTState p, const DScene s, int cur)
+{
+    const int n = p.count[cur];
+    const int* __restrict__ active = p.active[cur];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const int slot = active[i];
+        const float4 o = p.rayO[slot], d = p.rayD[slot];
+        HitRec h;
+        find_nearest<false>(s, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), 1e34f, h);
+        p.hit[slot] = make_float4(h.t, h.u, h.v, __int_as_float(h.obj));
+        p.hitTri[slot] = h.tri;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        p.count[cur ^ 1] = 0; // the shade stage of this iteration appends here
+        p.counters[0] += (unsigned long long)n;
+        p.counters[2] += 1;
+    }
+}
+
+// diffusereflection (tmplmath.h:535-544): uniform direction by rejection; the three draws fill z, y, x
+// (right-to-left argument evaluation of make_float3 in the reference build).
+__device__ __forceinline__ float3 diffuse_reflection(float3 N, uint32_t& seed)
+{
+    float3 R;
+    do
+    {
+        const float rz = random_float(seed) * 2 - 1;
+        const float ry = random_float(seed) * 2 - 1;
+        const float rx = random_float(seed) * 2 - 1;
+        R = f3(rx, ry, rz);
+    } while (dot(R, R) > 1);
+    if (dot(R, N) < 0) R = R * -1.0f;
+    return normalize(R);
+}
+
+// One bounce of Renderer::Sample (renderer.cpp:50-100).  The reference recursion returns
+// w0 * (w1 * (... * L)); the factors w_d are stored per depth and multiplied back in that order when
+// the path ends, so a sample is bit-identical to the recursive evaluation.
+__global__ void __launch_bounds__(128) k_pt_shade(const PTState p, const DScene s, const DCamera cam, int cur)
+{
+    const int n = p.count[cur];
+    const int* __restrict__ active = p.active[cur];
+    int* __restrict__ nextActive = p.active[cur ^ 1];
+    const int lane = threadIdx.x & 31;
+    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x)
+    {
+        const int i = base + threadIdx.x;
+        bool alive = false;
+        int slot = -1;
+        if (i < n)
+        {
+            slot = active[i];
+            alive = true;
+            const float4 o4 = p.rayO[slot], d4 = p.rayD[slot], h4 = p.hit[slot];
+            const float3 O = f3(o4.x, o4.y, o4.z), D = f3(d4.x, d4.y, d4.z);
+            const int flags = __float_as_int(d4.w);
+            const bool inside = flags & 1;
+            int depth = flags >> 8;
+            const int obj = __float_as_int(h4.w);
+            const float t = h4.x;
+            uint32_t seed = p.seed[slot];
+            float3 L = f3(0, 0, 0);
+            bool terminated = false;
+            if (obj == -1) L = sky_color(s, D), terminated = true;          // renderer.cpp:54
+            else if (depth >= p.depthLimit) terminated = true;               // renderer.cpp:55
+            else
+            {
+                const float3 I = O + t * D;
+                ShadeHit h;
+                float uu, vv;
+                hit_info(s, D, I, obj, p.hitTri[slot], h4.y, h4.z, h, uu, vv);
+                if (h.isLight) L = f3(s.light_color[0], s.light_color[1], s.light_color[2]), terminated = true; // :69
+                else
+                {
+                    float3 medium_scale = f3(1, 1, 1);
+                    if (inside)
+                    {
+                        const float3 a = h.absorption * -t; // renderer.cpp:76-80
+                        medium_scale = f3(expf(a.x), expf(a.y), expf(a.z));
+                    }
+                    const float r = random_float(seed);
+                    float3 w, nD;
+                    bool nInside = false;
+                    if (r < h.reflectivity)
+                    {
+                        nD = reflect(D, h.N); // HandleMirror :20-25
+                        w = h.albedo * medium_scale;
+                    }
+                    else if (r < h.reflectivity + h.refractivity)
+                    {
+                        // HandleDielectric :27-45
+                        w = h.albedo * medium_scale;
+                        nD = reflect(D, h.N);
+                        const float n1 = inside ? 1.2f : 1, n2 = inside ? 1 : 1.2f;
+                        const float eta = n1 / n2, cosi = dot(-D, h.N);
+                        const float cost2 = 1.0f - eta * eta * (1 - cosi * cosi);
+                        if (cost2 > 0)
+                        {
+                            const float a = n1 - n2, b = n1 + n2, R0 = (a * a) / (b * b), c = 1 - cosi;
+                            const float Fr = R0 + (1 - R0) * (c * c * c * c * c);
+                            const float3 T = eta * D + ((eta * cosi - sqrtf(fabsf(cost2))) * h.N);
+                            if (random_float(seed) > Fr) nD = T, nInside = !inside;
+                        }
+                    }
+                    else
+                    {
+                        nD = diffuse_reflection(h.N, seed);
+                        const float3 brdf = h.albedo * RT_INVPI;
+                        w = medium_scale * brdf * 2.0f * RT_PI * dot(nD, h.N); // renderer.cpp:98
+                    }
+                    const float3 nO = I + nD * p.eps;
+                    p.weights[(size_t)depth * p.slots + slot] = make_float4(w.x, w.y, w.z, 0);
+                    depth++;
+                    p.rayO[slot] = make_float4(nO.x, nO.y, nO.z, 0);
+                    p.rayD[slot] = make_float4(nD.x, nD.y, nD.z, __int_as_float((nInside ? 1 : 0) | (depth << 8)));
+                }
+            }
+            if (terminated)
+            {
+                for (int d = depth - 1; d >= 0; d--)
+                {
+                    const float4 w = p.weights[(size_t)d * p.slots + slot];
+                    L = f3(w.x, w.y, w.z) * L;
+                }
+                int pix = p.pix[slot]; // index of the NEXT pixel; the finished one is pix - 1
+                {
+                    const int tile = p.tileBegin + slot % p.nTiles;
+                    const int tx = tile % p.tilesX, ty = tile / p.tilesX;
+                    const int x = tx * 16 + ((pix - 1) & 15), y = ty * 16 + ((pix - 1) >> 4);
+                    float* a = (float*)(p.accum + (x + (size_t)y * p.W)); // renderer.cpp:124: accumulator += float4(sample, 0)
+                    atomicAdd(a + 0, L.x), atomicAdd(a + 1, L.y), atomicAdd(a + 2, L.z);
+                }
+                if (pix < 256)
+                {
+                    float3 nD;
+                    pt_generate(p, cam, slot, pix, seed, nD);
+                    p.rayO[slot] = make_float4(cam.pos.x, cam.pos.y, cam.pos.z, 0);
+                    p.rayD[slot] = make_float4(nD.x, nD.y, nD.z, __int_as_float(0));
+                    p.pix[slot] = pix + 1;
+                }
+                else alive = false;
+            }
+            p.seed[slot] = seed;
+        }
+        // compaction: one atomic per warp (ballot + popc), lanes write their rank
+        const unsigned mask = __ballot_sync(0xffffffffu, alive);
+        if (mask)
+        {
+            const int leader = __ffs(mask) - 1;
+            int pos = 0;
+            if (lane == leader) pos = atomicAdd(&p.count[cur ^ 1], __popc(mask));
+            pos = __shfl_sync(0xffffffffu, pos, leader);
+            if (alive) nextActive[pos + __popc(mask & ((1u << lane) - 1))] = slot;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Whitted wavefront
+// ---------------------------------------------------------------------------------------------
+struct WhState {
+    float4* rayO[2];   // O.xyz, -
+    float4* rayD[2];   // D.xyz, int flags = inside | depth << 8
+    float4* rayW[2];   // weight.xyz, int pixel
+    float4* hit;       // t, u, v, int objIdx
+    int* hitTri;
+    float4* shadow;    // 5 x float4 per entry: (O, tmax) (D, int pixel) (w~, -) (coef, -) (irradiance, -)
+    int* count;        // [0],[1] ray queues, [2] shadow queue, [3] overflow flag
+    unsigned long long* counters;
+    float4* accum;
+    int capacity, W, H, depthLimit;
+    float eps;
+};
+
+__global__ void __launch_bounds__(256) k_wh_generate(const WhState p, const DCamera cam)
+{
+    const int n = p.W * p.H;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const int x = i % p.W, y = i / p.W;
+        const float3 D = primary_dir(cam, (float)x, (float)y); // renderer.cpp:144
+        p.rayO[0][i] = make_float4(cam.pos.x, cam.pos.y, cam.pos.z, 0);
+        p.rayD[0][i] = make_float4(D.x, D.y, D.z, __int_as_float(0));
+        p.rayW[0][i] = make_float4(1, 1, 1, __int_as_float(i));
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.count[0] = n, p.count[1] = 0, p.count[2] = 0;
+}
+
+__global__ void __launch_bounds__(128) k_wh_extend(const WhState p, const DScene s, int cur)
+{
+    const int n = min(p.count[cur], p.capacity);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const float4 o = p.rayO[cur][i], d = p.rayD[cur][i];
+        HitRec h;
+        find_nearest<false>(s, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), 1e34f, h);
+        p.hit[i] = make_float4(h.t, h.u, h.v, __int_as_float(h.obj));
+        p.hitTri[i] = h.tri;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        p.count[cur ^ 1] = 0, p.count[2] = 0;
+        p.counters[0] += (unsigned long long)n;
+        p.counters[2] += 1;
+    }
+}
+
+__device__ __forceinline__ void splat(float4* accum, int pixel, float3 c)
+{
+    float* a = (float*)(accum + pixel);
+    atomicAdd(a + 0, c.x), atomicAdd(a + 1, c.y), atomicAdd(a + 2, c.z);
+}
+
+// warp-aggregated queue append; returns the slot or -1 (not pushing / overflow)
+__device__ __forceinline__ int queue_push(bool want, int* counter, int capacity, int* overflow)
+{
+    const unsigned mask = __ballot_sync(0xffffffffu, want);
+    if (!mask) return -1;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    int pos = 0;
+    if (lane == leader) pos = atomicAdd(counter, __popc(mask));
+    pos = __shfl_sync(0xffffffffu, pos, leader);
+    if (!want) return -1;
+    pos += __popc(mask & ((1u << lane) - 1));
+    if (pos >= capacity) { *overflow = 1; return -1; }
+    return pos;
+}
+
+// One level of Renderer::Trace (2. WhittedStyle/renderer.cpp:21-91), top-down: a ray's weight is the
+// product of the factors the reference applies on the way back up (medium_scale, reflectivity*albedo,
+// albedo*(1-Fr), albedo*Fr); the diffuse term keeps the reference's own grouping
+// diffuseness*brdf*(irradiance + ambient) by deferring it to the connect stage.
+__global__ void __launch_bounds__(128) k_wh_shade(const WhState p, const DScene s, int cur)
+{
+    const int n = min(p.count[cur], p.capacity);
+    const int nxt = cur ^ 1;
+    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x)
+    {
+        const int i = base + threadIdx.x;
+        bool push1 = false, push2 = false, pushS = false;
+        float3 o1, d1, w1, o2, d2, w2, so, sd, sw, scoef, sirr;
+        float stmax = 0;
+        int f1 = 0, f2 = 0, pixel = 0;
+        if (i < n)
+        {
+            const float4 o4 = p.rayO[cur][i], d4 = p.rayD[cur][i], w4 = p.rayW[cur][i], h4 = p.hit[i];
+            const float3 O = f3(o4.x, o4.y, o4.z), D = f3(d4.x, d4.y, d4.z), w = f3(w4.x, w4.y, w4.z);
+            pixel = __float_as_int(w4.w);
+            const int flags = __float_as_int(d4.w);
+            const bool inside = flags & 1;
+            const int depth = flags >> 8;
+            const int obj = __float_as_int(h4.w);
+            const float t = h4.x;
+            if (obj == -1) splat(p.accum, pixel, w * sky_color(s, D)); // renderer.cpp:25
+            else
+            {
+                const float3 I = O + t * D;
+                ShadeHit h;
+                float uu, vv;
+                hit_info(s, D, I, obj, p.hitTri[i], h4.y, h4.z, h, uu, vv);
+                if (h.isLight) splat(p.accum, pixel, w * f3(s.light_color[0], s.light_color[1], s.light_color[2]));
+                else
+                {
+                    float3 medium_scale = f3(1, 1, 1);
+                    if (inside) // renderer.cpp:81-88
+                        medium_scale = f3(expf(h.absorption.x * -t), expf(h.absorption.y * -t), expf(h.absorption.z * -t));
+                    const float3 wm = w * medium_scale;
+                    const float reflectivity = h.reflectivity, refractivity = h.refractivity;
+                    const float diffuseness = 1 - (reflectivity + refractivity);
+                    const bool deeper = depth + 1 <= p.depthLimit; // Trace returns 0 when depth > depthLimit (:23)
+                    if (reflectivity > 0.0f)
+                    {
+                        const float3 R = reflect(D, h.N);
+                        if (deeper) push1 = true, o1 = I + R * p.eps, d1 = R, w1 = wm * (reflectivity * h.albedo), f1 = (depth + 1) << 8;
+                    }
+                    else if (refractivity > 0.0f)
+                    {
+                        const float3 R = reflect(D, h.N);
+                        const float n1 = inside ? 1.2f : 1, n2 = inside ? 1 : 1.2f;
+                        const float eta = n1 / n2, cosi = dot(-D, h.N);
+                        const float cost2 = 1.0f - eta * eta * (1 - cosi * cosi);
+                        float Fr = 1;
+                        if (cost2 > 0)
+                        {
+                            const float a = n1 - n2, b = n1 + n2, R0 = (a * a) / (b * b), c = 1 - cosi;
+                            Fr = R0 + (1 - R0) * (c * c * c * c * c);
+                            const float3 T = eta * D + ((eta * cosi - sqrtf(fabsf(cost2))) * h.N);
+                            if (deeper) push2 = true, o2 = I + T * p.eps, d2 = T, w2 = wm * (h.albedo * (1 - Fr)), f2 = ((depth + 1) << 8) | (inside ? 0 : 1);
+                        }
+                        if (deeper) push1 = true, o1 = I + R * p.eps, d1 = R, w1 = wm * (h.albedo * Fr), f1 = (depth + 1) << 8;
+                    }
+                    if (diffuseness > 0)
+                    {
+                        // DirectIllumination renderer.cpp:105-126
+                        const float3 ambient = f3(0.3f, 0.3f, 0.3f);
+                        const float3 brdf = h.albedo * RT_INVPI;
+                        const float3 coef = diffuseness * brdf;
+                        float3 Lv = f3(s.light_pos[0], s.light_pos[1], s.light_pos[2]) - I;
+                        const float distance = sqrtf(dot(Lv, Lv));
+                        Lv = Lv * (1 / distance);
+                        const float ndotl = dot(h.N, Lv);
+                        if (ndotl < p.eps) splat(p.accum, pixel, wm * (coef * (f3(0, 0, 0) + ambient)));
+                        else
+                        {
+                            const float attenuation = 1 / (distance * distance);
+                            const float3 in_radiance = f3(s.light_color[0], s.light_color[1], s.light_color[2]) * attenuation;
+                            pushS = true, so = I + Lv * p.eps, sd = Lv, stmax = distance - 2 * p.eps;
+                            sw = wm, scoef = coef, sirr = in_radiance * dot(h.N, Lv);
+                        }
+                    }
+                }
+            }
+        }
+        // refraction ray first, reflection second (evaluation order of renderer.cpp:68-71; only the
+        // accumulation order depends on it)
+        int q = queue_push(push2, &p.count[nxt], p.capacity, &p.count[3]);
+        if (q >= 0)
+        {
+            p.rayO[nxt][q] = make_float4(o2.x, o2.y, o2.z, 0);
+            p.rayD[nxt][q] = make_float4(d2.x, d2.y, d2.z, __int_as_float(f2));
+            p.rayW[nxt][q] = make_float4(w2.x, w2.y, w2.z, __int_as_float(pixel));
+        }
+        q = queue_push(push1, &p.count[nxt], p.capacity, &p.count[3]);
+        if (q >= 0)
+        {
+            p.rayO[nxt][q] = make_float4(o1.x, o1.y, o1.z, 0);
+            p.rayD[nxt][q] = make_float4(d1.x, d1.y, d1.z, __int_as_float(f1));
+            p.rayW[nxt][q] = make_float4(w1.x, w1.y, w1.z, __int_as_float(pixel));
+        }
+        q = queue_push(pushS, &p.count[2], p.capacity, &p.count[3]);
+        if (q >= 0)
+        {
+            float4* e = p.shadow + 5 * (size_t)q;
+            e[0] = make_float4(so.x, so.y, so.z, stmax);
+            e[1] = make_float4(sd.x, sd.y, sd.z, __int_as_float(pixel));
+            e[2] = make_float4(sw.x, sw.y, sw.z, 0);
+            e[3] = make_float4(scoef.x, scoef.y, scoef.z, 0);
+            e[4] = make_float4(sirr.x, sirr.y, sirr.z, 0);
+        }
+    }
+}
+
+// connect: shadow rays in their own any-hit kernel (IsOccluded, file_scene.cpp:177-187), then
+// out_radiance += diffuseness * brdf * (irradiance + ambient) (renderer.cpp:74-79)
+__global__ void __launch_bounds__(128) k_wh_connect(const WhState p, const DScene s)
+{
+    const int n = min(p.count[2], p.capacity);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const float4* e = p.shadow + 5 * (size_t)i;
+        const float4 a = e[0], b = e[1], w = e[2], c = e[3], ir = e[4];
+        const bool occluded = is_occluded(s, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w);
+        const float3 irradiance = occluded ? f3(0, 0, 0) : f3(ir.x, ir.y, ir.z);
+        const float3 ambient = f3(0.3f, 0.3f, 0.3f);
+        splat(p.accum, __float_as_int(b.w), f3(w.x, w.y, w.z) * (f3(c.x, c.y, c.z) * (irradiance + ambient)));
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.counters[1] += (unsigned long long)n;
+}
+
+// screen->pixels: RGBF32_to_RGB8 (template/precomp.h:325-341, scalar branch) of accumulator * scale
+__global__ void k_to_rgb8(const float4* __restrict__ accum, uint32_t* __restrict__ out, int n, float scale)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const float4 a = accum[i];
+        const float x = a.x * scale, y = a.y * scale, z = a.z * scale;
+        const uint32_t r = (uint32_t)(255.0f * smin(1.0f, x));
+        const uint32_t g = (uint32_t)(255.0f * smin(1.0f, y));
+        const uint32_t b = (uint32_t)(255.0f * smin(1.0f, z));
+        out[i] = (r << 16) + (g << 8) + b;
+    }
+}
+
+} // namespace rtb
+
+using namespace rtb;
+
+struct rt_renderer {
+    rt_scene* scene = nullptr;
+    rt_render_params params = {};
+    DCamera cam = {};
+    cudaStream_t ownStream = nullptr, stream = nullptr;
+    float4* ownAccum = nullptr;
+    float4* accum = nullptr;
+    int sms = 148;
+    // path tracer
+    PTState pt = {};
+    int ptSlotsAllocated = 0;
+    std::vector<void*> allocations;
+    // whitted
+    WhState wh = {};
+    // counters
+    unsigned long long* dCounters = nullptr; // 4
+    int* dCount = nullptr;                   // 4
+    int* hCount = nullptr;                   // pinned
+    uint64_t paths = 0, launches = 0;
+    uint32_t* dPixels = nullptr;
+    bool overflowed = false;
+};
+
+template <class T>
+static rt_status ralloc(rt_renderer* r, T** p, size_t bytes)
+{
+    *p = nullptr;
+    RT_CUDA(cudaMalloc((void**)p, bytes ? bytes : 16));
+    r->allocations.push_back(*p);
+    return RT_OK;
+}
+
+static DCamera make_camera(const rt_camera& c, int W, int H)
+{
+    DCamera d;
+    d.pos = make_float3(c.pos[0], c.pos[1], c.pos[2]);
+    d.topLeft = make_float3(c.top_left[0], c.top_left[1], c.top_left[2]);
+    d.topRight = make_float3(c.top_right[0], c.top_right[1], c.top_right[2]);
+    d.bottomLeft = make_float3(c.bottom_left[0], c.bottom_left[1], c.bottom_left[2]);
+    d.invW = 1.0f / W, d.invH = 1.0f / H; // camera.h:26-27
+    return d;
+}
+
+static int num_tiles(const rt_render_params& p)
+{
+    const int all = (p.width / 16) * (p.height / 16); // renderer.cpp:151 (integer division)
+    const int end = p.tile_end > 0 ? (p.tile_end < all ? p.tile_end : all) : all;
+    const int n = end - p.tile_begin;
+    return n > 0 ? n : 0;
+}
+
+extern "C" {
+
+void rt_render_params_default(rt_render_params* p, int integrator, int width, int height)
+{
+    memset(p, 0, sizeof *p);
+    p->integrator = integrator, p->width = width, p->height = height;
+    p->depth_limit = 5, p->epsilon = 0.001f, p->seed_mode = RT_SEED_REFERENCE_TILE;
+}
+
+rt_status rt_renderer_create(rt_scene* scene, const rt_render_params* params, rt_renderer** out)
+{
+    if (!scene || !params || !out) { set_error("rt_renderer_create: null argument"); return RT_ERR_INVALID; }
+    *out = nullptr;
+    if (params->width <= 0 || params->height <= 0 || params->depth_limit < 0 || params->depth_limit > 64)
+    {
+        set_error("rt_renderer_create: bad width / height / depth_limit");
+        return RT_ERR_INVALID;
+    }
+    if (params->integrator != RT_INTEGRATOR_PATH && params->integrator != RT_INTEGRATOR_WHITTED)
+    {
+        set_error("rt_renderer_create: unknown integrator");
+        return RT_ERR_INVALID;
+    }
+    RT_CUDA(cudaSetDevice(scene->device));
+    rt_renderer* r = new rt_renderer();
+    r->scene = scene, r->params = *params;
+    cudaDeviceGetAttribute(&r->sms, cudaDevAttrMultiProcessorCount, scene->device);
+    rt_camera cam;
+    rt_camera_default(&cam, params->width, params->height);
+    r->cam = make_camera(cam, params->width, params->height);
+    rt_status st = RT_OK;
+    auto fail = [&](rt_status e) { rt_renderer_destroy(r); return e; };
+    if (cudaStreamCreateWithFlags(&r->ownStream, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream create failed"); return fail(RT_ERR_CUDA); }
+    r->stream = r->ownStream;
+    const size_t px = (size_t)params->width * params->height;
+    if ((st = ralloc(r, &r->ownAccum, px * 16)) != RT_OK) return fail(st);
+    r->accum = r->ownAccum;
+    if (cudaMemset(r->ownAccum, 0, px * 16) != cudaSuccess) return fail(RT_ERR_CUDA);
+    if ((st = ralloc(r, &r->dCounters, 4 * sizeof(unsigned long long))) != RT_OK) return fail(st);
+    if ((st = ralloc(r, &r->dCount, 4 * sizeof(int))) != RT_OK) return fail(st);
+    cudaMemset(r->dCounters, 0, 4 * sizeof(unsigned long long));
+    cudaMemset(r->dCount, 0, 4 * sizeof(int));
+    if (cudaMallocHost((void**)&r->hCount, 4 * sizeof(int)) != cudaSuccess) { set_error("pinned alloc failed"); return fail(RT_ERR_CUDA); }
+    if ((st = ralloc(r, &r->dPixels, px * 4)) != RT_OK) return fail(st);
+
+    if (params->integrator == RT_INTEGRATOR_WHITTED)
+    {
+        WhState& w = r->wh;
+        w.capacity = (int)(4 * px);
+        for (int k = 0; k < 2; k++)
+        {
+            if ((st = ralloc(r, &w.rayO[k], (size_t)w.capacity * 16)) != RT_OK) return fail(st);
+            if ((st = ralloc(r, &w.rayD[k], (size_t)w.capacity * 16)) != RT_OK) return fail(st);
+            if ((st = ralloc(r, &w.rayW[k], (size_t)w.capacity * 16)) != RT_OK) return fail(st);
+        }
+        if ((st = ralloc(r, &w.hit, (size_t)w.capacity * 16)) != RT_OK) return fail(st);
+        if ((st = ralloc(r, &w.hitTri, (size_t)w.capacity * 4)) != RT_OK) return fail(st);
+        if ((st = ralloc(r, &w.shadow, (size_t)w.capacity * 80)) != RT_OK) return fail(st);
+        w.count = r->dCount, w.counters = r->dCounters;
+        w.W = params->width, w.H = params->height, w.depthLimit = params->depth_limit, w.eps = params->epsilon;
+    }
+    *out = r;
+    return RT_OK;
+}
+
+void rt_renderer_destroy(rt_renderer* r)
+{
+    if (!r) return;
+    cudaSetDevice(r->scene->device);
+    if (r->stream) cudaStreamSynchronize(r->stream);
+    for (void* p : r->allocations) cudaFree(p);
+    if (r->hCount) cudaFreeHost(r->hCount);
+    if (r->ownStream) cudaStreamDestroy(r->ownStream);
+    delete r;
+}
+
+rt_status rt_renderer_set_stream(rt_renderer* r, void* stream)
+{
+    if (!r) return RT_ERR_INVALID;
+    r->stream = stream ? (cudaStream_t)stream : r->ownStream;
+    return RT_OK;
+}
+
+rt_status rt_renderer_set_accumulator(rt_renderer* r, void* d_accumulator)
+{
+    if (!r) return RT_ERR_INVALID;
+    r->accum = d_accumulator ? (float4*)d_accumulator : r->ownAccum;
+    return RT_OK;
+}
+
+rt_status rt_renderer_set_camera(rt_renderer* r, const rt_camera* cam)
+{
+    if (!r || !cam) return RT_ERR_INVALID;
+    r->cam = make_camera(*cam, r->params.width, r->params.height);
+    return RT_OK;
+}
+
+rt_status rt_renderer_clear(rt_renderer* r)
+{
+    if (!r) return RT_ERR_INVALID;
+    RT_CUDA(cudaSetDevice(r->scene->device));
+    RT_CUDA(cudaMemsetAsync(r->accum, 0, (size_t)r->params.width * r->params.height * 16, r->stream));
+    return RT_OK;
+}
+
+static rt_status pt_ensure_slots(rt_renderer* r, int slots)
+{
+    if (slots <= r->ptSlotsAllocated) return RT_OK;
+    // (re)allocate; old buffers stay in the allocation list until destroy (growth happens at most a few times)
+    PTState& p = r->pt;
+    rt_status st;
+    const size_t S = (size_t)slots;
+    if ((st = ralloc(r, &p.rayO, S * 16)) != RT_OK) return st;
+    if ((st = ralloc(r, &p.rayD, S * 16)) != RT_OK) return st;
+    if ((st = ralloc(r, &p.hit, S * 16)) != RT_OK) return st;
+    if ((st = ralloc(r, &p.hitTri, S * 4)) != RT_OK) return st;
+    if ((st = ralloc(r, &p.seed, S * 4)) != RT_OK) return st;
+    if ((st = ralloc(r, &p.pix, S * 4)) != RT_OK) return st;
+    const size_t levels = r->params.depth_limit > 0 ? r->params.depth_limit : 1;
+    if ((st = ralloc(r, &p.weights, S * 16 * levels)) != RT_OK) return st;
+    if ((st = ralloc(r, &p.active[0], S * 4)) != RT_OK) return st;
+    if ((st = ralloc(r, &p.active[1], S * 4)) != RT_OK) return st;
+    r->ptSlotsAllocated = slots;
+    return RT_OK;
+}
+
+static rt_status render_pt(rt_renderer* r, int first_spp, int count, int stride)
+{
+    const rt_render_params& P = r->params;
+    const int nTiles = num_tiles(P);
+    if (nTiles == 0 || count <= 0) return RT_OK;
+    int inFlight = P.max_frames_in_flight > 0 ? P.max_frames_in_flight : (1 << 20) / nTiles;
+    if (inFlight < 1) inFlight = 1;
+    if (inFlight > count) inFlight = count;
+    rt_status st = pt_ensure_slots(r, nTiles * inFlight);
+    if (st != RT_OK) return st;
+    PTState& p = r->pt;
+    p.count = r->dCount, p.counters = r->dCounters, p.accum = r->accum;
+    p.nTiles = nTiles, p.tilesX = P.width / 16, p.tileBegin = P.tile_begin;
+    p.W = P.width, p.H = P.height, p.depthLimit = P.depth_limit, p.seedMode = P.seed_mode, p.eps = P.epsilon;
+    p.stride = stride;
+    const int grid = r->sms * 8;
+    // every path makes at most depth_limit + 1 FindNearest queries, every slot 256 paths
+    const int maxIters = 256 * (P.depth_limit + 1) + 1;
+    for (int done = 0; done < count; done += inFlight)
+    {
+        const int frames = count - done < inFlight ? count - done : inFlight;
+        p.slots = nTiles * frames;
+        p.firstSpp = first_spp + done * stride;
+        k_pt_generate<<<r->sms * 4, 256, 0, r->stream>>>(p, r->cam);
+        r->launches++;
+        int cur = 0;
+        for (int it = 0; it < maxIters; it++)
+        {
+            k_pt_extend<<<grid, 128, 0, r->stream>>>(p, r->scene->d, cur);
+            k_pt_shade<<<grid, 128, 0, r->stream>>>(p, r->scene->d, r->cam, cur);
+            r->launches += 2;
+            cur ^= 1;
+            if ((it & 31) == 31)
+            {
+                RT_CUDA(cudaMemcpyAsync(r->hCount, p.count + cur, sizeof(int), cudaMemcpyDeviceToHost, r->stream));
+                RT_CUDA(cudaStreamSynchronize(r->stream));
+                if (r->hCount[0] == 0) break;
+            }
+        }
+        r->paths += (uint64_t)p.slots * 256;
+    }
+    RT_CUDA(cudaGetLastError());
+    return RT_OK;
+}
+
+static rt_status render_whitted(rt_renderer* r)
+{
+    const rt_render_params& P = r->params;
+    WhState& w = r->wh;
+    w.accum = r->accum;
+    const size_t px = (size_t)P.width * P.height;
+    // Tick overwrites the accumulator every frame (renderer.cpp:155)
+    RT_CUDA(cudaMemsetAsync(r->accum, 0, px * 16, r->stream));
+    k_wh_generate<<<r->sms * 4, 256, 0, r->stream>>>(w, r->cam);
+    r->launches++;
+    const int grid = r->sms * 8;
+    int cur = 0;
+    for (int depth = 0; depth <= P.depth_limit; depth++)
+    {
+        k_wh_extend<<<grid, 128, 0, r->stream>>>(w, r->scene->d, cur);
+        k_wh_shade<<<grid, 128, 0, r->stream>>>(w, r->scene->d, cur);
+        k_wh_connect<<<grid, 128, 0, r->stream>>>(w, r->scene->d);
+        r->launches += 3;
+        cur ^= 1;
+    }
+    r->paths += px;
+    RT_CUDA(cudaGetLastError());
+    return RT_OK;
+}
+
+rt_status rt_renderer_render(rt_renderer* r, int first_spp, int count, int stride)
+{
+    if (!r) { set_error("rt_renderer_render: null renderer"); return RT_ERR_INVALID; }
+    RT_CUDA(cudaSetDevice(r->scene->device));
+    if (r->params.integrator == RT_INTEGRATOR_PATH) return render_pt(r, first_spp, count, stride > 0 ? stride : 1);
+    return render_whitted(r);
+}
+
+rt_status rt_renderer_sync(rt_renderer* r)
+{
+    if (!r) return RT_ERR_INVALID;
+    RT_CUDA(cudaSetDevice(r->scene->device));
+    RT_CUDA(cudaStreamSynchronize(r->stream));
+    if (r->params.integrator == RT_INTEGRATOR_WHITTED)
+    {
+        RT_CUDA(cudaMemcpy(r->hCount, r->dCount, 4 * sizeof(int), cudaMemcpyDeviceToHost));
+        if (r->hCount[3]) { set_error("Whitted ray queue overflow (more than 4 rays per pixel alive at one depth)"); return RT_ERR_UNSUPPORTED; }
+    }
+    return RT_OK;
+}
+
+rt_status rt_renderer_read_accumulator(rt_renderer* r, float* host_rgba)
+{
+    if (!r || !host_rgba) return RT_ERR_INVALID;
+    rt_status st = rt_renderer_sync(r);
+    if (st != RT_OK) return st;
+    RT_CUDA(cudaMemcpy(host_rgba, r->accum, (size_t)r->params.width * r->params.height * 16, cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+
+rt_status rt_renderer_read_pixels(rt_renderer* r, float scale, uint32_t* host_rgb8)
+{
+    if (!r || !host_rgb8) return RT_ERR_INVALID;
+    RT_CUDA(cudaSetDevice(r->scene->device));
+    const int n = r->params.width * r->params.height;
+    k_to_rgb8<<<r->sms * 4, 256, 0, r->stream>>>(r->accum, r->dPixels, n, scale);
+    r->launches++;
+    RT_CUDA(cudaMemcpyAsync(host_rgb8, r->dPixels, (size_t)n * 4, cudaMemcpyDeviceToHost, r->stream));
+    RT_CUDA(cudaStreamSynchronize(r->stream));
+    return RT_OK;
+}
+
+void* rt_renderer_device_accumulator(rt_renderer* r) { return r ? r->accum : nullptr; }
+
+rt_status rt_renderer_get_counters(rt_renderer* r, rt_counters* out)
+{
+    if (!r || !out) return RT_ERR_INVALID;
+    rt_status st = rt_renderer_sync(r);
+    if (st != RT_OK) return st;
+    unsigned long long c[4];
+    RT_CUDA(cudaMemcpy(c, r->dCounters, sizeof c, cudaMemcpyDeviceToHost));
+    out->extension_rays = c[0], out->shadow_rays = c[1], out->wavefront_iterations = c[2];
+    out->paths = r->paths, out->kernel_launches = r->launches;
+    return RT_OK;
+}
+
+rt_status rt_renderer_reset_counters(rt_renderer* r)
+{
+    if (!r) return RT_ERR_INVALID;
+    rt_status st = rt_renderer_sync(r);
+    if (st != RT_OK) return st;
+    RT_CUDA(cudaMemset(r->dCounters, 0, 4 * sizeof(unsigned long long)));
+    r->paths = 0, r->launches = 0;
+    return RT_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,442 @@
+// rt_scene.cu — scene upload / re-layout and the batched Scene::FindNearest / IsOccluded entry points.
+//
+// Replaces (reference, /root/reference): FileScene::FindNearest / IsOccluded (infra/scene/file_scene.cpp:170-187),
+// TLASFileScene::FindNearest / IsOccluded (infra/scene/tlas_file_scene.cpp:201-218) and everything they
+// call: BVH::Intersect (infra/bvh.cpp:224-288), TLASBVH::Intersect (infra/tlas_bvh.cpp:83-111),
+// BLASBVH::Intersect (infra/blas_bvh.cpp:302-389), Quad / Plane tests (template/primitives.h:107-111,331-362).
+#include <cstdio>
+#include <cstring>
+
+#include "rt_internal.h"
+
+namespace rtb {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+bool cuda_ok(cudaError_t e, const char* what)
+{
+    if (e == cudaSuccess) return true;
+    g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernels: one thread per ray, AoS rt_ray (32 B) in, rt_hit (32 B) out — the C-ABI record layout.
+// Grid-stride so the launch is a whole number of waves (blocks = k x SM count).
+// ---------------------------------------------------------------------------------------------
+template <bool COUNTERS>
+__global__ void __launch_bounds__(128) k_find_nearest(const DScene s, const rt_ray* __restrict__ rays, rt_hit* __restrict__ hits, size_t n)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    {
+        const float4 a = __ldg((const float4*)(rays + i));
+        const float4 b = __ldg((const float4*)(rays + i) + 1);
+        HitRec h;
+        find_nearest<COUNTERS>(s, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, h);
+        float4* out = (float4*)(hits + i);
+        out[0] = make_float4(h.t, h.u, h.v, __int_as_float(h.obj));
+        out[1] = make_float4(__int_as_float(h.tri), __int_as_float(h.traversed), __int_as_float(h.tested), 0.0f);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_is_occluded(const DScene s, const rt_ray* __restrict__ rays, uint8_t* __restrict__ out, size_t n)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    {
+        const float4 a = __ldg((const float4*)(rays + i));
+        const float4 b = __ldg((const float4*)(rays + i) + 1);
+        out[i] = is_occluded(s, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w) ? 1 : 0;
+    }
+}
+
+static int grid_for(size_t n, int block, int device)
+{
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const size_t want = (n + block - 1) / block;
+    const size_t cap = (size_t)sms * 16; // 16 CTAs of 128 threads = full residency
+    size_t g = want < cap ? want : cap;
+    if (g > (size_t)sms) g = g / sms * sms; // whole waves
+    return (int)(g ? g : 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host: re-layout of the reference arrays into the device layout documented in rt_device.cuh
+// ---------------------------------------------------------------------------------------------
+struct Builder {
+    std::vector<float4> nodes, tris, inst, shade, inst_shade;
+    std::string error;
+
+    static float4 f4(float x, float y, float z, float w) { return make_float4(x, y, z, w); }
+    static float asf(int i) { float f; memcpy(&f, &i, 4); return f; }
+
+    // Lays one reference BVH out as fat nodes (DFS pre-order); returns the ref of its root.
+    int add_bvh(const rt_blas_desc& b, int triSlotBase)
+    {
+        if (b.tri_count == 0 || b.node_count == 0) { error = "empty BLAS"; return 0; }
+        const rt_bvh_node* N = b.nodes;
+        auto leaf_ref = [&](const rt_bvh_node& n) { return ~(triSlotBase + (int)n.left_first); };
+        if (N[0].tri_count > 0) return leaf_ref(N[0]);
+        struct Item { uint32_t node; int fat; };
+        std::vector<Item> todo;
+        const int rootFat = (int)(nodes.size() / 4);
+        nodes.resize(nodes.size() + 4);
+        todo.push_back({ 0u, rootFat });
+        while (!todo.empty())
+        {
+            const Item it = todo.back();
+            todo.pop_back();
+            const rt_bvh_node& p = N[it.node];
+            if (p.left_first + 1 >= b.node_count) { error = "BVH child index out of range"; return 0; }
+            const rt_bvh_node& L = N[p.left_first];
+            const rt_bvh_node& R = N[p.left_first + 1];
+            int refs[2];
+            const rt_bvh_node* ch[2] = { &L, &R };
+            // right first so that the left subtree is laid out directly after its parent
+            for (int k = 1; k >= 0; k--)
+            {
+                if (ch[k]->tri_count > 0)
+                {
+                    if ((uint64_t)ch[k]->left_first + ch[k]->tri_count > b.tri_count) { error = "leaf range out of bounds"; return 0; }
+                    refs[k] = leaf_ref(*ch[k]);
+                }
+                else
+                {
+                    refs[k] = (int)(nodes.size() / 4);
+                    nodes.resize(nodes.size() + 4);
+                    todo.push_back({ p.left_first + (uint32_t)k, refs[k] });
+                }
+            }
+            // DFS pre-order wants the left child processed first: it was pushed last, so it pops first
+            float4* f = &nodes[4 * (size_t)it.fat];
+            f[0] = f4(L.aabb_min[0], L.aabb_min[1], L.aabb_min[2], L.aabb_max[0]);
+            f[1] = f4(L.aabb_max[1], L.aabb_max[2], R.aabb_min[0], R.aabb_min[1]);
+            f[2] = f4(R.aabb_min[2], R.aabb_max[0], R.aabb_max[1], R.aabb_max[2]);
+            f[3] = f4(asf(refs[0]), asf(refs[1]), 0, 0);
+        }
+        return rootFat;
+    }
+
+    void add_tris(const rt_blas_desc& b)
+    {
+        const size_t base = tris.size() / 3;
+        tris.resize(tris.size() + 3 * (size_t)b.tri_count);
+        std::vector<uint8_t> last(b.tri_count, 0);
+        for (uint32_t i = 0; i < b.node_count; i++)
+            if (b.nodes[i].tri_count > 0)
+            {
+                const uint64_t end = (uint64_t)b.nodes[i].left_first + b.nodes[i].tri_count;
+                if (end <= b.tri_count) last[end - 1] = 1;
+            }
+        for (uint32_t j = 0; j < b.tri_count; j++)
+        {
+            const uint32_t triIdx = b.tri_indices[j];
+            if (triIdx >= b.tri_count) { error = "triangle index out of range"; return; }
+            const rt_tri& t = b.tris[triIdx];
+            float4* o = &tris[3 * (base + j)];
+            const int tag = (int)triIdx | (last[j] ? LAST_BIT : 0);
+            // edge1 / edge2 exactly as bvh.cpp:205-206 computes them per test (fp32 subtraction)
+            o[0] = f4(t.v0[0], t.v0[1], t.v0[2], asf(tag));
+            o[1] = f4(t.v1[0] - t.v0[0], t.v1[1] - t.v0[1], t.v1[2] - t.v0[2], asf(t.obj_idx));
+            o[2] = f4(t.v2[0] - t.v0[0], t.v2[1] - t.v0[1], t.v2[2] - t.v0[2], 0);
+        }
+        for (uint32_t j = 0; j < b.tri_count; j++)
+        {
+            const rt_tri& t = b.tris[j];
+            shade.push_back(f4(t.n0[0], t.n0[1], t.n0[2], t.n1[0]));
+            shade.push_back(f4(t.n1[1], t.n1[2], t.n2[0], t.n2[1]));
+            shade.push_back(f4(t.n2[2], t.uv0[0], t.uv0[1], t.uv1[0]));
+            shade.push_back(f4(t.uv1[1], t.uv2[0], t.uv2[1], asf(t.obj_idx)));
+        }
+    }
+
+    int add_tlas(const rt_scene_desc& d)
+    {
+        const rt_tlas_node* N = d.tlas_nodes;
+        auto leaf_ref = [&](const rt_tlas_node& n) { return ~(INSTANCE_BIT | (int)n.blas); };
+        if (N[0].left_right == 0) return leaf_ref(N[0]);
+        struct Item { uint32_t node; int fat; };
+        std::vector<Item> todo;
+        const int rootFat = (int)(nodes.size() / 4);
+        nodes.resize(nodes.size() + 4);
+        todo.push_back({ 0u, rootFat });
+        size_t guard = 0;
+        while (!todo.empty())
+        {
+            if (++guard > 4ull * d.tlas_node_count + 16) { error = "TLAS is not a tree"; return 0; }
+            const Item it = todo.back();
+            todo.pop_back();
+            const rt_tlas_node& p = N[it.node];
+            const uint32_t li = p.left_right & 0xffff, ri = p.left_right >> 16;
+            if (li >= d.tlas_node_count || ri >= d.tlas_node_count) { error = "TLAS child index out of range"; return 0; }
+            const rt_tlas_node* ch[2] = { &N[li], &N[ri] };
+            const uint32_t idx[2] = { li, ri };
+            int refs[2];
+            for (int k = 1; k >= 0; k--)
+            {
+                if (ch[k]->left_right == 0)
+                {
+                    if (ch[k]->blas >= d.blas_count) { error = "TLAS leaf BLAS index out of range"; return 0; }
+                    refs[k] = leaf_ref(*ch[k]);
+                }
+                else
+                {
+                    refs[k] = (int)(nodes.size() / 4);
+                    nodes.resize(nodes.size() + 4);
+                    todo.push_back({ idx[k], refs[k] });
+                }
+            }
+            const rt_tlas_node& L = *ch[0];
+            const rt_tlas_node& R = *ch[1];
+            float4* f = &nodes[4 * (size_t)it.fat];
+            f[0] = f4(L.aabb_min[0], L.aabb_min[1], L.aabb_min[2], L.aabb_max[0]);
+            f[1] = f4(L.aabb_max[1], L.aabb_max[2], R.aabb_min[0], R.aabb_min[1]);
+            f[2] = f4(R.aabb_min[2], R.aabb_max[0], R.aabb_max[1], R.aabb_max[2]);
+            f[3] = f4(asf(refs[0]), asf(refs[1]), 0, 0);
+        }
+        return rootFat;
+    }
+};
+
+template <class T>
+static rt_status upload(T** dst, const void* src, size_t bytes)
+{
+    *dst = nullptr;
+    if (bytes == 0) bytes = 16; // keep pointers valid
+    RT_CUDA(cudaMalloc((void**)dst, bytes));
+    if (src) RT_CUDA(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+    return RT_OK;
+}
+
+} // namespace rtb
+
+using namespace rtb;
+
+extern "C" {
+
+const char* rt_last_error(void) { return g_last_error.c_str(); }
+int rt_abi_version(void) { return RT_B200_ABI_VERSION; }
+
+int rt_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags, rt_scene** out)
+{
+    if (!desc || !out) { set_error("rt_scene_create: null argument"); return RT_ERR_INVALID; }
+    *out = nullptr;
+    if (desc->blas_count == 0 || !desc->blas) { set_error("rt_scene_create: no BLAS"); return RT_ERR_INVALID; }
+    if (desc->kind == RT_SCENE_FLAT && desc->blas_count != 1) { set_error("rt_scene_create: a flat scene has exactly one BVH"); return RT_ERR_INVALID; }
+    if (desc->kind == RT_SCENE_TLAS && (!desc->tlas_nodes || desc->tlas_node_count == 0)) { set_error("rt_scene_create: TLAS scene without TLAS nodes"); return RT_ERR_INVALID; }
+    if (desc->kind != RT_SCENE_FLAT && desc->kind != RT_SCENE_TLAS) { set_error("rt_scene_create: unknown scene kind"); return RT_ERR_INVALID; }
+    if (rt_device_count() <= device || device < 0) { set_error("rt_scene_create: no such CUDA device (there is no CPU fallback)"); return RT_ERR_NO_DEVICE; }
+
+    Builder B;
+    std::vector<int> rootRefs(desc->blas_count);
+    std::vector<int> triBase(desc->blas_count);
+    for (uint32_t i = 0; i < desc->blas_count; i++)
+    {
+        const rt_blas_desc& b = desc->blas[i];
+        if (!b.nodes || !b.tris || !b.tri_indices) { set_error("rt_scene_create: BLAS with null arrays"); return RT_ERR_INVALID; }
+        triBase[i] = (int)(B.tris.size() / 3);
+        rootRefs[i] = B.add_bvh(b, triBase[i]);
+        if (B.error.empty()) B.add_tris(b);
+        if (!B.error.empty()) { set_error("rt_scene_create: " + B.error); return RT_ERR_INVALID; }
+        const float* M = b.inv_T;
+        B.inst.push_back(Builder::f4(M[0], M[1], M[2], M[3]));
+        B.inst.push_back(Builder::f4(M[4], M[5], M[6], M[7]));
+        B.inst.push_back(Builder::f4(M[8], M[9], M[10], M[11]));
+        B.inst.push_back(Builder::f4(Builder::asf(rootRefs[i]), Builder::asf(b.obj_idx), 0, 0));
+        const float* T = b.T;
+        B.inst_shade.push_back(Builder::f4(T[0], T[1], T[2], T[3]));
+        B.inst_shade.push_back(Builder::f4(T[4], T[5], T[6], T[7]));
+        B.inst_shade.push_back(Builder::f4(T[8], T[9], T[10], T[11]));
+        B.inst_shade.push_back(Builder::f4(Builder::asf(triBase[i]), 0, 0, 0));
+    }
+    int rootRef = rootRefs[0];
+    if (desc->kind == RT_SCENE_TLAS)
+    {
+        rootRef = B.add_tlas(*desc);
+        if (!B.error.empty()) { set_error("rt_scene_create: " + B.error); return RT_ERR_INVALID; }
+        // GetHitInfo indexes blas[objIdx - 2] (tlas_file_scene.cpp:237): objIdx must be i + 2
+        for (uint32_t i = 0; i < desc->blas_count; i++)
+            if (desc->blas[i].obj_idx != (int)i + 2) { set_error("rt_scene_create: TLAS scenes need blas[i].obj_idx == i + 2"); return RT_ERR_INVALID; }
+    }
+
+    RT_CUDA(cudaSetDevice(device));
+    rt_scene* s = new rt_scene();
+    s->device = device, s->flags = flags;
+    rt_status st = RT_OK;
+    auto fail = [&](rt_status e) { rt_scene_destroy(s); return e; };
+    if ((st = upload(&s->nodes, B.nodes.data(), B.nodes.size() * 16)) != RT_OK) return fail(st);
+    if ((st = upload(&s->tris, B.tris.data(), B.tris.size() * 16)) != RT_OK) return fail(st);
+    if ((st = upload(&s->inst, B.inst.data(), B.inst.size() * 16)) != RT_OK) return fail(st);
+    if ((st = upload(&s->shade, B.shade.data(), B.shade.size() * 16)) != RT_OK) return fail(st);
+    if ((st = upload(&s->inst_shade, B.inst_shade.data(), B.inst_shade.size() * 16)) != RT_OK) return fail(st);
+    if ((st = upload(&s->obj_material, desc->obj_material, desc->obj_count * sizeof(int))) != RT_OK) return fail(st);
+    s->node_count = B.nodes.size() / 4, s->tri_count = B.tris.size() / 3, s->inst_count = desc->blas_count;
+    s->bytes_geometry = (B.nodes.size() + B.tris.size() + B.inst.size() + B.shade.size() + B.inst_shade.size()) * 16;
+
+    static_assert(sizeof(DMaterial) == sizeof(rt_material), "material layout");
+    if ((st = upload(&s->materials, desc->materials, desc->material_count * sizeof(rt_material))) != RT_OK) return fail(st);
+    size_t texels = 0;
+    for (uint32_t i = 0; i < desc->texture_count; i++) texels += (size_t)desc->textures[i].width * desc->textures[i].height;
+    if ((st = upload(&s->tex_pixels, nullptr, texels * 4)) != RT_OK) return fail(st);
+    std::vector<DTexture> tex(desc->texture_count);
+    size_t off = 0;
+    for (uint32_t i = 0; i < desc->texture_count; i++)
+    {
+        const size_t n = (size_t)desc->textures[i].width * desc->textures[i].height;
+        tex[i].pixels = s->tex_pixels + off, tex[i].width = desc->textures[i].width, tex[i].height = desc->textures[i].height;
+        if (n && cudaMemcpy(s->tex_pixels + off, desc->textures[i].pixels, n * 4, cudaMemcpyHostToDevice) != cudaSuccess)
+        {
+            set_error("rt_scene_create: texture upload failed");
+            return fail(RT_ERR_CUDA);
+        }
+        off += n;
+    }
+    s->bytes_textures = texels * 4;
+    if ((st = upload(&s->textures, tex.data(), tex.size() * sizeof(DTexture))) != RT_OK) return fail(st);
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream create failed"); return fail(RT_ERR_CUDA); }
+
+    DScene& d = s->d;
+    d.nodes = s->nodes, d.tris = s->tris, d.inst = s->inst, d.shade = s->shade, d.inst_shade = s->inst_shade;
+    d.obj_material = s->obj_material, d.materials = s->materials, d.textures = s->textures;
+    d.root_ref = rootRef, d.kind = desc->kind;
+    d.flat_obj_idx = desc->kind == RT_SCENE_FLAT ? desc->blas[0].obj_idx : -1;
+    d.skydome_texture = desc->skydome_texture, d.floor_texture = desc->floor_texture;
+    memcpy(d.floor_n, desc->floor_n, 12), d.floor_d = desc->floor_d, d.floor_invto = desc->floor_invto;
+    memcpy(d.light_T, desc->light_T, 64), memcpy(d.light_inv_T, desc->light_inv_T, 64), d.light_size = desc->light_size;
+    memcpy(d.light_color, desc->light_color, 12), memcpy(d.light_pos, desc->light_pos, 12);
+    *out = s;
+    return RT_OK;
+}
+
+void rt_scene_destroy(rt_scene* s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    cudaFree(s->nodes), cudaFree(s->tris), cudaFree(s->inst), cudaFree(s->shade), cudaFree(s->inst_shade);
+    cudaFree(s->obj_material), cudaFree(s->materials), cudaFree(s->textures), cudaFree(s->tex_pixels);
+    cudaFree(s->scratch_in), cudaFree(s->scratch_out);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+rt_status rt_find_nearest_device(rt_scene* s, const rt_ray* d_rays, rt_hit* d_hits, size_t n, void* stream)
+{
+    if (!s || (n && (!d_rays || !d_hits))) { set_error("rt_find_nearest_device: null argument"); return RT_ERR_INVALID; }
+    if (n == 0) return RT_OK;
+    RT_CUDA(cudaSetDevice(s->device));
+    const int grid = grid_for(n, 128, s->device);
+    if (s->flags & RT_SCENE_FLAG_COUNTERS)
+        k_find_nearest<true><<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays, d_hits, n);
+    else
+        k_find_nearest<false><<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays, d_hits, n);
+    RT_CUDA(cudaGetLastError());
+    return RT_OK;
+}
+
+rt_status rt_is_occluded_device(rt_scene* s, const rt_ray* d_rays, uint8_t* d_out, size_t n, void* stream)
+{
+    if (!s || (n && (!d_rays || !d_out))) { set_error("rt_is_occluded_device: null argument"); return RT_ERR_INVALID; }
+    if (n == 0) return RT_OK;
+    RT_CUDA(cudaSetDevice(s->device));
+    k_is_occluded<<<grid_for(n, 128, s->device), 128, 0, (cudaStream_t)stream>>>(s->d, d_rays, d_out, n);
+    RT_CUDA(cudaGetLastError());
+    return RT_OK;
+}
+
+static rt_status ensure_scratch(rt_scene* s, size_t inBytes, size_t outBytes)
+{
+    if (inBytes > s->scratch_in_bytes)
+    {
+        cudaFree(s->scratch_in), s->scratch_in = nullptr, s->scratch_in_bytes = 0;
+        RT_CUDA(cudaMalloc(&s->scratch_in, inBytes));
+        s->scratch_in_bytes = inBytes;
+    }
+    if (outBytes > s->scratch_out_bytes)
+    {
+        cudaFree(s->scratch_out), s->scratch_out = nullptr, s->scratch_out_bytes = 0;
+        RT_CUDA(cudaMalloc(&s->scratch_out, outBytes));
+        s->scratch_out_bytes = outBytes;
+    }
+    return RT_OK;
+}
+
+rt_status rt_find_nearest(rt_scene* s, const rt_ray* rays, rt_hit* hits, size_t n)
+{
+    if (!s || (n && (!rays || !hits))) { set_error("rt_find_nearest: null argument"); return RT_ERR_INVALID; }
+    if (n == 0) return RT_OK;
+    std::lock_guard<std::mutex> lock(s->scratch_mutex);
+    RT_CUDA(cudaSetDevice(s->device));
+    rt_status st = ensure_scratch(s, n * sizeof(rt_ray), n * sizeof(rt_hit));
+    if (st != RT_OK) return st;
+    RT_CUDA(cudaMemcpyAsync(s->scratch_in, rays, n * sizeof(rt_ray), cudaMemcpyHostToDevice, s->stream));
+    st = rt_find_nearest_device(s, (const rt_ray*)s->scratch_in, (rt_hit*)s->scratch_out, n, s->stream);
+    if (st != RT_OK) return st;
+    RT_CUDA(cudaMemcpyAsync(hits, s->scratch_out, n * sizeof(rt_hit), cudaMemcpyDeviceToHost, s->stream));
+    RT_CUDA(cudaStreamSynchronize(s->stream));
+    return RT_OK;
+}
+
+rt_status rt_is_occluded(rt_scene* s, const rt_ray* rays, uint8_t* occluded, size_t n)
+{
+    if (!s || (n && (!rays || !occluded))) { set_error("rt_is_occluded: null argument"); return RT_ERR_INVALID; }
+    if (n == 0) return RT_OK;
+    std::lock_guard<std::mutex> lock(s->scratch_mutex);
+    RT_CUDA(cudaSetDevice(s->device));
+    rt_status st = ensure_scratch(s, n * sizeof(rt_ray), n);
+    if (st != RT_OK) return st;
+    RT_CUDA(cudaMemcpyAsync(s->scratch_in, rays, n * sizeof(rt_ray), cudaMemcpyHostToDevice, s->stream));
+    st = rt_is_occluded_device(s, (const rt_ray*)s->scratch_in, (uint8_t*)s->scratch_out, n, s->stream);
+    if (st != RT_OK) return st;
+    RT_CUDA(cudaMemcpyAsync(occluded, s->scratch_out, n, cudaMemcpyDeviceToHost, s->stream));
+    RT_CUDA(cudaStreamSynchronize(s->stream));
+    return RT_OK;
+}
+
+// Camera::Camera() camera.h:12-21
+void rt_camera_default(rt_camera* c, int width, int height)
+{
+    const float aspect = (float)width / (float)height;
+    c->pos[0] = 0, c->pos[1] = 0, c->pos[2] = -2;
+    c->top_left[0] = -aspect, c->top_left[1] = 1, c->top_left[2] = 0;
+    c->top_right[0] = aspect, c->top_right[1] = 1, c->top_right[2] = 0;
+    c->bottom_left[0] = -aspect, c->bottom_left[1] = -1, c->bottom_left[2] = 0;
+}
+
+namespace {
+struct H3 { float x, y, z; };
+inline H3 hsub(H3 a, H3 b) { return { a.x - b.x, a.y - b.y, a.z - b.z }; }
+inline H3 hadd(H3 a, H3 b) { return { a.x + b.x, a.y + b.y, a.z + b.z }; }
+inline H3 hmul(float s, H3 a) { return { s * a.x, s * a.y, s * a.z }; }
+inline float hdot(H3 a, H3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline H3 hcross(H3 a, H3 b) { return { a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x }; }
+inline H3 hnorm(H3 v) { const float inv = 1.0f / sqrtf(hdot(v, v)); return { v.x * inv, v.y * inv, v.z * inv }; }
+}
+
+// Camera::SetCameraState camera.h:61-73
+void rt_camera_look_at(rt_camera* c, const float pos[3], const float target[3], int width, int height)
+{
+    const float aspect = (float)width / (float)height;
+    const H3 camPos = { pos[0], pos[1], pos[2] }, camTarget = { target[0], target[1], target[2] };
+    const H3 ahead = hnorm(hsub(camTarget, camPos));
+    const H3 tmpUp = { 0, 1, 0 };
+    H3 right = hnorm(hcross(tmpUp, ahead));
+    const H3 up = hnorm(hcross(ahead, right));
+    right = hnorm(hcross(up, ahead));
+    const H3 base = hadd(camPos, hmul(2, ahead));
+    const H3 tl = hadd(hsub(base, hmul(aspect, right)), up);
+    const H3 tr = hadd(hadd(base, hmul(aspect, right)), up);
+    const H3 bl = hsub(hsub(base, hmul(aspect, right)), up);
+    c->pos[0] = camPos.x, c->pos[1] = camPos.y, c->pos[2] = camPos.z;
+    c->top_left[0] = tl.x, c->top_left[1] = tl.y, c->top_left[2] = tl.z;
+    c->top_right[0] = tr.x, c->top_right[1] = tr.y, c->top_right[2] = tr.z;
+    c->bottom_left[0] = bl.x, c->bottom_left[1] = bl.y, c->bottom_left[2] = bl.z;
+}
+
+} // extern "C"

@@ -94,6 +94,16 @@ def main():
         p = os.path.join(assets, "textures", fn)
         if not os.path.exists(p):
             write_standin_png(p, seed=1234 + i, base=[(0.5, 0.36, 0.22), (0.6, 0.6, 0.62), (0.35, 0.45, 0.4)][i])
+    # tiny asset set for the committed golden fixture (tests/golden): small textures keep the flattened
+    # scene at a few hundred KB
+    gold = os.path.join(assets, "golden")
+    os.makedirs(gold, exist_ok=True)
+    if not os.path.exists(os.path.join(gold, "sky_small.hdr")):
+        write_standin_hdr(os.path.join(gold, "sky_small.hdr"), w=256, h=128)
+    for i, fn in enumerate(["floor_small.png", "tex_small.png"]):
+        if not os.path.exists(os.path.join(gold, fn)):
+            write_standin_png(os.path.join(gold, fn), seed=77 + i, size=128 if i else 200,
+                              base=[(0.5, 0.5, 0.55), (0.7, 0.45, 0.3)][i])
     return WORK
 
 

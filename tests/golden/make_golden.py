@@ -1,0 +1,74 @@
+#!/usr/bin/env python3
+"""Generate the committed golden vectors from the REFERENCE'S OWN CODE (oracle/_ref, built headless).
+
+Run here (where /root/reference is mounted):   python tests/golden/make_golden.py
+Outputs, per scene kind k in {file, tlas} (FileScene+USE_BVH / TLASFileScene+TLAS_USE_BVH):
+  tests/golden/golden_<k>.rtscene.gz   the reference's flattened scene (inputs)
+  tests/golden/golden_<k>.npz          what the reference computed on it:
+      cam_*            two cameras (default, look-at) as 4x3 (camPos, topLeft, topRight, bottomLeft)
+      prim<c>_*        FindNearest over every primary ray of camera c: t,u,v,obj,tri,traversed,tested
+      shadow_rays / shadow_occluded    IsOccluded over shadow rays from camera-0 hit points
+      info_N / info_uv / info_albedo   GetHitInfo + GetAlbedo / GetSkyColor for camera-0 primary hits
+      whitted<c>       Whitted accumulator (Renderer::Tick once)
+      pt<c>            path-tracer accumulator after FRAMES Ticks from spp = 1
+The scene (scenes/golden_scene.xml) uses tiny generated textures so the fixtures stay small.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+W, H, FRAMES = 128, 80, 3
+LOOK_AT = ((1.6, 0.9, -1.4), (0.0, -0.4, 1.0))
+
+
+def main():
+    from oracle.refhost import RefRenderer
+    import cpu_ray_tracer_b200 as rtb
+    from cpu_ray_tracer_b200 import api
+
+    for kind in ("file", "tlas"):
+        out = {}
+        wh = RefRenderer("whitted", kind, "golden_scene.xml", W, H)
+        pt = RefRenderer("pt", kind, "golden_scene.xml", W, H)
+        scene_path = os.path.join(HERE, f"golden_{kind}.rtscene")
+        pt.flatten(scene_path)
+        fs = rtb.FlatScene.load(scene_path)
+        fs.save(scene_path + ".gz")
+        os.remove(scene_path)
+        for c in (0, 1):
+            if c == 1:
+                wh.set_camera(*LOOK_AT)
+                pt.set_camera(*LOOK_AT)
+            out[f"cam{c}"] = pt.get_camera()
+            prim = pt.primary_hits()
+            for k in ("t", "u", "v", "obj", "tri", "traversed", "tested"):
+                out[f"prim{c}_{k}"] = prim[k]
+            if c == 0:
+                I = prim["O"] + prim["t"][:, None] * prim["D"]
+                m = prim["obj"] >= 0
+                L = fs.header["light_pos"][0][None, :] - I[m]
+                dist = np.sqrt((L * L).sum(1)).astype(np.float32)
+                L = (L / dist[:, None]).astype(np.float32)
+                sr = api.make_rays(I[m] + L * np.float32(0.001), L, dist - np.float32(0.002))
+                out["shadow_rays"] = sr
+                out["shadow_occluded"] = pt.is_occluded(sr["O"].copy(), sr["D"].copy(), sr["tmax"].copy())
+                N, uv, alb = pt.hit_info(prim["O"], prim["D"], prim)
+                out["info_N"], out["info_uv"], out["info_albedo"] = N, uv, alb
+            wh.tick(1)
+            out[f"whitted{c}"] = wh.accumulator()
+            pt.reset(1)
+            pt.tick(FRAMES)
+            out[f"pt{c}"] = pt.accumulator()
+        out["meta"] = np.array([W, H, FRAMES], np.int32)
+        out["look_at"] = np.array(LOOK_AT, np.float32)
+        np.savez_compressed(os.path.join(HERE, f"golden_{kind}.npz"), **out)
+        print(kind, "tris", fs.triangle_count, "hit fraction", float((out["prim0_obj"] >= 0).mean()))
+
+
+if __name__ == "__main__":
+    main()
