@@ -57,6 +57,12 @@ class rt_counters(C.Structure):
                 ("wavefront_iterations", C.c_uint64), ("kernel_launches", C.c_uint64)]
 
 
+class rt_stage_times(C.Structure):
+    _fields_ = [("ms", C.c_double * 4), ("launches", C.c_uint64 * 4)]
+
+
+STAGES = ("generate", "extend", "shade", "connect")
+
 # numpy record layouts of the POD arrays (same bytes as the reference's structs)
 NODE_DTYPE = np.dtype([("aabb_min", "<f4", 3), ("aabb_max", "<f4", 3), ("left_first", "<u4"), ("tri_count", "<u4")])
 TRI_DTYPE = np.dtype([("v0", "<f4", 3), ("v1", "<f4", 3), ("v2", "<f4", 3),

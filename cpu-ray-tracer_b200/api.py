@@ -30,6 +30,7 @@ EXPORTS = [
     "rt_renderer_set_camera", "rt_renderer_clear", "rt_renderer_render", "rt_renderer_sync",
     "rt_renderer_read_accumulator", "rt_renderer_read_pixels", "rt_renderer_device_accumulator",
     "rt_renderer_get_counters", "rt_renderer_reset_counters",
+    "rt_renderer_set_profiling", "rt_renderer_get_stage_times",
 ]
 
 
@@ -81,6 +82,8 @@ def lib():
     L.rt_renderer_device_accumulator.restype = vp
     L.rt_renderer_get_counters.argtypes = [vp, C.POINTER(abi.rt_counters)]
     L.rt_renderer_reset_counters.argtypes = [vp]
+    L.rt_renderer_set_profiling.argtypes = [vp, i32]
+    L.rt_renderer_get_stage_times.argtypes = [vp, C.POINTER(abi.rt_stage_times)]
     _lib = L
     return L
 
@@ -298,3 +301,14 @@ class GpuRenderer:
     def reset_counters(self):
         self._need()
         _check(lib().rt_renderer_reset_counters(self.handle))
+
+    def set_profiling(self, on):
+        self._need()
+        _check(lib().rt_renderer_set_profiling(self.handle, 1 if on else 0))
+
+    def stage_times(self):
+        """{stage: (device ms, launches)} since the last call (needs set_profiling(True))"""
+        self._need()
+        t = abi.rt_stage_times()
+        _check(lib().rt_renderer_get_stage_times(self.handle, C.byref(t)))
+        return {name: (float(t.ms[i]), int(t.launches[i])) for i, name in enumerate(abi.STAGES)}

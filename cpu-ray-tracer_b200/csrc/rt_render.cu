@@ -487,6 +487,38 @@ struct rt_renderer {
     uint64_t paths = 0, launches = 0;
     uint32_t* dPixels = nullptr;
     bool overflowed = false;
+    // per-stage profiling (rt_renderer_set_profiling)
+    bool profiling = false;
+    std::vector<cudaEvent_t> evPool;
+    size_t evUsed = 0;
+    struct Span { int stage; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    cudaEvent_t openEvent = nullptr;
+
+    void prof_begin()
+    {
+        if (!profiling) return;
+        openEvent = next_event();
+        cudaEventRecord(openEvent, stream);
+    }
+    void prof_end(int stage)
+    {
+        launches++;
+        if (!profiling) return;
+        cudaEvent_t b = next_event();
+        cudaEventRecord(b, stream);
+        spans.push_back({ stage, openEvent, b });
+    }
+    cudaEvent_t next_event()
+    {
+        if (evUsed == evPool.size())
+        {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            evPool.push_back(e);
+        }
+        return evPool[evUsed++];
+    }
 };
 
 template <class T>
@@ -588,6 +620,7 @@ void rt_renderer_destroy(rt_renderer* r)
     cudaSetDevice(r->scene->device);
     if (r->stream) cudaStreamSynchronize(r->stream);
     for (void* p : r->allocations) cudaFree(p);
+    for (cudaEvent_t e : r->evPool) cudaEventDestroy(e);
     if (r->hCount) cudaFreeHost(r->hCount);
     if (r->ownStream) cudaStreamDestroy(r->ownStream);
     delete r;
@@ -666,14 +699,18 @@ static rt_status render_pt(rt_renderer* r, int first_spp, int count, int stride)
         const int frames = count - done < inFlight ? count - done : inFlight;
         p.slots = nTiles * frames;
         p.firstSpp = first_spp + done * stride;
+        r->prof_begin();
         k_pt_generate<<<r->sms * 4, 256, 0, r->stream>>>(p, r->cam);
-        r->launches++;
+        r->prof_end(RT_STAGE_GENERATE);
         int cur = 0;
         for (int it = 0; it < maxIters; it++)
         {
+            r->prof_begin();
             k_pt_extend<<<grid, 128, 0, r->stream>>>(p, r->scene->d, cur);
+            r->prof_end(RT_STAGE_EXTEND);
+            r->prof_begin();
             k_pt_shade<<<grid, 128, 0, r->stream>>>(p, r->scene->d, r->cam, cur);
-            r->launches += 2;
+            r->prof_end(RT_STAGE_SHADE);
             cur ^= 1;
             if ((it & 31) == 31)
             {
@@ -696,16 +733,22 @@ static rt_status render_whitted(rt_renderer* r)
     const size_t px = (size_t)P.width * P.height;
     // Tick overwrites the accumulator every frame (renderer.cpp:155)
     RT_CUDA(cudaMemsetAsync(r->accum, 0, px * 16, r->stream));
+    r->prof_begin();
     k_wh_generate<<<r->sms * 4, 256, 0, r->stream>>>(w, r->cam);
-    r->launches++;
+    r->prof_end(RT_STAGE_GENERATE);
     const int grid = r->sms * 8;
     int cur = 0;
     for (int depth = 0; depth <= P.depth_limit; depth++)
     {
+        r->prof_begin();
         k_wh_extend<<<grid, 128, 0, r->stream>>>(w, r->scene->d, cur);
+        r->prof_end(RT_STAGE_EXTEND);
+        r->prof_begin();
         k_wh_shade<<<grid, 128, 0, r->stream>>>(w, r->scene->d, cur);
+        r->prof_end(RT_STAGE_SHADE);
+        r->prof_begin();
         k_wh_connect<<<grid, 128, 0, r->stream>>>(w, r->scene->d);
-        r->launches += 3;
+        r->prof_end(RT_STAGE_CONNECT);
         cur ^= 1;
     }
     r->paths += px;
@@ -766,6 +809,32 @@ rt_status rt_renderer_get_counters(rt_renderer* r, rt_counters* out)
     RT_CUDA(cudaMemcpy(c, r->dCounters, sizeof c, cudaMemcpyDeviceToHost));
     out->extension_rays = c[0], out->shadow_rays = c[1], out->wavefront_iterations = c[2];
     out->paths = r->paths, out->kernel_launches = r->launches;
+    return RT_OK;
+}
+
+rt_status rt_renderer_set_profiling(rt_renderer* r, int enabled)
+{
+    if (!r) return RT_ERR_INVALID;
+    rt_status st = rt_renderer_sync(r);
+    if (st != RT_OK) return st;
+    r->profiling = enabled != 0;
+    r->spans.clear(), r->evUsed = 0;
+    return RT_OK;
+}
+
+rt_status rt_renderer_get_stage_times(rt_renderer* r, rt_stage_times* out)
+{
+    if (!r || !out) return RT_ERR_INVALID;
+    rt_status st = rt_renderer_sync(r);
+    if (st != RT_OK) return st;
+    memset(out, 0, sizeof *out);
+    for (const rt_renderer::Span& sp : r->spans)
+    {
+        float ms = 0;
+        RT_CUDA(cudaEventElapsedTime(&ms, sp.a, sp.b));
+        out->ms[sp.stage] += ms, out->launches[sp.stage]++;
+    }
+    r->spans.clear(), r->evUsed = 0;
     return RT_OK;
 }
 

@@ -238,6 +238,19 @@ void* rt_renderer_device_accumulator(rt_renderer* r);
 rt_status rt_renderer_get_counters(rt_renderer* r, rt_counters* out);
 rt_status rt_renderer_reset_counters(rt_renderer* r);
 
+/* Per-stage device time (the reference's own instrumentation is a Timer around the pixel loop,
+ * template/precomp.h:146-157, and per-ray traversed/tested counters).  With profiling enabled every
+ * kernel launch is bracketed by CUDA events on the renderer's stream; rt_renderer_get_stage_times
+ * synchronises, sums the spans per stage, returns them and resets.  Costs ~2 event records per launch,
+ * so throughput numbers are taken with profiling off. */
+enum { RT_STAGE_GENERATE = 0, RT_STAGE_EXTEND = 1, RT_STAGE_SHADE = 2, RT_STAGE_CONNECT = 3, RT_STAGE_COUNT = 4 };
+typedef struct rt_stage_times {
+    double ms[RT_STAGE_COUNT];
+    uint64_t launches[RT_STAGE_COUNT];
+} rt_stage_times;
+rt_status rt_renderer_set_profiling(rt_renderer* r, int enabled);
+rt_status rt_renderer_get_stage_times(rt_renderer* r, rt_stage_times* out);
+
 #ifdef __cplusplus
 }
 #endif

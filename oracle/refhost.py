@@ -153,6 +153,27 @@ def _main(argv):
         secs = r.tick(frames)
         np.savez_compressed(out, accumulator=r.accumulator(), camera=r.get_camera(), seconds=secs,
                             threads=r.threads(), **{"prim_" + k: v for k, v in prim.items()})
+    elif cmd == "bench":
+        # one warm-up frame, then `frames` timed frames (Renderer::Tick), JSON on stdout
+        import json
+        integrator, kind, scene, W, H, frames = argv[1], argv[2], argv[3], int(argv[4]), int(argv[5]), int(argv[6])
+        fast = len(argv) > 7 and argv[7] == "1"
+        r = RefRenderer(integrator, kind, scene, W, H, fast=fast)
+        r.tick(1)
+        secs = r.tick(frames)
+        print(json.dumps({"seconds": secs, "threads": r.threads(), "frames": frames, "fast": fast}))
+    elif cmd == "bench_steps":
+        # warmup x frames untimed, then steps x frames timed; JSON on stdout
+        import json
+        integrator, kind, scene, W, H, frames, warmup, steps = argv[1], argv[2], argv[3], int(argv[4]), int(argv[5]), int(argv[6]), int(argv[7]), int(argv[8])
+        r = RefRenderer(integrator, kind, scene, W, H)
+        for _ in range(warmup):
+            r.tick(frames)
+        secs = 0.0
+        for _ in range(steps):
+            secs += r.tick(frames)
+        print(json.dumps({"seconds": secs, "threads": r.threads(), "frames": frames,
+                          "flags": "reference Renderer::Tick built headless with g++ -O2 -fopenmp -ffp-contract=off"}))
     elif cmd == "flatten":
         integrator, kind, scene, out = argv[1], argv[2], argv[3], os.path.abspath(argv[4])
         r = RefRenderer(integrator, kind, scene, 64, 64)

@@ -1,0 +1,311 @@
+"""Parity of the CUDA path against the oracle, through the C-ABI (run on the B200 box: pytest -m gpu).
+
+Bars (BASELINE.json north_star):
+  * hits (t, u, v, objIdx, triIdx) and the traversed/tested work counters: BIT-EXACT for every ray,
+    including rays with zero direction components (NaN slab semantics) — no documented ties needed;
+  * IsOccluded: equal booleans;
+  * Whitted radiance: max abs error <= WHITTED_TOL (top-down weights reassociate a few products);
+  * path tracer at equal spp with the reference's RNG: identical ray counts (same path decisions);
+    radiance equal up to libm ulps: per-pixel |diff| <= PT_TOL except sky-texel flips (CUDA's
+    atan2f/acosf differ from glibc's by <= 2 ulp; a lookup that lands on a texel border can pick the
+    neighbour), bounded by PT_FLIP_FRACTION of the pixels; RMSE / PSNR stated in the test.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, all_scene_names, biteq, random_rays, shadow_rays_from
+
+from cpu_ray_tracer_b200 import abi
+
+pytestmark = pytest.mark.gpu
+
+WHITTED_TOL = 2e-5        # absolute, radiance values reach 24
+PT_TOL = 1e-4             # absolute per channel, accumulated over the frames rendered
+PT_FLIP_FRACTION = 2e-4   # pixels allowed to differ by more (texel flips)
+PT_RMSE = 2e-3
+HIT_FIELDS = ("t", "u", "v", "obj_idx", "tri_idx", "traversed", "tested")
+
+SCENES = all_scene_names()
+
+
+def assert_hits_equal(ours, theirs, what):
+    for f in HIT_FIELDS:
+        a, b = ours[f], theirs[f]
+        assert biteq(a, b), f"{what}: {f} differs on {(a.view(np.uint32) != b.view(np.uint32)).sum()} of {len(a)} rays"
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_find_nearest_primary_bit_exact(name, oracles, gpu_scenes):
+    po, sc = oracles(name), gpu_scenes(name)
+    W, H = 320, 192
+    for cam in (po.camera_default(W, H), po.camera_look_at((1.6, 0.9, -1.4), (0.0, -0.4, 1.0), W, H)):
+        rays = po.primary_rays(cam, W, H)
+        ref, _ = po.find_nearest(rays)
+        got = sc.FindNearest(rays)
+        assert (ref["obj_idx"] >= 2).any()
+        assert_hits_equal(got, ref, name)
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_find_nearest_incoherent_and_degenerate_rays(name, oracles, gpu_scenes, flat_scenes):
+    """random rays, axis-aligned rays (rD = inf) and origins on node-box planes (0 * inf = NaN)"""
+    po, sc = oracles(name), gpu_scenes(name)
+    rays = random_rays(flat_scenes(name), 40000, seed=7)
+    ref, _ = po.find_nearest(rays)
+    assert_hits_equal(sc.FindNearest(rays), ref, name)
+    # bounded rays: Ray::t on entry limits every primitive and the BVH cull
+    rays["tmax"] = np.random.default_rng(3).uniform(0.05, 6.0, len(rays)).astype(np.float32)
+    ref, _ = po.find_nearest(rays)
+    assert_hits_equal(sc.FindNearest(rays), ref, name + " (bounded)")
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_secondary_rays_and_occlusion(name, oracles, gpu_scenes, flat_scenes):
+    po, sc = oracles(name), gpu_scenes(name)
+    W, H = 256, 160
+    rays = po.primary_rays(po.camera_default(W, H), W, H)
+    hits, _ = po.find_nearest(rays)
+    sr = shadow_rays_from(flat_scenes(name), rays, hits)
+    ref, _ = po.is_occluded(sr)
+    got = sc.IsOccluded(sr)
+    assert np.array_equal(got, ref)
+    # the same rays as closest-hit queries (incoherent secondary rays leaving surfaces)
+    sr2 = sr.copy()
+    sr2["tmax"] = 1e34
+    ref2, _ = po.find_nearest(sr2)
+    assert_hits_equal(sc.FindNearest(sr2), ref2, name + " (secondary)")
+
+
+def test_edge_cases_empty_ragged_single(oracles, gpu_scenes, flat_scenes):
+    name = "golden_tlas"
+    po, sc = oracles(name), gpu_scenes(name)
+    assert len(sc.FindNearest(np.zeros(0, abi.RAY_DTYPE))) == 0
+    assert len(sc.IsOccluded(np.zeros(0, abi.RAY_DTYPE))) == 0
+    rays = random_rays(flat_scenes(name), 4099, seed=11)  # prime length: ragged last warp / CTA
+    for n in (1, 31, 33, 127, 129, 4099):
+        ref, _ = po.find_nearest(rays[:n])
+        assert_hits_equal(sc.FindNearest(rays[:n]), ref, f"n={n}")
+        occ, _ = po.is_occluded(rays[:n])
+        assert np.array_equal(sc.IsOccluded(rays[:n]), occ)
+    # rays that can hit nothing: straight up from above everything
+    up = rays[:64].copy()
+    up["O"][:, 1] = 50.0
+    up["D"] = np.array([0, 1, 0], np.float32)
+    got = sc.FindNearest(up)
+    assert (got["obj_idx"] == -1).all() and (got["tri_idx"] == -1).all() and biteq(got["t"], up["tmax"])
+
+
+def test_error_behaviour(flat_scenes):
+    import ctypes as C
+    from cpu_ray_tracer_b200 import api
+    L = api.lib()
+    h = C.c_void_p()
+    assert L.rt_scene_create(None, 0, 0, C.byref(h)) == abi.RT_ERR_INVALID
+    d = flat_scenes("golden_file").desc()
+    d.kind = 7
+    assert L.rt_scene_create(C.byref(d), 0, 0, C.byref(h)) == abi.RT_ERR_INVALID
+    d = flat_scenes("golden_file").desc()
+    assert L.rt_scene_create(C.byref(d), 99, 0, C.byref(h)) == abi.RT_ERR_NO_DEVICE
+    assert b"no such CUDA device" in L.rt_last_error()
+    d = flat_scenes("golden_tlas").desc()
+    d.kind = abi.RT_SCENE_FLAT  # a flat scene with several BVHs is rejected
+    assert L.rt_scene_create(C.byref(d), 0, 0, C.byref(h)) == abi.RT_ERR_INVALID
+    assert L.rt_find_nearest(None, None, None, 4) == abi.RT_ERR_INVALID
+
+
+def test_device_pointer_entry_points(oracles, gpu_scenes, flat_scenes):
+    """rt_find_nearest_device / rt_is_occluded_device on buffers owned by torch"""
+    import torch
+    name = "golden_file"
+    po, sc = oracles(name), gpu_scenes(name)
+    rays = random_rays(flat_scenes(name), 10000, seed=5)
+    ref, _ = po.find_nearest(rays)
+    d_rays = torch.from_numpy(rays.view(np.uint8).reshape(-1, 32)).cuda()
+    d_hits = torch.empty((len(rays), 32), dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    sc.FindNearestDevice(d_rays.data_ptr(), d_hits.data_ptr(), len(rays), stream)
+    got = d_hits.cpu().numpy().reshape(-1).view(abi.HIT_DTYPE)
+    assert_hits_equal(got, ref, "device pointers")
+    d_occ = torch.empty(len(rays), dtype=torch.uint8, device="cuda")
+    sc.IsOccludedDevice(d_rays.data_ptr(), d_occ.data_ptr(), len(rays), stream)
+    occ, _ = po.is_occluded(rays)
+    assert np.array_equal(d_occ.cpu().numpy(), occ)
+
+
+# ------------------------------------------------------------------------------------------------
+# integrators
+# ------------------------------------------------------------------------------------------------
+def psnr(a, b, peak):
+    mse = float(np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2))
+    return np.inf if mse == 0 else 10 * np.log10(peak * peak / mse)
+
+
+def check_pt(gacc, oacc, frames, what):
+    d = np.abs(gacc[..., :3].astype(np.float64) - oacc[..., :3])
+    assert not np.isnan(gacc).any() or np.isnan(oacc).any()
+    d = np.nan_to_num(d)
+    worst = d.max(-1)
+    flips = int((worst > PT_TOL * frames).sum())
+    assert flips <= max(2, PT_FLIP_FRACTION * worst.size * frames), f"{what}: {flips} pixels differ by more than {PT_TOL * frames}"
+    rmse = float(np.sqrt((d ** 2).mean()))
+    assert rmse < PT_RMSE, f"{what}: RMSE {rmse}"
+    assert psnr(np.nan_to_num(gacc[..., :3]), np.nan_to_num(oacc[..., :3]), 24.0 * frames) > 70.0
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_whitted_vs_oracle(name, oracles, gpu_scenes):
+    from cpu_ray_tracer_b200 import api
+    from oracle import porthost
+    po, sc = oracles(name), gpu_scenes(name, counters=False)
+    W, H = 320, 192
+    cam = po.camera_default(W, H)
+    oacc, ost = po.render_whitted(cam, porthost.default_params(abi.RT_INTEGRATOR_WHITTED, W, H))
+    r = api.GpuRenderer(sc, abi.RT_INTEGRATOR_WHITTED, W, H).Init()
+    r.Tick(0)
+    gacc = r.accumulator
+    c = r.counters()
+    assert c["extension_rays"] == ost["extension_rays"] and c["shadow_rays"] == ost["shadow_rays"]
+    d = np.nan_to_num(np.abs(gacc - oacc))
+    assert d.max() <= WHITTED_TOL, f"{name}: max abs error {d.max()}"
+    same = (gacc.view(np.uint32) == oacc.view(np.uint32)).mean()
+    assert same > 0.9, f"{name}: only {same:.3f} of the floats are bit-identical"
+    # Tick overwrites (renderer.cpp:155): a second frame gives the same image, not twice the image
+    r.Tick(0)
+    assert np.nan_to_num(np.abs(r.accumulator - oacc)).max() <= WHITTED_TOL
+    # screen->pixels through RGBF32_to_RGB8
+    px, opx = r.screen_pixels(), po.to_rgb8(oacc, 1.0)
+    chan = lambda p: np.stack([(p >> 16) & 255, (p >> 8) & 255, p & 255], -1).astype(np.int32)
+    assert np.abs(chan(px) - chan(opx)).max() <= 1
+    r.close()
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_path_tracer_vs_oracle_reference_rng(name, oracles, gpu_scenes):
+    from cpu_ray_tracer_b200 import api
+    from oracle import porthost
+    po, sc = oracles(name), gpu_scenes(name, counters=False)
+    W, H, frames = 320, 192, 3
+    cam = po.camera_default(W, H)
+    oacc, ost = po.render_pt(cam, porthost.default_params(abi.RT_INTEGRATOR_PATH, W, H), 1, frames, 1)
+    r = api.GpuRenderer(sc, abi.RT_INTEGRATOR_PATH, W, H).Init()
+    for _ in range(frames):
+        r.Tick(0)  # one Renderer::Tick per call, spp advances 1, 2, 3
+    assert r.spp == 1 + frames
+    gacc = r.accumulator
+    c = r.counters()
+    # same RNG streams + bit-exact hits => every path takes the same decisions => same number of rays
+    assert c["extension_rays"] == ost["extension_rays"], (c, ost)
+    assert c["paths"] == ost["paths"] == W * H * frames
+    check_pt(gacc, oacc, frames, name)
+    # the same frames in ONE call (all (tile, frame) streams in flight together)
+    r.ClearAccumulator()
+    r.reset_counters()
+    r.render(frames, first_spp=1)
+    assert r.counters()["extension_rays"] == ost["extension_rays"]
+    check_pt(r.accumulator, oacc, frames, name + " (batched)")
+    r.close()
+
+
+@pytest.mark.parametrize("kind", ["file", "tlas"])
+def test_integrators_vs_committed_golden(kind, oracles, gpu_scenes):
+    """the vectors the reference's own build produced (tests/golden/make_golden.py), second camera too"""
+    from cpu_ray_tracer_b200 import api
+    g = np.load(os.path.join(GOLDEN, f"golden_{kind}.npz"))
+    W, H, frames = (int(x) for x in g["meta"])
+    sc = gpu_scenes(f"golden_{kind}", counters=False)
+    for c in (0, 1):
+        wh = api.GpuRenderer(sc, abi.RT_INTEGRATOR_WHITTED, W, H).Init()
+        pt = api.GpuRenderer(sc, abi.RT_INTEGRATOR_PATH, W, H).Init()
+        if c == 1:
+            wh.camera.SetCameraState(g["look_at"][0], g["look_at"][1])
+            pt.camera.SetCameraState(g["look_at"][0], g["look_at"][1])
+        wh.Tick(0)
+        assert np.nan_to_num(np.abs(wh.accumulator - g[f"whitted{c}"])).max() <= WHITTED_TOL
+        pt.render(frames)
+        check_pt(pt.accumulator, g[f"pt{c}"], frames, f"golden {kind} cam{c}")
+        wh.close(), pt.close()
+
+
+def test_path_tracer_per_pixel_seed_mode(oracles, gpu_scenes):
+    from cpu_ray_tracer_b200 import api
+    from oracle import porthost
+    name = "golden_file"
+    po, sc = oracles(name), gpu_scenes(name, counters=False)
+    W, H, frames = 128, 80, 2
+    cam = po.camera_default(W, H)
+    oacc, ost = po.render_pt(cam, porthost.default_params(abi.RT_INTEGRATOR_PATH, W, H, seed_mode=abi.RT_SEED_PER_PIXEL), 1, frames, 1)
+    r = api.GpuRenderer(sc, abi.RT_INTEGRATOR_PATH, W, H, seed_mode=abi.RT_SEED_PER_PIXEL).Init()
+    r.render(frames)
+    assert r.counters()["extension_rays"] == ost["extension_rays"]
+    check_pt(r.accumulator, oacc, frames, "per-pixel seeds")
+    r.close()
+
+
+def test_depth_limit_and_partial_tiles(oracles, gpu_scenes):
+    """depthLimit other than 5; a height that is not a multiple of 16 renders only whole tiles"""
+    from cpu_ray_tracer_b200 import api
+    from oracle import porthost
+    name = "golden_tlas"
+    po, sc = oracles(name), gpu_scenes(name, counters=False)
+    W, H = 144, 90  # 9 x 5 tiles, bottom 10 rows never rendered by the path tracer
+    cam = po.camera_default(W, H)
+    for depth in (0, 1, 3):
+        oacc, ost = po.render_pt(cam, porthost.default_params(abi.RT_INTEGRATOR_PATH, W, H, depth_limit=depth), 1, 2, 1)
+        r = api.GpuRenderer(sc, abi.RT_INTEGRATOR_PATH, W, H, depthLimit=depth).Init()
+        r.render(2)
+        assert r.counters()["extension_rays"] == ost["extension_rays"]
+        gacc = r.accumulator
+        check_pt(gacc, oacc, 2, f"depth {depth}")
+        assert (gacc[80:] == 0).all() and (oacc[80:] == 0).all()
+        r.close()
+        ow, _ = po.render_whitted(cam, porthost.default_params(abi.RT_INTEGRATOR_WHITTED, W, H, depth_limit=depth))
+        r = api.GpuRenderer(sc, abi.RT_INTEGRATOR_WHITTED, W, H, depthLimit=depth).Init()
+        r.Tick(0)
+        assert np.nan_to_num(np.abs(r.accumulator - ow)).max() <= WHITTED_TOL
+        r.close()
+
+
+def test_sharding_properties_full_size(gpu_scenes, oracles):
+    """BASELINE size (1920x1080): size-independent properties the multi-GPU split relies on.
+       frames:  render(spp 1..4) == render(1,3) + render(2,4)      (sample-index sharding, stride 2)
+       tiles:   render(all tiles) == render(first half) + render(second half)   (tile sharding)
+       rays:    the ray count is a deterministic function of (scene, camera, spp range)
+    Sums of the same samples in a different order: tolerance is float reassociation only."""
+    from cpu_ray_tracer_b200 import api
+    from conftest import baked_scenes
+    name = "wok_teapot_flat" if "wok_teapot_flat" in baked_scenes() else "golden_file"
+    sc = gpu_scenes(name, counters=False)
+    W, H = 1920, 1080
+    full = api.GpuRenderer(sc, abi.RT_INTEGRATOR_PATH, W, H).Init()
+    full.render(4, first_spp=1)
+    ref = full.accumulator
+    rays_full = full.counters()["extension_rays"]
+    assert (ref[1072:] == 0).all()  # 1080 % 16 = 8 rows never rendered
+    assert ref[:1072, :, :3].sum() > 0
+    # sample-index sharding
+    a = api.GpuRenderer(sc, abi.RT_INTEGRATOR_PATH, W, H).Init()
+    a.render(2, first_spp=1, stride=2)
+    a.render(2, first_spp=2, stride=2)
+    assert a.counters()["extension_rays"] == rays_full
+    assert np.abs(a.accumulator - ref).max() <= 1e-4
+    a.close()
+    # tile sharding
+    tiles = (W // 16) * (H // 16)
+    lo = api.GpuRenderer(sc, abi.RT_INTEGRATOR_PATH, W, H, tile_begin=0, tile_end=tiles // 2).Init()
+    hi = api.GpuRenderer(sc, abi.RT_INTEGRATOR_PATH, W, H, tile_begin=tiles // 2, tile_end=tiles).Init()
+    lo.render(4, first_spp=1), hi.render(4, first_spp=1)
+    assert lo.counters()["extension_rays"] + hi.counters()["extension_rays"] == rays_full
+    la, ha = lo.accumulator, hi.accumulator
+    assert not ((la[..., :3].sum(-1) != 0) & (ha[..., :3].sum(-1) != 0)).any()  # disjoint pixels
+    assert np.abs(la + ha - ref).max() <= 1e-4
+    lo.close(), hi.close()
+    # oracle spot check at full width on the top tile rows
+    po = oracles(name)
+    from oracle import porthost
+    p = porthost.default_params(abi.RT_INTEGRATOR_PATH, W, H)
+    p.tile_begin, p.tile_end = 0, 2 * (W // 16)
+    oacc, _ = po.render_pt(po.camera_default(W, H), p, 1, 4, 1)
+    check_pt(ref[:32], oacc[:32], 4, "1080p top rows")
+    full.close()
