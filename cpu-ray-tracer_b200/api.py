@@ -30,7 +30,8 @@ EXPORTS = [
     "rt_renderer_set_camera", "rt_renderer_clear", "rt_renderer_render", "rt_renderer_sync",
     "rt_renderer_read_accumulator", "rt_renderer_read_pixels", "rt_renderer_device_accumulator",
     "rt_renderer_get_counters", "rt_renderer_reset_counters",
-    "rt_renderer_set_profiling", "rt_renderer_get_stage_times",
+    "rt_renderer_set_profiling", "rt_renderer_get_stage_times", "rt_renderer_get_launch_spans",
+    "rt_renderer_get_queue_history",
 ]
 
 
@@ -84,6 +85,8 @@ def lib():
     L.rt_renderer_reset_counters.argtypes = [vp]
     L.rt_renderer_set_profiling.argtypes = [vp, i32]
     L.rt_renderer_get_stage_times.argtypes = [vp, C.POINTER(abi.rt_stage_times)]
+    L.rt_renderer_get_launch_spans.argtypes = [vp, vp, vp, sz, C.POINTER(sz)]
+    L.rt_renderer_get_queue_history.argtypes = [vp, vp, sz, C.POINTER(sz)]
     _lib = L
     return L
 
@@ -305,6 +308,22 @@ class GpuRenderer:
     def set_profiling(self, on):
         self._need()
         _check(lib().rt_renderer_set_profiling(self.handle, 1 if on else 0))
+
+    def launch_spans(self, capacity=1 << 16):
+        """(stage ids, ms) of every launch since profiling was switched on / last read, in launch order"""
+        self._need()
+        stage = np.zeros(capacity, np.int32)
+        ms = np.zeros(capacity, np.float32)
+        n = C.c_size_t()
+        _check(lib().rt_renderer_get_launch_spans(self.handle, stage.ctypes.data, ms.ctypes.data, capacity, C.byref(n)))
+        return stage[:n.value], ms[:n.value]
+
+    def queue_history(self, capacity=1 << 15):
+        self._need()
+        out = np.zeros(capacity, np.int32)
+        n = C.c_size_t()
+        _check(lib().rt_renderer_get_queue_history(self.handle, out.ctypes.data, capacity, C.byref(n)))
+        return out[:n.value]
 
     def stage_times(self):
         """{stage: (device ms, launches)} since the last call (needs set_profiling(True))"""

@@ -37,6 +37,8 @@ struct PTState {
     int* active[2];
     int* count;        // [2]
     unsigned long long* counters; // [0] extension rays, [1] shadow rays, [2] iterations
+    int* history;      // queued rays per iteration of the current batch
+    int iteration;
     float4* accum;
     int slots, nTiles, tilesX, tileBegin;
     int firstSpp, stride;
@@ -104,6 +106,7 @@ __global__ void __launch_bounds__(128) k_pt_extend(const PTState p, const DScene
         p.count[cur ^ 1] = 0; // the shade stage of this iteration appends here
         p.counters[0] += (unsigned long long)n;
         p.counters[2] += 1;
+        p.history[p.iteration] = n;
     }
 }
 
@@ -477,6 +480,7 @@ struct rt_renderer {
     // path tracer
     PTState pt = {};
     int ptSlotsAllocated = 0;
+    int ptIterations = 0;
     std::vector<void*> allocations;
     // whitted
     WhState wh = {};
@@ -672,6 +676,7 @@ static rt_status pt_ensure_slots(rt_renderer* r, int slots)
     if ((st = ralloc(r, &p.weights, S * 16 * levels)) != RT_OK) return st;
     if ((st = ralloc(r, &p.active[0], S * 4)) != RT_OK) return st;
     if ((st = ralloc(r, &p.active[1], S * 4)) != RT_OK) return st;
+    if (!p.history && (st = ralloc(r, &p.history, (size_t)(256 * 65 + 2) * 4)) != RT_OK) return st;
     r->ptSlotsAllocated = slots;
     return RT_OK;
 }
@@ -703,8 +708,11 @@ static rt_status render_pt(rt_renderer* r, int first_spp, int count, int stride)
         k_pt_generate<<<r->sms * 4, 256, 0, r->stream>>>(p, r->cam);
         r->prof_end(RT_STAGE_GENERATE);
         int cur = 0;
+        r->ptIterations = 0;
         for (int it = 0; it < maxIters; it++)
         {
+            p.iteration = it;
+            r->ptIterations = it + 1;
             r->prof_begin();
             k_pt_extend<<<grid, 128, 0, r->stream>>>(p, r->scene->d, cur);
             r->prof_end(RT_STAGE_EXTEND);
@@ -835,6 +843,34 @@ rt_status rt_renderer_get_stage_times(rt_renderer* r, rt_stage_times* out)
         out->ms[sp.stage] += ms, out->launches[sp.stage]++;
     }
     r->spans.clear(), r->evUsed = 0;
+    return RT_OK;
+}
+
+rt_status rt_renderer_get_launch_spans(rt_renderer* r, int32_t* stage, float* ms, size_t capacity, size_t* n)
+{
+    if (!r || !stage || !ms || !n) return RT_ERR_INVALID;
+    rt_status st = rt_renderer_sync(r);
+    if (st != RT_OK) return st;
+    size_t k = 0;
+    for (const rt_renderer::Span& sp : r->spans)
+    {
+        if (k == capacity) break;
+        RT_CUDA(cudaEventElapsedTime(&ms[k], sp.a, sp.b));
+        stage[k++] = sp.stage;
+    }
+    *n = k;
+    r->spans.clear(), r->evUsed = 0;
+    return RT_OK;
+}
+
+rt_status rt_renderer_get_queue_history(rt_renderer* r, int32_t* out, size_t capacity, size_t* n)
+{
+    if (!r || !out || !n) return RT_ERR_INVALID;
+    rt_status st = rt_renderer_sync(r);
+    if (st != RT_OK) return st;
+    size_t k = (size_t)r->ptIterations < capacity ? (size_t)r->ptIterations : capacity;
+    if (k && r->pt.history) RT_CUDA(cudaMemcpy(out, r->pt.history, k * 4, cudaMemcpyDeviceToHost));
+    *n = r->pt.history ? k : 0;
     return RT_OK;
 }
 

@@ -250,6 +250,11 @@ typedef struct rt_stage_times {
 } rt_stage_times;
 rt_status rt_renderer_set_profiling(rt_renderer* r, int enabled);
 rt_status rt_renderer_get_stage_times(rt_renderer* r, rt_stage_times* out);
+/* Same spans, one by one, in launch order (stage id + milliseconds); call INSTEAD of
+ * rt_renderer_get_stage_times (both reset).  *n receives the number written (<= capacity). */
+rt_status rt_renderer_get_launch_spans(rt_renderer* r, int32_t* stage, float* ms, size_t capacity, size_t* n);
+/* Path tracer: number of queued rays at every wavefront iteration of the last rt_renderer_render batch. */
+rt_status rt_renderer_get_queue_history(rt_renderer* r, int32_t* rays_per_iteration, size_t capacity, size_t* n);
 
 #ifdef __cplusplus
 }
