@@ -308,6 +308,163 @@ __device__ __forceinline__ bool quad_test(const DScene& s, float3 O, float3 D, f
     return false;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Persistent-warp traversal with dynamic ray replacement.
+//
+// The plain per-thread loop above leaves a warp running until its slowest ray is done: on the path
+// tracer's mixed queues ncu measured 7.3 of 32 lanes active per issued instruction (profiles/r1_v1_*).
+// Here every lane runs a small state machine (one node visit, leaf, instance entry or instance exit
+// per step) and a warp that has REFILL_LANES or more idle lanes pulls that many new rays from the
+// queue with ONE atomicAdd (ballot / popc / shfl), so lanes stay occupied while the queue lasts.
+// The per-ray visiting order is exactly the one of traverse<> (and the reference): only which ray
+// occupies which lane changes.
+//
+// Src supplies the rays and takes the results:
+//     bool load(int i, float3& O, float3& D, float& tmax)      ray i of the queue
+//     void world(int i, float3& O, float3& D)                  reload of the world-space ray (instance exit)
+//     void store(int i, const HitRec& h)
+// ------------------------------------------------------------------------------------------------
+constexpr int REFILL_LANES = 8;
+
+template <bool ANYHIT, bool COUNTERS, class Src>
+__device__ __forceinline__ void trace_queue(const DScene& s, Src& src, const int n, int* __restrict__ fetchCounter)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const float4* __restrict__ nodes = s.nodes;
+    const float4* __restrict__ tris = s.tris;
+    int stack[STACK_SIZE];
+    int sp = 0, cur = 0, rayIdx = -1, instObj = s.flat_obj_idx;
+    float3 O = f3(0, 0, 0), D = f3(0, 0, 0), rD = f3(0, 0, 0);
+    bool exact = false, has = false, queueEmpty = false;
+    HitRec hit;
+    hit.t = 0, hit.u = 0, hit.v = 0, hit.obj = -1, hit.tri = -1, hit.traversed = 0, hit.tested = 0;
+    while (true)
+    {
+        const unsigned idle = __ballot_sync(FULL, !has);
+        if (idle == FULL && queueEmpty) break;
+        if (!queueEmpty && (idle == FULL || __popc(idle) >= REFILL_LANES))
+        {
+            const int nIdle = __popc(idle);
+            const int leader = __ffs(idle) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(fetchCounter, nIdle);
+            base = __shfl_sync(FULL, base, leader);
+            if (base + nIdle >= n) queueEmpty = true;
+            if (!has)
+            {
+                const int i = base + __popc(idle & ((1u << lane) - 1));
+                float tmax;
+                if (i < n && src.load(i, O, D, tmax))
+                {
+                    rayIdx = i, has = true;
+                    // FindNearest prologue: light quad, floor plane (file_scene.cpp:172-173); IsOccluded: quad only
+                    hit.t = tmax, hit.u = 0, hit.v = 0, hit.obj = -1, hit.tri = -1, hit.traversed = 0, hit.tested = 0;
+                    float tq;
+                    bool done = false;
+                    if (ANYHIT)
+                    {
+                        if (quad_test(s, O, D, tmax, tq)) hit.obj = 0, done = true;
+                        hit.t = 1e34f;
+                    }
+                    else
+                    {
+                        if (quad_test(s, O, D, hit.t, tq)) hit.t = tq, hit.obj = 0;
+                        const float3 N = f3(s.floor_n[0], s.floor_n[1], s.floor_n[2]);
+                        const float tp = -(dot(O, N) + s.floor_d) / (dot(D, N));
+                        if (tp < hit.t && tp > 0) hit.t = tp, hit.obj = 1;
+                    }
+                    if (done) { src.store(rayIdx, hit); has = false; }
+                    else
+                    {
+                        rD = recip(D), exact = needs_exact_slab(O, D);
+                        sp = 0, cur = s.root_ref, instObj = s.flat_obj_idx;
+                    }
+                }
+            }
+            continue;
+        }
+        if (!has) continue;
+        // ---- one traversal step ----
+        bool pop = false;
+        if (cur >= 0)
+        {
+            if (COUNTERS) hit.traversed++;
+            const float4* nd = nodes + 4 * (size_t)cur;
+            const float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2);
+            const int4 n3 = __ldg((const int4*)(nd + 3));
+            float d1 = slab(O, rD, hit.t, exact, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y);
+            float d2 = slab(O, rD, hit.t, exact, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w);
+            int c1 = n3.x, c2 = n3.y;
+            if (d1 > d2) { const float tf = d1; d1 = d2; d2 = tf; const int tc = c1; c1 = c2; c2 = tc; }
+            if (d1 == 1e30f) pop = true;
+            else
+            {
+                cur = c1;
+                if (d2 != 1e30f) stack[sp++] = c2;
+            }
+        }
+        else
+        {
+            const int payload = ~cur;
+            pop = true;
+            if (payload == SENTINEL_PAYLOAD)
+            {
+                src.world(rayIdx, O, D); // blas_bvh.cpp:385-388
+                rD = recip(D), exact = needs_exact_slab(O, D);
+            }
+            else if (payload & INSTANCE_BIT)
+            {
+                if (COUNTERS) hit.traversed++, hit.tested = 0;
+                const float4* I = s.inst + 4 * (size_t)(payload & ~INSTANCE_BIT);
+                const float4 r0 = __ldg(I), r1 = __ldg(I + 1), r2 = __ldg(I + 2);
+                const int4 meta = __ldg((const int4*)(I + 3));
+                const float3 wO = O, wD = D; // in world space here: instances do not nest
+                O = f3((wO.x * r0.x + wO.y * r0.y) + (wO.z * r0.z + r0.w),
+                       (wO.x * r1.x + wO.y * r1.y) + (wO.z * r1.z + r1.w),
+                       (wO.x * r2.x + wO.y * r2.y) + (wO.z * r2.z + r2.w));
+                D = f3((wD.x * r0.x + wD.y * r0.y) + wD.z * r0.z,
+                       (wD.x * r1.x + wD.y * r1.y) + wD.z * r1.z,
+                       (wD.x * r2.x + wD.y * r2.y) + wD.z * r2.z);
+                rD = recip(D), exact = needs_exact_slab(O, D);
+                instObj = meta.y;
+                stack[sp++] = ~SENTINEL_PAYLOAD;
+                cur = meta.x;
+                pop = false;
+            }
+            else
+            {
+                if (COUNTERS) hit.traversed++;
+                int slot = payload;
+                while (true)
+                {
+                    const float4* T = tris + 3 * (size_t)slot;
+                    const float4 t0 = __ldg(T), t1 = __ldg(T + 1), t2 = __ldg(T + 2);
+                    const int tag = __float_as_int(t0.w);
+                    if (COUNTERS) hit.tested++;
+                    if (intersect_tri(O, D, f3(t0.x, t0.y, t0.z), f3(t1.x, t1.y, t1.z), f3(t2.x, t2.y, t2.z), hit.t, hit.u, hit.v))
+                    {
+                        hit.tri = tag & ~LAST_BIT;
+                        hit.obj = instObj >= 0 ? instObj : __float_as_int(t1.w);
+                        if (ANYHIT) { sp = 0; break; }
+                    }
+                    if (tag & LAST_BIT) break;
+                    slot++;
+                }
+            }
+        }
+        if (pop)
+        {
+            if (sp == 0)
+            {
+                src.store(rayIdx, hit);
+                has = false;
+            }
+            else cur = stack[--sp];
+        }
+    }
+}
+
 // BaseScene::FindNearest: file_scene.cpp:170-175 = tlas_file_scene.cpp:201-206
 template <bool COUNTERS>
 __device__ __forceinline__ void find_nearest(const DScene& s, float3 O, float3 D, float tmax, HitRec& hit)

@@ -1,6 +1,7 @@
 // rt_internal.h — host-side objects behind the opaque handles of include/rt_b200.h
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -42,4 +43,11 @@ struct rt_scene {
     void* scratch_out = nullptr;
     size_t scratch_in_bytes = 0, scratch_out_bytes = 0;
     cudaStream_t stream = nullptr;
+    // queue-fetch counters of the persistent traversal kernels: a ring, so that launches in flight on
+    // different streams do not share one
+    static constexpr int FETCH_RING = 256;
+    int* fetch_counters = nullptr;
+    std::atomic<unsigned> fetch_next{0};
+    bool persistent = true;
+    int* next_fetch_counter() { return fetch_counters + (fetch_next.fetch_add(1) % FETCH_RING); }
 };

@@ -20,6 +20,7 @@
 // refraction rays into the next queue and one shadow ray per diffuse hit into the shadow queue;
 //   connect   any-hit occlusion kernel over the shadow queue, adds the direct term when visible.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "rt_internal.h"
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(256) k_pt_generate(const PTState p, const DCam
         p.pix[slot] = 1;
         p.active[0][slot] = slot;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) p.count[0] = p.slots, p.count[1] = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.count[0] = p.slots, p.count[1] = 0, p.count[4] = 0;
 }
 
 __global__ void __launch_bounds__(128) k_pt_extend(const PTState p, const DScene s, int cur)
@@ -104,6 +105,46 @@ __global__ void __launch_bounds__(128) k_pt_extend(const PTState p, const DScene
     if (blockIdx.x == 0 && threadIdx.x == 0)
     {
         p.count[cur ^ 1] = 0; // the shade stage of this iteration appends here
+        p.counters[0] += (unsigned long long)n;
+        p.counters[2] += 1;
+        p.history[p.iteration] = n;
+    }
+}
+
+// extend, persistent-warp version (rt_device.cuh trace_queue): lanes pull rays from the compacted
+// slot queue as they free up
+struct PTSrc {
+    const PTState& p;
+    const int* __restrict__ active;
+    __device__ __forceinline__ bool load(int i, float3& O, float3& D, float& tmax) const
+    {
+        const int slot = active[i];
+        const float4 o = p.rayO[slot], d = p.rayD[slot];
+        O = f3(o.x, o.y, o.z), D = f3(d.x, d.y, d.z), tmax = 1e34f;
+        return true;
+    }
+    __device__ __forceinline__ void world(int i, float3& O, float3& D) const
+    {
+        const int slot = active[i];
+        const float4 o = p.rayO[slot], d = p.rayD[slot];
+        O = f3(o.x, o.y, o.z), D = f3(d.x, d.y, d.z);
+    }
+    __device__ __forceinline__ void store(int i, const HitRec& h) const
+    {
+        const int slot = active[i];
+        p.hit[slot] = make_float4(h.t, h.u, h.v, __int_as_float(h.obj));
+        p.hitTri[slot] = h.tri;
+    }
+};
+
+__global__ void __launch_bounds__(128) k_pt_extend_persistent(const PTState p, const DScene s, int cur)
+{
+    const int n = p.count[cur];
+    PTSrc src = { p, p.active[cur] };
+    trace_queue<false, false>(s, src, n, p.count + 4);
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        p.count[cur ^ 1] = 0;
         p.counters[0] += (unsigned long long)n;
         p.counters[2] += 1;
         p.history[p.iteration] = n;
@@ -135,6 +176,7 @@ __global__ void __launch_bounds__(128) k_pt_shade(const PTState p, const DScene 
     const int* __restrict__ active = p.active[cur];
     int* __restrict__ nextActive = p.active[cur ^ 1];
     const int lane = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.count[4] = 0; // fetch counter of the next extend launch
     for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x)
     {
         const int i = base + threadIdx.x;
@@ -276,7 +318,7 @@ __global__ void __launch_bounds__(256) k_wh_generate(const WhState p, const DCam
         p.rayD[0][i] = make_float4(D.x, D.y, D.z, __int_as_float(0));
         p.rayW[0][i] = make_float4(1, 1, 1, __int_as_float(i));
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) p.count[0] = n, p.count[1] = 0, p.count[2] = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.count[0] = n, p.count[1] = 0, p.count[2] = 0, p.count[4] = 0, p.count[5] = 0;
 }
 
 __global__ void __launch_bounds__(128) k_wh_extend(const WhState p, const DScene s, int cur)
@@ -293,6 +335,40 @@ __global__ void __launch_bounds__(128) k_wh_extend(const WhState p, const DScene
     if (blockIdx.x == 0 && threadIdx.x == 0)
     {
         p.count[cur ^ 1] = 0, p.count[2] = 0;
+        p.counters[0] += (unsigned long long)n;
+        p.counters[2] += 1;
+    }
+}
+
+struct WhSrc {
+    const WhState& p;
+    int cur;
+    __device__ __forceinline__ bool load(int i, float3& O, float3& D, float& tmax) const
+    {
+        const float4 o = p.rayO[cur][i], d = p.rayD[cur][i];
+        O = f3(o.x, o.y, o.z), D = f3(d.x, d.y, d.z), tmax = 1e34f;
+        return true;
+    }
+    __device__ __forceinline__ void world(int i, float3& O, float3& D) const
+    {
+        const float4 o = p.rayO[cur][i], d = p.rayD[cur][i];
+        O = f3(o.x, o.y, o.z), D = f3(d.x, d.y, d.z);
+    }
+    __device__ __forceinline__ void store(int i, const HitRec& h) const
+    {
+        p.hit[i] = make_float4(h.t, h.u, h.v, __int_as_float(h.obj));
+        p.hitTri[i] = h.tri;
+    }
+};
+
+__global__ void __launch_bounds__(128) k_wh_extend_persistent(const WhState p, const DScene s, int cur)
+{
+    const int n = min(p.count[cur], p.capacity);
+    WhSrc src = { p, cur };
+    trace_queue<false, false>(s, src, n, p.count + 4);
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        p.count[cur ^ 1] = 0, p.count[2] = 0, p.count[5] = 0;
         p.counters[0] += (unsigned long long)n;
         p.counters[2] += 1;
     }
@@ -328,6 +404,7 @@ __global__ void __launch_bounds__(128) k_wh_shade(const WhState p, const DScene 
 {
     const int n = min(p.count[cur], p.capacity);
     const int nxt = cur ^ 1;
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.count[4] = 0; // fetch counter of the next extend launch
     for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x)
     {
         const int i = base + threadIdx.x;
@@ -451,6 +528,40 @@ __global__ void __launch_bounds__(128) k_wh_connect(const WhState p, const DScen
     if (blockIdx.x == 0 && threadIdx.x == 0) p.counters[1] += (unsigned long long)n;
 }
 
+// connect, persistent-warp version: the shadow queue through trace_queue<ANYHIT>
+struct ShadowSrc {
+    const WhState& p;
+    __device__ __forceinline__ bool load(int i, float3& O, float3& D, float& tmax) const
+    {
+        const float4* e = p.shadow + 5 * (size_t)i;
+        const float4 a = e[0], b = e[1];
+        O = f3(a.x, a.y, a.z), D = f3(b.x, b.y, b.z), tmax = a.w;
+        return true;
+    }
+    __device__ __forceinline__ void world(int i, float3& O, float3& D) const
+    {
+        const float4* e = p.shadow + 5 * (size_t)i;
+        const float4 a = e[0], b = e[1];
+        O = f3(a.x, a.y, a.z), D = f3(b.x, b.y, b.z);
+    }
+    __device__ __forceinline__ void store(int i, const HitRec& h) const
+    {
+        const float4* e = p.shadow + 5 * (size_t)i;
+        const float4 b = e[1], w = e[2], c = e[3], ir = e[4];
+        const float3 irradiance = h.obj > -1 ? f3(0, 0, 0) : f3(ir.x, ir.y, ir.z);
+        const float3 ambient = f3(0.3f, 0.3f, 0.3f);
+        splat(p.accum, __float_as_int(b.w), f3(w.x, w.y, w.z) * (f3(c.x, c.y, c.z) * (irradiance + ambient)));
+    }
+};
+
+__global__ void __launch_bounds__(128) k_wh_connect_persistent(const WhState p, const DScene s)
+{
+    const int n = min(p.count[2], p.capacity);
+    ShadowSrc src = { p };
+    trace_queue<true, false>(s, src, n, p.count + 5);
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.counters[1] += (unsigned long long)n;
+}
+
 // screen->pixels: RGBF32_to_RGB8 (template/precomp.h:325-341, scalar branch) of accumulator * scale
 __global__ void k_to_rgb8(const float4* __restrict__ accum, uint32_t* __restrict__ out, int n, float scale)
 {
@@ -481,6 +592,7 @@ struct rt_renderer {
     PTState pt = {};
     int ptSlotsAllocated = 0;
     int ptIterations = 0;
+    bool persistent = true;
     std::vector<void*> allocations;
     // whitted
     WhState wh = {};
@@ -592,10 +704,15 @@ rt_status rt_renderer_create(rt_scene* scene, const rt_render_params* params, rt
     r->accum = r->ownAccum;
     if (cudaMemset(r->ownAccum, 0, px * 16) != cudaSuccess) return fail(RT_ERR_CUDA);
     if ((st = ralloc(r, &r->dCounters, 4 * sizeof(unsigned long long))) != RT_OK) return fail(st);
-    if ((st = ralloc(r, &r->dCount, 4 * sizeof(int))) != RT_OK) return fail(st);
+    if ((st = ralloc(r, &r->dCount, 8 * sizeof(int))) != RT_OK) return fail(st);
     cudaMemset(r->dCounters, 0, 4 * sizeof(unsigned long long));
-    cudaMemset(r->dCount, 0, 4 * sizeof(int));
-    if (cudaMallocHost((void**)&r->hCount, 4 * sizeof(int)) != cudaSuccess) { set_error("pinned alloc failed"); return fail(RT_ERR_CUDA); }
+    cudaMemset(r->dCount, 0, 8 * sizeof(int));
+    {
+        // A/B switch for profiling: RT_B200_TRAVERSAL=simple selects the one-thread-per-ray kernels
+        const char* e = getenv("RT_B200_TRAVERSAL");
+        r->persistent = !(e && strcmp(e, "simple") == 0);
+    }
+    if (cudaMallocHost((void**)&r->hCount, 8 * sizeof(int)) != cudaSuccess) { set_error("pinned alloc failed"); return fail(RT_ERR_CUDA); }
     if ((st = ralloc(r, &r->dPixels, px * 4)) != RT_OK) return fail(st);
 
     if (params->integrator == RT_INTEGRATOR_WHITTED)
@@ -714,7 +831,8 @@ static rt_status render_pt(rt_renderer* r, int first_spp, int count, int stride)
             p.iteration = it;
             r->ptIterations = it + 1;
             r->prof_begin();
-            k_pt_extend<<<grid, 128, 0, r->stream>>>(p, r->scene->d, cur);
+            if (r->persistent) k_pt_extend_persistent<<<grid, 128, 0, r->stream>>>(p, r->scene->d, cur);
+            else k_pt_extend<<<grid, 128, 0, r->stream>>>(p, r->scene->d, cur);
             r->prof_end(RT_STAGE_EXTEND);
             r->prof_begin();
             k_pt_shade<<<grid, 128, 0, r->stream>>>(p, r->scene->d, r->cam, cur);
@@ -749,13 +867,15 @@ static rt_status render_whitted(rt_renderer* r)
     for (int depth = 0; depth <= P.depth_limit; depth++)
     {
         r->prof_begin();
-        k_wh_extend<<<grid, 128, 0, r->stream>>>(w, r->scene->d, cur);
+        if (r->persistent) k_wh_extend_persistent<<<grid, 128, 0, r->stream>>>(w, r->scene->d, cur);
+        else k_wh_extend<<<grid, 128, 0, r->stream>>>(w, r->scene->d, cur);
         r->prof_end(RT_STAGE_EXTEND);
         r->prof_begin();
         k_wh_shade<<<grid, 128, 0, r->stream>>>(w, r->scene->d, cur);
         r->prof_end(RT_STAGE_SHADE);
         r->prof_begin();
-        k_wh_connect<<<grid, 128, 0, r->stream>>>(w, r->scene->d);
+        if (r->persistent) k_wh_connect_persistent<<<grid, 128, 0, r->stream>>>(w, r->scene->d);
+        else k_wh_connect<<<grid, 128, 0, r->stream>>>(w, r->scene->d);
         r->prof_end(RT_STAGE_CONNECT);
         cur ^= 1;
     }
@@ -779,7 +899,7 @@ rt_status rt_renderer_sync(rt_renderer* r)
     RT_CUDA(cudaStreamSynchronize(r->stream));
     if (r->params.integrator == RT_INTEGRATOR_WHITTED)
     {
-        RT_CUDA(cudaMemcpy(r->hCount, r->dCount, 4 * sizeof(int), cudaMemcpyDeviceToHost));
+        RT_CUDA(cudaMemcpy(r->hCount, r->dCount, 8 * sizeof(int), cudaMemcpyDeviceToHost));
         if (r->hCount[3]) { set_error("Whitted ray queue overflow (more than 4 rays per pixel alive at one depth)"); return RT_ERR_UNSUPPORTED; }
     }
     return RT_OK;

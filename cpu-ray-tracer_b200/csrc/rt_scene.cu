@@ -4,7 +4,9 @@
 // TLASFileScene::FindNearest / IsOccluded (infra/scene/tlas_file_scene.cpp:201-218) and everything they
 // call: BVH::Intersect (infra/bvh.cpp:224-288), TLASBVH::Intersect (infra/tlas_bvh.cpp:83-111),
 // BLASBVH::Intersect (infra/blas_bvh.cpp:302-389), Quad / Plane tests (template/primitives.h:107-111,331-362).
+#include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "rt_internal.h"
@@ -47,6 +49,49 @@ __global__ void __launch_bounds__(128) k_is_occluded(const DScene s, const rt_ra
         const float4 b = __ldg((const float4*)(rays + i) + 1);
         out[i] = is_occluded(s, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w) ? 1 : 0;
     }
+}
+
+// persistent-warp versions (rt_device.cuh trace_queue)
+struct AbiSrc {
+    const rt_ray* __restrict__ rays;
+    rt_hit* __restrict__ hits;
+    uint8_t* __restrict__ occluded;
+    __device__ __forceinline__ bool load(int i, float3& O, float3& D, float& tmax) const
+    {
+        const float4 a = __ldg((const float4*)(rays + i));
+        const float4 b = __ldg((const float4*)(rays + i) + 1);
+        O = f3(a.x, a.y, a.z), D = f3(b.x, b.y, b.z), tmax = a.w;
+        return true;
+    }
+    __device__ __forceinline__ void world(int i, float3& O, float3& D) const
+    {
+        const float4 a = __ldg((const float4*)(rays + i));
+        const float4 b = __ldg((const float4*)(rays + i) + 1);
+        O = f3(a.x, a.y, a.z), D = f3(b.x, b.y, b.z);
+    }
+    __device__ __forceinline__ void store(int i, const HitRec& h) const
+    {
+        if (hits)
+        {
+            float4* out = (float4*)(hits + i);
+            out[0] = make_float4(h.t, h.u, h.v, __int_as_float(h.obj));
+            out[1] = make_float4(__int_as_float(h.tri), __int_as_float(h.traversed), __int_as_float(h.tested), 0.0f);
+        }
+        else occluded[i] = h.obj > -1 ? 1 : 0;
+    }
+};
+
+template <bool COUNTERS>
+__global__ void __launch_bounds__(128) k_find_nearest_persistent(const DScene s, const rt_ray* rays, rt_hit* hits, int n, int* fetch)
+{
+    AbiSrc src = { rays, hits, nullptr };
+    trace_queue<false, COUNTERS>(s, src, n, fetch);
+}
+
+__global__ void __launch_bounds__(128) k_is_occluded_persistent(const DScene s, const rt_ray* rays, uint8_t* out, int n, int* fetch)
+{
+    AbiSrc src = { rays, nullptr, out };
+    trace_queue<true, false>(s, src, n, fetch);
 }
 
 static int grid_for(size_t n, int block, int device)
@@ -301,6 +346,11 @@ rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags,
     s->bytes_textures = texels * 4;
     if ((st = upload(&s->textures, tex.data(), tex.size() * sizeof(DTexture))) != RT_OK) return fail(st);
     if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream create failed"); return fail(RT_ERR_CUDA); }
+    if ((st = upload(&s->fetch_counters, nullptr, rt_scene::FETCH_RING * sizeof(int))) != RT_OK) return fail(st);
+    {
+        const char* e = getenv("RT_B200_TRAVERSAL");
+        s->persistent = !(e && strcmp(e, "simple") == 0);
+    }
 
     DScene& d = s->d;
     d.nodes = s->nodes, d.tris = s->tris, d.inst = s->inst, d.shade = s->shade, d.inst_shade = s->inst_shade;
@@ -321,7 +371,7 @@ void rt_scene_destroy(rt_scene* s)
     cudaSetDevice(s->device);
     cudaFree(s->nodes), cudaFree(s->tris), cudaFree(s->inst), cudaFree(s->shade), cudaFree(s->inst_shade);
     cudaFree(s->obj_material), cudaFree(s->materials), cudaFree(s->textures), cudaFree(s->tex_pixels);
-    cudaFree(s->scratch_in), cudaFree(s->scratch_out);
+    cudaFree(s->scratch_in), cudaFree(s->scratch_out), cudaFree(s->fetch_counters);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -332,10 +382,21 @@ rt_status rt_find_nearest_device(rt_scene* s, const rt_ray* d_rays, rt_hit* d_hi
     if (n == 0) return RT_OK;
     RT_CUDA(cudaSetDevice(s->device));
     const int grid = grid_for(n, 128, s->device);
-    if (s->flags & RT_SCENE_FLAG_COUNTERS)
-        k_find_nearest<true><<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays, d_hits, n);
-    else
-        k_find_nearest<false><<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays, d_hits, n);
+    const bool counters = s->flags & RT_SCENE_FLAG_COUNTERS;
+    if (s->persistent)
+    {
+        // one launch handles at most 2^30 rays (int queue indices); larger batches are chunked
+        for (size_t off = 0; off < n; off += (size_t)1 << 30)
+        {
+            const int m = (int)((n - off) < ((size_t)1 << 30) ? (n - off) : ((size_t)1 << 30));
+            int* fetch = s->next_fetch_counter();
+            RT_CUDA(cudaMemsetAsync(fetch, 0, sizeof(int), (cudaStream_t)stream));
+            if (counters) k_find_nearest_persistent<true><<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays + off, d_hits + off, m, fetch);
+            else k_find_nearest_persistent<false><<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays + off, d_hits + off, m, fetch);
+        }
+    }
+    else if (counters) k_find_nearest<true><<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays, d_hits, n);
+    else k_find_nearest<false><<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays, d_hits, n);
     RT_CUDA(cudaGetLastError());
     return RT_OK;
 }
@@ -345,7 +406,18 @@ rt_status rt_is_occluded_device(rt_scene* s, const rt_ray* d_rays, uint8_t* d_ou
     if (!s || (n && (!d_rays || !d_out))) { set_error("rt_is_occluded_device: null argument"); return RT_ERR_INVALID; }
     if (n == 0) return RT_OK;
     RT_CUDA(cudaSetDevice(s->device));
-    k_is_occluded<<<grid_for(n, 128, s->device), 128, 0, (cudaStream_t)stream>>>(s->d, d_rays, d_out, n);
+    const int grid = grid_for(n, 128, s->device);
+    if (s->persistent)
+    {
+        for (size_t off = 0; off < n; off += (size_t)1 << 30)
+        {
+            const int m = (int)((n - off) < ((size_t)1 << 30) ? (n - off) : ((size_t)1 << 30));
+            int* fetch = s->next_fetch_counter();
+            RT_CUDA(cudaMemsetAsync(fetch, 0, sizeof(int), (cudaStream_t)stream));
+            k_is_occluded_persistent<<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays + off, d_out + off, m, fetch);
+        }
+    }
+    else k_is_occluded<<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays, d_out, n);
     RT_CUDA(cudaGetLastError());
     return RT_OK;
 }

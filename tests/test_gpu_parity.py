@@ -309,3 +309,34 @@ def test_sharding_properties_full_size(gpu_scenes, oracles):
     oacc, _ = po.render_pt(po.camera_default(W, H), p, 1, 4, 1)
     check_pt(ref[:32], oacc[:32], 4, "1080p top rows")
     full.close()
+
+
+def test_simple_traversal_kernels_agree(monkeypatch, oracles, flat_scenes):
+    """RT_B200_TRAVERSAL=simple selects the one-thread-per-ray kernels (kept for A/B profiling); both
+    kernel families must give the oracle's bits"""
+    from cpu_ray_tracer_b200 import api
+    from oracle import porthost
+    monkeypatch.setenv("RT_B200_TRAVERSAL", "simple")
+    for name in ("golden_file", "golden_tlas"):
+        po = oracles(name)
+        flat = flat_scenes(name)
+        sc = api.open_scene(flat, counters=True)
+        rays = random_rays(flat, 20000, seed=21)
+        ref, _ = po.find_nearest(rays)
+        assert_hits_equal(sc.FindNearest(rays), ref, name + " (simple kernels)")
+        occ, _ = po.is_occluded(rays)
+        assert np.array_equal(sc.IsOccluded(rays), occ)
+        W, H = 128, 80
+        cam = po.camera_default(W, H)
+        oacc, ost = po.render_pt(cam, porthost.default_params(abi.RT_INTEGRATOR_PATH, W, H), 1, 2, 1)
+        r = api.GpuRenderer(sc, abi.RT_INTEGRATOR_PATH, W, H).Init()
+        r.render(2)
+        assert r.counters()["extension_rays"] == ost["extension_rays"]
+        check_pt(r.accumulator, oacc, 2, name + " (simple kernels)")
+        r.close()
+        ow, _ = po.render_whitted(cam, porthost.default_params(abi.RT_INTEGRATOR_WHITTED, W, H))
+        r = api.GpuRenderer(sc, abi.RT_INTEGRATOR_WHITTED, W, H).Init()
+        r.Tick(0)
+        assert np.nan_to_num(np.abs(r.accumulator - ow)).max() <= WHITTED_TOL
+        r.close()
+        sc.close()
