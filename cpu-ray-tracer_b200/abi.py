@@ -9,6 +9,7 @@ RT_SCENE_FLAT, RT_SCENE_TLAS = 0, 1
 RT_SCENE_FLAG_COUNTERS = 1
 RT_INTEGRATOR_WHITTED, RT_INTEGRATOR_PATH = 0, 1
 RT_SEED_REFERENCE_TILE, RT_SEED_PER_PIXEL = 0, 1
+RT_SCHEDULE_AUTO, RT_SCHEDULE_WAVEFRONT, RT_SCHEDULE_STREAMS = 0, 1, 2
 
 f3 = C.c_float * 3
 f16 = C.c_float * 16
@@ -49,7 +50,8 @@ class rt_camera(C.Structure):
 class rt_render_params(C.Structure):
     _fields_ = [("integrator", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
                 ("depth_limit", C.c_int32), ("epsilon", C.c_float), ("seed_mode", C.c_int32),
-                ("tile_begin", C.c_int32), ("tile_end", C.c_int32), ("max_frames_in_flight", C.c_int32)]
+                ("tile_begin", C.c_int32), ("tile_end", C.c_int32), ("max_frames_in_flight", C.c_int32),
+                ("schedule", C.c_int32)]
 
 
 class rt_counters(C.Structure):

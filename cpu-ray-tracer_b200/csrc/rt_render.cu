@@ -167,9 +167,65 @@ __device__ __forceinline__ float3 diffuse_reflection(float3 N, uint32_t& seed)
     return normalize(R);
 }
 
-// One bounce of Renderer::Sample (renderer.cpp:50-100).  The reference recursion returns
-// w0 * (w1 * (... * L)); the factors w_d are stored per depth and multiplied back in that order when
-// the path ends, so a sample is bit-identical to the recursive evaluation.
+// One bounce of Renderer::Sample (renderer.cpp:50-100) on register state.  Returns true when the
+// path ends here with leaf radiance L (sky :54, depth limit :55, light :69); otherwise the throughput
+// factor w of this bounce and the continuation ray.  Shared by the wavefront shade stage and the
+// stream kernel so both evaluate the very same expressions.
+__device__ __forceinline__ bool pt_bounce(const DScene& s, const float eps, const int depthLimit,
+    const float3 O, const float3 D, const bool inside, const int depth,
+    const float t, const float bu, const float bv, const int obj, const int tri, uint32_t& seed,
+    float3& L, float3& w, float3& nO, float3& nD, bool& nInside)
+{
+    L = f3(0, 0, 0);
+    if (obj == -1) { L = sky_color(s, D); return true; }
+    if (depth >= depthLimit) return true;
+    const float3 I = O + t * D;
+    ShadeHit h;
+    float uu, vv;
+    hit_info(s, D, I, obj, tri, bu, bv, h, uu, vv);
+    if (h.isLight) { L = f3(s.light_color[0], s.light_color[1], s.light_color[2]); return true; }
+    float3 medium_scale = f3(1, 1, 1);
+    if (inside)
+    {
+        const float3 a = h.absorption * -t; // renderer.cpp:76-80
+        medium_scale = f3(expf(a.x), expf(a.y), expf(a.z));
+    }
+    const float r = random_float(seed);
+    nInside = false;
+    if (r < h.reflectivity)
+    {
+        nD = reflect(D, h.N); // HandleMirror :20-25
+        w = h.albedo * medium_scale;
+    }
+    else if (r < h.reflectivity + h.refractivity)
+    {
+        // HandleDielectric :27-45
+        w = h.albedo * medium_scale;
+        nD = reflect(D, h.N);
+        const float n1 = inside ? 1.2f : 1, n2 = inside ? 1 : 1.2f;
+        const float eta = n1 / n2, cosi = dot(-D, h.N);
+        const float cost2 = 1.0f - eta * eta * (1 - cosi * cosi);
+        if (cost2 > 0)
+        {
+            const float a = n1 - n2, b = n1 + n2, R0 = (a * a) / (b * b), c = 1 - cosi;
+            const float Fr = R0 + (1 - R0) * (c * c * c * c * c);
+            const float3 T = eta * D + ((eta * cosi - sqrtf(fabsf(cost2))) * h.N);
+            if (random_float(seed) > Fr) nD = T, nInside = !inside;
+        }
+    }
+    else
+    {
+        nD = diffuse_reflection(h.N, seed);
+        const float3 brdf = h.albedo * RT_INVPI;
+        w = medium_scale * brdf * 2.0f * RT_PI * dot(nD, h.N); // renderer.cpp:98
+    }
+    nO = I + nD * eps;
+    return false;
+}
+
+// shade stage of the wavefront.  The reference recursion returns w0 * (w1 * (... * L)); the factors
+// w_d are stored per depth and multiplied back in that order when the path ends, so a sample is
+// bit-identical to the recursive evaluation.
 __global__ void __launch_bounds__(128) k_pt_shade(const PTState p, const DScene s, const DCamera cam, int cur)
 {
     const int n = p.count[cur];
@@ -187,75 +243,26 @@ __global__ void __launch_bounds__(128) k_pt_shade(const PTState p, const DScene 
             slot = active[i];
             alive = true;
             const float4 o4 = p.rayO[slot], d4 = p.rayD[slot], h4 = p.hit[slot];
-            const float3 O = f3(o4.x, o4.y, o4.z), D = f3(d4.x, d4.y, d4.z);
             const int flags = __float_as_int(d4.w);
-            const bool inside = flags & 1;
             int depth = flags >> 8;
-            const int obj = __float_as_int(h4.w);
-            const float t = h4.x;
             uint32_t seed = p.seed[slot];
-            float3 L = f3(0, 0, 0);
-            bool terminated = false;
-            if (obj == -1) L = sky_color(s, D), terminated = true;          // renderer.cpp:54
-            else if (depth >= p.depthLimit) terminated = true;               // renderer.cpp:55
-            else
+            float3 L, w, nO, nD;
+            bool nInside;
+            const bool terminated = pt_bounce(s, p.eps, p.depthLimit, f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z), flags & 1, depth,
+                h4.x, h4.y, h4.z, __float_as_int(h4.w), p.hitTri[slot], seed, L, w, nO, nD, nInside);
+            if (!terminated)
             {
-                const float3 I = O + t * D;
-                ShadeHit h;
-                float uu, vv;
-                hit_info(s, D, I, obj, p.hitTri[slot], h4.y, h4.z, h, uu, vv);
-                if (h.isLight) L = f3(s.light_color[0], s.light_color[1], s.light_color[2]), terminated = true; // :69
-                else
-                {
-                    float3 medium_scale = f3(1, 1, 1);
-                    if (inside)
-                    {
-                        const float3 a = h.absorption * -t; // renderer.cpp:76-80
-                        medium_scale = f3(expf(a.x), expf(a.y), expf(a.z));
-                    }
-                    const float r = random_float(seed);
-                    float3 w, nD;
-                    bool nInside = false;
-                    if (r < h.reflectivity)
-                    {
-                        nD = reflect(D, h.N); // HandleMirror :20-25
-                        w = h.albedo * medium_scale;
-                    }
-                    else if (r < h.reflectivity + h.refractivity)
-                    {
-                        // HandleDielectric :27-45
-                        w = h.albedo * medium_scale;
-                        nD = reflect(D, h.N);
-                        const float n1 = inside ? 1.2f : 1, n2 = inside ? 1 : 1.2f;
-                        const float eta = n1 / n2, cosi = dot(-D, h.N);
-                        const float cost2 = 1.0f - eta * eta * (1 - cosi * cosi);
-                        if (cost2 > 0)
-                        {
-                            const float a = n1 - n2, b = n1 + n2, R0 = (a * a) / (b * b), c = 1 - cosi;
-                            const float Fr = R0 + (1 - R0) * (c * c * c * c * c);
-                            const float3 T = eta * D + ((eta * cosi - sqrtf(fabsf(cost2))) * h.N);
-                            if (random_float(seed) > Fr) nD = T, nInside = !inside;
-                        }
-                    }
-                    else
-                    {
-                        nD = diffuse_reflection(h.N, seed);
-                        const float3 brdf = h.albedo * RT_INVPI;
-                        w = medium_scale * brdf * 2.0f * RT_PI * dot(nD, h.N); // renderer.cpp:98
-                    }
-                    const float3 nO = I + nD * p.eps;
-                    p.weights[(size_t)depth * p.slots + slot] = make_float4(w.x, w.y, w.z, 0);
-                    depth++;
-                    p.rayO[slot] = make_float4(nO.x, nO.y, nO.z, 0);
-                    p.rayD[slot] = make_float4(nD.x, nD.y, nD.z, __int_as_float((nInside ? 1 : 0) | (depth << 8)));
-                }
+                p.weights[(size_t)depth * p.slots + slot] = make_float4(w.x, w.y, w.z, 0);
+                depth++;
+                p.rayO[slot] = make_float4(nO.x, nO.y, nO.z, 0);
+                p.rayD[slot] = make_float4(nD.x, nD.y, nD.z, __int_as_float((nInside ? 1 : 0) | (depth << 8)));
             }
-            if (terminated)
+            else
             {
                 for (int d = depth - 1; d >= 0; d--)
                 {
-                    const float4 w = p.weights[(size_t)d * p.slots + slot];
-                    L = f3(w.x, w.y, w.z) * L;
+                    const float4 wd = p.weights[(size_t)d * p.slots + slot];
+                    L = f3(wd.x, wd.y, wd.z) * L;
                 }
                 int pix = p.pix[slot]; // index of the NEXT pixel; the finished one is pix - 1
                 {
@@ -267,10 +274,10 @@ __global__ void __launch_bounds__(128) k_pt_shade(const PTState p, const DScene 
                 }
                 if (pix < 256)
                 {
-                    float3 nD;
-                    pt_generate(p, cam, slot, pix, seed, nD);
+                    float3 gD;
+                    pt_generate(p, cam, slot, pix, seed, gD);
                     p.rayO[slot] = make_float4(cam.pos.x, cam.pos.y, cam.pos.z, 0);
-                    p.rayD[slot] = make_float4(nD.x, nD.y, nD.z, __int_as_float(0));
+                    p.rayD[slot] = make_float4(gD.x, gD.y, gD.z, __int_as_float(0));
                     p.pix[slot] = pix + 1;
                 }
                 else alive = false;
@@ -288,6 +295,94 @@ __global__ void __launch_bounds__(128) k_pt_shade(const PTState p, const DScene 
             if (alive) nextActive[pos + __popc(mask & ((1u << lane) - 1))] = slot;
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stream schedule: one persistent kernel, no global lock-step.
+//
+// With the reference's RNG a (tile, frame) stream is a serial chain of up to 256 x (depthLimit + 1)
+// rays.  The wavefront advances every stream by one ray per extend/shade launch pair, so a render
+// costs (longest chain) x (slowest ray of the iteration + shade + two launch gaps, cold L1 each
+// launch): profiles/r1_v2_pt_per_iteration_persistent.txt shows 1536 iterations that never drop below
+// ~70 us although the last 1000 of them carry a quarter of the rays.  Here every lane owns one stream
+// and runs it to completion in registers (ray, seed, pixel counter, throughput factors); a lane whose
+// stream ends pulls the next one (ballot / popc, one atomic per warp).  Streams are handed out tile by
+// tile, so the 32 lanes of a warp trace the same tile in 32 different frames: similar rays, warm L1.
+// ---------------------------------------------------------------------------------------------
+constexpr int STREAM_MAX_DEPTH = 8;
+
+__global__ void __launch_bounds__(128) k_pt_streams(const PTState p, const DScene s, const DCamera cam,
+    const int* __restrict__ tileOrder, const int frames, int* __restrict__ streamCounter)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int total = p.slots;
+    bool alive = false, poolEmpty = false;
+    int tile = 0, pix = 0, depth = 0;
+    bool inside = false;
+    uint32_t seed = 0;
+    float3 O = f3(0, 0, 0), D = f3(0, 0, 0);
+    float3 wst[STREAM_MAX_DEPTH];
+    unsigned long long rays = 0;
+    while (true)
+    {
+        const unsigned idle = __ballot_sync(FULL, !alive);
+        if (idle && !poolEmpty)
+        {
+            const int nIdle = __popc(idle);
+            const int leader = __ffs(idle) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(streamCounter, nIdle);
+            base = __shfl_sync(FULL, base, leader);
+            if (base + nIdle >= total) poolEmpty = true;
+            const int stream = base + __popc(idle & ((1u << lane) - 1));
+            if (!alive && stream < total)
+            {
+                const int k = stream / frames, frame = stream - k * frames;
+                tile = p.tileBegin + (tileOrder ? tileOrder[k] : k);
+                const int spp = p.firstSpp + frame * p.stride;
+                seed = pt_seed(p, tile, spp);
+                pix = 0, depth = 0, inside = false, alive = true;
+                const int tx = tile % p.tilesX, ty = tile / p.tilesX;
+                const float jy = random_float(seed), jx = random_float(seed);
+                D = primary_dir(cam, (float)(tx * 16) + jx, (float)(ty * 16) + jy);
+                O = cam.pos;
+            }
+        }
+        if (__ballot_sync(FULL, alive) == 0) break;
+        if (alive)
+        {
+            HitRec h;
+            find_nearest<false>(s, O, D, 1e34f, h);
+            rays++;
+            float3 L, w, nO, nD;
+            bool nInside;
+            if (!pt_bounce(s, p.eps, p.depthLimit, O, D, inside, depth, h.t, h.u, h.v, h.obj, h.tri, seed, L, w, nO, nD, nInside))
+            {
+                wst[depth] = w;
+                depth++, O = nO, D = nD, inside = nInside;
+            }
+            else
+            {
+                for (int d = depth - 1; d >= 0; d--) L = wst[d] * L;
+                const int tx = tile % p.tilesX, ty = tile / p.tilesX;
+                const int x = tx * 16 + (pix & 15), y = ty * 16 + (pix >> 4);
+                float* a = (float*)(p.accum + (x + (size_t)y * p.W));
+                atomicAdd(a + 0, L.x), atomicAdd(a + 1, L.y), atomicAdd(a + 2, L.z);
+                pix++;
+                if (pix < 256)
+                {
+                    const int nx = tx * 16 + (pix & 15), ny = ty * 16 + (pix >> 4);
+                    const float jy = random_float(seed), jx = random_float(seed);
+                    D = primary_dir(cam, (float)nx + jx, (float)ny + jy);
+                    O = cam.pos, depth = 0, inside = false;
+                }
+                else alive = false;
+            }
+        }
+    }
+    for (int off = 16; off; off >>= 1) rays += __shfl_xor_sync(FULL, rays, off);
+    if (lane == 0) atomicAdd(p.counters, rays);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -593,6 +688,8 @@ struct rt_renderer {
     int ptSlotsAllocated = 0;
     int ptIterations = 0;
     bool persistent = true;
+    bool useStreams = true;
+    int streamCtasPerSm = 8;
     std::vector<void*> allocations;
     // whitted
     WhState wh = {};
@@ -711,6 +808,12 @@ rt_status rt_renderer_create(rt_scene* scene, const rt_render_params* params, rt
         // A/B switch for profiling: RT_B200_TRAVERSAL=simple selects the one-thread-per-ray kernels
         const char* e = getenv("RT_B200_TRAVERSAL");
         r->persistent = !(e && strcmp(e, "simple") == 0);
+        // path-tracer schedule: params->schedule, overridable for A/B runs with RT_B200_PT_SCHEDULE
+        r->useStreams = params->schedule != RT_SCHEDULE_WAVEFRONT;
+        if ((e = getenv("RT_B200_PT_SCHEDULE")) != nullptr) r->useStreams = strcmp(e, "wavefront") != 0;
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams, 128, 0) == cudaSuccess && occ > 0) r->streamCtasPerSm = occ;
+        if ((e = getenv("RT_B200_STREAM_CTAS")) != nullptr && atoi(e) > 0) r->streamCtasPerSm = atoi(e);
     }
     if (cudaMallocHost((void**)&r->hCount, 8 * sizeof(int)) != cudaSuccess) { set_error("pinned alloc failed"); return fail(RT_ERR_CUDA); }
     if ((st = ralloc(r, &r->dPixels, px * 4)) != RT_OK) return fail(st);
@@ -798,11 +901,34 @@ static rt_status pt_ensure_slots(rt_renderer* r, int slots)
     return RT_OK;
 }
 
+static rt_status render_pt_streams(rt_renderer* r, int first_spp, int count, int stride)
+{
+    const rt_render_params& P = r->params;
+    const int nTiles = num_tiles(P);
+    PTState p = {};
+    p.counters = r->dCounters, p.accum = r->accum;
+    p.nTiles = nTiles, p.tilesX = P.width / 16, p.tileBegin = P.tile_begin;
+    p.W = P.width, p.H = P.height, p.depthLimit = P.depth_limit, p.seedMode = P.seed_mode, p.eps = P.epsilon;
+    p.stride = stride, p.firstSpp = first_spp;
+    // all frames of the call form one pool of nTiles x count streams (int range checked by the caller)
+    p.slots = nTiles * count;
+    RT_CUDA(cudaMemsetAsync(r->dCount + 6, 0, sizeof(int), r->stream));
+    r->prof_begin();
+    k_pt_streams<<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, nullptr, count, r->dCount + 6);
+    r->prof_end(RT_STAGE_EXTEND);
+    r->paths += (uint64_t)p.slots * 256;
+    RT_CUDA(cudaGetLastError());
+    return RT_OK;
+}
+
 static rt_status render_pt(rt_renderer* r, int first_spp, int count, int stride)
 {
     const rt_render_params& P = r->params;
     const int nTiles = num_tiles(P);
     if (nTiles == 0 || count <= 0) return RT_OK;
+    if (r->useStreams && P.seed_mode == RT_SEED_REFERENCE_TILE && P.depth_limit <= STREAM_MAX_DEPTH
+        && (long long)nTiles * count < (1ll << 30))
+        return render_pt_streams(r, first_spp, count, stride);
     int inFlight = P.max_frames_in_flight > 0 ? P.max_frames_in_flight : (1 << 20) / nTiles;
     if (inFlight < 1) inFlight = 1;
     if (inFlight > count) inFlight = count;

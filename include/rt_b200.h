@@ -201,7 +201,18 @@ typedef struct rt_render_params {
     int32_t tile_begin;     /* path tracer: render tiles [tile_begin, tile_end) of the          */
     int32_t tile_end;       /* (W/16)x(H/16) row-major tile grid; tile_end <= 0 = all tiles      */
     int32_t max_frames_in_flight; /* wavefront width = tiles x frames in flight; 0 = library default */
+    int32_t schedule;       /* path tracer, RT_SEED_REFERENCE_TILE: how the (tile, frame) streams are advanced */
 } rt_render_params;
+
+enum {
+    RT_SCHEDULE_AUTO = 0,      /* library default (streams) */
+    /* global wavefront: generate / extend / shade kernels over compacted SoA queues, every stream
+     * advances one ray per launch pair */
+    RT_SCHEDULE_WAVEFRONT = 1,
+    /* one persistent kernel, every lane runs its stream to completion and then pulls the next one:
+     * no global lock-step, path state in registers */
+    RT_SCHEDULE_STREAMS = 2
+};
 
 void rt_render_params_default(rt_render_params* p, int integrator, int width, int height);
 

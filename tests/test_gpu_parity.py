@@ -181,15 +181,16 @@ def test_whitted_vs_oracle(name, oracles, gpu_scenes):
     r.close()
 
 
+@pytest.mark.parametrize("schedule", [abi.RT_SCHEDULE_STREAMS, abi.RT_SCHEDULE_WAVEFRONT], ids=["streams", "wavefront"])
 @pytest.mark.parametrize("name", SCENES)
-def test_path_tracer_vs_oracle_reference_rng(name, oracles, gpu_scenes):
+def test_path_tracer_vs_oracle_reference_rng(name, schedule, oracles, gpu_scenes):
     from cpu_ray_tracer_b200 import api
     from oracle import porthost
     po, sc = oracles(name), gpu_scenes(name, counters=False)
     W, H, frames = 320, 192, 3
     cam = po.camera_default(W, H)
     oacc, ost = po.render_pt(cam, porthost.default_params(abi.RT_INTEGRATOR_PATH, W, H), 1, frames, 1)
-    r = api.GpuRenderer(sc, abi.RT_INTEGRATOR_PATH, W, H).Init()
+    r = api.GpuRenderer(sc, abi.RT_INTEGRATOR_PATH, W, H, schedule=schedule).Init()
     for _ in range(frames):
         r.Tick(0)  # one Renderer::Tick per call, spp advances 1, 2, 3
     assert r.spp == 1 + frames
@@ -282,6 +283,12 @@ def test_sharding_properties_full_size(gpu_scenes, oracles):
     full.render(4, first_spp=1)
     ref = full.accumulator
     rays_full = full.counters()["extension_rays"]
+    # the two schedules trace the same rays and build the same image
+    wf = api.GpuRenderer(sc, abi.RT_INTEGRATOR_PATH, W, H, schedule=abi.RT_SCHEDULE_WAVEFRONT).Init()
+    wf.render(4, first_spp=1)
+    assert wf.counters()["extension_rays"] == rays_full
+    assert np.abs(wf.accumulator - ref).max() <= 1e-4
+    wf.close()
     assert (ref[1072:] == 0).all()  # 1080 % 16 = 8 rows never rendered
     assert ref[:1072, :, :3].sum() > 0
     # sample-index sharding

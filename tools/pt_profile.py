@@ -10,7 +10,7 @@ name = sys.argv[1] if len(sys.argv) > 1 else "wok_teapot_flat"
 W, H, spp = 1920, 1080, int(sys.argv[2]) if len(sys.argv) > 2 else 64
 fs = rtb.FlatScene.load(os.path.join(ROOT, "oracle", "_ref", "scenes", name + ".rtscene.gz"))
 sc = api.open_scene(fs)
-r = api.GpuRenderer(sc, abi.RT_INTEGRATOR_PATH, W, H).Init()
+r = api.GpuRenderer(sc, abi.RT_INTEGRATOR_PATH, W, H, schedule=abi.RT_SCHEDULE_WAVEFRONT).Init()
 r.render(spp, first_spp=1); r.sync()
 r.set_profiling(True)
 r.reset_counters()
