@@ -19,6 +19,7 @@
 // Whitted.  Rays carry (pixel, weight); shade splats sky / light / ambient terms, pushes reflection and
 // refraction rays into the next queue and one shadow ray per diffuse hit into the shadow queue;
 //   connect   any-hit occlusion kernel over the shadow queue, adds the direct term when visible.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -385,6 +386,235 @@ __global__ void __launch_bounds__(128) k_pt_streams(const PTState p, const DScen
     if (lane == 0) atomicAdd(p.counters, rays);
 }
 
+// Pilot for the stream schedule: a stream's length is only known when it ends, and a long stream that
+// is handed out late becomes the tail of the whole render (a chain of ~1500 dependent rays).  Sixteen
+// throw-away paths per tile (own seeds, nothing is accumulated) estimate each tile's cost in node
+// visits + triangle tests + a per-ray constant; the host sorts tiles by it and the stream pool hands
+// them out longest first (LPT list scheduling).
+constexpr int PILOT_PATHS = 16;
+
+__global__ void __launch_bounds__(128) k_pt_pilot(const PTState p, const DScene s, const DCamera cam, unsigned int* __restrict__ cost)
+{
+    const int n = p.nTiles * PILOT_PATHS;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const int k = i / PILOT_PATHS, j = i - k * PILOT_PATHS;
+        const int tile = p.tileBegin + k;
+        const int tx = tile % p.tilesX, ty = tile / p.tilesX;
+        uint32_t seed = wang_hash((uint32_t)i * 2654435761u + 12345u) | 1u;
+        float3 O = cam.pos;
+        float3 D = primary_dir(cam, (float)(tx * 16 + (j & 3) * 4) + 4 * random_float(seed), (float)(ty * 16 + (j >> 2) * 4) + 4 * random_float(seed));
+        bool inside = false;
+        unsigned int c = 0;
+        for (int depth = 0;; depth++)
+        {
+            HitRec h;
+            find_nearest<true>(s, O, D, 1e34f, h);
+            c += 8u + (unsigned)h.traversed + 2u * (unsigned)h.tested;
+            float3 L, w, nO, nD;
+            bool nInside;
+            if (pt_bounce(s, p.eps, p.depthLimit, O, D, inside, depth, h.t, h.u, h.v, h.obj, h.tri, seed, L, w, nO, nD, nInside)) break;
+            O = nO, D = nD, inside = nInside;
+        }
+        atomicAdd(&cost[k], c);
+    }
+}
+
+// Stream kernel, version 2: per-lane state machine with warp-level action voting.
+//
+// ncu on version 1 (profiles/r1_v3_k_pt_streams_v1_ncu_full.txt): issue slots 69 % busy but only 7.9 of
+// 32 lanes active per instruction, because a warp waits for its slowest ray before it shades and lanes
+// sit out each other's node / triangle / shading code.  Here every lane is in one of the states
+//   NODE  next step is an interior-node visit          LEAF  next step is a triangle leaf, instance entry or exit
+//   SHADE traversal finished, the bounce is pending    DEAD  no stream (pool exhausted)
+// and each loop iteration the warp executes the ONE action most lanes are waiting for (ballot / popc),
+// so the lanes that take part in an instruction are a majority instead of the leftovers.  Per lane the
+// order of node visits, triangle tests, RNG draws and bounces is unchanged.
+enum { ST_DEAD = 0, ST_NODE = 1, ST_LEAF = 2, ST_SHADE = 3 };
+
+template <bool TLAS>
+__global__ void __launch_bounds__(128) k_pt_streams2(const PTState p, const DScene s, const DCamera cam,
+    const int* __restrict__ tileOrder, const int frames, int* __restrict__ streamCounter)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int total = p.slots;
+    const float4* __restrict__ nodes = s.nodes;
+    const float4* __restrict__ tris = s.tris;
+    bool poolEmpty = false;
+    int state = ST_DEAD;
+    // stream
+    int tile = 0, pix = 0, depth = 0;
+    bool inside = false;
+    uint32_t seed = 0;
+    float3 wO = f3(0, 0, 0), wD = f3(0, 0, 0); // the ray in world space
+    float3 wst[STREAM_MAX_DEPTH];
+    // traversal
+    float3 O = f3(0, 0, 0), D = f3(0, 0, 0), rD = f3(0, 0, 0); // the ray in the space being traversed
+    bool exact = false;
+    int stack[STACK_SIZE];
+    int sp = 0, cur = 0, instObj = -1;
+    float ht = 0, hu = 0, hv = 0;
+    int hobj = -1, htri = -1;
+    unsigned long long rays = 0;
+
+    // FindNearest prologue for the ray (wO, wD): light quad, floor plane (file_scene.cpp:172-173), then the BVH
+#define RT_START_RAY()                                                                         \
+    {                                                                                          \
+        ht = 1e34f, hu = 0, hv = 0, hobj = -1, htri = -1;                                      \
+        float tq;                                                                              \
+        if (quad_test(s, wO, wD, ht, tq)) ht = tq, hobj = 0;                                   \
+        const float3 fn = f3(s.floor_n[0], s.floor_n[1], s.floor_n[2]);                        \
+        const float tp = -(dot(wO, fn) + s.floor_d) / (dot(wD, fn));                           \
+        if (tp < ht && tp > 0) ht = tp, hobj = 1;                                              \
+        O = wO, D = wD, rD = recip(wD), exact = needs_exact_slab(wO, wD);                      \
+        sp = 0, cur = s.root_ref, instObj = s.flat_obj_idx;                                    \
+        state = cur >= 0 ? ST_NODE : ST_LEAF;                                                  \
+        rays++;                                                                                \
+    }
+
+    while (true)
+    {
+        const unsigned mDead = __ballot_sync(FULL, state == ST_DEAD);
+        if (mDead && !poolEmpty)
+        {
+            const int nIdle = __popc(mDead);
+            const int leader = __ffs(mDead) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(streamCounter, nIdle);
+            base = __shfl_sync(FULL, base, leader);
+            if (base + nIdle >= total) poolEmpty = true;
+            const int stream = base + __popc(mDead & ((1u << lane) - 1));
+            if (state == ST_DEAD && stream < total)
+            {
+                const int k = stream / frames, frame = stream - k * frames;
+                tile = p.tileBegin + (tileOrder ? tileOrder[k] : k);
+                seed = pt_seed(p, tile, p.firstSpp + frame * p.stride);
+                pix = 0, depth = 0, inside = false;
+                const int tx = tile % p.tilesX, ty = tile / p.tilesX;
+                const float jy = random_float(seed), jx = random_float(seed);
+                wD = primary_dir(cam, (float)(tx * 16) + jx, (float)(ty * 16) + jy);
+                wO = cam.pos;
+                RT_START_RAY();
+            }
+        }
+        const unsigned mNode = __ballot_sync(FULL, state == ST_NODE);
+        const unsigned mLeaf = __ballot_sync(FULL, state == ST_LEAF);
+        const unsigned mShade = __ballot_sync(FULL, state == ST_SHADE);
+        if ((mNode | mLeaf | mShade) == 0) break;
+        const int nN = __popc(mNode), nL = __popc(mLeaf), nS = __popc(mShade);
+        if (nN >= nL && nN >= nS)
+        {
+            if (state == ST_NODE)
+            {
+                const float4* nd = nodes + 4 * (size_t)cur;
+                const float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2);
+                const int4 n3 = __ldg((const int4*)(nd + 3));
+                float d1 = slab(O, rD, ht, exact, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y);
+                float d2 = slab(O, rD, ht, exact, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w);
+                int c1 = n3.x, c2 = n3.y;
+                if (d1 > d2) { const float tf = d1; d1 = d2; d2 = tf; const int tc = c1; c1 = c2; c2 = tc; }
+                if (d1 == 1e30f)
+                {
+                    if (sp == 0) state = ST_SHADE;
+                    else cur = stack[--sp], state = cur >= 0 ? ST_NODE : ST_LEAF;
+                }
+                else
+                {
+                    cur = c1, state = c1 >= 0 ? ST_NODE : ST_LEAF;
+                    if (d2 != 1e30f) stack[sp++] = c2;
+                }
+            }
+        }
+        else if (nL >= nS)
+        {
+            if (state == ST_LEAF)
+            {
+                const int payload = ~cur;
+                bool pop = true;
+                if (TLAS && payload == SENTINEL_PAYLOAD)
+                {
+                    O = wO, D = wD, rD = recip(wD), exact = needs_exact_slab(wO, wD); // blas_bvh.cpp:385-388
+                }
+                else if (TLAS && (payload & INSTANCE_BIT))
+                {
+                    const float4* I = s.inst + 4 * (size_t)(payload & ~INSTANCE_BIT);
+                    const float4 r0 = __ldg(I), r1 = __ldg(I + 1), r2 = __ldg(I + 2);
+                    const int4 meta = __ldg((const int4*)(I + 3));
+                    O = f3((wO.x * r0.x + wO.y * r0.y) + (wO.z * r0.z + r0.w),
+                           (wO.x * r1.x + wO.y * r1.y) + (wO.z * r1.z + r1.w),
+                           (wO.x * r2.x + wO.y * r2.y) + (wO.z * r2.z + r2.w));
+                    D = f3((wD.x * r0.x + wD.y * r0.y) + wD.z * r0.z,
+                           (wD.x * r1.x + wD.y * r1.y) + wD.z * r1.z,
+                           (wD.x * r2.x + wD.y * r2.y) + wD.z * r2.z);
+                    rD = recip(D), exact = needs_exact_slab(O, D);
+                    instObj = meta.y;
+                    stack[sp++] = ~SENTINEL_PAYLOAD;
+                    cur = meta.x, state = cur >= 0 ? ST_NODE : ST_LEAF;
+                    pop = false;
+                }
+                else
+                {
+                    int slot = payload;
+                    while (true)
+                    {
+                        const float4* T = tris + 3 * (size_t)slot;
+                        const float4 t0 = __ldg(T), t1 = __ldg(T + 1), t2 = __ldg(T + 2);
+                        const int tag = __float_as_int(t0.w);
+                        if (intersect_tri(O, D, f3(t0.x, t0.y, t0.z), f3(t1.x, t1.y, t1.z), f3(t2.x, t2.y, t2.z), ht, hu, hv))
+                        {
+                            htri = tag & ~LAST_BIT;
+                            hobj = instObj >= 0 ? instObj : __float_as_int(t1.w);
+                        }
+                        if (tag & LAST_BIT) break;
+                        slot++;
+                    }
+                }
+                if (pop)
+                {
+                    if (sp == 0) state = ST_SHADE;
+                    else cur = stack[--sp], state = cur >= 0 ? ST_NODE : ST_LEAF;
+                }
+            }
+        }
+        else
+        {
+            if (state == ST_SHADE)
+            {
+                float3 L, w, nO, nD;
+                bool nInside;
+                if (!pt_bounce(s, p.eps, p.depthLimit, wO, wD, inside, depth, ht, hu, hv, hobj, htri, seed, L, w, nO, nD, nInside))
+                {
+                    wst[depth] = w;
+                    depth++, wO = nO, wD = nD, inside = nInside;
+                    RT_START_RAY();
+                }
+                else
+                {
+                    for (int d = depth - 1; d >= 0; d--) L = wst[d] * L;
+                    const int tx = tile % p.tilesX, ty = tile / p.tilesX;
+                    const int x = tx * 16 + (pix & 15), y = ty * 16 + (pix >> 4);
+                    float* a = (float*)(p.accum + (x + (size_t)y * p.W));
+                    atomicAdd(a + 0, L.x), atomicAdd(a + 1, L.y), atomicAdd(a + 2, L.z);
+                    pix++;
+                    if (pix < 256)
+                    {
+                        const int nx = tx * 16 + (pix & 15), ny = ty * 16 + (pix >> 4);
+                        const float jy = random_float(seed), jx = random_float(seed);
+                        wD = primary_dir(cam, (float)nx + jx, (float)ny + jy);
+                        wO = cam.pos, depth = 0, inside = false;
+                        RT_START_RAY();
+                    }
+                    else state = ST_DEAD;
+                }
+            }
+        }
+    }
+#undef RT_START_RAY
+    for (int off = 16; off; off >>= 1) rays += __shfl_xor_sync(FULL, rays, off);
+    if (lane == 0) atomicAdd(p.counters, rays);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Whitted wavefront
 // ---------------------------------------------------------------------------------------------
@@ -690,6 +920,12 @@ struct rt_renderer {
     bool persistent = true;
     bool useStreams = true;
     int streamCtasPerSm = 8;
+    int streamKernel = 2;
+    bool streamLpt = true;
+    int* dTileOrder = nullptr;
+    unsigned int* dTileCost = nullptr;
+    int tileOrderCapacity = 0, tileOrderCount = 0;
+    bool tileOrderValid = false;
     std::vector<void*> allocations;
     // whitted
     WhState wh = {};
@@ -811,8 +1047,14 @@ rt_status rt_renderer_create(rt_scene* scene, const rt_render_params* params, rt
         // path-tracer schedule: params->schedule, overridable for A/B runs with RT_B200_PT_SCHEDULE
         r->useStreams = params->schedule != RT_SCHEDULE_WAVEFRONT;
         if ((e = getenv("RT_B200_PT_SCHEDULE")) != nullptr) r->useStreams = strcmp(e, "wavefront") != 0;
+        if ((e = getenv("RT_B200_STREAM_KERNEL")) != nullptr && atoi(e) > 0) r->streamKernel = atoi(e);
+        if ((e = getenv("RT_B200_STREAM_LPT")) != nullptr) r->streamLpt = atoi(e) != 0;
         int occ = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams, 128, 0) == cudaSuccess && occ > 0) r->streamCtasPerSm = occ;
+        cudaError_t oe;
+        if (r->streamKernel == 1) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams, 128, 0);
+        else if (scene->d.kind == RT_SCENE_TLAS) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams2<true>, 128, 0);
+        else oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams2<false>, 128, 0);
+        if (oe == cudaSuccess && occ > 0) r->streamCtasPerSm = occ;
         if ((e = getenv("RT_B200_STREAM_CTAS")) != nullptr && atoi(e) > 0) r->streamCtasPerSm = atoi(e);
     }
     if (cudaMallocHost((void**)&r->hCount, 8 * sizeof(int)) != cudaSuccess) { set_error("pinned alloc failed"); return fail(RT_ERR_CUDA); }
@@ -867,7 +1109,9 @@ rt_status rt_renderer_set_accumulator(rt_renderer* r, void* d_accumulator)
 rt_status rt_renderer_set_camera(rt_renderer* r, const rt_camera* cam)
 {
     if (!r || !cam) return RT_ERR_INVALID;
-    r->cam = make_camera(*cam, r->params.width, r->params.height);
+    const DCamera c = make_camera(*cam, r->params.width, r->params.height);
+    if (memcmp(&c, &r->cam, sizeof c) != 0) r->tileOrderValid = false; // the pilot's tile costs are per view
+    r->cam = c;
     return RT_OK;
 }
 
@@ -901,6 +1145,35 @@ static rt_status pt_ensure_slots(rt_renderer* r, int slots)
     return RT_OK;
 }
 
+// tile order for the stream pool: pilot cost per tile, sorted descending on the host (one small
+// round trip per render call; the order depends on scene, camera and tile range only, so it is cached)
+static rt_status pt_tile_order(rt_renderer* r, const PTState& p)
+{
+    const int n = p.nTiles;
+    if (r->tileOrderValid && r->tileOrderCount == n) return RT_OK;
+    if (r->tileOrderCapacity < n)
+    {
+        rt_status st;
+        if ((st = ralloc(r, &r->dTileOrder, (size_t)n * 4)) != RT_OK) return st;
+        if ((st = ralloc(r, &r->dTileCost, (size_t)n * 4)) != RT_OK) return st;
+        r->tileOrderCapacity = n;
+    }
+    RT_CUDA(cudaMemsetAsync(r->dTileCost, 0, (size_t)n * 4, r->stream));
+    r->prof_begin();
+    k_pt_pilot<<<r->sms * 4, 128, 0, r->stream>>>(p, r->scene->d, r->cam, r->dTileCost);
+    r->prof_end(RT_STAGE_GENERATE);
+    std::vector<unsigned int> cost(n);
+    RT_CUDA(cudaMemcpyAsync(cost.data(), r->dTileCost, (size_t)n * 4, cudaMemcpyDeviceToHost, r->stream));
+    RT_CUDA(cudaStreamSynchronize(r->stream));
+    std::vector<int> order(n);
+    for (int i = 0; i < n; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+    RT_CUDA(cudaMemcpyAsync(r->dTileOrder, order.data(), (size_t)n * 4, cudaMemcpyHostToDevice, r->stream));
+    RT_CUDA(cudaStreamSynchronize(r->stream)); // `order` is pageable host memory
+    r->tileOrderValid = true, r->tileOrderCount = n;
+    return RT_OK;
+}
+
 static rt_status render_pt_streams(rt_renderer* r, int first_spp, int count, int stride)
 {
     const rt_render_params& P = r->params;
@@ -913,8 +1186,17 @@ static rt_status render_pt_streams(rt_renderer* r, int first_spp, int count, int
     // all frames of the call form one pool of nTiles x count streams (int range checked by the caller)
     p.slots = nTiles * count;
     RT_CUDA(cudaMemsetAsync(r->dCount + 6, 0, sizeof(int), r->stream));
+    const int* order = nullptr;
+    if (r->streamLpt)
+    {
+        rt_status st = pt_tile_order(r, p);
+        if (st != RT_OK) return st;
+        order = r->dTileOrder;
+    }
     r->prof_begin();
-    k_pt_streams<<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, nullptr, count, r->dCount + 6);
+    if (r->streamKernel == 1) k_pt_streams<<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
+    else if (r->scene->d.kind == RT_SCENE_TLAS) k_pt_streams2<true><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
+    else k_pt_streams2<false><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
     r->prof_end(RT_STAGE_EXTEND);
     r->paths += (uint64_t)p.slots * 256;
     RT_CUDA(cudaGetLastError());
