@@ -1,0 +1,288 @@
+// rt_b200_adapters.h — C++ host side of the drop-in: the reference's Scene / Renderer surface served by
+// the CUDA library behind include/rt_b200.h.
+//
+// This header is compiled INSIDE the reference's translation unit (after its renderer.h), so it sees
+// the reference's own types (Tmpl8::Ray, float3, mat4, BVHNode, Tri, TLASBVHNode, BLASBVH, Material,
+// Texture, Camera, TheApp).  It contains no reference code; it only walks the containers the
+// reference's loaders and builders filled and calls the C-ABI.
+//
+//   rtb200::GpuScene<FileScene>       replaces FileScene      (infra/scene/file_scene.h, USE_BVH)
+//   rtb200::GpuScene<TLASFileScene>   replaces TLASFileScene  (infra/scene/tlas_file_scene.h, TLAS_USE_BVH)
+//       same BaseScene virtuals (infra/scene/base_scene.h:16-32); FindNearest / IsOccluded run on the
+//       GPU (single-ray calls are an n = 1 batch, plus batched overloads); the remaining queries
+//       (GetHitInfo, GetAlbedo, GetSkyColor, light) are answered by the host scene it owns, whose
+//       loaders / SAH / TLAS builders ran unchanged.
+//   rtb200::GpuRenderer<SceneT, INTEGRATOR>   replaces Renderer : TheApp
+//       (2. WhittedStyle/renderer.h:41-61, 3. PathTracer/renderer.h:29-53): Init / Tick /
+//       ClearAccumulator and the public members accumulator, camera, scene, spp, passes, depthLimit,
+//       energy keep their meaning; Tick renders the frame on the GPU and copies the float4 accumulator
+//       and screen->pixels back, so template.cpp's frame loop (template.cpp:305-338) works unchanged.
+//
+// Errors: the reference reports load failures with std::runtime_error (blas_bvh.cpp:11-14); so do the
+// adapters for every non-RT_OK status (message = rt_last_error()).  There is no CPU fallback: if the
+// library reports RT_ERR_NO_DEVICE the constructor throws.
+//
+// Requirements on the reference side: FileScene built with USE_BVH (README.md:45-51);
+// read access to TLASBVH::tlasNode / nodesUsed (private at tlas_bvh.h:27 — add an accessor or a friend)
+// and to Texture::pixels.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "rt_b200.h"
+
+namespace rtb200 {
+
+inline void check( rt_status st, const char* what )
+{
+	if (st != RT_OK) throw std::runtime_error( std::string( what ) + ": " + rt_last_error() );
+}
+
+static_assert(sizeof( Tmpl8::BVHNode ) == sizeof( rt_bvh_node ), "BVHNode layout (blas_bvh.h:13-20)");
+static_assert(sizeof( Tri ) == sizeof( rt_tri ), "Tri layout (helper.h:6-26)");
+static_assert(sizeof( Tmpl8::TLASBVHNode ) == sizeof( rt_tlas_node ), "TLASBVHNode layout (tlas_bvh.h:7-14)");
+
+// The tables rt_scene_desc points to; alive until rt_scene_create has uploaded them.
+struct FlattenedScene
+{
+	std::vector<rt_blas_desc> blas;
+	std::vector<int32_t> objMaterial;
+	std::vector<rt_material> materials;
+	std::vector<rt_texture> textures;
+	rt_scene_desc desc = {};
+};
+
+inline int AddTexture( FlattenedScene& f, const Tmpl8::Texture* tex )
+{
+	if (!tex || tex->width == 0 || tex->pixels.empty()) return -1;
+	rt_texture t;
+	t.pixels = (const uint32_t*)tex->pixels.data(), t.width = tex->width, t.height = tex->height;
+	f.textures.push_back( t );
+	return (int)f.textures.size() - 1;
+}
+
+// the parts FileScene and TLASFileScene share: skydome, floor plane, light quad, materials
+template <class HostScene> inline void FlattenCommon( HostScene& scene, FlattenedScene& f )
+{
+	rt_scene_desc& d = f.desc;
+	d.skydome_texture = AddTexture( f, &scene.skydome );
+	d.floor_texture = AddTexture( f, scene.primitiveMaterials[1].textureDiffuse.get() );
+	for (Tmpl8::Material* m : scene.materials)
+	{
+		rt_material fm = {};
+		fm.reflectivity = m->reflectivity, fm.refractivity = m->refractivity;
+		fm.absorption[0] = m->absorption.x, fm.absorption[1] = m->absorption.y, fm.absorption[2] = m->absorption.z;
+		fm.albedo[0] = m->albedo.x, fm.albedo[1] = m->albedo.y, fm.albedo[2] = m->albedo.z;
+		fm.is_light = m->isLight ? 1 : 0;
+		fm.texture = AddTexture( f, m->textureDiffuse.get() );
+		f.materials.push_back( fm );
+	}
+	d.floor_n[0] = scene.floor.N.x, d.floor_n[1] = scene.floor.N.y, d.floor_n[2] = scene.floor.N.z;
+	d.floor_d = scene.floor.d, d.floor_invto = scene.floor.invto;
+	memcpy( d.light_T, scene.light.T.cell, 64 ), memcpy( d.light_inv_T, scene.light.invT.cell, 64 );
+	d.light_size = scene.light.size;
+	const float3 lc = scene.GetLightColor(), lp = scene.GetLightPos();
+	d.light_color[0] = lc.x, d.light_color[1] = lc.y, d.light_color[2] = lc.z;
+	d.light_pos[0] = lp.x, d.light_pos[1] = lp.y, d.light_pos[2] = lp.z;
+}
+
+inline void FinishDesc( FlattenedScene& f )
+{
+	rt_scene_desc& d = f.desc;
+	d.blas = f.blas.data(), d.blas_count = (uint32_t)f.blas.size();
+	d.obj_material = f.objMaterial.data(), d.obj_count = (uint32_t)f.objMaterial.size();
+	d.materials = f.materials.data(), d.material_count = (uint32_t)f.materials.size();
+	d.textures = f.textures.data(), d.texture_count = (uint32_t)f.textures.size();
+}
+
+#ifdef USE_BVH
+// FileScene: one flat SAH BVH over every triangle (file_scene.cpp:4-62); the hit takes Tri::objIdx
+inline void Flatten( Tmpl8::FileScene& scene, FlattenedScene& f )
+{
+	f.desc.kind = RT_SCENE_FLAT;
+	rt_blas_desc b = {};
+	b.nodes = (const rt_bvh_node*)scene.acc.bvhNodes.data(), b.node_count = scene.acc.nodesUsed;
+	b.tris = (const rt_tri*)scene.acc.triangles.data(), b.tri_count = (uint32_t)scene.acc.triangles.size();
+	b.tri_indices = (const uint32_t*)scene.acc.triangleIndices.data();
+	const mat4 I;
+	memcpy( b.T, I.cell, 64 ), memcpy( b.inv_T, I.cell, 64 );
+	b.obj_idx = -1, b.mat_idx = -1;
+	f.blas.push_back( b );
+	for (auto* m : scene.models) f.objMaterial.push_back( m->matIdx );
+	FlattenCommon( scene, f );
+	FinishDesc( f );
+}
+#endif
+
+#ifdef TLAS_USE_BVH
+// TLASFileScene: one BLASBVH per <object> (tlas_file_scene.cpp:41-55) under the agglomerative TLAS
+inline void Flatten( Tmpl8::TLASFileScene& scene, FlattenedScene& f )
+{
+	f.desc.kind = RT_SCENE_TLAS;
+	for (Tmpl8::BLASBVH* blas : scene.tlas.blas)
+	{
+		rt_blas_desc b = {};
+		b.nodes = (const rt_bvh_node*)blas->bvhNodes.data(), b.node_count = blas->nodesUsed;
+		b.tris = (const rt_tri*)blas->triangles.data(), b.tri_count = (uint32_t)blas->triangles.size();
+		b.tri_indices = (const uint32_t*)blas->triangleIndices.data();
+		memcpy( b.T, blas->T.cell, 64 ), memcpy( b.inv_T, blas->invT.cell, 64 );
+		b.obj_idx = blas->objIdx, b.mat_idx = blas->matIdx;
+		f.blas.push_back( b );
+		f.objMaterial.push_back( blas->matIdx );
+	}
+	f.desc.tlas_nodes = (const rt_tlas_node*)scene.tlas.tlasNode;
+	f.desc.tlas_node_count = scene.tlas.nodesUsed;
+	FlattenCommon( scene, f );
+	FinishDesc( f );
+}
+#endif
+
+// ------------------------------------------------------------------------------------------------
+template <class HostScene> class GpuScene : public Tmpl8::BaseScene
+{
+public:
+	explicit GpuScene( const std::string& filePath, int device = 0 ) : host( filePath )
+	{
+		FlattenedScene f;
+		Flatten( host, f );
+		check( rt_scene_create( &f.desc, device, 0, &dev ), "rt_scene_create" );
+	}
+	GpuScene( const GpuScene& ) = delete;
+	GpuScene& operator=( const GpuScene& ) = delete;
+	~GpuScene() { rt_scene_destroy( dev ); }
+	// BaseScene, answered by the host scene (immutable after construction)
+	void SetTime( float t ) override { host.SetTime( t ); }
+	float3 GetSkyColor( const Tmpl8::Ray& ray ) const override { return host.GetSkyColor( ray ); }
+	float3 GetLightPos() const override { return host.GetLightPos(); }
+	float3 GetLightColor() const override { return host.GetLightColor(); }
+	float3 GetAlbedo( int objIdx, float3 I ) const override { return host.GetAlbedo( objIdx, I ); }
+	HitInfo GetHitInfo( const Tmpl8::Ray& ray, const float3 I ) override { return host.GetHitInfo( ray, I ); }
+	int GetTriangleCount() const override { return host.GetTriangleCount(); }
+	// BaseScene, answered by the GPU.  Per-ray, synchronous, in-out by reference like the reference
+	// (bvh.cpp:220 writes t / objIdx / triIdx / barycentric; a miss leaves objIdx == -1, ray.h:36).
+	void FindNearest( Tmpl8::Ray& ray ) override { FindNearest( &ray, 1 ); }
+	bool IsOccluded( const Tmpl8::Ray& ray ) override
+	{
+		uint8_t o = 0;
+		IsOccluded( &ray, 1, &o );
+		return o != 0;
+	}
+	// batched forms: what a caller that owns many rays should use
+	void FindNearest( Tmpl8::Ray* rays, size_t n )
+	{
+		in.resize( n ), out.resize( n );
+		for (size_t i = 0; i < n; i++) Pack( rays[i], in[i] );
+		check( rt_find_nearest( dev, in.data(), out.data(), n ), "rt_find_nearest" );
+		for (size_t i = 0; i < n; i++)
+		{
+			Tmpl8::Ray& r = rays[i];
+			r.t = out[i].t, r.barycentric = float2( out[i].u, out[i].v );
+			r.objIdx = out[i].obj_idx, r.triIdx = out[i].tri_idx;
+			r.traversed = out[i].traversed, r.tested = out[i].tested;
+		}
+	}
+	void IsOccluded( const Tmpl8::Ray* rays, size_t n, uint8_t* occluded )
+	{
+		in.resize( n );
+		for (size_t i = 0; i < n; i++) Pack( rays[i], in[i] );
+		check( rt_is_occluded( dev, in.data(), occluded, n ), "rt_is_occluded" );
+	}
+	rt_scene* Handle() const { return dev; }
+public:
+	HostScene host;
+private:
+	static void Pack( const Tmpl8::Ray& r, rt_ray& p )
+	{
+		p.O[0] = r.O.x, p.O[1] = r.O.y, p.O[2] = r.O.z, p.tmax = r.t;
+		p.D[0] = r.D.x, p.D[1] = r.D.y, p.D[2] = r.D.z, p.inside = r.inside ? 1 : 0;
+	}
+	rt_scene* dev = nullptr;
+	std::vector<rt_ray> in;
+	std::vector<rt_hit> out;
+};
+
+// ------------------------------------------------------------------------------------------------
+template <class HostScene, int INTEGRATOR> class GpuRenderer : public TheApp
+{
+public:
+	explicit GpuRenderer( const std::string& scenePath, int device = 0 ) : scene( scenePath, device ) {}
+	~GpuRenderer()
+	{
+		if (dev) rt_renderer_destroy( dev );
+		if (accumulator) FREE64( accumulator );
+	}
+	// Renderer::Init (renderer.cpp:8-13)
+	void Init() override
+	{
+		accumulator = (float4*)MALLOC64( (size_t)SCRWIDTH * SCRHEIGHT * 16 );
+		memset( accumulator, 0, (size_t)SCRWIDTH * SCRHEIGHT * 16 );
+		rt_render_params p;
+		rt_render_params_default( &p, INTEGRATOR, SCRWIDTH, SCRHEIGHT );
+		p.depth_limit = depthLimit, p.epsilon = EPSILON;
+		check( rt_renderer_create( scene.Handle(), &p, &dev ), "rt_renderer_create" );
+		createdDepthLimit = depthLimit;
+	}
+	// Renderer::ClearAccumulator (3. PathTracer/renderer.cpp:15-18)
+	void ClearAccumulator()
+	{
+		memset( accumulator, 0, (size_t)SCRWIDTH * SCRHEIGHT * 16 );
+		check( rt_renderer_clear( dev ), "rt_renderer_clear" );
+	}
+	// Renderer::Tick (3. PathTracer/renderer.cpp:144-168, 2. WhittedStyle/renderer.cpp:131-190)
+	void Tick( float deltaTime ) override
+	{
+		if (depthLimit != createdDepthLimit) // the UI may change depthLimit between frames
+		{
+			rt_renderer_destroy( dev ), dev = nullptr;
+			FREE64( accumulator );
+			Init();
+		}
+		if (INTEGRATOR == RT_INTEGRATOR_PATH && passes != 1)
+			throw std::runtime_error( "GpuRenderer: passes != 1 is not supported (one sample per pixel per Tick)" );
+		if (animating) scene.SetTime( anim_time += deltaTime * 0.002f ), ClearAccumulator();
+		rt_camera c;
+		Store( c.pos, camera.camPos ), Store( c.top_left, camera.topLeft );
+		Store( c.top_right, camera.topRight ), Store( c.bottom_left, camera.bottomLeft );
+		check( rt_renderer_set_camera( dev, &c ), "rt_renderer_set_camera" );
+		check( rt_renderer_render( dev, spp, 1, 1 ), "rt_renderer_render" );
+		check( rt_renderer_read_accumulator( dev, (float*)accumulator ), "rt_renderer_read_accumulator" );
+		const float scale = INTEGRATOR == RT_INTEGRATOR_PATH ? 1.0f / (spp + passes) : 1.0f; // renderer.cpp:119
+		if (screen) check( rt_renderer_read_pixels( dev, scale, (uint32_t*)screen->pixels ), "rt_renderer_read_pixels" );
+		if (INTEGRATOR == RT_INTEGRATOR_PATH)
+		{
+			if (camera.HandleInput( deltaTime )) ClearAccumulator();
+			else spp += passes;
+		}
+		else camera.HandleInput( deltaTime );
+	}
+	// `frames` Ticks in one call: all (tile, frame) RNG streams are in flight together on the GPU
+	void Render( int frames )
+	{
+		rt_camera c;
+		Store( c.pos, camera.camPos ), Store( c.top_left, camera.topLeft );
+		Store( c.top_right, camera.topRight ), Store( c.bottom_left, camera.bottomLeft );
+		check( rt_renderer_set_camera( dev, &c ), "rt_renderer_set_camera" );
+		check( rt_renderer_render( dev, spp, frames, 1 ), "rt_renderer_render" );
+		check( rt_renderer_read_accumulator( dev, (float*)accumulator ), "rt_renderer_read_accumulator" );
+		if (INTEGRATOR == RT_INTEGRATOR_PATH) spp += frames * passes;
+	}
+	rt_renderer* Handle() const { return dev; }
+	// data members, as in the reference's Renderer
+	int2 mousePos;
+	float4* accumulator = nullptr;
+	GpuScene<HostScene> scene;
+	Tmpl8::Camera camera;
+	int spp = 1, passes = 1;
+	bool animating = false;
+	float energy = 0, anim_time = 0;
+	int depthLimit = 5;
+private:
+	static void Store( float* p, const float3& v ) { p[0] = v.x, p[1] = v.y, p[2] = v.z; }
+	rt_renderer* dev = nullptr;
+	int createdDepthLimit = -1;
+};
+
+} // namespace rtb200

@@ -120,7 +120,7 @@ def patch_sources(d, integrator, big_tlas):
         edit("renderer.cpp", lambda s: sub(sub(s, r'system\("cls"\);', "", "cls"), r'\n\s*printf\("(Total|Average|Peak)[^\n]*', "", "prints", min_hits=6))
 
 
-def build_variant(integrator, scene_kind, cxx="g++", extra_flags=(), suffix="", big_tlas=False, verbose=False):
+def build_variant(integrator, scene_kind, cxx="g++", extra_flags=(), suffix="", big_tlas=False, verbose=False, gpuhost=False):
     os.makedirs(OUT, exist_ok=True)
     d = tempfile.mkdtemp(prefix="ref_build_")
     try:
@@ -142,14 +142,24 @@ def build_variant(integrator, scene_kind, cxx="g++", extra_flags=(), suffix="", 
                         "file_scene.cpp", "tlas_file_scene.cpp", "renderer.cpp"]:
                 f.write(f'#include "{src}"\n')
             f.write(f'#include "{os.path.join(HERE, "ref_api.cpp")}"\n')
-        out = os.path.join(OUT, f"libref_{integrator}_{scene_kind}{suffix}.so")
-        cmd = [cxx, "-std=c++17", "-O2", "-fopenmp", "-msse4.1", "-ffp-contract=off", "-fpermissive", "-w",
+            if gpuhost:
+                f.write(f'#include "{os.path.join(HERE, "gpuhost_api.cpp")}"\n')
+        out = os.path.join(OUT, f"lib{'gpuhost' if gpuhost else 'ref'}_{integrator}_{scene_kind}{suffix}.so")
+        if gpuhost:
+            # the C++ drop-in adapters (cpu-ray-tracer_b200/host) + the CUDA library behind the C-ABI
+            pkg = os.path.join(REPO, "cpu-ray-tracer_b200")
+            extra_flags = (*extra_flags, "-I" + os.path.join(REPO, "include"), "-I" + os.path.join(pkg, "host"),
+                           "-L" + pkg, "-lrt_b200", "-Wl,-rpath,$ORIGIN/../../cpu-ray-tracer_b200")
+        cmd = [cxx, "-std=c++17", "-O2", "-fopenmp", "-msse4.1", "-ffp-contract=off", "-fpermissive", "-w", "-Wno-psabi",
                "-shared", "-fPIC", *extra_flags,
                f"-DREF_SCENE_TYPE={SCENE_TYPES[scene_kind]}",
                f"-DREF_INTEGRATOR_{integrator.upper()}=1", f"-DREF_SCENE_{scene_kind.upper()}=1",
                "-I" + os.path.join(HERE, "shim"), "-I" + d,
                "-I" + os.path.join(REF, "lib"), "-I" + os.path.join(REF, "lib", "rapidxml-1.13"),
                unity, "-o", out]
+        if gpuhost:  # libraries after the object that needs them
+            libs = [f for f in cmd if f.startswith(("-L", "-l", "-Wl,"))]
+            cmd = [f for f in cmd if f not in libs] + libs
         if verbose:
             print(" ".join(cmd))
         subprocess.run(cmd, check=True)
@@ -158,7 +168,7 @@ def build_variant(integrator, scene_kind, cxx="g++", extra_flags=(), suffix="", 
         shutil.rmtree(d, ignore_errors=True)
 
 
-def build_all(verbose=False):
+def build_all(verbose=False, gpuhost=True):
     if not os.path.isdir(REF):
         raise FileNotFoundError(f"{REF} not present: oracle/_ref can only be (re)built where the reference is mounted")
     outs = []
@@ -169,9 +179,18 @@ def build_all(verbose=False):
     # (whitted-style-bvh.vcxproj:93-102); not a parity oracle
     for kind in ("file", "tlas"):
         outs.append(build_variant("pt", kind, extra_flags=("-O3", "-mavx2", "-mfma", "-ffast-math"), suffix="_fast", verbose=verbose))
+    if gpuhost:
+        outs += build_gpuhost(verbose=verbose)
     return outs
 
 
+def build_gpuhost(verbose=False):
+    """libgpuhost_*: the reference's loaders/builders + our C++ adapters + librt_b200.so (drop-in check)"""
+    if not os.path.exists(os.path.join(REPO, "cpu-ray-tracer_b200", "librt_b200.so")):
+        raise FileNotFoundError("build cpu-ray-tracer_b200/librt_b200.so first (python __graft_entry__.py)")
+    return [build_variant(integ, kind, verbose=verbose, gpuhost=True) for integ in ("whitted", "pt") for kind in ("file", "tlas")]
+
+
 if __name__ == "__main__":
-    for o in build_all(verbose="-v" in sys.argv):
+    for o in (build_gpuhost(verbose="-v" in sys.argv) if "gpuhost" in sys.argv else build_all(verbose="-v" in sys.argv)):
         print("built", o)
