@@ -31,7 +31,7 @@ EXPORTS = [
     "rt_renderer_read_accumulator", "rt_renderer_read_pixels", "rt_renderer_device_accumulator",
     "rt_renderer_get_counters", "rt_renderer_reset_counters",
     "rt_renderer_set_profiling", "rt_renderer_get_stage_times", "rt_renderer_get_launch_spans",
-    "rt_renderer_get_queue_history",
+    "rt_renderer_get_queue_history", "rt_measure_gather_bandwidth",
 ]
 
 
@@ -87,6 +87,7 @@ def lib():
     L.rt_renderer_get_stage_times.argtypes = [vp, C.POINTER(abi.rt_stage_times)]
     L.rt_renderer_get_launch_spans.argtypes = [vp, vp, vp, sz, C.POINTER(sz)]
     L.rt_renderer_get_queue_history.argtypes = [vp, vp, sz, C.POINTER(sz)]
+    L.rt_measure_gather_bandwidth.argtypes = [i32, sz, i32, C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -98,6 +99,13 @@ def _check(status):
 
 def device_count():
     return lib().rt_device_count()
+
+
+def measure_gather_bandwidth(working_set_bytes, bypass_l1=True, device=0):
+    """GB/s of random 64-byte gathers over a working set (L2 roofline denominator for L2-resident scenes)"""
+    out = C.c_double()
+    _check(lib().rt_measure_gather_bandwidth(device, working_set_bytes, 1 if bypass_l1 else 0, C.byref(out)))
+    return out.value
 
 
 class Camera:

@@ -34,7 +34,24 @@ def up_to_date():
     return all(os.path.getmtime(d) <= t for d in deps)
 
 
+HOST_LIB = os.path.join(HERE, "librt_host.so")
+HOST_SRC = os.path.join(HERE, "host", "bvh_build.cpp")
+
+
+def build_host(force=False, verbose=False):
+    """host-side builders (reference SAH BVH / TLAS restated): plain g++, strict IEEE like the oracle build"""
+    deps = [HOST_SRC, os.path.join(HERE, "..", "include", "rt_b200.h")]
+    if not force and os.path.exists(HOST_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(HOST_LIB) for d in deps):
+        return HOST_LIB
+    cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", HOST_SRC, "-o", HOST_LIB]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    return HOST_LIB
+
+
 def build(force=False, verbose=False, extra=()):
+    build_host(force, verbose)
     if not force and up_to_date():
         return LIB
     cmd = [nvcc(), *NVCC_FLAGS, *extra, *[os.path.join(CSRC, f) for f in SOURCES], "-o", LIB]

@@ -94,6 +94,41 @@ __global__ void __launch_bounds__(128) k_is_occluded_persistent(const DScene s, 
     trace_queue<true, false>(s, src, n, fetch);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Roofline denominator for L2-resident scenes: random 64-byte record gathers (the size and alignment of
+// one fat BVH node) over a working set, every thread keeping `ILP` independent gathers in flight.
+// bypassL1 = ld.global.cg (L2 bandwidth as the traversal sees it on an L1 miss); otherwise ld.global.nc.
+// ------------------------------------------------------------------------------------------------
+template <bool BYPASS_L1>
+__global__ void __launch_bounds__(256) k_gather64(const float4* __restrict__ data, unsigned recordMask, int iters, float* __restrict__ sink)
+{
+    unsigned h = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    float acc = 0;
+    for (int i = 0; i < iters; i++)
+    {
+        unsigned idx[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+        {
+            h ^= h << 13, h ^= h >> 17, h ^= h << 5;
+            idx[j] = h & recordMask;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+        {
+            const float4* r = data + 4 * (size_t)idx[j];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+            {
+                const float4 v = BYPASS_L1 ? __ldcg(r + q) : __ldg(r + q);
+                acc += v.x + v.w;
+            }
+        }
+    }
+    if (acc == 123.456f) *sink = acc; // keep the loads alive
+}
+
 static int grid_for(size_t n, int block, int device)
 {
     int sms = 148;
@@ -282,14 +317,26 @@ rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags,
     Builder B;
     std::vector<int> rootRefs(desc->blas_count);
     std::vector<int> triBase(desc->blas_count);
+    std::vector<uint32_t> firstOfGeometry; // distinct meshes seen so far (bounded: scenes share a handful)
     for (uint32_t i = 0; i < desc->blas_count; i++)
     {
         const rt_blas_desc& b = desc->blas[i];
         if (!b.nodes || !b.tris || !b.tri_indices) { set_error("rt_scene_create: BLAS with null arrays"); return RT_ERR_INVALID; }
-        triBase[i] = (int)(B.tris.size() / 3);
-        rootRefs[i] = B.add_bvh(b, triBase[i]);
-        if (B.error.empty()) B.add_tris(b);
-        if (!B.error.empty()) { set_error("rt_scene_create: " + B.error); return RT_ERR_INVALID; }
+        // true instancing: BLAS descriptors that point at the same reference arrays share
+        // one device copy of nodes / triangles / shading records; only the 2 x 64-byte instance records differ
+        int shared = -1;
+        for (uint32_t j : firstOfGeometry)
+            if (desc->blas[j].nodes == b.nodes && desc->blas[j].tris == b.tris && desc->blas[j].tri_indices == b.tri_indices &&
+                desc->blas[j].node_count == b.node_count && desc->blas[j].tri_count == b.tri_count) { shared = (int)j; break; }
+        if (shared >= 0) triBase[i] = triBase[shared], rootRefs[i] = rootRefs[shared];
+        else
+        {
+            triBase[i] = (int)(B.tris.size() / 3);
+            rootRefs[i] = B.add_bvh(b, triBase[i]);
+            if (B.error.empty()) B.add_tris(b);
+            if (!B.error.empty()) { set_error("rt_scene_create: " + B.error); return RT_ERR_INVALID; }
+            if (firstOfGeometry.size() < 64) firstOfGeometry.push_back(i);
+        }
         const float* M = b.inv_T;
         B.inst.push_back(Builder::f4(M[0], M[1], M[2], M[3]));
         B.inst.push_back(Builder::f4(M[4], M[5], M[6], M[7]));
@@ -472,6 +519,46 @@ rt_status rt_is_occluded(rt_scene* s, const rt_ray* rays, uint8_t* occluded, siz
 }
 
 // Camera::Camera() camera.h:12-21
+
+rt_status rt_measure_gather_bandwidth(int device, size_t working_set_bytes, int bypass_l1, double* gb_per_s)
+{
+    if (!gb_per_s || working_set_bytes < 64) { set_error("rt_measure_gather_bandwidth: bad argument"); return RT_ERR_INVALID; }
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) { set_error("no such CUDA device (there is no CPU fallback)"); return RT_ERR_NO_DEVICE; }
+    RT_CUDA(cudaSetDevice(device));
+    size_t records = 1;
+    while (records * 2 * 64 <= working_set_bytes) records *= 2; // power of two number of 64-byte records
+    float4* data = nullptr;
+    float* sink = nullptr;
+    RT_CUDA(cudaMalloc((void**)&data, records * 64));
+    RT_CUDA(cudaMalloc((void**)&sink, 4));
+    RT_CUDA(cudaMemset(data, 0, records * 64));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const int grid = sms * 8, block = 256, iters = 64;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a), cudaEventCreate(&b);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++)
+    {
+        cudaEventRecord(a);
+        if (bypass_l1) k_gather64<true><<<grid, block>>>(data, (unsigned)(records - 1), iters, sink);
+        else k_gather64<false><<<grid, block>>>(data, (unsigned)(records - 1), iters, sink);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        if (rep > 0 && ms < best) best = ms; // first launch warms the set into L2
+    }
+    cudaEventDestroy(a), cudaEventDestroy(b);
+    cudaError_t e = cudaGetLastError();
+    cudaFree(data), cudaFree(sink);
+    if (!cuda_ok(e, "k_gather64")) return RT_ERR_CUDA;
+    const double bytes = (double)grid * block * iters * 4 * 64;
+    *gb_per_s = bytes / (best * 1e-3) / 1e9;
+    return RT_OK;
+}
+
 void rt_camera_default(rt_camera* c, int width, int height)
 {
     const float aspect = (float)width / (float)height;

@@ -267,6 +267,14 @@ rt_status rt_renderer_get_launch_spans(rt_renderer* r, int32_t* stage, float* ms
 /* Path tracer: number of queued rays at every wavefront iteration of the last rt_renderer_render batch. */
 rt_status rt_renderer_get_queue_history(rt_renderer* r, int32_t* rays_per_iteration, size_t capacity, size_t* n);
 
+/* ---- diagnostics ------------------------------------------------------------------------------ */
+
+/* Measured bandwidth of random 64-byte record gathers (the size and alignment of one device BVH node) over
+ * a working set of `working_set_bytes` (rounded down to a power of two): the roofline denominator for
+ * scenes whose geometry is L2-resident (SURVEY.md section 8d asks for a measured L2 peak).  bypass_l1 != 0
+ * uses ld.global.cg.  No reference equivalent (the reference has no memory-hierarchy instrumentation). */
+rt_status rt_measure_gather_bandwidth(int device, size_t working_set_bytes, int bypass_l1, double* gb_per_s);
+
 #ifdef __cplusplus
 }
 #endif

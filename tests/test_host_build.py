@@ -1,0 +1,65 @@
+"""Host-side builders (cpu-ray-tracer_b200/host/bvh_build.cpp) reproduce the reference's builders bit for bit:
+fed the triangles of scenes the reference itself loaded and built (tests/golden, oracle/_ref/scenes), they
+must return the reference's node arrays, triangle order, instance inverses, world bounds and TLAS."""
+import numpy as np
+import pytest
+
+from conftest import all_scene_names, biteq
+
+from cpu_ray_tracer_b200 import abi, host_build
+
+
+def raw_equal(a, b):
+    return a.shape == b.shape and a.tobytes() == b.tobytes()
+
+
+@pytest.mark.parametrize("name", all_scene_names())
+def test_sah_builder_matches_reference(name, flat_scenes):
+    fs = flat_scenes(name)
+    for b in fs.blas_table:
+        t0, tn = int(b["tri_offset"]), int(b["tri_count"])
+        n0, nn = int(b["node_offset"]), int(b["node_count"])
+        tris = fs.tris[t0:t0 + tn]
+        nodes, idx, _ = host_build.build_bvh(tris)
+        assert len(nodes) == nn
+        assert raw_equal(idx, fs.tri_indices[t0:t0 + tn]), "triangle order differs from BVH::Build"
+        ref = fs.nodes[n0:n0 + nn]
+        for f in ("aabb_min", "aabb_max"):
+            assert biteq(nodes[f], ref[f]), f
+        assert np.array_equal(nodes["left_first"], ref["left_first"]) and np.array_equal(nodes["tri_count"], ref["tri_count"])
+
+
+@pytest.mark.parametrize("name", [n for n in all_scene_names() if n.endswith("tlas")])
+def test_tlas_builder_and_transforms_match_reference(name, flat_scenes):
+    fs = flat_scenes(name)
+    bounds = []
+    for b in fs.blas_table:
+        assert biteq(host_build.invert_rigid(b["T"]), b["inv_T"]), "FastInvertedTransformNoScale"
+        root = fs.nodes[int(b["node_offset"])]
+        bounds.append(host_build.world_bounds(root["aabb_min"], root["aabb_max"], b["T"]))
+    tlas = host_build.build_tlas(np.array(bounds))
+    assert len(tlas) == len(fs.tlas_nodes)
+    for f in ("aabb_min", "aabb_max"):
+        assert biteq(tlas[f], fs.tlas_nodes[f]), f
+    assert np.array_equal(tlas["left_right"], fs.tlas_nodes["left_right"])
+    leaf = tlas["left_right"] == 0   # interior nodes never set BLAS: the reference leaves malloc garbage there
+    assert np.array_equal(tlas["blas"][leaf], fs.tlas_nodes["blas"][leaf])
+
+
+def test_synthetic_scenes_are_well_formed_and_oracle_traceable():
+    from oracle import porthost
+    tris = host_build.terrain_mesh(5000, seed=3)
+    fs = host_build.flat_scene_from_tris(tris)
+    assert fs.kind == abi.RT_SCENE_FLAT and len(fs.nodes) <= 2 * len(tris) - 1
+    po = porthost.PortOracle(fs)
+    W, H = 64, 40
+    hits, st = po.find_nearest(po.primary_rays(po.camera_default(W, H), W, H))
+    assert (hits["obj_idx"] >= 2).mean() > 0.1
+    inst = host_build.instanced_grid(tris[:600], 27)
+    assert inst.kind == abi.RT_SCENE_TLAS and len(inst.blas_table) == 27 and len(inst.tlas_nodes) == 2 * 27
+    assert len(inst.tris) == 600                      # ONE copy of the mesh, 27 instances
+    po = porthost.PortOracle(inst)
+    hits, st = po.find_nearest(po.primary_rays(po.camera_default(W, H), W, H))
+    assert (hits["obj_idx"] >= 2).any() and st["blas_entries"] > 0
+    with pytest.raises(ValueError):
+        host_build.build_tlas(np.zeros((40000, 6), np.float32))   # 2 x 16-bit child indices
