@@ -1182,6 +1182,238 @@ __global__ void __launch_bounds__(128) k_pt_streams4(const PTState p, const DSce
     if (lane == 0) atomicAdd(p.counters, (unsigned long long)rays);
 }
 
+// Stream kernel, version 5 = version 2 (one stream per lane, state in registers, ballot vote) with what the
+// source-level profile of version 2 asked for (tools/ncu_source_hot.py on profiles/r1_v4_*):
+//   * MISS is voted separately from surface shading: sky lookups (atan2f / acosf / texel) no longer
+//     serialise against hit_info + lobe code inside one SHADE action (shading ran at 6.9 of 32 lanes);
+//   * one copy of "finish the sample, next pixel" and one copy of the FindNearest prologue, behind flags,
+//     instead of one per branch; the tile origin is kept in a register instead of tile % tilesX per sample;
+//   * a NODE action keeps stepping without a re-vote while >= 3/4 of the lanes that entered it are still in
+//     NODE (the vote was 10 % of all warp instructions), and the step itself selects instead of branching
+//     (the stack pop ran at 2.2 lanes behind its own BSSY / BSYNC pair);
+//   * every finished stream adds its duration (clock64) to its tile's cost: the next render call of the same
+//     view sorts tiles by MEASURED cost instead of the 16-path pilot estimate (longest-first hand-out).
+// Versions 3 (six REDUX-voted states) and 4 (K streams per lane in local memory) were measured slower
+// (profiles/r1_stream_kernel_*): more vote rounds per ray and L1 thrashing outweighed the better lane use.
+enum { ST_MISS = 4 };
+
+template <bool TLAS>
+__global__ void __launch_bounds__(128, 7) k_pt_streams5(const PTState p, const DScene s, const DCamera cam,
+    const int* __restrict__ tileOrder, const int frames, int* __restrict__ streamCounter, unsigned long long* __restrict__ tileCost)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int total = p.slots;
+    const float4* __restrict__ nodes = s.nodes;
+    const float4* __restrict__ tris = s.tris;
+    bool poolEmpty = false;
+    int state = ST_DEAD;
+    // stream
+    int tileXY = 0, pix = 0, depth = 0;
+    bool inside = false;
+    uint32_t seed = 0;
+    unsigned int t0 = 0; // clock() at stream start (32 bit: a stream lasts milliseconds)
+    float3 wO = f3(0, 0, 0), wD = f3(0, 0, 0); // the ray in world space
+    float3 wst[STREAM_MAX_DEPTH];
+    // traversal
+    float3 O = f3(0, 0, 0), D = f3(0, 0, 0), rD = f3(0, 0, 0); // the ray in the space being traversed (TLAS only; flat: wO, wD)
+    bool exact = false;
+    int stack[STACK_SIZE];
+    int sp = 0, cur = 0, instObj = -1;
+    float ht = 0, hu = 0, hv = 0;
+    int hobj = -1, htri = -1;
+    unsigned int rays = 0;
+#define TO (TLAS ? O : wO)
+#define TD (TLAS ? D : wD)
+
+    while (true)
+    {
+        const unsigned mNode = __ballot_sync(FULL, state == ST_NODE);
+        const unsigned mLeaf = __ballot_sync(FULL, state == ST_LEAF);
+        const unsigned mShade = __ballot_sync(FULL, state == ST_SHADE);
+        const unsigned mMiss = __ballot_sync(FULL, state == ST_MISS);
+        const unsigned mLive = mNode | mLeaf | mShade | mMiss;
+        bool start = false;
+        if (mLive != FULL && !poolEmpty)
+        {
+            // refill the dead lanes from the stream pool: one atomic per warp
+            const unsigned mDead = ~mLive;
+            const int nIdle = __popc(mDead);
+            const int leader = __ffs(mDead) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(streamCounter, nIdle);
+            base = __shfl_sync(FULL, base, leader);
+            if (base + nIdle >= total) poolEmpty = true;
+            const int stream = base + __popc(mDead & ((1u << lane) - 1));
+            if (state == ST_DEAD && stream < total)
+            {
+                const int k = stream / frames, frame = stream - k * frames;
+                const int tile = p.tileBegin + (tileOrder ? tileOrder[k] : k);
+                seed = pt_seed(p, tile, p.firstSpp + frame * p.stride);
+                const int tx = tile % p.tilesX, ty = tile / p.tilesX;
+                tileXY = (tx * 16) | ((ty * 16) << 16);
+                pix = 0, depth = 0, inside = false;
+                const float jy = random_float(seed), jx = random_float(seed);
+                wD = primary_dir(cam, (float)(tx * 16) + jx, (float)(ty * 16) + jy);
+                wO = cam.pos;
+                t0 = (unsigned int)clock();
+                start = true;
+            }
+        }
+        else
+        {
+            if (mLive == 0) break;
+            const int nN = __popc(mNode), nL = __popc(mLeaf), nS = __popc(mShade), nM = __popc(mMiss);
+            if (nN >= nL && nN >= nS && nN >= nM)
+            {
+                const int keep = nN - (nN >> 2);
+                do
+                {
+                    if (state == ST_NODE)
+                    {
+                        const float4* nd = nodes + 4 * (size_t)cur;
+                        const float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2);
+                        const int4 n3 = __ldg((const int4*)(nd + 3));
+                        const float a1 = slab(TO, rD, ht, exact, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y);
+                        const float a2 = slab(TO, rD, ht, exact, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w);
+                        // near child first, left on ties; far child pushed only when hit (bvh.cpp:246-257)
+                        const bool swp = a1 > a2;
+                        const float d1 = swp ? a2 : a1, d2 = swp ? a1 : a2;
+                        const int c1 = swp ? n3.y : n3.x, c2 = swp ? n3.x : n3.y;
+                        const bool miss = d1 == 1e30f, both = !miss && d2 != 1e30f;
+                        const int top = stack[sp > 0 ? sp - 1 : 0];
+                        if (both) stack[sp] = c2;
+                        const bool end = miss && sp == 0;
+                        cur = miss ? top : c1;
+                        sp += both ? 1 : (miss && sp > 0 ? -1 : 0);
+                        state = end ? (hobj == -1 ? ST_MISS : ST_SHADE) : (cur >= 0 ? ST_NODE : ST_LEAF);
+                    }
+                } while (__popc(__ballot_sync(FULL, state == ST_NODE)) >= keep);
+            }
+            else if (nL >= nS && nL >= nM)
+            {
+                if (state == ST_LEAF)
+                {
+                    const int payload = ~cur;
+                    bool pop = true;
+                    if (TLAS && payload == SENTINEL_PAYLOAD)
+                    {
+                        O = wO, D = wD, rD = recip(wD), exact = needs_exact_slab(wO, wD); // blas_bvh.cpp:385-388
+                    }
+                    else if (TLAS && (payload & INSTANCE_BIT))
+                    {
+                        const float4* I = s.inst + 4 * (size_t)(payload & ~INSTANCE_BIT);
+                        const float4 r0 = __ldg(I), r1 = __ldg(I + 1), r2 = __ldg(I + 2);
+                        const int4 meta = __ldg((const int4*)(I + 3));
+                        O = f3((wO.x * r0.x + wO.y * r0.y) + (wO.z * r0.z + r0.w),
+                               (wO.x * r1.x + wO.y * r1.y) + (wO.z * r1.z + r1.w),
+                               (wO.x * r2.x + wO.y * r2.y) + (wO.z * r2.z + r2.w));
+                        D = f3((wD.x * r0.x + wD.y * r0.y) + wD.z * r0.z,
+                               (wD.x * r1.x + wD.y * r1.y) + wD.z * r1.z,
+                               (wD.x * r2.x + wD.y * r2.y) + wD.z * r2.z);
+                        rD = recip(D), exact = needs_exact_slab(O, D);
+                        instObj = meta.y;
+                        stack[sp++] = ~SENTINEL_PAYLOAD;
+                        cur = meta.x, state = cur >= 0 ? ST_NODE : ST_LEAF;
+                        pop = false;
+                    }
+                    else
+                    {
+                        int slot = payload;
+                        while (true)
+                        {
+                            const float4* T = tris + 3 * (size_t)slot;
+                            const float4 t0_ = __ldg(T), t1 = __ldg(T + 1), t2 = __ldg(T + 2);
+                            const int tag = __float_as_int(t0_.w);
+                            if (intersect_tri(TO, TD, f3(t0_.x, t0_.y, t0_.z), f3(t1.x, t1.y, t1.z), f3(t2.x, t2.y, t2.z), ht, hu, hv))
+                            {
+                                htri = tag & ~LAST_BIT;
+                                hobj = instObj >= 0 ? instObj : __float_as_int(t1.w);
+                            }
+                            if (tag & LAST_BIT) break;
+                            slot++;
+                        }
+                    }
+                    if (pop)
+                    {
+                        if (sp == 0) state = hobj == -1 ? ST_MISS : ST_SHADE;
+                        else cur = stack[--sp], state = cur >= 0 ? ST_NODE : ST_LEAF;
+                    }
+                }
+            }
+            else
+            {
+                // MISS (sky, renderer.cpp:54) or surface shading, whichever more lanes wait for; then ONE copy
+                // of "sample finished -> splat, next pixel" for the lanes whose path ended
+                const bool doMiss = nM >= nS;
+                bool fin = false;
+                float3 L = f3(0, 0, 0);
+                if (doMiss)
+                {
+                    if (state == ST_MISS) L = sky_color(s, wD), fin = true;
+                }
+                else if (state == ST_SHADE)
+                {
+                    float3 w, I, N, nD;
+                    bool nInside;
+                    const int k = pt_surface(s, p.depthLimit, wO, wD, inside, depth, ht, hu, hv, hobj, htri, seed, L, w, I, N, nD, nInside);
+                    if (k == PT_END) fin = true;
+                    else
+                    {
+                        if (k == PT_DIFF)
+                        {
+                            nD = diffuse_reflection(N, seed);
+                            w = w * dot(nD, N);
+                        }
+                        wst[depth] = w;
+                        depth++, wO = I + nD * p.eps, wD = nD, inside = nInside;
+                        start = true;
+                    }
+                }
+                if (fin)
+                {
+                    for (int d = depth - 1; d >= 0; d--) L = wst[d] * L;
+                    const int x0 = tileXY & 0xffff, y0 = tileXY >> 16;
+                    float* a = (float*)(p.accum + ((x0 + (pix & 15)) + (size_t)(y0 + (pix >> 4)) * p.W)); // renderer.cpp:124
+                    atomicAdd(a + 0, L.x), atomicAdd(a + 1, L.y), atomicAdd(a + 2, L.z);
+                    pix++;
+                    if (pix < 256)
+                    {
+                        const float jy = random_float(seed), jx = random_float(seed);
+                        wD = primary_dir(cam, (float)(x0 + (pix & 15)) + jx, (float)(y0 + (pix >> 4)) + jy);
+                        wO = cam.pos, depth = 0, inside = false;
+                        start = true;
+                    }
+                    else
+                    {
+                        state = ST_DEAD;
+                        if (tileCost) atomicAdd(&tileCost[(y0 >> 4) * p.tilesX + (x0 >> 4) - p.tileBegin], (unsigned long long)((unsigned int)clock() - t0));
+                    }
+                }
+            }
+        }
+        if (start)
+        {
+            // FindNearest prologue for the ray (wO, wD): light quad, floor plane (file_scene.cpp:172-173), then the BVH
+            ht = 1e34f, hu = 0, hv = 0, hobj = -1, htri = -1;
+            float tq;
+            if (quad_test(s, wO, wD, ht, tq)) ht = tq, hobj = 0;
+            const float3 fn = f3(s.floor_n[0], s.floor_n[1], s.floor_n[2]);
+            const float tp = -(dot(wO, fn) + s.floor_d) / (dot(wD, fn));
+            if (tp < ht && tp > 0) ht = tp, hobj = 1;
+            if (TLAS) O = wO, D = wD;
+            rD = recip(wD), exact = needs_exact_slab(wO, wD);
+            sp = 0, cur = s.root_ref, instObj = s.flat_obj_idx;
+            state = cur >= 0 ? ST_NODE : ST_LEAF;
+            rays++;
+        }
+    }
+#undef TO
+#undef TD
+    for (int off = 16; off; off >>= 1) rays += __shfl_xor_sync(FULL, rays, off);
+    if (lane == 0) atomicAdd(p.counters, (unsigned long long)rays);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Whitted wavefront
 // ---------------------------------------------------------------------------------------------
@@ -1487,13 +1719,18 @@ struct rt_renderer {
     bool persistent = true;
     bool useStreams = true;
     int streamCtasPerSm = 8;
-    int streamKernel = 2;
+    int streamKernel = 5;
     int streamK = 2, streamNodeFast = 20;
+    bool streamMeasuredLpt = true;
     bool streamLpt = true;
     int* dTileOrder = nullptr;
     unsigned int* dTileCost = nullptr;
     int tileOrderCapacity = 0, tileOrderCount = 0;
     bool tileOrderValid = false;
+    unsigned long long* dTileClock = nullptr; // per-tile sum of stream durations of the last stream-kernel launch
+    int tileOrderSource = 0;                  // 0 none, 1 pilot estimate, 2 measured durations
+    bool tileClockRecorded = false;
+    int lastStreamFrames = 1;
     std::vector<void*> allocations;
     // whitted
     WhState wh = {};
@@ -1629,9 +1866,12 @@ rt_status rt_renderer_create(rt_scene* scene, const rt_render_params* params, rt
         int occ = 0;
         cudaError_t oe;
         if ((e = getenv("RT_B200_STREAM_K")) != nullptr && atoi(e) > 0) r->streamK = atoi(e);
+        if ((e = getenv("RT_B200_STREAM_MEASURED_LPT")) != nullptr) r->streamMeasuredLpt = atoi(e) != 0;
         if ((e = getenv("RT_B200_STREAM_NODEFAST")) != nullptr && atoi(e) > 0) r->streamNodeFast = atoi(e);
         if (r->streamKernel == 1) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams, 128, 0);
         else if (r->streamKernel == 4) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, streams4_kernel(scene->d.kind == RT_SCENE_TLAS, r->streamK), 128, 0);
+        else if (r->streamKernel == 5 && scene->d.kind == RT_SCENE_TLAS) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams5<true>, 128, 0);
+        else if (r->streamKernel == 5) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams5<false>, 128, 0);
         else if (r->streamKernel == 3 && scene->d.kind == RT_SCENE_TLAS) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams3<true>, 128, 0);
         else if (r->streamKernel == 3) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams3<false>, 128, 0);
         else if (scene->d.kind == RT_SCENE_TLAS) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams2<true>, 128, 0);
@@ -1732,12 +1972,37 @@ static rt_status pt_ensure_slots(rt_renderer* r, int slots)
 static rt_status pt_tile_order(rt_renderer* r, const PTState& p)
 {
     const int n = p.nTiles;
-    if (r->tileOrderValid && r->tileOrderCount == n) return RT_OK;
+    if (r->tileOrderValid && r->tileOrderCount == n)
+    {
+        if (r->tileOrderSource == 1 && r->tileClockRecorded && r->streamMeasuredLpt)
+        {
+            // the previous launch of this view timed every stream: re-sort by measured tile cost, once
+            std::vector<unsigned long long> clk(n);
+            RT_CUDA(cudaMemcpyAsync(clk.data(), r->dTileClock, (size_t)n * 8, cudaMemcpyDeviceToHost, r->stream));
+            RT_CUDA(cudaStreamSynchronize(r->stream));
+            std::vector<int> order(n);
+            for (int i = 0; i < n; i++) order[i] = i;
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return clk[a] > clk[b]; });
+            if (getenv("RT_B200_DEBUG"))
+            {
+                double sum = 0;
+                for (int i = 0; i < n; i++) sum += (double)clk[i];
+                fprintf(stderr, "[rt_b200] measured tile cost (cycles per stream, launch of %d frames): max %.0f  p99 %.0f  median %.0f  mean %.0f\n",
+                    r->lastStreamFrames, (double)clk[order[0]] / r->lastStreamFrames, (double)clk[order[n / 100]] / r->lastStreamFrames,
+                    (double)clk[order[n / 2]] / r->lastStreamFrames, sum / n / r->lastStreamFrames);
+            }
+            RT_CUDA(cudaMemcpyAsync(r->dTileOrder, order.data(), (size_t)n * 4, cudaMemcpyHostToDevice, r->stream));
+            RT_CUDA(cudaStreamSynchronize(r->stream));
+            r->tileOrderSource = 2;
+        }
+        return RT_OK;
+    }
     if (r->tileOrderCapacity < n)
     {
         rt_status st;
         if ((st = ralloc(r, &r->dTileOrder, (size_t)n * 4)) != RT_OK) return st;
         if ((st = ralloc(r, &r->dTileCost, (size_t)n * 4)) != RT_OK) return st;
+        if ((st = ralloc(r, &r->dTileClock, (size_t)n * 8)) != RT_OK) return st;
         r->tileOrderCapacity = n;
     }
     RT_CUDA(cudaMemsetAsync(r->dTileCost, 0, (size_t)n * 4, r->stream));
@@ -1753,6 +2018,7 @@ static rt_status pt_tile_order(rt_renderer* r, const PTState& p)
     RT_CUDA(cudaMemcpyAsync(r->dTileOrder, order.data(), (size_t)n * 4, cudaMemcpyHostToDevice, r->stream));
     RT_CUDA(cudaStreamSynchronize(r->stream)); // `order` is pageable host memory
     r->tileOrderValid = true, r->tileOrderCount = n;
+    r->tileOrderSource = 1, r->tileClockRecorded = false;
     return RT_OK;
 }
 
@@ -1777,6 +2043,15 @@ static rt_status render_pt_streams(rt_renderer* r, int first_spp, int count, int
     }
     r->prof_begin();
     if (r->streamKernel == 1) k_pt_streams<<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
+    else if (r->streamKernel == 5)
+    {
+        // time the streams of this launch only while the tile order still comes from the pilot
+        unsigned long long* clk = (order && r->tileOrderSource == 1 && r->streamMeasuredLpt) ? r->dTileClock : nullptr;
+        if (clk) RT_CUDA(cudaMemsetAsync(clk, 0, (size_t)nTiles * 8, r->stream));
+        if (r->scene->d.kind == RT_SCENE_TLAS) k_pt_streams5<true><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6, clk);
+        else k_pt_streams5<false><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6, clk);
+        if (clk) r->tileClockRecorded = true, r->lastStreamFrames = count;
+    }
     else if (r->streamKernel == 4)
         streams4_kernel(r->scene->d.kind == RT_SCENE_TLAS, r->streamK)<<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6, r->streamNodeFast);
     else if (r->streamKernel == 3 && r->scene->d.kind == RT_SCENE_TLAS) k_pt_streams3<true><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
