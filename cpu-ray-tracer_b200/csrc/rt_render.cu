@@ -335,80 +335,6 @@ __global__ void __launch_bounds__(128) k_pt_shade(const PTState p, const DScene 
 // ---------------------------------------------------------------------------------------------
 constexpr int STREAM_MAX_DEPTH = 8;
 
-__global__ void __launch_bounds__(128) k_pt_streams(const PTState p, const DScene s, const DCamera cam,
-    const int* __restrict__ tileOrder, const int frames, int* __restrict__ streamCounter)
-{
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int total = p.slots;
-    bool alive = false, poolEmpty = false;
-    int tile = 0, pix = 0, depth = 0;
-    bool inside = false;
-    uint32_t seed = 0;
-    float3 O = f3(0, 0, 0), D = f3(0, 0, 0);
-    float3 wst[STREAM_MAX_DEPTH];
-    unsigned long long rays = 0;
-    while (true)
-    {
-        const unsigned idle = __ballot_sync(FULL, !alive);
-        if (idle && !poolEmpty)
-        {
-            const int nIdle = __popc(idle);
-            const int leader = __ffs(idle) - 1;
-            int base = 0;
-            if (lane == leader) base = atomicAdd(streamCounter, nIdle);
-            base = __shfl_sync(FULL, base, leader);
-            if (base + nIdle >= total) poolEmpty = true;
-            const int stream = base + __popc(idle & ((1u << lane) - 1));
-            if (!alive && stream < total)
-            {
-                const int k = stream / frames, frame = stream - k * frames;
-                tile = p.tileBegin + (tileOrder ? tileOrder[k] : k);
-                const int spp = p.firstSpp + frame * p.stride;
-                seed = pt_seed(p, tile, spp);
-                pix = 0, depth = 0, inside = false, alive = true;
-                const int tx = tile % p.tilesX, ty = tile / p.tilesX;
-                const float jy = random_float(seed), jx = random_float(seed);
-                D = primary_dir(cam, (float)(tx * 16) + jx, (float)(ty * 16) + jy);
-                O = cam.pos;
-            }
-        }
-        if (__ballot_sync(FULL, alive) == 0) break;
-        if (alive)
-        {
-            HitRec h;
-            find_nearest<false>(s, O, D, 1e34f, h);
-            rays++;
-            float3 L, w, nO, nD;
-            bool nInside;
-            if (!pt_bounce(s, p.eps, p.depthLimit, O, D, inside, depth, h.t, h.u, h.v, h.obj, h.tri, seed, L, w, nO, nD, nInside))
-            {
-                wst[depth] = w;
-                depth++, O = nO, D = nD, inside = nInside;
-            }
-            else
-            {
-                for (int d = depth - 1; d >= 0; d--) L = wst[d] * L;
-                const int tx = tile % p.tilesX, ty = tile / p.tilesX;
-                const int x = tx * 16 + (pix & 15), y = ty * 16 + (pix >> 4);
-                float* a = (float*)(p.accum + (x + (size_t)y * p.W));
-                atomicAdd(a + 0, L.x), atomicAdd(a + 1, L.y), atomicAdd(a + 2, L.z);
-                pix++;
-                if (pix < 256)
-                {
-                    const int nx = tx * 16 + (pix & 15), ny = ty * 16 + (pix >> 4);
-                    const float jy = random_float(seed), jx = random_float(seed);
-                    D = primary_dir(cam, (float)nx + jx, (float)ny + jy);
-                    O = cam.pos, depth = 0, inside = false;
-                }
-                else alive = false;
-            }
-        }
-    }
-    for (int off = 16; off; off >>= 1) rays += __shfl_xor_sync(FULL, rays, off);
-    if (lane == 0) atomicAdd(p.counters, rays);
-}
-
 // Pilot for the stream schedule: a stream's length is only known when it ends, and a long stream that
 // is handed out late becomes the tail of the whole render (a chain of ~1500 dependent rays).  Sixteen
 // throw-away paths per tile (own seeds, nothing is accumulated) estimate each tile's cost in node
@@ -638,550 +564,6 @@ __global__ void __launch_bounds__(128) k_pt_streams2(const PTState p, const DSce
     if (lane == 0) atomicAdd(p.counters, rays);
 }
 
-// Stream kernel, version 3: six voted states, the winner found with two REDUX adds.
-//
-// ncu on version 2 (profiles/r1_v4_*): 12.9 of 32 lanes per instruction; by region (tools/ncu_source_hot.py)
-// shading 46 % of the warp instructions at 6.9 lanes, node visits 30 % at 15.0, leaves 11 % at 10.2, voting /
-// refill 13 % at 32.  Shading is that thin because one SHADE action serialises sky lookups, surface shading,
-// the rejection loop of the diffuse lobe (RNG at 4 lanes) and two copies of the ray set-up.  Here each of
-// those is its own state, so every piece of code runs with the plurality of the warp's lanes behind it:
-//   START  FindNearest prologue (light quad, floor plane, 1/D)          NODE   one interior-node visit
-//   LEAF   triangle leaf / instance entry / instance exit               MISS   sky lookup, sample done
-//   HIT    surface shading up to the lobe choice (pt_surface)           DIFF   one rejection-sampling draw
-// A finished sample multiplies the stored throughput factors, splats, and generates the next pixel's
-// primary ray from the same RNG stream (-> START) or retires the lane (-> DEAD, refilled from the pool).
-// The per-lane order of node visits, triangle tests and RNG draws is unchanged, so results are bit-identical
-// to versions 1 / 2 and to the wavefront.  The vote is two REDUX.SUM over 6-bit per-state counters instead
-// of four ballots; a NODE action keeps stepping without a re-vote while most of its lanes are still in NODE.
-enum { S_DEAD = 0, S_DIFF = 1, S_HIT = 2, S_MISS = 3, S_START = 4, S_LEAF = 5, S_NODE = 6 };
-
-template <bool TLAS>
-__global__ void __launch_bounds__(128) k_pt_streams3(const PTState p, const DScene s, const DCamera cam,
-    const int* __restrict__ tileOrder, const int frames, int* __restrict__ streamCounter)
-{
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int total = p.slots;
-    const float4* __restrict__ nodes = s.nodes;
-    const float4* __restrict__ tris = s.tris;
-    bool poolEmpty = false;
-    int state = S_DEAD;
-    // stream
-    int tileXY = 0, pix = 0, depth = 0; // tileXY = x0 | y0 << 16: pixel origin of the tile
-    bool inside = false;
-    uint32_t seed = 0;
-    float3 wO = f3(0, 0, 0), wD = f3(0, 0, 0); // the ray in world space (DIFF: hit point and normal)
-    float3 wst[STREAM_MAX_DEPTH];
-    // traversal
-    float3 O = f3(0, 0, 0), D = f3(0, 0, 0), rD = f3(0, 0, 0); // the ray in the space being traversed
-    bool exact = false;
-    int stack[STACK_SIZE];
-    int sp = 0, cur = 0, instObj = -1;
-    float ht = 0, hu = 0, hv = 0;
-    int hobj = -1, htri = -1;
-    unsigned int rays = 0;
-    // flat scenes never leave world space: traverse with (wO, wD) and save six registers
-#define TO (TLAS ? O : wO)
-#define TD (TLAS ? D : wD)
-
-    // the sample of pixel `pix` is complete with leaf radiance L_: renderer.cpp:124 accumulator += sample,
-    // then the next pixel's jittered primary ray (:125-126) or the end of the tile
-#define RT_FINISH_SAMPLE(L_)                                                                   \
-    {                                                                                          \
-        float3 Ls = (L_);                                                                      \
-        for (int d = depth - 1; d >= 0; d--) Ls = wst[d] * Ls;                                 \
-        const int x0 = tileXY & 0xffff, y0 = tileXY >> 16;                                     \
-        float* a = (float*)(p.accum + ((x0 + (pix & 15)) + (size_t)(y0 + (pix >> 4)) * p.W)); \
-        atomicAdd(a + 0, Ls.x), atomicAdd(a + 1, Ls.y), atomicAdd(a + 2, Ls.z);                \
-        pix++;                                                                                 \
-        if (pix < 256)                                                                         \
-        {                                                                                      \
-            const float jy = random_float(seed), jx = random_float(seed);                      \
-            wD = primary_dir(cam, (float)(x0 + (pix & 15)) + jx, (float)(y0 + (pix >> 4)) + jy); \
-            wO = cam.pos, depth = 0, inside = false, state = S_START;                          \
-        }                                                                                      \
-        else state = S_DEAD;                                                                   \
-    }
-
-    while (true)
-    {
-        // ---- vote: per-state lane counts in 6-bit fields (a lane count can be 32) ----
-        const unsigned va = __reduce_add_sync(FULL, state >= S_START ? 1u << (6 * (state - S_START)) : 0u); // START, LEAF, NODE
-        const unsigned vb = __reduce_add_sync(FULL, (state >= S_DIFF && state <= S_MISS) ? 1u << (6 * (state - S_DIFF)) : 0u); // DIFF, HIT, MISS
-        if (!poolEmpty)
-        {
-            const unsigned live = (va & 63) + ((va >> 6) & 63) + ((va >> 12) & 63) + (vb & 63) + ((vb >> 6) & 63) + ((vb >> 12) & 63);
-            if (live < 32)
-            {
-                // refill the dead lanes from the stream pool: one atomic per warp
-                const unsigned mDead = __ballot_sync(FULL, state == S_DEAD);
-                const int nIdle = __popc(mDead);
-                const int leader = __ffs(mDead) - 1;
-                int base = 0;
-                if (lane == leader) base = atomicAdd(streamCounter, nIdle);
-                base = __shfl_sync(FULL, base, leader);
-                if (base + nIdle >= total) poolEmpty = true;
-                const int stream = base + __popc(mDead & ((1u << lane) - 1));
-                if (state == S_DEAD && stream < total)
-                {
-                    const int k = stream / frames, frame = stream - k * frames;
-                    const int tile = p.tileBegin + (tileOrder ? tileOrder[k] : k);
-                    seed = pt_seed(p, tile, p.firstSpp + frame * p.stride);
-                    const int tx = tile % p.tilesX, ty = tile / p.tilesX;
-                    tileXY = (tx * 16) | ((ty * 16) << 16);
-                    pix = 0, depth = 0, inside = false;
-                    const float jy = random_float(seed), jx = random_float(seed);
-                    wD = primary_dir(cam, (float)(tx * 16) + jx, (float)(ty * 16) + jy);
-                    wO = cam.pos;
-                    state = S_START;
-                }
-                continue;
-            }
-        }
-        else if ((va | vb) == 0) break;
-        // winner = state with the most lanes; ties go to the higher state id (NODE first)
-        int best = ((va & 63) << 3) | S_START;
-        best = max(best, (int)(((va >> 6) & 63) << 3) | S_LEAF);
-        best = max(best, (int)(((va >> 12) & 63) << 3) | S_NODE);
-        best = max(best, (int)((vb & 63) << 3) | S_DIFF);
-        best = max(best, (int)(((vb >> 6) & 63) << 3) | S_HIT);
-        best = max(best, (int)(((vb >> 12) & 63) << 3) | S_MISS);
-        const int action = best & 7;
-
-        if (action == S_NODE)
-        {
-            const int keep = (best >> 3) - (best >> 5); // stay in the node loop while >= 3/4 of the entry lanes are in NODE
-            do
-            {
-                if (state == S_NODE)
-                {
-                    const float4* nd = nodes + 4 * (size_t)cur;
-                    const float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2);
-                    const int4 n3 = __ldg((const int4*)(nd + 3));
-                    float d1 = slab(TO, rD, ht, exact, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y);
-                    float d2 = slab(TO, rD, ht, exact, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w);
-                    int c1 = n3.x, c2 = n3.y;
-                    if (d1 > d2) { const float tf = d1; d1 = d2; d2 = tf; const int tc = c1; c1 = c2; c2 = tc; }
-                    if (d1 == 1e30f)
-                    {
-                        if (sp == 0) state = hobj == -1 ? S_MISS : S_HIT;
-                        else cur = stack[--sp], state = cur >= 0 ? S_NODE : S_LEAF;
-                    }
-                    else
-                    {
-                        cur = c1, state = c1 >= 0 ? S_NODE : S_LEAF;
-                        if (d2 != 1e30f) stack[sp++] = c2;
-                    }
-                }
-            } while (__popc(__ballot_sync(FULL, state == S_NODE)) >= keep && keep > 0);
-        }
-        else if (action == S_LEAF)
-        {
-            if (state == S_LEAF)
-            {
-                const int payload = ~cur;
-                bool pop = true;
-                if (TLAS && payload == SENTINEL_PAYLOAD)
-                {
-                    O = wO, D = wD, rD = recip(wD), exact = needs_exact_slab(wO, wD); // blas_bvh.cpp:385-388
-                }
-                else if (TLAS && (payload & INSTANCE_BIT))
-                {
-                    const float4* I = s.inst + 4 * (size_t)(payload & ~INSTANCE_BIT);
-                    const float4 r0 = __ldg(I), r1 = __ldg(I + 1), r2 = __ldg(I + 2);
-                    const int4 meta = __ldg((const int4*)(I + 3));
-                    O = f3((wO.x * r0.x + wO.y * r0.y) + (wO.z * r0.z + r0.w),
-                           (wO.x * r1.x + wO.y * r1.y) + (wO.z * r1.z + r1.w),
-                           (wO.x * r2.x + wO.y * r2.y) + (wO.z * r2.z + r2.w));
-                    D = f3((wD.x * r0.x + wD.y * r0.y) + wD.z * r0.z,
-                           (wD.x * r1.x + wD.y * r1.y) + wD.z * r1.z,
-                           (wD.x * r2.x + wD.y * r2.y) + wD.z * r2.z);
-                    rD = recip(D), exact = needs_exact_slab(O, D);
-                    instObj = meta.y;
-                    stack[sp++] = ~SENTINEL_PAYLOAD;
-                    cur = meta.x, state = cur >= 0 ? S_NODE : S_LEAF;
-                    pop = false;
-                }
-                else
-                {
-                    int slot = payload;
-                    while (true)
-                    {
-                        const float4* T = tris + 3 * (size_t)slot;
-                        const float4 t0 = __ldg(T), t1 = __ldg(T + 1), t2 = __ldg(T + 2);
-                        const int tag = __float_as_int(t0.w);
-                        if (intersect_tri(TO, TD, f3(t0.x, t0.y, t0.z), f3(t1.x, t1.y, t1.z), f3(t2.x, t2.y, t2.z), ht, hu, hv))
-                        {
-                            htri = tag & ~LAST_BIT;
-                            hobj = instObj >= 0 ? instObj : __float_as_int(t1.w);
-                        }
-                        if (tag & LAST_BIT) break;
-                        slot++;
-                    }
-                }
-                if (pop)
-                {
-                    if (sp == 0) state = hobj == -1 ? S_MISS : S_HIT;
-                    else cur = stack[--sp], state = cur >= 0 ? S_NODE : S_LEAF;
-                }
-            }
-        }
-        else if (action == S_START)
-        {
-            if (state == S_START)
-            {
-                // FindNearest prologue for the ray (wO, wD): light quad, floor plane (file_scene.cpp:172-173)
-                ht = 1e34f, hu = 0, hv = 0, hobj = -1, htri = -1;
-                float tq;
-                if (quad_test(s, wO, wD, ht, tq)) ht = tq, hobj = 0;
-                const float3 fn = f3(s.floor_n[0], s.floor_n[1], s.floor_n[2]);
-                const float tp = -(dot(wO, fn) + s.floor_d) / (dot(wD, fn));
-                if (tp < ht && tp > 0) ht = tp, hobj = 1;
-                if (TLAS) O = wO, D = wD;
-                rD = recip(wD), exact = needs_exact_slab(wO, wD);
-                sp = 0, cur = s.root_ref, instObj = s.flat_obj_idx;
-                state = cur >= 0 ? S_NODE : S_LEAF;
-                rays++;
-            }
-        }
-        else if (action == S_MISS)
-        {
-            if (state == S_MISS)
-            {
-                const float3 L = sky_color(s, wD); // renderer.cpp:54
-                RT_FINISH_SAMPLE(L);
-            }
-        }
-        else if (action == S_HIT)
-        {
-            if (state == S_HIT)
-            {
-                float3 L, w, I, N, nD;
-                bool nInside;
-                const int k = pt_surface(s, p.depthLimit, wO, wD, inside, depth, ht, hu, hv, hobj, htri, seed, L, w, I, N, nD, nInside);
-                if (k == PT_END) RT_FINISH_SAMPLE(L)
-                else
-                {
-                    wst[depth] = w;
-                    if (k == PT_NEXT) depth++, wO = I + nD * p.eps, wD = nD, inside = nInside, state = S_START;
-                    else wO = I, wD = N, state = S_DIFF;
-                }
-            }
-        }
-        else // S_DIFF: one draw of diffusereflection's rejection loop (tmplmath.h:535-544)
-        {
-            if (state == S_DIFF)
-            {
-                const float rz = random_float(seed) * 2 - 1;
-                const float ry = random_float(seed) * 2 - 1;
-                const float rx = random_float(seed) * 2 - 1;
-                float3 R = f3(rx, ry, rz);
-                if (!(dot(R, R) > 1))
-                {
-                    if (dot(R, wD) < 0) R = R * -1.0f;
-                    R = normalize(R);
-                    wst[depth] = wst[depth] * dot(R, wD); // renderer.cpp:98, the last factor
-                    depth++, wO = wO + R * p.eps, wD = R, inside = false, state = S_START;
-                }
-            }
-        }
-    }
-#undef RT_FINISH_SAMPLE
-#undef TO
-#undef TD
-    for (int off = 16; off; off >>= 1) rays += __shfl_xor_sync(FULL, rays, off);
-    if (lane == 0) atomicAdd(p.counters, (unsigned long long)rays);
-}
-
-// Stream kernel, version 4: K streams per lane.
-//
-// Measured on versions 2 / 3 (gpurun_out/pt_time4.log): throughput grows almost linearly with the resident
-// CTAs per SM (2 -> 1.95, 4 -> 3.3, 6 -> 4.4, 7 -> 4.75 Grays/s at 256 spp), i.e. a warp is bound by the latency of
-// its own vote -> action -> vote chain, and most lanes sit out most actions (12.9 of 32 active).  More vote
-// rounds per ray (version 3) made it slower.  So instead of finer states, every lane owns K streams: the
-// parked streams live in local memory (L1), and for the voted action a lane runs whichever of its streams
-// is in that state.  A lane takes part in an action with probability 1 - (1 - p)^K instead of p.
-// States and per-stream order of node visits / triangle tests / RNG draws are those of version 2.
-struct LaneStream {
-    float3 wO, wD, rD;       // world-space ray, 1 / direction of the space being traversed
-    float ht, hu, hv;        // best hit so far
-    int hobj, htri;
-    int cur, sp;
-    uint32_t seed;
-    int tileXY, misc;        // misc = pix | depth << 9 | inside << 13 | exact << 14
-    float3 O, D;             // TLAS only: the ray in the space being traversed
-    int instObj;
-    int stack[STACK_SIZE];
-    float3 wst[STREAM_MAX_DEPTH];
-};
-
-template <bool TLAS, int K>
-__global__ void __launch_bounds__(128) k_pt_streams4(const PTState p, const DScene s, const DCamera cam,
-    const int* __restrict__ tileOrder, const int frames, int* __restrict__ streamCounter, const int nodeFast)
-{
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int total = p.slots;
-    const float4* __restrict__ nodes = s.nodes;
-    const float4* __restrict__ tris = s.tris;
-    LaneStream st[K];
-    int state[K];
-#pragma unroll
-    for (int k = 0; k < K; k++) state[k] = ST_DEAD;
-    bool poolEmpty = false;
-    unsigned int rays = 0, iter = 0;
-
-#define RT4_SET_STATE(k_, v_)                                   \
-    {                                                           \
-        _Pragma("unroll") for (int kk = 0; kk < K; kk++)        \
-            if (kk == (k_)) state[kk] = (v_);                   \
-    }
-    // FindNearest prologue for the ray (wO, wD) of stream S_ (file_scene.cpp:172-173); -> NODE / LEAF
-#define RT4_START_RAY(S_, wO_, wD_, newState_)                                                 \
-    {                                                                                          \
-        float ht_ = 1e34f;                                                                     \
-        int hobj_ = -1;                                                                        \
-        float tq;                                                                              \
-        if (quad_test(s, wO_, wD_, ht_, tq)) ht_ = tq, hobj_ = 0;                              \
-        const float3 fn = f3(s.floor_n[0], s.floor_n[1], s.floor_n[2]);                        \
-        const float tp = -(dot(wO_, fn) + s.floor_d) / (dot(wD_, fn));                         \
-        if (tp < ht_ && tp > 0) ht_ = tp, hobj_ = 1;                                           \
-        S_.ht = ht_, S_.hu = 0, S_.hv = 0, S_.hobj = hobj_, S_.htri = -1;                      \
-        S_.wO = wO_, S_.wD = wD_, S_.rD = recip(wD_);                                          \
-        if (TLAS) S_.O = wO_, S_.D = wD_, S_.instObj = s.flat_obj_idx;                         \
-        S_.sp = 0, S_.cur = s.root_ref;                                                        \
-        newState_ = s.root_ref >= 0 ? ST_NODE : ST_LEAF;                                       \
-        rays++;                                                                                \
-    }
-
-    while (true)
-    {
-        iter++;
-        // ---- vote ----
-        bool hasN = false;
-#pragma unroll
-        for (int k = 0; k < K; k++) hasN |= state[k] == ST_NODE;
-        const unsigned mNode = __ballot_sync(FULL, hasN);
-        int action = ST_NODE;
-        const int nN = __popc(mNode);
-        if (nN < nodeFast)
-        {
-            bool hasL = false, hasS = false, hasD = false;
-#pragma unroll
-            for (int k = 0; k < K; k++) hasL |= state[k] == ST_LEAF, hasS |= state[k] == ST_SHADE, hasD |= state[k] == ST_DEAD;
-            const unsigned mDead = __ballot_sync(FULL, hasD);
-            if (mDead && !poolEmpty)
-            {
-                // refill every dead slot from the stream pool: one atomic per warp
-                int want = 0;
-#pragma unroll
-                for (int k = 0; k < K; k++) want += state[k] == ST_DEAD;
-                int incl = want;
-#pragma unroll
-                for (int off = 1; off < 32; off <<= 1)
-                {
-                    const int t = __shfl_up_sync(FULL, incl, off);
-                    if (lane >= off) incl += t;
-                }
-                const int nWant = __shfl_sync(FULL, incl, 31);
-                int base = 0;
-                if (lane == 0) base = atomicAdd(streamCounter, nWant);
-                base = __shfl_sync(FULL, base, 0);
-                if (base + nWant >= total) poolEmpty = true;
-                int stream = base + incl - want;
-#pragma unroll
-                for (int k = 0; k < K; k++)
-                    if (state[k] == ST_DEAD && stream < total)
-                    {
-                        const int q = stream / frames, frame = stream - q * frames;
-                        const int tile = p.tileBegin + (tileOrder ? tileOrder[q] : q);
-                        uint32_t seed = pt_seed(p, tile, p.firstSpp + frame * p.stride);
-                        const int tx = tile % p.tilesX, ty = tile / p.tilesX;
-                        const float jy = random_float(seed), jx = random_float(seed);
-                        const float3 gD = primary_dir(cam, (float)(tx * 16) + jx, (float)(ty * 16) + jy);
-                        LaneStream& S = st[k];
-                        S.seed = seed, S.tileXY = (tx * 16) | ((ty * 16) << 16);
-                        int ns;
-                        RT4_START_RAY(S, cam.pos, gD, ns);
-                        S.misc = needs_exact_slab(cam.pos, gD) ? (1 << 14) : 0;
-                        state[k] = ns;
-                        stream++;
-                    }
-                continue;
-            }
-            const unsigned mLeaf = __ballot_sync(FULL, hasL);
-            const unsigned mShade = __ballot_sync(FULL, hasS);
-            if ((mNode | mLeaf | mShade) == 0) break;
-            const int nL = __popc(mLeaf), nS = __popc(mShade);
-            if (nN >= nL && nN >= nS) action = ST_NODE;
-            else if (nL >= nS) action = ST_LEAF;
-            else action = ST_SHADE;
-        }
-        // the stream this lane runs: one of its streams in the voted state (rotating preference)
-        int k = -1;
-#pragma unroll
-        for (int kk = 0; kk < K; kk++)
-        {
-            const int c = (kk + (int)iter) % K;
-            if (state[c] == action) k = c;
-        }
-
-        if (action == ST_NODE)
-        {
-            float3 O = f3(0, 0, 0), rD = f3(0, 0, 0);
-            float ht = 0;
-            int cur = 0, sp = 0, ns = -1;
-            bool exact = false;
-            if (k >= 0)
-            {
-                const LaneStream& S = st[k];
-                O = TLAS ? S.O : S.wO, rD = S.rD, ht = S.ht, cur = S.cur, sp = S.sp, exact = (S.misc >> 14) & 1;
-                ns = ST_NODE;
-            }
-            const int keep = nN - (nN >> 2);
-            do
-            {
-                if (ns == ST_NODE)
-                {
-                    const float4* nd = nodes + 4 * (size_t)cur;
-                    const float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2);
-                    const int4 n3 = __ldg((const int4*)(nd + 3));
-                    float d1 = slab(O, rD, ht, exact, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y);
-                    float d2 = slab(O, rD, ht, exact, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w);
-                    int c1 = n3.x, c2 = n3.y;
-                    if (d1 > d2) { const float tf = d1; d1 = d2; d2 = tf; const int tc = c1; c1 = c2; c2 = tc; }
-                    if (d1 == 1e30f)
-                    {
-                        if (sp == 0) ns = ST_SHADE;
-                        else cur = st[k].stack[--sp], ns = cur >= 0 ? ST_NODE : ST_LEAF;
-                    }
-                    else
-                    {
-                        cur = c1, ns = c1 >= 0 ? ST_NODE : ST_LEAF;
-                        if (d2 != 1e30f) st[k].stack[sp++] = c2;
-                    }
-                }
-            } while (__popc(__ballot_sync(FULL, ns == ST_NODE)) >= keep && keep > 0);
-            if (k >= 0)
-            {
-                st[k].cur = cur, st[k].sp = sp;
-                RT4_SET_STATE(k, ns);
-            }
-        }
-        else if (action == ST_LEAF)
-        {
-            if (k >= 0)
-            {
-                LaneStream& S = st[k];
-                int cur = S.cur, sp = S.sp, ns = ST_LEAF;
-                const int payload = ~cur;
-                bool pop = true;
-                if (TLAS && payload == SENTINEL_PAYLOAD)
-                {
-                    // blas_bvh.cpp:385-388: back to world space
-                    const float3 wO = S.wO, wD = S.wD;
-                    S.O = wO, S.D = wD, S.rD = recip(wD);
-                    S.misc = (S.misc & ~(1 << 14)) | (needs_exact_slab(wO, wD) ? (1 << 14) : 0);
-                }
-                else if (TLAS && (payload & INSTANCE_BIT))
-                {
-                    const float4* I = s.inst + 4 * (size_t)(payload & ~INSTANCE_BIT);
-                    const float4 r0 = __ldg(I), r1 = __ldg(I + 1), r2 = __ldg(I + 2);
-                    const int4 meta = __ldg((const int4*)(I + 3));
-                    const float3 wO = S.wO, wD = S.wD;
-                    const float3 O = f3((wO.x * r0.x + wO.y * r0.y) + (wO.z * r0.z + r0.w),
-                                        (wO.x * r1.x + wO.y * r1.y) + (wO.z * r1.z + r1.w),
-                                        (wO.x * r2.x + wO.y * r2.y) + (wO.z * r2.z + r2.w));
-                    const float3 D = f3((wD.x * r0.x + wD.y * r0.y) + wD.z * r0.z,
-                                        (wD.x * r1.x + wD.y * r1.y) + wD.z * r1.z,
-                                        (wD.x * r2.x + wD.y * r2.y) + wD.z * r2.z);
-                    S.O = O, S.D = D, S.rD = recip(D);
-                    S.misc = (S.misc & ~(1 << 14)) | (needs_exact_slab(O, D) ? (1 << 14) : 0);
-                    S.instObj = meta.y;
-                    S.stack[sp++] = ~SENTINEL_PAYLOAD;
-                    cur = meta.x, ns = cur >= 0 ? ST_NODE : ST_LEAF;
-                    pop = false;
-                }
-                else
-                {
-                    const float3 O = TLAS ? S.O : S.wO, D = TLAS ? S.D : S.wD;
-                    float ht = S.ht, hu = 0, hv = 0;
-                    int htri = -1, hobj = -1;
-                    const int instObj = TLAS ? S.instObj : s.flat_obj_idx;
-                    bool any = false;
-                    int slot = payload;
-                    while (true)
-                    {
-                        const float4* T = tris + 3 * (size_t)slot;
-                        const float4 t0 = __ldg(T), t1 = __ldg(T + 1), t2 = __ldg(T + 2);
-                        const int tag = __float_as_int(t0.w);
-                        if (intersect_tri(O, D, f3(t0.x, t0.y, t0.z), f3(t1.x, t1.y, t1.z), f3(t2.x, t2.y, t2.z), ht, hu, hv))
-                        {
-                            htri = tag & ~LAST_BIT;
-                            hobj = instObj >= 0 ? instObj : __float_as_int(t1.w);
-                            any = true;
-                        }
-                        if (tag & LAST_BIT) break;
-                        slot++;
-                    }
-                    if (any) S.ht = ht, S.hu = hu, S.hv = hv, S.htri = htri, S.hobj = hobj;
-                }
-                if (pop)
-                {
-                    if (sp == 0) ns = ST_SHADE;
-                    else cur = S.stack[--sp], ns = cur >= 0 ? ST_NODE : ST_LEAF;
-                }
-                S.cur = cur, S.sp = sp;
-                RT4_SET_STATE(k, ns);
-            }
-        }
-        else
-        {
-            if (k >= 0)
-            {
-                LaneStream& S = st[k];
-                const float3 wO = S.wO, wD = S.wD;
-                int misc = S.misc;
-                int pix = misc & 511, depth = (misc >> 9) & 15;
-                const bool inside = (misc >> 13) & 1;
-                uint32_t seed = S.seed;
-                float3 L, w, nO, nD;
-                bool nInside;
-                int ns;
-                if (!pt_bounce(s, p.eps, p.depthLimit, wO, wD, inside, depth, S.ht, S.hu, S.hv, S.hobj, S.htri, seed, L, w, nO, nD, nInside))
-                {
-                    S.wst[depth] = w;
-                    depth++;
-                    RT4_START_RAY(S, nO, nD, ns);
-                    misc = pix | (depth << 9) | ((nInside ? 1 : 0) << 13) | ((needs_exact_slab(nO, nD) ? 1 : 0) << 14);
-                }
-                else
-                {
-                    for (int d = depth - 1; d >= 0; d--) L = S.wst[d] * L;
-                    const int x0 = S.tileXY & 0xffff, y0 = S.tileXY >> 16;
-                    float* a = (float*)(p.accum + ((x0 + (pix & 15)) + (size_t)(y0 + (pix >> 4)) * p.W));
-                    atomicAdd(a + 0, L.x), atomicAdd(a + 1, L.y), atomicAdd(a + 2, L.z);
-                    pix++;
-                    if (pix < 256)
-                    {
-                        const float jy = random_float(seed), jx = random_float(seed);
-                        const float3 gD = primary_dir(cam, (float)(x0 + (pix & 15)) + jx, (float)(y0 + (pix >> 4)) + jy);
-                        RT4_START_RAY(S, cam.pos, gD, ns);
-                        misc = pix | ((needs_exact_slab(cam.pos, gD) ? 1 : 0) << 14);
-                    }
-                    else ns = ST_DEAD;
-                }
-                S.seed = seed, S.misc = misc;
-                RT4_SET_STATE(k, ns);
-            }
-        }
-    }
-#undef RT4_START_RAY
-#undef RT4_SET_STATE
-    for (int off = 16; off; off >>= 1) rays += __shfl_xor_sync(FULL, rays, off);
-    if (lane == 0) atomicAdd(p.counters, (unsigned long long)rays);
-}
-
 // Stream kernel, version 5 = version 2 (one stream per lane, state in registers, ballot vote) with what the
 // source-level profile of version 2 asked for (tools/ncu_source_hot.py on profiles/r1_v4_*):
 //   * MISS is voted separately from surface shading: sky lookups (atan2f / acosf / texel) no longer
@@ -1193,13 +575,17 @@ __global__ void __launch_bounds__(128) k_pt_streams4(const PTState p, const DSce
 //     (the stack pop ran at 2.2 lanes behind its own BSSY / BSYNC pair);
 //   * every finished stream adds its duration (clock64) to its tile's cost: the next render call of the same
 //     view sorts tiles by MEASURED cost instead of the 16-path pilot estimate (longest-first hand-out).
-// Versions 3 (six REDUX-voted states) and 4 (K streams per lane in local memory) were measured slower
-// (profiles/r1_stream_kernel_*): more vote rounds per ray and L1 thrashing outweighed the better lane use.
+// Three other designs were built, parity-checked and measured slower, then removed (numbers in
+// profiles/r1_stream_kernel_*.txt): six REDUX-voted states (more vote rounds per ray), K streams per lane in
+// local memory (lanes 13.7 -> 17.4 but the parked state thrashes L1: hit rate 83 -> 64 %), and a per-warp pool
+// of 64 streams in shared memory with traverse-only lanes and batched shading (lanes 17.3, but only 20 warps
+// per SM fit and every warp's iteration got longer).  The kernel is bound by per-warp instruction latency x
+// SIMD efficiency; throughput grows almost linearly with resident warps.
 enum { ST_MISS = 4 };
 
-template <bool TLAS>
-__global__ void __launch_bounds__(128, 7) k_pt_streams5(const PTState p, const DScene s, const DCamera cam,
-    const int* __restrict__ tileOrder, const int frames, int* __restrict__ streamCounter, unsigned long long* __restrict__ tileCost)
+template <bool TLAS, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_pt_streams5(const PTState p, const DScene s, const DCamera cam,
+    const int* __restrict__ tileOrder, const int frames, int* __restrict__ streamCounter, unsigned long long* __restrict__ tileCost, const int keepShift)
 {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -1266,7 +652,7 @@ __global__ void __launch_bounds__(128, 7) k_pt_streams5(const PTState p, const D
             const int nN = __popc(mNode), nL = __popc(mLeaf), nS = __popc(mShade), nM = __popc(mMiss);
             if (nN >= nL && nN >= nS && nN >= nM)
             {
-                const int keep = nN - (nN >> 2);
+                const int keep = nN - (nN >> keepShift);
                 do
                 {
                     if (state == ST_NODE)
@@ -1719,9 +1105,9 @@ struct rt_renderer {
     bool persistent = true;
     bool useStreams = true;
     int streamCtasPerSm = 8;
-    int streamKernel = 5;
-    int streamK = 2, streamNodeFast = 20;
+    int streamKernel = 5; // 5 = current; 2 = the previous version, kept for A/B profiling (RT_B200_STREAM_KERNEL)
     bool streamMeasuredLpt = true;
+    int streamMinB = 7, streamKeepShift = 2;
     bool streamLpt = true;
     int* dTileOrder = nullptr;
     unsigned int* dTileCost = nullptr;
@@ -1776,12 +1162,12 @@ struct rt_renderer {
 };
 
 
-// stream kernel version 4: dispatch on (TLAS, K)
-typedef void (*Streams4Fn)(const PTState, const DScene, const DCamera, const int*, const int, int*, const int);
-static Streams4Fn streams4_kernel(bool tlas, int K)
+// stream kernel version 5: dispatch on (TLAS, min CTAs per SM the register budget is bounded for)
+typedef void (*Streams5Fn)(const PTState, const DScene, const DCamera, const int*, const int, int*, unsigned long long*, const int);
+static Streams5Fn streams5_kernel(bool tlas, int minb)
 {
-    if (tlas) return K == 1 ? k_pt_streams4<true, 1> : K == 3 ? k_pt_streams4<true, 3> : K == 4 ? k_pt_streams4<true, 4> : k_pt_streams4<true, 2>;
-    return K == 1 ? k_pt_streams4<false, 1> : K == 3 ? k_pt_streams4<false, 3> : K == 4 ? k_pt_streams4<false, 4> : k_pt_streams4<false, 2>;
+    if (tlas) return minb <= 6 ? k_pt_streams5<true, 6> : minb >= 8 ? k_pt_streams5<true, 8> : k_pt_streams5<true, 7>;
+    return minb <= 6 ? k_pt_streams5<false, 6> : minb >= 8 ? k_pt_streams5<false, 8> : k_pt_streams5<false, 7>;
 }
 
 template <class T>
@@ -1865,15 +1251,13 @@ rt_status rt_renderer_create(rt_scene* scene, const rt_render_params* params, rt
         if ((e = getenv("RT_B200_STREAM_LPT")) != nullptr) r->streamLpt = atoi(e) != 0;
         int occ = 0;
         cudaError_t oe;
-        if ((e = getenv("RT_B200_STREAM_K")) != nullptr && atoi(e) > 0) r->streamK = atoi(e);
         if ((e = getenv("RT_B200_STREAM_MEASURED_LPT")) != nullptr) r->streamMeasuredLpt = atoi(e) != 0;
-        if ((e = getenv("RT_B200_STREAM_NODEFAST")) != nullptr && atoi(e) > 0) r->streamNodeFast = atoi(e);
-        if (r->streamKernel == 1) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams, 128, 0);
-        else if (r->streamKernel == 4) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, streams4_kernel(scene->d.kind == RT_SCENE_TLAS, r->streamK), 128, 0);
-        else if (r->streamKernel == 5 && scene->d.kind == RT_SCENE_TLAS) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams5<true>, 128, 0);
-        else if (r->streamKernel == 5) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams5<false>, 128, 0);
-        else if (r->streamKernel == 3 && scene->d.kind == RT_SCENE_TLAS) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams3<true>, 128, 0);
-        else if (r->streamKernel == 3) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams3<false>, 128, 0);
+        if (r->streamKernel == 5)
+        {
+            if ((e = getenv("RT_B200_STREAM_MINB")) != nullptr && atoi(e) > 0) r->streamMinB = atoi(e);
+            if ((e = getenv("RT_B200_STREAM_KEEPSHIFT")) != nullptr && atoi(e) > 0) r->streamKeepShift = atoi(e);
+            oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, streams5_kernel(scene->d.kind == RT_SCENE_TLAS, r->streamMinB), 128, 0);
+        }
         else if (scene->d.kind == RT_SCENE_TLAS) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams2<true>, 128, 0);
         else oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams2<false>, 128, 0);
         if (oe == cudaSuccess && occ > 0) r->streamCtasPerSm = occ;
@@ -2042,20 +1426,14 @@ static rt_status render_pt_streams(rt_renderer* r, int first_spp, int count, int
         order = r->dTileOrder;
     }
     r->prof_begin();
-    if (r->streamKernel == 1) k_pt_streams<<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
-    else if (r->streamKernel == 5)
+    if (r->streamKernel == 5)
     {
         // time the streams of this launch only while the tile order still comes from the pilot
         unsigned long long* clk = (order && r->tileOrderSource == 1 && r->streamMeasuredLpt) ? r->dTileClock : nullptr;
         if (clk) RT_CUDA(cudaMemsetAsync(clk, 0, (size_t)nTiles * 8, r->stream));
-        if (r->scene->d.kind == RT_SCENE_TLAS) k_pt_streams5<true><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6, clk);
-        else k_pt_streams5<false><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6, clk);
+        streams5_kernel(r->scene->d.kind == RT_SCENE_TLAS, r->streamMinB)<<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6, clk, r->streamKeepShift);
         if (clk) r->tileClockRecorded = true, r->lastStreamFrames = count;
     }
-    else if (r->streamKernel == 4)
-        streams4_kernel(r->scene->d.kind == RT_SCENE_TLAS, r->streamK)<<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6, r->streamNodeFast);
-    else if (r->streamKernel == 3 && r->scene->d.kind == RT_SCENE_TLAS) k_pt_streams3<true><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
-    else if (r->streamKernel == 3) k_pt_streams3<false><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
     else if (r->scene->d.kind == RT_SCENE_TLAS) k_pt_streams2<true><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
     else k_pt_streams2<false><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
     r->prof_end(RT_STAGE_EXTEND);
