@@ -817,8 +817,9 @@ struct WhState {
     float eps;
 };
 
-__global__ void __launch_bounds__(256) k_wh_generate(const WhState p, const DCamera cam)
+__global__ void __launch_bounds__(256) k_wh_generate(const WhState p, const DCamera* __restrict__ camPtr)
 {
+    const DCamera cam = *camPtr; // in device memory so that the captured frame graph can be replayed with a new camera
     const int n = p.W * p.H;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     {
@@ -1120,6 +1121,11 @@ struct rt_renderer {
     std::vector<void*> allocations;
     // whitted
     WhState wh = {};
+    DCamera* dCam = nullptr;   // camera in device memory (read by k_wh_generate)
+    bool whGraphEnabled = true;
+    cudaGraphExec_t whGraphExec = nullptr;
+    float4* whGraphAccum = nullptr;
+    int whGraphLaunches = 0;
     // counters
     unsigned long long* dCounters = nullptr; // 4
     int* dCount = nullptr;                   // 4
@@ -1280,6 +1286,8 @@ rt_status rt_renderer_create(rt_scene* scene, const rt_render_params* params, rt
         if ((st = ralloc(r, &w.hitTri, (size_t)w.capacity * 4)) != RT_OK) return fail(st);
         if ((st = ralloc(r, &w.shadow, (size_t)w.capacity * 80)) != RT_OK) return fail(st);
         w.count = r->dCount, w.counters = r->dCounters;
+        if ((st = ralloc(r, &r->dCam, sizeof(DCamera))) != RT_OK) return fail(st);
+        { const char* e = getenv("RT_B200_WHITTED_GRAPH"); if (e) r->whGraphEnabled = atoi(e) != 0; }
         w.W = params->width, w.H = params->height, w.depthLimit = params->depth_limit, w.eps = params->epsilon;
     }
     *out = r;
@@ -1294,6 +1302,7 @@ void rt_renderer_destroy(rt_renderer* r)
     for (void* p : r->allocations) cudaFree(p);
     for (cudaEvent_t e : r->evPool) cudaEventDestroy(e);
     if (r->hCount) cudaFreeHost(r->hCount);
+    if (r->whGraphExec) cudaGraphExecDestroy(r->whGraphExec);
     if (r->ownStream) cudaStreamDestroy(r->ownStream);
     delete r;
 }
@@ -1498,16 +1507,16 @@ static rt_status render_pt(rt_renderer* r, int first_spp, int count, int stride)
     return RT_OK;
 }
 
-static rt_status render_whitted(rt_renderer* r)
+// the launches of one Whitted frame (Renderer::Tick, 2. WhittedStyle/renderer.cpp:131-157)
+static void whitted_frame_launches(rt_renderer* r)
 {
     const rt_render_params& P = r->params;
     WhState& w = r->wh;
-    w.accum = r->accum;
     const size_t px = (size_t)P.width * P.height;
     // Tick overwrites the accumulator every frame (renderer.cpp:155)
-    RT_CUDA(cudaMemsetAsync(r->accum, 0, px * 16, r->stream));
+    cudaMemsetAsync(r->accum, 0, px * 16, r->stream);
     r->prof_begin();
-    k_wh_generate<<<r->sms * 4, 256, 0, r->stream>>>(w, r->cam);
+    k_wh_generate<<<r->sms * 4, 256, 0, r->stream>>>(w, r->dCam);
     r->prof_end(RT_STAGE_GENERATE);
     const int grid = r->sms * 8;
     int cur = 0;
@@ -1526,7 +1535,43 @@ static rt_status render_whitted(rt_renderer* r)
         r->prof_end(RT_STAGE_CONNECT);
         cur ^= 1;
     }
-    r->paths += px;
+}
+
+// A Whitted frame is 2 + 3 * (depthLimit + 1) short launches (20 at depth 5): at 640x360 the frame is bound by
+// launch latency, so the sequence is captured once into a CUDA graph and replayed; only the camera (device
+// memory) changes between frames.  The graph is rebuilt when the accumulator pointer changes.
+static rt_status render_whitted(rt_renderer* r)
+{
+    const rt_render_params& P = r->params;
+    r->wh.accum = r->accum;
+    // pageable source: the runtime stages the 56 bytes before returning, so r->cam may change right after
+    RT_CUDA(cudaMemcpyAsync(r->dCam, &r->cam, sizeof(DCamera), cudaMemcpyHostToDevice, r->stream));
+    const bool useGraph = r->whGraphEnabled && !r->profiling;
+    if (useGraph)
+    {
+        if (r->whGraphExec && r->whGraphAccum != r->accum)
+        {
+            cudaGraphExecDestroy(r->whGraphExec);
+            r->whGraphExec = nullptr;
+        }
+        if (!r->whGraphExec)
+        {
+            cudaGraph_t g = nullptr;
+            RT_CUDA(cudaStreamBeginCapture(r->stream, cudaStreamCaptureModeThreadLocal));
+            const uint64_t before = r->launches;
+            whitted_frame_launches(r);
+            r->whGraphLaunches = (int)(r->launches - before);
+            r->launches = before;
+            RT_CUDA(cudaStreamEndCapture(r->stream, &g));
+            RT_CUDA(cudaGraphInstantiate(&r->whGraphExec, g, 0));
+            cudaGraphDestroy(g);
+            r->whGraphAccum = r->accum;
+        }
+        RT_CUDA(cudaGraphLaunch(r->whGraphExec, r->stream));
+        r->launches += r->whGraphLaunches;
+    }
+    else whitted_frame_launches(r);
+    r->paths += (size_t)P.width * P.height;
     RT_CUDA(cudaGetLastError());
     return RT_OK;
 }
