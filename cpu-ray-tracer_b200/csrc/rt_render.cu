@@ -585,7 +585,7 @@ enum { ST_MISS = 4 };
 
 template <bool TLAS, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_pt_streams5(const PTState p, const DScene s, const DCamera cam,
-    const int* __restrict__ tileOrder, const int frames, int* __restrict__ streamCounter, unsigned long long* __restrict__ tileCost, const int keepShift)
+    const int* __restrict__ tileOrder, const int frames, int* __restrict__ streamCounter, unsigned long long* __restrict__ tileCost, const int keepShift, const unsigned laneMask)
 {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -620,10 +620,11 @@ __global__ void __launch_bounds__(128, MINB) k_pt_streams5(const PTState p, cons
         const unsigned mMiss = __ballot_sync(FULL, state == ST_MISS);
         const unsigned mLive = mNode | mLeaf | mShade | mMiss;
         bool start = false;
-        if (mLive != FULL && !poolEmpty)
+        if ((~mLive & laneMask) != 0 && !poolEmpty)
         {
-            // refill the dead lanes from the stream pool: one atomic per warp
-            const unsigned mDead = ~mLive;
+            // refill the dead lanes from the stream pool: one atomic per warp.  laneMask caps the streams per warp
+            // for small jobs (fewer streams than lanes): a chain runs faster the fewer neighbours it waits for
+            const unsigned mDead = ~mLive & laneMask;
             const int nIdle = __popc(mDead);
             const int leader = __ffs(mDead) - 1;
             int base = 0;
@@ -631,7 +632,7 @@ __global__ void __launch_bounds__(128, MINB) k_pt_streams5(const PTState p, cons
             base = __shfl_sync(FULL, base, leader);
             if (base + nIdle >= total) poolEmpty = true;
             const int stream = base + __popc(mDead & ((1u << lane) - 1));
-            if (state == ST_DEAD && stream < total)
+            if (state == ST_DEAD && ((laneMask >> lane) & 1) && stream < total)
             {
                 const int k = stream / frames, frame = stream - k * frames;
                 const int tile = p.tileBegin + (tileOrder ? tileOrder[k] : k);
@@ -1109,6 +1110,7 @@ struct rt_renderer {
     int streamKernel = 5; // 5 = current; 2 = the previous version, kept for A/B profiling (RT_B200_STREAM_KERNEL)
     bool streamMeasuredLpt = true;
     int streamMinB = 7, streamKeepShift = 2;
+    bool streamLaneCap = true;
     bool streamLpt = true;
     int* dTileOrder = nullptr;
     unsigned int* dTileCost = nullptr;
@@ -1169,7 +1171,7 @@ struct rt_renderer {
 
 
 // stream kernel version 5: dispatch on (TLAS, min CTAs per SM the register budget is bounded for)
-typedef void (*Streams5Fn)(const PTState, const DScene, const DCamera, const int*, const int, int*, unsigned long long*, const int);
+typedef void (*Streams5Fn)(const PTState, const DScene, const DCamera, const int*, const int, int*, unsigned long long*, const int, const unsigned);
 static Streams5Fn streams5_kernel(bool tlas, int minb)
 {
     if (tlas) return minb <= 6 ? k_pt_streams5<true, 6> : minb >= 8 ? k_pt_streams5<true, 8> : k_pt_streams5<true, 7>;
@@ -1262,6 +1264,7 @@ rt_status rt_renderer_create(rt_scene* scene, const rt_render_params* params, rt
         {
             if ((e = getenv("RT_B200_STREAM_MINB")) != nullptr && atoi(e) > 0) r->streamMinB = atoi(e);
             if ((e = getenv("RT_B200_STREAM_KEEPSHIFT")) != nullptr && atoi(e) > 0) r->streamKeepShift = atoi(e);
+            if ((e = getenv("RT_B200_STREAM_LANECAP")) != nullptr) r->streamLaneCap = atoi(e) != 0;
             oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, streams5_kernel(scene->d.kind == RT_SCENE_TLAS, r->streamMinB), 128, 0);
         }
         else if (scene->d.kind == RT_SCENE_TLAS) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams2<true>, 128, 0);
@@ -1440,7 +1443,13 @@ static rt_status render_pt_streams(rt_renderer* r, int first_spp, int count, int
         // time the streams of this launch only while the tile order still comes from the pilot
         unsigned long long* clk = (order && r->tileOrderSource == 1 && r->streamMeasuredLpt) ? r->dTileClock : nullptr;
         if (clk) RT_CUDA(cudaMemsetAsync(clk, 0, (size_t)nTiles * 8, r->stream));
-        streams5_kernel(r->scene->d.kind == RT_SCENE_TLAS, r->streamMinB)<<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6, clk, r->streamKeepShift);
+        // small jobs: spread the streams over all resident warps instead of filling the first warps completely
+        const long long warps = (long long)r->sms * r->streamCtasPerSm * 4;
+        long long perWarp = ((long long)p.slots + warps - 1) / warps;
+        if (perWarp < 1) perWarp = 1;
+        if (perWarp > 32 || !r->streamLaneCap) perWarp = 32;
+        const unsigned laneMask = perWarp >= 32 ? 0xffffffffu : ((1u << perWarp) - 1);
+        streams5_kernel(r->scene->d.kind == RT_SCENE_TLAS, r->streamMinB)<<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6, clk, r->streamKeepShift, laneMask);
         if (clk) r->tileClockRecorded = true, r->lastStreamFrames = count;
     }
     else if (r->scene->d.kind == RT_SCENE_TLAS) k_pt_streams2<true><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
