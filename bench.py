@@ -46,6 +46,22 @@ def scene_file():
             "FALLBACK golden scene (oracle/_ref/scenes missing): path tracer, FileScene BVH-SAH, 1920x1080, 64 spp")
 
 
+def ncu_dram_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel on this workload, from the committed
+    `ncu --set full` capture (profiles/, tools/ncu_summary.py); bytes, or None when no capture is committed"""
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_k_pt_streams5_ncu_full.txt")))
+    if not files:
+        return None, None
+    total, unit_scale = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for line in open(files[-1]):
+        m = re.match(r"dram__bytes_(read|write)\.sum\s+(\w+)\s+([0-9.]+)", line)
+        if m:
+            total += float(m.group(3)) * unit_scale.get(m.group(2), 1.0)
+    return (total if total > 0 else None), os.path.relpath(files[-1], ROOT)
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -282,6 +298,7 @@ def bench_ours(args):
             cp = r.counters()
             r.set_profiling(False)
             work = oracle_work_per_ray(flat, W, H, frames=2)
+            traffic, traffic_src = ncu_dram_traffic()
             ext_ms, ext_launches = st["extend"]
             total_ms = sum(v[0] for v in st.values())
             achieved = work["bytes_per_ray"] * cp["extension_rays"] / (ext_ms / 1e3) / 1e9
@@ -290,7 +307,8 @@ def bench_ours(args):
             l2_peak = api.measure_gather_bandwidth(8 << 20, bypass_l1=True, device=local)
             l1l2_peak = api.measure_gather_bandwidth(8 << 20, bypass_l1=False, device=local)
             roofline = {"bound": "hbm", "kernel": "k_pt_streams2 (traversal + shading of every (tile, frame) RNG stream, persistent)", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind + " HBM copy bandwidth",
+                        "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write)",
+                        "traffic_source": traffic_src, "peak_kind": peak_kind + " HBM copy bandwidth",
                         "algorithmic_bytes_per_ray": work["bytes_per_ray"],
                         "work_per_ray": {"interior_visits": work["I"], "tri_tests": work["T"], "blas_entries": work["B"]},
                         "algorithmic_bytes_per_launch": work["bytes_per_ray"] * cp["extension_rays"] / max(ext_launches, 1),

@@ -347,3 +347,76 @@ def test_simple_traversal_kernels_agree(monkeypatch, oracles, flat_scenes):
         assert np.nan_to_num(np.abs(r.accumulator - ow)).max() <= WHITTED_TOL
         r.close()
         sc.close()
+
+
+def test_depth_limit_above_stream_kernel_capacity_uses_wavefront(oracles, gpu_scenes):
+    """depthLimit > 8 does not fit the stream kernel's register-resident throughput stack: the renderer falls
+    back to the wavefront schedule and still matches the oracle"""
+    from cpu_ray_tracer_b200 import api
+    from oracle import porthost
+    name = "golden_file"
+    po, sc = oracles(name), gpu_scenes(name, counters=False)
+    W, H, frames, depth = 96, 64, 2, 11
+    cam = po.camera_default(W, H)
+    oacc, ost = po.render_pt(cam, porthost.default_params(abi.RT_INTEGRATOR_PATH, W, H, depth_limit=depth), 1, frames, 1)
+    r = api.GpuRenderer(sc, abi.RT_INTEGRATOR_PATH, W, H, depthLimit=depth).Init()
+    r.render(frames)
+    c = r.counters()
+    assert c["extension_rays"] == ost["extension_rays"] and c["wavefront_iterations"] > 0
+    check_pt(r.accumulator, oacc, frames, "depth 11")
+    r.close()
+
+
+def test_large_batches_counters_and_profiling_api(oracles, gpu_scenes, flat_scenes):
+    """a batch larger than one launch chunk, counter reset, per-stage times, path-tracer display scale"""
+    from cpu_ray_tracer_b200 import api
+    from oracle import porthost
+    name = "golden_tlas"
+    po, sc = oracles(name), gpu_scenes(name)
+    base = random_rays(flat_scenes(name), 1 << 16, seed=3)
+    rays = np.tile(base, 40)                      # 2.6 M rays through one rt_find_nearest call
+    got = sc.FindNearest(rays)
+    ref, _ = po.find_nearest(base)
+    for k in (0, 17, 39):
+        assert_hits_equal(got[k * len(base):(k + 1) * len(base)], ref, f"copy {k}")
+    occ = sc.IsOccluded(rays)
+    oref, _ = po.is_occluded(base)
+    assert np.array_equal(occ.reshape(40, -1), np.broadcast_to(oref, (40, len(base))))
+    W, H = 128, 80
+    r = api.GpuRenderer(sc, abi.RT_INTEGRATOR_PATH, W, H, schedule=abi.RT_SCHEDULE_WAVEFRONT).Init()
+    r.set_profiling(True)
+    r.render(2)
+    st = r.stage_times()
+    assert st["extend"][1] > 0 and st["shade"][1] == st["extend"][1] and st["extend"][0] > 0
+    r.set_profiling(False)
+    c = r.counters()
+    assert c["paths"] == W * H * 2 and c["kernel_launches"] > 0
+    r.reset_counters()
+    assert r.counters()["extension_rays"] == 0 and r.counters()["paths"] == 0
+    # screen->pixels: accumulator / (spp + passes) as the reference displays it after 2 Ticks from spp = 1
+    acc = r.accumulator
+    px = r.screen_pixels(scale=1.0 / 3.0)
+    opx = po.to_rgb8(acc, 1.0 / 3.0)
+    assert np.array_equal(px, opx)
+    r.close()
+
+
+def test_renderer_argument_errors(gpu_scenes):
+    import ctypes as C
+    from cpu_ray_tracer_b200 import api
+    L = api.lib()
+    sc = gpu_scenes("golden_file")
+    p = abi.rt_render_params()
+    L.rt_render_params_default(C.byref(p), abi.RT_INTEGRATOR_PATH, 64, 64)
+    assert p.depth_limit == 5 and abs(p.epsilon - 0.001) < 1e-9 and p.seed_mode == abi.RT_SEED_REFERENCE_TILE
+    h = C.c_void_p()
+    p.width = 0
+    assert L.rt_renderer_create(sc.handle, C.byref(p), C.byref(h)) == abi.RT_ERR_INVALID
+    p.width, p.integrator = 64, 9
+    assert L.rt_renderer_create(sc.handle, C.byref(p), C.byref(h)) == abi.RT_ERR_INVALID
+    assert L.rt_renderer_create(None, C.byref(p), C.byref(h)) == abi.RT_ERR_INVALID
+    assert L.rt_renderer_render(None, 1, 1, 1) == abi.RT_ERR_INVALID
+    out = C.c_double()
+    assert L.rt_measure_gather_bandwidth(0, 16, 1, C.byref(out)) == abi.RT_ERR_INVALID
+    assert L.rt_measure_gather_bandwidth(99, 1 << 20, 1, C.byref(out)) == abi.RT_ERR_NO_DEVICE
+    assert api.measure_gather_bandwidth(4 << 20) > 100.0
