@@ -138,10 +138,17 @@ def oracle_work_per_ray(flat, W, H, frames):
     return {"I": I, "T": T, "B": B, "bytes_per_ray": 64 * I + 52 * T + 64 * B + 48, "rays": rays, "seconds": secs, "stats": st}
 
 
+def host_thread_env():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the reference's CPU loop must get all host threads"""
+    env = dict(os.environ)
+    env["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+    return env
+
+
 def run_reference_subprocess(frames, W, H, fast):
     """the reference's Renderer::Tick x frames on this box's host cores (own process: it chdir()s)"""
     cmd = [sys.executable, "-m", "oracle.refhost", "bench", "pt", "file", SCENE_XML, str(W), str(H), str(frames), "1" if fast else "0"]
-    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900, env=host_thread_env())
     if out.returncode != 0:
         raise RuntimeError(out.stderr[-2000:])
     return json.loads(out.stdout.strip().splitlines()[-1])
@@ -357,6 +364,7 @@ def bench_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)  # before libgomp loads (torchrun sets it to 1)
     from oracle import refhost
     W, H = args.width, args.height
     frames = 4  # bounded sample per step: 4 of the workload's 64 frames
@@ -381,7 +389,7 @@ def bench_reference(args):
     else:
         cmd = [sys.executable, "-m", "oracle.refhost", "bench_steps", "pt", "file", SCENE_XML, str(W), str(H), str(frames),
                str(args.warmup), str(args.steps)]
-        outp = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=1500)
+        outp = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=1500, env=host_thread_env())
         if outp.returncode != 0:
             raise RuntimeError(outp.stderr[-2000:])
         res = json.loads(outp.stdout.strip().splitlines()[-1])
