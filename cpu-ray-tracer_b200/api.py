@@ -211,7 +211,7 @@ class GpuRenderer:
     """Renderer : TheApp (2. WhittedStyle/renderer.h:41-61, 3. PathTracer/renderer.h:29-53)."""
 
     def __init__(self, scene: GpuScene, integrator, width, height, depthLimit=5, seed_mode=abi.RT_SEED_REFERENCE_TILE,
-                 tile_begin=0, tile_end=0, max_frames_in_flight=0, schedule=abi.RT_SCHEDULE_AUTO):
+                 tile_begin=0, tile_end=0, max_frames_in_flight=0, schedule=abi.RT_SCHEDULE_AUTO, lookahead_frames=0):
         self.scene = scene
         self.integrator = integrator
         self.width, self.height = width, height
@@ -225,6 +225,7 @@ class GpuRenderer:
         self.params.tile_begin, self.params.tile_end = tile_begin, tile_end
         self.params.max_frames_in_flight = max_frames_in_flight
         self.params.schedule = schedule
+        self.params.lookahead_frames = lookahead_frames
         self.handle = C.c_void_p()
         self._initialised = False
 

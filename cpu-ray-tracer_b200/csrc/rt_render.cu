@@ -42,6 +42,7 @@ struct PTState {
     int* history;      // queued rays per iteration of the current batch
     int iteration;
     float4* accum;
+    float4* frameBuf;  // optional: one W x H float4 image per frame of the launch (look-ahead mode), else nullptr
     int slots, nTiles, tilesX, tileBegin;
     int firstSpp, stride;
     int W, H, depthLimit, seedMode;
@@ -639,7 +640,7 @@ __global__ void __launch_bounds__(128, MINB) k_pt_streams5(const PTState p, cons
                 seed = pt_seed(p, tile, p.firstSpp + frame * p.stride);
                 const int tx = tile % p.tilesX, ty = tile / p.tilesX;
                 tileXY = (tx * 16) | ((ty * 16) << 16);
-                pix = 0, depth = 0, inside = false;
+                pix = frame << 9, depth = 0, inside = false; // pix = pixel of the tile (9 bits) | frame of the launch << 9
                 const float jy = random_float(seed), jx = random_float(seed);
                 wD = primary_dir(cam, (float)(tx * 16) + jx, (float)(ty * 16) + jy);
                 wO = cam.pos;
@@ -761,13 +762,20 @@ __global__ void __launch_bounds__(128, MINB) k_pt_streams5(const PTState p, cons
                 {
                     for (int d = depth - 1; d >= 0; d--) L = wst[d] * L;
                     const int x0 = tileXY & 0xffff, y0 = tileXY >> 16;
-                    float* a = (float*)(p.accum + ((x0 + (pix & 15)) + (size_t)(y0 + (pix >> 4)) * p.W)); // renderer.cpp:124
-                    atomicAdd(a + 0, L.x), atomicAdd(a + 1, L.y), atomicAdd(a + 2, L.z);
-                    pix++;
-                    if (pix < 256)
+                    const int px = pix & 511;
+                    const size_t pixel = (x0 + (px & 15)) + (size_t)(y0 + (px >> 4)) * p.W;
+                    if (p.frameBuf) p.frameBuf[(size_t)(pix >> 9) * ((size_t)p.W * p.H) + pixel] = make_float4(L.x, L.y, L.z, 0); // the frame's own image
+                    else
                     {
+                        float* a = (float*)(p.accum + pixel); // renderer.cpp:124
+                        atomicAdd(a + 0, L.x), atomicAdd(a + 1, L.y), atomicAdd(a + 2, L.z);
+                    }
+                    pix++;
+                    if ((pix & 511) < 256)
+                    {
+                        const int nx = pix & 511;
                         const float jy = random_float(seed), jx = random_float(seed);
-                        wD = primary_dir(cam, (float)(x0 + (pix & 15)) + jx, (float)(y0 + (pix >> 4)) + jy);
+                        wD = primary_dir(cam, (float)(x0 + (nx & 15)) + jx, (float)(y0 + (nx >> 4)) + jy);
                         wO = cam.pos, depth = 0, inside = false;
                         start = true;
                     }
@@ -1074,6 +1082,19 @@ __global__ void __launch_bounds__(128) k_wh_connect_persistent(const WhState p, 
     if (blockIdx.x == 0 && threadIdx.x == 0) p.counters[1] += (unsigned long long)n;
 }
 
+// look-ahead mode: accumulator += the image of one frame (renderer.cpp:124, one float add per channel per frame,
+// in spp order like the reference's Tick sequence)
+__global__ void k_add_frame(float4* __restrict__ accum, const float4* __restrict__ frame, int n)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        float4 a = accum[i];
+        const float4 f = frame[i];
+        a.x += f.x, a.y += f.y, a.z += f.z;
+        accum[i] = a;
+    }
+}
+
 // screen->pixels: RGBF32_to_RGB8 (template/precomp.h:325-341, scalar branch) of accumulator * scale
 __global__ void k_to_rgb8(const float4* __restrict__ accum, uint32_t* __restrict__ out, int n, float scale)
 {
@@ -1110,6 +1131,10 @@ struct rt_renderer {
     int streamKernel = 5; // 5 = current; 2 = the previous version, kept for A/B profiling (RT_B200_STREAM_KERNEL)
     bool streamMeasuredLpt = true;
     int streamMinB = 7, streamKeepShift = 2;
+    // look-ahead (rt_render_params.lookahead_frames): frames rendered ahead of the Tick sequence
+    float4* dFrameBuf = nullptr;
+    int aheadCapacity = 0, aheadBase = 0, aheadStride = 1, aheadReady = 0;
+    bool aheadValid = false;
     bool streamLaneCap = true;
     bool streamLpt = true;
     int* dTileOrder = nullptr;
@@ -1328,7 +1353,7 @@ rt_status rt_renderer_set_camera(rt_renderer* r, const rt_camera* cam)
 {
     if (!r || !cam) return RT_ERR_INVALID;
     const DCamera c = make_camera(*cam, r->params.width, r->params.height);
-    if (memcmp(&c, &r->cam, sizeof c) != 0) r->tileOrderValid = false; // the pilot's tile costs are per view
+    if (memcmp(&c, &r->cam, sizeof c) != 0) r->tileOrderValid = false, r->aheadValid = false; // tile costs and frames rendered ahead are per view
     r->cam = c;
     return RT_OK;
 }
@@ -1418,12 +1443,12 @@ static rt_status pt_tile_order(rt_renderer* r, const PTState& p)
     return RT_OK;
 }
 
-static rt_status render_pt_streams(rt_renderer* r, int first_spp, int count, int stride)
+static rt_status render_pt_streams(rt_renderer* r, int first_spp, int count, int stride, float4* frameBuf = nullptr)
 {
     const rt_render_params& P = r->params;
     const int nTiles = num_tiles(P);
     PTState p = {};
-    p.counters = r->dCounters, p.accum = r->accum;
+    p.counters = r->dCounters, p.accum = r->accum, p.frameBuf = frameBuf;
     p.nTiles = nTiles, p.tilesX = P.width / 16, p.tileBegin = P.tile_begin;
     p.W = P.width, p.H = P.height, p.depthLimit = P.depth_limit, p.seedMode = P.seed_mode, p.eps = P.epsilon;
     p.stride = stride, p.firstSpp = first_spp;
@@ -1467,7 +1492,36 @@ static rt_status render_pt(rt_renderer* r, int first_spp, int count, int stride)
     if (nTiles == 0 || count <= 0) return RT_OK;
     if (r->useStreams && P.seed_mode == RT_SEED_REFERENCE_TILE && P.depth_limit <= STREAM_MAX_DEPTH
         && (long long)nTiles * count < (1ll << 30))
+    {
+        const int L = P.lookahead_frames;
+        if (count == 1 && L > 1 && r->streamKernel == 5 && (long long)nTiles * L < (1ll << 30))
+        {
+            // one Tick per call: serve the frame from the images rendered ahead, rendering L more when it is not there
+            const size_t px = (size_t)P.width * P.height;
+            const bool hit = r->aheadValid && r->aheadStride == stride && first_spp >= r->aheadBase &&
+                             (first_spp - r->aheadBase) % stride == 0 && (first_spp - r->aheadBase) / stride < r->aheadReady;
+            if (!hit)
+            {
+                if (r->aheadCapacity < L)
+                {
+                    rt_status st = ralloc(r, &r->dFrameBuf, px * 16 * (size_t)L);
+                    if (st != RT_OK) return st;
+                    // pixels outside the rendered tiles (1080 % 16 rows, tile ranges of other shards) stay zero
+                    RT_CUDA(cudaMemsetAsync(r->dFrameBuf, 0, px * 16 * (size_t)L, r->stream));
+                    r->aheadCapacity = L;
+                }
+                rt_status st = render_pt_streams(r, first_spp, L, stride, r->dFrameBuf);
+                if (st != RT_OK) return st;
+                r->aheadValid = true, r->aheadBase = first_spp, r->aheadStride = stride, r->aheadReady = L;
+            }
+            const int k = (first_spp - r->aheadBase) / stride;
+            k_add_frame<<<r->sms * 4, 256, 0, r->stream>>>(r->accum, r->dFrameBuf + (size_t)k * px, (int)px);
+            r->launches++;
+            RT_CUDA(cudaGetLastError());
+            return RT_OK;
+        }
         return render_pt_streams(r, first_spp, count, stride);
+    }
     int inFlight = P.max_frames_in_flight > 0 ? P.max_frames_in_flight : (1 << 20) / nTiles;
     if (inFlight < 1) inFlight = 1;
     if (inFlight > count) inFlight = count;

@@ -222,6 +222,8 @@ public:
 		rt_render_params p;
 		rt_render_params_default( &p, INTEGRATOR, SCRWIDTH, SCRHEIGHT );
 		p.depth_limit = depthLimit, p.epsilon = EPSILON;
+		// one Tick per frame is how the reference runs: render `lookahead` frames per launch, reveal one per Tick
+		p.lookahead_frames = INTEGRATOR == RT_INTEGRATOR_PATH ? lookahead : 0;
 		check( rt_renderer_create( scene.Handle(), &p, &dev ), "rt_renderer_create" );
 		createdDepthLimit = depthLimit;
 	}
@@ -279,6 +281,7 @@ public:
 	bool animating = false;
 	float energy = 0, anim_time = 0;
 	int depthLimit = 5;
+	int lookahead = 32; // frames rendered ahead of the Tick sequence (set before Init; 0 = off)
 private:
 	static void Store( float* p, const float3& v ) { p[0] = v.x, p[1] = v.y, p[2] = v.z; }
 	rt_renderer* dev = nullptr;

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RT_B200_ABI_VERSION 1
+#define RT_B200_ABI_VERSION 2
 
 typedef int rt_status;
 enum {
@@ -202,6 +202,13 @@ typedef struct rt_render_params {
     int32_t tile_end;       /* (W/16)x(H/16) row-major tile grid; tile_end <= 0 = all tiles      */
     int32_t max_frames_in_flight; /* wavefront width = tiles x frames in flight; 0 = library default */
     int32_t schedule;       /* path tracer, RT_SEED_REFERENCE_TILE: how the (tile, frame) streams are advanced */
+    /* Path tracer, one-Tick-per-call use (rt_renderer_render with count == 1): render this many frames ahead in
+     * one launch, each into its own image, and add them to the accumulator one per call, in spp order.  The
+     * accumulator after every call is exactly what that many Renderer::Tick calls produce (frames depend only
+     * on scene, camera and their spp counter, 3. PathTracer/renderer.cpp:120), but a frame costs ~1 ms instead
+     * of the ~25 ms a single 256-pixel RNG chain per tile takes on its own.  A camera change discards the
+     * frames not yet shown.  0 / 1 = off.  Counters include the rays of frames rendered ahead. */
+    int32_t lookahead_frames;
 } rt_render_params;
 
 enum {

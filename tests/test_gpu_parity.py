@@ -420,3 +420,45 @@ def test_renderer_argument_errors(gpu_scenes):
     assert L.rt_measure_gather_bandwidth(0, 16, 1, C.byref(out)) == abi.RT_ERR_INVALID
     assert L.rt_measure_gather_bandwidth(99, 1 << 20, 1, C.byref(out)) == abi.RT_ERR_NO_DEVICE
     assert api.measure_gather_bandwidth(4 << 20) > 100.0
+
+
+def test_lookahead_ticks_reproduce_the_tick_sequence(oracles, gpu_scenes):
+    """lookahead_frames: frames are rendered ahead in one launch and revealed one per Tick, summed in spp order —
+    after EVERY Tick the accumulator is what the reference holds after that many Ticks; a camera change discards
+    the frames rendered ahead"""
+    from cpu_ray_tracer_b200 import api
+    from oracle import porthost
+    name = "golden_tlas"
+    po, sc = oracles(name), gpu_scenes(name, counters=False)
+    W, H, ticks, L = 128, 80, 7, 4
+    cam = po.camera_default(W, H)
+    p = porthost.default_params(abi.RT_INTEGRATOR_PATH, W, H)
+    r = api.GpuRenderer(sc, abi.RT_INTEGRATOR_PATH, W, H, lookahead_frames=L).Init()
+    single = api.GpuRenderer(sc, abi.RT_INTEGRATOR_PATH, W, H).Init()   # one frame per launch, no look-ahead
+    oacc, gsum = None, np.zeros((H, W, 4), np.float32)
+    for k in range(ticks):
+        oacc, _ = po.render_pt(cam, p, 1 + k, 1, 1, accumulator=oacc)
+        r.Tick(0)
+        g = r.accumulator
+        check_pt(g, oacc, k + 1, f"tick {k + 1}")
+        # the floats that differ from the oracle differ by libm ulps (expf, atan2f, acosf), not by summation order
+        same = (g[..., :3].view(np.uint32) == oacc[..., :3].view(np.uint32)).mean()
+        assert same > 0.95, f"tick {k + 1}: only {same:.4f} bit-identical"
+        # bit-exact against the frames rendered one by one and summed in spp order on the host
+        single.ClearAccumulator()
+        single.render(1, first_spp=1 + k)
+        gsum = gsum + single.accumulator
+        assert biteq(g[..., :3], gsum[..., :3]), f"tick {k + 1}: look-ahead accumulator differs from the ordered sum of single frames"
+    single.close()
+    assert r.spp == 1 + ticks
+    # 7 Ticks with 4 frames per launch: two launches rendered 8 frames
+    assert r.counters()["paths"] == W * H * 8
+    # camera change: the frame rendered ahead for spp 8 with the old camera must not be used
+    look = ((1.6, 0.9, -1.4), (0.0, -0.4, 1.0))
+    r.camera.SetCameraState(*look)
+    r.ClearAccumulator()
+    r.Tick(0)
+    cam2 = po.camera_look_at(look[0], look[1], W, H)
+    o2, _ = po.render_pt(cam2, p, 1 + ticks, 1, 1)
+    check_pt(r.accumulator, o2, 1, "after camera change")
+    r.close()
