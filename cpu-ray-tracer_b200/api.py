@@ -31,7 +31,7 @@ EXPORTS = [
     "rt_renderer_read_accumulator", "rt_renderer_read_pixels", "rt_renderer_device_accumulator",
     "rt_renderer_get_counters", "rt_renderer_reset_counters",
     "rt_renderer_set_profiling", "rt_renderer_get_stage_times", "rt_renderer_get_launch_spans",
-    "rt_renderer_get_queue_history", "rt_measure_gather_bandwidth",
+    "rt_renderer_get_queue_history", "rt_measure_gather_bandwidth", "rt_build_bvh",
 ]
 
 
@@ -88,6 +88,7 @@ def lib():
     L.rt_renderer_get_launch_spans.argtypes = [vp, vp, vp, sz, C.POINTER(sz)]
     L.rt_renderer_get_queue_history.argtypes = [vp, vp, sz, C.POINTER(sz)]
     L.rt_measure_gather_bandwidth.argtypes = [i32, sz, i32, C.POINTER(C.c_double)]
+    L.rt_build_bvh.argtypes = [i32, vp, C.c_uint32, vp, vp, C.POINTER(C.c_uint32), C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -99,6 +100,17 @@ def _check(status):
 
 def device_count():
     return lib().rt_device_count()
+
+
+def build_bvh_gpu(tris, device=0):
+    """BVH::Build on the GPU (rt_build_bvh): TRI_DTYPE array -> (nodes[:nodesUsed], tri_indices, kernel milliseconds)"""
+    tris = np.ascontiguousarray(tris, abi.TRI_DTYPE)
+    n = len(tris)
+    nodes = np.zeros(max(2 * n - 1, 1), abi.NODE_DTYPE)
+    idx = np.zeros(n, np.uint32)
+    used, ms = C.c_uint32(), C.c_double()
+    _check(lib().rt_build_bvh(device, tris.ctypes.data, n, nodes.ctypes.data, idx.ctypes.data, C.byref(used), C.byref(ms)))
+    return nodes[:used.value].copy(), idx, ms.value
 
 
 def measure_gather_bandwidth(working_set_bytes, bypass_l1=True, device=0):

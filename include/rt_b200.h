@@ -274,6 +274,17 @@ rt_status rt_renderer_get_launch_spans(rt_renderer* r, int32_t* stage, float* ms
 /* Path tracer: number of queued rays at every wavefront iteration of the last rt_renderer_render batch. */
 rt_status rt_renderer_get_queue_history(rt_renderer* r, int32_t* rays_per_iteration, size_t capacity, size_t* n);
 
+/* ---- scene construction on the device ----------------------------------- */
+
+/* BVH::Build / BLASBVH::Build (bvh.cpp:4-24, 45-178 = blas_bvh.cpp:82-257) on the GPU: binned SAH, 8 bins per
+ * axis, leaves of <= 2 triangles, the reference's cost model and its index partition.  Host buffers in, host
+ * buffers out, in the reference's layouts: nodes_out needs 2n - 1 entries, tri_indices_out n entries.  The
+ * output is bit-identical to what the reference's recursive builder produces (node boxes, node numbering and
+ * triangle order).  Triangle centroids are read from tris[i].centroid, as the reference's loaders set them.
+ * device_ms (optional) receives the kernel time without the host<->device copies. */
+rt_status rt_build_bvh(int device, const rt_tri* tris, uint32_t n, rt_bvh_node* nodes_out, uint32_t* tri_indices_out,
+                       uint32_t* nodes_used, double* device_ms);
+
 /* ---- diagnostics ------------------------------------------------------------------------------ */
 
 /* Measured bandwidth of random 64-byte record gathers (the size and alignment of one device BVH node) over

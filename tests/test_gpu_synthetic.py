@@ -65,3 +65,40 @@ def test_synthetic_path_tracer_vs_oracle(which, synth):
     assert np.nan_to_num(np.abs(r.accumulator - ow)).max() <= 2e-5
     r.close()
     sc.close()
+
+
+def _soup(n, seed):
+    """random triangle soup with clustered sizes, duplicate centroids and degenerate (zero-extent) axes"""
+    from cpu_ray_tracer_b200 import host_build
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(-3, 3, (n, 3)).astype(np.float32)
+    c[: n // 8] = c[0]                      # many identical centroids: bins collapse, splits fail
+    c[n // 8: n // 4, 1] = np.float32(0.5)  # a slab: one axis has zero centroid extent
+    e = rng.uniform(0.01, 0.4, (n, 3, 3)).astype(np.float32)
+    return host_build.make_tris(c + e[:, 0], c + e[:, 1], c + e[:, 2])
+
+
+@pytest.mark.parametrize("case", ["golden", "terrain", "soup_small", "soup", "tiny"])
+def test_gpu_bvh_builder_is_bit_identical_to_the_reference_builder(case, flat_scenes):
+    """rt_build_bvh (csrc/rt_build.cu) against host/bvh_build.cpp, which tests/test_host_build.py pins to the
+    reference's own builder: node boxes, node numbering and triangle order, bit for bit"""
+    from cpu_ray_tracer_b200 import api, host_build
+    if case == "golden":
+        fs = flat_scenes("golden_file")
+        sets = [fs.tris] + [flat_scenes("golden_tlas").tris[int(b["tri_offset"]):int(b["tri_offset"]) + int(b["tri_count"])]
+                            for b in flat_scenes("golden_tlas").blas_table]
+    elif case == "terrain":
+        sets = [host_build.terrain_mesh(150000, seed=11)]
+    elif case == "soup_small":
+        sets = [_soup(n, n) for n in (3, 4, 7, 33, 257, 1000)]
+    elif case == "soup":
+        sets = [_soup(200000, 5)]
+    else:
+        sets = [_soup(1, 1), _soup(2, 2)]
+    for tris in sets:
+        ref_nodes, ref_idx, _ = host_build.build_bvh(tris)
+        nodes, idx, ms = api.build_bvh_gpu(tris)
+        assert len(nodes) == len(ref_nodes), (case, len(tris))
+        assert np.array_equal(idx, ref_idx), f"{case}: triangle order differs ({(idx != ref_idx).sum()} of {len(idx)})"
+        assert nodes.tobytes() == ref_nodes.tobytes(), f"{case}: node array differs"
+        assert ms >= 0

@@ -63,3 +63,47 @@ def test_synthetic_scenes_are_well_formed_and_oracle_traceable():
     assert (hits["obj_idx"] >= 2).any() and st["blas_entries"] > 0
     with pytest.raises(ValueError):
         host_build.build_tlas(np.zeros((40000, 6), np.float32))   # 2 x 16-bit child indices
+
+
+def test_swap_partition_closed_form():
+    """the closed form the GPU builder (csrc/rt_build.cu) uses for the reference's two-cursor swap partition
+    (bvh.cpp:88-95), checked against the loop itself on random inputs"""
+    import random
+
+    def swap_loop(flags):
+        x = list(range(len(flags)))
+        i, j = 0, len(x) - 1
+        while i <= j:
+            if flags[x[i]]:
+                i += 1
+            else:
+                x[i], x[j] = x[j], x[i]
+                j -= 1
+        return x
+
+    def closed_form(flags):
+        n, G = len(flags), sum(flags)
+        left_bad = [p for p in range(G) if not flags[p]]
+        right_good_desc = [p for p in range(n - 1, G - 1, -1) if flags[p]]
+        M = len(left_bad)
+        out = [None] * n
+        for p in range(n):
+            good, left = flags[p], p < G
+            if good and left:
+                dst = p
+            elif not good and (left or p == G):
+                m = left_bad.index(p) + 1 if left else M + 1
+                dst = n - 1 if m == 1 else right_good_desc[m - 2] - 1
+            elif not good:
+                dst = p - 1
+            else:
+                dst = left_bad[right_good_desc.index(p)]
+            assert out[dst] is None
+            out[dst] = p
+        return out
+
+    rnd = random.Random(7)
+    for _ in range(20000):
+        n, pr = rnd.randint(1, 18), rnd.random()
+        flags = [rnd.random() < pr for _ in range(n)]
+        assert swap_loop(flags) == closed_form(flags), flags
