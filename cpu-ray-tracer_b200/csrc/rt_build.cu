@@ -103,41 +103,128 @@ __global__ void k_build_level_reset(BNode* nodes, int first, int count, float* _
     }
 }
 
-__global__ void k_build_centroid_bounds(int n, int first, const int* __restrict__ posNode, const uint32_t* __restrict__ idx,
-    const float* __restrict__ cen, BNode* nodes)
+// The three reductions into per-node records (centroid bounds, bins, child boxes) are where the build spends
+// its time: at the top levels millions of triangles target the same few addresses (95 % of the first version's
+// time, profiles/r1_gpu_bvh_build.jsonl).  Positions of a node are contiguous, so every CTA walks one
+// contiguous chunk of positions and keeps the record of the node it is currently inside in shared memory
+// (fast atomics, no global contention); it is flushed with one global atomic per word when the CTA crosses
+// into another node and at the end.  Positions of other nodes inside a step go straight to global memory,
+// which is where nodes are small and contention is low anyway.
+constexpr int BUILD_BLOCK = 256;
+
+__global__ void __launch_bounds__(BUILD_BLOCK) k_build_centroid_bounds(int n, int chunk, int first, const int* __restrict__ posNode,
+    const uint32_t* __restrict__ idx, const float* __restrict__ cen, BNode* nodes)
 {
-    for (int pos = blockIdx.x * blockDim.x + threadIdx.x; pos < n; pos += gridDim.x * blockDim.x)
+    __shared__ float sbox[6];
+    __shared__ int skey;
+    const int begin = blockIdx.x * chunk, end = min(n, begin + chunk);
+    int kcur = -1;
+    for (int base = begin; base < end; base += BUILD_BLOCK)
     {
-        const int k = posNode[pos];
-        if (k < first || nodes[k].count <= 2) continue;
-        const float* c = cen + 3 * (size_t)idx[pos];
-        for (int a = 0; a < 3; a++) atomic_min_float(&nodes[k].cmin[a], c[a]), atomic_max_float(&nodes[k].cmax[a], c[a]);
+        const int pos = base + threadIdx.x;
+        int k = pos < end ? posNode[pos] : -1;
+        if (k >= 0 && (k < first || nodes[k].count <= 2)) k = -1; // not a node that may split at this level
+        if (threadIdx.x == 0) skey = k;
+        __syncthreads();
+        const int kstep = skey;
+        if (kstep != kcur)
+        {
+            if (kcur >= 0 && threadIdx.x < 6)
+            {
+                if (threadIdx.x < 3) atomic_min_float(&nodes[kcur].cmin[threadIdx.x], sbox[threadIdx.x]);
+                else atomic_max_float(&nodes[kcur].cmax[threadIdx.x - 3], sbox[threadIdx.x]);
+            }
+            __syncthreads();
+            if (threadIdx.x < 6) sbox[threadIdx.x] = threadIdx.x < 3 ? 1e30f : -1e30f;
+            kcur = kstep;
+            __syncthreads();
+        }
+        if (k >= 0)
+        {
+            const float* c = cen + 3 * (size_t)idx[pos];
+            if (k == kcur)
+                for (int a = 0; a < 3; a++) atomic_min_float(&sbox[a], c[a]), atomic_max_float(&sbox[3 + a], c[a]);
+            else
+                for (int a = 0; a < 3; a++) atomic_min_float(&nodes[k].cmin[a], c[a]), atomic_max_float(&nodes[k].cmax[a], c[a]);
+        }
+        __syncthreads();
+    }
+    if (kcur >= 0 && threadIdx.x < 6)
+    {
+        if (threadIdx.x < 3) atomic_min_float(&nodes[kcur].cmin[threadIdx.x], sbox[threadIdx.x]);
+        else atomic_max_float(&nodes[kcur].cmax[threadIdx.x - 3], sbox[threadIdx.x]);
     }
 }
 
 // bvh.cpp:138-149: bin index per axis, bin count and bin bounds
-__global__ void k_build_bin(int n, int first, const int* __restrict__ posNode, const uint32_t* __restrict__ idx,
+__global__ void __launch_bounds__(BUILD_BLOCK) k_build_bin(int n, int chunk, int first, const int* __restrict__ posNode, const uint32_t* __restrict__ idx,
     const float* __restrict__ cen, const float* __restrict__ tmin, const float* __restrict__ tmax, const BNode* __restrict__ nodes,
     float* binB, int* binC)
 {
-    for (int pos = blockIdx.x * blockDim.x + threadIdx.x; pos < n; pos += gridDim.x * blockDim.x)
+    __shared__ float sB[3 * BINS * 6];
+    __shared__ int sC[3 * BINS];
+    __shared__ int skey;
+    const int begin = blockIdx.x * chunk, end = min(n, begin + chunk);
+    int kcur = -1;
+    auto flush = [&]() {
+        if (kcur < 0) return;
+        const size_t slot0 = (size_t)(kcur - first) * 3 * BINS;
+        for (int i = threadIdx.x; i < 3 * BINS; i += BUILD_BLOCK)
+            if (sC[i])
+            {
+                atomicAdd(&binC[slot0 + i], sC[i]);
+                float* bb = binB + 6 * (slot0 + i);
+                for (int c = 0; c < 3; c++) atomic_min_float(&bb[c], sB[6 * i + c]), atomic_max_float(&bb[3 + c], sB[6 * i + 3 + c]);
+            }
+    };
+    for (int base = begin; base < end; base += BUILD_BLOCK)
     {
-        const int k = posNode[pos];
-        if (k < first || nodes[k].count <= 2) continue;
-        const uint32_t t = idx[pos];
-        for (int a = 0; a < 3; a++)
+        const int pos = base + threadIdx.x;
+        int k = pos < end ? posNode[pos] : -1;
+        if (k >= 0 && (k < first || nodes[k].count <= 2)) k = -1;
+        if (threadIdx.x == 0) skey = k;
+        __syncthreads();
+        const int kstep = skey;
+        if (kstep != kcur)
         {
-            const float lo = nodes[k].cmin[a], hi = nodes[k].cmax[a];
-            if (lo == hi) continue;
-            const float scale = BINS / (hi - lo);
-            int b = (int)((cen[3 * (size_t)t + a] - lo) * scale);
-            if (b > BINS - 1) b = BINS - 1;
-            const size_t slot = ((size_t)(k - first) * 3 + a) * BINS + b;
-            atomicAdd(&binC[slot], 1);
-            float* bb = binB + 6 * slot;
-            for (int c = 0; c < 3; c++) atomic_min_float(&bb[c], tmin[3 * (size_t)t + c]), atomic_max_float(&bb[3 + c], tmax[3 * (size_t)t + c]);
+            flush();
+            __syncthreads();
+            for (int i = threadIdx.x; i < 3 * BINS; i += BUILD_BLOCK)
+            {
+                sC[i] = 0;
+                for (int c = 0; c < 3; c++) sB[6 * i + c] = 1e34f, sB[6 * i + 3 + c] = -1e34f;
+            }
+            kcur = kstep;
+            __syncthreads();
         }
+        if (k >= 0)
+        {
+            const uint32_t t = idx[pos];
+            for (int a = 0; a < 3; a++)
+            {
+                const float lo = nodes[k].cmin[a], hi = nodes[k].cmax[a];
+                if (lo == hi) continue;
+                const float scale = BINS / (hi - lo);
+                int b = (int)((cen[3 * (size_t)t + a] - lo) * scale);
+                if (b > BINS - 1) b = BINS - 1;
+                if (k == kcur)
+                {
+                    const int i = a * BINS + b;
+                    atomicAdd(&sC[i], 1);
+                    for (int c = 0; c < 3; c++) atomic_min_float(&sB[6 * i + c], tmin[3 * (size_t)t + c]), atomic_max_float(&sB[6 * i + 3 + c], tmax[3 * (size_t)t + c]);
+                }
+                else
+                {
+                    const size_t slot = ((size_t)(k - first) * 3 + a) * BINS + b;
+                    atomicAdd(&binC[slot], 1);
+                    float* bb = binB + 6 * slot;
+                    for (int c = 0; c < 3; c++) atomic_min_float(&bb[c], tmin[3 * (size_t)t + c]), atomic_max_float(&bb[3 + c], tmax[3 * (size_t)t + c]);
+                }
+            }
+        }
+        __syncthreads();
     }
+    flush();
 }
 
 __device__ __forceinline__ float box_area(const float* mn, const float* mx) // aabb::Area, tmplmath.h:593-598
@@ -306,20 +393,53 @@ __global__ void k_build_children(BNode* nodes, int first, int count, const int* 
     }
 }
 
-// UpdateNodeBounds of both children (bvh.cpp:110-111) + the node of every position for the next level
-__global__ void k_build_descend(int n, int first, int* __restrict__ posNode, const uint32_t* __restrict__ idx,
+// UpdateNodeBounds of both children (bvh.cpp:110-111) + the node of every position for the next level;
+// the two child boxes of the node a CTA is inside live in shared memory (see k_build_centroid_bounds)
+__global__ void __launch_bounds__(BUILD_BLOCK) k_build_descend(int n, int chunk, int first, int* __restrict__ posNode, const uint32_t* __restrict__ idx,
     const float* __restrict__ tmin, const float* __restrict__ tmax, BNode* nodes)
 {
-    for (int pos = blockIdx.x * blockDim.x + threadIdx.x; pos < n; pos += gridDim.x * blockDim.x)
+    __shared__ float sbox[12]; // left min, left max, right min, right max
+    __shared__ int skey;
+    const int begin = blockIdx.x * chunk, end = min(n, begin + chunk);
+    int kcur = -1;
+    auto flush = [&]() {
+        if (kcur < 0 || threadIdx.x >= 12) return;
+        BNode& c = nodes[nodes[kcur].left + threadIdx.x / 6];
+        const int w = threadIdx.x % 6;
+        if (w < 3) atomic_min_float(&c.bmin[w], sbox[threadIdx.x]);
+        else atomic_max_float(&c.bmax[w - 3], sbox[threadIdx.x]);
+    };
+    for (int base = begin; base < end; base += BUILD_BLOCK)
     {
-        const int k = posNode[pos];
-        if (k < first || !nodes[k].splitting) continue;
-        const int child = nodes[k].left + (((uint32_t)pos - nodes[k].start < nodes[k].leftCount) ? 0 : 1);
-        posNode[pos] = child;
-        const uint32_t t = idx[pos];
-        for (int a = 0; a < 3; a++)
-            atomic_min_float(&nodes[child].bmin[a], tmin[3 * (size_t)t + a]), atomic_max_float(&nodes[child].bmax[a], tmax[3 * (size_t)t + a]);
+        const int pos = base + threadIdx.x;
+        int k = pos < end ? posNode[pos] : -1;
+        if (k >= 0 && (k < first || !nodes[k].splitting)) k = -1;
+        if (threadIdx.x == 0) skey = k;
+        __syncthreads();
+        const int kstep = skey;
+        if (kstep != kcur)
+        {
+            flush();
+            __syncthreads();
+            if (threadIdx.x < 12) sbox[threadIdx.x] = (threadIdx.x % 6) < 3 ? 1e30f : -1e30f;
+            kcur = kstep;
+            __syncthreads();
+        }
+        if (k >= 0)
+        {
+            const int side = ((uint32_t)pos - nodes[k].start < nodes[k].leftCount) ? 0 : 1;
+            const int child = nodes[k].left + side;
+            posNode[pos] = child;
+            const uint32_t t = idx[pos];
+            if (k == kcur)
+                for (int a = 0; a < 3; a++) atomic_min_float(&sbox[6 * side + a], tmin[3 * (size_t)t + a]), atomic_max_float(&sbox[6 * side + 3 + a], tmax[3 * (size_t)t + a]);
+            else
+                for (int a = 0; a < 3; a++)
+                    atomic_min_float(&nodes[child].bmin[a], tmin[3 * (size_t)t + a]), atomic_max_float(&nodes[child].bmax[a], tmax[3 * (size_t)t + a]);
+        }
+        __syncthreads();
     }
+    flush();
 }
 
 __global__ void k_build_count_interior(BNode* nodes, int first, int count)
@@ -416,6 +536,8 @@ extern "C" rt_status rt_build_bvh(int device, const rt_tri* tris, uint32_t n, rt
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     const int grid = sms * 8, block = 256;
+    // contiguous chunk of positions per CTA for the privatised reductions (a multiple of the CTA size)
+    const int chunk = (int)((((size_t)N + grid - 1) / grid + BUILD_BLOCK - 1) / BUILD_BLOCK * BUILD_BLOCK);
     auto gridFor = [&](size_t items) { const size_t g = (items + block - 1) / block; return (int)(g < (size_t)grid ? (g ? g : 1) : grid); };
 
     RT_CUDA(cudaMemcpy(dTris, tris, (size_t)n * sizeof(rt_tri), cudaMemcpyHostToDevice));
@@ -444,8 +566,8 @@ extern "C" rt_status rt_build_bvh(int device, const rt_tri* tris, uint32_t n, rt
             }
         }
         k_build_level_reset<<<gridFor((size_t)count * 3 * BINS), block>>>(nodes, first, count, binB, binC);
-        k_build_centroid_bounds<<<grid, block>>>(N, first, posNode, idx, cen, nodes);
-        k_build_bin<<<grid, block>>>(N, first, posNode, idx, cen, tmin, tmax, nodes, binB, binC);
+        k_build_centroid_bounds<<<grid, BUILD_BLOCK>>>(N, chunk, first, posNode, idx, cen, nodes);
+        k_build_bin<<<grid, BUILD_BLOCK>>>(N, chunk, first, posNode, idx, cen, tmin, tmax, nodes, binB, binC);
         k_build_split<<<gridFor(count), block>>>(nodes, first, count, binB, binC);
         k_build_flags<<<grid, block>>>(N, first, posNode, idx, cen, nodes, good);
         cub::DeviceScan::ExclusiveSumByKey(temp, tempBytes, posNode, good, goodBefore, N);
@@ -468,7 +590,7 @@ extern "C" rt_status rt_build_bvh(int device, const rt_tri* tris, uint32_t n, rt
         {
             k_build_node_init<<<gridFor(nextCount), block>>>(nodes, nextFirst, nextCount, 0u, 0u);
             k_build_children<<<gridFor(count), block>>>(nodes, first, count, rank, nextFirst);
-            k_build_descend<<<grid, block>>>(N, first, posNode, idx, tmin, tmax, nodes);
+            k_build_descend<<<grid, BUILD_BLOCK>>>(N, chunk, first, posNode, idx, tmin, tmax, nodes);
         }
         total += nextCount;
         first = nextFirst, count = nextCount;

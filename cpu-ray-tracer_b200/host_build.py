@@ -133,9 +133,11 @@ def _materials(kinds):
     return m
 
 
-def flat_scene_from_tris(tris, materials=None):
-    """FileScene + USE_BVH equivalent: one SAH BVH over all triangles, generated sky, untextured floor"""
-    nodes, idx, _ = build_bvh(tris)
+def flat_scene_from_tris(tris, materials=None, builder=None):
+    """FileScene + USE_BVH equivalent: one SAH BVH over all triangles, generated sky, untextured floor.
+    builder: callable(tris) -> (nodes, tri_indices, _); default = the host restatement, api.build_bvh_gpu = the
+    GPU builder (same arrays bit for bit)"""
+    nodes, idx, _ = (builder or build_bvh)(tris)
     sky, w, h = _gradient_sky()
     bt = np.zeros(1, BLAS_TABLE_DTYPE)
     bt[0]["node_count"], bt[0]["tri_count"] = len(nodes), len(tris)
