@@ -5,7 +5,7 @@ import ctypes as C
 import numpy as np
 
 RT_OK, RT_ERR_INVALID, RT_ERR_NO_DEVICE, RT_ERR_CUDA, RT_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
-RT_SCENE_FLAT, RT_SCENE_TLAS = 0, 1
+RT_SCENE_FLAT, RT_SCENE_TLAS, RT_SCENE_FLAT_KDTREE, RT_SCENE_FLAT_GRID = 0, 1, 2, 3
 RT_SCENE_FLAG_COUNTERS = 1
 RT_INTEGRATOR_WHITTED, RT_INTEGRATOR_PATH = 0, 1
 RT_SEED_REFERENCE_TILE, RT_SEED_PER_PIXEL = 0, 1
@@ -30,6 +30,11 @@ class rt_texture(C.Structure):
     _fields_ = [("pixels", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32)]
 
 
+class rt_grid_desc(C.Structure):
+    _fields_ = [("resolution", C.c_int32 * 3), ("cell_size", f3), ("bounds_min", f3), ("bounds_max", f3),
+                ("cell_start", C.c_void_p), ("tri_indices", C.c_void_p), ("index_count", C.c_uint32)]
+
+
 class rt_scene_desc(C.Structure):
     _fields_ = [("kind", C.c_int32),
                 ("blas", C.POINTER(rt_blas_desc)), ("blas_count", C.c_uint32),
@@ -40,7 +45,10 @@ class rt_scene_desc(C.Structure):
                 ("skydome_texture", C.c_int32), ("floor_texture", C.c_int32),
                 ("floor_n", f3), ("floor_d", C.c_float), ("floor_invto", C.c_float),
                 ("light_T", f16), ("light_inv_T", f16), ("light_size", C.c_float),
-                ("light_color", f3), ("light_pos", f3)]
+                ("light_color", f3), ("light_pos", f3),
+                ("kd_nodes", C.c_void_p), ("kd_node_count", C.c_uint32),
+                ("kd_tri_indices", C.c_void_p), ("kd_tri_index_count", C.c_uint32),
+                ("grid", C.POINTER(rt_grid_desc))]
 
 
 class rt_camera(C.Structure):
@@ -72,10 +80,14 @@ TRI_DTYPE = np.dtype([("v0", "<f4", 3), ("v1", "<f4", 3), ("v2", "<f4", 3),
                       ("uv0", "<f4", 2), ("uv1", "<f4", 2), ("uv2", "<f4", 2),
                       ("centroid", "<f4", 3), ("obj_idx", "<i4")])
 TLAS_NODE_DTYPE = np.dtype([("aabb_min", "<f4", 3), ("left_right", "<u4"), ("aabb_max", "<f4", 3), ("blas", "<u4")])
+KD_NODE_DTYPE = np.dtype([("aabb_min", "<f4", 3), ("left", "<i4"), ("aabb_max", "<f4", 3), ("right", "<i4"),
+                          ("split_axis", "<i4"), ("split_distance", "<f4"), ("tri_start", "<u4"), ("tri_count", "<u4")])
+GRID_HEADER_DTYPE = np.dtype([("resolution", "<i4", 3), ("cell_size", "<f4", 3), ("bounds_min", "<f4", 3), ("bounds_max", "<f4", 3)])
 MATERIAL_DTYPE = np.dtype([("reflectivity", "<f4"), ("refractivity", "<f4"), ("absorption", "<f4", 3),
                            ("albedo", "<f4", 3), ("is_light", "<i4"), ("texture", "<i4")])
 RAY_DTYPE = np.dtype([("O", "<f4", 3), ("tmax", "<f4"), ("D", "<f4", 3), ("inside", "<i4")])
 HIT_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("obj_idx", "<i4"), ("tri_idx", "<i4"),
                       ("traversed", "<i4"), ("tested", "<i4"), ("reserved", "<i4")])
 assert NODE_DTYPE.itemsize == 32 and TRI_DTYPE.itemsize == 112 and TLAS_NODE_DTYPE.itemsize == 32
+assert KD_NODE_DTYPE.itemsize == 48 and GRID_HEADER_DTYPE.itemsize == 48
 assert MATERIAL_DTYPE.itemsize == 40 and RAY_DTYPE.itemsize == 32 and HIT_DTYPE.itemsize == 32

@@ -153,7 +153,7 @@ class GpuScene:
     def __init__(self, flat: FlatScene, device=0, counters=False):
         if isinstance(flat, (str, os.PathLike)):
             flat = FlatScene.load(flat)
-        if self.KIND is not None and flat.kind != self.KIND:
+        if self.KIND is not None and flat.kind not in self.KIND:
             raise ValueError(f"{type(self).__name__} needs a scene of kind {self.KIND}, got {flat.kind}")
         self.flat = flat
         self.device = device
@@ -204,13 +204,14 @@ class GpuScene:
 
 
 class GpuFileScene(GpuScene):
-    """FileScene with USE_BVH (infra/scene/file_scene.h): one flat SAH BVH over all triangles."""
-    KIND = abi.RT_SCENE_FLAT
+    """FileScene (infra/scene/file_scene.h) with the accelerator its file_scene.h:10-12 switch selects: one flat
+    SAH BVH over all triangles (USE_BVH), the KD-tree it ships with (USE_KDTree) or the uniform grid (USE_Grid)."""
+    KIND = (abi.RT_SCENE_FLAT, abi.RT_SCENE_FLAT_KDTREE, abi.RT_SCENE_FLAT_GRID)
 
 
 class GpuTLASFileScene(GpuScene):
     """TLASFileScene with TLAS_USE_BVH (infra/scene/tlas_file_scene.h): TLAS over per-object BLAS."""
-    KIND = abi.RT_SCENE_TLAS
+    KIND = (abi.RT_SCENE_TLAS,)
 
 
 def open_scene(path_or_flat, device=0, counters=False):

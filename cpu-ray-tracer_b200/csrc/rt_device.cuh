@@ -64,13 +64,21 @@ struct DScene {
     const DMaterial* materials;
     const DTexture* textures;
     int root_ref;
-    int kind;          // RT_SCENE_FLAT / RT_SCENE_TLAS
+    int kind;          // RT_SCENE_FLAT / RT_SCENE_TLAS / RT_SCENE_FLAT_KDTREE / RT_SCENE_FLAT_GRID
     int flat_obj_idx;  // objIdx override for the flat BVH (-1: take the triangle's)
     int skydome_texture, floor_texture;
     float floor_n[3], floor_d, floor_invto;
     float light_T[16], light_inv_T[16], light_size;
     float light_color[3], light_pos[3];
+    // the other two FileScene accelerators (layouts documented next to their traversals below)
+    const float4* kd_nodes;   // RT_SCENE_FLAT_KDTREE: 32-byte nodes, node 0 = root
+    const int2* grid_cells;   // RT_SCENE_FLAT_GRID: (first triangle slot, count) per cell
+    int grid_res[3];
+    float grid_cell[3], grid_min[3], grid_max[3];
 };
+
+// which accelerator a kernel is compiled for (template parameter, so the BVH kernels carry no extra code)
+enum { ACCEL_BVH = 0 /* flat BVH and TLAS */, ACCEL_KD = 2, ACCEL_GRID = 3 };
 
 // ------------------------------------------------------------------------------------------------
 // float3 helpers, written so that each reference expression maps 1:1 (template/tmplmath.h)
@@ -465,8 +473,185 @@ __device__ __forceinline__ void trace_queue(const DScene& s, Src& src, const int
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// KD-tree (FileScene as the reference ships it, file_scene.h:10-12).
+//   Device node, 32 B = 2 x float4 (built by rt_scene.cu from rt_kd_node, children made adjacent):
+//     k0 = (min.x, min.y, min.z, max.x)
+//     k1 = (max.y, max.z, int a, b)    interior: a = left << 2 | axis (right = left + 1), b = float split plane
+//                                      leaf:     a = ~first triangle slot,               b = int triangle count
+//   Leaf triangles are copies in leaf order in `tris` (same 48-byte records as the BVH; a triangle that
+//   straddles split planes is stored once per leaf that lists it), so a leaf is one contiguous run.
+//   Traversal: KDTree::IntersectKDTree (kdtree.cpp:148-209) with the recursion unrolled onto a stack of
+//   (far child, split t): the reference returns from a node without visiting the far child when
+//   `ray.t < t` after the near child (:184, :203) - that test is made when the entry is popped, with the
+//   ray.t of that moment, exactly as the recursion does.  Every node's own box is slab-tested on entry
+//   (:151-152, tmin / tmax feed the child choice), the split distance is a true division (:172), and the
+//   `tmin + 0.001` / `tmax - 0.001` comparisons are carried out in double like the reference's literals.
+// ------------------------------------------------------------------------------------------------
+constexpr int KD_STACK_SIZE = 32; // rt_scene_create rejects trees deeper than this (the reference stops at depth 20)
+
+__device__ __forceinline__ bool slab_range(float3 O, float3 rD, float rayT, bool exact,
+    float bminx, float bminy, float bminz, float bmaxx, float bmaxy, float bmaxz, float& tminOut, float& tmaxOut)
+{
+    const float tx1 = (bminx - O.x) * rD.x, tx2 = (bmaxx - O.x) * rD.x;
+    const float ty1 = (bminy - O.y) * rD.y, ty2 = (bmaxy - O.y) * rD.y;
+    const float tz1 = (bminz - O.z) * rD.z, tz2 = (bmaxz - O.z) * rD.z;
+    float tmin, tmax;
+    if (!exact)
+    {
+        tmin = fminf(tx1, tx2), tmax = fmaxf(tx1, tx2);
+        tmin = fmaxf(tmin, fminf(ty1, ty2)), tmax = fminf(tmax, fmaxf(ty1, ty2));
+        tmin = fmaxf(tmin, fminf(tz1, tz2)), tmax = fminf(tmax, fmaxf(tz1, tz2));
+    }
+    else
+    {
+        tmin = smin(tx1, tx2), tmax = smax(tx1, tx2);
+        tmin = smax(tmin, smin(ty1, ty2)), tmax = smin(tmax, smax(ty1, ty2));
+        tmin = smax(tmin, smin(tz1, tz2)), tmax = smin(tmax, smax(tz1, tz2));
+    }
+    tminOut = tmin, tmaxOut = tmax;
+    return tmax >= tmin && tmin < rayT && tmax > 0;
+}
+
+__device__ __forceinline__ float axis_of(float3 a, int axis) { return axis == 0 ? a.x : (axis == 1 ? a.y : a.z); }
+
+// One leaf / cell: `count` consecutive triangle records starting at `slot` (kdtree.cpp:155-161, grid.cpp:124-137).
+template <bool ANYHIT, bool COUNTERS>
+__device__ __forceinline__ bool test_run(const float4* __restrict__ tris, int slot, int count, float3 O, float3 D, HitRec& hit)
+{
+    for (int i = 0; i < count; i++, slot++)
+    {
+        const float4* T = tris + 3 * (size_t)slot;
+        const float4 t0 = __ldg(T), t1 = __ldg(T + 1), t2 = __ldg(T + 2);
+        if (COUNTERS) hit.tested++;
+        if (intersect_tri(O, D, f3(t0.x, t0.y, t0.z), f3(t1.x, t1.y, t1.z), f3(t2.x, t2.y, t2.z), hit.t, hit.u, hit.v))
+        {
+            hit.tri = __float_as_int(t0.w) & ~LAST_BIT;
+            hit.obj = __float_as_int(t1.w);
+            if (ANYHIT) return true;
+        }
+    }
+    return false;
+}
+
+template <bool ANYHIT, bool COUNTERS>
+__device__ __forceinline__ void traverse_kd(const DScene& s, const float3 O, const float3 D, HitRec& hit)
+{
+    const float3 rD = recip(D);
+    const bool exact = needs_exact_slab(O, D);
+    const float4* __restrict__ nodes = s.kd_nodes;
+    int stackNode[KD_STACK_SIZE];
+    float stackT[KD_STACK_SIZE];
+    int sp = 0, cur = 0;
+    while (true)
+    {
+        if (COUNTERS) hit.traversed++;
+        const float4 k0 = __ldg(nodes + 2 * (size_t)cur), k1 = __ldg(nodes + 2 * (size_t)cur + 1);
+        float tmin, tmax;
+        bool descend = false;
+        if (slab_range(O, rD, hit.t, exact, k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, tmin, tmax))
+        {
+            const int a = __float_as_int(k1.z);
+            if (a < 0)
+            {
+                if (test_run<ANYHIT, COUNTERS>(s.tris, ~a, __float_as_int(k1.w), O, D, hit)) return;
+            }
+            else
+            {
+                const int axis = a & 3, left = a >> 2;
+                const float Da = axis_of(D, axis);
+                const float t = (k1.w - axis_of(O, axis)) / Da;        // kdtree.cpp:171-172
+                const bool pos = Da > 0;
+                const int nearC = pos ? left : left + 1, farC = pos ? left + 1 : left;
+                if ((double)t < (double)tmin + 0.001) cur = farC;       // :177 / :196: only the far side is crossed
+                else if ((double)t > (double)tmax - 0.001) cur = nearC; // :182 / :201
+                else stackNode[sp] = farC, stackT[sp] = t, sp++, cur = nearC;
+                descend = true;
+            }
+        }
+        if (descend) continue;
+        while (true)
+        {
+            if (sp == 0) return;
+            sp--;
+            if (!(hit.t < stackT[sp])) { cur = stackNode[sp]; break; } // :189 / :208 `if (ray.t < t) return;`
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Uniform grid: Grid::IntersectGrid (grid.cpp:94-153), 3D-DDA without mailboxing (grid.h:7).
+//   Device layout: grid_cells[cell] = (first triangle slot, count), triangles copied in cell order into
+//   `tris` (a triangle overlapping several cells is stored once per cell).
+//   cvtt_x86: static_cast<int>(float) on the reference's x86 build (cvttss2si) yields INT_MIN for NaN and for
+//   values outside int range; CUDA's conversion saturates, so the out-of-range case is restated.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int cvtt_x86(float x)
+{
+    return (x >= 2147483648.0f || x < -2147483648.0f || x != x) ? (int)0x80000000u : (int)x;
+}
+
+template <bool ANYHIT, bool COUNTERS>
+__device__ __forceinline__ void traverse_grid(const DScene& s, const float3 O, const float3 D, HitRec& hit)
+{
+    const float3 rD = recip(D);
+    float tminU, tmaxU;
+    if (!slab_range(O, rD, hit.t, needs_exact_slab(O, D), s.grid_min[0], s.grid_min[1], s.grid_min[2],
+                    s.grid_max[0], s.grid_max[1], s.grid_max[2], tminU, tmaxU)) return;
+    int cell[3], step[3], exitc[3];
+    float deltaT[3], nextT[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+    {
+        const float rayOrigCell = axis_of(O, i) - s.grid_min[i];
+        cell[i] = clampi(cvtt_x86(floorf(rayOrigCell / s.grid_cell[i])), 0, s.grid_res[i] - 1);
+        if (axis_of(D, i) < 0)
+        {
+            deltaT[i] = -s.grid_cell[i] * axis_of(rD, i);
+            nextT[i] = (cell[i] * s.grid_cell[i] - rayOrigCell) * axis_of(rD, i);
+            exitc[i] = -1, step[i] = -1;
+        }
+        else
+        {
+            deltaT[i] = s.grid_cell[i] * axis_of(rD, i);
+            nextT[i] = ((cell[i] + 1) * s.grid_cell[i] - rayOrigCell) * axis_of(rD, i);
+            exitc[i] = s.grid_res[i], step[i] = 1;
+        }
+    }
+    const int resX = s.grid_res[0], resXY = s.grid_res[0] * s.grid_res[1];
+    while (true)
+    {
+        if (COUNTERS) hit.traversed++;
+        const int2 c = __ldg(s.grid_cells + (unsigned)(cell[0] + cell[1] * resX + cell[2] * resXY));
+        if (test_run<ANYHIT, COUNTERS>(s.tris, c.x, c.y, O, D, hit)) return;
+        // grid.cpp:139-144: k = (x<y)<<2 | (x<z)<<1 | (y<z), map = {2,1,2,1,2,2,0,0}
+        const bool xy = nextT[0] < nextT[1], xz = nextT[0] < nextT[2], yz = nextT[1] < nextT[2];
+        const int axis = xy ? (xz ? 0 : 2) : (yz ? 1 : 2);
+        // the unrolled selects keep cell / nextT in registers (no dynamically indexed local arrays)
+        const float nt = axis == 0 ? nextT[0] : (axis == 1 ? nextT[1] : nextT[2]);
+        if (hit.t < nt) return;
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            if (axis == i) cell[i] += step[i];
+        const int ca = axis == 0 ? cell[0] : (axis == 1 ? cell[1] : cell[2]);
+        const int ea = axis == 0 ? exitc[0] : (axis == 1 ? exitc[1] : exitc[2]);
+        if (ca == ea) return;
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            if (axis == i) nextT[i] += deltaT[i];
+    }
+}
+
+template <int ACCEL, bool ANYHIT, bool COUNTERS>
+__device__ __forceinline__ void accel_traverse(const DScene& s, const float3 O, const float3 D, HitRec& hit)
+{
+    if (ACCEL == ACCEL_KD) traverse_kd<ANYHIT, COUNTERS>(s, O, D, hit);
+    else if (ACCEL == ACCEL_GRID) traverse_grid<ANYHIT, COUNTERS>(s, O, D, hit);
+    else traverse<ANYHIT, COUNTERS>(s, O, D, hit);
+}
+
 // BaseScene::FindNearest: file_scene.cpp:170-175 = tlas_file_scene.cpp:201-206
-template <bool COUNTERS>
+template <bool COUNTERS, int ACCEL = ACCEL_BVH>
 __device__ __forceinline__ void find_nearest(const DScene& s, float3 O, float3 D, float tmax, HitRec& hit)
 {
     hit.t = tmax, hit.u = 0, hit.v = 0, hit.obj = -1, hit.tri = -1, hit.traversed = 0, hit.tested = 0;
@@ -478,18 +663,21 @@ __device__ __forceinline__ void find_nearest(const DScene& s, float3 O, float3 D
         const float t = -(dot(O, N) + s.floor_d) / (dot(D, N));
         if (t < hit.t && t > 0) hit.t = t, hit.obj = 1;
     }
-    traverse<false, COUNTERS>(s, O, D, hit);
+    accel_traverse<ACCEL, false, COUNTERS>(s, O, D, hit);
 }
 
 // BaseScene::IsOccluded: file_scene.cpp:177-187 = tlas_file_scene.cpp:208-218 (SURVEY quirk Q2:
-// geometry is tested with t = 1e34, the floor never occludes, the light quad uses the real t)
+// geometry is tested with t = 1e34, the floor never occludes, the light quad uses the real t).
+// Any-hit is exact for all three accelerators: the reference runs its closest-hit traversal and only asks
+// whether objIdx was set, and until the first accepted triangle the visiting order is the same.
+template <int ACCEL = ACCEL_BVH>
 __device__ __forceinline__ bool is_occluded(const DScene& s, float3 O, float3 D, float tmax)
 {
     float tq;
     if (quad_test(s, O, D, tmax, tq)) return true;
     HitRec hit;
     hit.t = 1e34f, hit.u = 0, hit.v = 0, hit.obj = -1, hit.tri = -1, hit.traversed = 0, hit.tested = 0;
-    traverse<true, false>(s, O, D, hit);
+    accel_traverse<ACCEL, true, false>(s, O, D, hit);
     return hit.obj > -1;
 }
 

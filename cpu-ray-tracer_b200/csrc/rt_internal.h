@@ -31,6 +31,8 @@ struct rt_scene {
     float4* inst = nullptr;
     float4* shade = nullptr;
     float4* inst_shade = nullptr;
+    float4* kd_nodes = nullptr;   // RT_SCENE_FLAT_KDTREE
+    int2* grid_cells = nullptr;   // RT_SCENE_FLAT_GRID
     int* obj_material = nullptr;
     rtb::DMaterial* materials = nullptr;
     rtb::DTexture* textures = nullptr;

@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(256) k_pt_generate(const PTState p, const DCam
     if (blockIdx.x == 0 && threadIdx.x == 0) p.count[0] = p.slots, p.count[1] = 0, p.count[4] = 0;
 }
 
+template <int ACCEL>
 __global__ void __launch_bounds__(128) k_pt_extend(const PTState p, const DScene s, int cur)
 {
     const int n = p.count[cur];
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(128) k_pt_extend(const PTState p, const DScene
         const int slot = active[i];
         const float4 o = p.rayO[slot], d = p.rayD[slot];
         HitRec h;
-        find_nearest<false>(s, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), 1e34f, h);
+        find_nearest<false, ACCEL>(s, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), 1e34f, h);
         p.hit[slot] = make_float4(h.t, h.u, h.v, __int_as_float(h.obj));
         p.hitTri[slot] = h.tri;
     }
@@ -859,6 +860,7 @@ __global__ void __launch_bounds__(256) k_wh_generate(const WhState p, const DCam
     if (blockIdx.x == 0 && threadIdx.x == 0) p.count[0] = n, p.count[1] = 0, p.count[2] = 0, p.count[4] = 0, p.count[5] = 0;
 }
 
+template <int ACCEL>
 __global__ void __launch_bounds__(128) k_wh_extend(const WhState p, const DScene s, int cur)
 {
     const int n = min(p.count[cur], p.capacity);
@@ -866,7 +868,7 @@ __global__ void __launch_bounds__(128) k_wh_extend(const WhState p, const DScene
     {
         const float4 o = p.rayO[cur][i], d = p.rayD[cur][i];
         HitRec h;
-        find_nearest<false>(s, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), 1e34f, h);
+        find_nearest<false, ACCEL>(s, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), 1e34f, h);
         p.hit[i] = make_float4(h.t, h.u, h.v, __int_as_float(h.obj));
         p.hitTri[i] = h.tri;
     }
@@ -1051,6 +1053,7 @@ __global__ void __launch_bounds__(128) k_wh_shade(const WhState p, const DScene 
 
 // connect: shadow rays in their own any-hit kernel (IsOccluded, file_scene.cpp:177-187), then
 // out_radiance += diffuseness * brdf * (irradiance + ambient) (renderer.cpp:74-79)
+template <int ACCEL>
 __global__ void __launch_bounds__(128) k_wh_connect(const WhState p, const DScene s)
 {
     const int n = min(p.count[2], p.capacity);
@@ -1058,7 +1061,7 @@ __global__ void __launch_bounds__(128) k_wh_connect(const WhState p, const DScen
     {
         const float4* e = p.shadow + 5 * (size_t)i;
         const float4 a = e[0], b = e[1], w = e[2], c = e[3], ir = e[4];
-        const bool occluded = is_occluded(s, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w);
+        const bool occluded = is_occluded<ACCEL>(s, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w);
         const float3 irradiance = occluded ? f3(0, 0, 0) : f3(ir.x, ir.y, ir.z);
         const float3 ambient = f3(0.3f, 0.3f, 0.3f);
         splat(p.accum, __float_as_int(b.w), f3(w.x, w.y, w.z) * (f3(c.x, c.y, c.z) * (irradiance + ambient)));
@@ -1298,6 +1301,8 @@ rt_status rt_renderer_create(rt_scene* scene, const rt_render_params* params, rt
         // path-tracer schedule: params->schedule, overridable for A/B runs with RT_B200_PT_SCHEDULE
         r->useStreams = params->schedule != RT_SCHEDULE_WAVEFRONT;
         if ((e = getenv("RT_B200_PT_SCHEDULE")) != nullptr) r->useStreams = strcmp(e, "wavefront") != 0;
+        const bool altAccel = scene->d.kind == RT_SCENE_FLAT_KDTREE || scene->d.kind == RT_SCENE_FLAT_GRID;
+        if (altAccel) r->useStreams = false; // the stream kernels' state machine is written for the BVH
         if ((e = getenv("RT_B200_STREAM_KERNEL")) != nullptr && atoi(e) > 0) r->streamKernel = atoi(e);
         if ((e = getenv("RT_B200_STREAM_LPT")) != nullptr) r->streamLpt = atoi(e) != 0;
         int occ = 0;
@@ -1551,6 +1556,7 @@ static rt_status render_pt(rt_renderer* r, int first_spp, int count, int stride)
     p.W = P.width, p.H = P.height, p.depthLimit = P.depth_limit, p.seedMode = P.seed_mode, p.eps = P.epsilon;
     p.stride = stride;
     const int grid = r->sms * 8;
+    const int kind = r->scene->d.kind;
     // every path makes at most depth_limit + 1 FindNearest queries, every slot 256 paths
     const int maxIters = 256 * (P.depth_limit + 1) + 1;
     for (int done = 0; done < count; done += inFlight)
@@ -1568,8 +1574,10 @@ static rt_status render_pt(rt_renderer* r, int first_spp, int count, int stride)
             p.iteration = it;
             r->ptIterations = it + 1;
             r->prof_begin();
-            if (r->persistent) k_pt_extend_persistent<<<grid, 128, 0, r->stream>>>(p, r->scene->d, cur);
-            else k_pt_extend<<<grid, 128, 0, r->stream>>>(p, r->scene->d, cur);
+            if (kind == RT_SCENE_FLAT_KDTREE) k_pt_extend<ACCEL_KD><<<grid, 128, 0, r->stream>>>(p, r->scene->d, cur);
+            else if (kind == RT_SCENE_FLAT_GRID) k_pt_extend<ACCEL_GRID><<<grid, 128, 0, r->stream>>>(p, r->scene->d, cur);
+            else if (r->persistent) k_pt_extend_persistent<<<grid, 128, 0, r->stream>>>(p, r->scene->d, cur);
+            else k_pt_extend<ACCEL_BVH><<<grid, 128, 0, r->stream>>>(p, r->scene->d, cur);
             r->prof_end(RT_STAGE_EXTEND);
             r->prof_begin();
             k_pt_shade<<<grid, 128, 0, r->stream>>>(p, r->scene->d, r->cam, cur);
@@ -1600,19 +1608,24 @@ static void whitted_frame_launches(rt_renderer* r)
     k_wh_generate<<<r->sms * 4, 256, 0, r->stream>>>(w, r->dCam);
     r->prof_end(RT_STAGE_GENERATE);
     const int grid = r->sms * 8;
+    const int kind = r->scene->d.kind;
     int cur = 0;
     for (int depth = 0; depth <= P.depth_limit; depth++)
     {
         r->prof_begin();
-        if (r->persistent) k_wh_extend_persistent<<<grid, 128, 0, r->stream>>>(w, r->scene->d, cur);
-        else k_wh_extend<<<grid, 128, 0, r->stream>>>(w, r->scene->d, cur);
+        if (kind == RT_SCENE_FLAT_KDTREE) k_wh_extend<ACCEL_KD><<<grid, 128, 0, r->stream>>>(w, r->scene->d, cur);
+        else if (kind == RT_SCENE_FLAT_GRID) k_wh_extend<ACCEL_GRID><<<grid, 128, 0, r->stream>>>(w, r->scene->d, cur);
+        else if (r->persistent) k_wh_extend_persistent<<<grid, 128, 0, r->stream>>>(w, r->scene->d, cur);
+        else k_wh_extend<ACCEL_BVH><<<grid, 128, 0, r->stream>>>(w, r->scene->d, cur);
         r->prof_end(RT_STAGE_EXTEND);
         r->prof_begin();
         k_wh_shade<<<grid, 128, 0, r->stream>>>(w, r->scene->d, cur);
         r->prof_end(RT_STAGE_SHADE);
         r->prof_begin();
-        if (r->persistent) k_wh_connect_persistent<<<grid, 128, 0, r->stream>>>(w, r->scene->d);
-        else k_wh_connect<<<grid, 128, 0, r->stream>>>(w, r->scene->d);
+        if (kind == RT_SCENE_FLAT_KDTREE) k_wh_connect<ACCEL_KD><<<grid, 128, 0, r->stream>>>(w, r->scene->d);
+        else if (kind == RT_SCENE_FLAT_GRID) k_wh_connect<ACCEL_GRID><<<grid, 128, 0, r->stream>>>(w, r->scene->d);
+        else if (r->persistent) k_wh_connect_persistent<<<grid, 128, 0, r->stream>>>(w, r->scene->d);
+        else k_wh_connect<ACCEL_BVH><<<grid, 128, 0, r->stream>>>(w, r->scene->d);
         r->prof_end(RT_STAGE_CONNECT);
         cur ^= 1;
     }

@@ -26,7 +26,7 @@ bool cuda_ok(cudaError_t e, const char* what)
 // kernels: one thread per ray, AoS rt_ray (32 B) in, rt_hit (32 B) out — the C-ABI record layout.
 // Grid-stride so the launch is a whole number of waves (blocks = k x SM count).
 // ---------------------------------------------------------------------------------------------
-template <bool COUNTERS>
+template <bool COUNTERS, int ACCEL>
 __global__ void __launch_bounds__(128) k_find_nearest(const DScene s, const rt_ray* __restrict__ rays, rt_hit* __restrict__ hits, size_t n)
 {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -34,20 +34,21 @@ __global__ void __launch_bounds__(128) k_find_nearest(const DScene s, const rt_r
         const float4 a = __ldg((const float4*)(rays + i));
         const float4 b = __ldg((const float4*)(rays + i) + 1);
         HitRec h;
-        find_nearest<COUNTERS>(s, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, h);
+        find_nearest<COUNTERS, ACCEL>(s, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, h);
         float4* out = (float4*)(hits + i);
         out[0] = make_float4(h.t, h.u, h.v, __int_as_float(h.obj));
         out[1] = make_float4(__int_as_float(h.tri), __int_as_float(h.traversed), __int_as_float(h.tested), 0.0f);
     }
 }
 
+template <int ACCEL>
 __global__ void __launch_bounds__(128) k_is_occluded(const DScene s, const rt_ray* __restrict__ rays, uint8_t* __restrict__ out, size_t n)
 {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     {
         const float4 a = __ldg((const float4*)(rays + i));
         const float4 b = __ldg((const float4*)(rays + i) + 1);
-        out[i] = is_occluded(s, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w) ? 1 : 0;
+        out[i] = is_occluded<ACCEL>(s, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w) ? 1 : 0;
     }
 }
 
@@ -278,6 +279,99 @@ struct Builder {
     }
 };
 
+// One 48-byte triangle record of the alternative accelerators (leaf / cell order, no LAST_BIT: runs carry a count)
+static void push_tri_record(std::vector<float4>& out, const rt_tri& t, uint32_t triIdx)
+{
+    out.push_back(Builder::f4(t.v0[0], t.v0[1], t.v0[2], Builder::asf((int)triIdx)));
+    out.push_back(Builder::f4(t.v1[0] - t.v0[0], t.v1[1] - t.v0[1], t.v1[2] - t.v0[2], Builder::asf(t.obj_idx)));
+    out.push_back(Builder::f4(t.v2[0] - t.v0[0], t.v2[1] - t.v0[1], t.v2[2] - t.v0[2], 0));
+}
+
+static void push_shade_records(std::vector<float4>& shade, const rt_blas_desc& b)
+{
+    for (uint32_t j = 0; j < b.tri_count; j++)
+    {
+        const rt_tri& t = b.tris[j];
+        shade.push_back(Builder::f4(t.n0[0], t.n0[1], t.n0[2], t.n1[0]));
+        shade.push_back(Builder::f4(t.n1[1], t.n1[2], t.n2[0], t.n2[1]));
+        shade.push_back(Builder::f4(t.n2[2], t.uv0[0], t.uv0[1], t.uv1[0]));
+        shade.push_back(Builder::f4(t.uv1[1], t.uv2[0], t.uv2[1], Builder::asf(t.obj_idx)));
+    }
+}
+
+// rt_kd_node[] (reference KDTreeNode graph flattened by the host) -> 32-byte device nodes in DFS pre-order with
+// adjacent children + leaf-ordered triangle records.  Layout: rt_device.cuh, "KD-tree".
+static bool build_kd(const rt_scene_desc& d, std::vector<float4>& kd, std::vector<float4>& tris, std::string& error)
+{
+    const rt_blas_desc& b = d.blas[0];
+    struct Item { uint32_t src; uint32_t dst; int depth; };
+    std::vector<Item> todo;
+    kd.resize(2);
+    todo.push_back({ 0u, 0u, 0 });
+    size_t visited = 0;
+    while (!todo.empty())
+    {
+        const Item it = todo.back();
+        todo.pop_back();
+        if (++visited > d.kd_node_count) { error = "KD-tree is not a tree"; return false; }
+        if (it.depth >= KD_STACK_SIZE) { error = "KD-tree deeper than 31 levels"; return false; }
+        const rt_kd_node& n = d.kd_nodes[it.src];
+        float4 k0 = Builder::f4(n.aabb_min[0], n.aabb_min[1], n.aabb_min[2], n.aabb_max[0]), k1;
+        if (n.left < 0 || n.right < 0)
+        {
+            if ((uint64_t)n.tri_start + n.tri_count > d.kd_tri_index_count) { error = "KD leaf range out of bounds"; return false; }
+            const int slot = (int)(tris.size() / 3);
+            for (uint32_t i = 0; i < n.tri_count; i++)
+            {
+                const uint32_t triIdx = d.kd_tri_indices[n.tri_start + i];
+                if (triIdx >= b.tri_count) { error = "KD triangle index out of range"; return false; }
+                push_tri_record(tris, b.tris[triIdx], triIdx);
+            }
+            k1 = Builder::f4(n.aabb_max[1], n.aabb_max[2], Builder::asf(~slot), Builder::asf((int)n.tri_count));
+        }
+        else
+        {
+            if ((uint32_t)n.left >= d.kd_node_count || (uint32_t)n.right >= d.kd_node_count) { error = "KD child index out of range"; return false; }
+            if (n.split_axis < 0 || n.split_axis > 2) { error = "KD split axis out of range"; return false; }
+            const uint32_t left = (uint32_t)(kd.size() / 2);
+            if (left >= (1u << 29)) { error = "KD-tree too large"; return false; }
+            kd.resize(kd.size() + 4);
+            // kdtree.cpp:171: splitPos = aabbMin[axis] + splitDistance (one fp32 add, the same on the host)
+            const float splitPos = n.aabb_min[n.split_axis] + n.split_distance;
+            k1 = Builder::f4(n.aabb_max[1], n.aabb_max[2], Builder::asf((int)(left << 2 | (uint32_t)n.split_axis)), splitPos);
+            todo.push_back({ (uint32_t)n.right, left + 1, it.depth + 1 });
+            todo.push_back({ (uint32_t)n.left, left, it.depth + 1 });
+        }
+        kd[2 * (size_t)it.dst] = k0, kd[2 * (size_t)it.dst + 1] = k1;
+    }
+    return true;
+}
+
+// rt_grid_desc -> (first slot, count) per cell + cell-ordered triangle records.  Layout: rt_device.cuh, "Uniform grid".
+static bool build_grid(const rt_scene_desc& d, std::vector<int2>& cells, std::vector<float4>& tris, std::string& error)
+{
+    const rt_grid_desc& g = *d.grid;
+    const rt_blas_desc& b = d.blas[0];
+    if (!g.cell_start || (!g.tri_indices && g.index_count)) { error = "grid with null arrays"; return false; }
+    for (int i = 0; i < 3; i++)
+        if (g.resolution[i] < 1 || g.resolution[i] > 1024) { error = "grid resolution out of range"; return false; }
+    const size_t n = (size_t)g.resolution[0] * g.resolution[1] * g.resolution[2];
+    cells.resize(n);
+    for (size_t c = 0; c < n; c++)
+    {
+        const uint32_t a = g.cell_start[c], e = g.cell_start[c + 1];
+        if (e < a || e > g.index_count) { error = "grid cell range out of bounds"; return false; }
+        cells[c] = make_int2((int)(tris.size() / 3), (int)(e - a));
+        for (uint32_t j = a; j < e; j++)
+        {
+            const uint32_t triIdx = g.tri_indices[j];
+            if (triIdx >= b.tri_count) { error = "grid triangle index out of range"; return false; }
+            push_tri_record(tris, b.tris[triIdx], triIdx);
+        }
+    }
+    return true;
+}
+
 template <class T>
 static rt_status upload(T** dst, const void* src, size_t bytes)
 {
@@ -311,16 +405,32 @@ rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags,
     if (desc->blas_count == 0 || !desc->blas) { set_error("rt_scene_create: no BLAS"); return RT_ERR_INVALID; }
     if (desc->kind == RT_SCENE_FLAT && desc->blas_count != 1) { set_error("rt_scene_create: a flat scene has exactly one BVH"); return RT_ERR_INVALID; }
     if (desc->kind == RT_SCENE_TLAS && (!desc->tlas_nodes || desc->tlas_node_count == 0)) { set_error("rt_scene_create: TLAS scene without TLAS nodes"); return RT_ERR_INVALID; }
-    if (desc->kind != RT_SCENE_FLAT && desc->kind != RT_SCENE_TLAS) { set_error("rt_scene_create: unknown scene kind"); return RT_ERR_INVALID; }
+    const bool alt = desc->kind == RT_SCENE_FLAT_KDTREE || desc->kind == RT_SCENE_FLAT_GRID;
+    if (desc->kind != RT_SCENE_FLAT && desc->kind != RT_SCENE_TLAS && !alt) { set_error("rt_scene_create: unknown scene kind"); return RT_ERR_INVALID; }
+    if (alt && (desc->blas_count != 1 || !desc->blas[0].tris || desc->blas[0].tri_count == 0)) { set_error("rt_scene_create: a KD-tree / grid scene has exactly one triangle array"); return RT_ERR_INVALID; }
+    if (desc->kind == RT_SCENE_FLAT_KDTREE && (!desc->kd_nodes || desc->kd_node_count == 0 || (!desc->kd_tri_indices && desc->kd_tri_index_count))) { set_error("rt_scene_create: KD-tree scene without KD nodes"); return RT_ERR_INVALID; }
+    if (desc->kind == RT_SCENE_FLAT_GRID && !desc->grid) { set_error("rt_scene_create: grid scene without a grid"); return RT_ERR_INVALID; }
     if (rt_device_count() <= device || device < 0) { set_error("rt_scene_create: no such CUDA device (there is no CPU fallback)"); return RT_ERR_NO_DEVICE; }
 
     Builder B;
+    std::vector<float4> kdNodes;
+    std::vector<int2> gridCells;
     std::vector<int> rootRefs(desc->blas_count);
     std::vector<int> triBase(desc->blas_count);
     std::vector<uint32_t> firstOfGeometry; // distinct meshes seen so far (bounded: scenes share a handful)
     for (uint32_t i = 0; i < desc->blas_count; i++)
     {
         const rt_blas_desc& b = desc->blas[i];
+        if (alt)
+        {
+            // FileScene with its KD-tree or grid: triangles in leaf / cell order, shading records by triIdx as for the BVH
+            const bool ok = desc->kind == RT_SCENE_FLAT_KDTREE ? build_kd(*desc, kdNodes, B.tris, B.error) : build_grid(*desc, gridCells, B.tris, B.error);
+            if (!ok) { set_error("rt_scene_create: " + B.error); return RT_ERR_INVALID; }
+            push_shade_records(B.shade, b);
+            triBase[i] = 0, rootRefs[i] = 0;
+            for (int k = 0; k < 4; k++) B.inst.push_back(Builder::f4(0, 0, 0, 0)), B.inst_shade.push_back(Builder::f4(0, 0, 0, 0));
+            break;
+        }
         if (!b.nodes || !b.tris || !b.tri_indices) { set_error("rt_scene_create: BLAS with null arrays"); return RT_ERR_INVALID; }
         // true instancing: BLAS descriptors that point at the same reference arrays share
         // one device copy of nodes / triangles / shading records; only the 2 x 64-byte instance records differ
@@ -369,8 +479,12 @@ rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags,
     if ((st = upload(&s->shade, B.shade.data(), B.shade.size() * 16)) != RT_OK) return fail(st);
     if ((st = upload(&s->inst_shade, B.inst_shade.data(), B.inst_shade.size() * 16)) != RT_OK) return fail(st);
     if ((st = upload(&s->obj_material, desc->obj_material, desc->obj_count * sizeof(int))) != RT_OK) return fail(st);
+    if ((st = upload(&s->kd_nodes, kdNodes.data(), kdNodes.size() * 16)) != RT_OK) return fail(st);
+    if ((st = upload(&s->grid_cells, gridCells.data(), gridCells.size() * sizeof(int2))) != RT_OK) return fail(st);
     s->node_count = B.nodes.size() / 4, s->tri_count = B.tris.size() / 3, s->inst_count = desc->blas_count;
-    s->bytes_geometry = (B.nodes.size() + B.tris.size() + B.inst.size() + B.shade.size() + B.inst_shade.size()) * 16;
+    s->bytes_geometry = (B.nodes.size() + B.tris.size() + B.inst.size() + B.shade.size() + B.inst_shade.size() + kdNodes.size()) * 16 + gridCells.size() * sizeof(int2);
+    if (desc->kind == RT_SCENE_FLAT_KDTREE) s->node_count = kdNodes.size() / 2;
+    if (desc->kind == RT_SCENE_FLAT_GRID) s->node_count = gridCells.size();
 
     static_assert(sizeof(DMaterial) == sizeof(rt_material), "material layout");
     if ((st = upload(&s->materials, desc->materials, desc->material_count * sizeof(rt_material))) != RT_OK) return fail(st);
@@ -396,7 +510,9 @@ rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags,
     if ((st = upload(&s->fetch_counters, nullptr, rt_scene::FETCH_RING * sizeof(int))) != RT_OK) return fail(st);
     {
         const char* e = getenv("RT_B200_TRAVERSAL");
-        s->persistent = !(e && strcmp(e, "simple") == 0);
+        // the persistent-warp state machine (trace_queue) is written for the BVH; KD-tree / grid scenes use the
+        // one-thread-per-ray kernels
+        s->persistent = !(e && strcmp(e, "simple") == 0) && !alt;
     }
 
     DScene& d = s->d;
@@ -404,6 +520,11 @@ rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags,
     d.obj_material = s->obj_material, d.materials = s->materials, d.textures = s->textures;
     d.root_ref = rootRef, d.kind = desc->kind;
     d.flat_obj_idx = desc->kind == RT_SCENE_FLAT ? desc->blas[0].obj_idx : -1;
+    d.kd_nodes = s->kd_nodes, d.grid_cells = s->grid_cells;
+    if (desc->kind == RT_SCENE_FLAT_GRID)
+        for (int i = 0; i < 3; i++)
+            d.grid_res[i] = desc->grid->resolution[i], d.grid_cell[i] = desc->grid->cell_size[i],
+            d.grid_min[i] = desc->grid->bounds_min[i], d.grid_max[i] = desc->grid->bounds_max[i];
     d.skydome_texture = desc->skydome_texture, d.floor_texture = desc->floor_texture;
     memcpy(d.floor_n, desc->floor_n, 12), d.floor_d = desc->floor_d, d.floor_invto = desc->floor_invto;
     memcpy(d.light_T, desc->light_T, 64), memcpy(d.light_inv_T, desc->light_inv_T, 64), d.light_size = desc->light_size;
@@ -417,6 +538,7 @@ void rt_scene_destroy(rt_scene* s)
     if (!s) return;
     cudaSetDevice(s->device);
     cudaFree(s->nodes), cudaFree(s->tris), cudaFree(s->inst), cudaFree(s->shade), cudaFree(s->inst_shade);
+    cudaFree(s->kd_nodes), cudaFree(s->grid_cells);
     cudaFree(s->obj_material), cudaFree(s->materials), cudaFree(s->textures), cudaFree(s->tex_pixels);
     cudaFree(s->scratch_in), cudaFree(s->scratch_out), cudaFree(s->fetch_counters);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -442,8 +564,14 @@ rt_status rt_find_nearest_device(rt_scene* s, const rt_ray* d_rays, rt_hit* d_hi
             else k_find_nearest_persistent<false><<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays + off, d_hits + off, m, fetch);
         }
     }
-    else if (counters) k_find_nearest<true><<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays, d_hits, n);
-    else k_find_nearest<false><<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays, d_hits, n);
+    else
+    {
+        void (*k)(const DScene, const rt_ray*, rt_hit*, size_t) =
+            s->d.kind == RT_SCENE_FLAT_KDTREE ? (counters ? k_find_nearest<true, ACCEL_KD> : k_find_nearest<false, ACCEL_KD>) :
+            s->d.kind == RT_SCENE_FLAT_GRID   ? (counters ? k_find_nearest<true, ACCEL_GRID> : k_find_nearest<false, ACCEL_GRID>) :
+                                                (counters ? k_find_nearest<true, ACCEL_BVH> : k_find_nearest<false, ACCEL_BVH>);
+        k<<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays, d_hits, n);
+    }
     RT_CUDA(cudaGetLastError());
     return RT_OK;
 }
@@ -464,7 +592,9 @@ rt_status rt_is_occluded_device(rt_scene* s, const rt_ray* d_rays, uint8_t* d_ou
             k_is_occluded_persistent<<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays + off, d_out + off, m, fetch);
         }
     }
-    else k_is_occluded<<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays, d_out, n);
+    else if (s->d.kind == RT_SCENE_FLAT_KDTREE) k_is_occluded<ACCEL_KD><<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays, d_out, n);
+    else if (s->d.kind == RT_SCENE_FLAT_GRID) k_is_occluded<ACCEL_GRID><<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays, d_out, n);
+    else k_is_occluded<ACCEL_BVH><<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays, d_out, n);
     RT_CUDA(cudaGetLastError());
     return RT_OK;
 }

@@ -12,6 +12,9 @@
 //   rtb_invert_rigid  mat4::FastInvertedTransformNoScale    (tmplmath.h:745-768)
 //   rtb_build_tlas    TLASBVH::Build / FindBestMatch        (tlas_bvh.cpp:17-70), without the 256-instance
 //                     cap of `int nodeIdx[256]`; child indices stay 2 x 16 bit
+//   rtb_kd_*          KDTree::Build / Subdivide             (kdtree.cpp:4-112), flattened into rt_kd_node[]
+//   rtb_grid_*        Grid::Build                           (grid.cpp:4-60), flattened into rt_grid_desc arrays
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -148,9 +151,188 @@ struct BvhBuilder {
     }
 };
 
+// KDTree::Build (kdtree.cpp:4-43) + Subdivide (:45-112): spatial median on the longest axis, depth <= 20, leaves
+// of <= 2 triangles, a triangle goes left when its box ends before the plane, right when it starts after
+// `splitPos - 0.001` (double arithmetic, :70), else into both.  Nodes are numbered the way the flattener of the
+// reference build numbers them (children allocated when the parent is visited, depth first, left first) and leaf
+// lists are concatenated in that visiting order.
+struct KdBuilder {
+    const rt_tri* tris;
+    std::vector<Box> triBounds;
+    std::vector<rt_kd_node> nodes;
+    std::vector<uint32_t> leafIdx;
+    uint32_t maxDepth = 0;
+
+    void build(uint32_t n)
+    {
+        triBounds.resize(n);
+        Box all;
+        std::vector<uint32_t> idx(n);
+        for (uint32_t i = 0; i < n; i++)
+        {
+            Box b;
+            b.grow(tris[i].v0), b.grow(tris[i].v1), b.grow(tris[i].v2);
+            all.grow(b);
+            triBounds[i] = b, idx[i] = i;
+        }
+        nodes.emplace_back();
+        memset(&nodes[0], 0, sizeof(rt_kd_node));
+        memcpy(nodes[0].aabb_min, all.mn, 12), memcpy(nodes[0].aabb_max, all.mx, 12);
+        subdivide(0, idx, 0);
+    }
+
+    void leaf(uint32_t n, const std::vector<uint32_t>& idx)
+    {
+        nodes[n].left = nodes[n].right = -1;
+        nodes[n].tri_start = (uint32_t)leafIdx.size(), nodes[n].tri_count = (uint32_t)idx.size();
+        leafIdx.insert(leafIdx.end(), idx.begin(), idx.end());
+    }
+
+    void subdivide(uint32_t n, std::vector<uint32_t>& idx, int depth)
+    {
+        if (depth >= 20 || idx.size() <= 2) { leaf(n, idx); return; } // m_maxBuildDepth kdtree.h:31, :48-50
+        if ((uint32_t)depth > maxDepth) maxDepth = depth;
+        float mn[3], mx[3], extent[3];
+        memcpy(mn, nodes[n].aabb_min, 12), memcpy(mx, nodes[n].aabb_max, 12);
+        for (int a = 0; a < 3; a++) extent[a] = mx[a] - mn[a];
+        int axis = 0;
+        if (extent[1] > extent[0]) axis = 1;
+        if (extent[2] > extent[axis]) axis = 2;
+        const float distance = extent[axis] * 0.5f;
+        const float splitPos = mn[axis] + distance;
+        std::vector<uint32_t> left, right;
+        for (uint32_t t : idx)
+        {
+            if (triBounds[t].mx[axis] < splitPos) left.push_back(t);
+            else if (triBounds[t].mn[axis] > splitPos - 0.001) right.push_back(t);
+            else left.push_back(t), right.push_back(t);
+        }
+        idx.clear();
+        idx.shrink_to_fit();
+        const uint32_t l = (uint32_t)nodes.size(), r = l + 1;
+        nodes.emplace_back(), nodes.emplace_back();
+        memset(&nodes[l], 0, 2 * sizeof(rt_kd_node));
+        nodes[n].left = (int32_t)l, nodes[n].right = (int32_t)r;
+        nodes[n].split_axis = axis, nodes[n].split_distance = distance;
+        memcpy(nodes[l].aabb_min, mn, 12), memcpy(nodes[l].aabb_max, mx, 12), nodes[l].aabb_max[axis] = splitPos;
+        memcpy(nodes[r].aabb_min, mn, 12), memcpy(nodes[r].aabb_max, mx, 12), nodes[r].aabb_min[axis] = splitPos;
+        subdivide(l, left, depth + 1);
+        subdivide(r, right, depth + 1);
+    }
+};
+
+// max(a, min(f, b)), tmplmath.h:436
+inline int clampi(int f, int a, int b) { const int m = f < b ? f : b; return a > m ? a : m; }
+
+// Grid::Build (grid.cpp:4-60)
+struct GridBuilder {
+    int32_t res[3];
+    float cell[3], mn[3], mx[3];
+    std::vector<uint32_t> cellStart, idx;
+
+    void build(const rt_tri* tris, uint32_t n)
+    {
+        Box all;
+        std::vector<Box> tb(n);
+        for (uint32_t i = 0; i < n; i++)
+        {
+            tb[i].grow(tris[i].v0), tb[i].grow(tris[i].v1), tb[i].grow(tris[i].v2);
+            all.grow(tb[i]);
+        }
+        memcpy(mn, all.mn, 12), memcpy(mx, all.mx, 12);
+        float size[3];
+        for (int a = 0; a < 3; a++) size[a] = mx[a] - mn[a];
+        const float cubeRoot = powf(5 * (int)n / (size[0] * size[1] * size[2]), 1 / 3.f); // :18
+        for (int a = 0; a < 3; a++)
+        {
+            res[a] = static_cast<int>(floorf(size[a] * cubeRoot));
+            res[a] = res[a] < 128 ? res[a] : 128;  // max(1, min(resolution, 128)) :22
+            res[a] = 1 > res[a] ? 1 : res[a];
+        }
+        for (int a = 0; a < 3; a++) cell[a] = size[a] / res[a];
+        const size_t cells = (size_t)res[0] * res[1] * res[2];
+        std::vector<uint32_t> count(cells + 1, 0);
+        auto range = [&](uint32_t i, int lo[3], int hi[3]) {
+            for (int a = 0; a < 3; a++)
+            {
+                lo[a] = clampi(static_cast<int>((tb[i].mn[a] - mn[a]) / cell[a]), 0, res[a] - 1);
+                hi[a] = clampi(static_cast<int>((tb[i].mx[a] - mn[a]) / cell[a]), 0, res[a] - 1);
+            }
+        };
+        for (int pass = 0; pass < 2; pass++)
+        {
+            // pass 0 counts, pass 1 fills: per cell the triangles end up in increasing index order, as push_back leaves them
+            for (uint32_t i = 0; i < n; i++)
+            {
+                int lo[3], hi[3];
+                range(i, lo, hi);
+                for (int z = lo[2]; z <= hi[2]; ++z)
+                    for (int y = lo[1]; y <= hi[1]; ++y)
+                        for (int x = lo[0]; x <= hi[0]; ++x)
+                        {
+                            const size_t c = (size_t)x + (size_t)y * res[0] + (size_t)z * res[0] * res[1];
+                            if (pass == 0) count[c + 1]++;
+                            else idx[count[c]++] = i;
+                        }
+            }
+            if (pass == 0)
+            {
+                for (size_t c = 0; c < cells; c++) count[c + 1] += count[c];
+                cellStart = count;
+                idx.resize(count[cells]);
+            }
+        }
+    }
+};
+
 } // namespace
 
 extern "C" {
+
+// KD-tree / grid builders hand their variable-size output over through a handle: build, query the sizes, copy, free.
+void* rtb_kd_build(const rt_tri* tris, uint32_t n)
+{
+    if (!tris || n == 0) return nullptr;
+    KdBuilder* b = new KdBuilder();
+    b->tris = tris;
+    b->build(n);
+    return b;
+}
+void rtb_kd_sizes(void* h, uint32_t* nodes, uint32_t* indices, uint32_t* max_depth)
+{
+    KdBuilder* b = (KdBuilder*)h;
+    *nodes = (uint32_t)b->nodes.size(), *indices = (uint32_t)b->leafIdx.size(), *max_depth = b->maxDepth;
+}
+void rtb_kd_copy(void* h, rt_kd_node* nodes_out, uint32_t* indices_out)
+{
+    KdBuilder* b = (KdBuilder*)h;
+    memcpy(nodes_out, b->nodes.data(), b->nodes.size() * sizeof(rt_kd_node));
+    if (!b->leafIdx.empty()) memcpy(indices_out, b->leafIdx.data(), b->leafIdx.size() * 4);
+}
+void rtb_kd_free(void* h) { delete (KdBuilder*)h; }
+
+void* rtb_grid_build(const rt_tri* tris, uint32_t n)
+{
+    if (!tris || n == 0) return nullptr;
+    GridBuilder* g = new GridBuilder();
+    g->build(tris, n);
+    return g;
+}
+// header12: resolution (3 x int32), cell size, bounds min, bounds max (3 floats each) = the grid_header chunk
+void rtb_grid_sizes(void* h, void* header12, uint32_t* cells, uint32_t* indices)
+{
+    GridBuilder* g = (GridBuilder*)h;
+    char* o = (char*)header12;
+    memcpy(o, g->res, 12), memcpy(o + 12, g->cell, 12), memcpy(o + 24, g->mn, 12), memcpy(o + 36, g->mx, 12);
+    *cells = (uint32_t)g->cellStart.size() - 1, *indices = (uint32_t)g->idx.size();
+}
+void rtb_grid_copy(void* h, uint32_t* cell_start_out, uint32_t* indices_out)
+{
+    GridBuilder* g = (GridBuilder*)h;
+    memcpy(cell_start_out, g->cellStart.data(), g->cellStart.size() * 4);
+    if (!g->idx.empty()) memcpy(indices_out, g->idx.data(), g->idx.size() * 4);
+}
+void rtb_grid_free(void* h) { delete (GridBuilder*)h; }
 
 // nodes_out: 2n - 1 entries, tri_indices_out: n entries.  Centroids are read from the triangles
 // (the reference sets them to (v0 + v1 + v2) * 0.3333f when it loads a model, model.cpp:77).

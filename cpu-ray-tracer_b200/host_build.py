@@ -33,6 +33,15 @@ def lib():
         L.rtb_world_bounds.argtypes = [vp, vp, vp, vp]
         L.rtb_invert_rigid.argtypes = [vp, vp]
         L.rtb_build_tlas.argtypes = [vp, C.c_uint32, vp, C.POINTER(C.c_uint32)]
+        u32p = C.POINTER(C.c_uint32)
+        L.rtb_kd_build.argtypes, L.rtb_kd_build.restype = [vp, C.c_uint32], vp
+        L.rtb_kd_sizes.argtypes, L.rtb_kd_sizes.restype = [vp, u32p, u32p, u32p], None
+        L.rtb_kd_copy.argtypes, L.rtb_kd_copy.restype = [vp, vp, vp], None
+        L.rtb_kd_free.argtypes, L.rtb_kd_free.restype = [vp], None
+        L.rtb_grid_build.argtypes, L.rtb_grid_build.restype = [vp, C.c_uint32], vp
+        L.rtb_grid_sizes.argtypes, L.rtb_grid_sizes.restype = [vp, vp, u32p, u32p], None
+        L.rtb_grid_copy.argtypes, L.rtb_grid_copy.restype = [vp, vp, vp], None
+        L.rtb_grid_free.argtypes, L.rtb_grid_free.restype = [vp], None
         _lib = L
     return _lib
 
@@ -48,6 +57,58 @@ def build_bvh(tris):
     if rc != 0:
         raise ValueError(f"rtb_build_bvh failed: {rc}")
     return nodes[:used.value].copy(), idx, depth.value
+
+
+def build_kdtree(tris):
+    """KDTree::Build (kdtree.cpp:4-112) on a TRI_DTYPE array -> (kd_nodes, kd_tri_indices, max_depth), flattened as
+    include/rt_b200.h rt_kd_node documents"""
+    tris = np.ascontiguousarray(tris, abi.TRI_DTYPE)
+    h = lib().rtb_kd_build(tris.ctypes.data, len(tris))
+    if not h:
+        raise ValueError("rtb_kd_build failed")
+    nn, ni, depth = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    lib().rtb_kd_sizes(h, C.byref(nn), C.byref(ni), C.byref(depth))
+    nodes = np.zeros(nn.value, abi.KD_NODE_DTYPE)
+    idx = np.zeros(ni.value, np.uint32)
+    lib().rtb_kd_copy(h, nodes.ctypes.data, idx.ctypes.data)
+    lib().rtb_kd_free(h)
+    return nodes, idx, depth.value
+
+
+def build_grid(tris):
+    """Grid::Build (grid.cpp:4-60) on a TRI_DTYPE array -> (grid_header[1], cell_start, tri_indices)"""
+    tris = np.ascontiguousarray(tris, abi.TRI_DTYPE)
+    h = lib().rtb_grid_build(tris.ctypes.data, len(tris))
+    if not h:
+        raise ValueError("rtb_grid_build failed")
+    hdr = np.zeros(1, abi.GRID_HEADER_DTYPE)
+    nc, ni = C.c_uint32(), C.c_uint32()
+    lib().rtb_grid_sizes(h, hdr.ctypes.data, C.byref(nc), C.byref(ni))
+    start = np.zeros(nc.value + 1, np.uint32)
+    idx = np.zeros(ni.value, np.uint32)
+    lib().rtb_grid_copy(h, start.ctypes.data, idx.ctypes.data)
+    lib().rtb_grid_free(h)
+    return hdr, start, idx
+
+
+def with_accelerator(flat, accel):
+    """The same FileScene with another of its accelerators (file_scene.h:10-12): accel = "kdtree" | "grid".
+    Triangles, materials and textures are shared with `flat`; the BVH arrays are dropped."""
+    chunks = {k: getattr(flat, k) for k in ("header", "blas_table", "tris", "obj_material", "materials", "tex_table", "tex_pixels")}
+    chunks["header"] = flat.header.copy()
+    chunks["blas_table"] = flat.blas_table[:1].copy()
+    chunks["blas_table"]["node_offset"], chunks["blas_table"]["node_count"] = 0, 0
+    chunks["nodes"], chunks["tri_indices"] = np.zeros(0, abi.NODE_DTYPE), np.zeros(0, np.uint32)
+    chunks["tlas_nodes"] = np.zeros(0, abi.TLAS_NODE_DTYPE)
+    if accel == "kdtree":
+        chunks["header"]["kind"] = abi.RT_SCENE_FLAT_KDTREE
+        chunks["kd_nodes"], chunks["kd_tri_indices"], _ = build_kdtree(flat.tris)
+    elif accel == "grid":
+        chunks["header"]["kind"] = abi.RT_SCENE_FLAT_GRID
+        chunks["grid_header"], chunks["grid_cell_start"], chunks["grid_tri_indices"] = build_grid(flat.tris)
+    else:
+        raise ValueError(accel)
+    return FlatScene(chunks)
 
 
 def invert_rigid(T):

@@ -13,6 +13,9 @@ constructors ran (file_scene.cpp:4-62, tlas_file_scene.cpp:4-93), in the referen
     materials    rt_material[]
     tex_table    per texture: offset into tex_pixels, width, height
     tex_pixels   uint[]      packed 0x00RRGGBB (texture.h:31-34)
+    kd_nodes     rt_kd_node[] (48 B) + kd_tri_indices uint[]      kind 2: FileScene with its KD-tree (kdtree.cpp)
+    grid_header  resolution / cellSize / localBounds + grid_cell_start uint[cells+1] + grid_tri_indices uint[]
+                                                                  kind 3: FileScene with its uniform grid (grid.cpp)
 
 File layout: "RTSCN001", u32 chunk count, u32 pad, then per chunk: char name[24], u64 nbytes, payload
 padded to 8 bytes.  A ".gz" suffix means the whole file is gzip-compressed.
@@ -39,7 +42,10 @@ _CHUNK_DTYPES = {
     "header": HEADER_DTYPE, "blas_table": BLAS_TABLE_DTYPE, "nodes": abi.NODE_DTYPE, "tris": abi.TRI_DTYPE,
     "tri_indices": np.dtype("<u4"), "tlas_nodes": abi.TLAS_NODE_DTYPE, "obj_material": np.dtype("<i4"),
     "materials": abi.MATERIAL_DTYPE, "tex_table": TEX_TABLE_DTYPE, "tex_pixels": np.dtype("<u4"),
+    "kd_nodes": abi.KD_NODE_DTYPE, "kd_tri_indices": np.dtype("<u4"),
+    "grid_header": abi.GRID_HEADER_DTYPE, "grid_cell_start": np.dtype("<u4"), "grid_tri_indices": np.dtype("<u4"),
 }
+_OPTIONAL = ("kd_nodes", "kd_tri_indices", "grid_header", "grid_cell_start", "grid_tri_indices")
 
 
 class FlatScene:
@@ -56,6 +62,8 @@ class FlatScene:
         self.materials = chunks["materials"]
         self.tex_table = chunks["tex_table"]
         self.tex_pixels = chunks["tex_pixels"]
+        for name in _OPTIONAL:
+            setattr(self, name, chunks.get(name))
         self._keep = None
 
     @property
@@ -88,7 +96,7 @@ class FlatScene:
     def save(self, path):
         opener = gzip.open if str(path).endswith(".gz") else open
         names = ["header", "blas_table", "nodes", "tris", "tri_indices", "tlas_nodes", "obj_material",
-                 "materials", "tex_table", "tex_pixels"]
+                 "materials", "tex_table", "tex_pixels"] + [n for n in _OPTIONAL if getattr(self, n) is not None]
         with opener(path, "wb") as f:
             f.write(b"RTSCN001" + struct.pack("<II", len(names), 0))
             for name in names:
@@ -136,5 +144,20 @@ class FlatScene:
         d.light_size = float(h["light_size"])
         d.light_color = abi.f3(*h["light_color"].tolist())
         d.light_pos = abi.f3(*h["light_pos"].tolist())
-        self._keep = (blas, tex)
+        grid = None
+        if self.kd_nodes is not None:
+            d.kd_nodes, d.kd_node_count = self.kd_nodes.ctypes.data, len(self.kd_nodes)
+            d.kd_tri_indices, d.kd_tri_index_count = self.kd_tri_indices.ctypes.data, len(self.kd_tri_indices)
+        if self.grid_header is not None:
+            g = self.grid_header[0]
+            grid = abi.rt_grid_desc()
+            grid.resolution = (C.c_int32 * 3)(*g["resolution"].tolist())
+            grid.cell_size = abi.f3(*g["cell_size"].tolist())
+            grid.bounds_min = abi.f3(*g["bounds_min"].tolist())
+            grid.bounds_max = abi.f3(*g["bounds_max"].tolist())
+            grid.cell_start = self.grid_cell_start.ctypes.data
+            grid.tri_indices = self.grid_tri_indices.ctypes.data
+            grid.index_count = len(self.grid_tri_indices)
+            d.grid = C.pointer(grid)
+        self._keep = (blas, tex, grid)
         return d

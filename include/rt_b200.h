@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RT_B200_ABI_VERSION 2
+#define RT_B200_ABI_VERSION 3
 
 typedef int rt_status;
 enum {
@@ -97,7 +97,39 @@ typedef struct rt_texture {
     int32_t width, height;
 } rt_texture;
 
-enum { RT_SCENE_FLAT = 0 /* FileScene, USE_BVH */, RT_SCENE_TLAS = 1 /* TLASFileScene, TLAS_USE_BVH */ };
+/* One node of the reference's KD-tree (KDTreeNode, infra/blas_kdtree.h:16-25; built by KDTree::Subdivide,
+ * infra/kdtree.cpp:45-112).  The reference links nodes by pointer and keeps a std::vector<uint> per leaf;
+ * the host flattens them once after KDTree::Build (loop shown in INTEGRATION.md): node 0 = root,
+ * left / right = node indices (-1 in a leaf), a leaf's triangle list = kd_tri_indices[tri_start .. +tri_count)
+ * in the leaf's own order (a triangle straddling a split plane is listed in several leaves). */
+typedef struct rt_kd_node {
+    float aabb_min[3];
+    int32_t left;
+    float aabb_max[3];
+    int32_t right;
+    int32_t split_axis;
+    float split_distance;   /* split plane = aabb_min[split_axis] + split_distance (kdtree.cpp:171) */
+    uint32_t tri_start, tri_count;
+} rt_kd_node;
+
+/* The reference's uniform grid (Grid, infra/grid.h:25-34; built by Grid::Build, infra/grid.cpp:4-60), flattened:
+ * cell (x, y, z) has index x + y*res.x + z*res.x*res.y (grid.cpp:52) and lists
+ * tri_indices[cell_start[i] .. cell_start[i+1]) in the order Grid::Build pushed them. */
+typedef struct rt_grid_desc {
+    int32_t resolution[3];
+    float cell_size[3];
+    float bounds_min[3], bounds_max[3];   /* Grid::localBounds */
+    const uint32_t* cell_start;           /* resolution.x*y*z + 1 entries */
+    const uint32_t* tri_indices;
+    uint32_t index_count;
+} rt_grid_desc;
+
+enum {
+    RT_SCENE_FLAT = 0,          /* FileScene, USE_BVH */
+    RT_SCENE_TLAS = 1,          /* TLASFileScene, TLAS_USE_BVH */
+    RT_SCENE_FLAT_KDTREE = 2,   /* FileScene, USE_KDTree (the configuration the reference ships, file_scene.h:10-12) */
+    RT_SCENE_FLAT_GRID = 3      /* FileScene, USE_Grid */
+};
 
 typedef struct rt_scene_desc {
     int32_t kind;
@@ -123,6 +155,14 @@ typedef struct rt_scene_desc {
     float light_size;               /* half edge */
     float light_color[3];           /* GetLightColor(): (24,24,22) */
     float light_pos[3];             /* GetLightPos() */
+    /* ABI v3: the other two accelerators of FileScene.  For these kinds blas[0]
+     * carries only tris / tri_count / obj_idx = -1 (KDTree::triangles, Grid::triangles); nodes and tri_indices
+     * are ignored. */
+    const rt_kd_node* kd_nodes;     /* RT_SCENE_FLAT_KDTREE */
+    uint32_t kd_node_count;
+    const uint32_t* kd_tri_indices;
+    uint32_t kd_tri_index_count;
+    const rt_grid_desc* grid;       /* RT_SCENE_FLAT_GRID */
 } rt_scene_desc;
 
 /* ---- rays and hits (Ray, template/ray.h:6-41, as plain records) ------------------------------ */
@@ -160,7 +200,8 @@ rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags,
 void rt_scene_destroy(rt_scene* scene);
 
 /* Batched BaseScene::FindNearest (file_scene.cpp:170-175 / tlas_file_scene.cpp:201-206):
- * light quad, floor plane, then the BVH / TLAS.  Host buffers; H2D + kernel + D2H inside the call. */
+ * light quad, floor plane, then the accelerator: BVH (bvh.cpp:224-288), TLAS (tlas_bvh.cpp:83-111), KD-tree
+ * (kdtree.cpp:144-210) or grid (grid.cpp:94-161).  Host buffers; H2D + kernel + D2H inside the call. */
 rt_status rt_find_nearest(rt_scene* scene, const rt_ray* rays, rt_hit* hits, size_t n);
 /* Batched BaseScene::IsOccluded (file_scene.cpp:177-187 / tlas_file_scene.cpp:208-218). */
 rt_status rt_is_occluded(rt_scene* scene, const rt_ray* rays, uint8_t* occluded, size_t n);

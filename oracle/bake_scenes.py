@@ -24,6 +24,13 @@ SCENES = {
     "instanced_tlas": ("tlas", "instanced_scene.xml"),         # BASELINE config 3
     "inside_flat": ("file", "inside_scene.xml"),
     "wok_teapot_tlas": ("tlas", "wok_teapot_scene.xml"),
+    # FileScene with its other two accelerators: KD-tree as shipped, uniform grid
+    "wok_teapot_kd": ("file_kd", "wok_teapot_scene.xml"),
+    "wok_teapot_grid": ("file_grid", "wok_teapot_scene.xml"),
+    "bunny_kd": ("file_kd", "bunny_scene.xml"),
+    "bunny_grid": ("file_grid", "bunny_scene.xml"),
+    "inside_kd": ("file_kd", "inside_scene.xml"),
+    "inside_grid": ("file_grid", "inside_scene.xml"),
 }
 
 

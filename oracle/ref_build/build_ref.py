@@ -30,7 +30,7 @@ REF = os.environ.get("RT_REFERENCE_DIR", "/root/reference")
 
 TEMPLATE_FILES = ["tmplmath.h", "tmplmath.cpp", "common.h", "ray.h", "camera.h", "primitives.h",
                   "texture.h", "material.h"]
-INFRA_FILES = ["bvh.h", "bvh.cpp", "blas_bvh.h", "blas_bvh.cpp", "tlas_bvh.h", "tlas_bvh.cpp",
+INFRA_FILES = ["kdtree.cpp", "grid.cpp", "bvh.h", "bvh.cpp", "blas_bvh.h", "blas_bvh.cpp", "tlas_bvh.h", "tlas_bvh.cpp",
                "grid.h", "blas_grid.h", "tlas_grid.h", "kdtree.h", "blas_kdtree.h", "tlas_kdtree.h",
                "helper.h", "hit_info.h", "model.h", "model.cpp"]
 SCENE_FILES = ["base_scene.h", "file_scene.h", "file_scene.cpp", "tlas_file_scene.h", "tlas_file_scene.cpp"]
@@ -45,7 +45,7 @@ def sub(text, pattern, repl, name, count=0, flags=0, min_hits=1):
     return new
 
 
-def patch_sources(d, integrator, big_tlas):
+def patch_sources(d, integrator, big_tlas, accel="bvh"):
     def edit(fn, fun):
         p = os.path.join(d, fn)
         with open(p, encoding="utf-8-sig") as f:
@@ -84,8 +84,15 @@ def patch_sources(d, integrator, big_tlas):
     # compile-time screen size becomes the shim's run-time globals (camera.h:4-5)
     edit("camera.h", lambda s: sub(s, r"#define SCRWIDTH\s+\d+\s*\n#define SCRHEIGHT\s+\d+", "", "scr size"))
     # README.md:45-51: choose the BVH in FileScene (ships as KD-tree, file_scene.h:10-12)
-    edit("file_scene.h", lambda s: sub(sub(s, r"//#define USE_BVH", "#define USE_BVH", "use bvh"),
-                                       r"#define USE_KDTree", "//#define USE_KDTree", "no kdtree"))
+    # accel == "kdtree" keeps the shipped configuration
+    if accel == "bvh":
+        edit("file_scene.h", lambda s: sub(sub(s, r"//#define USE_BVH", "#define USE_BVH", "use bvh"),
+                                           r"#define USE_KDTree", "//#define USE_KDTree", "no kdtree"))
+    elif accel == "grid":
+        edit("file_scene.h", lambda s: sub(sub(s, r"//#define USE_Grid", "#define USE_Grid", "use grid"),
+                                           r"#define USE_KDTree", "//#define USE_KDTree", "no kdtree"))
+        # resolution / cellSize / gridCells are private (grid.h:25-30); the flattener copies them
+        edit("grid.h", lambda s: sub(s, r"private:", "public:", "grid private", min_hits=2))
     # TLAS internals are needed by the flattener (tlas_bvh.h:27 keeps tlasNode private)
     edit("tlas_bvh.h", lambda s: sub(s, r"private:", "public:", "tlas private"))
     # texel array is private (texture.h:98-101); the flattener copies it
@@ -120,7 +127,7 @@ def patch_sources(d, integrator, big_tlas):
         edit("renderer.cpp", lambda s: sub(sub(s, r'system\("cls"\);', "", "cls"), r'\n\s*printf\("(Total|Average|Peak)[^\n]*', "", "prints", min_hits=6))
 
 
-def build_variant(integrator, scene_kind, cxx="g++", extra_flags=(), suffix="", big_tlas=False, verbose=False, gpuhost=False):
+def build_variant(integrator, scene_kind, cxx="g++", extra_flags=(), suffix="", big_tlas=False, verbose=False, gpuhost=False, accel="bvh"):
     os.makedirs(OUT, exist_ok=True)
     d = tempfile.mkdtemp(prefix="ref_build_")
     try:
@@ -134,12 +141,12 @@ def build_variant(integrator, scene_kind, cxx="g++", extra_flags=(), suffix="", 
             shutil.copy(os.path.join(REF, RENDERER_DIRS[integrator], fn), d)
         for fn in os.listdir(d):
             os.chmod(os.path.join(d, fn), 0o644)
-        patch_sources(d, integrator, big_tlas)
+        patch_sources(d, integrator, big_tlas, accel)
         unity = os.path.join(d, "unity.cpp")
         with open(unity, "w") as f:
             f.write('#include "precomp.h"\n')
-            for src in ["tmplmath.cpp", "bvh.cpp", "blas_bvh.cpp", "tlas_bvh.cpp", "model.cpp",
-                        "file_scene.cpp", "tlas_file_scene.cpp", "renderer.cpp"]:
+            for src in ["tmplmath.cpp", "bvh.cpp", "blas_bvh.cpp", "tlas_bvh.cpp", "model.cpp"] + \
+                       {"kdtree": ["kdtree.cpp"], "grid": ["grid.cpp"]}.get(accel, []) + ["file_scene.cpp", "tlas_file_scene.cpp", "renderer.cpp"]:
                 f.write(f'#include "{src}"\n')
             f.write(f'#include "{os.path.join(HERE, "ref_api.cpp")}"\n')
             if gpuhost:
@@ -171,14 +178,21 @@ def build_variant(integrator, scene_kind, cxx="g++", extra_flags=(), suffix="", 
 def build_all(verbose=False, gpuhost=True):
     if not os.path.isdir(REF):
         raise FileNotFoundError(f"{REF} not present: oracle/_ref can only be (re)built where the reference is mounted")
-    outs = []
+    jobs = []
     for integ in ("whitted", "pt"):
         for kind in ("file", "tlas"):
-            outs.append(build_variant(integ, kind, verbose=verbose))
+            jobs.append(dict(integrator=integ, scene_kind=kind))
     # "reference-like" flags for the CPU baseline: mirrors MSVC /O2 /arch:AVX2 /fp:fast
     # (whitted-style-bvh.vcxproj:93-102); not a parity oracle
     for kind in ("file", "tlas"):
-        outs.append(build_variant("pt", kind, extra_flags=("-O3", "-mavx2", "-mfma", "-ffast-math"), suffix="_fast", verbose=verbose))
+        jobs.append(dict(integrator="pt", scene_kind=kind, extra_flags=("-O3", "-mavx2", "-mfma", "-ffast-math"), suffix="_fast"))
+    # FileScene as shipped: KD-tree accelerator (file_scene.h:10-12), and its third option, the uniform grid
+    for integ in ("whitted", "pt"):
+        jobs.append(dict(integrator=integ, scene_kind="file", suffix="_kd", accel="kdtree"))
+        jobs.append(dict(integrator=integ, scene_kind="file", suffix="_grid", accel="grid"))
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:  # g++ subprocesses, one temp dir each
+        outs = list(ex.map(lambda kw: build_variant(verbose=verbose, **kw), jobs))
     if gpuhost:
         outs += build_gpuhost(verbose=verbose)
     return outs

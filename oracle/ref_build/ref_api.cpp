@@ -233,7 +233,79 @@ int ref_flatten( const char* out_path )
 	std::vector<uint> triIdx;
 	std::vector<int32_t> objMaterial;
 	FlatHeader h = {};
-#ifdef REF_SCENE_FILE
+#if defined(REF_SCENE_FILE) && defined(USE_KDTree)
+	// FileScene as shipped (file_scene.h:10-12): spatial-median KD-tree, pointer nodes, per-leaf index vectors
+	// (kdtree.cpp:45-112).  Flattened depth first: node 0 = root, children by index, leaf lists concatenated.
+	h.kind = 2;
+	struct FlatKdNode { float aabbMin[3]; int32_t left; float aabbMax[3]; int32_t right; int32_t splitAxis; float splitDistance; uint32_t triStart, triCount; };
+	std::vector<FlatKdNode> kdNodes;
+	std::vector<uint> kdTriIdx;
+	{
+		std::vector<std::pair<KDTreeNode*, int>> todo; // node, slot
+		kdNodes.push_back( FlatKdNode() );
+		todo.push_back( { scene.acc.rootNode, 0 } );
+		while (!todo.empty())
+		{
+			auto it = todo.back();
+			todo.pop_back();
+			KDTreeNode* n = it.first;
+			FlatKdNode f = {};
+			f.aabbMin[0] = n->aabbMin.x, f.aabbMin[1] = n->aabbMin.y, f.aabbMin[2] = n->aabbMin.z;
+			f.aabbMax[0] = n->aabbMax.x, f.aabbMax[1] = n->aabbMax.y, f.aabbMax[2] = n->aabbMax.z;
+			f.splitAxis = n->splitAxis, f.splitDistance = n->splitDistance;
+			f.left = f.right = -1;
+			if (n->isLeaf)
+			{
+				f.triStart = (uint32_t)kdTriIdx.size(), f.triCount = (uint32_t)n->triIndices.size();
+				kdTriIdx.insert( kdTriIdx.end(), n->triIndices.begin(), n->triIndices.end() );
+			}
+			else
+			{
+				f.left = (int32_t)kdNodes.size(), f.right = f.left + 1;
+				kdNodes.push_back( FlatKdNode() ), kdNodes.push_back( FlatKdNode() );
+				todo.push_back( { n->right, f.right } ), todo.push_back( { n->left, f.left } );
+			}
+			kdNodes[it.second] = f;
+		}
+		FlatBlas b = {};
+		b.tri_count = (uint32_t)scene.acc.triangles.size();
+		mat4 I;
+		memcpy( b.T, I.cell, 64 ), memcpy( b.invT, I.cell, 64 );
+		b.obj_idx = -1, b.mat_idx = -1;
+		blasTable.push_back( b );
+		tris = scene.acc.triangles;
+		for (auto* m : scene.models) objMaterial.push_back( m->matIdx );
+	}
+	w.chunk( "kd_nodes", kdNodes.data(), kdNodes.size() * sizeof( FlatKdNode ) );
+	w.chunk( "kd_tri_indices", kdTriIdx.data(), kdTriIdx.size() * sizeof( uint ) );
+#elif defined(REF_SCENE_FILE) && defined(USE_Grid)
+	// FileScene with the uniform grid (grid.cpp:4-60): per-cell index vectors concatenated in cell order
+	h.kind = 3;
+	struct FlatGridHeader { int32_t resolution[3]; float cellSize[3], boundsMin[3], boundsMax[3]; } gh = {};
+	std::vector<uint> cellStart, gridTriIdx;
+	{
+		Grid& g = scene.acc;
+		for (int i = 0; i < 3; i++)
+			gh.resolution[i] = g.resolution[i], gh.cellSize[i] = g.cellSize[i], gh.boundsMin[i] = g.localBounds.bmin[i], gh.boundsMax[i] = g.localBounds.bmax[i];
+		for (const GridCell& c : g.gridCells)
+		{
+			cellStart.push_back( (uint)gridTriIdx.size() );
+			for (int t : c.triIndices) gridTriIdx.push_back( (uint)t );
+		}
+		cellStart.push_back( (uint)gridTriIdx.size() );
+		FlatBlas b = {};
+		b.tri_count = (uint32_t)g.triangles.size();
+		mat4 I;
+		memcpy( b.T, I.cell, 64 ), memcpy( b.invT, I.cell, 64 );
+		b.obj_idx = -1, b.mat_idx = -1;
+		blasTable.push_back( b );
+		tris = g.triangles;
+		for (auto* m : scene.models) objMaterial.push_back( m->matIdx );
+	}
+	w.chunk( "grid_header", &gh, sizeof( gh ) );
+	w.chunk( "grid_cell_start", cellStart.data(), cellStart.size() * sizeof( uint ) );
+	w.chunk( "grid_tri_indices", gridTriIdx.data(), gridTriIdx.size() * sizeof( uint ) );
+#elif defined(REF_SCENE_FILE)
 	h.kind = 0;
 	{
 		FlatBlas b = {};

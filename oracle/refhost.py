@@ -22,6 +22,7 @@ u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
 
 
 def lib_path(integrator, kind, fast=False):
+    """kind: file | tlas | file_kd (FileScene with the KD-tree it ships with)"""
     return os.path.join(REF_DIR, f"libref_{integrator}_{kind}{'_fast' if fast else ''}.so")
 
 

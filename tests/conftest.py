@@ -36,7 +36,7 @@ def scene_path(name):
 
 
 def all_scene_names():
-    return ["golden_file", "golden_tlas"] + baked_scenes()
+    return ["golden_file", "golden_tlas", "golden_kd", "golden_grid"] + baked_scenes()
 
 
 @pytest.fixture(scope="session")
@@ -105,9 +105,16 @@ def random_rays(flat, n, seed):
         D[axis * k:(axis + 1) * k, axis] = 0.0
     D[3 * k:4 * k] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, k)] * rng.choice([-1.0, 1.0], (k, 1)).astype(np.float32)
     # origins exactly on node-box planes: 0 * inf = NaN in the slab test
-    nodes = flat.nodes
-    pick = rng.integers(0, len(nodes), k)
-    O[3 * k:4 * k] = nodes["aabb_min"][pick]
+    if flat.kind == 2:      # KD-tree: node boxes (a split plane is the max / min of the two children)
+        planes = flat.kd_nodes["aabb_min"]
+    elif flat.kind == 3:    # grid: cell corners
+        g = flat.grid_header[0]
+        ijk = np.stack([rng.integers(0, int(r) + 1, 4 * k) for r in g["resolution"]], 1)
+        planes = (g["bounds_min"][None, :] + ijk.astype(np.float32) * g["cell_size"][None, :]).astype(np.float32)
+    else:
+        planes = flat.nodes["aabb_min"]
+    pick = rng.integers(0, len(planes), k)
+    O[3 * k:4 * k] = planes[pick]
     nrm = np.linalg.norm(D, axis=1, keepdims=True)
     D = (D / np.where(nrm > 0, nrm, 1)).astype(np.float32)
     return api.make_rays(O, D)

@@ -2,7 +2,8 @@
 """Generate the committed golden vectors from the REFERENCE'S OWN CODE (oracle/_ref, built headless).
 
 Run here (where /root/reference is mounted):   python tests/golden/make_golden.py
-Outputs, per scene kind k in {file, tlas} (FileScene+USE_BVH / TLASFileScene+TLAS_USE_BVH):
+Outputs, per scene kind k in {file, tlas, kd, grid} (FileScene+USE_BVH / TLASFileScene+TLAS_USE_BVH /
+FileScene+USE_KDTree as shipped / FileScene+USE_Grid); `make_golden.py kd grid` regenerates only those:
   tests/golden/golden_<k>.rtscene.gz   the reference's flattened scene (inputs)
   tests/golden/golden_<k>.npz          what the reference computed on it:
       cam_*            two cameras (default, look-at) as 4x3 (camPos, topLeft, topRight, bottomLeft)
@@ -31,10 +32,11 @@ def main():
     import cpu_ray_tracer_b200 as rtb
     from cpu_ray_tracer_b200 import api
 
-    for kind in ("file", "tlas"):
+    libkind = {"file": "file", "tlas": "tlas", "kd": "file_kd", "grid": "file_grid"}
+    for kind in (sys.argv[1:] or list(libkind)):
         out = {}
-        wh = RefRenderer("whitted", kind, "golden_scene.xml", W, H)
-        pt = RefRenderer("pt", kind, "golden_scene.xml", W, H)
+        wh = RefRenderer("whitted", libkind[kind], "golden_scene.xml", W, H)
+        pt = RefRenderer("pt", libkind[kind], "golden_scene.xml", W, H)
         scene_path = os.path.join(HERE, f"golden_{kind}.rtscene")
         pt.flatten(scene_path)
         fs = rtb.FlatScene.load(scene_path)

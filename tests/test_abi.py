@@ -30,14 +30,14 @@ def test_library_exports_every_declared_symbol():
     for name in declared_functions():
         assert hasattr(L, name), f"librt_b200.so does not export {name}"
     assert set(api.EXPORTS) == set(declared_functions())
-    assert L.rt_abi_version() == 2
+    assert L.rt_abi_version() == 3
 
 
 def test_struct_sizes_match_header(tmp_path):
     """compile a C probe against the header and compare sizeof() with the ctypes mirror"""
     from cpu_ray_tracer_b200 import abi
     structs = ["rt_bvh_node", "rt_tri", "rt_tlas_node", "rt_blas_desc", "rt_material", "rt_texture",
-               "rt_scene_desc", "rt_ray", "rt_hit", "rt_camera", "rt_render_params", "rt_counters"]
+               "rt_scene_desc", "rt_ray", "rt_hit", "rt_camera", "rt_render_params", "rt_counters", "rt_kd_node", "rt_grid_desc"]
     probe = tmp_path / "probe.c"
     probe.write_text('#include <stdio.h>\n#include "rt_b200.h"\nint main(void){\n' +
                      "".join(f'printf("{s} %zu\\n", sizeof({s}));\n' for s in structs) + "return 0;}\n")
@@ -50,6 +50,7 @@ def test_struct_sizes_match_header(tmp_path):
               "rt_blas_desc": C.sizeof(abi.rt_blas_desc), "rt_texture": C.sizeof(abi.rt_texture),
               "rt_scene_desc": C.sizeof(abi.rt_scene_desc), "rt_camera": C.sizeof(abi.rt_camera),
               "rt_render_params": C.sizeof(abi.rt_render_params), "rt_counters": C.sizeof(abi.rt_counters),
+              "rt_kd_node": abi.KD_NODE_DTYPE.itemsize, "rt_grid_desc": C.sizeof(abi.rt_grid_desc),
               "rt_material_ct": C.sizeof(abi.rt_material)}
     for s in structs:
         assert int(sizes[s]) == mirror[s], s

@@ -209,7 +209,7 @@ def test_path_tracer_vs_oracle_reference_rng(name, schedule, oracles, gpu_scenes
     r.close()
 
 
-@pytest.mark.parametrize("kind", ["file", "tlas"])
+@pytest.mark.parametrize("kind", ["file", "tlas", "kd", "grid"])
 def test_integrators_vs_committed_golden(kind, oracles, gpu_scenes):
     """the vectors the reference's own build produced (tests/golden/make_golden.py), second camera too"""
     from cpu_ray_tracer_b200 import api

@@ -13,7 +13,36 @@ def raw_equal(a, b):
     return a.shape == b.shape and a.tobytes() == b.tobytes()
 
 
-@pytest.mark.parametrize("name", all_scene_names())
+def _is_alt(name):
+    return name.endswith(("_kd", "_grid"))
+
+
+@pytest.mark.parametrize("name", [n for n in all_scene_names() if n.endswith("_kd")])
+def test_kdtree_builder_matches_reference(name, flat_scenes):
+    """KDTree::Build restated on the host: same nodes (boxes, split axis / distance, links), same leaf lists"""
+    fs = flat_scenes(name)
+    nodes, idx, depth = host_build.build_kdtree(fs.tris)
+    assert depth <= 20 and len(nodes) == len(fs.kd_nodes)
+    assert raw_equal(nodes, fs.kd_nodes), "KD nodes differ from KDTree::Build"
+    assert raw_equal(idx, fs.kd_tri_indices), "KD leaf lists differ"
+
+
+@pytest.mark.parametrize("name", [n for n in all_scene_names() if n.endswith("_grid")])
+def test_grid_builder_matches_reference(name, flat_scenes):
+    fs = flat_scenes(name)
+    hdr, start, idx = host_build.build_grid(fs.tris)
+    assert raw_equal(hdr, fs.grid_header), "resolution / cell size / bounds differ from Grid::Build"
+    assert raw_equal(start, fs.grid_cell_start) and raw_equal(idx, fs.grid_tri_indices)
+
+
+def test_with_accelerator_rebuilds_the_same_scene(flat_scenes):
+    kd = host_build.with_accelerator(flat_scenes("golden_file"), "kdtree")
+    assert kd.kind == abi.RT_SCENE_FLAT_KDTREE and raw_equal(kd.kd_nodes, flat_scenes("golden_kd").kd_nodes)
+    gr = host_build.with_accelerator(flat_scenes("golden_file"), "grid")
+    assert gr.kind == abi.RT_SCENE_FLAT_GRID and raw_equal(gr.grid_tri_indices, flat_scenes("golden_grid").grid_tri_indices)
+
+
+@pytest.mark.parametrize("name", [n for n in all_scene_names() if not _is_alt(n)])
 def test_sah_builder_matches_reference(name, flat_scenes):
     fs = flat_scenes(name)
     for b in fs.blas_table:
