@@ -534,27 +534,35 @@ __device__ __forceinline__ bool test_run(const float4* __restrict__ tris, int sl
     return false;
 }
 
-template <bool ANYHIT, bool COUNTERS>
-__device__ __forceinline__ void traverse_kd(const DScene& s, const float3 O, const float3 D, HitRec& hit)
-{
-    const float3 rD = recip(D);
-    const bool exact = needs_exact_slab(O, D);
-    const float4* __restrict__ nodes = s.kd_nodes;
+// The traversal as a cursor: start() positions it on the root, step() visits ONE node (box test, then either the
+// whole leaf or the child choice) and returns true when the ray is finished.  traverse_kd() just loops it; the
+// stream kernel of the path tracer (rt_render.cu) interleaves steps of 32 lanes under a warp vote.
+struct KdCursor {
+    int cur, sp;
+    float3 rD;
+    bool exact;
     int stackNode[KD_STACK_SIZE];
     float stackT[KD_STACK_SIZE];
-    int sp = 0, cur = 0;
-    while (true)
+
+    __device__ __forceinline__ bool start(const DScene&, const float3 O, const float3 D, const HitRec&)
+    {
+        rD = recip(D), exact = needs_exact_slab(O, D), cur = 0, sp = 0;
+        return false;
+    }
+
+    template <bool ANYHIT, bool COUNTERS>
+    __device__ __forceinline__ bool step(const DScene& s, const float3 O, const float3 D, HitRec& hit)
     {
         if (COUNTERS) hit.traversed++;
+        const float4* __restrict__ nodes = s.kd_nodes;
         const float4 k0 = __ldg(nodes + 2 * (size_t)cur), k1 = __ldg(nodes + 2 * (size_t)cur + 1);
         float tmin, tmax;
-        bool descend = false;
         if (slab_range(O, rD, hit.t, exact, k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, tmin, tmax))
         {
             const int a = __float_as_int(k1.z);
             if (a < 0)
             {
-                if (test_run<ANYHIT, COUNTERS>(s.tris, ~a, __float_as_int(k1.w), O, D, hit)) return;
+                if (test_run<ANYHIT, COUNTERS>(s.tris, ~a, __float_as_int(k1.w), O, D, hit)) return true;
             }
             else
             {
@@ -566,17 +574,24 @@ __device__ __forceinline__ void traverse_kd(const DScene& s, const float3 O, con
                 if ((double)t < (double)tmin + 0.001) cur = farC;       // :177 / :196: only the far side is crossed
                 else if ((double)t > (double)tmax - 0.001) cur = nearC; // :182 / :201
                 else stackNode[sp] = farC, stackT[sp] = t, sp++, cur = nearC;
-                descend = true;
+                return false;
             }
         }
-        if (descend) continue;
         while (true)
         {
-            if (sp == 0) return;
+            if (sp == 0) return true;
             sp--;
-            if (!(hit.t < stackT[sp])) { cur = stackNode[sp]; break; } // :189 / :208 `if (ray.t < t) return;`
+            if (!(hit.t < stackT[sp])) { cur = stackNode[sp]; return false; } // :189 / :208 `if (ray.t < t) return;`
         }
     }
+};
+
+template <bool ANYHIT, bool COUNTERS>
+__device__ __forceinline__ void traverse_kd(const DScene& s, const float3 O, const float3 D, HitRec& hit)
+{
+    KdCursor c;
+    if (c.start(s, O, D, hit)) return;
+    while (!c.template step<ANYHIT, COUNTERS>(s, O, D, hit)) {}
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -591,55 +606,70 @@ __device__ __forceinline__ int cvtt_x86(float x)
     return (x >= 2147483648.0f || x < -2147483648.0f || x != x) ? (int)0x80000000u : (int)x;
 }
 
-template <bool ANYHIT, bool COUNTERS>
-__device__ __forceinline__ void traverse_grid(const DScene& s, const float3 O, const float3 D, HitRec& hit)
-{
-    const float3 rD = recip(D);
-    float tminU, tmaxU;
-    if (!slab_range(O, rD, hit.t, needs_exact_slab(O, D), s.grid_min[0], s.grid_min[1], s.grid_min[2],
-                    s.grid_max[0], s.grid_max[1], s.grid_max[2], tminU, tmaxU)) return;
-    int cell[3], step[3], exitc[3];
+// Cursor form, as for the KD-tree: start() runs the bounds test and the DDA set-up (grid.cpp:96-120, true = the
+// ray misses the grid), step() visits ONE cell and advances (grid.cpp:122-152).
+struct GridCursor {
+    int cell[3], stp[3], exitc[3];
     float deltaT[3], nextT[3];
-#pragma unroll
-    for (int i = 0; i < 3; i++)
+
+    __device__ __forceinline__ bool start(const DScene& s, const float3 O, const float3 D, const HitRec& hit)
     {
-        const float rayOrigCell = axis_of(O, i) - s.grid_min[i];
-        cell[i] = clampi(cvtt_x86(floorf(rayOrigCell / s.grid_cell[i])), 0, s.grid_res[i] - 1);
-        if (axis_of(D, i) < 0)
+        const float3 rD = recip(D);
+        float tminU, tmaxU;
+        if (!slab_range(O, rD, hit.t, needs_exact_slab(O, D), s.grid_min[0], s.grid_min[1], s.grid_min[2],
+                        s.grid_max[0], s.grid_max[1], s.grid_max[2], tminU, tmaxU)) return true;
+#pragma unroll
+        for (int i = 0; i < 3; i++)
         {
-            deltaT[i] = -s.grid_cell[i] * axis_of(rD, i);
-            nextT[i] = (cell[i] * s.grid_cell[i] - rayOrigCell) * axis_of(rD, i);
-            exitc[i] = -1, step[i] = -1;
+            const float rayOrigCell = axis_of(O, i) - s.grid_min[i];
+            cell[i] = clampi(cvtt_x86(floorf(rayOrigCell / s.grid_cell[i])), 0, s.grid_res[i] - 1);
+            if (axis_of(D, i) < 0)
+            {
+                deltaT[i] = -s.grid_cell[i] * axis_of(rD, i);
+                nextT[i] = (cell[i] * s.grid_cell[i] - rayOrigCell) * axis_of(rD, i);
+                exitc[i] = -1, stp[i] = -1;
+            }
+            else
+            {
+                deltaT[i] = s.grid_cell[i] * axis_of(rD, i);
+                nextT[i] = ((cell[i] + 1) * s.grid_cell[i] - rayOrigCell) * axis_of(rD, i);
+                exitc[i] = s.grid_res[i], stp[i] = 1;
+            }
         }
-        else
-        {
-            deltaT[i] = s.grid_cell[i] * axis_of(rD, i);
-            nextT[i] = ((cell[i] + 1) * s.grid_cell[i] - rayOrigCell) * axis_of(rD, i);
-            exitc[i] = s.grid_res[i], step[i] = 1;
-        }
+        return false;
     }
-    const int resX = s.grid_res[0], resXY = s.grid_res[0] * s.grid_res[1];
-    while (true)
+
+    template <bool ANYHIT, bool COUNTERS>
+    __device__ __forceinline__ bool step(const DScene& s, const float3 O, const float3 D, HitRec& hit)
     {
         if (COUNTERS) hit.traversed++;
-        const int2 c = __ldg(s.grid_cells + (unsigned)(cell[0] + cell[1] * resX + cell[2] * resXY));
-        if (test_run<ANYHIT, COUNTERS>(s.tris, c.x, c.y, O, D, hit)) return;
+        const int2 c = __ldg(s.grid_cells + (unsigned)(cell[0] + cell[1] * s.grid_res[0] + cell[2] * s.grid_res[0] * s.grid_res[1]));
+        if (test_run<ANYHIT, COUNTERS>(s.tris, c.x, c.y, O, D, hit)) return true;
         // grid.cpp:139-144: k = (x<y)<<2 | (x<z)<<1 | (y<z), map = {2,1,2,1,2,2,0,0}
         const bool xy = nextT[0] < nextT[1], xz = nextT[0] < nextT[2], yz = nextT[1] < nextT[2];
         const int axis = xy ? (xz ? 0 : 2) : (yz ? 1 : 2);
-        // the unrolled selects keep cell / nextT in registers (no dynamically indexed local arrays)
+        // unrolled selects keep cell / nextT in registers (no dynamically indexed local arrays)
         const float nt = axis == 0 ? nextT[0] : (axis == 1 ? nextT[1] : nextT[2]);
-        if (hit.t < nt) return;
+        if (hit.t < nt) return true;
 #pragma unroll
         for (int i = 0; i < 3; i++)
-            if (axis == i) cell[i] += step[i];
+            if (axis == i) cell[i] += stp[i];
         const int ca = axis == 0 ? cell[0] : (axis == 1 ? cell[1] : cell[2]);
         const int ea = axis == 0 ? exitc[0] : (axis == 1 ? exitc[1] : exitc[2]);
-        if (ca == ea) return;
+        if (ca == ea) return true;
 #pragma unroll
         for (int i = 0; i < 3; i++)
             if (axis == i) nextT[i] += deltaT[i];
+        return false;
     }
+};
+
+template <bool ANYHIT, bool COUNTERS>
+__device__ __forceinline__ void traverse_grid(const DScene& s, const float3 O, const float3 D, HitRec& hit)
+{
+    GridCursor c;
+    if (c.start(s, O, D, hit)) return;
+    while (!c.template step<ANYHIT, COUNTERS>(s, O, D, hit)) {}
 }
 
 template <int ACCEL, bool ANYHIT, bool COUNTERS>

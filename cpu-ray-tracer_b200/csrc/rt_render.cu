@@ -344,6 +344,7 @@ constexpr int STREAM_MAX_DEPTH = 8;
 // them out longest first (LPT list scheduling).
 constexpr int PILOT_PATHS = 16;
 
+template <int ACCEL>
 __global__ void __launch_bounds__(128) k_pt_pilot(const PTState p, const DScene s, const DCamera cam, unsigned int* __restrict__ cost)
 {
     const int n = p.nTiles * PILOT_PATHS;
@@ -360,7 +361,7 @@ __global__ void __launch_bounds__(128) k_pt_pilot(const PTState p, const DScene 
         for (int depth = 0;; depth++)
         {
             HitRec h;
-            find_nearest<true>(s, O, D, 1e34f, h);
+            find_nearest<true, ACCEL>(s, O, D, 1e34f, h);
             c += 8u + (unsigned)h.traversed + 2u * (unsigned)h.tested;
             float3 L, w, nO, nD;
             bool nInside;
@@ -558,6 +559,118 @@ __global__ void __launch_bounds__(128) k_pt_streams2(const PTState p, const DSce
                     }
                     else state = ST_DEAD;
                 }
+            }
+        }
+    }
+#undef RT_START_RAY
+    for (int off = 16; off; off >>= 1) rays += __shfl_xor_sync(FULL, rays, off);
+    if (lane == 0) atomicAdd(p.counters, rays);
+}
+
+// Stream kernel for FileScene's other accelerators (KD-tree, uniform grid): the same schedule as version 2 - one
+// (tile, frame) RNG stream per lane, path state in registers, lanes pull the next stream when theirs ends - with
+// the traversal expressed through the accelerator's cursor (rt_device.cuh KdCursor / GridCursor: one node or one
+// cell per step).  Two live states, TRAV and SHADE: the warp runs the action most lanes wait for and keeps stepping
+// the traversal without a new vote while at least 3/4 of the lanes that entered are still traversing.
+template <int ACCEL> struct CursorOf { typedef KdCursor type; };
+template <> struct CursorOf<ACCEL_GRID> { typedef GridCursor type; };
+enum { SA_DEAD = 0, SA_TRAV = 1, SA_SHADE = 2 };
+
+template <int ACCEL>
+__global__ void __launch_bounds__(128) k_pt_streams_alt(const PTState p, const DScene s, const DCamera cam,
+    const int* __restrict__ tileOrder, const int frames, int* __restrict__ streamCounter)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int total = p.slots;
+    bool poolEmpty = false;
+    int state = SA_DEAD;
+    int tile = 0, pix = 0, depth = 0;
+    bool inside = false;
+    uint32_t seed = 0;
+    float3 wO = f3(0, 0, 0), wD = f3(0, 0, 0);
+    float3 wst[STREAM_MAX_DEPTH];
+    typename CursorOf<ACCEL>::type cursor;
+    HitRec hit;
+    hit.t = 0, hit.u = 0, hit.v = 0, hit.obj = -1, hit.tri = -1, hit.traversed = 0, hit.tested = 0;
+    unsigned long long rays = 0;
+
+    // FindNearest prologue for the ray (wO, wD): light quad, floor plane (file_scene.cpp:172-173), then the accelerator
+#define RT_START_RAY()                                                                         \
+    {                                                                                          \
+        hit.t = 1e34f, hit.u = 0, hit.v = 0, hit.obj = -1, hit.tri = -1;                       \
+        float tq;                                                                              \
+        if (quad_test(s, wO, wD, hit.t, tq)) hit.t = tq, hit.obj = 0;                          \
+        const float3 fn = f3(s.floor_n[0], s.floor_n[1], s.floor_n[2]);                        \
+        const float tp = -(dot(wO, fn) + s.floor_d) / (dot(wD, fn));                           \
+        if (tp < hit.t && tp > 0) hit.t = tp, hit.obj = 1;                                     \
+        state = cursor.start(s, wO, wD, hit) ? SA_SHADE : SA_TRAV;                             \
+        rays++;                                                                                \
+    }
+
+    while (true)
+    {
+        const unsigned mDead = __ballot_sync(FULL, state == SA_DEAD);
+        if (mDead && !poolEmpty)
+        {
+            const int nIdle = __popc(mDead);
+            const int leader = __ffs(mDead) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(streamCounter, nIdle);
+            base = __shfl_sync(FULL, base, leader);
+            if (base + nIdle >= total) poolEmpty = true;
+            const int stream = base + __popc(mDead & ((1u << lane) - 1));
+            if (state == SA_DEAD && stream < total)
+            {
+                const int k = stream / frames, frame = stream - k * frames;
+                tile = p.tileBegin + (tileOrder ? tileOrder[k] : k);
+                seed = pt_seed(p, tile, p.firstSpp + frame * p.stride);
+                pix = 0, depth = 0, inside = false;
+                const int tx = tile % p.tilesX, ty = tile / p.tilesX;
+                const float jy = random_float(seed), jx = random_float(seed);
+                wD = primary_dir(cam, (float)(tx * 16) + jx, (float)(ty * 16) + jy);
+                wO = cam.pos;
+                RT_START_RAY();
+            }
+        }
+        const unsigned mTrav = __ballot_sync(FULL, state == SA_TRAV);
+        const unsigned mShade = __ballot_sync(FULL, state == SA_SHADE);
+        if ((mTrav | mShade) == 0) break;
+        if (__popc(mTrav) >= __popc(mShade))
+        {
+            const int keep = (__popc(mTrav) * 3 + 3) >> 2;
+            do
+            {
+                if (state == SA_TRAV && cursor.template step<false, false>(s, wO, wD, hit)) state = SA_SHADE;
+            } while (__popc(__ballot_sync(FULL, state == SA_TRAV)) >= keep);
+        }
+        else if (state == SA_SHADE)
+        {
+            float3 L, w, nO, nD;
+            bool nInside;
+            if (!pt_bounce(s, p.eps, p.depthLimit, wO, wD, inside, depth, hit.t, hit.u, hit.v, hit.obj, hit.tri, seed, L, w, nO, nD, nInside))
+            {
+                wst[depth] = w;
+                depth++, wO = nO, wD = nD, inside = nInside;
+                RT_START_RAY();
+            }
+            else
+            {
+                for (int d = depth - 1; d >= 0; d--) L = wst[d] * L;
+                const int tx = tile % p.tilesX, ty = tile / p.tilesX;
+                const int x = tx * 16 + (pix & 15), y = ty * 16 + (pix >> 4);
+                float* a = (float*)(p.accum + (x + (size_t)y * p.W));
+                atomicAdd(a + 0, L.x), atomicAdd(a + 1, L.y), atomicAdd(a + 2, L.z);
+                pix++;
+                if (pix < 256)
+                {
+                    const int nx = tx * 16 + (pix & 15), ny = ty * 16 + (pix >> 4);
+                    const float jy = random_float(seed), jx = random_float(seed);
+                    wD = primary_dir(cam, (float)nx + jx, (float)ny + jy);
+                    wO = cam.pos, depth = 0, inside = false;
+                    RT_START_RAY();
+                }
+                else state = SA_DEAD;
             }
         }
     }
@@ -1302,8 +1415,8 @@ rt_status rt_renderer_create(rt_scene* scene, const rt_render_params* params, rt
         r->useStreams = params->schedule != RT_SCHEDULE_WAVEFRONT;
         if ((e = getenv("RT_B200_PT_SCHEDULE")) != nullptr) r->useStreams = strcmp(e, "wavefront") != 0;
         const bool altAccel = scene->d.kind == RT_SCENE_FLAT_KDTREE || scene->d.kind == RT_SCENE_FLAT_GRID;
-        if (altAccel) r->useStreams = false; // the stream kernels' state machine is written for the BVH
         if ((e = getenv("RT_B200_STREAM_KERNEL")) != nullptr && atoi(e) > 0) r->streamKernel = atoi(e);
+        if (altAccel) r->streamKernel = 0; // k_pt_streams_alt: versions 2 / 5 are state machines over the BVH layout
         if ((e = getenv("RT_B200_STREAM_LPT")) != nullptr) r->streamLpt = atoi(e) != 0;
         int occ = 0;
         cudaError_t oe;
@@ -1315,6 +1428,8 @@ rt_status rt_renderer_create(rt_scene* scene, const rt_render_params* params, rt
             if ((e = getenv("RT_B200_STREAM_LANECAP")) != nullptr) r->streamLaneCap = atoi(e) != 0;
             oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, streams5_kernel(scene->d.kind == RT_SCENE_TLAS, r->streamMinB), 128, 0);
         }
+        else if (scene->d.kind == RT_SCENE_FLAT_KDTREE) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams_alt<ACCEL_KD>, 128, 0);
+        else if (scene->d.kind == RT_SCENE_FLAT_GRID) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams_alt<ACCEL_GRID>, 128, 0);
         else if (scene->d.kind == RT_SCENE_TLAS) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams2<true>, 128, 0);
         else oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams2<false>, 128, 0);
         if (oe == cudaSuccess && occ > 0) r->streamCtasPerSm = occ;
@@ -1451,7 +1566,9 @@ static rt_status pt_tile_order(rt_renderer* r, const PTState& p)
     }
     RT_CUDA(cudaMemsetAsync(r->dTileCost, 0, (size_t)n * 4, r->stream));
     r->prof_begin();
-    k_pt_pilot<<<r->sms * 4, 128, 0, r->stream>>>(p, r->scene->d, r->cam, r->dTileCost);
+    if (r->scene->d.kind == RT_SCENE_FLAT_KDTREE) k_pt_pilot<ACCEL_KD><<<r->sms * 4, 128, 0, r->stream>>>(p, r->scene->d, r->cam, r->dTileCost);
+    else if (r->scene->d.kind == RT_SCENE_FLAT_GRID) k_pt_pilot<ACCEL_GRID><<<r->sms * 4, 128, 0, r->stream>>>(p, r->scene->d, r->cam, r->dTileCost);
+    else k_pt_pilot<ACCEL_BVH><<<r->sms * 4, 128, 0, r->stream>>>(p, r->scene->d, r->cam, r->dTileCost);
     r->prof_end(RT_STAGE_GENERATE);
     std::vector<unsigned int> cost(n);
     RT_CUDA(cudaMemcpyAsync(cost.data(), r->dTileCost, (size_t)n * 4, cudaMemcpyDeviceToHost, r->stream));
@@ -1500,6 +1617,8 @@ static rt_status render_pt_streams(rt_renderer* r, int first_spp, int count, int
         streams5_kernel(r->scene->d.kind == RT_SCENE_TLAS, r->streamMinB)<<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6, clk, r->streamKeepShift, laneMask);
         if (clk) r->tileClockRecorded = true, r->lastStreamFrames = count;
     }
+    else if (r->scene->d.kind == RT_SCENE_FLAT_KDTREE) k_pt_streams_alt<ACCEL_KD><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
+    else if (r->scene->d.kind == RT_SCENE_FLAT_GRID) k_pt_streams_alt<ACCEL_GRID><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
     else if (r->scene->d.kind == RT_SCENE_TLAS) k_pt_streams2<true><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
     else k_pt_streams2<false><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
     r->prof_end(RT_STAGE_EXTEND);

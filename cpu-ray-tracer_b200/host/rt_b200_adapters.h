@@ -6,7 +6,8 @@
 // Texture, Camera, TheApp).  It contains no reference code; it only walks the containers the
 // reference's loaders and builders filled and calls the C-ABI.
 //
-//   rtb200::GpuScene<FileScene>       replaces FileScene      (infra/scene/file_scene.h, USE_BVH)
+//   rtb200::GpuScene<FileScene>       replaces FileScene      (infra/scene/file_scene.h; whichever of USE_BVH /
+//                                     USE_KDTree - the shipped default - / USE_Grid file_scene.h:10-12 selects)
 //   rtb200::GpuScene<TLASFileScene>   replaces TLASFileScene  (infra/scene/tlas_file_scene.h, TLAS_USE_BVH)
 //       same BaseScene virtuals (infra/scene/base_scene.h:16-32); FindNearest / IsOccluded run on the
 //       GPU (single-ray calls are an n = 1 batch, plus batched overloads); the remaining queries
@@ -22,9 +23,9 @@
 // adapters for every non-RT_OK status (message = rt_last_error()).  There is no CPU fallback: if the
 // library reports RT_ERR_NO_DEVICE the constructor throws.
 //
-// Requirements on the reference side: FileScene built with USE_BVH (README.md:45-51);
-// read access to TLASBVH::tlasNode / nodesUsed (private at tlas_bvh.h:27 — add an accessor or a friend)
-// and to Texture::pixels.
+// Requirements on the reference side: read access to TLASBVH::tlasNode / nodesUsed (private at
+// tlas_bvh.h:27 — add an accessor or a friend), to Texture::pixels and, for USE_Grid, to Grid::resolution /
+// cellSize / gridCells (private at grid.h:25-30).
 #pragma once
 #include <cstdint>
 #include <cstring>
@@ -52,6 +53,10 @@ struct FlattenedScene
 	std::vector<int32_t> objMaterial;
 	std::vector<rt_material> materials;
 	std::vector<rt_texture> textures;
+	std::vector<rt_kd_node> kdNodes;      // USE_KDTree: KDTreeNode graph, flattened
+	std::vector<uint32_t> altTriIdx;      // KD leaf lists / grid cell lists, concatenated
+	std::vector<uint32_t> gridCellStart;  // USE_Grid
+	rt_grid_desc grid = {};
 	rt_scene_desc desc = {};
 };
 
@@ -112,6 +117,84 @@ inline void Flatten( Tmpl8::FileScene& scene, FlattenedScene& f )
 	b.obj_idx = -1, b.mat_idx = -1;
 	f.blas.push_back( b );
 	for (auto* m : scene.models) f.objMaterial.push_back( m->matIdx );
+	FlattenCommon( scene, f );
+	FinishDesc( f );
+}
+#endif
+
+#if defined(USE_KDTree) || defined(USE_Grid)
+// the one triangle array KDTree / Grid index into (kdtree.h:33, grid.h:33); nodes / tri_indices stay null
+template <class Acc> inline void FlattenTriangles( Tmpl8::FileScene& scene, Acc& acc, FlattenedScene& f )
+{
+	rt_blas_desc b = {};
+	b.tris = (const rt_tri*)acc.triangles.data(), b.tri_count = (uint32_t)acc.triangles.size();
+	const mat4 I;
+	memcpy( b.T, I.cell, 64 ), memcpy( b.inv_T, I.cell, 64 );
+	b.obj_idx = -1, b.mat_idx = -1;
+	f.blas.push_back( b );
+	for (auto* m : scene.models) f.objMaterial.push_back( m->matIdx );
+}
+#endif
+
+#ifdef USE_KDTree
+// FileScene as shipped: the pointer-linked KDTreeNode graph (blas_kdtree.h:16-25) becomes rt_kd_node[]: node 0 = root,
+// children numbered when their parent is visited (depth first, left first), per-leaf index vectors concatenated
+inline void Flatten( Tmpl8::FileScene& scene, FlattenedScene& f )
+{
+	f.desc.kind = RT_SCENE_FLAT_KDTREE;
+	FlattenTriangles( scene, scene.acc, f );
+	std::vector<std::pair<const Tmpl8::KDTreeNode*, uint32_t>> todo;
+	f.kdNodes.push_back( rt_kd_node() );
+	todo.push_back( { scene.acc.rootNode, 0u } );
+	while (!todo.empty())
+	{
+		const Tmpl8::KDTreeNode* n = todo.back().first;
+		const uint32_t slot = todo.back().second;
+		todo.pop_back();
+		rt_kd_node k = {};
+		k.aabb_min[0] = n->aabbMin.x, k.aabb_min[1] = n->aabbMin.y, k.aabb_min[2] = n->aabbMin.z;
+		k.aabb_max[0] = n->aabbMax.x, k.aabb_max[1] = n->aabbMax.y, k.aabb_max[2] = n->aabbMax.z;
+		k.split_axis = n->splitAxis, k.split_distance = n->splitDistance;
+		k.left = k.right = -1;
+		if (n->isLeaf)
+		{
+			k.tri_start = (uint32_t)f.altTriIdx.size(), k.tri_count = (uint32_t)n->triIndices.size();
+			f.altTriIdx.insert( f.altTriIdx.end(), n->triIndices.begin(), n->triIndices.end() );
+		}
+		else
+		{
+			k.left = (int32_t)f.kdNodes.size(), k.right = k.left + 1;
+			f.kdNodes.push_back( rt_kd_node() ), f.kdNodes.push_back( rt_kd_node() );
+			todo.push_back( { n->right, (uint32_t)k.right } ), todo.push_back( { n->left, (uint32_t)k.left } );
+		}
+		f.kdNodes[slot] = k;
+	}
+	f.desc.kd_nodes = f.kdNodes.data(), f.desc.kd_node_count = (uint32_t)f.kdNodes.size();
+	f.desc.kd_tri_indices = f.altTriIdx.data(), f.desc.kd_tri_index_count = (uint32_t)f.altTriIdx.size();
+	FlattenCommon( scene, f );
+	FinishDesc( f );
+}
+#endif
+
+#ifdef USE_Grid
+// FileScene with the uniform grid: per-cell index vectors (blas_grid.h:8-11) concatenated in cell order
+inline void Flatten( Tmpl8::FileScene& scene, FlattenedScene& f )
+{
+	f.desc.kind = RT_SCENE_FLAT_GRID;
+	Tmpl8::Grid& g = scene.acc;
+	FlattenTriangles( scene, g, f );
+	for (int i = 0; i < 3; i++)
+		f.grid.resolution[i] = g.resolution[i], f.grid.cell_size[i] = g.cellSize[i],
+		f.grid.bounds_min[i] = g.localBounds.bmin[i], f.grid.bounds_max[i] = g.localBounds.bmax[i];
+	for (const Tmpl8::GridCell& c : g.gridCells)
+	{
+		f.gridCellStart.push_back( (uint32_t)f.altTriIdx.size() );
+		for (int t : c.triIndices) f.altTriIdx.push_back( (uint32_t)t );
+	}
+	f.gridCellStart.push_back( (uint32_t)f.altTriIdx.size() );
+	f.grid.cell_start = f.gridCellStart.data(), f.grid.tri_indices = f.altTriIdx.data();
+	f.grid.index_count = (uint32_t)f.altTriIdx.size();
+	f.desc.grid = &f.grid;
 	FlattenCommon( scene, f );
 	FinishDesc( f );
 }

@@ -202,7 +202,13 @@ def build_gpuhost(verbose=False):
     """libgpuhost_*: the reference's loaders/builders + our C++ adapters + librt_b200.so (drop-in check)"""
     if not os.path.exists(os.path.join(REPO, "cpu-ray-tracer_b200", "librt_b200.so")):
         raise FileNotFoundError("build cpu-ray-tracer_b200/librt_b200.so first (python __graft_entry__.py)")
-    return [build_variant(integ, kind, verbose=verbose, gpuhost=True) for integ in ("whitted", "pt") for kind in ("file", "tlas")]
+    jobs = [dict(integrator=integ, scene_kind=kind) for integ in ("whitted", "pt") for kind in ("file", "tlas")]
+    # FileScene with the KD-tree it ships with / the grid, through the same adapter header
+    jobs += [dict(integrator="pt", scene_kind="file", suffix="_kd", accel="kdtree"),
+             dict(integrator="whitted", scene_kind="file", suffix="_grid", accel="grid")]
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(6, os.cpu_count() or 1)) as ex:
+        return list(ex.map(lambda kw: build_variant(verbose=verbose, gpuhost=True, **kw), jobs))
 
 
 if __name__ == "__main__":
