@@ -27,7 +27,7 @@ EXPORTS = [
     "rt_find_nearest", "rt_is_occluded", "rt_find_nearest_device", "rt_is_occluded_device",
     "rt_camera_default", "rt_camera_look_at", "rt_render_params_default",
     "rt_renderer_create", "rt_renderer_destroy", "rt_renderer_set_stream", "rt_renderer_set_accumulator",
-    "rt_renderer_set_camera", "rt_renderer_clear", "rt_renderer_render", "rt_renderer_sync",
+    "rt_renderer_set_camera", "rt_renderer_set_passes", "rt_renderer_clear", "rt_renderer_render", "rt_renderer_sync",
     "rt_renderer_read_accumulator", "rt_renderer_read_pixels", "rt_renderer_device_accumulator",
     "rt_renderer_get_counters", "rt_renderer_reset_counters",
     "rt_renderer_set_profiling", "rt_renderer_get_stage_times", "rt_renderer_get_launch_spans",
@@ -74,6 +74,7 @@ def lib():
     L.rt_renderer_set_stream.argtypes = [vp, vp]
     L.rt_renderer_set_accumulator.argtypes = [vp, vp]
     L.rt_renderer_set_camera.argtypes = [vp, C.POINTER(abi.rt_camera)]
+    L.rt_renderer_set_passes.argtypes = [vp, i32]
     L.rt_renderer_clear.argtypes = [vp]
     L.rt_renderer_render.argtypes = [vp, i32, i32, i32]
     L.rt_renderer_sync.argtypes = [vp]
@@ -280,16 +281,20 @@ class GpuRenderer:
         _check(lib().rt_renderer_set_accumulator(self.handle, device_ptr))
 
     def Tick(self, deltaTime=0.0):
-        """One frame.  Path tracer: one sample per pixel with the current `spp`, then spp += passes
+        """One frame.  Path tracer: `passes` samples per pixel with the current `spp`, then spp += passes
         (renderer.cpp:144-168).  Whitted: overwrites the accumulator (renderer.cpp:131-157)."""
         self.render(1)
 
-    def render(self, frames, first_spp=None, stride=1):
-        """`frames` Ticks in one call (frames run concurrently on the GPU; result = running them in order)."""
+    def render(self, frames, first_spp=None, stride=None):
+        """`frames` Ticks in one call (frames run concurrently on the GPU; result = running them in order).
+        Every Tick takes `passes` samples per pixel and advances spp by `passes` (renderer.cpp:123,167), so the
+        default stride between the frames' spp counters is `passes`."""
         self._need()
         _check(lib().rt_renderer_set_camera(self.handle, C.byref(self.camera.c)))
+        if self.integrator == abi.RT_INTEGRATOR_PATH:
+            _check(lib().rt_renderer_set_passes(self.handle, int(self.passes)))
         first = self.spp if first_spp is None else first_spp
-        _check(lib().rt_renderer_render(self.handle, first, frames, stride))
+        _check(lib().rt_renderer_render(self.handle, first, frames, self.passes if stride is None else stride))
         if self.integrator == abi.RT_INTEGRATOR_PATH and first_spp is None:
             self.spp += frames * self.passes
 

@@ -34,7 +34,7 @@ struct PTState {
     float4* hit;       // t, u, v, int objIdx
     int* hitTri;
     uint32_t* seed;
-    int* pix;          // next pixel of the tile this slot will generate (0..256)
+    int* pix;          // next SAMPLE of the tile this slot will generate (0..256 * passes); its pixel = sample / passes
     float4* weights;   // [depth_limit][slots]: throughput factor of every bounce (see k_pt_shade)
     int* active[2];
     int* count;        // [2]
@@ -46,6 +46,7 @@ struct PTState {
     int slots, nTiles, tilesX, tileBegin;
     int firstSpp, stride;
     int W, H, depthLimit, seedMode;
+    int passes;        // Renderer::passes: samples per pixel per frame, consecutive in the tile's stream (renderer.cpp:123)
     float eps;
 };
 
@@ -290,7 +291,8 @@ __global__ void __launch_bounds__(128) k_pt_shade(const PTState p, const DScene 
                     const float4 wd = p.weights[(size_t)d * p.slots + slot];
                     L = f3(wd.x, wd.y, wd.z) * L;
                 }
-                int pix = p.pix[slot]; // index of the NEXT pixel; the finished one is pix - 1
+                const int smp = p.pix[slot]; // index of the NEXT sample; the finished one is smp - 1
+                const int pix = (smp - 1) / p.passes + 1; // pixel after the finished sample's pixel
                 {
                     const int tile = p.tileBegin + slot % p.nTiles;
                     const int tx = tile % p.tilesX, ty = tile / p.tilesX;
@@ -298,13 +300,13 @@ __global__ void __launch_bounds__(128) k_pt_shade(const PTState p, const DScene 
                     float* a = (float*)(p.accum + (x + (size_t)y * p.W)); // renderer.cpp:124: accumulator += float4(sample, 0)
                     atomicAdd(a + 0, L.x), atomicAdd(a + 1, L.y), atomicAdd(a + 2, L.z);
                 }
-                if (pix < 256)
+                if (smp < 256 * p.passes)
                 {
                     float3 gD;
-                    pt_generate(p, cam, slot, pix, seed, gD);
+                    pt_generate(p, cam, slot, smp / p.passes, seed, gD);
                     p.rayO[slot] = make_float4(cam.pos.x, cam.pos.y, cam.pos.z, 0);
                     p.rayD[slot] = make_float4(gD.x, gD.y, gD.z, __int_as_float(0));
-                    p.pix[slot] = pix + 1;
+                    p.pix[slot] = smp + 1;
                 }
                 else alive = false;
             }
@@ -545,13 +547,15 @@ __global__ void __launch_bounds__(128) k_pt_streams2(const PTState p, const DSce
                 {
                     for (int d = depth - 1; d >= 0; d--) L = wst[d] * L;
                     const int tx = tile % p.tilesX, ty = tile / p.tilesX;
-                    const int x = tx * 16 + (pix & 15), y = ty * 16 + (pix >> 4);
+                    const int px = pix / p.passes; // pix counts samples: `passes` consecutive ones per pixel
+                    const int x = tx * 16 + (px & 15), y = ty * 16 + (px >> 4);
                     float* a = (float*)(p.accum + (x + (size_t)y * p.W));
                     atomicAdd(a + 0, L.x), atomicAdd(a + 1, L.y), atomicAdd(a + 2, L.z);
                     pix++;
-                    if (pix < 256)
+                    if (pix < 256 * p.passes)
                     {
-                        const int nx = tx * 16 + (pix & 15), ny = ty * 16 + (pix >> 4);
+                        const int npx = pix / p.passes;
+                        const int nx = tx * 16 + (npx & 15), ny = ty * 16 + (npx >> 4);
                         const float jy = random_float(seed), jx = random_float(seed);
                         wD = primary_dir(cam, (float)nx + jx, (float)ny + jy);
                         wO = cam.pos, depth = 0, inside = false;
@@ -658,13 +662,15 @@ __global__ void __launch_bounds__(128) k_pt_streams_alt(const PTState p, const D
             {
                 for (int d = depth - 1; d >= 0; d--) L = wst[d] * L;
                 const int tx = tile % p.tilesX, ty = tile / p.tilesX;
-                const int x = tx * 16 + (pix & 15), y = ty * 16 + (pix >> 4);
+                const int px = pix / p.passes; // pix counts samples: `passes` consecutive ones per pixel
+                const int x = tx * 16 + (px & 15), y = ty * 16 + (px >> 4);
                 float* a = (float*)(p.accum + (x + (size_t)y * p.W));
                 atomicAdd(a + 0, L.x), atomicAdd(a + 1, L.y), atomicAdd(a + 2, L.z);
                 pix++;
-                if (pix < 256)
+                if (pix < 256 * p.passes)
                 {
-                    const int nx = tx * 16 + (pix & 15), ny = ty * 16 + (pix >> 4);
+                    const int npx = pix / p.passes;
+                    const int nx = tx * 16 + (npx & 15), ny = ty * 16 + (npx >> 4);
                     const float jy = random_float(seed), jx = random_float(seed);
                     wD = primary_dir(cam, (float)nx + jx, (float)ny + jy);
                     wO = cam.pos, depth = 0, inside = false;
@@ -776,7 +782,7 @@ __global__ void __launch_bounds__(128, MINB) k_pt_streams5(const PTState p, cons
                 seed = pt_seed(p, tile, p.firstSpp + frame * p.stride);
                 const int tx = tile % p.tilesX, ty = tile / p.tilesX;
                 tileXY = (tx * 16) | ((ty * 16) << 16);
-                pix = frame << 9, depth = 0, inside = false; // pix = pixel of the tile (9 bits) | frame of the launch << 9
+                pix = frame << 12, depth = 0, inside = false; // pix = sample of the tile (12 bits: 256 x passes <= 2048) | frame of the launch << 12
                 const float jy = random_float(seed), jx = random_float(seed);
                 wD = primary_dir(cam, (float)(tx * 16) + jx, (float)(ty * 16) + jy);
                 wO = cam.pos;
@@ -894,18 +900,18 @@ __global__ void __launch_bounds__(128, MINB) k_pt_streams5(const PTState p, cons
                 {
                     for (int d = depth - 1; d >= 0; d--) L = wst[d] * L;
                     const int x0 = tileXY & 0xffff, y0 = tileXY >> 16;
-                    const int px = pix & 511;
+                    const int px = (pix & 4095) / p.passes; // `passes` consecutive samples per pixel (renderer.cpp:123)
                     const size_t pixel = (x0 + (px & 15)) + (size_t)(y0 + (px >> 4)) * p.W;
-                    if (p.frameBuf) p.frameBuf[(size_t)(pix >> 9) * ((size_t)p.W * p.H) + pixel] = make_float4(L.x, L.y, L.z, 0); // the frame's own image
+                    if (p.frameBuf) p.frameBuf[(size_t)(pix >> 12) * ((size_t)p.W * p.H) + pixel] = make_float4(L.x, L.y, L.z, 0); // the frame's own image
                     else
                     {
                         float* a = (float*)(p.accum + pixel); // renderer.cpp:124
                         atomicAdd(a + 0, L.x), atomicAdd(a + 1, L.y), atomicAdd(a + 2, L.z);
                     }
                     pix++;
-                    if ((pix & 511) < 256)
+                    if ((pix & 4095) < 256 * p.passes)
                     {
-                        const int nx = pix & 511;
+                        const int nx = (pix & 4095) / p.passes;
                         const float jy = random_float(seed), jx = random_float(seed);
                         wD = primary_dir(cam, (float)(x0 + (nx & 15)) + jx, (float)(y0 + (nx >> 4)) + jy);
                         wO = cam.pos, depth = 0, inside = false;
@@ -1261,6 +1267,7 @@ struct rt_renderer {
     int ptIterations = 0;
     bool persistent = true;
     bool useStreams = true;
+    int passes = 1;   // Renderer::passes (3. PathTracer/renderer.h:50), changeable between frames like the UI slider does
     int streamCtasPerSm = 8;
     int streamKernel = 5; // 5 = current; 2 = the previous version, kept for A/B profiling (RT_B200_STREAM_KERNEL)
     bool streamMeasuredLpt = true;
@@ -1391,6 +1398,8 @@ rt_status rt_renderer_create(rt_scene* scene, const rt_render_params* params, rt
     RT_CUDA(cudaSetDevice(scene->device));
     rt_renderer* r = new rt_renderer();
     r->scene = scene, r->params = *params;
+    r->passes = params->passes > 0 ? params->passes : 1;
+    if (r->passes > 8) { set_error("rt_renderer_create: passes > 8 (the reference's slider stops at 4)"); delete r; return RT_ERR_UNSUPPORTED; }
     cudaDeviceGetAttribute(&r->sms, cudaDevAttrMultiProcessorCount, scene->device);
     rt_camera cam;
     rt_camera_default(&cam, params->width, params->height);
@@ -1480,6 +1489,16 @@ rt_status rt_renderer_set_stream(rt_renderer* r, void* stream)
     return RT_OK;
 }
 
+// Renderer::passes (the UI's "spp" slider, 3. PathTracer/renderer.cpp:182): samples per pixel per Tick
+rt_status rt_renderer_set_passes(rt_renderer* r, int passes)
+{
+    if (!r || passes < 1) { set_error("rt_renderer_set_passes: bad argument"); return RT_ERR_INVALID; }
+    if (passes > 8) { set_error("rt_renderer_set_passes: passes > 8 (the reference's slider stops at 4)"); return RT_ERR_UNSUPPORTED; }
+    if (passes != r->passes) r->aheadValid = false; // frames rendered ahead were rendered with the old value
+    r->passes = passes;
+    return RT_OK;
+}
+
 rt_status rt_renderer_set_accumulator(rt_renderer* r, void* d_accumulator)
 {
     if (!r) return RT_ERR_INVALID;
@@ -1521,7 +1540,7 @@ static rt_status pt_ensure_slots(rt_renderer* r, int slots)
     if ((st = ralloc(r, &p.weights, S * 16 * levels)) != RT_OK) return st;
     if ((st = ralloc(r, &p.active[0], S * 4)) != RT_OK) return st;
     if ((st = ralloc(r, &p.active[1], S * 4)) != RT_OK) return st;
-    if (!p.history && (st = ralloc(r, &p.history, (size_t)(256 * 65 + 2) * 4)) != RT_OK) return st;
+    if (!p.history && (st = ralloc(r, &p.history, (size_t)(256 * 8 * 65 + 2) * 4)) != RT_OK) return st;
     r->ptSlotsAllocated = slots;
     return RT_OK;
 }
@@ -1590,7 +1609,7 @@ static rt_status render_pt_streams(rt_renderer* r, int first_spp, int count, int
     PTState p = {};
     p.counters = r->dCounters, p.accum = r->accum, p.frameBuf = frameBuf;
     p.nTiles = nTiles, p.tilesX = P.width / 16, p.tileBegin = P.tile_begin;
-    p.W = P.width, p.H = P.height, p.depthLimit = P.depth_limit, p.seedMode = P.seed_mode, p.eps = P.epsilon;
+    p.W = P.width, p.H = P.height, p.depthLimit = P.depth_limit, p.seedMode = P.seed_mode, p.eps = P.epsilon, p.passes = r->passes;
     p.stride = stride, p.firstSpp = first_spp;
     // all frames of the call form one pool of nTiles x count streams (int range checked by the caller)
     p.slots = nTiles * count;
@@ -1622,7 +1641,7 @@ static rt_status render_pt_streams(rt_renderer* r, int first_spp, int count, int
     else if (r->scene->d.kind == RT_SCENE_TLAS) k_pt_streams2<true><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
     else k_pt_streams2<false><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
     r->prof_end(RT_STAGE_EXTEND);
-    r->paths += (uint64_t)p.slots * 256;
+    r->paths += (uint64_t)p.slots * 256 * r->passes;
     RT_CUDA(cudaGetLastError());
     return RT_OK;
 }
@@ -1636,7 +1655,9 @@ static rt_status render_pt(rt_renderer* r, int first_spp, int count, int stride)
         && (long long)nTiles * count < (1ll << 30))
     {
         const int L = P.lookahead_frames;
-        if (count == 1 && L > 1 && r->streamKernel == 5 && (long long)nTiles * L < (1ll << 30))
+        // (with passes > 1 a frame image would hold the SUM of a pixel's samples, which the accumulator then receives in
+        // one add instead of `passes` adds: not the Tick sequence bit for bit, so look-ahead serves passes == 1 only)
+        if (count == 1 && L > 1 && r->streamKernel == 5 && r->passes == 1 && (long long)nTiles * L < (1ll << 30))
         {
             // one Tick per call: serve the frame from the images rendered ahead, rendering L more when it is not there
             const size_t px = (size_t)P.width * P.height;
@@ -1672,12 +1693,12 @@ static rt_status render_pt(rt_renderer* r, int first_spp, int count, int stride)
     PTState& p = r->pt;
     p.count = r->dCount, p.counters = r->dCounters, p.accum = r->accum;
     p.nTiles = nTiles, p.tilesX = P.width / 16, p.tileBegin = P.tile_begin;
-    p.W = P.width, p.H = P.height, p.depthLimit = P.depth_limit, p.seedMode = P.seed_mode, p.eps = P.epsilon;
+    p.W = P.width, p.H = P.height, p.depthLimit = P.depth_limit, p.seedMode = P.seed_mode, p.eps = P.epsilon, p.passes = r->passes;
     p.stride = stride;
     const int grid = r->sms * 8;
     const int kind = r->scene->d.kind;
     // every path makes at most depth_limit + 1 FindNearest queries, every slot 256 paths
-    const int maxIters = 256 * (P.depth_limit + 1) + 1;
+    const int maxIters = 256 * r->passes * (P.depth_limit + 1) + 1;
     for (int done = 0; done < count; done += inFlight)
     {
         const int frames = count - done < inFlight ? count - done : inFlight;
@@ -1709,7 +1730,7 @@ static rt_status render_pt(rt_renderer* r, int first_spp, int count, int stride)
                 if (r->hCount[0] == 0) break;
             }
         }
-        r->paths += (uint64_t)p.slots * 256;
+        r->paths += (uint64_t)p.slots * 256 * r->passes;
     }
     RT_CUDA(cudaGetLastError());
     return RT_OK;

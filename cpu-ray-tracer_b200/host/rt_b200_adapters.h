@@ -325,14 +325,14 @@ public:
 			FREE64( accumulator );
 			Init();
 		}
-		if (INTEGRATOR == RT_INTEGRATOR_PATH && passes != 1)
-			throw std::runtime_error( "GpuRenderer: passes != 1 is not supported (one sample per pixel per Tick)" );
+		// the UI's "spp" slider changes `passes` between frames (renderer.cpp:182): samples per pixel per Tick
+		if (INTEGRATOR == RT_INTEGRATOR_PATH) check( rt_renderer_set_passes( dev, passes ), "rt_renderer_set_passes" );
 		if (animating) scene.SetTime( anim_time += deltaTime * 0.002f ), ClearAccumulator();
 		rt_camera c;
 		Store( c.pos, camera.camPos ), Store( c.top_left, camera.topLeft );
 		Store( c.top_right, camera.topRight ), Store( c.bottom_left, camera.bottomLeft );
 		check( rt_renderer_set_camera( dev, &c ), "rt_renderer_set_camera" );
-		check( rt_renderer_render( dev, spp, 1, 1 ), "rt_renderer_render" );
+		check( rt_renderer_render( dev, spp, 1, passes ), "rt_renderer_render" );
 		check( rt_renderer_read_accumulator( dev, (float*)accumulator ), "rt_renderer_read_accumulator" );
 		const float scale = INTEGRATOR == RT_INTEGRATOR_PATH ? 1.0f / (spp + passes) : 1.0f; // renderer.cpp:119
 		if (screen) check( rt_renderer_read_pixels( dev, scale, (uint32_t*)screen->pixels ), "rt_renderer_read_pixels" );
@@ -350,7 +350,8 @@ public:
 		Store( c.pos, camera.camPos ), Store( c.top_left, camera.topLeft );
 		Store( c.top_right, camera.topRight ), Store( c.bottom_left, camera.bottomLeft );
 		check( rt_renderer_set_camera( dev, &c ), "rt_renderer_set_camera" );
-		check( rt_renderer_render( dev, spp, frames, 1 ), "rt_renderer_render" );
+		if (INTEGRATOR == RT_INTEGRATOR_PATH) check( rt_renderer_set_passes( dev, passes ), "rt_renderer_set_passes" );
+		check( rt_renderer_render( dev, spp, frames, passes ), "rt_renderer_render" );
 		check( rt_renderer_read_accumulator( dev, (float*)accumulator ), "rt_renderer_read_accumulator" );
 		if (INTEGRATOR == RT_INTEGRATOR_PATH) spp += frames * passes;
 	}

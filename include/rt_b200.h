@@ -250,6 +250,10 @@ typedef struct rt_render_params {
      * of the ~25 ms a single 256-pixel RNG chain per tile takes on its own.  A camera change discards the
      * frames not yet shown.  0 / 1 = off.  Counters include the rays of frames rendered ahead. */
     int32_t lookahead_frames;
+    /* Renderer::passes (3. PathTracer/renderer.h:50, the UI's "spp" slider 1..4): samples per pixel per Tick, drawn
+     * consecutively from the tile's stream (renderer.cpp:123-126); a Tick then advances spp by `passes`, so the frames of
+     * a fresh renderer are first_spp = 1, stride = passes.  0 = 1.  ABI v3. */
+    int32_t passes;
 } rt_render_params;
 
 enum {
@@ -280,6 +284,8 @@ rt_status rt_renderer_set_stream(rt_renderer* r, void* stream);
  * later reduced with NCCL) instead of the renderer's own. */
 rt_status rt_renderer_set_accumulator(rt_renderer* r, void* d_accumulator);
 rt_status rt_renderer_set_camera(rt_renderer* r, const rt_camera* cam);
+/* Public member Renderer::passes; takes effect with the next rt_renderer_render.  1 <= passes <= 8. */
+rt_status rt_renderer_set_passes(rt_renderer* r, int passes);
 /* Renderer::ClearAccumulator (3. PathTracer/renderer.cpp:15-18). */
 rt_status rt_renderer_clear(rt_renderer* r);
 /* `count` calls of Renderer::Tick (one frame each), for the frames whose reference `spp` counter

@@ -60,6 +60,8 @@ def main(integrator, kind, xml, W, H, frames):
             L.ref_reset(1)
             if L.gh_reset(1) != 0:
                 raise SystemExit(L.gh_last_error().decode())
+            if integrator == "pt":  # second camera: two samples per pixel per Tick (the UI's "spp" slider, renderer.cpp:182)
+                L.ref_set_passes(2), L.gh_set_passes(2)
         tag = "cam0" if cam is None else "cam1"
         # Renderer::Tick x frames on both sides
         L.ref_tick(frames)

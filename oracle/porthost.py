@@ -110,9 +110,10 @@ class PortOracle:
         return out
 
 
-def default_params(integrator, w, h, seed_mode=abi.RT_SEED_REFERENCE_TILE, depth_limit=5):
+def default_params(integrator, w, h, seed_mode=abi.RT_SEED_REFERENCE_TILE, depth_limit=5, passes=1):
     p = abi.rt_render_params()
     p.integrator, p.width, p.height = integrator, w, h
     p.depth_limit, p.epsilon, p.seed_mode = depth_limit, 0.001, seed_mode
     p.tile_begin, p.tile_end, p.max_frames_in_flight, p.schedule = 0, 0, 0, 0
+    p.passes = passes
     return p

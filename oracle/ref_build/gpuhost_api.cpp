@@ -63,6 +63,7 @@ const float* gh_accumulator() { return (const float*)g_gh->accumulator; }
 const unsigned int* gh_screen() { return g_gh->screen->pixels; }
 int gh_spp() { return g_gh->spp; }
 void gh_set_depth_limit( int d ) { g_gh->depthLimit = d; }
+void gh_set_passes( int p ) { g_gh->passes = p; }
 int gh_triangle_count() { return g_gh->scene.GetTriangleCount(); }
 
 int gh_reset( int spp )

@@ -151,6 +151,7 @@ def _main(argv):
             cam = [float(x) for x in argv[8:14]]
             r.set_camera(cam[:3], cam[3:])
         prim = r.primary_hits()
+        r.set_passes(int(os.environ.get("RT_REF_PASSES", "1")))  # Renderer::passes (path tracer only)
         secs = r.tick(frames)
         np.savez_compressed(out, accumulator=r.accumulator(), camera=r.get_camera(), seconds=secs,
                             threads=r.threads(), **{"prim_" + k: v for k, v in prim.items()})

@@ -209,6 +209,32 @@ def test_path_tracer_vs_oracle_reference_rng(name, schedule, oracles, gpu_scenes
     r.close()
 
 
+@pytest.mark.parametrize("schedule", [abi.RT_SCHEDULE_STREAMS, abi.RT_SCHEDULE_WAVEFRONT], ids=["streams", "wavefront"])
+@pytest.mark.parametrize("name", ["golden_file", "golden_tlas", "golden_kd", "golden_grid"])
+def test_path_tracer_passes(name, schedule, oracles, gpu_scenes):
+    """Renderer::passes > 1: consecutive samples per pixel from the tile's stream, spp advancing by `passes` per Tick"""
+    from cpu_ray_tracer_b200 import api
+    from oracle import porthost
+    po, sc = oracles(name), gpu_scenes(name, counters=False)
+    W, H, frames, passes = 192, 112, 2, 3
+    cam = po.camera_default(W, H)
+    oacc, ost = po.render_pt(cam, porthost.default_params(abi.RT_INTEGRATOR_PATH, W, H, passes=passes), 1, frames, passes)
+    r = api.GpuRenderer(sc, abi.RT_INTEGRATOR_PATH, W, H, schedule=schedule, lookahead_frames=8).Init()
+    r.passes = passes
+    for _ in range(frames):
+        r.Tick(0)
+    assert r.spp == 1 + frames * passes
+    c = r.counters()
+    assert c["extension_rays"] == ost["extension_rays"] and c["paths"] == ost["paths"] == W * H * frames * passes
+    check_pt(r.accumulator, oacc, frames * passes, name)
+    # the slider moves back to 1 between frames: the next Tick continues at the current spp with one sample per pixel
+    r.passes = 1
+    r.Tick(0)
+    oacc, _ = po.render_pt(cam, porthost.default_params(abi.RT_INTEGRATOR_PATH, W, H), 1 + frames * passes, 1, 1, accumulator=oacc)
+    check_pt(r.accumulator, oacc, frames * passes + 1, name + " (passes back to 1)")
+    r.close()
+
+
 @pytest.mark.parametrize("kind", ["file", "tlas", "kd", "grid"])
 def test_integrators_vs_committed_golden(kind, oracles, gpu_scenes):
     """the vectors the reference's own build produced (tests/golden/make_golden.py), second camera too"""

@@ -126,3 +126,23 @@ def test_oracle_vs_live_reference(integ, kind, xml, baked, tmp_path):
     else:
         acc, _ = po.render_whitted(cam, porthost.default_params(abi.RT_INTEGRATOR_WHITTED, W, H))
     assert biteq(acc, ref["accumulator"])
+
+
+def test_oracle_passes_vs_live_reference(tmp_path):
+    """Renderer::passes = 2 (two consecutive samples per pixel from the tile's stream, spp advancing by 2 per Tick)"""
+    if not _ref_available():
+        pytest.skip("oracle/_ref not built here (needs /root/reference)")
+    import subprocess
+    import sys
+    import cpu_ray_tracer_b200 as rtb
+    from oracle import porthost
+    from conftest import ROOT, scene_path
+    W, H, frames = 160, 96, 2
+    out = tmp_path / "ref.npz"
+    subprocess.run([sys.executable, "-m", "oracle.refhost", "dump", "pt", "file", "wok_teapot_scene.xml", str(W), str(H), str(out), str(frames)],
+                   check=True, cwd=ROOT, env=dict(os.environ, RT_REF_PASSES="2"))
+    ref = np.load(out)
+    po = porthost.PortOracle(rtb.FlatScene.load(scene_path("wok_teapot_flat")))
+    acc, st = po.render_pt(po.camera_default(W, H), porthost.default_params(abi.RT_INTEGRATOR_PATH, W, H, passes=2), 1, frames, 2)
+    assert st["paths"] == W * (H // 16 * 16) * frames * 2
+    assert biteq(acc, ref["accumulator"])
