@@ -515,30 +515,36 @@ __device__ __forceinline__ bool slab_range(float3 O, float3 rD, float rayT, bool
 
 __device__ __forceinline__ float axis_of(float3 a, int axis) { return axis == 0 ? a.x : (axis == 1 ? a.y : a.z); }
 
-// One leaf / cell: `count` consecutive triangle records starting at `slot` (kdtree.cpp:155-161, grid.cpp:124-137).
-template <bool ANYHIT, bool COUNTERS>
-__device__ __forceinline__ bool test_run(const float4* __restrict__ tris, int slot, int count, float3 O, float3 D, HitRec& hit)
+// Cursor protocol shared by the KD-tree and the grid.  A traversal alternates between ADVANCING through the structure
+// (one node / one cell per step) and testing a RUN of consecutive triangle records (a leaf / a cell); the two are
+// separate steps so that a warp can vote them as separate actions: ncu on a first version that tested the run inside
+// the node step showed the triangle code at 2 of 32 lanes and 70 % of all instructions
+// (profiles/r1_k_pt_streams_alt_*_source_hotspots.txt).
+//   start()      position on the root / the entry cell; true = the ray is finished (misses the structure)
+//   step()       CUR_CONTINUE another step() is due, CUR_RUN a run (runSlot, runCount > 0) is pending, CUR_DONE finished
+//   tri_step()   test ONE triangle of the pending run (kdtree.cpp:155-161, grid.cpp:124-137); same return codes, CUR_RUN
+//                while triangles remain; after the last one the cursor continues the way the reference does after its
+//                leaf loop (KD-tree: return to the parent's pending far child; grid: advance to the next cell)
+enum { CUR_CONTINUE = 0, CUR_DONE = 1, CUR_RUN = 2 };
+
+template <bool COUNTERS>
+__device__ __forceinline__ bool test_one(const float4* __restrict__ tris, int slot, float3 O, float3 D, HitRec& hit)
 {
-    for (int i = 0; i < count; i++, slot++)
+    const float4* T = tris + 3 * (size_t)slot;
+    const float4 t0 = __ldg(T), t1 = __ldg(T + 1), t2 = __ldg(T + 2);
+    if (COUNTERS) hit.tested++;
+    if (intersect_tri(O, D, f3(t0.x, t0.y, t0.z), f3(t1.x, t1.y, t1.z), f3(t2.x, t2.y, t2.z), hit.t, hit.u, hit.v))
     {
-        const float4* T = tris + 3 * (size_t)slot;
-        const float4 t0 = __ldg(T), t1 = __ldg(T + 1), t2 = __ldg(T + 2);
-        if (COUNTERS) hit.tested++;
-        if (intersect_tri(O, D, f3(t0.x, t0.y, t0.z), f3(t1.x, t1.y, t1.z), f3(t2.x, t2.y, t2.z), hit.t, hit.u, hit.v))
-        {
-            hit.tri = __float_as_int(t0.w) & ~LAST_BIT;
-            hit.obj = __float_as_int(t1.w);
-            if (ANYHIT) return true;
-        }
+        hit.tri = __float_as_int(t0.w) & ~LAST_BIT;
+        hit.obj = __float_as_int(t1.w);
+        return true;
     }
     return false;
 }
 
-// The traversal as a cursor: start() positions it on the root, step() visits ONE node (box test, then either the
-// whole leaf or the child choice) and returns true when the ray is finished.  traverse_kd() just loops it; the
-// stream kernel of the path tracer (rt_render.cu) interleaves steps of 32 lanes under a warp vote.
 struct KdCursor {
     int cur, sp;
+    int runSlot, runCount;
     float3 rD;
     bool exact;
     int stackNode[KD_STACK_SIZE];
@@ -546,12 +552,25 @@ struct KdCursor {
 
     __device__ __forceinline__ bool start(const DScene&, const float3 O, const float3 D, const HitRec&)
     {
-        rD = recip(D), exact = needs_exact_slab(O, D), cur = 0, sp = 0;
+        rD = recip(D), exact = needs_exact_slab(O, D), cur = 0, sp = 0, runCount = 0;
         return false;
     }
 
-    template <bool ANYHIT, bool COUNTERS>
-    __device__ __forceinline__ bool step(const DScene& s, const float3 O, const float3 D, HitRec& hit)
+    // the recursion's unwinding: skip the pending far children the reference returns past (`if (ray.t < t) return;`, :189 / :208).
+    // (Tried: (node, t) packed into 8-byte entries plus a running minimum of the pending t so that "the hit lies before
+    // every pending plane" ends the ray without walking the stack - no faster, profiles/r1_kdtree_grid_accelerators.txt.)
+    __device__ __forceinline__ int pop(const HitRec& hit)
+    {
+        while (true)
+        {
+            if (sp == 0) return CUR_DONE;
+            sp--;
+            if (!(hit.t < stackT[sp])) { cur = stackNode[sp]; return CUR_CONTINUE; }
+        }
+    }
+
+    template <bool COUNTERS>
+    __device__ __forceinline__ int step(const DScene& s, const float3 O, const float3 D, HitRec& hit)
     {
         if (COUNTERS) hit.traversed++;
         const float4* __restrict__ nodes = s.kd_nodes;
@@ -562,7 +581,8 @@ struct KdCursor {
             const int a = __float_as_int(k1.z);
             if (a < 0)
             {
-                if (test_run<ANYHIT, COUNTERS>(s.tris, ~a, __float_as_int(k1.w), O, D, hit)) return true;
+                runSlot = ~a, runCount = __float_as_int(k1.w);
+                if (runCount > 0) return CUR_RUN;
             }
             else
             {
@@ -574,24 +594,41 @@ struct KdCursor {
                 if ((double)t < (double)tmin + 0.001) cur = farC;       // :177 / :196: only the far side is crossed
                 else if ((double)t > (double)tmax - 0.001) cur = nearC; // :182 / :201
                 else stackNode[sp] = farC, stackT[sp] = t, sp++, cur = nearC;
-                return false;
+                return CUR_CONTINUE;
             }
         }
-        while (true)
-        {
-            if (sp == 0) return true;
-            sp--;
-            if (!(hit.t < stackT[sp])) { cur = stackNode[sp]; return false; } // :189 / :208 `if (ray.t < t) return;`
-        }
+        return pop(hit);
+    }
+
+    template <bool ANYHIT, bool COUNTERS>
+    __device__ __forceinline__ int tri_step(const DScene& s, const float3 O, const float3 D, HitRec& hit)
+    {
+        const bool accepted = test_one<COUNTERS>(s.tris, runSlot, O, D, hit);
+        if (ANYHIT && accepted) return CUR_DONE;
+        runSlot++;
+        if (--runCount > 0) return CUR_RUN;
+        return pop(hit);
     }
 };
+
+// one thread per ray: the cursor driven to completion
+template <class Cursor, bool ANYHIT, bool COUNTERS>
+__device__ __forceinline__ void run_cursor(const DScene& s, const float3 O, const float3 D, HitRec& hit)
+{
+    Cursor c;
+    if (c.start(s, O, D, hit)) return;
+    while (true)
+    {
+        int r = c.template step<COUNTERS>(s, O, D, hit);
+        while (r == CUR_RUN) r = c.template tri_step<ANYHIT, COUNTERS>(s, O, D, hit);
+        if (r == CUR_DONE) return;
+    }
+}
 
 template <bool ANYHIT, bool COUNTERS>
 __device__ __forceinline__ void traverse_kd(const DScene& s, const float3 O, const float3 D, HitRec& hit)
 {
-    KdCursor c;
-    if (c.start(s, O, D, hit)) return;
-    while (!c.template step<ANYHIT, COUNTERS>(s, O, D, hit)) {}
+    run_cursor<KdCursor, ANYHIT, COUNTERS>(s, O, D, hit);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -606,16 +643,18 @@ __device__ __forceinline__ int cvtt_x86(float x)
     return (x >= 2147483648.0f || x < -2147483648.0f || x != x) ? (int)0x80000000u : (int)x;
 }
 
-// Cursor form, as for the KD-tree: start() runs the bounds test and the DDA set-up (grid.cpp:96-120, true = the
-// ray misses the grid), step() visits ONE cell and advances (grid.cpp:122-152).
+// Cursor (protocol above): start() runs the bounds test and the DDA set-up (grid.cpp:96-120), step() fetches the
+// current cell's run, tri_step() tests one triangle and, after the last one, advances the DDA (grid.cpp:139-152).
 struct GridCursor {
     int cell[3], stp[3], exitc[3];
+    int runSlot, runCount;
     float deltaT[3], nextT[3];
 
     __device__ __forceinline__ bool start(const DScene& s, const float3 O, const float3 D, const HitRec& hit)
     {
         const float3 rD = recip(D);
         float tminU, tmaxU;
+        runCount = 0;
         if (!slab_range(O, rD, hit.t, needs_exact_slab(O, D), s.grid_min[0], s.grid_min[1], s.grid_min[2],
                         s.grid_max[0], s.grid_max[1], s.grid_max[2], tminU, tmaxU)) return true;
 #pragma unroll
@@ -639,37 +678,52 @@ struct GridCursor {
         return false;
     }
 
-    template <bool ANYHIT, bool COUNTERS>
-    __device__ __forceinline__ bool step(const DScene& s, const float3 O, const float3 D, HitRec& hit)
+    // grid.cpp:139-152: pick the axis of the nearest cell boundary, stop when the hit lies before it or the grid ends
+    __device__ __forceinline__ int advance(const HitRec& hit)
     {
-        if (COUNTERS) hit.traversed++;
-        const int2 c = __ldg(s.grid_cells + (unsigned)(cell[0] + cell[1] * s.grid_res[0] + cell[2] * s.grid_res[0] * s.grid_res[1]));
-        if (test_run<ANYHIT, COUNTERS>(s.tris, c.x, c.y, O, D, hit)) return true;
-        // grid.cpp:139-144: k = (x<y)<<2 | (x<z)<<1 | (y<z), map = {2,1,2,1,2,2,0,0}
+        // k = (x<y)<<2 | (x<z)<<1 | (y<z), map = {2,1,2,1,2,2,0,0}
         const bool xy = nextT[0] < nextT[1], xz = nextT[0] < nextT[2], yz = nextT[1] < nextT[2];
         const int axis = xy ? (xz ? 0 : 2) : (yz ? 1 : 2);
         // unrolled selects keep cell / nextT in registers (no dynamically indexed local arrays)
         const float nt = axis == 0 ? nextT[0] : (axis == 1 ? nextT[1] : nextT[2]);
-        if (hit.t < nt) return true;
+        if (hit.t < nt) return CUR_DONE;
 #pragma unroll
         for (int i = 0; i < 3; i++)
             if (axis == i) cell[i] += stp[i];
         const int ca = axis == 0 ? cell[0] : (axis == 1 ? cell[1] : cell[2]);
         const int ea = axis == 0 ? exitc[0] : (axis == 1 ? exitc[1] : exitc[2]);
-        if (ca == ea) return true;
+        if (ca == ea) return CUR_DONE;
 #pragma unroll
         for (int i = 0; i < 3; i++)
             if (axis == i) nextT[i] += deltaT[i];
-        return false;
+        return CUR_CONTINUE;
+    }
+
+    template <bool COUNTERS>
+    __device__ __forceinline__ int step(const DScene& s, const float3 O, const float3 D, HitRec& hit)
+    {
+        if (COUNTERS) hit.traversed++;
+        const int2 c = __ldg(s.grid_cells + (unsigned)(cell[0] + cell[1] * s.grid_res[0] + cell[2] * s.grid_res[0] * s.grid_res[1]));
+        runSlot = c.x, runCount = c.y;
+        if (runCount > 0) return CUR_RUN;
+        return advance(hit);
+    }
+
+    template <bool ANYHIT, bool COUNTERS>
+    __device__ __forceinline__ int tri_step(const DScene& s, const float3 O, const float3 D, HitRec& hit)
+    {
+        const bool accepted = test_one<COUNTERS>(s.tris, runSlot, O, D, hit);
+        if (ANYHIT && accepted) return CUR_DONE;
+        runSlot++;
+        if (--runCount > 0) return CUR_RUN;
+        return advance(hit);
     }
 };
 
 template <bool ANYHIT, bool COUNTERS>
 __device__ __forceinline__ void traverse_grid(const DScene& s, const float3 O, const float3 D, HitRec& hit)
 {
-    GridCursor c;
-    if (c.start(s, O, D, hit)) return;
-    while (!c.template step<ANYHIT, COUNTERS>(s, O, D, hit)) {}
+    run_cursor<GridCursor, ANYHIT, COUNTERS>(s, O, D, hit);
 }
 
 template <int ACCEL, bool ANYHIT, bool COUNTERS>
@@ -678,6 +732,104 @@ __device__ __forceinline__ void accel_traverse(const DScene& s, const float3 O, 
     if (ACCEL == ACCEL_KD) traverse_kd<ANYHIT, COUNTERS>(s, O, D, hit);
     else if (ACCEL == ACCEL_GRID) traverse_grid<ANYHIT, COUNTERS>(s, O, D, hit);
     else traverse<ANYHIT, COUNTERS>(s, O, D, hit);
+}
+
+// Persistent-warp traversal with ray replacement for the cursor accelerators: the KD-tree / grid counterpart of
+// trace_queue<> above (same Src interface, same refill rule).  Lanes are IDLE, advancing (TRAV) or inside a triangle
+// run (TRI); the warp executes the action most lanes wait for and repeats it while >= 3/4 of them stay in that state.
+template <class Cursor, bool ANYHIT, bool COUNTERS, class Src>
+__device__ __forceinline__ void trace_queue_cursor(const DScene& s, Src& src, const int n, int* __restrict__ fetchCounter)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    enum { Q_IDLE = 0, Q_TRAV = 1, Q_TRI = 2 };
+    int state = Q_IDLE, rayIdx = -1;
+    bool queueEmpty = false;
+    float3 O = f3(0, 0, 0), D = f3(0, 0, 0);
+    Cursor cursor;
+    HitRec hit;
+    hit.t = 0, hit.u = 0, hit.v = 0, hit.obj = -1, hit.tri = -1, hit.traversed = 0, hit.tested = 0;
+    while (true)
+    {
+        const unsigned idle = __ballot_sync(FULL, state == Q_IDLE);
+        if (idle == FULL && queueEmpty) break;
+        if (!queueEmpty && (idle == FULL || __popc(idle) >= REFILL_LANES))
+        {
+            const int nIdle = __popc(idle);
+            const int leader = __ffs(idle) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(fetchCounter, nIdle);
+            base = __shfl_sync(FULL, base, leader);
+            if (base + nIdle >= n) queueEmpty = true;
+            if (state == Q_IDLE)
+            {
+                const int i = base + __popc(idle & ((1u << lane) - 1));
+                float tmax;
+                if (i < n && src.load(i, O, D, tmax))
+                {
+                    rayIdx = i;
+                    // FindNearest prologue: light quad, floor plane (file_scene.cpp:172-173); IsOccluded: quad only
+                    hit.t = tmax, hit.u = 0, hit.v = 0, hit.obj = -1, hit.tri = -1, hit.traversed = 0, hit.tested = 0;
+                    float tq;
+                    bool done = false;
+                    if (ANYHIT)
+                    {
+                        if (quad_test(s, O, D, tmax, tq)) hit.obj = 0, done = true;
+                        hit.t = 1e34f;
+                    }
+                    else
+                    {
+                        if (quad_test(s, O, D, hit.t, tq)) hit.t = tq, hit.obj = 0;
+                        const float3 N = f3(s.floor_n[0], s.floor_n[1], s.floor_n[2]);
+                        const float tp = -(dot(O, N) + s.floor_d) / (dot(D, N));
+                        if (tp < hit.t && tp > 0) hit.t = tp, hit.obj = 1;
+                    }
+                    if (!done) done = cursor.start(s, O, D, hit);
+                    if (done) src.store(rayIdx, hit);
+                    else state = Q_TRAV;
+                }
+            }
+            continue;
+        }
+        const int nT = __popc(__ballot_sync(FULL, state == Q_TRAV)), nR = __popc(__ballot_sync(FULL, state == Q_TRI));
+        if (nT >= nR)
+        {
+            const int keep = (nT * 3 + 3) >> 2;
+            do
+            {
+                if (state == Q_TRAV)
+                {
+                    const int r = cursor.template step<COUNTERS>(s, O, D, hit);
+                    state = r == CUR_DONE ? Q_IDLE : (r == CUR_RUN ? Q_TRI : Q_TRAV);
+                    if (r == CUR_DONE) src.store(rayIdx, hit);
+                }
+            } while (keep > 0 && __popc(__ballot_sync(FULL, state == Q_TRAV)) >= keep);
+        }
+        else
+        {
+            const int keep = (nR * 3 + 3) >> 2;
+            do
+            {
+                if (state == Q_TRI)
+                {
+                    const int r = cursor.template tri_step<ANYHIT, COUNTERS>(s, O, D, hit);
+                    state = r == CUR_DONE ? Q_IDLE : (r == CUR_RUN ? Q_TRI : Q_TRAV);
+                    if (r == CUR_DONE) src.store(rayIdx, hit);
+                }
+            } while (__popc(__ballot_sync(FULL, state == Q_TRI)) >= keep);
+        }
+    }
+}
+
+template <int ACCEL> struct CursorOf { typedef KdCursor type; };
+template <> struct CursorOf<ACCEL_GRID> { typedef GridCursor type; };
+
+// the persistent-warp queue traversal of the accelerator a kernel is compiled for
+template <int ACCEL, bool ANYHIT, bool COUNTERS, class Src>
+__device__ __forceinline__ void accel_trace_queue(const DScene& s, Src& src, const int n, int* __restrict__ fetchCounter)
+{
+    if (ACCEL == ACCEL_BVH) trace_queue<ANYHIT, COUNTERS>(s, src, n, fetchCounter);
+    else trace_queue_cursor<typename CursorOf<ACCEL>::type, ANYHIT, COUNTERS>(s, src, n, fetchCounter);
 }
 
 // BaseScene::FindNearest: file_scene.cpp:170-175 = tlas_file_scene.cpp:201-206

@@ -141,11 +141,12 @@ struct PTSrc {
     }
 };
 
+template <int ACCEL>
 __global__ void __launch_bounds__(128) k_pt_extend_persistent(const PTState p, const DScene s, int cur)
 {
     const int n = p.count[cur];
     PTSrc src = { p, p.active[cur] };
-    trace_queue<false, false>(s, src, n, p.count + 4);
+    accel_trace_queue<ACCEL, false, false>(s, src, n, p.count + 4);
     if (blockIdx.x == 0 && threadIdx.x == 0)
     {
         p.count[cur ^ 1] = 0;
@@ -573,12 +574,11 @@ __global__ void __launch_bounds__(128) k_pt_streams2(const PTState p, const DSce
 
 // Stream kernel for FileScene's other accelerators (KD-tree, uniform grid): the same schedule as version 2 - one
 // (tile, frame) RNG stream per lane, path state in registers, lanes pull the next stream when theirs ends - with
-// the traversal expressed through the accelerator's cursor (rt_device.cuh KdCursor / GridCursor: one node or one
-// cell per step).  Two live states, TRAV and SHADE: the warp runs the action most lanes wait for and keeps stepping
-// the traversal without a new vote while at least 3/4 of the lanes that entered are still traversing.
-template <int ACCEL> struct CursorOf { typedef KdCursor type; };
-template <> struct CursorOf<ACCEL_GRID> { typedef GridCursor type; };
-enum { SA_DEAD = 0, SA_TRAV = 1, SA_SHADE = 2 };
+// the traversal expressed through the accelerator's cursor (rt_device.cuh KdCursor / GridCursor).  Three live states:
+// TRAV (one node / one cell per step), TRI (one triangle of a leaf's / cell's run per step) and SHADE; the warp runs the
+// action most lanes wait for and keeps repeating a TRAV or TRI action without a new vote while at least 3/4 of the lanes
+// that entered it are still in that state.
+enum { SA_DEAD = 0, SA_TRAV = 1, SA_SHADE = 2, SA_TRI = 3 };
 
 template <int ACCEL>
 __global__ void __launch_bounds__(128) k_pt_streams_alt(const PTState p, const DScene s, const DCamera cam,
@@ -638,15 +638,33 @@ __global__ void __launch_bounds__(128) k_pt_streams_alt(const PTState p, const D
             }
         }
         const unsigned mTrav = __ballot_sync(FULL, state == SA_TRAV);
+        const unsigned mTri = __ballot_sync(FULL, state == SA_TRI);
         const unsigned mShade = __ballot_sync(FULL, state == SA_SHADE);
-        if ((mTrav | mShade) == 0) break;
-        if (__popc(mTrav) >= __popc(mShade))
+        if ((mTrav | mTri | mShade) == 0) break;
+        const int nT = __popc(mTrav), nR = __popc(mTri), nS = __popc(mShade);
+        if (nT >= nR && nT >= nS)
         {
-            const int keep = (__popc(mTrav) * 3 + 3) >> 2;
+            const int keep = (nT * 3 + 3) >> 2;
             do
             {
-                if (state == SA_TRAV && cursor.template step<false, false>(s, wO, wD, hit)) state = SA_SHADE;
+                if (state == SA_TRAV)
+                {
+                    const int r = cursor.template step<false>(s, wO, wD, hit);
+                    state = r == CUR_DONE ? SA_SHADE : (r == CUR_RUN ? SA_TRI : SA_TRAV);
+                }
             } while (__popc(__ballot_sync(FULL, state == SA_TRAV)) >= keep);
+        }
+        else if (nR >= nS)
+        {
+            const int keep = (nR * 3 + 3) >> 2;
+            do
+            {
+                if (state == SA_TRI)
+                {
+                    const int r = cursor.template tri_step<false, false>(s, wO, wD, hit);
+                    state = r == CUR_DONE ? SA_SHADE : (r == CUR_RUN ? SA_TRI : SA_TRAV);
+                }
+            } while (__popc(__ballot_sync(FULL, state == SA_TRI)) >= keep);
         }
         else if (state == SA_SHADE)
         {
@@ -1020,11 +1038,12 @@ struct WhSrc {
     }
 };
 
+template <int ACCEL>
 __global__ void __launch_bounds__(128) k_wh_extend_persistent(const WhState p, const DScene s, int cur)
 {
     const int n = min(p.count[cur], p.capacity);
     WhSrc src = { p, cur };
-    trace_queue<false, false>(s, src, n, p.count + 4);
+    accel_trace_queue<ACCEL, false, false>(s, src, n, p.count + 4);
     if (blockIdx.x == 0 && threadIdx.x == 0)
     {
         p.count[cur ^ 1] = 0, p.count[2] = 0, p.count[5] = 0;
@@ -1214,11 +1233,12 @@ struct ShadowSrc {
     }
 };
 
+template <int ACCEL>
 __global__ void __launch_bounds__(128) k_wh_connect_persistent(const WhState p, const DScene s)
 {
     const int n = min(p.count[2], p.capacity);
     ShadowSrc src = { p };
-    trace_queue<true, false>(s, src, n, p.count + 5);
+    accel_trace_queue<ACCEL, true, false>(s, src, n, p.count + 5);
     if (blockIdx.x == 0 && threadIdx.x == 0) p.counters[1] += (unsigned long long)n;
 }
 
@@ -1621,12 +1641,13 @@ static rt_status render_pt_streams(rt_renderer* r, int first_spp, int count, int
         if (st != RT_OK) return st;
         order = r->dTileOrder;
     }
+    // time the streams of this launch only while the tile order still comes from the pilot
+    // (the BVH kernel only: on the KD-tree / grid kernel the measured order was no better than the pilot's, profiles/r1_kdtree_grid_*)
+    unsigned long long* clk = (order && r->tileOrderSource == 1 && r->streamMeasuredLpt && r->streamKernel == 5) ? r->dTileClock : nullptr;
+    if (clk) RT_CUDA(cudaMemsetAsync(clk, 0, (size_t)nTiles * 8, r->stream));
     r->prof_begin();
     if (r->streamKernel == 5)
     {
-        // time the streams of this launch only while the tile order still comes from the pilot
-        unsigned long long* clk = (order && r->tileOrderSource == 1 && r->streamMeasuredLpt) ? r->dTileClock : nullptr;
-        if (clk) RT_CUDA(cudaMemsetAsync(clk, 0, (size_t)nTiles * 8, r->stream));
         // small jobs: spread the streams over all resident warps instead of filling the first warps completely
         const long long warps = (long long)r->sms * r->streamCtasPerSm * 4;
         long long perWarp = ((long long)p.slots + warps - 1) / warps;
@@ -1634,13 +1655,13 @@ static rt_status render_pt_streams(rt_renderer* r, int first_spp, int count, int
         if (perWarp > 32 || !r->streamLaneCap) perWarp = 32;
         const unsigned laneMask = perWarp >= 32 ? 0xffffffffu : ((1u << perWarp) - 1);
         streams5_kernel(r->scene->d.kind == RT_SCENE_TLAS, r->streamMinB)<<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6, clk, r->streamKeepShift, laneMask);
-        if (clk) r->tileClockRecorded = true, r->lastStreamFrames = count;
     }
     else if (r->scene->d.kind == RT_SCENE_FLAT_KDTREE) k_pt_streams_alt<ACCEL_KD><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
     else if (r->scene->d.kind == RT_SCENE_FLAT_GRID) k_pt_streams_alt<ACCEL_GRID><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
     else if (r->scene->d.kind == RT_SCENE_TLAS) k_pt_streams2<true><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
     else k_pt_streams2<false><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
     r->prof_end(RT_STAGE_EXTEND);
+    if (clk) r->tileClockRecorded = true, r->lastStreamFrames = count;
     r->paths += (uint64_t)p.slots * 256 * r->passes;
     RT_CUDA(cudaGetLastError());
     return RT_OK;
@@ -1714,9 +1735,17 @@ static rt_status render_pt(rt_renderer* r, int first_spp, int count, int stride)
             p.iteration = it;
             r->ptIterations = it + 1;
             r->prof_begin();
-            if (kind == RT_SCENE_FLAT_KDTREE) k_pt_extend<ACCEL_KD><<<grid, 128, 0, r->stream>>>(p, r->scene->d, cur);
-            else if (kind == RT_SCENE_FLAT_GRID) k_pt_extend<ACCEL_GRID><<<grid, 128, 0, r->stream>>>(p, r->scene->d, cur);
-            else if (r->persistent) k_pt_extend_persistent<<<grid, 128, 0, r->stream>>>(p, r->scene->d, cur);
+            if (kind == RT_SCENE_FLAT_KDTREE)
+            {
+                if (r->persistent) k_pt_extend_persistent<ACCEL_KD><<<grid, 128, 0, r->stream>>>(p, r->scene->d, cur);
+                else k_pt_extend<ACCEL_KD><<<grid, 128, 0, r->stream>>>(p, r->scene->d, cur);
+            }
+            else if (kind == RT_SCENE_FLAT_GRID)
+            {
+                if (r->persistent) k_pt_extend_persistent<ACCEL_GRID><<<grid, 128, 0, r->stream>>>(p, r->scene->d, cur);
+                else k_pt_extend<ACCEL_GRID><<<grid, 128, 0, r->stream>>>(p, r->scene->d, cur);
+            }
+            else if (r->persistent) k_pt_extend_persistent<ACCEL_BVH><<<grid, 128, 0, r->stream>>>(p, r->scene->d, cur);
             else k_pt_extend<ACCEL_BVH><<<grid, 128, 0, r->stream>>>(p, r->scene->d, cur);
             r->prof_end(RT_STAGE_EXTEND);
             r->prof_begin();
@@ -1753,18 +1782,34 @@ static void whitted_frame_launches(rt_renderer* r)
     for (int depth = 0; depth <= P.depth_limit; depth++)
     {
         r->prof_begin();
-        if (kind == RT_SCENE_FLAT_KDTREE) k_wh_extend<ACCEL_KD><<<grid, 128, 0, r->stream>>>(w, r->scene->d, cur);
-        else if (kind == RT_SCENE_FLAT_GRID) k_wh_extend<ACCEL_GRID><<<grid, 128, 0, r->stream>>>(w, r->scene->d, cur);
-        else if (r->persistent) k_wh_extend_persistent<<<grid, 128, 0, r->stream>>>(w, r->scene->d, cur);
+        if (kind == RT_SCENE_FLAT_KDTREE)
+        {
+            if (r->persistent) k_wh_extend_persistent<ACCEL_KD><<<grid, 128, 0, r->stream>>>(w, r->scene->d, cur);
+            else k_wh_extend<ACCEL_KD><<<grid, 128, 0, r->stream>>>(w, r->scene->d, cur);
+        }
+        else if (kind == RT_SCENE_FLAT_GRID)
+        {
+            if (r->persistent) k_wh_extend_persistent<ACCEL_GRID><<<grid, 128, 0, r->stream>>>(w, r->scene->d, cur);
+            else k_wh_extend<ACCEL_GRID><<<grid, 128, 0, r->stream>>>(w, r->scene->d, cur);
+        }
+        else if (r->persistent) k_wh_extend_persistent<ACCEL_BVH><<<grid, 128, 0, r->stream>>>(w, r->scene->d, cur);
         else k_wh_extend<ACCEL_BVH><<<grid, 128, 0, r->stream>>>(w, r->scene->d, cur);
         r->prof_end(RT_STAGE_EXTEND);
         r->prof_begin();
         k_wh_shade<<<grid, 128, 0, r->stream>>>(w, r->scene->d, cur);
         r->prof_end(RT_STAGE_SHADE);
         r->prof_begin();
-        if (kind == RT_SCENE_FLAT_KDTREE) k_wh_connect<ACCEL_KD><<<grid, 128, 0, r->stream>>>(w, r->scene->d);
-        else if (kind == RT_SCENE_FLAT_GRID) k_wh_connect<ACCEL_GRID><<<grid, 128, 0, r->stream>>>(w, r->scene->d);
-        else if (r->persistent) k_wh_connect_persistent<<<grid, 128, 0, r->stream>>>(w, r->scene->d);
+        if (kind == RT_SCENE_FLAT_KDTREE)
+        {
+            if (r->persistent) k_wh_connect_persistent<ACCEL_KD><<<grid, 128, 0, r->stream>>>(w, r->scene->d);
+            else k_wh_connect<ACCEL_KD><<<grid, 128, 0, r->stream>>>(w, r->scene->d);
+        }
+        else if (kind == RT_SCENE_FLAT_GRID)
+        {
+            if (r->persistent) k_wh_connect_persistent<ACCEL_GRID><<<grid, 128, 0, r->stream>>>(w, r->scene->d);
+            else k_wh_connect<ACCEL_GRID><<<grid, 128, 0, r->stream>>>(w, r->scene->d);
+        }
+        else if (r->persistent) k_wh_connect_persistent<ACCEL_BVH><<<grid, 128, 0, r->stream>>>(w, r->scene->d);
         else k_wh_connect<ACCEL_BVH><<<grid, 128, 0, r->stream>>>(w, r->scene->d);
         r->prof_end(RT_STAGE_CONNECT);
         cur ^= 1;

@@ -82,17 +82,18 @@ struct AbiSrc {
     }
 };
 
-template <bool COUNTERS>
+template <bool COUNTERS, int ACCEL>
 __global__ void __launch_bounds__(128) k_find_nearest_persistent(const DScene s, const rt_ray* rays, rt_hit* hits, int n, int* fetch)
 {
     AbiSrc src = { rays, hits, nullptr };
-    trace_queue<false, COUNTERS>(s, src, n, fetch);
+    accel_trace_queue<ACCEL, false, COUNTERS>(s, src, n, fetch);
 }
 
+template <int ACCEL>
 __global__ void __launch_bounds__(128) k_is_occluded_persistent(const DScene s, const rt_ray* rays, uint8_t* out, int n, int* fetch)
 {
     AbiSrc src = { rays, nullptr, out };
-    trace_queue<true, false>(s, src, n, fetch);
+    accel_trace_queue<ACCEL, true, false>(s, src, n, fetch);
 }
 
 
@@ -510,9 +511,7 @@ rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags,
     if ((st = upload(&s->fetch_counters, nullptr, rt_scene::FETCH_RING * sizeof(int))) != RT_OK) return fail(st);
     {
         const char* e = getenv("RT_B200_TRAVERSAL");
-        // the persistent-warp state machine (trace_queue) is written for the BVH; KD-tree / grid scenes use the
-        // one-thread-per-ray kernels
-        s->persistent = !(e && strcmp(e, "simple") == 0) && !alt;
+        s->persistent = !(e && strcmp(e, "simple") == 0);
     }
 
     DScene& d = s->d;
@@ -560,8 +559,11 @@ rt_status rt_find_nearest_device(rt_scene* s, const rt_ray* d_rays, rt_hit* d_hi
             const int m = (int)((n - off) < ((size_t)1 << 30) ? (n - off) : ((size_t)1 << 30));
             int* fetch = s->next_fetch_counter();
             RT_CUDA(cudaMemsetAsync(fetch, 0, sizeof(int), (cudaStream_t)stream));
-            if (counters) k_find_nearest_persistent<true><<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays + off, d_hits + off, m, fetch);
-            else k_find_nearest_persistent<false><<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays + off, d_hits + off, m, fetch);
+            void (*k)(const DScene, const rt_ray*, rt_hit*, int, int*) =
+                s->d.kind == RT_SCENE_FLAT_KDTREE ? (counters ? k_find_nearest_persistent<true, ACCEL_KD> : k_find_nearest_persistent<false, ACCEL_KD>) :
+                s->d.kind == RT_SCENE_FLAT_GRID   ? (counters ? k_find_nearest_persistent<true, ACCEL_GRID> : k_find_nearest_persistent<false, ACCEL_GRID>) :
+                                                    (counters ? k_find_nearest_persistent<true, ACCEL_BVH> : k_find_nearest_persistent<false, ACCEL_BVH>);
+            k<<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays + off, d_hits + off, m, fetch);
         }
     }
     else
@@ -589,7 +591,9 @@ rt_status rt_is_occluded_device(rt_scene* s, const rt_ray* d_rays, uint8_t* d_ou
             const int m = (int)((n - off) < ((size_t)1 << 30) ? (n - off) : ((size_t)1 << 30));
             int* fetch = s->next_fetch_counter();
             RT_CUDA(cudaMemsetAsync(fetch, 0, sizeof(int), (cudaStream_t)stream));
-            k_is_occluded_persistent<<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays + off, d_out + off, m, fetch);
+            if (s->d.kind == RT_SCENE_FLAT_KDTREE) k_is_occluded_persistent<ACCEL_KD><<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays + off, d_out + off, m, fetch);
+            else if (s->d.kind == RT_SCENE_FLAT_GRID) k_is_occluded_persistent<ACCEL_GRID><<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays + off, d_out + off, m, fetch);
+            else k_is_occluded_persistent<ACCEL_BVH><<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays + off, d_out + off, m, fetch);
         }
     }
     else if (s->d.kind == RT_SCENE_FLAT_KDTREE) k_is_occluded<ACCEL_KD><<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays, d_out, n);
