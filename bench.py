@@ -10,7 +10,7 @@ with skydome, 1920x1080, 64 spp, reference RNG (one xorshift stream per 16x16 ti
   value        Mrays/s, scene resident in HBM, CUDA-event time of the K steps (L2 flushed between steps)
   e2e          the same job through the public Renderer surface (GpuRenderer: set camera, render, read the
                float4 accumulator back to host memory) — host<->device copies inside the timed region
-  roofline     dominant kernel (k_pt_streams2, the persistent stream kernel: one launch per step):
+  roofline     dominant kernel (k_pt_streams5, the persistent stream kernel: one launch per step):
                algorithmic bytes per ray (64*I + 52*T + 64*B + 48 with the oracle's BVH2 work counts) x rays
                / its CUDA-event time, vs MEASURED_PEAKS.json
   cpu_baseline the reference's own multithreaded CPU render loop (oracle/_ref, built headless from the
@@ -313,7 +313,7 @@ def bench_ours(args):
             # L1 bypassed (what a node fetch costs on an L1 miss) and through L1 (.nc, as the kernel loads)
             l2_peak = api.measure_gather_bandwidth(8 << 20, bypass_l1=True, device=local)
             l1l2_peak = api.measure_gather_bandwidth(8 << 20, bypass_l1=False, device=local)
-            roofline = {"bound": "hbm", "kernel": "k_pt_streams2 (traversal + shading of every (tile, frame) RNG stream, persistent)", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            roofline = {"bound": "hbm", "kernel": "k_pt_streams5 (traversal + shading of every (tile, frame) RNG stream, persistent)", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                         "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write)",
                         "traffic_source": traffic_src, "peak_kind": peak_kind + " HBM copy bandwidth",
                         "algorithmic_bytes_per_ray": work["bytes_per_ray"],
