@@ -5,7 +5,8 @@ import ctypes as C
 import numpy as np
 
 RT_OK, RT_ERR_INVALID, RT_ERR_NO_DEVICE, RT_ERR_CUDA, RT_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
-RT_SCENE_FLAT, RT_SCENE_TLAS, RT_SCENE_FLAT_KDTREE, RT_SCENE_FLAT_GRID = 0, 1, 2, 3
+RT_SCENE_FLAT, RT_SCENE_TLAS, RT_SCENE_FLAT_KDTREE, RT_SCENE_FLAT_GRID, RT_SCENE_TLAS_KDTREE, RT_SCENE_TLAS_GRID = 0, 1, 2, 3, 4, 5
+TLAS_KINDS = (RT_SCENE_TLAS, RT_SCENE_TLAS_KDTREE, RT_SCENE_TLAS_GRID)
 RT_SCENE_FLAG_COUNTERS = 1
 RT_INTEGRATOR_WHITTED, RT_INTEGRATOR_PATH = 0, 1
 RT_SEED_REFERENCE_TILE, RT_SEED_PER_PIXEL = 0, 1
@@ -35,6 +36,12 @@ class rt_grid_desc(C.Structure):
                 ("cell_start", C.c_void_p), ("tri_indices", C.c_void_p), ("index_count", C.c_uint32)]
 
 
+class rt_blas_accel(C.Structure):
+    _fields_ = [("kd_nodes", C.c_void_p), ("kd_node_count", C.c_uint32),
+                ("kd_tri_indices", C.c_void_p), ("kd_tri_index_count", C.c_uint32),
+                ("grid", C.POINTER(rt_grid_desc))]
+
+
 class rt_scene_desc(C.Structure):
     _fields_ = [("kind", C.c_int32),
                 ("blas", C.POINTER(rt_blas_desc)), ("blas_count", C.c_uint32),
@@ -48,7 +55,8 @@ class rt_scene_desc(C.Structure):
                 ("light_color", f3), ("light_pos", f3),
                 ("kd_nodes", C.c_void_p), ("kd_node_count", C.c_uint32),
                 ("kd_tri_indices", C.c_void_p), ("kd_tri_index_count", C.c_uint32),
-                ("grid", C.POINTER(rt_grid_desc))]
+                ("grid", C.POINTER(rt_grid_desc)),
+                ("blas_accel", C.POINTER(rt_blas_accel))]
 
 
 class rt_camera(C.Structure):
@@ -83,6 +91,9 @@ TLAS_NODE_DTYPE = np.dtype([("aabb_min", "<f4", 3), ("left_right", "<u4"), ("aab
 KD_NODE_DTYPE = np.dtype([("aabb_min", "<f4", 3), ("left", "<i4"), ("aabb_max", "<f4", 3), ("right", "<i4"),
                           ("split_axis", "<i4"), ("split_distance", "<f4"), ("tri_start", "<u4"), ("tri_count", "<u4")])
 GRID_HEADER_DTYPE = np.dtype([("resolution", "<i4", 3), ("cell_size", "<f4", 3), ("bounds_min", "<f4", 3), ("bounds_max", "<f4", 3)])
+BLAS_KD_TABLE_DTYPE = np.dtype([("node_offset", "<u4"), ("node_count", "<u4"), ("idx_offset", "<u4"), ("idx_count", "<u4")])
+BLAS_GRID_TABLE_DTYPE = np.dtype([("resolution", "<i4", 3), ("cell_size", "<f4", 3), ("bounds_min", "<f4", 3), ("bounds_max", "<f4", 3),
+                                  ("cell_offset", "<u4"), ("cell_count", "<u4"), ("idx_offset", "<u4"), ("idx_count", "<u4")])
 MATERIAL_DTYPE = np.dtype([("reflectivity", "<f4"), ("refractivity", "<f4"), ("absorption", "<f4", 3),
                            ("albedo", "<f4", 3), ("is_light", "<i4"), ("texture", "<i4")])
 RAY_DTYPE = np.dtype([("O", "<f4", 3), ("tmax", "<f4"), ("D", "<f4", 3), ("inside", "<i4")])

@@ -211,13 +211,14 @@ class GpuFileScene(GpuScene):
 
 
 class GpuTLASFileScene(GpuScene):
-    """TLASFileScene with TLAS_USE_BVH (infra/scene/tlas_file_scene.h): TLAS over per-object BLAS."""
-    KIND = (abi.RT_SCENE_TLAS,)
+    """TLASFileScene (infra/scene/tlas_file_scene.h): the agglomerative TLAS over per-object BLAS of the kind its
+    tlas_file_scene.h:12-14 switch selects - BVH (TLAS_USE_BVH), KD-tree (TLAS_USE_KDTree) or grid (TLAS_USE_Grid)."""
+    KIND = abi.TLAS_KINDS
 
 
 def open_scene(path_or_flat, device=0, counters=False):
     flat = FlatScene.load(path_or_flat) if isinstance(path_or_flat, (str, os.PathLike)) else path_or_flat
-    cls = GpuTLASFileScene if flat.kind == abi.RT_SCENE_TLAS else GpuFileScene
+    cls = GpuTLASFileScene if flat.kind in abi.TLAS_KINDS else GpuFileScene
     return cls(flat, device=device, counters=counters)
 
 

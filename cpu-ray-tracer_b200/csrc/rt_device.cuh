@@ -71,14 +71,15 @@ struct DScene {
     float light_T[16], light_inv_T[16], light_size;
     float light_color[3], light_pos[3];
     // the other two FileScene accelerators (layouts documented next to their traversals below)
-    const float4* kd_nodes;   // RT_SCENE_FLAT_KDTREE: 32-byte nodes, node 0 = root
-    const int2* grid_cells;   // RT_SCENE_FLAT_GRID: (first triangle slot, count) per cell
-    int grid_res[3];
-    float grid_cell[3], grid_min[3], grid_max[3];
+    const float4* kd_nodes;    // KD-tree kinds: 32-byte nodes of every tree (flat scene: node 0 = root)
+    const int2* grid_cells;    // grid kinds: (first triangle slot, count) per cell, all grids concatenated
+    const float4* grid_params; // grid kinds: 64 B per grid = (int res.xyz, int first cell) (cellSize.xyz, -) (boundsMin.xyz, -) (boundsMax.xyz, -)
 };
 
-// which accelerator a kernel is compiled for (template parameter, so the BVH kernels carry no extra code)
-enum { ACCEL_BVH = 0 /* flat BVH and TLAS */, ACCEL_KD = 2, ACCEL_GRID = 3 };
+// which accelerator a kernel is compiled for (template parameter, so the BVH kernels carry no extra code):
+// the values are the scene kinds of include/rt_b200.h
+enum { ACCEL_BVH = 0 /* flat BVH and TLAS over BVHs */, ACCEL_KD = 2, ACCEL_GRID = 3, ACCEL_TLAS_KD = 4, ACCEL_TLAS_GRID = 5 };
+__host__ __device__ __forceinline__ bool kind_is_tlas(int kind) { return kind == 1 || kind == ACCEL_TLAS_KD || kind == ACCEL_TLAS_GRID; }
 
 // ------------------------------------------------------------------------------------------------
 // float3 helpers, written so that each reference expression maps 1:1 (template/tmplmath.h)
@@ -528,7 +529,7 @@ __device__ __forceinline__ float axis_of(float3 a, int axis) { return axis == 0 
 enum { CUR_CONTINUE = 0, CUR_DONE = 1, CUR_RUN = 2 };
 
 template <bool COUNTERS>
-__device__ __forceinline__ bool test_one(const float4* __restrict__ tris, int slot, float3 O, float3 D, HitRec& hit)
+__device__ __forceinline__ bool test_one(const float4* __restrict__ tris, int slot, int ownObj, float3 O, float3 D, HitRec& hit)
 {
     const float4* T = tris + 3 * (size_t)slot;
     const float4 t0 = __ldg(T), t1 = __ldg(T + 1), t2 = __ldg(T + 2);
@@ -536,7 +537,7 @@ __device__ __forceinline__ bool test_one(const float4* __restrict__ tris, int sl
     if (intersect_tri(O, D, f3(t0.x, t0.y, t0.z), f3(t1.x, t1.y, t1.z), f3(t2.x, t2.y, t2.z), hit.t, hit.u, hit.v))
     {
         hit.tri = __float_as_int(t0.w) & ~LAST_BIT;
-        hit.obj = __float_as_int(t1.w);
+        hit.obj = ownObj >= 0 ? ownObj : __float_as_int(t1.w); // BLAS' objIdx (blas_kdtree.cpp:333, blas_grid.cpp:185) or Tri::objIdx
         return true;
     }
     return false;
@@ -545,14 +546,16 @@ __device__ __forceinline__ bool test_one(const float4* __restrict__ tris, int sl
 struct KdCursor {
     int cur, sp;
     int runSlot, runCount;
+    int ownObj; // -1: KDTree of a flat scene; >= 0: BLASKDTree with this objIdx
     float3 rD;
     bool exact;
     int stackNode[KD_STACK_SIZE];
     float stackT[KD_STACK_SIZE];
 
-    __device__ __forceinline__ bool start(const DScene&, const float3 O, const float3 D, const HitRec&)
+    // ref = index of the tree's root in kd_nodes
+    __device__ __forceinline__ bool start(const DScene&, const float3 O, const float3 D, const HitRec&, int ref, int own)
     {
-        rD = recip(D), exact = needs_exact_slab(O, D), cur = 0, sp = 0, runCount = 0;
+        rD = recip(D), exact = needs_exact_slab(O, D), cur = ref, sp = 0, runCount = 0, ownObj = own;
         return false;
     }
 
@@ -565,7 +568,8 @@ struct KdCursor {
         {
             if (sp == 0) return CUR_DONE;
             sp--;
-            if (!(hit.t < stackT[sp])) { cur = stackNode[sp]; return CUR_CONTINUE; }
+            // BLASKDTree additionally requires that the current hit belongs to this BLAS (blas_kdtree.cpp:373,392)
+            if (!((ownObj < 0 || hit.obj == ownObj) && hit.t < stackT[sp])) { cur = stackNode[sp]; return CUR_CONTINUE; }
         }
     }
 
@@ -603,7 +607,7 @@ struct KdCursor {
     template <bool ANYHIT, bool COUNTERS>
     __device__ __forceinline__ int tri_step(const DScene& s, const float3 O, const float3 D, HitRec& hit)
     {
-        const bool accepted = test_one<COUNTERS>(s.tris, runSlot, O, D, hit);
+        const bool accepted = test_one<COUNTERS>(s.tris, runSlot, ownObj, O, D, hit);
         if (ANYHIT && accepted) return CUR_DONE;
         runSlot++;
         if (--runCount > 0) return CUR_RUN;
@@ -616,7 +620,7 @@ template <class Cursor, bool ANYHIT, bool COUNTERS>
 __device__ __forceinline__ void run_cursor(const DScene& s, const float3 O, const float3 D, HitRec& hit)
 {
     Cursor c;
-    if (c.start(s, O, D, hit)) return;
+    if (c.start(s, O, D, hit, 0, -1)) return;
     while (true)
     {
         int r = c.template step<COUNTERS>(s, O, D, hit);
@@ -625,11 +629,6 @@ __device__ __forceinline__ void run_cursor(const DScene& s, const float3 O, cons
     }
 }
 
-template <bool ANYHIT, bool COUNTERS>
-__device__ __forceinline__ void traverse_kd(const DScene& s, const float3 O, const float3 D, HitRec& hit)
-{
-    run_cursor<KdCursor, ANYHIT, COUNTERS>(s, O, D, hit);
-}
 
 // ------------------------------------------------------------------------------------------------
 // Uniform grid: Grid::IntersectGrid (grid.cpp:94-153), 3D-DDA without mailboxing (grid.h:7).
@@ -648,31 +647,38 @@ __device__ __forceinline__ int cvtt_x86(float x)
 struct GridCursor {
     int cell[3], stp[3], exitc[3];
     int runSlot, runCount;
+    int ownObj;                  // -1: Grid of a flat scene; >= 0: BLASGrid with this objIdx
+    int resX, resXY, cellBase;   // cell index = cellBase + x + y * resX + z * resXY
     float deltaT[3], nextT[3];
 
-    __device__ __forceinline__ bool start(const DScene& s, const float3 O, const float3 D, const HitRec& hit)
+    // ref = index of the grid's 64-byte parameter record
+    __device__ __forceinline__ bool start(const DScene& s, const float3 O, const float3 D, const HitRec& hit, int ref, int own)
     {
+        const float4* P = s.grid_params + 4 * (size_t)ref;
+        const int4 g0 = __ldg((const int4*)P);
+        const float4 g1 = __ldg(P + 1), g2 = __ldg(P + 2), g3 = __ldg(P + 3);
+        const int res[3] = { g0.x, g0.y, g0.z };
+        const float cs[3] = { g1.x, g1.y, g1.z }, bmin[3] = { g2.x, g2.y, g2.z };
         const float3 rD = recip(D);
         float tminU, tmaxU;
-        runCount = 0;
-        if (!slab_range(O, rD, hit.t, needs_exact_slab(O, D), s.grid_min[0], s.grid_min[1], s.grid_min[2],
-                        s.grid_max[0], s.grid_max[1], s.grid_max[2], tminU, tmaxU)) return true;
+        runCount = 0, ownObj = own, resX = g0.x, resXY = g0.x * g0.y, cellBase = g0.w;
+        if (!slab_range(O, rD, hit.t, needs_exact_slab(O, D), g2.x, g2.y, g2.z, g3.x, g3.y, g3.z, tminU, tmaxU)) return true;
 #pragma unroll
         for (int i = 0; i < 3; i++)
         {
-            const float rayOrigCell = axis_of(O, i) - s.grid_min[i];
-            cell[i] = clampi(cvtt_x86(floorf(rayOrigCell / s.grid_cell[i])), 0, s.grid_res[i] - 1);
+            const float rayOrigCell = axis_of(O, i) - bmin[i];
+            cell[i] = clampi(cvtt_x86(floorf(rayOrigCell / cs[i])), 0, res[i] - 1);
             if (axis_of(D, i) < 0)
             {
-                deltaT[i] = -s.grid_cell[i] * axis_of(rD, i);
-                nextT[i] = (cell[i] * s.grid_cell[i] - rayOrigCell) * axis_of(rD, i);
+                deltaT[i] = -cs[i] * axis_of(rD, i);
+                nextT[i] = (cell[i] * cs[i] - rayOrigCell) * axis_of(rD, i);
                 exitc[i] = -1, stp[i] = -1;
             }
             else
             {
-                deltaT[i] = s.grid_cell[i] * axis_of(rD, i);
-                nextT[i] = ((cell[i] + 1) * s.grid_cell[i] - rayOrigCell) * axis_of(rD, i);
-                exitc[i] = s.grid_res[i], stp[i] = 1;
+                deltaT[i] = cs[i] * axis_of(rD, i);
+                nextT[i] = ((cell[i] + 1) * cs[i] - rayOrigCell) * axis_of(rD, i);
+                exitc[i] = res[i], stp[i] = 1;
             }
         }
         return false;
@@ -703,7 +709,7 @@ struct GridCursor {
     __device__ __forceinline__ int step(const DScene& s, const float3 O, const float3 D, HitRec& hit)
     {
         if (COUNTERS) hit.traversed++;
-        const int2 c = __ldg(s.grid_cells + (unsigned)(cell[0] + cell[1] * s.grid_res[0] + cell[2] * s.grid_res[0] * s.grid_res[1]));
+        const int2 c = __ldg(s.grid_cells + (unsigned)(cellBase + cell[0] + cell[1] * resX + cell[2] * resXY));
         runSlot = c.x, runCount = c.y;
         if (runCount > 0) return CUR_RUN;
         return advance(hit);
@@ -712,7 +718,7 @@ struct GridCursor {
     template <bool ANYHIT, bool COUNTERS>
     __device__ __forceinline__ int tri_step(const DScene& s, const float3 O, const float3 D, HitRec& hit)
     {
-        const bool accepted = test_one<COUNTERS>(s.tris, runSlot, O, D, hit);
+        const bool accepted = test_one<COUNTERS>(s.tris, runSlot, ownObj, O, D, hit);
         if (ANYHIT && accepted) return CUR_DONE;
         runSlot++;
         if (--runCount > 0) return CUR_RUN;
@@ -720,18 +726,99 @@ struct GridCursor {
     }
 };
 
-template <bool ANYHIT, bool COUNTERS>
-__device__ __forceinline__ void traverse_grid(const DScene& s, const float3 O, const float3 D, HitRec& hit)
-{
-    run_cursor<GridCursor, ANYHIT, COUNTERS>(s, O, D, hit);
-}
+
+// ------------------------------------------------------------------------------------------------
+// TLASFileScene over per-object KD-trees / grids (TLAS_USE_KDTree / TLAS_USE_Grid, tlas_file_scene.h:12-14).
+// The top level is the same agglomerative BVH as for TLAS_USE_BVH (tlas_kdtree.cpp:83-110 = tlas_grid.cpp:83-110 =
+// tlas_bvh.cpp:83-111), stored as the same fat nodes; a TLAS leaf enters BLASKDTree::Intersect (blas_kdtree.cpp:420-431) /
+// BLASGrid::Intersect (blas_grid.cpp:232-246): world -> object transform in the SSE lane-sum order, the BLAS cursor run
+// to completion, then the TLAS stack continues.  The cursor protocol is the one above; world-space (O, D) come from the
+// caller, the object-space ray lives in the cursor.
+// ------------------------------------------------------------------------------------------------
+template <class Blas>
+struct TlasCursor {
+    Blas blas;
+    float3 Ol, Dl, rDw;
+    bool exactW, inBlas;
+    int cur, sp;
+    int stack[STACK_SIZE];
+
+    __device__ __forceinline__ bool start(const DScene& s, const float3 O, const float3 D, const HitRec&, int, int)
+    {
+        rDw = recip(D), exactW = needs_exact_slab(O, D), cur = s.root_ref, sp = 0, inBlas = false;
+        blas.runCount = 0;
+        return false;
+    }
+
+    __device__ __forceinline__ int pop_tlas()
+    {
+        if (sp == 0) return CUR_DONE;
+        cur = stack[--sp];
+        return CUR_CONTINUE;
+    }
+
+    template <bool COUNTERS>
+    __device__ __forceinline__ int step(const DScene& s, const float3 O, const float3 D, HitRec& hit)
+    {
+        if (inBlas)
+        {
+            const int r = blas.template step<COUNTERS>(s, Ol, Dl, hit);
+            if (r != CUR_DONE) return r;
+            inBlas = false; // blas_kdtree.cpp:427-430: O, D, rD restored, the hit record carried over
+            return pop_tlas();
+        }
+        if (cur >= 0)
+        {
+            if (COUNTERS) hit.traversed++;
+            const float4* n = s.nodes + 4 * (size_t)cur;
+            const float4 n0 = __ldg(n), n1 = __ldg(n + 1), n2 = __ldg(n + 2);
+            const int4 n3 = __ldg((const int4*)(n + 3));
+            float d1 = slab(O, rDw, hit.t, exactW, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y);
+            float d2 = slab(O, rDw, hit.t, exactW, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w);
+            int c1 = n3.x, c2 = n3.y;
+            if (d1 > d2) { const float tf = d1; d1 = d2; d2 = tf; const int tc = c1; c1 = c2; c2 = tc; }
+            if (d1 == 1e30f) return pop_tlas();
+            cur = c1;
+            if (d2 != 1e30f) stack[sp++] = c2;
+            return CUR_CONTINUE;
+        }
+        // TLAS leaf: enter the instance (Ray(const Ray&) drops `tested`, ray.h:10-14)
+        if (COUNTERS) hit.traversed++, hit.tested = 0;
+        const float4* I = s.inst + 4 * (size_t)(~cur & ~INSTANCE_BIT);
+        const float4 r0 = __ldg(I), r1 = __ldg(I + 1), r2 = __ldg(I + 2);
+        const int4 meta = __ldg((const int4*)(I + 3));
+        Ol = f3((O.x * r0.x + O.y * r0.y) + (O.z * r0.z + r0.w),
+                (O.x * r1.x + O.y * r1.y) + (O.z * r1.z + r1.w),
+                (O.x * r2.x + O.y * r2.y) + (O.z * r2.z + r2.w));
+        Dl = f3((D.x * r0.x + D.y * r0.y) + D.z * r0.z,
+                (D.x * r1.x + D.y * r1.y) + D.z * r1.z,
+                (D.x * r2.x + D.y * r2.y) + D.z * r2.z);
+        if (blas.start(s, Ol, Dl, hit, meta.x, meta.y)) return pop_tlas();
+        inBlas = true;
+        return CUR_CONTINUE;
+    }
+
+    template <bool ANYHIT, bool COUNTERS>
+    __device__ __forceinline__ int tri_step(const DScene& s, const float3 O, const float3 D, HitRec& hit)
+    {
+        const int r = blas.template tri_step<ANYHIT, COUNTERS>(s, Ol, Dl, hit);
+        if (r != CUR_DONE) return r;
+        if (ANYHIT && hit.obj > -1) return CUR_DONE; // occluded: the whole query ends, not just this instance
+        inBlas = false;
+        return pop_tlas();
+    }
+};
+
+template <int ACCEL> struct CursorOf { typedef KdCursor type; };
+template <> struct CursorOf<ACCEL_GRID> { typedef GridCursor type; };
+template <> struct CursorOf<ACCEL_TLAS_KD> { typedef TlasCursor<KdCursor> type; };
+template <> struct CursorOf<ACCEL_TLAS_GRID> { typedef TlasCursor<GridCursor> type; };
 
 template <int ACCEL, bool ANYHIT, bool COUNTERS>
 __device__ __forceinline__ void accel_traverse(const DScene& s, const float3 O, const float3 D, HitRec& hit)
 {
-    if (ACCEL == ACCEL_KD) traverse_kd<ANYHIT, COUNTERS>(s, O, D, hit);
-    else if (ACCEL == ACCEL_GRID) traverse_grid<ANYHIT, COUNTERS>(s, O, D, hit);
-    else traverse<ANYHIT, COUNTERS>(s, O, D, hit);
+    if (ACCEL == ACCEL_BVH) traverse<ANYHIT, COUNTERS>(s, O, D, hit);
+    else run_cursor<typename CursorOf<ACCEL>::type, ANYHIT, COUNTERS>(s, O, D, hit);
 }
 
 // Persistent-warp traversal with ray replacement for the cursor accelerators: the KD-tree / grid counterpart of
@@ -784,7 +871,7 @@ __device__ __forceinline__ void trace_queue_cursor(const DScene& s, Src& src, co
                         const float tp = -(dot(O, N) + s.floor_d) / (dot(D, N));
                         if (tp < hit.t && tp > 0) hit.t = tp, hit.obj = 1;
                     }
-                    if (!done) done = cursor.start(s, O, D, hit);
+                    if (!done) done = cursor.start(s, O, D, hit, 0, -1);
                     if (done) src.store(rayIdx, hit);
                     else state = Q_TRAV;
                 }
@@ -820,9 +907,6 @@ __device__ __forceinline__ void trace_queue_cursor(const DScene& s, Src& src, co
         }
     }
 }
-
-template <int ACCEL> struct CursorOf { typedef KdCursor type; };
-template <> struct CursorOf<ACCEL_GRID> { typedef GridCursor type; };
 
 // the persistent-warp queue traversal of the accelerator a kernel is compiled for
 template <int ACCEL, bool ANYHIT, bool COUNTERS, class Src>
@@ -927,7 +1011,7 @@ __device__ __forceinline__ void hit_info(const DScene& s, float3 D, float3 I, in
     {
         int triBase = 0;
         float4 r0, r1, r2;
-        const bool tlas = s.kind == 1;
+        const bool tlas = kind_is_tlas(s.kind);
         if (tlas)
         {
             const float4* IS = s.inst_shade + 4 * (size_t)(obj - 2);

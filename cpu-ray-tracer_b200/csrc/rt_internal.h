@@ -21,6 +21,17 @@ bool cuda_ok(cudaError_t e, const char* what);
 
 } // namespace rtb
 
+// Runs CALL with `A` = the accelerator id the scene kind selects (kernel template argument).
+#define RT_FOR_ACCEL(kind, CALL)                                                           \
+    switch (kind)                                                                          \
+    {                                                                                      \
+    case RT_SCENE_FLAT_KDTREE: { constexpr int A = rtb::ACCEL_KD; CALL; } break;               \
+    case RT_SCENE_FLAT_GRID: { constexpr int A = rtb::ACCEL_GRID; CALL; } break;               \
+    case RT_SCENE_TLAS_KDTREE: { constexpr int A = rtb::ACCEL_TLAS_KD; CALL; } break;          \
+    case RT_SCENE_TLAS_GRID: { constexpr int A = rtb::ACCEL_TLAS_GRID; CALL; } break;          \
+    default: { constexpr int A = rtb::ACCEL_BVH; CALL; } break;                                \
+    }
+
 struct rt_scene {
     int device = 0;
     uint32_t flags = 0;
@@ -33,6 +44,7 @@ struct rt_scene {
     float4* inst_shade = nullptr;
     float4* kd_nodes = nullptr;   // RT_SCENE_FLAT_KDTREE
     int2* grid_cells = nullptr;   // RT_SCENE_FLAT_GRID
+    float4* grid_params = nullptr;
     int* obj_material = nullptr;
     rtb::DMaterial* materials = nullptr;
     rtb::DTexture* textures = nullptr;

@@ -608,7 +608,7 @@ __global__ void __launch_bounds__(128) k_pt_streams_alt(const PTState p, const D
         const float3 fn = f3(s.floor_n[0], s.floor_n[1], s.floor_n[2]);                        \
         const float tp = -(dot(wO, fn) + s.floor_d) / (dot(wD, fn));                           \
         if (tp < hit.t && tp > 0) hit.t = tp, hit.obj = 1;                                     \
-        state = cursor.start(s, wO, wD, hit) ? SA_SHADE : SA_TRAV;                             \
+        state = cursor.start(s, wO, wD, hit, 0, -1) ? SA_SHADE : SA_TRAV;                      \
         rays++;                                                                                \
     }
 
@@ -1273,6 +1273,8 @@ __global__ void k_to_rgb8(const float4* __restrict__ accum, uint32_t* __restrict
 
 using namespace rtb;
 
+static bool is_alt_kind(int kind) { return kind >= RT_SCENE_FLAT_KDTREE && kind <= RT_SCENE_TLAS_GRID; }
+
 struct rt_renderer {
     rt_scene* scene = nullptr;
     rt_render_params params = {};
@@ -1443,7 +1445,7 @@ rt_status rt_renderer_create(rt_scene* scene, const rt_render_params* params, rt
         // path-tracer schedule: params->schedule, overridable for A/B runs with RT_B200_PT_SCHEDULE
         r->useStreams = params->schedule != RT_SCHEDULE_WAVEFRONT;
         if ((e = getenv("RT_B200_PT_SCHEDULE")) != nullptr) r->useStreams = strcmp(e, "wavefront") != 0;
-        const bool altAccel = scene->d.kind == RT_SCENE_FLAT_KDTREE || scene->d.kind == RT_SCENE_FLAT_GRID;
+        const bool altAccel = is_alt_kind(scene->d.kind);
         if ((e = getenv("RT_B200_STREAM_KERNEL")) != nullptr && atoi(e) > 0) r->streamKernel = atoi(e);
         if (altAccel) r->streamKernel = 0; // k_pt_streams_alt: versions 2 / 5 are state machines over the BVH layout
         if ((e = getenv("RT_B200_STREAM_LPT")) != nullptr) r->streamLpt = atoi(e) != 0;
@@ -1459,6 +1461,8 @@ rt_status rt_renderer_create(rt_scene* scene, const rt_render_params* params, rt
         }
         else if (scene->d.kind == RT_SCENE_FLAT_KDTREE) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams_alt<ACCEL_KD>, 128, 0);
         else if (scene->d.kind == RT_SCENE_FLAT_GRID) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams_alt<ACCEL_GRID>, 128, 0);
+        else if (scene->d.kind == RT_SCENE_TLAS_KDTREE) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams_alt<ACCEL_TLAS_KD>, 128, 0);
+        else if (scene->d.kind == RT_SCENE_TLAS_GRID) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams_alt<ACCEL_TLAS_GRID>, 128, 0);
         else if (scene->d.kind == RT_SCENE_TLAS) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams2<true>, 128, 0);
         else oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams2<false>, 128, 0);
         if (oe == cudaSuccess && occ > 0) r->streamCtasPerSm = occ;
@@ -1605,9 +1609,7 @@ static rt_status pt_tile_order(rt_renderer* r, const PTState& p)
     }
     RT_CUDA(cudaMemsetAsync(r->dTileCost, 0, (size_t)n * 4, r->stream));
     r->prof_begin();
-    if (r->scene->d.kind == RT_SCENE_FLAT_KDTREE) k_pt_pilot<ACCEL_KD><<<r->sms * 4, 128, 0, r->stream>>>(p, r->scene->d, r->cam, r->dTileCost);
-    else if (r->scene->d.kind == RT_SCENE_FLAT_GRID) k_pt_pilot<ACCEL_GRID><<<r->sms * 4, 128, 0, r->stream>>>(p, r->scene->d, r->cam, r->dTileCost);
-    else k_pt_pilot<ACCEL_BVH><<<r->sms * 4, 128, 0, r->stream>>>(p, r->scene->d, r->cam, r->dTileCost);
+    RT_FOR_ACCEL(r->scene->d.kind, (k_pt_pilot<A><<<r->sms * 4, 128, 0, r->stream>>>(p, r->scene->d, r->cam, r->dTileCost)));
     r->prof_end(RT_STAGE_GENERATE);
     std::vector<unsigned int> cost(n);
     RT_CUDA(cudaMemcpyAsync(cost.data(), r->dTileCost, (size_t)n * 4, cudaMemcpyDeviceToHost, r->stream));
@@ -1658,6 +1660,8 @@ static rt_status render_pt_streams(rt_renderer* r, int first_spp, int count, int
     }
     else if (r->scene->d.kind == RT_SCENE_FLAT_KDTREE) k_pt_streams_alt<ACCEL_KD><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
     else if (r->scene->d.kind == RT_SCENE_FLAT_GRID) k_pt_streams_alt<ACCEL_GRID><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
+    else if (r->scene->d.kind == RT_SCENE_TLAS_KDTREE) k_pt_streams_alt<ACCEL_TLAS_KD><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
+    else if (r->scene->d.kind == RT_SCENE_TLAS_GRID) k_pt_streams_alt<ACCEL_TLAS_GRID><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
     else if (r->scene->d.kind == RT_SCENE_TLAS) k_pt_streams2<true><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
     else k_pt_streams2<false><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
     r->prof_end(RT_STAGE_EXTEND);
@@ -1735,18 +1739,8 @@ static rt_status render_pt(rt_renderer* r, int first_spp, int count, int stride)
             p.iteration = it;
             r->ptIterations = it + 1;
             r->prof_begin();
-            if (kind == RT_SCENE_FLAT_KDTREE)
-            {
-                if (r->persistent) k_pt_extend_persistent<ACCEL_KD><<<grid, 128, 0, r->stream>>>(p, r->scene->d, cur);
-                else k_pt_extend<ACCEL_KD><<<grid, 128, 0, r->stream>>>(p, r->scene->d, cur);
-            }
-            else if (kind == RT_SCENE_FLAT_GRID)
-            {
-                if (r->persistent) k_pt_extend_persistent<ACCEL_GRID><<<grid, 128, 0, r->stream>>>(p, r->scene->d, cur);
-                else k_pt_extend<ACCEL_GRID><<<grid, 128, 0, r->stream>>>(p, r->scene->d, cur);
-            }
-            else if (r->persistent) k_pt_extend_persistent<ACCEL_BVH><<<grid, 128, 0, r->stream>>>(p, r->scene->d, cur);
-            else k_pt_extend<ACCEL_BVH><<<grid, 128, 0, r->stream>>>(p, r->scene->d, cur);
+            if (r->persistent) { RT_FOR_ACCEL(kind, (k_pt_extend_persistent<A><<<grid, 128, 0, r->stream>>>(p, r->scene->d, cur))); }
+            else { RT_FOR_ACCEL(kind, (k_pt_extend<A><<<grid, 128, 0, r->stream>>>(p, r->scene->d, cur))); }
             r->prof_end(RT_STAGE_EXTEND);
             r->prof_begin();
             k_pt_shade<<<grid, 128, 0, r->stream>>>(p, r->scene->d, r->cam, cur);
@@ -1782,35 +1776,15 @@ static void whitted_frame_launches(rt_renderer* r)
     for (int depth = 0; depth <= P.depth_limit; depth++)
     {
         r->prof_begin();
-        if (kind == RT_SCENE_FLAT_KDTREE)
-        {
-            if (r->persistent) k_wh_extend_persistent<ACCEL_KD><<<grid, 128, 0, r->stream>>>(w, r->scene->d, cur);
-            else k_wh_extend<ACCEL_KD><<<grid, 128, 0, r->stream>>>(w, r->scene->d, cur);
-        }
-        else if (kind == RT_SCENE_FLAT_GRID)
-        {
-            if (r->persistent) k_wh_extend_persistent<ACCEL_GRID><<<grid, 128, 0, r->stream>>>(w, r->scene->d, cur);
-            else k_wh_extend<ACCEL_GRID><<<grid, 128, 0, r->stream>>>(w, r->scene->d, cur);
-        }
-        else if (r->persistent) k_wh_extend_persistent<ACCEL_BVH><<<grid, 128, 0, r->stream>>>(w, r->scene->d, cur);
-        else k_wh_extend<ACCEL_BVH><<<grid, 128, 0, r->stream>>>(w, r->scene->d, cur);
+        if (r->persistent) { RT_FOR_ACCEL(kind, (k_wh_extend_persistent<A><<<grid, 128, 0, r->stream>>>(w, r->scene->d, cur))); }
+        else { RT_FOR_ACCEL(kind, (k_wh_extend<A><<<grid, 128, 0, r->stream>>>(w, r->scene->d, cur))); }
         r->prof_end(RT_STAGE_EXTEND);
         r->prof_begin();
         k_wh_shade<<<grid, 128, 0, r->stream>>>(w, r->scene->d, cur);
         r->prof_end(RT_STAGE_SHADE);
         r->prof_begin();
-        if (kind == RT_SCENE_FLAT_KDTREE)
-        {
-            if (r->persistent) k_wh_connect_persistent<ACCEL_KD><<<grid, 128, 0, r->stream>>>(w, r->scene->d);
-            else k_wh_connect<ACCEL_KD><<<grid, 128, 0, r->stream>>>(w, r->scene->d);
-        }
-        else if (kind == RT_SCENE_FLAT_GRID)
-        {
-            if (r->persistent) k_wh_connect_persistent<ACCEL_GRID><<<grid, 128, 0, r->stream>>>(w, r->scene->d);
-            else k_wh_connect<ACCEL_GRID><<<grid, 128, 0, r->stream>>>(w, r->scene->d);
-        }
-        else if (r->persistent) k_wh_connect_persistent<ACCEL_BVH><<<grid, 128, 0, r->stream>>>(w, r->scene->d);
-        else k_wh_connect<ACCEL_BVH><<<grid, 128, 0, r->stream>>>(w, r->scene->d);
+        if (r->persistent) { RT_FOR_ACCEL(kind, (k_wh_connect_persistent<A><<<grid, 128, 0, r->stream>>>(w, r->scene->d))); }
+        else { RT_FOR_ACCEL(kind, (k_wh_connect<A><<<grid, 128, 0, r->stream>>>(w, r->scene->d))); }
         r->prof_end(RT_STAGE_CONNECT);
         cur ^= 1;
     }

@@ -302,13 +302,18 @@ static void push_shade_records(std::vector<float4>& shade, const rt_blas_desc& b
 
 // rt_kd_node[] (reference KDTreeNode graph flattened by the host) -> 32-byte device nodes in DFS pre-order with
 // adjacent children + leaf-ordered triangle records.  Layout: rt_device.cuh, "KD-tree".
-static bool build_kd(const rt_scene_desc& d, std::vector<float4>& kd, std::vector<float4>& tris, std::string& error)
+struct KdSource { const rt_kd_node* kd_nodes; uint32_t kd_node_count; const uint32_t* kd_tri_indices; uint32_t kd_tri_index_count; };
+
+// Appends one tree to `kd` (the root's node index is returned in rootOut) and its leaf runs to `tris`.
+static bool build_kd(const KdSource& d, const rt_blas_desc& b, std::vector<float4>& kd, std::vector<float4>& tris, int& rootOut, std::string& error)
 {
-    const rt_blas_desc& b = d.blas[0];
+    if (!d.kd_nodes || d.kd_node_count == 0 || (!d.kd_tri_indices && d.kd_tri_index_count)) { error = "KD-tree without nodes"; return false; }
     struct Item { uint32_t src; uint32_t dst; int depth; };
     std::vector<Item> todo;
-    kd.resize(2);
-    todo.push_back({ 0u, 0u, 0 });
+    const uint32_t root = (uint32_t)(kd.size() / 2);
+    rootOut = (int)root;
+    kd.resize(kd.size() + 2);
+    todo.push_back({ 0u, root, 0 });
     size_t visited = 0;
     while (!todo.empty())
     {
@@ -349,20 +354,28 @@ static bool build_kd(const rt_scene_desc& d, std::vector<float4>& kd, std::vecto
 }
 
 // rt_grid_desc -> (first slot, count) per cell + cell-ordered triangle records.  Layout: rt_device.cuh, "Uniform grid".
-static bool build_grid(const rt_scene_desc& d, std::vector<int2>& cells, std::vector<float4>& tris, std::string& error)
+// Appends one grid: its cells to `cells`, its 64-byte parameter record to `params` (record index in recOut), its runs to `tris`.
+static bool build_grid(const rt_grid_desc* gp, const rt_blas_desc& b, std::vector<int2>& cells, std::vector<float4>& params, std::vector<float4>& tris, int& recOut, std::string& error)
 {
-    const rt_grid_desc& g = *d.grid;
-    const rt_blas_desc& b = d.blas[0];
+    if (!gp) { error = "grid scene without a grid"; return false; }
+    const rt_grid_desc& g = *gp;
     if (!g.cell_start || (!g.tri_indices && g.index_count)) { error = "grid with null arrays"; return false; }
     for (int i = 0; i < 3; i++)
         if (g.resolution[i] < 1 || g.resolution[i] > 1024) { error = "grid resolution out of range"; return false; }
     const size_t n = (size_t)g.resolution[0] * g.resolution[1] * g.resolution[2];
-    cells.resize(n);
+    const size_t base = cells.size();
+    if (base + n >= (1ull << 31)) { error = "too many grid cells"; return false; }
+    recOut = (int)(params.size() / 4);
+    params.push_back(Builder::f4(Builder::asf(g.resolution[0]), Builder::asf(g.resolution[1]), Builder::asf(g.resolution[2]), Builder::asf((int)base)));
+    params.push_back(Builder::f4(g.cell_size[0], g.cell_size[1], g.cell_size[2], 0));
+    params.push_back(Builder::f4(g.bounds_min[0], g.bounds_min[1], g.bounds_min[2], 0));
+    params.push_back(Builder::f4(g.bounds_max[0], g.bounds_max[1], g.bounds_max[2], 0));
+    cells.resize(base + n);
     for (size_t c = 0; c < n; c++)
     {
         const uint32_t a = g.cell_start[c], e = g.cell_start[c + 1];
         if (e < a || e > g.index_count) { error = "grid cell range out of bounds"; return false; }
-        cells[c] = make_int2((int)(tris.size() / 3), (int)(e - a));
+        cells[base + c] = make_int2((int)(tris.size() / 3), (int)(e - a));
         for (uint32_t j = a; j < e; j++)
         {
             const uint32_t triIdx = g.tri_indices[j];
@@ -407,14 +420,16 @@ rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags,
     if (desc->kind == RT_SCENE_FLAT && desc->blas_count != 1) { set_error("rt_scene_create: a flat scene has exactly one BVH"); return RT_ERR_INVALID; }
     if (desc->kind == RT_SCENE_TLAS && (!desc->tlas_nodes || desc->tlas_node_count == 0)) { set_error("rt_scene_create: TLAS scene without TLAS nodes"); return RT_ERR_INVALID; }
     const bool alt = desc->kind == RT_SCENE_FLAT_KDTREE || desc->kind == RT_SCENE_FLAT_GRID;
-    if (desc->kind != RT_SCENE_FLAT && desc->kind != RT_SCENE_TLAS && !alt) { set_error("rt_scene_create: unknown scene kind"); return RT_ERR_INVALID; }
+    const bool tlasAlt = desc->kind == RT_SCENE_TLAS_KDTREE || desc->kind == RT_SCENE_TLAS_GRID;
+    const bool anyTlas = desc->kind == RT_SCENE_TLAS || tlasAlt;
+    if (desc->kind != RT_SCENE_FLAT && !anyTlas && !alt) { set_error("rt_scene_create: unknown scene kind"); return RT_ERR_INVALID; }
     if (alt && (desc->blas_count != 1 || !desc->blas[0].tris || desc->blas[0].tri_count == 0)) { set_error("rt_scene_create: a KD-tree / grid scene has exactly one triangle array"); return RT_ERR_INVALID; }
-    if (desc->kind == RT_SCENE_FLAT_KDTREE && (!desc->kd_nodes || desc->kd_node_count == 0 || (!desc->kd_tri_indices && desc->kd_tri_index_count))) { set_error("rt_scene_create: KD-tree scene without KD nodes"); return RT_ERR_INVALID; }
-    if (desc->kind == RT_SCENE_FLAT_GRID && !desc->grid) { set_error("rt_scene_create: grid scene without a grid"); return RT_ERR_INVALID; }
+    if (tlasAlt && !desc->blas_accel) { set_error("rt_scene_create: TLAS KD-tree / grid scene without blas_accel"); return RT_ERR_INVALID; }
+    if (tlasAlt && (!desc->tlas_nodes || desc->tlas_node_count == 0)) { set_error("rt_scene_create: TLAS scene without TLAS nodes"); return RT_ERR_INVALID; }
     if (rt_device_count() <= device || device < 0) { set_error("rt_scene_create: no such CUDA device (there is no CPU fallback)"); return RT_ERR_NO_DEVICE; }
 
     Builder B;
-    std::vector<float4> kdNodes;
+    std::vector<float4> kdNodes, gridParams;
     std::vector<int2> gridCells;
     std::vector<int> rootRefs(desc->blas_count);
     std::vector<int> triBase(desc->blas_count);
@@ -425,13 +440,43 @@ rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags,
         if (alt)
         {
             // FileScene with its KD-tree or grid: triangles in leaf / cell order, shading records by triIdx as for the BVH
-            const bool ok = desc->kind == RT_SCENE_FLAT_KDTREE ? build_kd(*desc, kdNodes, B.tris, B.error) : build_grid(*desc, gridCells, B.tris, B.error);
+            const KdSource ks = { desc->kd_nodes, desc->kd_node_count, desc->kd_tri_indices, desc->kd_tri_index_count };
+            int ref = 0;
+            const bool ok = desc->kind == RT_SCENE_FLAT_KDTREE ? build_kd(ks, b, kdNodes, B.tris, ref, B.error)
+                                                               : build_grid(desc->grid, b, gridCells, gridParams, B.tris, ref, B.error);
             if (!ok) { set_error("rt_scene_create: " + B.error); return RT_ERR_INVALID; }
             push_shade_records(B.shade, b);
             triBase[i] = 0, rootRefs[i] = 0;
             for (int k = 0; k < 4; k++) B.inst.push_back(Builder::f4(0, 0, 0, 0)), B.inst_shade.push_back(Builder::f4(0, 0, 0, 0));
             break;
         }
+        if (tlasAlt)
+        {
+            // TLASFileScene over per-object KD-trees / grids: instance record = invT rows + (root node | grid record, objIdx);
+            // descriptors that point at the same arrays share one device copy (true instancing, as for the BVH kind)
+            if (!b.tris || b.tri_count == 0) { set_error("rt_scene_create: BLAS without triangles"); return RT_ERR_INVALID; }
+            const rt_blas_accel& a = desc->blas_accel[i];
+            int shared = -1;
+            for (uint32_t j : firstOfGeometry)
+            {
+                const rt_blas_accel& o = desc->blas_accel[j];
+                if (desc->blas[j].tris == b.tris && desc->blas[j].tri_count == b.tri_count &&
+                    (desc->kind == RT_SCENE_TLAS_KDTREE ? (o.kd_nodes == a.kd_nodes && o.kd_tri_indices == a.kd_tri_indices) : (o.grid == a.grid))) { shared = (int)j; break; }
+            }
+            if (shared >= 0) triBase[i] = triBase[shared], rootRefs[i] = rootRefs[shared];
+            else
+            {
+                triBase[i] = (int)(B.shade.size() / 4);
+                const KdSource ks = { a.kd_nodes, a.kd_node_count, a.kd_tri_indices, a.kd_tri_index_count };
+                const bool ok = desc->kind == RT_SCENE_TLAS_KDTREE ? build_kd(ks, b, kdNodes, B.tris, rootRefs[i], B.error)
+                                                                   : build_grid(a.grid, b, gridCells, gridParams, B.tris, rootRefs[i], B.error);
+                if (!ok) { set_error("rt_scene_create: " + B.error); return RT_ERR_INVALID; }
+                push_shade_records(B.shade, b);
+                if (firstOfGeometry.size() < 64) firstOfGeometry.push_back(i);
+            }
+        }
+        else
+        {
         if (!b.nodes || !b.tris || !b.tri_indices) { set_error("rt_scene_create: BLAS with null arrays"); return RT_ERR_INVALID; }
         // true instancing: BLAS descriptors that point at the same reference arrays share
         // one device copy of nodes / triangles / shading records; only the 2 x 64-byte instance records differ
@@ -448,6 +493,7 @@ rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags,
             if (!B.error.empty()) { set_error("rt_scene_create: " + B.error); return RT_ERR_INVALID; }
             if (firstOfGeometry.size() < 64) firstOfGeometry.push_back(i);
         }
+        }
         const float* M = b.inv_T;
         B.inst.push_back(Builder::f4(M[0], M[1], M[2], M[3]));
         B.inst.push_back(Builder::f4(M[4], M[5], M[6], M[7]));
@@ -460,7 +506,7 @@ rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags,
         B.inst_shade.push_back(Builder::f4(Builder::asf(triBase[i]), 0, 0, 0));
     }
     int rootRef = rootRefs[0];
-    if (desc->kind == RT_SCENE_TLAS)
+    if (anyTlas)
     {
         rootRef = B.add_tlas(*desc);
         if (!B.error.empty()) { set_error("rt_scene_create: " + B.error); return RT_ERR_INVALID; }
@@ -482,10 +528,11 @@ rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags,
     if ((st = upload(&s->obj_material, desc->obj_material, desc->obj_count * sizeof(int))) != RT_OK) return fail(st);
     if ((st = upload(&s->kd_nodes, kdNodes.data(), kdNodes.size() * 16)) != RT_OK) return fail(st);
     if ((st = upload(&s->grid_cells, gridCells.data(), gridCells.size() * sizeof(int2))) != RT_OK) return fail(st);
+    if ((st = upload(&s->grid_params, gridParams.data(), gridParams.size() * 16)) != RT_OK) return fail(st);
     s->node_count = B.nodes.size() / 4, s->tri_count = B.tris.size() / 3, s->inst_count = desc->blas_count;
     s->bytes_geometry = (B.nodes.size() + B.tris.size() + B.inst.size() + B.shade.size() + B.inst_shade.size() + kdNodes.size()) * 16 + gridCells.size() * sizeof(int2);
-    if (desc->kind == RT_SCENE_FLAT_KDTREE) s->node_count = kdNodes.size() / 2;
-    if (desc->kind == RT_SCENE_FLAT_GRID) s->node_count = gridCells.size();
+    if (desc->kind == RT_SCENE_FLAT_KDTREE || desc->kind == RT_SCENE_TLAS_KDTREE) s->node_count += kdNodes.size() / 2;
+    if (desc->kind == RT_SCENE_FLAT_GRID || desc->kind == RT_SCENE_TLAS_GRID) s->node_count += gridCells.size();
 
     static_assert(sizeof(DMaterial) == sizeof(rt_material), "material layout");
     if ((st = upload(&s->materials, desc->materials, desc->material_count * sizeof(rt_material))) != RT_OK) return fail(st);
@@ -519,11 +566,7 @@ rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags,
     d.obj_material = s->obj_material, d.materials = s->materials, d.textures = s->textures;
     d.root_ref = rootRef, d.kind = desc->kind;
     d.flat_obj_idx = desc->kind == RT_SCENE_FLAT ? desc->blas[0].obj_idx : -1;
-    d.kd_nodes = s->kd_nodes, d.grid_cells = s->grid_cells;
-    if (desc->kind == RT_SCENE_FLAT_GRID)
-        for (int i = 0; i < 3; i++)
-            d.grid_res[i] = desc->grid->resolution[i], d.grid_cell[i] = desc->grid->cell_size[i],
-            d.grid_min[i] = desc->grid->bounds_min[i], d.grid_max[i] = desc->grid->bounds_max[i];
+    d.kd_nodes = s->kd_nodes, d.grid_cells = s->grid_cells, d.grid_params = s->grid_params;
     d.skydome_texture = desc->skydome_texture, d.floor_texture = desc->floor_texture;
     memcpy(d.floor_n, desc->floor_n, 12), d.floor_d = desc->floor_d, d.floor_invto = desc->floor_invto;
     memcpy(d.light_T, desc->light_T, 64), memcpy(d.light_inv_T, desc->light_inv_T, 64), d.light_size = desc->light_size;
@@ -537,7 +580,7 @@ void rt_scene_destroy(rt_scene* s)
     if (!s) return;
     cudaSetDevice(s->device);
     cudaFree(s->nodes), cudaFree(s->tris), cudaFree(s->inst), cudaFree(s->shade), cudaFree(s->inst_shade);
-    cudaFree(s->kd_nodes), cudaFree(s->grid_cells);
+    cudaFree(s->kd_nodes), cudaFree(s->grid_cells), cudaFree(s->grid_params);
     cudaFree(s->obj_material), cudaFree(s->materials), cudaFree(s->textures), cudaFree(s->tex_pixels);
     cudaFree(s->scratch_in), cudaFree(s->scratch_out), cudaFree(s->fetch_counters);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -559,19 +602,15 @@ rt_status rt_find_nearest_device(rt_scene* s, const rt_ray* d_rays, rt_hit* d_hi
             const int m = (int)((n - off) < ((size_t)1 << 30) ? (n - off) : ((size_t)1 << 30));
             int* fetch = s->next_fetch_counter();
             RT_CUDA(cudaMemsetAsync(fetch, 0, sizeof(int), (cudaStream_t)stream));
-            void (*k)(const DScene, const rt_ray*, rt_hit*, int, int*) =
-                s->d.kind == RT_SCENE_FLAT_KDTREE ? (counters ? k_find_nearest_persistent<true, ACCEL_KD> : k_find_nearest_persistent<false, ACCEL_KD>) :
-                s->d.kind == RT_SCENE_FLAT_GRID   ? (counters ? k_find_nearest_persistent<true, ACCEL_GRID> : k_find_nearest_persistent<false, ACCEL_GRID>) :
-                                                    (counters ? k_find_nearest_persistent<true, ACCEL_BVH> : k_find_nearest_persistent<false, ACCEL_BVH>);
+            void (*k)(const DScene, const rt_ray*, rt_hit*, int, int*) = nullptr;
+            RT_FOR_ACCEL(s->d.kind, (k = counters ? k_find_nearest_persistent<true, A> : k_find_nearest_persistent<false, A>));
             k<<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays + off, d_hits + off, m, fetch);
         }
     }
     else
     {
-        void (*k)(const DScene, const rt_ray*, rt_hit*, size_t) =
-            s->d.kind == RT_SCENE_FLAT_KDTREE ? (counters ? k_find_nearest<true, ACCEL_KD> : k_find_nearest<false, ACCEL_KD>) :
-            s->d.kind == RT_SCENE_FLAT_GRID   ? (counters ? k_find_nearest<true, ACCEL_GRID> : k_find_nearest<false, ACCEL_GRID>) :
-                                                (counters ? k_find_nearest<true, ACCEL_BVH> : k_find_nearest<false, ACCEL_BVH>);
+        void (*k)(const DScene, const rt_ray*, rt_hit*, size_t) = nullptr;
+        RT_FOR_ACCEL(s->d.kind, (k = counters ? k_find_nearest<true, A> : k_find_nearest<false, A>));
         k<<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays, d_hits, n);
     }
     RT_CUDA(cudaGetLastError());
@@ -591,14 +630,10 @@ rt_status rt_is_occluded_device(rt_scene* s, const rt_ray* d_rays, uint8_t* d_ou
             const int m = (int)((n - off) < ((size_t)1 << 30) ? (n - off) : ((size_t)1 << 30));
             int* fetch = s->next_fetch_counter();
             RT_CUDA(cudaMemsetAsync(fetch, 0, sizeof(int), (cudaStream_t)stream));
-            if (s->d.kind == RT_SCENE_FLAT_KDTREE) k_is_occluded_persistent<ACCEL_KD><<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays + off, d_out + off, m, fetch);
-            else if (s->d.kind == RT_SCENE_FLAT_GRID) k_is_occluded_persistent<ACCEL_GRID><<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays + off, d_out + off, m, fetch);
-            else k_is_occluded_persistent<ACCEL_BVH><<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays + off, d_out + off, m, fetch);
+            RT_FOR_ACCEL(s->d.kind, (k_is_occluded_persistent<A><<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays + off, d_out + off, m, fetch)));
         }
     }
-    else if (s->d.kind == RT_SCENE_FLAT_KDTREE) k_is_occluded<ACCEL_KD><<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays, d_out, n);
-    else if (s->d.kind == RT_SCENE_FLAT_GRID) k_is_occluded<ACCEL_GRID><<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays, d_out, n);
-    else k_is_occluded<ACCEL_BVH><<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays, d_out, n);
+    else { RT_FOR_ACCEL(s->d.kind, (k_is_occluded<A><<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays, d_out, n))); }
     RT_CUDA(cudaGetLastError());
     return RT_OK;
 }

@@ -8,7 +8,8 @@
 //
 //   rtb200::GpuScene<FileScene>       replaces FileScene      (infra/scene/file_scene.h; whichever of USE_BVH /
 //                                     USE_KDTree - the shipped default - / USE_Grid file_scene.h:10-12 selects)
-//   rtb200::GpuScene<TLASFileScene>   replaces TLASFileScene  (infra/scene/tlas_file_scene.h, TLAS_USE_BVH)
+//   rtb200::GpuScene<TLASFileScene>   replaces TLASFileScene  (infra/scene/tlas_file_scene.h; TLAS_USE_BVH, TLAS_USE_KDTree
+//                                     or TLAS_USE_Grid, whichever tlas_file_scene.h:12-14 selects)
 //       same BaseScene virtuals (infra/scene/base_scene.h:16-32); FindNearest / IsOccluded run on the
 //       GPU (single-ray calls are an n = 1 batch, plus batched overloads); the remaining queries
 //       (GetHitInfo, GetAlbedo, GetSkyColor, light) are answered by the host scene it owns, whose
@@ -53,10 +54,12 @@ struct FlattenedScene
 	std::vector<int32_t> objMaterial;
 	std::vector<rt_material> materials;
 	std::vector<rt_texture> textures;
-	std::vector<rt_kd_node> kdNodes;      // USE_KDTree: KDTreeNode graph, flattened
+	std::vector<rt_kd_node> kdNodes;      // USE_KDTree / TLAS_USE_KDTree: KDTreeNode graph(s), flattened
 	std::vector<uint32_t> altTriIdx;      // KD leaf lists / grid cell lists, concatenated
-	std::vector<uint32_t> gridCellStart;  // USE_Grid
+	std::vector<uint32_t> gridCellStart;  // USE_Grid / TLAS_USE_Grid
 	rt_grid_desc grid = {};
+	std::vector<rt_grid_desc> blasGrids;  // TLAS_USE_Grid: one per BLAS
+	std::vector<rt_blas_accel> blasAccel; // TLAS_USE_KDTree / TLAS_USE_Grid: parallel to blas
 	rt_scene_desc desc = {};
 };
 
@@ -136,20 +139,20 @@ template <class Acc> inline void FlattenTriangles( Tmpl8::FileScene& scene, Acc&
 }
 #endif
 
-#ifdef USE_KDTree
-// FileScene as shipped: the pointer-linked KDTreeNode graph (blas_kdtree.h:16-25) becomes rt_kd_node[]: node 0 = root,
-// children numbered when their parent is visited (depth first, left first), per-leaf index vectors concatenated
-inline void Flatten( Tmpl8::FileScene& scene, FlattenedScene& f )
+#if defined(USE_KDTree) || defined(TLAS_USE_KDTree)
+// The pointer-linked KDTreeNode graph (blas_kdtree.h:16-25) appended to kdNodes as rt_kd_node[]: the tree's first node is
+// its root, children are numbered when their parent is visited (depth first, left first), per-leaf index vectors are
+// concatenated; child indices and tri_start are relative to the tree's own first node / first index
+inline void FlattenKdTree( const Tmpl8::KDTreeNode* root, std::vector<rt_kd_node>& kdNodes, std::vector<uint32_t>& triIdx )
 {
-	f.desc.kind = RT_SCENE_FLAT_KDTREE;
-	FlattenTriangles( scene, scene.acc, f );
-	std::vector<std::pair<const Tmpl8::KDTreeNode*, uint32_t>> todo;
-	f.kdNodes.push_back( rt_kd_node() );
-	todo.push_back( { scene.acc.rootNode, 0u } );
+	const size_t nodeBase = kdNodes.size(), idxBase = triIdx.size();
+	std::vector<std::pair<const Tmpl8::KDTreeNode*, size_t>> todo;
+	kdNodes.push_back( rt_kd_node() );
+	todo.push_back( { root, nodeBase } );
 	while (!todo.empty())
 	{
 		const Tmpl8::KDTreeNode* n = todo.back().first;
-		const uint32_t slot = todo.back().second;
+		const size_t slot = todo.back().second;
 		todo.pop_back();
 		rt_kd_node k = {};
 		k.aabb_min[0] = n->aabbMin.x, k.aabb_min[1] = n->aabbMin.y, k.aabb_min[2] = n->aabbMin.z;
@@ -158,21 +161,50 @@ inline void Flatten( Tmpl8::FileScene& scene, FlattenedScene& f )
 		k.left = k.right = -1;
 		if (n->isLeaf)
 		{
-			k.tri_start = (uint32_t)f.altTriIdx.size(), k.tri_count = (uint32_t)n->triIndices.size();
-			f.altTriIdx.insert( f.altTriIdx.end(), n->triIndices.begin(), n->triIndices.end() );
+			k.tri_start = (uint32_t)(triIdx.size() - idxBase), k.tri_count = (uint32_t)n->triIndices.size();
+			triIdx.insert( triIdx.end(), n->triIndices.begin(), n->triIndices.end() );
 		}
 		else
 		{
-			k.left = (int32_t)f.kdNodes.size(), k.right = k.left + 1;
-			f.kdNodes.push_back( rt_kd_node() ), f.kdNodes.push_back( rt_kd_node() );
-			todo.push_back( { n->right, (uint32_t)k.right } ), todo.push_back( { n->left, (uint32_t)k.left } );
+			k.left = (int32_t)(kdNodes.size() - nodeBase), k.right = k.left + 1;
+			kdNodes.push_back( rt_kd_node() ), kdNodes.push_back( rt_kd_node() );
+			todo.push_back( { n->right, nodeBase + k.right } ), todo.push_back( { n->left, nodeBase + k.left } );
 		}
-		f.kdNodes[slot] = k;
+		kdNodes[slot] = k;
 	}
+}
+#endif
+
+#ifdef USE_KDTree
+// FileScene as shipped
+inline void Flatten( Tmpl8::FileScene& scene, FlattenedScene& f )
+{
+	f.desc.kind = RT_SCENE_FLAT_KDTREE;
+	FlattenTriangles( scene, scene.acc, f );
+	FlattenKdTree( scene.acc.rootNode, f.kdNodes, f.altTriIdx );
 	f.desc.kd_nodes = f.kdNodes.data(), f.desc.kd_node_count = (uint32_t)f.kdNodes.size();
 	f.desc.kd_tri_indices = f.altTriIdx.data(), f.desc.kd_tri_index_count = (uint32_t)f.altTriIdx.size();
 	FlattenCommon( scene, f );
 	FinishDesc( f );
+}
+#endif
+
+#if defined(USE_Grid) || defined(TLAS_USE_Grid)
+// Grid / BLASGrid: per-cell index vectors (blas_grid.h:8-11) concatenated in cell order; cell_start is relative to this
+// grid's own first index.  The pointers of `g` are filled in by the caller once the vectors have stopped growing.
+template <class G> inline void FlattenGrid( G& grid, rt_grid_desc& g, std::vector<uint32_t>& cellStart, std::vector<uint32_t>& triIdx )
+{
+	const size_t idxBase = triIdx.size();
+	for (int i = 0; i < 3; i++)
+		g.resolution[i] = grid.resolution[i], g.cell_size[i] = grid.cellSize[i],
+		g.bounds_min[i] = grid.localBounds.bmin[i], g.bounds_max[i] = grid.localBounds.bmax[i];
+	for (const Tmpl8::GridCell& c : grid.gridCells)
+	{
+		cellStart.push_back( (uint32_t)(triIdx.size() - idxBase) );
+		for (int t : c.triIndices) triIdx.push_back( (uint32_t)t );
+	}
+	cellStart.push_back( (uint32_t)(triIdx.size() - idxBase) );
+	g.index_count = (uint32_t)(triIdx.size() - idxBase);
 }
 #endif
 
@@ -183,17 +215,8 @@ inline void Flatten( Tmpl8::FileScene& scene, FlattenedScene& f )
 	f.desc.kind = RT_SCENE_FLAT_GRID;
 	Tmpl8::Grid& g = scene.acc;
 	FlattenTriangles( scene, g, f );
-	for (int i = 0; i < 3; i++)
-		f.grid.resolution[i] = g.resolution[i], f.grid.cell_size[i] = g.cellSize[i],
-		f.grid.bounds_min[i] = g.localBounds.bmin[i], f.grid.bounds_max[i] = g.localBounds.bmax[i];
-	for (const Tmpl8::GridCell& c : g.gridCells)
-	{
-		f.gridCellStart.push_back( (uint32_t)f.altTriIdx.size() );
-		for (int t : c.triIndices) f.altTriIdx.push_back( (uint32_t)t );
-	}
-	f.gridCellStart.push_back( (uint32_t)f.altTriIdx.size() );
+	FlattenGrid( g, f.grid, f.gridCellStart, f.altTriIdx );
 	f.grid.cell_start = f.gridCellStart.data(), f.grid.tri_indices = f.altTriIdx.data();
-	f.grid.index_count = (uint32_t)f.altTriIdx.size();
 	f.desc.grid = &f.grid;
 	FlattenCommon( scene, f );
 	FinishDesc( f );
@@ -216,6 +239,63 @@ inline void Flatten( Tmpl8::TLASFileScene& scene, FlattenedScene& f )
 		f.blas.push_back( b );
 		f.objMaterial.push_back( blas->matIdx );
 	}
+	f.desc.tlas_nodes = (const rt_tlas_node*)scene.tlas.tlasNode;
+	f.desc.tlas_node_count = scene.tlas.nodesUsed;
+	FlattenCommon( scene, f );
+	FinishDesc( f );
+}
+#endif
+
+#if defined(TLAS_USE_KDTree) || defined(TLAS_USE_Grid)
+// TLASFileScene over per-object KD-trees / grids: the same agglomerative TLAS (tlas_kdtree.cpp:17-70 = tlas_grid.cpp:17-70),
+// BLASKDTree / BLASGrid leaves (needs read access to TLASKDTree::tlasNode / TLASGrid::tlasNode and, for the grid, to
+// BLASGrid::resolution / cellSize / triangles / gridCells, private in the reference)
+inline void Flatten( Tmpl8::TLASFileScene& scene, FlattenedScene& f )
+{
+	struct Range { size_t node, nodes, idx, idxs, cell; };
+	std::vector<Range> ranges;
+#ifdef TLAS_USE_KDTree
+	f.desc.kind = RT_SCENE_TLAS_KDTREE;
+	static_assert(sizeof( Tmpl8::TLASKDTreeNode ) == sizeof( rt_tlas_node ), "TLASKDTreeNode layout (tlas_kdtree.h:6-13)");
+#else
+	f.desc.kind = RT_SCENE_TLAS_GRID;
+	static_assert(sizeof( Tmpl8::TLASGridNode ) == sizeof( rt_tlas_node ), "TLASGridNode layout (tlas_grid.h:7-14)");
+	f.blasGrids.resize( scene.tlas.blas.size() );
+#endif
+	size_t i = 0;
+	for (auto* blas : scene.tlas.blas)
+	{
+		rt_blas_desc b = {};
+		b.tris = (const rt_tri*)blas->triangles.data(), b.tri_count = (uint32_t)blas->triangles.size();
+		memcpy( b.T, blas->T.cell, 64 ), memcpy( b.inv_T, blas->invT.cell, 64 );
+		b.obj_idx = blas->objIdx, b.mat_idx = blas->matIdx;
+		f.blas.push_back( b );
+		f.objMaterial.push_back( blas->matIdx );
+		Range r = { f.kdNodes.size(), 0, f.altTriIdx.size(), 0, f.gridCellStart.size() };
+#ifdef TLAS_USE_KDTree
+		FlattenKdTree( blas->rootNode, f.kdNodes, f.altTriIdx );
+#else
+		FlattenGrid( *blas, f.blasGrids[i], f.gridCellStart, f.altTriIdx );
+#endif
+		r.nodes = f.kdNodes.size() - r.node, r.idxs = f.altTriIdx.size() - r.idx;
+		ranges.push_back( r );
+		i++;
+	}
+	f.blasAccel.resize( ranges.size() );
+	for (i = 0; i < ranges.size(); i++) // pointers only now: the vectors no longer grow
+	{
+		rt_blas_accel a = {};
+#ifdef TLAS_USE_KDTree
+		a.kd_nodes = f.kdNodes.data() + ranges[i].node, a.kd_node_count = (uint32_t)ranges[i].nodes;
+		a.kd_tri_indices = f.altTriIdx.data() + ranges[i].idx, a.kd_tri_index_count = (uint32_t)ranges[i].idxs;
+#else
+		f.blasGrids[i].cell_start = f.gridCellStart.data() + ranges[i].cell;
+		f.blasGrids[i].tri_indices = f.altTriIdx.data() + ranges[i].idx;
+		a.grid = &f.blasGrids[i];
+#endif
+		f.blasAccel[i] = a;
+	}
+	f.desc.blas_accel = f.blasAccel.data();
 	f.desc.tlas_nodes = (const rt_tlas_node*)scene.tlas.tlasNode;
 	f.desc.tlas_node_count = scene.tlas.nodesUsed;
 	FlattenCommon( scene, f );

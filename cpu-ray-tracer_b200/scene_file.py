@@ -16,6 +16,9 @@ constructors ran (file_scene.cpp:4-62, tlas_file_scene.cpp:4-93), in the referen
     kd_nodes     rt_kd_node[] (48 B) + kd_tri_indices uint[]      kind 2: FileScene with its KD-tree (kdtree.cpp)
     grid_header  resolution / cellSize / localBounds + grid_cell_start uint[cells+1] + grid_tri_indices uint[]
                                                                   kind 3: FileScene with its uniform grid (grid.cpp)
+    blas_kd_table / blas_grid_table   per BLAS: ranges into kd_nodes + kd_tri_indices, or grid header + ranges into
+                 grid_cell_start (cells + 1 entries per BLAS) + grid_tri_indices       kinds 4 / 5: TLASFileScene over
+                 per-object KD-trees / grids (tlas_kdtree.cpp, tlas_grid.cpp); indices are relative to the BLAS' own range
 
 File layout: "RTSCN001", u32 chunk count, u32 pad, then per chunk: char name[24], u64 nbytes, payload
 padded to 8 bytes.  A ".gz" suffix means the whole file is gzip-compressed.
@@ -44,8 +47,9 @@ _CHUNK_DTYPES = {
     "materials": abi.MATERIAL_DTYPE, "tex_table": TEX_TABLE_DTYPE, "tex_pixels": np.dtype("<u4"),
     "kd_nodes": abi.KD_NODE_DTYPE, "kd_tri_indices": np.dtype("<u4"),
     "grid_header": abi.GRID_HEADER_DTYPE, "grid_cell_start": np.dtype("<u4"), "grid_tri_indices": np.dtype("<u4"),
+    "blas_kd_table": abi.BLAS_KD_TABLE_DTYPE, "blas_grid_table": abi.BLAS_GRID_TABLE_DTYPE,
 }
-_OPTIONAL = ("kd_nodes", "kd_tri_indices", "grid_header", "grid_cell_start", "grid_tri_indices")
+_OPTIONAL = ("kd_nodes", "kd_tri_indices", "grid_header", "grid_cell_start", "grid_tri_indices", "blas_kd_table", "blas_grid_table")
 
 
 class FlatScene:
@@ -91,7 +95,33 @@ class FlatScene:
             dt = _CHUNK_DTYPES[name]
             chunks[name] = np.frombuffer(data, dtype=dt, count=nbytes // dt.itemsize, offset=off).copy()
             off += (nbytes + 7) & ~7
-        return FlatScene(chunks)
+        fs = FlatScene(chunks)
+        if fs.kind == abi.RT_SCENE_TLAS_KDTREE and fs.blas_kd_table is None:
+            fs.rebuild_blas_kdtrees()
+        return fs
+
+    def rebuild_blas_kdtrees(self):
+        """A kind-4 file may omit the per-object KD-trees (the reference's median-split trees reach 20 MB for a 4 k-triangle
+        scene): they are rebuilt here with the host restatement of BLASKDTree::Build (host/bvh_build.cpp, byte-identical to
+        the reference's trees on every scene it flattened, tests/test_host_build.py)."""
+        from . import host_build
+        nodes, idx, table = [], [], np.zeros(len(self.blas_table), abi.BLAS_KD_TABLE_DTYPE)
+        no, io = 0, 0
+        for i, b in enumerate(self.blas_table):
+            t0, tn = int(b["tri_offset"]), int(b["tri_count"])
+            n, ix, _ = host_build.build_kdtree(self.tris[t0:t0 + tn])
+            table[i] = (no, len(n), io, len(ix))
+            nodes.append(n), idx.append(ix)
+            no, io = no + len(n), io + len(ix)
+        self.kd_nodes, self.kd_tri_indices, self.blas_kd_table = np.concatenate(nodes), np.concatenate(idx), table
+
+    def save_without_kdtrees(self, path):
+        keep = self.kd_nodes, self.kd_tri_indices, self.blas_kd_table
+        self.kd_nodes = self.kd_tri_indices = self.blas_kd_table = None
+        try:
+            self.save(path)
+        finally:
+            self.kd_nodes, self.kd_tri_indices, self.blas_kd_table = keep
 
     def save(self, path):
         opener = gzip.open if str(path).endswith(".gz") else open
@@ -145,6 +175,30 @@ class FlatScene:
         d.light_color = abi.f3(*h["light_color"].tolist())
         d.light_pos = abi.f3(*h["light_pos"].tolist())
         grid = None
+        if self.blas_kd_table is not None or self.blas_grid_table is not None:
+            # TLASFileScene over per-object KD-trees / grids
+            accel = (abi.rt_blas_accel * nb)()
+            grids = (abi.rt_grid_desc * nb)()
+            for i in range(nb):
+                if self.blas_kd_table is not None:
+                    k = self.blas_kd_table[i]
+                    accel[i].kd_nodes = self.kd_nodes.ctypes.data + int(k["node_offset"]) * 48
+                    accel[i].kd_node_count = int(k["node_count"])
+                    accel[i].kd_tri_indices = self.kd_tri_indices.ctypes.data + int(k["idx_offset"]) * 4
+                    accel[i].kd_tri_index_count = int(k["idx_count"])
+                else:
+                    g = self.blas_grid_table[i]
+                    grids[i].resolution = (C.c_int32 * 3)(*g["resolution"].tolist())
+                    grids[i].cell_size = abi.f3(*g["cell_size"].tolist())
+                    grids[i].bounds_min = abi.f3(*g["bounds_min"].tolist())
+                    grids[i].bounds_max = abi.f3(*g["bounds_max"].tolist())
+                    grids[i].cell_start = self.grid_cell_start.ctypes.data + int(g["cell_offset"]) * 4
+                    grids[i].tri_indices = self.grid_tri_indices.ctypes.data + int(g["idx_offset"]) * 4
+                    grids[i].index_count = int(g["idx_count"])
+                    accel[i].grid = C.pointer(grids[i])
+            d.blas_accel = C.cast(accel, C.POINTER(abi.rt_blas_accel))
+            self._keep = (blas, tex, accel, grids)
+            return d
         if self.kd_nodes is not None:
             d.kd_nodes, d.kd_node_count = self.kd_nodes.ctypes.data, len(self.kd_nodes)
             d.kd_tri_indices, d.kd_tri_index_count = self.kd_tri_indices.ctypes.data, len(self.kd_tri_indices)

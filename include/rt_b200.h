@@ -124,11 +124,25 @@ typedef struct rt_grid_desc {
     uint32_t index_count;
 } rt_grid_desc;
 
+/* Per-BLAS KD-tree / grid of TLASFileScene built with TLAS_USE_KDTree / TLAS_USE_Grid (tlas_file_scene.h:12-14):
+ * BLASKDTree (infra/blas_kdtree.h:27-58) or BLASGrid (infra/blas_grid.h:13-41), flattened like the flat-scene forms
+ * above; node / cell indices and tri_start are relative to this BLAS' own arrays.  The TLAS above them is the same
+ * agglomerative BVH as for TLAS_USE_BVH (tlas_kdtree.cpp:17-70 = tlas_grid.cpp:17-70 = tlas_bvh.cpp:17-70). */
+typedef struct rt_blas_accel {
+    const rt_kd_node* kd_nodes;     /* RT_SCENE_TLAS_KDTREE */
+    uint32_t kd_node_count;
+    const uint32_t* kd_tri_indices;
+    uint32_t kd_tri_index_count;
+    const rt_grid_desc* grid;       /* RT_SCENE_TLAS_GRID */
+} rt_blas_accel;
+
 enum {
     RT_SCENE_FLAT = 0,          /* FileScene, USE_BVH */
     RT_SCENE_TLAS = 1,          /* TLASFileScene, TLAS_USE_BVH */
     RT_SCENE_FLAT_KDTREE = 2,   /* FileScene, USE_KDTree (the configuration the reference ships, file_scene.h:10-12) */
-    RT_SCENE_FLAT_GRID = 3      /* FileScene, USE_Grid */
+    RT_SCENE_FLAT_GRID = 3,     /* FileScene, USE_Grid */
+    RT_SCENE_TLAS_KDTREE = 4,   /* TLASFileScene, TLAS_USE_KDTree */
+    RT_SCENE_TLAS_GRID = 5      /* TLASFileScene, TLAS_USE_Grid */
 };
 
 typedef struct rt_scene_desc {
@@ -163,6 +177,9 @@ typedef struct rt_scene_desc {
     const uint32_t* kd_tri_indices;
     uint32_t kd_tri_index_count;
     const rt_grid_desc* grid;       /* RT_SCENE_FLAT_GRID */
+    /* RT_SCENE_TLAS_KDTREE / RT_SCENE_TLAS_GRID: blas_count entries, parallel to blas[] (which then carries tris /
+     * tri_count / T / inv_T / obj_idx / mat_idx; nodes and tri_indices are ignored) */
+    const rt_blas_accel* blas_accel;
 } rt_scene_desc;
 
 /* ---- rays and hits (Ray, template/ray.h:6-41, as plain records) ------------------------------ */

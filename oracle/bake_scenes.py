@@ -31,6 +31,10 @@ SCENES = {
     "bunny_grid": ("file_grid", "bunny_scene.xml"),
     "inside_kd": ("file_kd", "inside_scene.xml"),
     "inside_grid": ("file_grid", "inside_scene.xml"),
+    # TLASFileScene over per-object KD-trees / grids (TLAS_USE_KDTree / TLAS_USE_Grid)
+    # (one scene each: a flattened median-split KD-tree per object is ~10x the size of the BVH scene)
+    "inside_tlas_grid": ("tlas_grid", "inside_scene.xml"),
+    "instanced_tlas_kd": ("tlas_kd", "instanced_scene.xml"),
 }
 
 

@@ -30,7 +30,7 @@ REF = os.environ.get("RT_REFERENCE_DIR", "/root/reference")
 
 TEMPLATE_FILES = ["tmplmath.h", "tmplmath.cpp", "common.h", "ray.h", "camera.h", "primitives.h",
                   "texture.h", "material.h"]
-INFRA_FILES = ["kdtree.cpp", "grid.cpp", "bvh.h", "bvh.cpp", "blas_bvh.h", "blas_bvh.cpp", "tlas_bvh.h", "tlas_bvh.cpp",
+INFRA_FILES = ["kdtree.cpp", "grid.cpp", "blas_grid.cpp", "tlas_grid.cpp", "blas_kdtree.cpp", "tlas_kdtree.cpp", "bvh.h", "bvh.cpp", "blas_bvh.h", "blas_bvh.cpp", "tlas_bvh.h", "tlas_bvh.cpp",
                "grid.h", "blas_grid.h", "tlas_grid.h", "kdtree.h", "blas_kdtree.h", "tlas_kdtree.h",
                "helper.h", "hit_info.h", "model.h", "model.cpp"]
 SCENE_FILES = ["base_scene.h", "file_scene.h", "file_scene.cpp", "tlas_file_scene.h", "tlas_file_scene.cpp"]
@@ -45,7 +45,7 @@ def sub(text, pattern, repl, name, count=0, flags=0, min_hits=1):
     return new
 
 
-def patch_sources(d, integrator, big_tlas, accel="bvh"):
+def patch_sources(d, integrator, big_tlas, accel="bvh", tlas_accel="bvh"):
     def edit(fn, fun):
         p = os.path.join(d, fn)
         with open(p, encoding="utf-8-sig") as f:
@@ -93,6 +93,14 @@ def patch_sources(d, integrator, big_tlas, accel="bvh"):
                                            r"#define USE_KDTree", "//#define USE_KDTree", "no kdtree"))
         # resolution / cellSize / gridCells are private (grid.h:25-30); the flattener copies them
         edit("grid.h", lambda s: sub(s, r"private:", "public:", "grid private", min_hits=2))
+    # TLASFileScene with BLAS grids / BLAS KD-trees under the same agglomerative TLAS (tlas_file_scene.h:12-14)
+    if tlas_accel != "bvh":
+        want = {"grid": "TLAS_USE_Grid", "kdtree": "TLAS_USE_KDTree"}[tlas_accel]
+        edit("tlas_file_scene.h", lambda s: sub(sub(s, r"#define TLAS_USE_BVH", "//#define TLAS_USE_BVH", "no tlas bvh"),
+                                                r"//#define " + want, "#define " + want, "tlas accel"))
+        hdrs = {"grid": ("tlas_grid.h", "blas_grid.h"), "kdtree": ("tlas_kdtree.h", "blas_kdtree.h")}[tlas_accel]
+        for h in hdrs:  # tlasNode / nodesUsed, BLASGrid::resolution / cellSize / triangles / gridCells are private
+            edit(h, lambda s: sub(s, r"private:", "public:", "tlas alt private", min_hits=2))
     # TLAS internals are needed by the flattener (tlas_bvh.h:27 keeps tlasNode private)
     edit("tlas_bvh.h", lambda s: sub(s, r"private:", "public:", "tlas private"))
     # texel array is private (texture.h:98-101); the flattener copies it
@@ -127,7 +135,7 @@ def patch_sources(d, integrator, big_tlas, accel="bvh"):
         edit("renderer.cpp", lambda s: sub(sub(s, r'system\("cls"\);', "", "cls"), r'\n\s*printf\("(Total|Average|Peak)[^\n]*', "", "prints", min_hits=6))
 
 
-def build_variant(integrator, scene_kind, cxx="g++", extra_flags=(), suffix="", big_tlas=False, verbose=False, gpuhost=False, accel="bvh"):
+def build_variant(integrator, scene_kind, cxx="g++", extra_flags=(), suffix="", big_tlas=False, verbose=False, gpuhost=False, accel="bvh", tlas_accel="bvh"):
     os.makedirs(OUT, exist_ok=True)
     d = tempfile.mkdtemp(prefix="ref_build_")
     try:
@@ -141,12 +149,13 @@ def build_variant(integrator, scene_kind, cxx="g++", extra_flags=(), suffix="", 
             shutil.copy(os.path.join(REF, RENDERER_DIRS[integrator], fn), d)
         for fn in os.listdir(d):
             os.chmod(os.path.join(d, fn), 0o644)
-        patch_sources(d, integrator, big_tlas, accel)
+        patch_sources(d, integrator, big_tlas, accel, tlas_accel)
         unity = os.path.join(d, "unity.cpp")
         with open(unity, "w") as f:
             f.write('#include "precomp.h"\n')
             for src in ["tmplmath.cpp", "bvh.cpp", "blas_bvh.cpp", "tlas_bvh.cpp", "model.cpp"] + \
-                       {"kdtree": ["kdtree.cpp"], "grid": ["grid.cpp"]}.get(accel, []) + ["file_scene.cpp", "tlas_file_scene.cpp", "renderer.cpp"]:
+                       {"kdtree": ["kdtree.cpp"], "grid": ["grid.cpp"]}.get(accel, []) + \
+                       {"kdtree": ["blas_kdtree.cpp", "tlas_kdtree.cpp"], "grid": ["blas_grid.cpp", "tlas_grid.cpp"]}.get(tlas_accel, []) + ["file_scene.cpp", "tlas_file_scene.cpp", "renderer.cpp"]:
                 f.write(f'#include "{src}"\n')
             f.write(f'#include "{os.path.join(HERE, "ref_api.cpp")}"\n')
             if gpuhost:
@@ -190,6 +199,9 @@ def build_all(verbose=False, gpuhost=True):
     for integ in ("whitted", "pt"):
         jobs.append(dict(integrator=integ, scene_kind="file", suffix="_kd", accel="kdtree"))
         jobs.append(dict(integrator=integ, scene_kind="file", suffix="_grid", accel="grid"))
+        # TLASFileScene over per-object KD-trees / grids (TLAS_USE_KDTree / TLAS_USE_Grid)
+        jobs.append(dict(integrator=integ, scene_kind="tlas", suffix="_kd", tlas_accel="kdtree"))
+        jobs.append(dict(integrator=integ, scene_kind="tlas", suffix="_grid", tlas_accel="grid"))
     from concurrent.futures import ThreadPoolExecutor
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:  # g++ subprocesses, one temp dir each
         outs = list(ex.map(lambda kw: build_variant(verbose=verbose, **kw), jobs))
@@ -205,9 +217,11 @@ def build_gpuhost(verbose=False):
     jobs = [dict(integrator=integ, scene_kind=kind) for integ in ("whitted", "pt") for kind in ("file", "tlas")]
     # FileScene with the KD-tree it ships with / the grid, through the same adapter header
     jobs += [dict(integrator="pt", scene_kind="file", suffix="_kd", accel="kdtree"),
-             dict(integrator="whitted", scene_kind="file", suffix="_grid", accel="grid")]
+             dict(integrator="whitted", scene_kind="file", suffix="_grid", accel="grid"),
+             dict(integrator="whitted", scene_kind="tlas", suffix="_kd", tlas_accel="kdtree"),
+             dict(integrator="pt", scene_kind="tlas", suffix="_grid", tlas_accel="grid")]
     from concurrent.futures import ThreadPoolExecutor
-    with ThreadPoolExecutor(max_workers=min(6, os.cpu_count() or 1)) as ex:
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         return list(ex.map(lambda kw: build_variant(verbose=verbose, gpuhost=True, **kw), jobs))
 
 

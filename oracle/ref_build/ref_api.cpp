@@ -222,6 +222,63 @@ static int add_texture( const Texture* tex, std::vector<FlatTexture>& table, std
 	return (int)table.size() - 1;
 }
 
+struct FlatKdNode { float aabbMin[3]; int32_t left; float aabbMax[3]; int32_t right; int32_t splitAxis; float splitDistance; uint32_t triStart, triCount; };
+struct FlatGridHeader { int32_t resolution[3]; float cellSize[3], boundsMin[3], boundsMax[3]; };
+struct FlatBlasKd { uint32_t node_offset, node_count, idx_offset, idx_count; };                 // per BLAS, chunk "blas_kd_table"
+struct FlatBlasGrid { FlatGridHeader h; uint32_t cell_offset, cell_count, idx_offset, idx_count; }; // per BLAS, chunk "blas_grid_table"
+
+#if defined(USE_KDTree) || defined(TLAS_USE_KDTree)
+// KDTreeNode graph (blas_kdtree.h:16-25) -> flat nodes: root first, children numbered when their parent is visited (depth
+// first, left first), child indices and triStart relative to this tree's first node / first index
+static void flatten_kd( KDTreeNode* root, std::vector<FlatKdNode>& kdNodes, std::vector<uint>& kdTriIdx )
+{
+	const size_t nodeBase = kdNodes.size(), idxBase = kdTriIdx.size();
+	std::vector<std::pair<KDTreeNode*, size_t>> todo; // node, slot
+	kdNodes.push_back( FlatKdNode() );
+	todo.push_back( { root, nodeBase } );
+	while (!todo.empty())
+	{
+		auto it = todo.back();
+		todo.pop_back();
+		KDTreeNode* n = it.first;
+		FlatKdNode f = {};
+		f.aabbMin[0] = n->aabbMin.x, f.aabbMin[1] = n->aabbMin.y, f.aabbMin[2] = n->aabbMin.z;
+		f.aabbMax[0] = n->aabbMax.x, f.aabbMax[1] = n->aabbMax.y, f.aabbMax[2] = n->aabbMax.z;
+		f.splitAxis = n->splitAxis, f.splitDistance = n->splitDistance;
+		f.left = f.right = -1;
+		if (n->isLeaf)
+		{
+			f.triStart = (uint32_t)(kdTriIdx.size() - idxBase), f.triCount = (uint32_t)n->triIndices.size();
+			kdTriIdx.insert( kdTriIdx.end(), n->triIndices.begin(), n->triIndices.end() );
+		}
+		else
+		{
+			f.left = (int32_t)(kdNodes.size() - nodeBase), f.right = f.left + 1;
+			kdNodes.push_back( FlatKdNode() ), kdNodes.push_back( FlatKdNode() );
+			todo.push_back( { n->right, nodeBase + f.right } ), todo.push_back( { n->left, nodeBase + f.left } );
+		}
+		kdNodes[it.second] = f;
+	}
+}
+#endif
+
+#if defined(USE_Grid) || defined(TLAS_USE_Grid)
+} // extern "C" (templates need C++ linkage)
+template <class G> static void flatten_grid( G& g, FlatGridHeader& gh, std::vector<uint>& cellStart, std::vector<uint>& gridTriIdx )
+{
+	const size_t idxBase = gridTriIdx.size();
+	for (int i = 0; i < 3; i++)
+		gh.resolution[i] = g.resolution[i], gh.cellSize[i] = g.cellSize[i], gh.boundsMin[i] = g.localBounds.bmin[i], gh.boundsMax[i] = g.localBounds.bmax[i];
+	for (const GridCell& c : g.gridCells)
+	{
+		cellStart.push_back( (uint)(gridTriIdx.size() - idxBase) );
+		for (int t : c.triIndices) gridTriIdx.push_back( (uint)t );
+	}
+	cellStart.push_back( (uint)(gridTriIdx.size() - idxBase) );
+}
+extern "C" {
+#endif
+
 int ref_flatten( const char* out_path )
 {
 	auto& scene = g_renderer->scene;
@@ -237,36 +294,10 @@ int ref_flatten( const char* out_path )
 	// FileScene as shipped (file_scene.h:10-12): spatial-median KD-tree, pointer nodes, per-leaf index vectors
 	// (kdtree.cpp:45-112).  Flattened depth first: node 0 = root, children by index, leaf lists concatenated.
 	h.kind = 2;
-	struct FlatKdNode { float aabbMin[3]; int32_t left; float aabbMax[3]; int32_t right; int32_t splitAxis; float splitDistance; uint32_t triStart, triCount; };
 	std::vector<FlatKdNode> kdNodes;
 	std::vector<uint> kdTriIdx;
 	{
-		std::vector<std::pair<KDTreeNode*, int>> todo; // node, slot
-		kdNodes.push_back( FlatKdNode() );
-		todo.push_back( { scene.acc.rootNode, 0 } );
-		while (!todo.empty())
-		{
-			auto it = todo.back();
-			todo.pop_back();
-			KDTreeNode* n = it.first;
-			FlatKdNode f = {};
-			f.aabbMin[0] = n->aabbMin.x, f.aabbMin[1] = n->aabbMin.y, f.aabbMin[2] = n->aabbMin.z;
-			f.aabbMax[0] = n->aabbMax.x, f.aabbMax[1] = n->aabbMax.y, f.aabbMax[2] = n->aabbMax.z;
-			f.splitAxis = n->splitAxis, f.splitDistance = n->splitDistance;
-			f.left = f.right = -1;
-			if (n->isLeaf)
-			{
-				f.triStart = (uint32_t)kdTriIdx.size(), f.triCount = (uint32_t)n->triIndices.size();
-				kdTriIdx.insert( kdTriIdx.end(), n->triIndices.begin(), n->triIndices.end() );
-			}
-			else
-			{
-				f.left = (int32_t)kdNodes.size(), f.right = f.left + 1;
-				kdNodes.push_back( FlatKdNode() ), kdNodes.push_back( FlatKdNode() );
-				todo.push_back( { n->right, f.right } ), todo.push_back( { n->left, f.left } );
-			}
-			kdNodes[it.second] = f;
-		}
+		flatten_kd( scene.acc.rootNode, kdNodes, kdTriIdx );
 		FlatBlas b = {};
 		b.tri_count = (uint32_t)scene.acc.triangles.size();
 		mat4 I;
@@ -281,18 +312,11 @@ int ref_flatten( const char* out_path )
 #elif defined(REF_SCENE_FILE) && defined(USE_Grid)
 	// FileScene with the uniform grid (grid.cpp:4-60): per-cell index vectors concatenated in cell order
 	h.kind = 3;
-	struct FlatGridHeader { int32_t resolution[3]; float cellSize[3], boundsMin[3], boundsMax[3]; } gh = {};
+	FlatGridHeader gh = {};
 	std::vector<uint> cellStart, gridTriIdx;
 	{
 		Grid& g = scene.acc;
-		for (int i = 0; i < 3; i++)
-			gh.resolution[i] = g.resolution[i], gh.cellSize[i] = g.cellSize[i], gh.boundsMin[i] = g.localBounds.bmin[i], gh.boundsMax[i] = g.localBounds.bmax[i];
-		for (const GridCell& c : g.gridCells)
-		{
-			cellStart.push_back( (uint)gridTriIdx.size() );
-			for (int t : c.triIndices) gridTriIdx.push_back( (uint)t );
-		}
-		cellStart.push_back( (uint)gridTriIdx.size() );
+		flatten_grid( g, gh, cellStart, gridTriIdx );
 		FlatBlas b = {};
 		b.tri_count = (uint32_t)g.triangles.size();
 		mat4 I;
@@ -319,6 +343,54 @@ int ref_flatten( const char* out_path )
 		triIdx = scene.acc.triangleIndices;
 		for (auto* m : scene.models) objMaterial.push_back( m->matIdx );
 	}
+#elif defined(TLAS_USE_KDTree)
+	// TLASFileScene over per-object KD-trees: the same agglomerative TLAS (tlas_kdtree.cpp:17-70), BLASKDTree leaves
+	h.kind = 4;
+	std::vector<FlatKdNode> kdNodes;
+	std::vector<uint> kdTriIdx;
+	std::vector<FlatBlasKd> kdTable;
+	for (BLASKDTree* blas : scene.tlas.blas)
+	{
+		FlatBlas b = {};
+		b.tri_offset = (uint32_t)tris.size(), b.tri_count = (uint32_t)blas->triangles.size();
+		memcpy( b.T, blas->T.cell, 64 ), memcpy( b.invT, blas->invT.cell, 64 );
+		b.obj_idx = blas->objIdx, b.mat_idx = blas->matIdx;
+		blasTable.push_back( b );
+		FlatBlasKd k = { (uint32_t)kdNodes.size(), 0, (uint32_t)kdTriIdx.size(), 0 };
+		flatten_kd( blas->rootNode, kdNodes, kdTriIdx );
+		k.node_count = (uint32_t)kdNodes.size() - k.node_offset, k.idx_count = (uint32_t)kdTriIdx.size() - k.idx_offset;
+		kdTable.push_back( k );
+		tris.insert( tris.end(), blas->triangles.begin(), blas->triangles.end() );
+		objMaterial.push_back( blas->matIdx );
+	}
+	w.chunk( "tlas_nodes", scene.tlas.tlasNode, sizeof( TLASKDTreeNode ) * scene.tlas.nodesUsed );
+	w.chunk( "blas_kd_table", kdTable.data(), kdTable.size() * sizeof( FlatBlasKd ) );
+	w.chunk( "kd_nodes", kdNodes.data(), kdNodes.size() * sizeof( FlatKdNode ) );
+	w.chunk( "kd_tri_indices", kdTriIdx.data(), kdTriIdx.size() * sizeof( uint ) );
+#elif defined(TLAS_USE_Grid)
+	// TLASFileScene over per-object uniform grids (tlas_grid.cpp:17-70, blas_grid.cpp)
+	h.kind = 5;
+	std::vector<uint> cellStart, gridTriIdx;
+	std::vector<FlatBlasGrid> gridTable;
+	for (BLASGrid* blas : scene.tlas.blas)
+	{
+		FlatBlas b = {};
+		b.tri_offset = (uint32_t)tris.size(), b.tri_count = (uint32_t)blas->triangles.size();
+		memcpy( b.T, blas->T.cell, 64 ), memcpy( b.invT, blas->invT.cell, 64 );
+		b.obj_idx = blas->objIdx, b.mat_idx = blas->matIdx;
+		blasTable.push_back( b );
+		FlatBlasGrid g = {};
+		g.cell_offset = (uint32_t)cellStart.size(), g.idx_offset = (uint32_t)gridTriIdx.size();
+		flatten_grid( *blas, g.h, cellStart, gridTriIdx );
+		g.cell_count = (uint32_t)cellStart.size() - g.cell_offset - 1, g.idx_count = (uint32_t)gridTriIdx.size() - g.idx_offset;
+		gridTable.push_back( g );
+		tris.insert( tris.end(), blas->triangles.begin(), blas->triangles.end() );
+		objMaterial.push_back( blas->matIdx );
+	}
+	w.chunk( "tlas_nodes", scene.tlas.tlasNode, sizeof( TLASGridNode ) * scene.tlas.nodesUsed );
+	w.chunk( "blas_grid_table", gridTable.data(), gridTable.size() * sizeof( FlatBlasGrid ) );
+	w.chunk( "grid_cell_start", cellStart.data(), cellStart.size() * sizeof( uint ) );
+	w.chunk( "grid_tri_indices", gridTriIdx.data(), gridTriIdx.size() * sizeof( uint ) );
 #else
 	h.kind = 1;
 	for (BLASBVH* blas : scene.tlas.blas)

@@ -36,7 +36,7 @@ def scene_path(name):
 
 
 def all_scene_names():
-    return ["golden_file", "golden_tlas", "golden_kd", "golden_grid"] + baked_scenes()
+    return ["golden_file", "golden_tlas", "golden_kd", "golden_grid", "golden_tlas_kd", "golden_tlas_grid"] + baked_scenes()
 
 
 @pytest.fixture(scope="session")
@@ -105,8 +105,10 @@ def random_rays(flat, n, seed):
         D[axis * k:(axis + 1) * k, axis] = 0.0
     D[3 * k:4 * k] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, k)] * rng.choice([-1.0, 1.0], (k, 1)).astype(np.float32)
     # origins exactly on node-box planes: 0 * inf = NaN in the slab test
-    if flat.kind == 2:      # KD-tree: node boxes (a split plane is the max / min of the two children)
+    if flat.kind in (2, 4): # KD-tree(s): node boxes (a split plane is the max / min of the two children); kind 4: object space
         planes = flat.kd_nodes["aabb_min"]
+    elif flat.kind == 5:    # per-object grids: TLAS node boxes
+        planes = flat.tlas_nodes["aabb_min"]
     elif flat.kind == 3:    # grid: cell corners
         g = flat.grid_header[0]
         ijk = np.stack([rng.integers(0, int(r) + 1, 4 * k) for r in g["resolution"]], 1)

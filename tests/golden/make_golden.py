@@ -2,8 +2,9 @@
 """Generate the committed golden vectors from the REFERENCE'S OWN CODE (oracle/_ref, built headless).
 
 Run here (where /root/reference is mounted):   python tests/golden/make_golden.py
-Outputs, per scene kind k in {file, tlas, kd, grid} (FileScene+USE_BVH / TLASFileScene+TLAS_USE_BVH /
-FileScene+USE_KDTree as shipped / FileScene+USE_Grid); `make_golden.py kd grid` regenerates only those:
+Outputs, per scene kind k in {file, tlas, kd, grid, tlas_kd, tlas_grid} (FileScene+USE_BVH / TLASFileScene+TLAS_USE_BVH /
+FileScene+USE_KDTree as shipped / FileScene+USE_Grid / TLASFileScene+TLAS_USE_KDTree / +TLAS_USE_Grid);
+`make_golden.py kd grid` regenerates only those:
   tests/golden/golden_<k>.rtscene.gz   the reference's flattened scene (inputs)
   tests/golden/golden_<k>.npz          what the reference computed on it:
       cam_*            two cameras (default, look-at) as 4x3 (camPos, topLeft, topRight, bottomLeft)
@@ -32,7 +33,7 @@ def main():
     import cpu_ray_tracer_b200 as rtb
     from cpu_ray_tracer_b200 import api
 
-    libkind = {"file": "file", "tlas": "tlas", "kd": "file_kd", "grid": "file_grid"}
+    libkind = {"file": "file", "tlas": "tlas", "kd": "file_kd", "grid": "file_grid", "tlas_kd": "tlas_kd", "tlas_grid": "tlas_grid"}
     for kind in (sys.argv[1:] or list(libkind)):
         out = {}
         wh = RefRenderer("whitted", libkind[kind], "golden_scene.xml", W, H)
@@ -40,7 +41,13 @@ def main():
         scene_path = os.path.join(HERE, f"golden_{kind}.rtscene")
         pt.flatten(scene_path)
         fs = rtb.FlatScene.load(scene_path)
-        fs.save(scene_path + ".gz")
+        if kind == "tlas_kd":
+            # 430 804 KD nodes for 3 852 triangles (4.4 MB gzipped): the fixture keeps triangles / transforms / TLAS and the
+            # loader rebuilds the per-object trees (FlatScene.rebuild_blas_kdtrees); the vectors below still pin every hit
+            # and every traversed / tested counter the reference produced on ITS trees
+            fs.save_without_kdtrees(scene_path + ".gz")
+        else:
+            fs.save(scene_path + ".gz")
         os.remove(scene_path)
         for c in (0, 1):
             if c == 1:

@@ -18,7 +18,9 @@ WHITTED_TOL = 2e-5
 CASES = [("pt", "file", "wok_teapot_scene.xml"), ("pt", "tlas", "inside_scene.xml"),
          ("whitted", "file", "bunny_scene.xml"), ("whitted", "tlas", "instanced_scene.xml"),
          # FileScene exactly as the reference ships it (KD-tree), and with its grid
-         ("pt", "file_kd", "wok_teapot_scene.xml"), ("whitted", "file_grid", "bunny_scene.xml")]
+         ("pt", "file_kd", "wok_teapot_scene.xml"), ("whitted", "file_grid", "bunny_scene.xml"),
+         # TLASFileScene over per-object KD-trees / grids
+         ("whitted", "tlas_kd", "instanced_scene.xml"), ("pt", "tlas_grid", "inside_scene.xml")]
 
 
 def test_adapter_header_cites_and_covers_the_surface():

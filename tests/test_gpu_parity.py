@@ -210,7 +210,7 @@ def test_path_tracer_vs_oracle_reference_rng(name, schedule, oracles, gpu_scenes
 
 
 @pytest.mark.parametrize("schedule", [abi.RT_SCHEDULE_STREAMS, abi.RT_SCHEDULE_WAVEFRONT], ids=["streams", "wavefront"])
-@pytest.mark.parametrize("name", ["golden_file", "golden_tlas", "golden_kd", "golden_grid"])
+@pytest.mark.parametrize("name", ["golden_file", "golden_tlas", "golden_kd", "golden_grid", "golden_tlas_kd", "golden_tlas_grid"])
 def test_path_tracer_passes(name, schedule, oracles, gpu_scenes):
     """Renderer::passes > 1: consecutive samples per pixel from the tile's stream, spp advancing by `passes` per Tick"""
     from cpu_ray_tracer_b200 import api
@@ -235,7 +235,7 @@ def test_path_tracer_passes(name, schedule, oracles, gpu_scenes):
     r.close()
 
 
-@pytest.mark.parametrize("kind", ["file", "tlas", "kd", "grid"])
+@pytest.mark.parametrize("kind", ["file", "tlas", "kd", "grid", "tlas_kd", "tlas_grid"])
 def test_integrators_vs_committed_golden(kind, oracles, gpu_scenes):
     """the vectors the reference's own build produced (tests/golden/make_golden.py), second camera too"""
     from cpu_ray_tracer_b200 import api

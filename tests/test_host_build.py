@@ -17,22 +17,39 @@ def _is_alt(name):
     return name.endswith(("_kd", "_grid"))
 
 
-@pytest.mark.parametrize("name", [n for n in all_scene_names() if n.endswith("_kd")])
+@pytest.mark.parametrize("name", [n for n in all_scene_names() if n.endswith("_kd") and n != "golden_tlas_kd"])
 def test_kdtree_builder_matches_reference(name, flat_scenes):
-    """KDTree::Build restated on the host: same nodes (boxes, split axis / distance, links), same leaf lists"""
+    """KDTree::Build / BLASKDTree::Build restated on the host: same nodes (boxes, split axis / distance, links), same
+    leaf lists, per object for TLAS scenes (golden_tlas_kd is excluded: its trees are rebuilt by this very builder)"""
     fs = flat_scenes(name)
-    nodes, idx, depth = host_build.build_kdtree(fs.tris)
-    assert depth <= 20 and len(nodes) == len(fs.kd_nodes)
-    assert raw_equal(nodes, fs.kd_nodes), "KD nodes differ from KDTree::Build"
-    assert raw_equal(idx, fs.kd_tri_indices), "KD leaf lists differ"
+    if fs.blas_kd_table is None:
+        nodes, idx, depth = host_build.build_kdtree(fs.tris)
+        assert depth <= 20 and len(nodes) == len(fs.kd_nodes)
+        assert raw_equal(nodes, fs.kd_nodes), "KD nodes differ from KDTree::Build"
+        assert raw_equal(idx, fs.kd_tri_indices), "KD leaf lists differ"
+        return
+    for b, k in zip(fs.blas_table, fs.blas_kd_table):
+        t0, tn = int(b["tri_offset"]), int(b["tri_count"])
+        nodes, idx, _ = host_build.build_kdtree(fs.tris[t0:t0 + tn])
+        n0, nn, i0, ni = (int(k[f]) for f in ("node_offset", "node_count", "idx_offset", "idx_count"))
+        assert raw_equal(nodes, fs.kd_nodes[n0:n0 + nn]) and raw_equal(idx, fs.kd_tri_indices[i0:i0 + ni])
 
 
 @pytest.mark.parametrize("name", [n for n in all_scene_names() if n.endswith("_grid")])
 def test_grid_builder_matches_reference(name, flat_scenes):
     fs = flat_scenes(name)
-    hdr, start, idx = host_build.build_grid(fs.tris)
-    assert raw_equal(hdr, fs.grid_header), "resolution / cell size / bounds differ from Grid::Build"
-    assert raw_equal(start, fs.grid_cell_start) and raw_equal(idx, fs.grid_tri_indices)
+    if fs.blas_grid_table is None:
+        hdr, start, idx = host_build.build_grid(fs.tris)
+        assert raw_equal(hdr, fs.grid_header), "resolution / cell size / bounds differ from Grid::Build"
+        assert raw_equal(start, fs.grid_cell_start) and raw_equal(idx, fs.grid_tri_indices)
+        return
+    for b, g in zip(fs.blas_table, fs.blas_grid_table):
+        t0, tn = int(b["tri_offset"]), int(b["tri_count"])
+        hdr, start, idx = host_build.build_grid(fs.tris[t0:t0 + tn])
+        for f in ("resolution", "cell_size", "bounds_min", "bounds_max"):
+            assert raw_equal(np.ascontiguousarray(hdr[0][f]), np.ascontiguousarray(g[f])), f
+        c0, cn, i0, ni = (int(g[f]) for f in ("cell_offset", "cell_count", "idx_offset", "idx_count"))
+        assert raw_equal(start, fs.grid_cell_start[c0:c0 + cn + 1]) and raw_equal(idx, fs.grid_tri_indices[i0:i0 + ni])
 
 
 def test_with_accelerator_rebuilds_the_same_scene(flat_scenes):
@@ -58,14 +75,22 @@ def test_sah_builder_matches_reference(name, flat_scenes):
         assert np.array_equal(nodes["left_first"], ref["left_first"]) and np.array_equal(nodes["tri_count"], ref["tri_count"])
 
 
-@pytest.mark.parametrize("name", [n for n in all_scene_names() if n.endswith("tlas")])
+@pytest.mark.parametrize("name", [n for n in all_scene_names() if "tlas" in n])
 def test_tlas_builder_and_transforms_match_reference(name, flat_scenes):
+    """the agglomerative TLAS is the same for all three BLAS kinds; the leaf boxes are the BLAS' local bounds under T"""
     fs = flat_scenes(name)
     bounds = []
-    for b in fs.blas_table:
+    for i, b in enumerate(fs.blas_table):
         assert biteq(host_build.invert_rigid(b["T"]), b["inv_T"]), "FastInvertedTransformNoScale"
-        root = fs.nodes[int(b["node_offset"])]
-        bounds.append(host_build.world_bounds(root["aabb_min"], root["aabb_max"], b["T"]))
+        if fs.blas_kd_table is not None:
+            root = fs.kd_nodes[int(fs.blas_kd_table[i]["node_offset"])]
+            lo, hi = root["aabb_min"], root["aabb_max"]
+        elif fs.blas_grid_table is not None:
+            lo, hi = fs.blas_grid_table[i]["bounds_min"], fs.blas_grid_table[i]["bounds_max"]
+        else:
+            root = fs.nodes[int(b["node_offset"])]
+            lo, hi = root["aabb_min"], root["aabb_max"]
+        bounds.append(host_build.world_bounds(lo, hi, b["T"]))
     tlas = host_build.build_tlas(np.array(bounds))
     assert len(tlas) == len(fs.tlas_nodes)
     for f in ("aabb_min", "aabb_max"):

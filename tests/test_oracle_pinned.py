@@ -23,7 +23,7 @@ def cam_from(po, g, c, W, H):
     return cam
 
 
-@pytest.mark.parametrize("kind", ["file", "tlas", "kd", "grid"])
+@pytest.mark.parametrize("kind", ["file", "tlas", "kd", "grid", "tlas_kd", "tlas_grid"])
 @pytest.mark.parametrize("c", [0, 1])
 def test_oracle_find_nearest_vs_golden(oracles, kind, c):
     g = golden(kind)
@@ -36,7 +36,7 @@ def test_oracle_find_nearest_vs_golden(oracles, kind, c):
         assert biteq(hits[ours], g[f"prim{c}_{theirs}"]), ours
 
 
-@pytest.mark.parametrize("kind", ["file", "tlas", "kd", "grid"])
+@pytest.mark.parametrize("kind", ["file", "tlas", "kd", "grid", "tlas_kd", "tlas_grid"])
 def test_oracle_occlusion_and_shading_vs_golden(oracles, kind):
     g = golden(kind)
     W, H, _ = (int(x) for x in g["meta"])
@@ -51,7 +51,7 @@ def test_oracle_occlusion_and_shading_vs_golden(oracles, kind):
     assert biteq(N, g["info_N"]) and biteq(uv, g["info_uv"]) and biteq(albedo, g["info_albedo"])
 
 
-@pytest.mark.parametrize("kind", ["file", "tlas", "kd", "grid"])
+@pytest.mark.parametrize("kind", ["file", "tlas", "kd", "grid", "tlas_kd", "tlas_grid"])
 @pytest.mark.parametrize("c", [0, 1])
 def test_oracle_integrators_vs_golden(oracles, kind, c):
     from oracle import porthost
@@ -84,14 +84,17 @@ def test_oracle_pt_frame_split_is_exact(oracles):
 # ---- live reference (only where oracle/_ref was built, i.e. where /root/reference is mounted) ----
 def _ref_available():
     from oracle import refhost
-    return all(refhost.available(i, k) for i in ("pt", "whitted") for k in ("file", "tlas", "file_kd", "file_grid"))
+    return all(refhost.available(i, k) for i in ("pt", "whitted") for k in ("file", "tlas", "file_kd", "file_grid", "tlas_kd", "tlas_grid"))
 
 
 LIVE = [("pt", "file", "wok_teapot_scene.xml", "wok_teapot_flat"), ("whitted", "file", "bunny_scene.xml", "bunny_flat"),
         ("pt", "tlas", "inside_scene.xml", "inside_tlas"), ("whitted", "tlas", "instanced_scene.xml", "instanced_tlas"),
         # FileScene with the KD-tree it ships with (file_scene.h:10-12) and with the uniform grid
         ("pt", "file_kd", "wok_teapot_scene.xml", "wok_teapot_kd"), ("whitted", "file_kd", "bunny_scene.xml", "bunny_kd"),
-        ("pt", "file_grid", "wok_teapot_scene.xml", "wok_teapot_grid"), ("whitted", "file_grid", "inside_scene.xml", "inside_grid")]
+        ("pt", "file_grid", "wok_teapot_scene.xml", "wok_teapot_grid"), ("whitted", "file_grid", "inside_scene.xml", "inside_grid"),
+        # TLASFileScene over per-object KD-trees / grids
+        ("pt", "tlas_kd", "instanced_scene.xml", "instanced_tlas_kd"), ("whitted", "tlas_kd", "instanced_scene.xml", "instanced_tlas_kd"),
+        ("pt", "tlas_grid", "inside_scene.xml", "inside_tlas_grid"), ("whitted", "tlas_grid", "inside_scene.xml", "inside_tlas_grid")]
 
 
 @pytest.mark.parametrize("integ,kind,xml,baked", LIVE)
