@@ -821,6 +821,166 @@ __device__ __forceinline__ void accel_traverse(const DScene& s, const float3 O, 
     else run_cursor<typename CursorOf<ACCEL>::type, ANYHIT, COUNTERS>(s, O, D, hit);
 }
 
+// One interior-node visit of the ordered traversal (bvh.cpp:242-257) on register state: both child boxes from one
+// 64-byte record, near child first, left on ties, far child pushed only when hit; selects instead of branches.
+template <bool EXACT>
+__device__ __forceinline__ void node_step(const float4* __restrict__ nodes, const float3 O, const float3 rD, const float ht,
+    int* stack, int& sp, int& cur, bool& end)
+{
+    const float4* nd = nodes + 4 * (size_t)cur;
+    const float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2);
+    const int4 n3 = __ldg((const int4*)(nd + 3));
+    const float a1 = slab(O, rD, ht, EXACT, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y);
+    const float a2 = slab(O, rD, ht, EXACT, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w);
+    const bool swp = a1 > a2;
+    const float d1 = swp ? a2 : a1, d2 = swp ? a1 : a2;
+    const int c1 = swp ? n3.y : n3.x, c2 = swp ? n3.x : n3.y;
+    const bool miss = d1 == 1e30f, both = !miss && d2 != 1e30f;
+    const int top = stack[sp > 0 ? sp - 1 : 0];
+    if (both) stack[sp] = c2;
+    end = miss && sp == 0;
+    cur = miss ? top : c1;
+    sp += both ? 1 : (miss && sp > 0 ? -1 : 0);
+}
+
+// trace_queue with a warp vote, the schedule of the path tracer's stream kernel applied to ray queues: every iteration the
+// warp runs ONE action - interior-node visits (repeated while >= 3/4 of the lanes that entered are still on interior nodes)
+// or leaf / instance steps - whichever more lanes wait for, instead of serialising both inside every iteration.
+// Same per-ray visiting order, same refill rule, same Src interface as trace_queue<>.
+template <bool ANYHIT, bool COUNTERS, class Src>
+__device__ __forceinline__ void trace_queue_voted(const DScene& s, Src& src, const int n, int* __restrict__ fetchCounter)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const float4* __restrict__ nodes = s.nodes;
+    const float4* __restrict__ tris = s.tris;
+    int stack[STACK_SIZE];
+    int sp = 0, cur = 0, rayIdx = -1, instObj = s.flat_obj_idx;
+    float3 O = f3(0, 0, 0), D = f3(0, 0, 0), rD = f3(0, 0, 0);
+    bool exact = false, has = false, queueEmpty = false;
+    HitRec hit;
+    hit.t = 0, hit.u = 0, hit.v = 0, hit.obj = -1, hit.tri = -1, hit.traversed = 0, hit.tested = 0;
+    while (true)
+    {
+        const unsigned idle = __ballot_sync(FULL, !has);
+        if (idle == FULL && queueEmpty) break;
+        if (!queueEmpty && (idle == FULL || __popc(idle) >= REFILL_LANES))
+        {
+            const int nIdle = __popc(idle);
+            const int leader = __ffs(idle) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(fetchCounter, nIdle);
+            base = __shfl_sync(FULL, base, leader);
+            if (base + nIdle >= n) queueEmpty = true;
+            if (!has)
+            {
+                const int i = base + __popc(idle & ((1u << lane) - 1));
+                float tmax;
+                if (i < n && src.load(i, O, D, tmax))
+                {
+                    rayIdx = i, has = true;
+                    // FindNearest prologue: light quad, floor plane (file_scene.cpp:172-173); IsOccluded: quad only
+                    hit.t = tmax, hit.u = 0, hit.v = 0, hit.obj = -1, hit.tri = -1, hit.traversed = 0, hit.tested = 0;
+                    float tq;
+                    bool done = false;
+                    if (ANYHIT)
+                    {
+                        if (quad_test(s, O, D, tmax, tq)) hit.obj = 0, done = true;
+                        hit.t = 1e34f;
+                    }
+                    else
+                    {
+                        if (quad_test(s, O, D, hit.t, tq)) hit.t = tq, hit.obj = 0;
+                        const float3 N = f3(s.floor_n[0], s.floor_n[1], s.floor_n[2]);
+                        const float tp = -(dot(O, N) + s.floor_d) / (dot(D, N));
+                        if (tp < hit.t && tp > 0) hit.t = tp, hit.obj = 1;
+                    }
+                    if (done) { src.store(rayIdx, hit); has = false; }
+                    else
+                    {
+                        rD = recip(D), exact = needs_exact_slab(O, D);
+                        sp = 0, cur = s.root_ref, instObj = s.flat_obj_idx;
+                    }
+                }
+            }
+            continue;
+        }
+        const int nN = __popc(__ballot_sync(FULL, has && cur >= 0)), nL = __popc(__ballot_sync(FULL, has && cur < 0));
+        if (nN >= nL)
+        {
+            const int keep = nN - (nN >> 2);
+            bool inNode = has && cur >= 0;
+            const bool anyExact = __any_sync(FULL, inNode && exact);
+            do
+            {
+                if (inNode)
+                {
+                    if (COUNTERS) hit.traversed++;
+                    bool end;
+                    if (anyExact) node_step<true>(nodes, O, rD, hit.t, stack, sp, cur, end);
+                    else node_step<false>(nodes, O, rD, hit.t, stack, sp, cur, end);
+                    if (end) src.store(rayIdx, hit), has = false;
+                    inNode = !end && cur >= 0;
+                }
+            } while (__popc(__ballot_sync(FULL, inNode)) >= keep);
+        }
+        else if (has && cur < 0)
+        {
+            const int payload = ~cur;
+            bool pop = true;
+            if (payload == SENTINEL_PAYLOAD)
+            {
+                src.world(rayIdx, O, D); // blas_bvh.cpp:385-388
+                rD = recip(D), exact = needs_exact_slab(O, D);
+            }
+            else if (payload & INSTANCE_BIT)
+            {
+                if (COUNTERS) hit.traversed++, hit.tested = 0;
+                const float4* I = s.inst + 4 * (size_t)(payload & ~INSTANCE_BIT);
+                const float4 r0 = __ldg(I), r1 = __ldg(I + 1), r2 = __ldg(I + 2);
+                const int4 meta = __ldg((const int4*)(I + 3));
+                const float3 wO = O, wD = D; // in world space here: instances do not nest
+                O = f3((wO.x * r0.x + wO.y * r0.y) + (wO.z * r0.z + r0.w),
+                       (wO.x * r1.x + wO.y * r1.y) + (wO.z * r1.z + r1.w),
+                       (wO.x * r2.x + wO.y * r2.y) + (wO.z * r2.z + r2.w));
+                D = f3((wD.x * r0.x + wD.y * r0.y) + wD.z * r0.z,
+                       (wD.x * r1.x + wD.y * r1.y) + wD.z * r1.z,
+                       (wD.x * r2.x + wD.y * r2.y) + wD.z * r2.z);
+                rD = recip(D), exact = needs_exact_slab(O, D);
+                instObj = meta.y;
+                stack[sp++] = ~SENTINEL_PAYLOAD;
+                cur = meta.x;
+                pop = false;
+            }
+            else
+            {
+                if (COUNTERS) hit.traversed++;
+                int slot = payload;
+                while (true)
+                {
+                    const float4* T = tris + 3 * (size_t)slot;
+                    const float4 t0 = __ldg(T), t1 = __ldg(T + 1), t2 = __ldg(T + 2);
+                    const int tag = __float_as_int(t0.w);
+                    if (COUNTERS) hit.tested++;
+                    if (intersect_tri(O, D, f3(t0.x, t0.y, t0.z), f3(t1.x, t1.y, t1.z), f3(t2.x, t2.y, t2.z), hit.t, hit.u, hit.v))
+                    {
+                        hit.tri = tag & ~LAST_BIT;
+                        hit.obj = instObj >= 0 ? instObj : __float_as_int(t1.w);
+                        if (ANYHIT) { sp = 0; break; }
+                    }
+                    if (tag & LAST_BIT) break;
+                    slot++;
+                }
+            }
+            if (pop)
+            {
+                if (sp == 0) src.store(rayIdx, hit), has = false;
+                else cur = stack[--sp];
+            }
+        }
+    }
+}
+
 // Persistent-warp traversal with ray replacement for the cursor accelerators: the KD-tree / grid counterpart of
 // trace_queue<> above (same Src interface, same refill rule).  Lanes are IDLE, advancing (TRAV) or inside a triangle
 // run (TRI); the warp executes the action most lanes wait for and repeats it while >= 3/4 of them stay in that state.
@@ -908,11 +1068,14 @@ __device__ __forceinline__ void trace_queue_cursor(const DScene& s, Src& src, co
     }
 }
 
-// the persistent-warp queue traversal of the accelerator a kernel is compiled for
-template <int ACCEL, bool ANYHIT, bool COUNTERS, class Src>
+// the persistent-warp queue traversal of the accelerator a kernel is compiled for (VOTED: trace_queue_voted for the BVH;
+// measured +3..13 % on incoherent closest-hit queues and -5..17 % on coherent and any-hit ones, so it is opt-in:
+// profiles/r1_ray_queue_voted_vs_plain.txt)
+template <int ACCEL, bool ANYHIT, bool COUNTERS, class Src, bool VOTED = false>
 __device__ __forceinline__ void accel_trace_queue(const DScene& s, Src& src, const int n, int* __restrict__ fetchCounter)
 {
-    if (ACCEL == ACCEL_BVH) trace_queue<ANYHIT, COUNTERS>(s, src, n, fetchCounter);
+    if (ACCEL == ACCEL_BVH && VOTED) trace_queue_voted<ANYHIT, COUNTERS>(s, src, n, fetchCounter);
+    else if (ACCEL == ACCEL_BVH) trace_queue<ANYHIT, COUNTERS>(s, src, n, fetchCounter);
     else trace_queue_cursor<typename CursorOf<ACCEL>::type, ANYHIT, COUNTERS>(s, src, n, fetchCounter);
 }
 

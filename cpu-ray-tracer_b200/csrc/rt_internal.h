@@ -62,6 +62,6 @@ struct rt_scene {
     static constexpr int FETCH_RING = 256;
     int* fetch_counters = nullptr;
     std::atomic<unsigned> fetch_next{0};
-    bool persistent = true;
+    bool persistent = true, voted = false;
     int* next_fetch_counter() { return fetch_counters + (fetch_next.fetch_add(1) % FETCH_RING); }
 };

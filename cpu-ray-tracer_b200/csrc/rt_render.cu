@@ -703,27 +703,6 @@ __global__ void __launch_bounds__(128) k_pt_streams_alt(const PTState p, const D
     if (lane == 0) atomicAdd(p.counters, rays);
 }
 
-// One interior-node visit of the ordered traversal (bvh.cpp:242-257) on register state: both child boxes from one
-// 64-byte record, near child first, left on ties, far child pushed only when hit; selects instead of branches.
-template <bool EXACT>
-__device__ __forceinline__ void node_step(const float4* __restrict__ nodes, const float3 O, const float3 rD, const float ht,
-    int* stack, int& sp, int& cur, bool& end)
-{
-    const float4* nd = nodes + 4 * (size_t)cur;
-    const float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2);
-    const int4 n3 = __ldg((const int4*)(nd + 3));
-    const float a1 = slab(O, rD, ht, EXACT, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y);
-    const float a2 = slab(O, rD, ht, EXACT, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w);
-    const bool swp = a1 > a2;
-    const float d1 = swp ? a2 : a1, d2 = swp ? a1 : a2;
-    const int c1 = swp ? n3.y : n3.x, c2 = swp ? n3.x : n3.y;
-    const bool miss = d1 == 1e30f, both = !miss && d2 != 1e30f;
-    const int top = stack[sp > 0 ? sp - 1 : 0];
-    if (both) stack[sp] = c2;
-    end = miss && sp == 0;
-    cur = miss ? top : c1;
-    sp += both ? 1 : (miss && sp > 0 ? -1 : 0);
-}
 
 // Stream kernel, version 5 = version 2 (one stream per lane, state in registers, ballot vote) with what the
 // source-level profile of version 2 asked for (tools/ncu_source_hot.py on profiles/r1_v4_*):

@@ -82,18 +82,18 @@ struct AbiSrc {
     }
 };
 
-template <bool COUNTERS, int ACCEL>
+template <bool COUNTERS, int ACCEL, bool VOTED>
 __global__ void __launch_bounds__(128) k_find_nearest_persistent(const DScene s, const rt_ray* rays, rt_hit* hits, int n, int* fetch)
 {
     AbiSrc src = { rays, hits, nullptr };
-    accel_trace_queue<ACCEL, false, COUNTERS>(s, src, n, fetch);
+    accel_trace_queue<ACCEL, false, COUNTERS, AbiSrc, VOTED>(s, src, n, fetch);
 }
 
-template <int ACCEL>
+template <int ACCEL, bool VOTED>
 __global__ void __launch_bounds__(128) k_is_occluded_persistent(const DScene s, const rt_ray* rays, uint8_t* out, int n, int* fetch)
 {
     AbiSrc src = { rays, nullptr, out };
-    accel_trace_queue<ACCEL, true, false>(s, src, n, fetch);
+    accel_trace_queue<ACCEL, true, false, AbiSrc, VOTED>(s, src, n, fetch);
 }
 
 
@@ -559,6 +559,7 @@ rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags,
     {
         const char* e = getenv("RT_B200_TRAVERSAL");
         s->persistent = !(e && strcmp(e, "simple") == 0);
+        s->voted = e && strcmp(e, "voted") == 0; // RT_B200_TRAVERSAL=voted: the queue traversal with the stream kernel's action vote (A/B)
     }
 
     DScene& d = s->d;
@@ -603,7 +604,8 @@ rt_status rt_find_nearest_device(rt_scene* s, const rt_ray* d_rays, rt_hit* d_hi
             int* fetch = s->next_fetch_counter();
             RT_CUDA(cudaMemsetAsync(fetch, 0, sizeof(int), (cudaStream_t)stream));
             void (*k)(const DScene, const rt_ray*, rt_hit*, int, int*) = nullptr;
-            RT_FOR_ACCEL(s->d.kind, (k = counters ? k_find_nearest_persistent<true, A> : k_find_nearest_persistent<false, A>));
+            if (s->voted) { RT_FOR_ACCEL(s->d.kind, (k = counters ? k_find_nearest_persistent<true, A, true> : k_find_nearest_persistent<false, A, true>)); }
+            else { RT_FOR_ACCEL(s->d.kind, (k = counters ? k_find_nearest_persistent<true, A, false> : k_find_nearest_persistent<false, A, false>)); }
             k<<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays + off, d_hits + off, m, fetch);
         }
     }
@@ -630,7 +632,8 @@ rt_status rt_is_occluded_device(rt_scene* s, const rt_ray* d_rays, uint8_t* d_ou
             const int m = (int)((n - off) < ((size_t)1 << 30) ? (n - off) : ((size_t)1 << 30));
             int* fetch = s->next_fetch_counter();
             RT_CUDA(cudaMemsetAsync(fetch, 0, sizeof(int), (cudaStream_t)stream));
-            RT_FOR_ACCEL(s->d.kind, (k_is_occluded_persistent<A><<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays + off, d_out + off, m, fetch)));
+            if (s->voted) { RT_FOR_ACCEL(s->d.kind, (k_is_occluded_persistent<A, true><<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays + off, d_out + off, m, fetch))); }
+            else { RT_FOR_ACCEL(s->d.kind, (k_is_occluded_persistent<A, false><<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays + off, d_out + off, m, fetch))); }
         }
     }
     else { RT_FOR_ACCEL(s->d.kind, (k_is_occluded<A><<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays, d_out, n))); }

@@ -70,6 +70,12 @@ class FlatScene:
             setattr(self, name, chunks.get(name))
         self._keep = None
 
+    def copy(self):
+        """deep copy of the arrays (not of the ctypes tables a previous desc() call left behind)"""
+        names = ["header", "blas_table", "nodes", "tris", "tri_indices", "tlas_nodes", "obj_material", "materials",
+                 "tex_table", "tex_pixels"] + [n for n in _OPTIONAL if getattr(self, n) is not None]
+        return FlatScene({n: np.array(getattr(self, n), copy=True) for n in names})
+
     @property
     def kind(self):
         return int(self.header["kind"][0])

@@ -118,7 +118,6 @@ def test_error_behaviour(flat_scenes):
 def test_error_behaviour_kdtree_and_grid_inputs(flat_scenes):
     """malformed flattened KD-trees / grids are rejected with RT_ERR_INVALID and a message, never traversed"""
     import ctypes as C
-    import copy
     from cpu_ray_tracer_b200 import api
     L = api.lib()
     h = C.c_void_p()
@@ -127,26 +126,26 @@ def test_error_behaviour_kdtree_and_grid_inputs(flat_scenes):
         d = fs.desc()
         return L.rt_scene_create(C.byref(d), 0, 0, C.byref(h)), L.rt_last_error()
 
-    kd = copy.deepcopy(flat_scenes("golden_kd"))
+    kd = flat_scenes("golden_kd").copy()
     interior = int(np.argmax(kd.kd_nodes["left"] >= 0))
     kd.kd_nodes["left"][interior] = len(kd.kd_nodes) + 5
     st, msg = create(kd)
     assert st == abi.RT_ERR_INVALID and b"child index" in msg
-    kd = copy.deepcopy(flat_scenes("golden_kd"))
+    kd = flat_scenes("golden_kd").copy()
     kd.kd_tri_indices[0] = len(kd.tris) + 1
     leaf = int(np.argmax((kd.kd_nodes["left"] < 0) & (kd.kd_nodes["tri_count"] > 0) & (kd.kd_nodes["tri_start"] == 0)))
     assert kd.kd_nodes["tri_start"][leaf] == 0
     st, msg = create(kd)
     assert st == abi.RT_ERR_INVALID and b"triangle index" in msg
-    kd = copy.deepcopy(flat_scenes("golden_kd"))
+    kd = flat_scenes("golden_kd").copy()
     kd.kd_nodes["right"][interior] = 0   # a cycle through the root
     st, msg = create(kd)
     assert st == abi.RT_ERR_INVALID and (b"not a tree" in msg or b"deeper" in msg)
-    gr = copy.deepcopy(flat_scenes("golden_grid"))
+    gr = flat_scenes("golden_grid").copy()
     gr.grid_cell_start[3] = len(gr.grid_tri_indices) + 7
     st, msg = create(gr)
     assert st == abi.RT_ERR_INVALID and b"cell range" in msg
-    gr = copy.deepcopy(flat_scenes("golden_grid"))
+    gr = flat_scenes("golden_grid").copy()
     gr.grid_header["resolution"][0][1] = 0
     st, msg = create(gr)
     assert st == abi.RT_ERR_INVALID and b"resolution" in msg
