@@ -67,7 +67,7 @@ class rt_render_params(C.Structure):
     _fields_ = [("integrator", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
                 ("depth_limit", C.c_int32), ("epsilon", C.c_float), ("seed_mode", C.c_int32),
                 ("tile_begin", C.c_int32), ("tile_end", C.c_int32), ("max_frames_in_flight", C.c_int32),
-                ("schedule", C.c_int32), ("lookahead_frames", C.c_int32), ("passes", C.c_int32)]
+                ("schedule", C.c_int32), ("lookahead_frames", C.c_int32), ("passes", C.c_int32), ("tile_step", C.c_int32)]
 
 
 class rt_counters(C.Structure):

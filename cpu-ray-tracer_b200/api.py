@@ -226,7 +226,7 @@ class GpuRenderer:
     """Renderer : TheApp (2. WhittedStyle/renderer.h:41-61, 3. PathTracer/renderer.h:29-53)."""
 
     def __init__(self, scene: GpuScene, integrator, width, height, depthLimit=5, seed_mode=abi.RT_SEED_REFERENCE_TILE,
-                 tile_begin=0, tile_end=0, max_frames_in_flight=0, schedule=abi.RT_SCHEDULE_AUTO, lookahead_frames=0):
+                 tile_begin=0, tile_end=0, max_frames_in_flight=0, schedule=abi.RT_SCHEDULE_AUTO, lookahead_frames=0, tile_step=1):
         self.scene = scene
         self.integrator = integrator
         self.width, self.height = width, height
@@ -237,7 +237,7 @@ class GpuRenderer:
         lib().rt_render_params_default(C.byref(self.params), integrator, width, height)
         self.params.depth_limit = depthLimit
         self.params.seed_mode = seed_mode
-        self.params.tile_begin, self.params.tile_end = tile_begin, tile_end
+        self.params.tile_begin, self.params.tile_end, self.params.tile_step = tile_begin, tile_end, tile_step
         self.params.max_frames_in_flight = max_frames_in_flight
         self.params.schedule = schedule
         self.params.lookahead_frames = lookahead_frames

@@ -43,7 +43,7 @@ struct PTState {
     int iteration;
     float4* accum;
     float4* frameBuf;  // optional: one W x H float4 image per frame of the launch (look-ahead mode), else nullptr
-    int slots, nTiles, tilesX, tileBegin;
+    int slots, nTiles, tilesX, tileBegin, tileStep; // the job's k-th tile is tileBegin + k * tileStep
     int firstSpp, stride;
     int W, H, depthLimit, seedMode;
     int passes;        // Renderer::passes: samples per pixel per frame, consecutive in the tile's stream (renderer.cpp:123)
@@ -60,7 +60,7 @@ __device__ __forceinline__ uint32_t pt_seed(const PTState& p, int tile, int spp)
 // y first, then x (argument evaluation order of the reference build, see oracle/ref_build).
 __device__ __forceinline__ void pt_generate(const PTState& p, const DCamera& cam, int slot, int pix, uint32_t& seed, float3& D)
 {
-    const int tile = p.tileBegin + slot % p.nTiles;
+    const int tile = p.tileBegin + (slot % p.nTiles) * p.tileStep;
     const int tx = tile % p.tilesX, ty = tile / p.tilesX;
     const int x = tx * 16 + (pix & 15), y = ty * 16 + (pix >> 4);
     if (p.seedMode == RT_SEED_PER_PIXEL)
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(256) k_pt_generate(const PTState p, const DCam
 {
     for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < p.slots; slot += gridDim.x * blockDim.x)
     {
-        const int tile = p.tileBegin + slot % p.nTiles;
+        const int tile = p.tileBegin + (slot % p.nTiles) * p.tileStep;
         const int spp = p.firstSpp + (slot / p.nTiles) * p.stride;
         uint32_t seed = pt_seed(p, tile, spp);
         float3 D;
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(128) k_pt_shade(const PTState p, const DScene 
                 const int smp = p.pix[slot]; // index of the NEXT sample; the finished one is smp - 1
                 const int pix = (smp - 1) / p.passes + 1; // pixel after the finished sample's pixel
                 {
-                    const int tile = p.tileBegin + slot % p.nTiles;
+                    const int tile = p.tileBegin + (slot % p.nTiles) * p.tileStep;
                     const int tx = tile % p.tilesX, ty = tile / p.tilesX;
                     const int x = tx * 16 + ((pix - 1) & 15), y = ty * 16 + ((pix - 1) >> 4);
                     float* a = (float*)(p.accum + (x + (size_t)y * p.W)); // renderer.cpp:124: accumulator += float4(sample, 0)
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(128) k_pt_pilot(const PTState p, const DScene 
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     {
         const int k = i / PILOT_PATHS, j = i - k * PILOT_PATHS;
-        const int tile = p.tileBegin + k;
+        const int tile = p.tileBegin + k * p.tileStep;
         const int tx = tile % p.tilesX, ty = tile / p.tilesX;
         uint32_t seed = wang_hash((uint32_t)i * 2654435761u + 12345u) | 1u;
         float3 O = cam.pos;
@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(128) k_pt_streams2(const PTState p, const DSce
             if (state == ST_DEAD && stream < total)
             {
                 const int k = stream / frames, frame = stream - k * frames;
-                tile = p.tileBegin + (tileOrder ? tileOrder[k] : k);
+                tile = p.tileBegin + (tileOrder ? tileOrder[k] : k) * p.tileStep;
                 seed = pt_seed(p, tile, p.firstSpp + frame * p.stride);
                 pix = 0, depth = 0, inside = false;
                 const int tx = tile % p.tilesX, ty = tile / p.tilesX;
@@ -627,7 +627,7 @@ __global__ void __launch_bounds__(128) k_pt_streams_alt(const PTState p, const D
             if (state == SA_DEAD && stream < total)
             {
                 const int k = stream / frames, frame = stream - k * frames;
-                tile = p.tileBegin + (tileOrder ? tileOrder[k] : k);
+                tile = p.tileBegin + (tileOrder ? tileOrder[k] : k) * p.tileStep;
                 seed = pt_seed(p, tile, p.firstSpp + frame * p.stride);
                 pix = 0, depth = 0, inside = false;
                 const int tx = tile % p.tilesX, ty = tile / p.tilesX;
@@ -775,7 +775,7 @@ __global__ void __launch_bounds__(128, MINB) k_pt_streams5(const PTState p, cons
             if (state == ST_DEAD && ((laneMask >> lane) & 1) && stream < total)
             {
                 const int k = stream / frames, frame = stream - k * frames;
-                const int tile = p.tileBegin + (tileOrder ? tileOrder[k] : k);
+                const int tile = p.tileBegin + (tileOrder ? tileOrder[k] : k) * p.tileStep;
                 seed = pt_seed(p, tile, p.firstSpp + frame * p.stride);
                 const int tx = tile % p.tilesX, ty = tile / p.tilesX;
                 tileXY = (tx * 16) | ((ty * 16) << 16);
@@ -917,7 +917,7 @@ __global__ void __launch_bounds__(128, MINB) k_pt_streams5(const PTState p, cons
                     else
                     {
                         state = ST_DEAD;
-                        if (tileCost) atomicAdd(&tileCost[(y0 >> 4) * p.tilesX + (x0 >> 4) - p.tileBegin], (unsigned long long)((unsigned int)clock() - t0));
+                        if (tileCost) atomicAdd(&tileCost[((y0 >> 4) * p.tilesX + (x0 >> 4) - p.tileBegin) / p.tileStep], (unsigned long long)((unsigned int)clock() - t0));
                     }
                 }
             }
@@ -1369,7 +1369,8 @@ static int num_tiles(const rt_render_params& p)
 {
     const int all = (p.width / 16) * (p.height / 16); // renderer.cpp:151 (integer division)
     const int end = p.tile_end > 0 ? (p.tile_end < all ? p.tile_end : all) : all;
-    const int n = end - p.tile_begin;
+    const int step = p.tile_step > 0 ? p.tile_step : 1;
+    const int n = (end - p.tile_begin + step - 1) / step; // tiles tile_begin, tile_begin + step, ... < end
     return n > 0 ? n : 0;
 }
 
@@ -1609,7 +1610,7 @@ static rt_status render_pt_streams(rt_renderer* r, int first_spp, int count, int
     const int nTiles = num_tiles(P);
     PTState p = {};
     p.counters = r->dCounters, p.accum = r->accum, p.frameBuf = frameBuf;
-    p.nTiles = nTiles, p.tilesX = P.width / 16, p.tileBegin = P.tile_begin;
+    p.nTiles = nTiles, p.tilesX = P.width / 16, p.tileBegin = P.tile_begin, p.tileStep = P.tile_step > 0 ? P.tile_step : 1;
     p.W = P.width, p.H = P.height, p.depthLimit = P.depth_limit, p.seedMode = P.seed_mode, p.eps = P.epsilon, p.passes = r->passes;
     p.stride = stride, p.firstSpp = first_spp;
     // all frames of the call form one pool of nTiles x count streams (int range checked by the caller)
@@ -1696,7 +1697,7 @@ static rt_status render_pt(rt_renderer* r, int first_spp, int count, int stride)
     if (st != RT_OK) return st;
     PTState& p = r->pt;
     p.count = r->dCount, p.counters = r->dCounters, p.accum = r->accum;
-    p.nTiles = nTiles, p.tilesX = P.width / 16, p.tileBegin = P.tile_begin;
+    p.nTiles = nTiles, p.tilesX = P.width / 16, p.tileBegin = P.tile_begin, p.tileStep = P.tile_step > 0 ? P.tile_step : 1;
     p.W = P.width, p.H = P.height, p.depthLimit = P.depth_limit, p.seedMode = P.seed_mode, p.eps = P.epsilon, p.passes = r->passes;
     p.stride = stride;
     const int grid = r->sms * 8;

@@ -6,7 +6,9 @@ data-path exchange; the only collective is one reduce of the float4 accumulators
 
   sample-index sharding (default): rank r renders the frames whose reference `spp` counter is
       first_spp + r, first_spp + r + N, ...      (seeds depend on spp: InitSeed(tx + ty*W + spp*1799))
-  tile sharding: rank r renders a contiguous range of the (W/16) x (H/16) row-major tile grid
+  tile sharding: rank r renders every N-th tile of the (W/16) x (H/16) row-major tile grid starting at tile r
+      (interleaved, the default: cost varies across an image, 6.1x -> see profiles/r1_c4_multi_gpu_tile_sharding.jsonl)
+      or a contiguous range of it
 
 Both give, after the sum over ranks, the single-process image up to float reassociation.
 This module is host logic only (no CUDA): the caller supplies the per-rank render function.
@@ -25,6 +27,10 @@ class FrameShard:
 class TileShard:
     tile_begin: int
     tile_end: int
+    tile_step: int = 1
+
+    def tiles(self):
+        return range(self.tile_begin, self.tile_end, self.tile_step)
 
 
 def frame_shard(rank, world, first_spp, frames):
@@ -35,11 +41,13 @@ def frame_shard(rank, world, first_spp, frames):
     return FrameShard(first_spp + rank, count, world)
 
 
-def tile_shard(rank, world, width, height):
-    """contiguous tile ranges whose sizes differ by at most one tile"""
+def tile_shard(rank, world, width, height, interleaved=False):
+    """contiguous tile ranges whose sizes differ by at most one tile, or (interleaved) tiles rank, rank + world, ..."""
     if not 0 <= rank < world:
         raise ValueError(f"rank {rank} outside world {world}")
     tiles = (width // 16) * (height // 16)  # integer division as renderer.cpp:151 (SURVEY Q13)
+    if interleaved:
+        return TileShard(rank, tiles, world)
     base, extra = divmod(tiles, world)
     begin = rank * base + min(rank, extra)
     return TileShard(begin, begin + base + (1 if rank < extra else 0))
@@ -66,7 +74,8 @@ def render_sharded(render_frames, acc, first_spp, frames, mode="frames", width=N
     """Runs this rank's share and reduces onto rank 0.
 
     render_frames(first_spp, count, stride) accumulates into `acc` (a torch tensor the renderer writes to);
-    render_tiles(tile_begin, tile_end, first_spp, count) likewise for mode == "tiles".
+    render_tiles(tile_begin, tile_end, first_spp, count[, tile_step]) likewise for mode == "tiles" (contiguous ranges)
+    and mode == "tiles_interleaved".
     """
     import torch.distributed as dist
     init = dist.is_available() and dist.is_initialized()
@@ -80,6 +89,10 @@ def render_sharded(render_frames, acc, first_spp, frames, mode="frames", width=N
         t = tile_shard(rank, world, width, height)
         if t.tile_end > t.tile_begin:
             render_tiles(t.tile_begin, t.tile_end, first_spp, frames)
+    elif mode == "tiles_interleaved":
+        t = tile_shard(rank, world, width, height, interleaved=True)
+        if t.tile_end > t.tile_begin:
+            render_tiles(t.tile_begin, t.tile_end, first_spp, frames, t.tile_step)
     else:
         raise ValueError(mode)
     return reduce_accumulator(acc)

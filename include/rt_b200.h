@@ -271,6 +271,10 @@ typedef struct rt_render_params {
      * consecutively from the tile's stream (renderer.cpp:123-126); a Tick then advances spp by `passes`, so the frames of
      * a fresh renderer are first_spp = 1, stride = passes.  0 = 1.  ABI v3. */
     int32_t passes;
+    /* Path tracer: render every tile_step-th tile of [tile_begin, tile_end) (0 = 1).  N processes with tile_begin = rank,
+     * tile_step = N split a frame into interleaved tiles, which balances better than contiguous ranges when cost varies
+     * across the image.  ABI v3. */
+    int32_t tile_step;
 } rt_render_params;
 
 enum {

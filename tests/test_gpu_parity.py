@@ -376,6 +376,18 @@ def test_sharding_properties_full_size(gpu_scenes, oracles):
     assert not ((la[..., :3].sum(-1) != 0) & (ha[..., :3].sum(-1) != 0)).any()  # disjoint pixels
     assert np.abs(la + ha - ref).max() <= 1e-4
     lo.close(), hi.close()
+    # interleaved tile sharding (tile_step): three "ranks", both schedules
+    for sched in (abi.RT_SCHEDULE_STREAMS, abi.RT_SCHEDULE_WAVEFRONT):
+        parts = [api.GpuRenderer(sc, abi.RT_INTEGRATOR_PATH, W, H, tile_begin=k, tile_end=tiles, tile_step=3, schedule=sched).Init() for k in range(3)]
+        for q in parts:
+            q.render(4, first_spp=1)
+        assert sum(q.counters()["extension_rays"] for q in parts) == rays_full
+        accs = [q.accumulator for q in parts]
+        hit = sum((x[..., :3].sum(-1) != 0).astype(np.int32) for x in accs)
+        assert hit.max() <= 1                                                         # disjoint pixels
+        assert np.abs(accs[0] + accs[1] + accs[2] - ref).max() <= 1e-4
+        for q in parts:
+            q.close()
     # oracle spot check at full width on the top tile rows
     po = oracles(name)
     from oracle import porthost
@@ -386,19 +398,20 @@ def test_sharding_properties_full_size(gpu_scenes, oracles):
     full.close()
 
 
-def test_simple_traversal_kernels_agree(monkeypatch, oracles, flat_scenes):
-    """RT_B200_TRAVERSAL=simple selects the one-thread-per-ray kernels (kept for A/B profiling); both
-    kernel families must give the oracle's bits"""
+@pytest.mark.parametrize("mode", ["simple", "voted"])
+def test_alternative_traversal_kernels_agree(mode, monkeypatch, oracles, flat_scenes):
+    """RT_B200_TRAVERSAL=simple selects the one-thread-per-ray kernels, =voted the ray-queue traversal with the stream
+    kernel's action vote (both kept for A/B profiling); every kernel family must give the oracle's bits"""
     from cpu_ray_tracer_b200 import api
     from oracle import porthost
-    monkeypatch.setenv("RT_B200_TRAVERSAL", "simple")
-    for name in ("golden_file", "golden_tlas"):
+    monkeypatch.setenv("RT_B200_TRAVERSAL", mode)
+    for name in ("golden_file", "golden_tlas") + (("golden_kd", "golden_tlas_grid") if mode == "simple" else ()):
         po = oracles(name)
         flat = flat_scenes(name)
         sc = api.open_scene(flat, counters=True)
         rays = random_rays(flat, 20000, seed=21)
         ref, _ = po.find_nearest(rays)
-        assert_hits_equal(sc.FindNearest(rays), ref, name + " (simple kernels)")
+        assert_hits_equal(sc.FindNearest(rays), ref, name + f" ({mode} kernels)")
         occ, _ = po.is_occluded(rays)
         assert np.array_equal(sc.IsOccluded(rays), occ)
         W, H = 128, 80

@@ -42,9 +42,9 @@ def _worker(rank, world, port, mode, out_dir):
             _, st = po.render_pt(cam, p, first_spp, count, stride, accumulator=acc)
             rays[0] += st["extension_rays"]
 
-        def render_tiles(tile_begin, tile_end, first_spp, count):
+        def render_tiles(tile_begin, tile_end, first_spp, count, tile_step=1):
             p = porthost.default_params(abi.RT_INTEGRATOR_PATH, W, H)
-            p.tile_begin, p.tile_end = tile_begin, tile_end
+            p.tile_begin, p.tile_end, p.tile_step = tile_begin, tile_end, tile_step
             _, st = po.render_pt(cam, p, first_spp, count, 1, accumulator=acc)
             rays[0] += st["extension_rays"]
 
@@ -59,7 +59,7 @@ def _worker(rank, world, port, mode, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["frames", "tiles"])
+@pytest.mark.parametrize("mode", ["frames", "tiles", "tiles_interleaved"])
 def test_two_rank_sharding_reduces_to_the_single_process_image(mode, tmp_path):
     import torch.multiprocessing as mp
     port = _free_port()
@@ -67,7 +67,7 @@ def test_two_rank_sharding_reduces_to_the_single_process_image(mode, tmp_path):
     z = np.load(tmp_path / f"{mode}.npz")
     assert int(z["rays"]) == int(z["rays_full"])          # the shards trace exactly the job's rays, once
     assert z["full"][..., :3].sum() > 0
-    if mode == "tiles":
+    if mode.startswith("tiles"):
         # disjoint pixels: the sum has nothing to reassociate
         assert np.array_equal(z["sharded"].view(np.uint32), z["full"].view(np.uint32))
     else:
@@ -90,5 +90,8 @@ def test_shard_arithmetic():
             assert all(a.tile_end == b.tile_begin for a, b in zip(shards, shards[1:]))
             sizes = [s.tile_end - s.tile_begin for s in shards]
             assert max(sizes) - min(sizes) <= 1
+            inter = [list(parallel.tile_shard(r, world, w, h, interleaved=True).tiles()) for r in range(world)]
+            assert sorted(t for r in inter for t in r) == list(range(tiles))
+            assert max(len(r) for r in inter) - min(len(r) for r in inter) <= 1
     with pytest.raises(ValueError):
         parallel.frame_shard(2, 2, 1, 4)
