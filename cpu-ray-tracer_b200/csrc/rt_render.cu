@@ -58,17 +58,19 @@ __device__ __forceinline__ uint32_t pt_seed(const PTState& p, int tile, int spp)
 
 // Generates the primary ray of pixel `pix` of the slot's tile (renderer.cpp:121-126): jitter draws
 // y first, then x (argument evaluation order of the reference build, see oracle/ref_build).
-__device__ __forceinline__ void pt_generate(const PTState& p, const DCamera& cam, int slot, int pix, uint32_t& seed, float3& D)
+__device__ __forceinline__ uint32_t pt_pixel_seed(const PTState& p, int x, int y, int spp)
+{
+    uint32_t seed = init_seed((uint32_t)(x + y * p.W) + (uint32_t)spp * 0x9E3779B1u);
+    return seed == 0 ? 0x12345678u : seed;
+}
+
+__device__ __forceinline__ void pt_generate(const PTState& p, const DCamera& cam, int slot, int pix, uint32_t& seed, float3& D, bool firstPass = true)
 {
     const int tile = p.tileBegin + (slot % p.nTiles) * p.tileStep;
     const int tx = tile % p.tilesX, ty = tile / p.tilesX;
     const int x = tx * 16 + (pix & 15), y = ty * 16 + (pix >> 4);
-    if (p.seedMode == RT_SEED_PER_PIXEL)
-    {
-        const int spp = p.firstSpp + (slot / p.nTiles) * p.stride;
-        seed = init_seed((uint32_t)(x + y * p.W) + (uint32_t)spp * 0x9E3779B1u);
-        if (seed == 0) seed = 0x12345678u;
-    }
+    if (p.seedMode == RT_SEED_PER_PIXEL && firstPass) // one stream per pixel per frame, shared by the pixel's `passes` samples
+        seed = pt_pixel_seed(p, x, y, p.firstSpp + (slot / p.nTiles) * p.stride);
     const float jy = random_float(seed);
     const float jx = random_float(seed);
     D = primary_dir(cam, (float)x + jx, (float)y + jy);
@@ -304,7 +306,7 @@ __global__ void __launch_bounds__(128) k_pt_shade(const PTState p, const DScene 
                 if (smp < 256 * p.passes)
                 {
                     float3 gD;
-                    pt_generate(p, cam, slot, smp / p.passes, seed, gD);
+                    pt_generate(p, cam, slot, smp / p.passes, seed, gD, smp % p.passes == 0);
                     p.rayO[slot] = make_float4(cam.pos.x, cam.pos.y, cam.pos.z, 0);
                     p.rayD[slot] = make_float4(gD.x, gD.y, gD.z, __int_as_float(0));
                     p.pix[slot] = smp + 1;
@@ -760,7 +762,8 @@ __global__ void __launch_bounds__(128, MINB) k_pt_streams5(const PTState p, cons
         const unsigned mMiss = __ballot_sync(FULL, state == ST_MISS);
         const unsigned mLive = mNode | mLeaf | mShade | mMiss;
         bool start = false;
-        if ((~mLive & laneMask) != 0 && !poolEmpty)
+        // (per-pixel streams end after every path: refill in batches of >= 8 lanes so that refills do not alternate with actions)
+        if ((~mLive & laneMask) != 0 && !poolEmpty && (p.seedMode != RT_SEED_PER_PIXEL || mLive == 0 || __popc(~mLive & laneMask) >= 8))
         {
             // refill the dead lanes from the stream pool: one atomic per warp.  laneMask caps the streams per warp
             // for small jobs (fewer streams than lanes): a chain runs faster the fewer neighbours it waits for
@@ -774,14 +777,19 @@ __global__ void __launch_bounds__(128, MINB) k_pt_streams5(const PTState p, cons
             const int stream = base + __popc(mDead & ((1u << lane) - 1));
             if (state == ST_DEAD && ((laneMask >> lane) & 1) && stream < total)
             {
-                const int k = stream / frames, frame = stream - k * frames;
+                // RT_SEED_REFERENCE_TILE: a stream is a (tile, frame) pair and runs the tile's 256 pixels; RT_SEED_PER_PIXEL:
+                // a stream is ONE pixel of a (tile, frame) pair (32 consecutive streams = two pixel rows of one tile)
+                const bool perPixel = p.seedMode == RT_SEED_PER_PIXEL;
+                const int unit = perPixel ? stream >> 8 : stream, px0 = perPixel ? stream & 255 : 0;
+                const int k = unit / frames, frame = unit - k * frames;
                 const int tile = p.tileBegin + (tileOrder ? tileOrder[k] : k) * p.tileStep;
-                seed = pt_seed(p, tile, p.firstSpp + frame * p.stride);
                 const int tx = tile % p.tilesX, ty = tile / p.tilesX;
+                const int x = tx * 16 + (px0 & 15), y = ty * 16 + (px0 >> 4);
+                seed = perPixel ? pt_pixel_seed(p, x, y, p.firstSpp + frame * p.stride) : pt_seed(p, tile, p.firstSpp + frame * p.stride);
                 tileXY = (tx * 16) | ((ty * 16) << 16);
-                pix = frame << 12, depth = 0, inside = false; // pix = sample of the tile (12 bits: 256 x passes <= 2048) | frame of the launch << 12
+                pix = (px0 * p.passes) | (frame << 12), depth = 0, inside = false; // pix = sample of the tile (12 bits: 256 x passes <= 2048) | frame of the launch << 12
                 const float jy = random_float(seed), jx = random_float(seed);
-                wD = primary_dir(cam, (float)(tx * 16) + jx, (float)(ty * 16) + jy);
+                wD = primary_dir(cam, (float)x + jx, (float)y + jy);
                 wO = cam.pos;
                 t0 = (unsigned int)clock();
                 start = true;
@@ -906,7 +914,7 @@ __global__ void __launch_bounds__(128, MINB) k_pt_streams5(const PTState p, cons
                         atomicAdd(a + 0, L.x), atomicAdd(a + 1, L.y), atomicAdd(a + 2, L.z);
                     }
                     pix++;
-                    if ((pix & 4095) < 256 * p.passes)
+                    if (p.seedMode == RT_SEED_PER_PIXEL ? (pix & 4095) % p.passes != 0 : (pix & 4095) < 256 * p.passes)
                     {
                         const int nx = (pix & 4095) / p.passes;
                         const float jy = random_float(seed), jx = random_float(seed);
@@ -1613,11 +1621,12 @@ static rt_status render_pt_streams(rt_renderer* r, int first_spp, int count, int
     p.nTiles = nTiles, p.tilesX = P.width / 16, p.tileBegin = P.tile_begin, p.tileStep = P.tile_step > 0 ? P.tile_step : 1;
     p.W = P.width, p.H = P.height, p.depthLimit = P.depth_limit, p.seedMode = P.seed_mode, p.eps = P.epsilon, p.passes = r->passes;
     p.stride = stride, p.firstSpp = first_spp;
-    // all frames of the call form one pool of nTiles x count streams (int range checked by the caller)
-    p.slots = nTiles * count;
+    // all frames of the call form one pool of nTiles x count streams (x 256 with one stream per pixel; int range checked by the caller)
+    const bool perPixel = P.seed_mode == RT_SEED_PER_PIXEL;
+    p.slots = nTiles * count * (perPixel ? 256 : 1);
     RT_CUDA(cudaMemsetAsync(r->dCount + 6, 0, sizeof(int), r->stream));
     const int* order = nullptr;
-    if (r->streamLpt)
+    if (r->streamLpt && !perPixel) // per-pixel streams are one path long: nothing to balance
     {
         rt_status st = pt_tile_order(r, p);
         if (st != RT_OK) return st;
@@ -1646,7 +1655,7 @@ static rt_status render_pt_streams(rt_renderer* r, int first_spp, int count, int
     else k_pt_streams2<false><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
     r->prof_end(RT_STAGE_EXTEND);
     if (clk) r->tileClockRecorded = true, r->lastStreamFrames = count;
-    r->paths += (uint64_t)p.slots * 256 * r->passes;
+    r->paths += (uint64_t)nTiles * count * 256 * r->passes;
     RT_CUDA(cudaGetLastError());
     return RT_OK;
 }
@@ -1656,13 +1665,14 @@ static rt_status render_pt(rt_renderer* r, int first_spp, int count, int stride)
     const rt_render_params& P = r->params;
     const int nTiles = num_tiles(P);
     if (nTiles == 0 || count <= 0) return RT_OK;
-    if (r->useStreams && P.seed_mode == RT_SEED_REFERENCE_TILE && P.depth_limit <= STREAM_MAX_DEPTH
-        && (long long)nTiles * count < (1ll << 30))
+    const long long streamsPerFrame = (long long)nTiles * (P.seed_mode == RT_SEED_PER_PIXEL ? 256 : 1);
+    if (r->useStreams && (P.seed_mode == RT_SEED_REFERENCE_TILE || r->streamKernel == 5) && P.depth_limit <= STREAM_MAX_DEPTH
+        && streamsPerFrame * count < (1ll << 30))
     {
         const int L = P.lookahead_frames;
         // (with passes > 1 a frame image would hold the SUM of a pixel's samples, which the accumulator then receives in
         // one add instead of `passes` adds: not the Tick sequence bit for bit, so look-ahead serves passes == 1 only)
-        if (count == 1 && L > 1 && r->streamKernel == 5 && r->passes == 1 && (long long)nTiles * L < (1ll << 30))
+        if (count == 1 && L > 1 && r->streamKernel == 5 && r->passes == 1 && streamsPerFrame * L < (1ll << 30))
         {
             // one Tick per call: serve the frame from the images rendered ahead, rendering L more when it is not there
             const size_t px = (size_t)P.width * P.height;

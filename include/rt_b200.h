@@ -246,7 +246,8 @@ enum {
      * InitSeed(tx + ty*W + spp*1799), carried serially through the tile's 256 pixels
      * (3. PathTracer/renderer.cpp:117-131).  Every (tile, frame) stream is one wavefront slot. */
     RT_SEED_REFERENCE_TILE = 0,
-    /* one independent stream per pixel per frame (not the reference's sequence; same estimator) */
+    /* one independent stream per pixel per frame (not the reference's sequence; same estimator): no serial chain through
+     * a tile, so every pixel of every frame is its own unit of parallelism */
     RT_SEED_PER_PIXEL = 1
 };
 

@@ -297,18 +297,23 @@ def test_integrators_vs_committed_golden(kind, oracles, gpu_scenes):
         wh.close(), pt.close()
 
 
-def test_path_tracer_per_pixel_seed_mode(oracles, gpu_scenes):
+@pytest.mark.parametrize("schedule", [abi.RT_SCHEDULE_STREAMS, abi.RT_SCHEDULE_WAVEFRONT], ids=["streams", "wavefront"])
+@pytest.mark.parametrize("name,passes", [("golden_file", 1), ("golden_tlas", 2), ("golden_kd", 1)])
+def test_path_tracer_per_pixel_seed_mode(name, passes, schedule, oracles, gpu_scenes):
+    """RT_SEED_PER_PIXEL: one stream per pixel per frame (shared by the pixel's `passes` samples); the stream kernel runs
+    every pixel as its own stream, the wavefront as before"""
     from cpu_ray_tracer_b200 import api
     from oracle import porthost
-    name = "golden_file"
     po, sc = oracles(name), gpu_scenes(name, counters=False)
     W, H, frames = 128, 80, 2
     cam = po.camera_default(W, H)
-    oacc, ost = po.render_pt(cam, porthost.default_params(abi.RT_INTEGRATOR_PATH, W, H, seed_mode=abi.RT_SEED_PER_PIXEL), 1, frames, 1)
-    r = api.GpuRenderer(sc, abi.RT_INTEGRATOR_PATH, W, H, seed_mode=abi.RT_SEED_PER_PIXEL).Init()
+    oacc, ost = po.render_pt(cam, porthost.default_params(abi.RT_INTEGRATOR_PATH, W, H, seed_mode=abi.RT_SEED_PER_PIXEL, passes=passes), 1, frames, passes)
+    r = api.GpuRenderer(sc, abi.RT_INTEGRATOR_PATH, W, H, seed_mode=abi.RT_SEED_PER_PIXEL, schedule=schedule).Init()
+    r.passes = passes
     r.render(frames)
-    assert r.counters()["extension_rays"] == ost["extension_rays"]
-    check_pt(r.accumulator, oacc, frames, "per-pixel seeds")
+    c = r.counters()
+    assert c["extension_rays"] == ost["extension_rays"] and c["paths"] == ost["paths"] == W * H * frames * passes
+    check_pt(r.accumulator, oacc, frames * passes, "per-pixel seeds")
     r.close()
 
 

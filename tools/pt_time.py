@@ -13,7 +13,7 @@ tag = f"kernel={os.environ.get('RT_B200_STREAM_KERNEL', 'default')} sched={os.en
 for name in names:
     fs = rtb.FlatScene.load(os.path.join(ROOT, "oracle", "_ref", "scenes", name + ".rtscene.gz"))
     sc = api.open_scene(fs)
-    r = api.GpuRenderer(sc, abi.RT_INTEGRATOR_PATH, W, H).Init()
+    r = api.GpuRenderer(sc, abi.RT_INTEGRATOR_PATH, W, H, seed_mode=int(os.environ.get("RT_SEED_MODE", "0"))).Init()
     for spp in spps:
         r.render(spp, first_spp=1); r.sync()
         best = 1e9
