@@ -725,7 +725,7 @@ __global__ void __launch_bounds__(128) k_pt_streams_alt(const PTState p, const D
 // SIMD efficiency; throughput grows almost linearly with resident warps.
 enum { ST_MISS = 4 };
 
-template <bool TLAS, int MINB>
+template <bool TLAS, int MINB, bool PERPIXEL>
 __global__ void __launch_bounds__(128, MINB) k_pt_streams5(const PTState p, const DScene s, const DCamera cam,
     const int* __restrict__ tileOrder, const int frames, int* __restrict__ streamCounter, unsigned long long* __restrict__ tileCost, const int keepShift, const unsigned laneMask)
 {
@@ -763,7 +763,7 @@ __global__ void __launch_bounds__(128, MINB) k_pt_streams5(const PTState p, cons
         const unsigned mLive = mNode | mLeaf | mShade | mMiss;
         bool start = false;
         // (per-pixel streams end after every path: refill in batches of >= 8 lanes so that refills do not alternate with actions)
-        if ((~mLive & laneMask) != 0 && !poolEmpty && (p.seedMode != RT_SEED_PER_PIXEL || mLive == 0 || __popc(~mLive & laneMask) >= 8))
+        if ((~mLive & laneMask) != 0 && !poolEmpty && (!PERPIXEL || mLive == 0 || __popc(~mLive & laneMask) >= 8))
         {
             // refill the dead lanes from the stream pool: one atomic per warp.  laneMask caps the streams per warp
             // for small jobs (fewer streams than lanes): a chain runs faster the fewer neighbours it waits for
@@ -779,7 +779,7 @@ __global__ void __launch_bounds__(128, MINB) k_pt_streams5(const PTState p, cons
             {
                 // RT_SEED_REFERENCE_TILE: a stream is a (tile, frame) pair and runs the tile's 256 pixels; RT_SEED_PER_PIXEL:
                 // a stream is ONE pixel of a (tile, frame) pair (32 consecutive streams = two pixel rows of one tile)
-                const bool perPixel = p.seedMode == RT_SEED_PER_PIXEL;
+                const bool perPixel = PERPIXEL;
                 const int unit = perPixel ? stream >> 8 : stream, px0 = perPixel ? stream & 255 : 0;
                 const int k = unit / frames, frame = unit - k * frames;
                 const int tile = p.tileBegin + (tileOrder ? tileOrder[k] : k) * p.tileStep;
@@ -914,7 +914,7 @@ __global__ void __launch_bounds__(128, MINB) k_pt_streams5(const PTState p, cons
                         atomicAdd(a + 0, L.x), atomicAdd(a + 1, L.y), atomicAdd(a + 2, L.z);
                     }
                     pix++;
-                    if (p.seedMode == RT_SEED_PER_PIXEL ? (pix & 4095) % p.passes != 0 : (pix & 4095) < 256 * p.passes)
+                    if (PERPIXEL ? (pix & 4095) % p.passes != 0 : (pix & 4095) < 256 * p.passes)
                     {
                         const int nx = (pix & 4095) / p.passes;
                         const float jy = random_float(seed), jx = random_float(seed);
@@ -1347,10 +1347,16 @@ struct rt_renderer {
 
 // stream kernel version 5: dispatch on (TLAS, min CTAs per SM the register budget is bounded for)
 typedef void (*Streams5Fn)(const PTState, const DScene, const DCamera, const int*, const int, int*, unsigned long long*, const int, const unsigned);
-static Streams5Fn streams5_kernel(bool tlas, int minb)
+template <bool PERPIXEL>
+static Streams5Fn streams5_kernel_for(bool tlas, int minb)
 {
-    if (tlas) return minb <= 6 ? k_pt_streams5<true, 6> : minb >= 8 ? k_pt_streams5<true, 8> : k_pt_streams5<true, 7>;
-    return minb <= 6 ? k_pt_streams5<false, 6> : minb >= 8 ? k_pt_streams5<false, 8> : k_pt_streams5<false, 7>;
+    if (tlas) return minb <= 6 ? k_pt_streams5<true, 6, PERPIXEL> : minb >= 8 ? k_pt_streams5<true, 8, PERPIXEL> : k_pt_streams5<true, 7, PERPIXEL>;
+    return minb <= 6 ? k_pt_streams5<false, 6, PERPIXEL> : minb >= 8 ? k_pt_streams5<false, 8, PERPIXEL> : k_pt_streams5<false, 7, PERPIXEL>;
+}
+// the seed mode is a template argument so that the reference-RNG kernel carries none of the per-pixel stream code
+static Streams5Fn streams5_kernel(bool tlas, int minb, bool perPixel = false)
+{
+    return perPixel ? streams5_kernel_for<true>(tlas, minb) : streams5_kernel_for<false>(tlas, minb);
 }
 
 template <class T>
@@ -1645,7 +1651,7 @@ static rt_status render_pt_streams(rt_renderer* r, int first_spp, int count, int
         if (perWarp < 1) perWarp = 1;
         if (perWarp > 32 || !r->streamLaneCap) perWarp = 32;
         const unsigned laneMask = perWarp >= 32 ? 0xffffffffu : ((1u << perWarp) - 1);
-        streams5_kernel(r->scene->d.kind == RT_SCENE_TLAS, r->streamMinB)<<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6, clk, r->streamKeepShift, laneMask);
+        streams5_kernel(r->scene->d.kind == RT_SCENE_TLAS, r->streamMinB, perPixel)<<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6, clk, r->streamKeepShift, laneMask);
     }
     else if (r->scene->d.kind == RT_SCENE_FLAT_KDTREE) k_pt_streams_alt<ACCEL_KD><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
     else if (r->scene->d.kind == RT_SCENE_FLAT_GRID) k_pt_streams_alt<ACCEL_GRID><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
