@@ -62,6 +62,29 @@ def ncu_dram_traffic():
     return (total if total > 0 else None), os.path.relpath(files[-1], ROOT)
 
 
+def ncu_issue_figures():
+    """instruction-issue figures of the dominant kernel from the same committed capture (the limit that actually binds):
+    issue slots busy, active lanes per warp instruction, warp instructions per launch"""
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_k_pt_streams5_ncu_full.txt")))
+    if not files:
+        return None
+    want = {"smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_slots_busy_pct",
+            "smsp__thread_inst_executed_per_inst_executed.ratio": "active_lanes_per_instruction",
+            "smsp__inst_executed.sum": "warp_instructions_per_launch", "l1tex__t_sector_hit_rate.pct": "l1_hit_pct",
+            "lts__t_sector_hit_rate.pct": "l2_hit_pct"}
+    out = {"source": os.path.relpath(files[-1], ROOT)}
+    for line in open(files[-1]):
+        parts = line.split()
+        if parts and parts[0] in want:
+            try:
+                out[want[parts[0]]] = float(parts[-1])
+            except ValueError:
+                pass
+    return out
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -325,8 +348,9 @@ def bench_ours(args):
                         "l2": {"note": "the 1.7 MB of nodes+triangles is L2-resident (ncu: DRAM traffic ~0.1 GB per launch), so HBM is not the "
                                        "binding roofline; peaks below are MEASURED random 64-byte gathers (rt_measure_gather_bandwidth, 8 MB set): "
                                        "'peak' with L1 bypassed, 'peak_through_l1' with ld.global.nc.  Algorithmic traffic above the L2 gather "
-                                       "peak is served by L1 (ncu: 82 % L1 hit rate); the kernel is bound by instruction issue x SIMD efficiency",
-                               "peak": l2_peak, "frac": achieved / l2_peak, "peak_through_l1": l1l2_peak, "frac_through_l1": achieved / l1l2_peak}}
+                                       "peak is served by L1 (ncu: 84 % L1 hit rate); the kernel is bound by instruction issue x SIMD efficiency (see 'issue')",
+                               "peak": l2_peak, "frac": achieved / l2_peak, "peak_through_l1": l1l2_peak, "frac_through_l1": achieved / l1l2_peak},
+                        "issue": ncu_issue_figures()}
 
             def gpu_rays_for(first, count):
                 r.reset_counters()
