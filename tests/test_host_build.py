@@ -161,3 +161,27 @@ def test_swap_partition_closed_form():
         n, pr = rnd.randint(1, 18), rnd.random()
         flags = [rnd.random() < pr for _ in range(n)]
         assert swap_loop(flags) == closed_form(flags), flags
+
+
+@pytest.mark.parametrize("name", ["golden_kd", "golden_grid", "golden_tlas_kd", "golden_tlas_grid"])
+def test_rtscene_roundtrip_of_kdtree_and_grid_chunks(name, flat_scenes, tmp_path):
+    """.rtscene save -> load keeps every chunk of the KD-tree / grid scene kinds byte for byte, and the rt_scene_desc built
+    from the reloaded file points at equal arrays (host data format, no GPU)"""
+    import cpu_ray_tracer_b200 as rtb
+    fs = flat_scenes(name)
+    p = tmp_path / (name + ".rtscene.gz")
+    fs.save(str(p))
+    back = rtb.FlatScene.load(str(p))
+    assert back.kind == fs.kind
+    for chunk in ("header", "blas_table", "tris", "tlas_nodes", "obj_material", "materials", "tex_table", "tex_pixels",
+                  "kd_nodes", "kd_tri_indices", "grid_header", "grid_cell_start", "grid_tri_indices", "blas_kd_table", "blas_grid_table"):
+        a, b = getattr(fs, chunk), getattr(back, chunk)
+        assert (a is None) == (b is None), chunk
+        if a is not None:
+            assert raw_equal(np.ascontiguousarray(a), np.ascontiguousarray(b)), chunk
+    d = back.desc()
+    assert d.kind == fs.kind and d.blas_count == len(fs.blas_table)
+    if fs.kind in (abi.RT_SCENE_TLAS_KDTREE, abi.RT_SCENE_TLAS_GRID):
+        assert bool(d.blas_accel) and d.tlas_node_count == len(fs.tlas_nodes)
+    c = back.copy()
+    assert c.kind == fs.kind and raw_equal(c.tris, fs.tris)
