@@ -315,6 +315,16 @@ def test_path_tracer_per_pixel_seed_mode(name, passes, schedule, oracles, gpu_sc
     assert c["extension_rays"] == ost["extension_rays"] and c["paths"] == ost["paths"] == W * H * frames * passes
     check_pt(r.accumulator, oacc, frames * passes, "per-pixel seeds")
     r.close()
+    if passes == 1:
+        # one Tick per call with look-ahead frames and interleaved tile shards: same image
+        parts = [api.GpuRenderer(sc, abi.RT_INTEGRATOR_PATH, W, H, seed_mode=abi.RT_SEED_PER_PIXEL, schedule=schedule,
+                                 lookahead_frames=4, tile_begin=k, tile_end=(W // 16) * (H // 16), tile_step=2).Init() for k in range(2)]
+        for q in parts:
+            for _ in range(frames):
+                q.Tick(0)
+        check_pt(parts[0].accumulator + parts[1].accumulator, oacc, frames, "per-pixel seeds, look-ahead, interleaved tiles")
+        for q in parts:
+            q.close()
 
 
 def test_depth_limit_and_partial_tiles(oracles, gpu_scenes):
