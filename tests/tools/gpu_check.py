@@ -1,7 +1,7 @@
 """Quick GPU-vs-oracle check used during development (the real tests live in tests/)."""
 import os, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import cpu_ray_tracer_b200 as rtb
 from cpu_ray_tracer_b200 import abi, api

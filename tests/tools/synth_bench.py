@@ -1,4 +1,5 @@
-"""BASELINE configs[3] and configs[4] at full size (development / measurement tool; run on the GPU box).
+"""BASELINE configs[3] and configs[4] at full size (measurement tool with an oracle parity sample, hence under tests/: only
+tests/, smoke() and bench.py's CPU legs may execute oracle/; run on the GPU box).
   c5: synthetic ~10M-triangle mesh in one flat SAH BVH (host-built with the reference's algorithm):
       coherent primary vs incoherent bounce closest-hit vs shadow any-hit through the C-ABI device entry points
   c4: one ~5k-triangle mesh instanced ~20k times under a TLAS (~100M triangles, ONE device copy of the mesh):
@@ -6,7 +7,7 @@
 usage: synth_bench.py c5 [n_tris] | c4 [n_instances] [spp] [W H]"""
 import json, os, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 import torch

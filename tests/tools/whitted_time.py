@@ -1,7 +1,7 @@
 """Whitted frame time on the GPU next to the reference's CPU loop (BASELINE configs[0]: bunny 640x360, 1 spp).
 usage: whitted_time.py [scene] [W H] [xml for the CPU reference]"""
 import json, os, subprocess, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import cpu_ray_tracer_b200 as rtb
 from cpu_ray_tracer_b200 import abi, api
