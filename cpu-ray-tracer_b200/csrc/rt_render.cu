@@ -64,13 +64,24 @@ __device__ __forceinline__ uint32_t pt_pixel_seed(const PTState& p, int x, int y
     return seed == 0 ? 0x12345678u : seed;
 }
 
-__device__ __forceinline__ void pt_generate(const PTState& p, const DCamera& cam, int slot, int pix, uint32_t& seed, float3& D, bool firstPass = true)
+// Wavefront slots.  RT_SEED_REFERENCE_TILE: slot = (tile, frame), it walks the tile's 256 pixels with the tile's stream.
+// RT_SEED_PER_PIXEL: slot = (tile, frame, pixel) with the pixel's own stream - every pixel of every frame in flight is
+// its own slot, so a batch needs only passes x (depthLimit + 1) extend / shade iterations.
+__device__ __forceinline__ void pt_slot(const PTState& p, int slot, int& tile, int& frame, int& px0)
 {
-    const int tile = p.tileBegin + (slot % p.nTiles) * p.tileStep;
+    const bool perPixel = p.seedMode == RT_SEED_PER_PIXEL;
+    const int unit = perPixel ? slot >> 8 : slot;
+    px0 = perPixel ? slot & 255 : 0;
+    tile = p.tileBegin + (unit % p.nTiles) * p.tileStep;
+    frame = unit / p.nTiles;
+}
+
+__device__ __forceinline__ void pt_generate(const PTState& p, const DCamera& cam, int slot, int pix, uint32_t& seed, float3& D)
+{
+    int tile, frame, px0;
+    pt_slot(p, slot, tile, frame, px0);
     const int tx = tile % p.tilesX, ty = tile / p.tilesX;
     const int x = tx * 16 + (pix & 15), y = ty * 16 + (pix >> 4);
-    if (p.seedMode == RT_SEED_PER_PIXEL && firstPass) // one stream per pixel per frame, shared by the pixel's `passes` samples
-        seed = pt_pixel_seed(p, x, y, p.firstSpp + (slot / p.nTiles) * p.stride);
     const float jy = random_float(seed);
     const float jx = random_float(seed);
     D = primary_dir(cam, (float)x + jx, (float)y + jy);
@@ -80,15 +91,17 @@ __global__ void __launch_bounds__(256) k_pt_generate(const PTState p, const DCam
 {
     for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < p.slots; slot += gridDim.x * blockDim.x)
     {
-        const int tile = p.tileBegin + (slot % p.nTiles) * p.tileStep;
-        const int spp = p.firstSpp + (slot / p.nTiles) * p.stride;
-        uint32_t seed = pt_seed(p, tile, spp);
+        int tile, frame, px0;
+        pt_slot(p, slot, tile, frame, px0);
+        const int spp = p.firstSpp + frame * p.stride;
+        const int tx = tile % p.tilesX, ty = tile / p.tilesX;
+        uint32_t seed = p.seedMode == RT_SEED_PER_PIXEL ? pt_pixel_seed(p, tx * 16 + (px0 & 15), ty * 16 + (px0 >> 4), spp) : pt_seed(p, tile, spp);
         float3 D;
-        pt_generate(p, cam, slot, 0, seed, D);
+        pt_generate(p, cam, slot, px0, seed, D);
         p.rayO[slot] = make_float4(cam.pos.x, cam.pos.y, cam.pos.z, 0);
         p.rayD[slot] = make_float4(D.x, D.y, D.z, __int_as_float(0));
         p.seed[slot] = seed;
-        p.pix[slot] = 1;
+        p.pix[slot] = px0 * p.passes + 1; // index of the next sample
         p.active[0][slot] = slot;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) p.count[0] = p.slots, p.count[1] = 0, p.count[4] = 0;
@@ -296,17 +309,19 @@ __global__ void __launch_bounds__(128) k_pt_shade(const PTState p, const DScene 
                 }
                 const int smp = p.pix[slot]; // index of the NEXT sample; the finished one is smp - 1
                 const int pix = (smp - 1) / p.passes + 1; // pixel after the finished sample's pixel
+                int tile, frame, px0;
+                pt_slot(p, slot, tile, frame, px0);
                 {
-                    const int tile = p.tileBegin + (slot % p.nTiles) * p.tileStep;
                     const int tx = tile % p.tilesX, ty = tile / p.tilesX;
                     const int x = tx * 16 + ((pix - 1) & 15), y = ty * 16 + ((pix - 1) >> 4);
                     float* a = (float*)(p.accum + (x + (size_t)y * p.W)); // renderer.cpp:124: accumulator += float4(sample, 0)
                     atomicAdd(a + 0, L.x), atomicAdd(a + 1, L.y), atomicAdd(a + 2, L.z);
                 }
-                if (smp < 256 * p.passes)
+                // the slot's last sample: the tile's 256 x passes-th, or (one slot per pixel) the pixel's passes-th
+                if (smp < (p.seedMode == RT_SEED_PER_PIXEL ? (px0 + 1) * p.passes : 256 * p.passes))
                 {
                     float3 gD;
-                    pt_generate(p, cam, slot, smp / p.passes, seed, gD, smp % p.passes == 0);
+                    pt_generate(p, cam, slot, smp / p.passes, seed, gD);
                     p.rayO[slot] = make_float4(cam.pos.x, cam.pos.y, cam.pos.z, 0);
                     p.rayD[slot] = make_float4(gD.x, gD.y, gD.z, __int_as_float(0));
                     p.pix[slot] = smp + 1;
@@ -1706,10 +1721,13 @@ static rt_status render_pt(rt_renderer* r, int first_spp, int count, int stride)
         }
         return render_pt_streams(r, first_spp, count, stride);
     }
-    int inFlight = P.max_frames_in_flight > 0 ? P.max_frames_in_flight : (1 << 20) / nTiles;
+    // wavefront: slots per frame = tiles (reference RNG: a slot walks its tile) or pixels (one stream per pixel)
+    const bool wfPerPixel = P.seed_mode == RT_SEED_PER_PIXEL;
+    const int slotsPerFrame = nTiles * (wfPerPixel ? 256 : 1);
+    int inFlight = P.max_frames_in_flight > 0 ? P.max_frames_in_flight : (wfPerPixel ? 8 << 20 : 1 << 20) / slotsPerFrame;
     if (inFlight < 1) inFlight = 1;
     if (inFlight > count) inFlight = count;
-    rt_status st = pt_ensure_slots(r, nTiles * inFlight);
+    rt_status st = pt_ensure_slots(r, slotsPerFrame * inFlight);
     if (st != RT_OK) return st;
     PTState& p = r->pt;
     p.count = r->dCount, p.counters = r->dCounters, p.accum = r->accum;
@@ -1719,11 +1737,11 @@ static rt_status render_pt(rt_renderer* r, int first_spp, int count, int stride)
     const int grid = r->sms * 8;
     const int kind = r->scene->d.kind;
     // every path makes at most depth_limit + 1 FindNearest queries, every slot 256 paths
-    const int maxIters = 256 * r->passes * (P.depth_limit + 1) + 1;
+    const int maxIters = (wfPerPixel ? 1 : 256) * r->passes * (P.depth_limit + 1) + 1;
     for (int done = 0; done < count; done += inFlight)
     {
         const int frames = count - done < inFlight ? count - done : inFlight;
-        p.slots = nTiles * frames;
+        p.slots = slotsPerFrame * frames;
         p.firstSpp = first_spp + done * stride;
         r->prof_begin();
         k_pt_generate<<<r->sms * 4, 256, 0, r->stream>>>(p, r->cam);
@@ -1749,7 +1767,7 @@ static rt_status render_pt(rt_renderer* r, int first_spp, int count, int stride)
                 if (r->hCount[0] == 0) break;
             }
         }
-        r->paths += (uint64_t)p.slots * 256 * r->passes;
+        r->paths += (uint64_t)nTiles * frames * 256 * r->passes;
     }
     RT_CUDA(cudaGetLastError());
     return RT_OK;
