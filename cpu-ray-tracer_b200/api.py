@@ -9,7 +9,7 @@ Same names, argument meaning and error behaviour as the reference classes, batch
         Init, Tick, ClearAccumulator, accumulator, camera, spp, passes, depthLimit
 
 There is no CPU fallback anywhere in this module: if librt_b200.so is missing or no CUDA device is
-visible the calls raise (RtError / OSError).  The C++ twin of these adapters is csrc/host/gpu_scene.h.
+visible the calls raise (RtError / OSError).  The C++ twin of these adapters is host/rt_b200_adapters.h.
 """
 import ctypes as C
 import os

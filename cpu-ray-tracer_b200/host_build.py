@@ -91,9 +91,56 @@ def build_grid(tris):
     return hdr, start, idx
 
 
+def _with_blas_accelerator(flat, accel):
+    """TLASFileScene with per-object KD-trees / grids (tlas_file_scene.h:12-14) from one with per-object BVHs: same
+    triangles, transforms and TLAS (the TLAS is the same agglomerative BVH for all three BLAS kinds; its leaf boxes
+    are the BLAS' local bounds, which every builder derives from the same vertices).  BLAS that share a triangle
+    range (true instancing) share one tree / grid: their table rows point at the same ranges."""
+    chunks = {k: getattr(flat, k) for k in ("tris", "tlas_nodes", "obj_material", "materials", "tex_table", "tex_pixels")}
+    chunks["header"] = flat.header.copy()
+    chunks["blas_table"] = flat.blas_table.copy()
+    chunks["blas_table"]["node_offset"], chunks["blas_table"]["node_count"] = 0, 0
+    chunks["nodes"], chunks["tri_indices"] = np.zeros(0, abi.NODE_DTYPE), np.zeros(0, np.uint32)
+    built = {}
+    if accel == "kdtree":
+        chunks["header"]["kind"] = abi.RT_SCENE_TLAS_KDTREE
+        table, nodes, idx, no, io = np.zeros(len(flat.blas_table), abi.BLAS_KD_TABLE_DTYPE), [], [], 0, 0
+        for i, b in enumerate(flat.blas_table):
+            key = (int(b["tri_offset"]), int(b["tri_count"]))
+            if key not in built:
+                n, ix, _ = build_kdtree(flat.tris[key[0]:key[0] + key[1]])
+                built[key] = (no, len(n), io, len(ix))
+                nodes.append(n), idx.append(ix)
+                no, io = no + len(n), io + len(ix)
+            table[i] = built[key]
+        chunks["blas_kd_table"], chunks["kd_nodes"], chunks["kd_tri_indices"] = table, np.concatenate(nodes), np.concatenate(idx)
+    elif accel == "grid":
+        chunks["header"]["kind"] = abi.RT_SCENE_TLAS_GRID
+        table, starts, idx, co, io = np.zeros(len(flat.blas_table), abi.BLAS_GRID_TABLE_DTYPE), [], [], 0, 0
+        for i, b in enumerate(flat.blas_table):
+            key = (int(b["tri_offset"]), int(b["tri_count"]))
+            if key not in built:
+                hdr, st, ix = build_grid(flat.tris[key[0]:key[0] + key[1]])
+                row = np.zeros(1, abi.BLAS_GRID_TABLE_DTYPE)
+                for f in ("resolution", "cell_size", "bounds_min", "bounds_max"):
+                    row[f] = hdr[f]
+                row["cell_offset"], row["cell_count"], row["idx_offset"], row["idx_count"] = co, len(st) - 1, io, len(ix)
+                built[key] = row[0]
+                starts.append(st), idx.append(ix)
+                co, io = co + len(st), io + len(ix)
+            table[i] = built[key]
+        chunks["blas_grid_table"], chunks["grid_cell_start"], chunks["grid_tri_indices"] = table, np.concatenate(starts), np.concatenate(idx)
+    else:
+        raise ValueError(accel)
+    return FlatScene(chunks)
+
+
 def with_accelerator(flat, accel):
-    """The same FileScene with another of its accelerators (file_scene.h:10-12): accel = "kdtree" | "grid".
+    """The same FileScene with another of its accelerators (file_scene.h:10-12): accel = "kdtree" | "grid"; for a
+    TLASFileScene, the same scene with per-object KD-trees / grids (tlas_file_scene.h:12-14).
     Triangles, materials and textures are shared with `flat`; the BVH arrays are dropped."""
+    if flat.kind == abi.RT_SCENE_TLAS:
+        return _with_blas_accelerator(flat, accel)
     chunks = {k: getattr(flat, k) for k in ("header", "blas_table", "tris", "obj_material", "materials", "tex_table", "tex_pixels")}
     chunks["header"] = flat.header.copy()
     chunks["blas_table"] = flat.blas_table[:1].copy()

@@ -16,11 +16,21 @@ pytestmark = pytest.mark.gpu
 def synth():
     from cpu_ray_tracer_b200 import host_build
     terrain = host_build.terrain_mesh(120000, seed=5)
-    return {"terrain": host_build.flat_scene_from_tris(terrain),
-            "instanced": host_build.instanced_grid(host_build.terrain_mesh(1200, seed=9, size=0.8, height=0.5), 343)}
+    flat = host_build.flat_scene_from_tris(terrain)
+    inst = host_build.instanced_grid(host_build.terrain_mesh(1200, seed=9, size=0.8, height=0.5), 343)
+    small = host_build.instanced_grid(host_build.terrain_mesh(1200, seed=9, size=0.8, height=0.5), 64)
+    return {"terrain": flat, "instanced": inst,
+            # the other accelerators on host-built scenes; the instanced ones share ONE tree / grid between all instances
+            "terrain_kd": host_build.with_accelerator(host_build.flat_scene_from_tris(host_build.terrain_mesh(20000, seed=5)), "kdtree"),
+            "terrain_grid": host_build.with_accelerator(flat, "grid"),
+            "instanced_kd": host_build.with_accelerator(small, "kdtree"),
+            "instanced_grid": host_build.with_accelerator(inst, "grid")}
 
 
-@pytest.mark.parametrize("which", ["terrain", "instanced"])
+ALL_SYNTH = ["terrain", "instanced", "terrain_kd", "terrain_grid", "instanced_kd", "instanced_grid"]
+
+
+@pytest.mark.parametrize("which", ALL_SYNTH)
 def test_synthetic_traversal_bit_exact(which, synth):
     from cpu_ray_tracer_b200 import api
     from oracle import porthost
@@ -38,12 +48,12 @@ def test_synthetic_traversal_bit_exact(which, synth):
     rr = random_rays(fs, 30000, seed=13)
     ref, _ = po.find_nearest(rr)
     assert_hits_equal(sc.FindNearest(rr), ref, which + " (random)")
-    if which == "instanced":
+    if which.startswith("instanced"):
         assert st["blas_entries"] > len(rays) * 0.05
     sc.close()
 
 
-@pytest.mark.parametrize("which", ["terrain", "instanced"])
+@pytest.mark.parametrize("which", ALL_SYNTH)
 def test_synthetic_path_tracer_vs_oracle(which, synth):
     from cpu_ray_tracer_b200 import api
     from oracle import porthost

@@ -185,3 +185,28 @@ def test_rtscene_roundtrip_of_kdtree_and_grid_chunks(name, flat_scenes, tmp_path
         assert bool(d.blas_accel) and d.tlas_node_count == len(fs.tlas_nodes)
     c = back.copy()
     assert c.kind == fs.kind and raw_equal(c.tris, fs.tris)
+
+
+@pytest.mark.parametrize("accel,kind", [("kdtree", abi.RT_SCENE_TLAS_KDTREE), ("grid", abi.RT_SCENE_TLAS_GRID)])
+def test_with_accelerator_on_tlas_scenes(accel, kind, flat_scenes):
+    """a TLAS-over-BVH scene rebuilt over per-object KD-trees / grids equals what the reference built for that
+    configuration (same XML, tests/golden), and instances that share a mesh share one tree / grid"""
+    from oracle import porthost
+    ref = flat_scenes("golden_tlas_kd" if accel == "kdtree" else "golden_tlas_grid")
+    got = host_build.with_accelerator(flat_scenes("golden_tlas"), accel)
+    assert got.kind == kind and raw_equal(got.tlas_nodes["left_right"], ref.tlas_nodes["left_right"])
+    for f in ("aabb_min", "aabb_max"):
+        assert biteq(got.tlas_nodes[f], ref.tlas_nodes[f])
+    if accel == "kdtree":
+        assert raw_equal(got.kd_nodes, ref.kd_nodes) and raw_equal(got.kd_tri_indices, ref.kd_tri_indices)
+        assert raw_equal(got.blas_kd_table, ref.blas_kd_table)
+    else:
+        assert raw_equal(got.grid_tri_indices, ref.grid_tri_indices) and raw_equal(got.blas_grid_table, ref.blas_grid_table)
+    tris = host_build.terrain_mesh(800, seed=5, size=1.0, height=0.5)
+    inst = host_build.with_accelerator(host_build.instanced_grid(tris, 27), accel)
+    table = inst.blas_kd_table if accel == "kdtree" else inst.blas_grid_table
+    assert len(table) == 27 and len(set(table.tobytes()[i * table.itemsize:(i + 1) * table.itemsize] for i in range(27))) == 1
+    po = porthost.PortOracle(inst)
+    W, H = 64, 40
+    hits, st = po.find_nearest(po.primary_rays(po.camera_default(W, H), W, H))
+    assert (hits["obj_idx"] >= 2).any() and st["blas_entries"] > 0
