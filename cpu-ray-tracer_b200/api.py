@@ -20,7 +20,8 @@ from . import abi
 from .scene_file import FlatScene
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librt_b200.so")
+# RT_B200_LIB: another build of the same library (development A/B runs, e.g. build.py --cuda-math); the default is in-tree
+LIB_PATH = os.environ.get("RT_B200_LIB") or os.path.join(HERE, "librt_b200.so")
 
 EXPORTS = [
     "rt_last_error", "rt_abi_version", "rt_device_count", "rt_scene_create", "rt_scene_destroy",
@@ -31,7 +32,7 @@ EXPORTS = [
     "rt_renderer_read_accumulator", "rt_renderer_read_pixels", "rt_renderer_device_accumulator",
     "rt_renderer_get_counters", "rt_renderer_reset_counters",
     "rt_renderer_set_profiling", "rt_renderer_get_stage_times", "rt_renderer_get_launch_spans",
-    "rt_renderer_get_queue_history", "rt_measure_gather_bandwidth", "rt_build_bvh",
+    "rt_renderer_get_queue_history", "rt_measure_gather_bandwidth", "rt_build_bvh", "rt_eval_shading_math",
 ]
 
 
@@ -90,6 +91,7 @@ def lib():
     L.rt_renderer_get_queue_history.argtypes = [vp, vp, sz, C.POINTER(sz)]
     L.rt_measure_gather_bandwidth.argtypes = [i32, sz, i32, C.POINTER(C.c_double)]
     L.rt_build_bvh.argtypes = [i32, vp, C.c_uint32, vp, vp, C.POINTER(C.c_uint32), C.POINTER(C.c_double)]
+    L.rt_eval_shading_math.argtypes = [i32, i32, vp, vp, vp, sz]
     _lib = L
     return L
 
@@ -119,6 +121,15 @@ def measure_gather_bandwidth(working_set_bytes, bypass_l1=True, device=0):
     out = C.c_double()
     _check(lib().rt_measure_gather_bandwidth(device, working_set_bytes, 1 if bypass_l1 else 0, C.byref(out)))
     return out.value
+
+
+def eval_shading_math(fn, a, b=None, device=0):
+    """expf / acosf / atan2f as the shading kernels compute them, evaluated on the device (rt_eval_shading_math)"""
+    a = np.ascontiguousarray(a, np.float32)
+    b = None if b is None else np.ascontiguousarray(b, np.float32)
+    out = np.empty_like(a)
+    _check(lib().rt_eval_shading_math(device, fn, a.ctypes.data, None if b is None else b.ctypes.data, out.ctypes.data, a.size))
+    return out
 
 
 class Camera:

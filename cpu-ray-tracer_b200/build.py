@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librt_b200.so")
 SOURCES = ["rt_scene.cu", "rt_render.cu", "rt_build.cu"]
-HEADERS = ["rt_device.cuh", "rt_internal.h", os.path.join("..", "..", "include", "rt_b200.h")]
+HEADERS = ["rt_device.cuh", "rt_glibc_math.cuh", "rt_internal.h", os.path.join("..", "..", "include", "rt_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
@@ -61,6 +61,20 @@ def build(force=False, verbose=False, extra=()):
     return LIB
 
 
+def build_cuda_math(verbose=False):
+    """development A/B: the same library with CUDA's expf / atan2f / acosf instead of the glibc restatements
+    (librt_b200_cudamath.so, selected with RT_B200_LIB; not built by default, not used by the tests)"""
+    out = os.path.join(HERE, "librt_b200_cudamath.so")
+    cmd = [nvcc(), *NVCC_FLAGS, "-DRT_B200_GLIBC_MATH=0", *[os.path.join(CSRC, f) for f in SOURCES], "-o", out]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    return out
+
+
 if __name__ == "__main__":
-    extra = ["-Xptxas", "-v"] if "-v" in sys.argv else []
-    print(build(force=True, verbose=True, extra=extra))
+    if "--cuda-math" in sys.argv:
+        print(build_cuda_math(verbose=True))
+    else:
+        extra = ["-Xptxas", "-v"] if "-v" in sys.argv else []
+        print(build(force=True, verbose=True, extra=extra))

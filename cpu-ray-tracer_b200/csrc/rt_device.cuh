@@ -8,6 +8,21 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+// RT_B200_GLIBC_MATH (default 1): expf / atan2f / acosf of the shading code are glibc 2.39's routines restated for the
+// device (rt_glibc_math.cuh: same bits as the host libm the reference's CPU build calls) instead of CUDA's (<= 2 ulp away).
+#ifndef RT_B200_GLIBC_MATH
+#define RT_B200_GLIBC_MATH 1
+#endif
+#if RT_B200_GLIBC_MATH
+#include "rt_glibc_math.cuh"
+#define rt_expf rt_glibc_expf
+#define rt_atan2f rt_glibc_atan2f
+#define rt_acosf rt_glibc_acosf
+#else
+#define rt_expf expf
+#define rt_atan2f atan2f
+#define rt_acosf acosf
+#endif
 
 namespace rtb {
 
@@ -1130,12 +1145,12 @@ __device__ __forceinline__ float3 texture_sample(const DScene& s, int tex, float
     return f3(((pixel >> 16) & 0xFF) * rgbScale, ((pixel >> 8) & 0xFF) * rgbScale, (pixel & 0xFF) * rgbScale);
 }
 
-// GetSkyColor: file_scene.cpp:142-154.  atan2f / acosf are CUDA's (<= 2 ulp from glibc's): a texel
-// can flip at a texel border, which is why radiance parity is a tolerance and hit parity is exact.
+// GetSkyColor: file_scene.cpp:142-154.  rt_atan2f / rt_acosf: glibc's routines restated (rt_glibc_math.cuh), so the texel
+// chosen is the reference's; with RT_B200_GLIBC_MATH=0 they are CUDA's (<= 2 ulp away: a lookup on a texel border can flip).
 __device__ __forceinline__ float3 sky_color(const DScene& s, float3 D)
 {
-    const float phi = atan2f(-D.z, D.x) + RT_PI;
-    const float theta = acosf(-D.y);
+    const float phi = rt_atan2f(-D.z, D.x) + RT_PI;
+    const float theta = rt_acosf(-D.y);
     const float u = phi * RT_INV2PI;
     const float v = theta * RT_INVPI;
     return texture_sample(s, s.skydome_texture, u, v);

@@ -213,7 +213,7 @@ __device__ __forceinline__ int pt_surface(const DScene& s, const int depthLimit,
     if (inside)
     {
         const float3 a = h.absorption * -t; // renderer.cpp:76-80
-        medium_scale = f3(expf(a.x), expf(a.y), expf(a.z));
+        medium_scale = f3(rt_expf(a.x), rt_expf(a.y), rt_expf(a.z));
     }
     const float r = random_float(seed);
     nInside = false;
@@ -1114,7 +1114,7 @@ __global__ void __launch_bounds__(128) k_wh_shade(const WhState p, const DScene 
                 {
                     float3 medium_scale = f3(1, 1, 1);
                     if (inside) // renderer.cpp:81-88
-                        medium_scale = f3(expf(h.absorption.x * -t), expf(h.absorption.y * -t), expf(h.absorption.z * -t));
+                        medium_scale = f3(rt_expf(h.absorption.x * -t), rt_expf(h.absorption.y * -t), rt_expf(h.absorption.z * -t));
                     const float3 wm = w * medium_scale;
                     const float reflectivity = h.reflectivity, refractivity = h.refractivity;
                     const float diffuseness = 1 - (reflectivity + refractivity);

@@ -96,6 +96,13 @@ __global__ void __launch_bounds__(128) k_is_occluded_persistent(const DScene s, 
     accel_trace_queue<ACCEL, true, false, AbiSrc, VOTED>(s, src, n, fetch);
 }
 
+// rt_eval_shading_math: the transcendental routines of the shading code (rt_expf / rt_acosf / rt_atan2f of rt_device.cuh)
+// evaluated on the device, for the parity tests against the host libm
+__global__ void __launch_bounds__(256) k_eval_shading_math(int fn, const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = fn == RT_MATH_EXPF ? rt_expf(a[i]) : fn == RT_MATH_ACOSF ? rt_acosf(a[i]) : rt_atan2f(a[i], b[i]);
+}
 
 // ------------------------------------------------------------------------------------------------
 // Roofline denominator for L2-resident scenes: random 64-byte record gathers (the size and alignment of
@@ -729,6 +736,31 @@ rt_status rt_measure_gather_bandwidth(int device, size_t working_set_bytes, int 
     const double bytes = (double)grid * block * iters * 4 * 64;
     *gb_per_s = bytes / (best * 1e-3) / 1e9;
     return RT_OK;
+}
+
+rt_status rt_eval_shading_math(int device, int fn, const float* a, const float* b, float* out, size_t n)
+{
+    if (fn < RT_MATH_EXPF || fn > RT_MATH_ATAN2F || (n && (!a || !out || (fn == RT_MATH_ATAN2F && !b)))) { set_error("rt_eval_shading_math: bad argument"); return RT_ERR_INVALID; }
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) { set_error("no such CUDA device (there is no CPU fallback)"); return RT_ERR_NO_DEVICE; }
+    if (n == 0) return RT_OK;
+    RT_CUDA(cudaSetDevice(device));
+    float *da = nullptr, *db = nullptr, *dout = nullptr;
+    const size_t bytes = n * sizeof(float);
+    cudaError_t e = cudaMalloc((void**)&da, bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dout, bytes);
+    if (e == cudaSuccess && fn == RT_MATH_ATAN2F) e = cudaMalloc((void**)&db, bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(da, a, bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && db) e = cudaMemcpy(db, b, bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+    {
+        const unsigned grid = (unsigned)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+        k_eval_shading_math<<<grid, 256>>>(fn, da, db, dout, n);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, dout, bytes, cudaMemcpyDeviceToHost);
+    cudaFree(da), cudaFree(db), cudaFree(dout);
+    return cuda_ok(e, "rt_eval_shading_math") ? RT_OK : RT_ERR_CUDA;
 }
 
 void rt_camera_default(rt_camera* c, int width, int height)

@@ -362,6 +362,17 @@ rt_status rt_build_bvh(int device, const rt_tri* tris, uint32_t n, rt_bvh_node* 
  * uses ld.global.cg.  No reference equivalent (the reference has no memory-hierarchy instrumentation). */
 rt_status rt_measure_gather_bandwidth(int device, size_t working_set_bytes, int bypass_l1, double* gb_per_s);
 
+/* Evaluates, ON THE DEVICE, the transcendental routines the shading kernels use, over host arrays of n arguments:
+ * fn = RT_MATH_EXPF: out[i] = expf(a[i])   (Beer's law, renderer.cpp:76-80; b is ignored and may be NULL)
+ * fn = RT_MATH_ACOSF: out[i] = acosf(a[i]), fn = RT_MATH_ATAN2F: out[i] = atan2f(a[i], b[i])   (GetSkyColor,
+ * file_scene.cpp:142-154).  The kernels call glibc 2.39's routines restated for the device (csrc/rt_glibc_math.cuh), so
+ * out[] must equal the host libm's results bit for bit; the parity tests check exactly that.  Test instrumentation:
+ * the reference has no equivalent entry point. */
+#define RT_MATH_EXPF 0
+#define RT_MATH_ACOSF 1
+#define RT_MATH_ATAN2F 2
+rt_status rt_eval_shading_math(int device, int fn, const float* a, const float* b, float* out, size_t n);
+
 #ifdef __cplusplus
 }
 #endif
