@@ -1128,32 +1128,76 @@ __device__ __forceinline__ bool is_occluded(const DScene& s, float3 O, float3 D,
 // ------------------------------------------------------------------------------------------------
 // textures, sky, hit shading queries
 // ------------------------------------------------------------------------------------------------
-// Texture::Sample: texture.h:61-96 (nearest, clamp, v flip, 0x00RRGGBB)
-__device__ __forceinline__ float3 texture_sample(const DScene& s, int tex, float u, float v)
+// Texture::Sample: texture.h:61-96 (nearest, clamp, v flip, 0x00RRGGBB), split into texel choice and fetch
+__device__ __forceinline__ void texture_texel(const DTexture& T, float u, float v, int& x, int& y, float& fx, float& fy)
 {
-    if (tex < 0) return f3(0, 0, 0);
-    const DTexture T = s.textures[tex];
-    if (T.width * T.height == 0) return f3(0, 0, 0);
     u = clampf(u, 0.0f, 1.0f);
     v = 1 - clampf(v, 0.0f, 1.0f);
-    int x = (int)(u * T.width);
-    int y = (int)(v * T.height);
-    x = clampi(x, 0, T.width - 1);
-    y = clampi(y, 0, T.height - 1);
+    fx = u * T.width, fy = v * T.height;
+    x = clampi((int)fx, 0, T.width - 1);
+    y = clampi((int)fy, 0, T.height - 1);
+}
+
+__device__ __forceinline__ float3 texture_fetch(const DTexture& T, int x, int y)
+{
     const uint32_t pixel = __ldg(T.pixels + (x + y * T.width));
     const float rgbScale = 1 / 255.0f;
     return f3(((pixel >> 16) & 0xFF) * rgbScale, ((pixel >> 8) & 0xFF) * rgbScale, (pixel & 0xFF) * rgbScale);
 }
 
-// GetSkyColor: file_scene.cpp:142-154.  rt_atan2f / rt_acosf: glibc's routines restated (rt_glibc_math.cuh), so the texel
-// chosen is the reference's; with RT_B200_GLIBC_MATH=0 they are CUDA's (<= 2 ulp away: a lookup on a texel border can flip).
-__device__ __forceinline__ float3 sky_color(const DScene& s, float3 D)
+__device__ __forceinline__ float3 texture_sample(const DScene& s, int tex, float u, float v)
+{
+    if (tex < 0) return f3(0, 0, 0);
+    const DTexture T = s.textures[tex];
+    if (T.width * T.height == 0) return f3(0, 0, 0);
+    int x, y;
+    float fx, fy;
+    texture_texel(T, u, v, x, y, fx, fy);
+    return texture_fetch(T, x, y);
+}
+
+// GetSkyColor: file_scene.cpp:142-154.  The texel must be the one the reference picks, i.e. the one glibc's atan2f / acosf lead to.
+// Misses are shaded by one to three lanes of a warp (the MISS state of the stream kernel), so every instruction here is paid almost
+// per ray: running the restated glibc routines for every lookup cost 10-20 % of the whole path tracer (profiles/r1_glibc_math.txt).
+// Instead the texel is first computed with CUDA's atan2f / acosf and ACCEPTED only when u * width and v * height are further from
+// a texel border than the two libraries can disagree; otherwise (about 4e-6 * (width + height) of the lookups, 2.5 % for a 4096 x 2048
+// sky) the restated routines decide.  Bound: each library is within 4 ulp of the true angle (CUDA documents 2 ulp for both functions,
+// fdlibm's routines stay below 2 including the y / x rounding), so phi and theta differ by at most 8 ulp(pi) = 1.9e-6, u = phi / 2pi
+// by 3.0e-7 and v = theta / pi by 6.1e-7, plus 1.2e-7 for the two roundings of each product: 4.2e-7 * width and 7.3e-7 * height in texel
+// units, plus one ulp of the product itself (1.2e-7 * size).  the v flip 1 - v adds another 1.2e-7 * height.
+// RT_SKY_TEXEL_MARGIN = 2e-6 per unit of size is twice the larger of the two sums.
+// NaN directions and the clamped ends (u * width = 0 or width) fail the test and take the exact path too.
+#define RT_SKY_TEXEL_MARGIN 2e-6f
+__device__ __forceinline__ void sky_texel_exact(const DTexture& T, float3 D, int& x, int& y)
 {
     const float phi = rt_atan2f(-D.z, D.x) + RT_PI;
     const float theta = rt_acosf(-D.y);
-    const float u = phi * RT_INV2PI;
-    const float v = theta * RT_INVPI;
-    return texture_sample(s, s.skydome_texture, u, v);
+    float fx, fy;
+    texture_texel(T, phi * RT_INV2PI, theta * RT_INVPI, x, y, fx, fy);
+}
+
+__device__ __forceinline__ bool sky_texel_filtered(const DTexture& T, float3 D, int& x, int& y)
+{
+    const float phi = atan2f(-D.z, D.x) + RT_PI;
+    const float theta = acosf(-D.y);
+    float fx, fy;
+    texture_texel(T, phi * RT_INV2PI, theta * RT_INVPI, x, y, fx, fy);
+    return fabsf(fx - rintf(fx)) > RT_SKY_TEXEL_MARGIN * T.width && fabsf(fy - rintf(fy)) > RT_SKY_TEXEL_MARGIN * T.height;
+}
+
+__device__ __forceinline__ float3 sky_color(const DScene& s, float3 D)
+{
+    const int tex = s.skydome_texture;
+    if (tex < 0) return f3(0, 0, 0);
+    const DTexture T = s.textures[tex];
+    if (T.width * T.height == 0) return f3(0, 0, 0);
+    int x, y;
+#if RT_B200_GLIBC_MATH
+    if (!sky_texel_filtered(T, D, x, y)) sky_texel_exact(T, D, x, y);
+#else
+    sky_texel_filtered(T, D, x, y); // CUDA's atan2f / acosf only (<= 2 ulp away: a lookup on a texel border can flip)
+#endif
+    return texture_fetch(T, x, y);
 }
 
 struct ShadeHit {

@@ -101,7 +101,23 @@ __global__ void __launch_bounds__(128) k_is_occluded_persistent(const DScene s, 
 __global__ void __launch_bounds__(256) k_eval_shading_math(int fn, const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, size_t n)
 {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        out[i] = fn == RT_MATH_EXPF ? rt_expf(a[i]) : fn == RT_MATH_ACOSF ? rt_acosf(a[i]) : rt_atan2f(a[i], b[i]);
+    {
+        if (fn == RT_MATH_SKY_TEXEL)
+        {
+            // direction from azimuth a and height b; a 4096 x 2048 sky: 1 = the filtered lookup accepted its texel and it is the one the
+            // restated glibc routines choose, 0 = the filter handed the lookup to them, -1 = accepted a different texel (must not happen)
+            const float h = fminf(fmaxf(b[i], -1.0f), 1.0f), r = sqrtf(1.0f - h * h);
+            const float3 D = f3(cosf(a[i]) * r, h, sinf(a[i]) * r);
+            DTexture T;
+            T.pixels = nullptr, T.width = 4096, T.height = 2048;
+            int x, y, xe, ye;
+            const bool accepted = sky_texel_filtered(T, D, x, y);
+            sky_texel_exact(T, D, xe, ye);
+            out[i] = !accepted ? 0.0f : (x == xe && y == ye) ? 1.0f : -1.0f;
+        }
+        else
+            out[i] = fn == RT_MATH_EXPF ? rt_expf(a[i]) : fn == RT_MATH_ACOSF ? rt_acosf(a[i]) : rt_atan2f(a[i], b[i]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -740,7 +756,7 @@ rt_status rt_measure_gather_bandwidth(int device, size_t working_set_bytes, int 
 
 rt_status rt_eval_shading_math(int device, int fn, const float* a, const float* b, float* out, size_t n)
 {
-    if (fn < RT_MATH_EXPF || fn > RT_MATH_ATAN2F || (n && (!a || !out || (fn == RT_MATH_ATAN2F && !b)))) { set_error("rt_eval_shading_math: bad argument"); return RT_ERR_INVALID; }
+    if (fn < RT_MATH_EXPF || fn > RT_MATH_SKY_TEXEL || (n && (!a || !out || (fn >= RT_MATH_ATAN2F && !b)))) { set_error("rt_eval_shading_math: bad argument"); return RT_ERR_INVALID; }
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) { set_error("no such CUDA device (there is no CPU fallback)"); return RT_ERR_NO_DEVICE; }
     if (n == 0) return RT_OK;
@@ -749,7 +765,7 @@ rt_status rt_eval_shading_math(int device, int fn, const float* a, const float* 
     const size_t bytes = n * sizeof(float);
     cudaError_t e = cudaMalloc((void**)&da, bytes);
     if (e == cudaSuccess) e = cudaMalloc((void**)&dout, bytes);
-    if (e == cudaSuccess && fn == RT_MATH_ATAN2F) e = cudaMalloc((void**)&db, bytes);
+    if (e == cudaSuccess && fn >= RT_MATH_ATAN2F) e = cudaMalloc((void**)&db, bytes);
     if (e == cudaSuccess) e = cudaMemcpy(da, a, bytes, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && db) e = cudaMemcpy(db, b, bytes, cudaMemcpyHostToDevice);
     if (e == cudaSuccess)

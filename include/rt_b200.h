@@ -371,6 +371,11 @@ rt_status rt_measure_gather_bandwidth(int device, size_t working_set_bytes, int 
 #define RT_MATH_EXPF 0
 #define RT_MATH_ACOSF 1
 #define RT_MATH_ATAN2F 2
+/* fn = RT_MATH_SKY_TEXEL: the sky lookup's texel choice for the direction with azimuth a[i] (radians) and height b[i] in [-1, 1] over a
+ * 4096 x 2048 skydome: out[i] = 1 when the fast lookup (CUDA's atan2f / acosf) accepted its texel and it is the texel the glibc
+ * routines give, 0 when the lookup was too close to a texel border and was handed to the glibc routines, -1 when the fast lookup
+ * accepted a different texel (the parity tests require that this never happens). */
+#define RT_MATH_SKY_TEXEL 3
 rt_status rt_eval_shading_math(int device, int fn, const float* a, const float* b, float* out, size_t n);
 
 #ifdef __cplusplus

@@ -97,6 +97,26 @@ def test_device_math_equals_host_libm(checker):
         assert not bad.any(), f"{what}: {int(bad.sum())} of {a.size} device results differ from libm, first at {a[bad][:4]}"
 
 
+@pytest.mark.gpu
+def test_sky_texel_filter_never_accepts_a_different_texel():
+    """the sky lookup accepts the texel found with CUDA's atan2f / acosf only away from texel borders (rt_device.cuh, sky_color):
+    whenever it accepts, the texel is the one the restated glibc routines choose; the rest (a few %) goes to those routines"""
+    from cpu_ray_tracer_b200 import api
+    rng = np.random.default_rng(5)
+    n = 16_000_000
+    az = rng.uniform(-np.pi, np.pi, n).astype(np.float32)
+    h = rng.uniform(-1, 1, n).astype(np.float32)
+    # directions on texel borders of the 4096 x 2048 sky (phi = 2 pi i / 4096, theta = pi j / 2048) and just beside them
+    i, j = rng.integers(0, 4096, n // 8), rng.integers(1, 2048, n // 8)
+    jitter = rng.choice(np.float32([0, 1e-7, -1e-7, 1e-6, -1e-6, 3e-6, -3e-6, 1e-5]), n // 8)
+    az[: n // 8] = (2 * np.pi * i / 4096 - np.pi + jitter).astype(np.float32)
+    h[n // 8: n // 4] = (-np.cos(np.pi * j / 2048 + jitter)).astype(np.float32)
+    out = api.eval_shading_math(abi.RT_MATH_SKY_TEXEL, az, h)
+    assert not (out < 0).any(), f"{int((out < 0).sum())} lookups accepted a texel that differs from glibc's"
+    handed = float((out[n // 4:] == 0).mean())
+    assert 0.005 < handed < 0.06, f"fraction of random lookups handed to the exact routines: {handed}"
+
+
 def render_pair(name, oracles, gpu_scenes, schedule, W=320, H=192, frames=3):
     from cpu_ray_tracer_b200 import api
     from oracle import porthost
