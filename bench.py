@@ -208,6 +208,25 @@ def cpu_baseline(flat, W, H, gpu_rays_for):
             "sample": f"{frames} frames of the 1920x1080 workload, oracle/rt_oracle.c with OpenMP, {secs:.2f} s"}
 
 
+def alt_build_line(args):
+    """The same timed loop with librt_b200_cudamath.so (build.py --cuda-math: CUDA's expf / atan2f / acosf instead of the restated
+    glibc routines; radiance then matches the reference within the tolerance of tests/test_gpu_parity.py instead of bit for bit),
+    in a child process after this one's measurements.  Reported beside the headline, never as the headline."""
+    alt = os.path.join(ROOT, "cpu-ray-tracer_b200", "librt_b200_cudamath.so")
+    if os.environ.get("RT_B200_LIB") or not os.path.exists(alt):
+        return None
+    try:
+        cmd = [sys.executable, os.path.abspath(__file__), "--steps", str(args.steps), "--warmup", str(args.warmup), "--width", str(args.width),
+               "--height", str(args.height), "--spp", str(args.spp), "--kernel-only"]
+        env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+        env["RT_B200_LIB"] = alt
+        outp = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=300, env=env)
+        res = json.loads(outp.stdout.strip().splitlines()[-1])
+        return {"value": res["value"], "unit": "Mrays/s", "ms_per_step": res["ms_per_step"], "library": res["library"]}
+    except Exception as ex:
+        return {"value": None, "note": f"child run failed: {ex}"}
+
+
 def bench_ours(args):
     import torch
     import torch.distributed as dist
@@ -282,6 +301,9 @@ def bench_ours(args):
         ms = float(tmax[0])
     total_rays, total_paths, launches = float(t[1]), float(t[2]), int(t[3])
     value = total_rays / (ms / 1e3) / 1e6
+    if args.kernel_only:  # child run of alt_build_line(): the device-timed number of another build of the library
+        print(json.dumps({"value": value, "ms_per_step": ms / args.steps, "clocks": clocks, "library": os.path.basename(api.LIB_PATH)}))
+        return None
 
     # ---- e2e: the public Renderer surface with host memory on both sides -------------------------
     host_acc = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
@@ -362,6 +384,7 @@ def bench_ours(args):
                 baseline = cpu_baseline(flat, W, H, gpu_rays_for)
             except Exception as ex:  # never lose the GPU line because the CPU leg failed
                 baseline = {"value": None, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex}"}
+        alt = alt_build_line(args) if world == 1 else None
         out = {"metric": "path-traced Mrays/s @1080p", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f32", "data": "synthetic camera path over the reference's wok/teapot assets "
@@ -375,7 +398,10 @@ def bench_ours(args):
                "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": cam_bytes, "d2h_bytes_per_step": H * W * 16,
                        "api": "GpuRenderer.camera.SetCameraState + render + accumulator read-back to pinned host memory",
                        "checksum": checksum},
-               "roofline": roofline, "cpu_baseline": baseline}
+               "roofline": roofline, "cpu_baseline": baseline,
+               "libm": {"build": "expf / atan2f / acosf of the shading code = glibc 2.39's routines restated on the device (csrc/rt_glibc_math.cuh): "
+                                 "with one Tick per frame the accumulator equals the reference's bit for bit (tests/test_glibc_math.py)",
+                        "cuda_libm_build": alt}}
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
@@ -447,6 +473,7 @@ def main():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--spp", type=int, default=64)
+    ap.add_argument("--kernel-only", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.impl == "reference":
         bench_reference(args)
