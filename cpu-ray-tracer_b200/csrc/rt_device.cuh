@@ -1157,8 +1157,8 @@ __device__ __forceinline__ float3 texture_sample(const DScene& s, int tex, float
 }
 
 // GetSkyColor: file_scene.cpp:142-154.  The texel must be the one the reference picks, i.e. the one glibc's atan2f / acosf lead to.
-// Misses are shaded by one to three lanes of a warp (the MISS state of the stream kernel), so every instruction here is paid almost
-// per ray: running the restated glibc routines for every lookup cost 10-20 % of the whole path tracer (profiles/r1_glibc_math.txt).
+// Half of the bench scene's primary rays end here; running the restated glibc routines (two IEEE divisions and a square root more
+// than CUDA's, no FMA contraction) for every lookup measured 5-20 % on the whole path tracer (profiles/r1_glibc_math.txt).
 // Instead the texel is first computed with CUDA's atan2f / acosf and ACCEPTED only when u * width and v * height are further from
 // a texel border than the two libraries can disagree; otherwise (about 4e-6 * (width + height) of the lookups, 2.5 % for a 4096 x 2048
 // sky) the restated routines decide.  Bound: each library is within 4 ulp of the true angle (CUDA documents 2 ulp for both functions,
