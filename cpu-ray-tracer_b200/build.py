@@ -78,8 +78,23 @@ def build_cuda_math(force=False, verbose=False):
     return CUDA_MATH_LIB
 
 
+def build_ab_variants(verbose=False):
+    """development A/B (tools/ncu_ab_libm.sh): glibc expf with CUDA's sky routines, and the reverse"""
+    outs = []
+    for tag, flags in (("glibcexpf", ["-DRT_B200_GLIBC_SKY=0"]), ("glibcsky", ["-DRT_B200_GLIBC_EXPF=0"])):
+        out = os.path.join(HERE, f"librt_b200_{tag}.so")
+        cmd = [nvcc(), *NVCC_FLAGS, *flags, *[os.path.join(CSRC, f) for f in SOURCES], "-o", out]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True)
+        outs.append(out)
+    return outs
+
+
 if __name__ == "__main__":
-    if "--cuda-math" in sys.argv:
+    if "--ab-variants" in sys.argv:
+        print(build_ab_variants(verbose=True))
+    elif "--cuda-math" in sys.argv:
         print(build_cuda_math(force=True, verbose=True))
     else:
         extra = ["-Xptxas", "-v"] if "-v" in sys.argv else []

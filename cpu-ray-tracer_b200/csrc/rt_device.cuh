@@ -13,13 +13,23 @@
 #ifndef RT_B200_GLIBC_MATH
 #define RT_B200_GLIBC_MATH 1
 #endif
-#if RT_B200_GLIBC_MATH
+// the two halves separately, for A/B builds only (tools/ncu_ab_libm.sh): Beer's law expf, sky lookup atan2f / acosf
+#ifndef RT_B200_GLIBC_EXPF
+#define RT_B200_GLIBC_EXPF RT_B200_GLIBC_MATH
+#endif
+#ifndef RT_B200_GLIBC_SKY
+#define RT_B200_GLIBC_SKY RT_B200_GLIBC_MATH
+#endif
 #include "rt_glibc_math.cuh"
+#if RT_B200_GLIBC_EXPF
 #define rt_expf rt_glibc_expf
+#else
+#define rt_expf expf
+#endif
+#if RT_B200_GLIBC_SKY
 #define rt_atan2f rt_glibc_atan2f
 #define rt_acosf rt_glibc_acosf
 #else
-#define rt_expf expf
 #define rt_atan2f atan2f
 #define rt_acosf acosf
 #endif
@@ -1192,7 +1202,7 @@ __device__ __forceinline__ float3 sky_color(const DScene& s, float3 D)
     const DTexture T = s.textures[tex];
     if (T.width * T.height == 0) return f3(0, 0, 0);
     int x, y;
-#if RT_B200_GLIBC_MATH
+#if RT_B200_GLIBC_SKY
     if (!sky_texel_filtered(T, D, x, y)) sky_texel_exact(T, D, x, y);
 #else
     sky_texel_filtered(T, D, x, y); // CUDA's atan2f / acosf only (<= 2 ulp away: a lookup on a texel border can flip)
