@@ -67,6 +67,23 @@ def test_no_cpu_fallback(flat_scenes):
     assert e.value.status == abi.RT_ERR_NO_DEVICE
 
 
+def test_eval_shading_math_argument_checks():
+    """rt_eval_shading_math validates before it touches the device; without a device it refuses like every compute call"""
+    import numpy as np
+    from cpu_ray_tracer_b200 import abi, api
+    L = api.lib()
+    a = np.zeros(4, np.float32)
+    out = np.zeros(4, np.float32)
+    assert L.rt_eval_shading_math(0, 7, a.ctypes.data, None, out.ctypes.data, 4) == abi.RT_ERR_INVALID
+    assert L.rt_eval_shading_math(0, abi.RT_MATH_ATAN2F, a.ctypes.data, None, out.ctypes.data, 4) == abi.RT_ERR_INVALID
+    assert L.rt_eval_shading_math(0, abi.RT_MATH_EXPF, None, None, out.ctypes.data, 4) == abi.RT_ERR_INVALID
+    assert L.rt_eval_shading_math(99, abi.RT_MATH_EXPF, a.ctypes.data, None, out.ctypes.data, 4) == abi.RT_ERR_NO_DEVICE
+    if api.device_count() == 0:
+        with pytest.raises(api.RtError) as e:
+            api.eval_shading_math(abi.RT_MATH_EXPF, a)
+        assert e.value.status == abi.RT_ERR_NO_DEVICE
+
+
 def test_product_does_not_touch_the_oracle():
     """the oracle is test infrastructure: nothing under the package may import or link it"""
     pkg = os.path.join(ROOT, "cpu-ray-tracer_b200")
