@@ -74,7 +74,9 @@ def ncu_issue_figures():
             "smsp__thread_inst_executed_per_inst_executed.ratio": "active_lanes_per_instruction",
             "smsp__inst_executed.sum": "warp_instructions_per_launch", "l1tex__t_sector_hit_rate.pct": "l1_hit_pct",
             "lts__t_sector_hit_rate.pct": "l2_hit_pct"}
-    out = {"source": os.path.relpath(files[-1], ROOT)}
+    out = {"source": os.path.relpath(files[-1], ROOT),
+           "captured_on": "the CUDA-libm build of the kernel (v7); the default build adds the glibc-exact expf / sky fallback code, "
+                          "not yet captured under ncu (tools/ncu_ab_libm.sh)"}
     for line in open(files[-1]):
         parts = line.split()
         if parts and parts[0] in want:
