@@ -210,11 +210,18 @@ def cpu_baseline(flat, W, H, gpu_rays_for):
             "sample": f"{frames} frames of the 1920x1080 workload, oracle/rt_oracle.c with OpenMP, {secs:.2f} s"}
 
 
-def alt_build_line(args):
-    """The same timed loop with librt_b200_cudamath.so (build.py --cuda-math: CUDA's expf / atan2f / acosf instead of the restated
-    glibc routines; radiance then matches the reference within the tolerance of tests/test_gpu_parity.py instead of bit for bit),
-    in a child process after this one's measurements.  Reported beside the headline, never as the headline."""
-    alt = os.path.join(ROOT, "cpu-ray-tracer_b200", "librt_b200_cudamath.so")
+VARIANT_NOTES = {
+    "cudamath": "CUDA's expf / atan2f / acosf (radiance within the tolerance of tests/test_gpu_parity.py instead of bit-identical)",
+    "glibcexpf": "glibc expf only (sky lookup with CUDA's routines): half of the default build's exact code",
+    "glibcsky": "glibc sky routines only (CUDA's expf): the other half",
+    "ffexpf": "default build with expf in float-float arithmetic (same bits as glibc's, double routine only near rounding boundaries; experimental)",
+}
+
+
+def alt_build_line(args, tag="cudamath"):
+    """The same timed loop with another build of the library (cpu-ray-tracer_b200/build.py VARIANTS, librt_b200_<tag>.so), in a child
+    process after this one's measurements.  Reported beside the headline, never as the headline."""
+    alt = os.path.join(ROOT, "cpu-ray-tracer_b200", f"librt_b200_{tag}.so")
     if os.environ.get("RT_B200_LIB") or not os.path.exists(alt):
         return None
     try:
@@ -224,9 +231,18 @@ def alt_build_line(args):
         env["RT_B200_LIB"] = alt
         outp = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=300, env=env)
         res = json.loads(outp.stdout.strip().splitlines()[-1])
-        return {"value": res["value"], "unit": "Mrays/s", "ms_per_step": res["ms_per_step"], "library": res["library"]}
+        return {"value": res["value"], "unit": "Mrays/s", "ms_per_step": res["ms_per_step"], "library": res["library"], "what": VARIANT_NOTES.get(tag)}
     except Exception as ex:
         return {"value": None, "note": f"child run failed: {ex}"}
+
+
+def alt_build_lines(args):
+    out = {}
+    for tag in VARIANT_NOTES:
+        res = alt_build_line(args, tag)
+        if res is not None:
+            out[tag] = res
+    return out or None
 
 
 def bench_ours(args):
@@ -386,7 +402,7 @@ def bench_ours(args):
                 baseline = cpu_baseline(flat, W, H, gpu_rays_for)
             except Exception as ex:  # never lose the GPU line because the CPU leg failed
                 baseline = {"value": None, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex}"}
-        alt = alt_build_line(args) if world == 1 else None
+        alt = alt_build_lines(args) if world == 1 else None
         out = {"metric": "path-traced Mrays/s @1080p", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f32", "data": "synthetic camera path over the reference's wok/teapot assets "
@@ -403,7 +419,7 @@ def bench_ours(args):
                "roofline": roofline, "cpu_baseline": baseline,
                "libm": {"build": "expf / atan2f / acosf of the shading code = glibc 2.39's routines restated on the device (csrc/rt_glibc_math.cuh): "
                                  "with one Tick per frame the accumulator equals the reference's bit for bit (tests/test_glibc_math.py)",
-                        "cuda_libm_build": alt}}
+                        "variants": alt}}
         print(json.dumps(out))
     if world > 1:
         dist.barrier()

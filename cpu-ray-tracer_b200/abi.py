@@ -11,7 +11,7 @@ RT_SCENE_FLAG_COUNTERS = 1
 RT_INTEGRATOR_WHITTED, RT_INTEGRATOR_PATH = 0, 1
 RT_SEED_REFERENCE_TILE, RT_SEED_PER_PIXEL = 0, 1
 RT_SCHEDULE_AUTO, RT_SCHEDULE_WAVEFRONT, RT_SCHEDULE_STREAMS = 0, 1, 2
-RT_MATH_EXPF, RT_MATH_ACOSF, RT_MATH_ATAN2F, RT_MATH_SKY_TEXEL = 0, 1, 2, 3
+RT_MATH_EXPF, RT_MATH_ACOSF, RT_MATH_ATAN2F, RT_MATH_SKY_TEXEL, RT_MATH_EXPF_FF = 0, 1, 2, 3, 4
 
 f3 = C.c_float * 3
 f16 = C.c_float * 16

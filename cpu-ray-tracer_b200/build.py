@@ -61,39 +61,49 @@ def build(force=False, verbose=False, extra=()):
     return LIB
 
 
-CUDA_MATH_LIB = os.path.join(HERE, "librt_b200_cudamath.so")
+# Build variants of the same library (same ABI, selected with RT_B200_LIB).  bench.py times each of them beside the default build in a
+# child process ("libm.variants" of the bench line); nothing else loads them and the tests run against the default build only.
+#   cudamath   CUDA's expf / atan2f / acosf: radiance within the tolerance of tests/test_gpu_parity.py instead of bit-identical
+#   glibcexpf  glibc expf + CUDA's sky routines        } the two halves of the default build separately:
+#   glibcsky   CUDA's expf + glibc sky routines        } which one carries the cost (profiles/r1_glibc_math.txt)
+#   ffexpf     the default build with expf evaluated in float-float arithmetic (rt_glibc_expf_ff: same bits, double routine only
+#              near rounding boundaries) - experimental
+VARIANTS = {"cudamath": ["-DRT_B200_GLIBC_MATH=0"], "glibcexpf": ["-DRT_B200_GLIBC_SKY=0"], "glibcsky": ["-DRT_B200_GLIBC_EXPF=0"],
+            "ffexpf": ["-DRT_B200_EXPF_FF=1"]}
+
+
+def variant_path(tag):
+    return os.path.join(HERE, f"librt_b200_{tag}.so")
+
+
+CUDA_MATH_LIB = variant_path("cudamath")
+
+
+def build_variants(tags=None, force=False, verbose=False):
+    """compiles the stale ones of the variants in parallel (one nvcc each)"""
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    procs = []
+    for tag in (tags or list(VARIANTS)):
+        out = variant_path(tag)
+        if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+            continue
+        cmd = [nvcc(), *NVCC_FLAGS, *VARIANTS[tag], *[os.path.join(CSRC, f) for f in SOURCES], "-o", out]
+        if verbose:
+            print(" ".join(cmd))
+        procs.append((tag, subprocess.Popen(cmd)))
+    for tag, pr in procs:
+        if pr.wait() != 0:
+            raise RuntimeError(f"nvcc failed for the {tag} variant")
+    return [variant_path(t) for t in (tags or list(VARIANTS))]
 
 
 def build_cuda_math(force=False, verbose=False):
-    """The same library with CUDA's expf / atan2f / acosf instead of the glibc restatements (librt_b200_cudamath.so, selected with
-    RT_B200_LIB): radiance within the tolerance of tests/test_gpu_parity.py instead of bit-identical.  bench.py times it beside the
-    default build; nothing else loads it."""
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    if not force and os.path.exists(CUDA_MATH_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(CUDA_MATH_LIB) for d in deps):
-        return CUDA_MATH_LIB
-    cmd = [nvcc(), *NVCC_FLAGS, "-DRT_B200_GLIBC_MATH=0", *[os.path.join(CSRC, f) for f in SOURCES], "-o", CUDA_MATH_LIB]
-    if verbose:
-        print(" ".join(cmd))
-    subprocess.run(cmd, check=True)
-    return CUDA_MATH_LIB
-
-
-def build_ab_variants(verbose=False):
-    """development A/B (tools/ncu_ab_libm.sh): glibc expf with CUDA's sky routines, and the reverse"""
-    outs = []
-    for tag, flags in (("glibcexpf", ["-DRT_B200_GLIBC_SKY=0"]), ("glibcsky", ["-DRT_B200_GLIBC_EXPF=0"])):
-        out = os.path.join(HERE, f"librt_b200_{tag}.so")
-        cmd = [nvcc(), *NVCC_FLAGS, *flags, *[os.path.join(CSRC, f) for f in SOURCES], "-o", out]
-        if verbose:
-            print(" ".join(cmd))
-        subprocess.run(cmd, check=True)
-        outs.append(out)
-    return outs
+    return build_variants(["cudamath"], force, verbose)[0]
 
 
 if __name__ == "__main__":
-    if "--ab-variants" in sys.argv:
-        print(build_ab_variants(verbose=True))
+    if "--variants" in sys.argv or "--ab-variants" in sys.argv:
+        print(build_variants(force=True, verbose=True))
     elif "--cuda-math" in sys.argv:
         print(build_cuda_math(force=True, verbose=True))
     else:

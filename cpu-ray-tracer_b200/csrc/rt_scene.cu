@@ -115,6 +115,8 @@ __global__ void __launch_bounds__(256) k_eval_shading_math(int fn, const float* 
             sky_texel_exact(T, D, xe, ye);
             out[i] = !accepted ? 0.0f : (x == xe && y == ye) ? 1.0f : -1.0f;
         }
+        else if (fn == RT_MATH_EXPF_FF)
+            out[i] = rt_glibc_expf_ff(a[i]);
         else
             out[i] = fn == RT_MATH_EXPF ? rt_expf(a[i]) : fn == RT_MATH_ACOSF ? rt_acosf(a[i]) : rt_atan2f(a[i], b[i]);
     }
@@ -756,7 +758,7 @@ rt_status rt_measure_gather_bandwidth(int device, size_t working_set_bytes, int 
 
 rt_status rt_eval_shading_math(int device, int fn, const float* a, const float* b, float* out, size_t n)
 {
-    if (fn < RT_MATH_EXPF || fn > RT_MATH_SKY_TEXEL || (n && (!a || !out || (fn >= RT_MATH_ATAN2F && !b)))) { set_error("rt_eval_shading_math: bad argument"); return RT_ERR_INVALID; }
+    if (fn < RT_MATH_EXPF || fn > RT_MATH_EXPF_FF || (n && (!a || !out || ((fn == RT_MATH_ATAN2F || fn == RT_MATH_SKY_TEXEL) && !b)))) { set_error("rt_eval_shading_math: bad argument"); return RT_ERR_INVALID; }
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) { set_error("no such CUDA device (there is no CPU fallback)"); return RT_ERR_NO_DEVICE; }
     if (n == 0) return RT_OK;
@@ -765,7 +767,7 @@ rt_status rt_eval_shading_math(int device, int fn, const float* a, const float* 
     const size_t bytes = n * sizeof(float);
     cudaError_t e = cudaMalloc((void**)&da, bytes);
     if (e == cudaSuccess) e = cudaMalloc((void**)&dout, bytes);
-    if (e == cudaSuccess && fn >= RT_MATH_ATAN2F) e = cudaMalloc((void**)&db, bytes);
+    if (e == cudaSuccess && (fn == RT_MATH_ATAN2F || fn == RT_MATH_SKY_TEXEL)) e = cudaMalloc((void**)&db, bytes);
     if (e == cudaSuccess) e = cudaMemcpy(da, a, bytes, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && db) e = cudaMemcpy(db, b, bytes, cudaMemcpyHostToDevice);
     if (e == cudaSuccess)

@@ -376,6 +376,9 @@ rt_status rt_measure_gather_bandwidth(int device, size_t working_set_bytes, int 
  * routines give, 0 when the lookup was too close to a texel border and was handed to the glibc routines, -1 when the fast lookup
  * accepted a different texel (the parity tests require that this never happens). */
 #define RT_MATH_SKY_TEXEL 3
+/* fn = RT_MATH_EXPF_FF: out[i] = expf(a[i]) through the float-float evaluation of csrc/rt_glibc_math.cuh (experimental build variant
+ * RT_B200_EXPF_FF: same bits as glibc's expf, double arithmetic only near rounding boundaries); b is ignored. */
+#define RT_MATH_EXPF_FF 4
 rt_status rt_eval_shading_math(int device, int fn, const float* a, const float* b, float* out, size_t n);
 
 #ifdef __cplusplus

@@ -41,6 +41,7 @@ def test_alt_build_child_failure_is_reported_not_raised(monkeypatch, tmp_path):
     assert res is None or res["value"] is not None or "failed" in res["note"]  # (a GPU box returns the timed line)
     monkeypatch.setenv("RT_B200_LIB", "/nonexistent.so")
     assert bench.alt_build_line(args) is None  # never recurses when a library override is already active
+    assert bench.alt_build_lines(args) is None
 
 
 def test_reference_arm_prints_the_contract_line():

@@ -5,8 +5,8 @@
 # 1. timing control without a profiler, both builds, same box;  2. one ncu --set full capture of the second k_pt_streams5 launch of
 # each build (source-level, -lineinfo);  3. text summaries + per-source-line hot spots into gpurun_out/ (the .ncu-rep files are
 # removed: two of them exceed what gpurun brings back).  Compare the two *_source_hot.txt files line by line.
-# Before the call, here (no GPU needed): python cpu-ray-tracer_b200/build.py --ab-variants   builds librt_b200_glibcexpf.so (glibc expf,
-# CUDA sky routines) and librt_b200_glibcsky.so (the reverse); when present they are timed too, which splits the cost in two.
+# build() also compiles librt_b200_glibcexpf.so (glibc expf, CUDA sky routines), librt_b200_glibcsky.so (the reverse) and
+# librt_b200_ffexpf.so (float-float expf); when present they are timed too, which splits the cost.
 set -u
 OUT=gpurun_out
 mkdir -p $OUT
@@ -17,7 +17,7 @@ for tag in glibc cuda glibc cuda; do
     timeout 60 python tools/pt_time.py $SCENE 64 >> $OUT/ab_libm_time_$tag.log 2>&1
 done
 cat $OUT/ab_libm_time_glibc.log $OUT/ab_libm_time_cuda.log
-for tag in glibcexpf glibcsky; do
+for tag in glibcexpf glibcsky ffexpf; do
     lib=$PWD/cpu-ray-tracer_b200/librt_b200_$tag.so
     [ -f $lib ] && RT_B200_LIB=$lib timeout 60 python tools/pt_time.py $SCENE 64 2>&1 | sed "s/^/$tag: /" | tee -a $OUT/ab_libm_time_variants.log
 done
