@@ -229,7 +229,7 @@ def alt_build_line(args, tag="cudamath"):
                "--height", str(args.height), "--spp", str(args.spp), "--kernel-only"]
         env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
         env["RT_B200_LIB"] = alt
-        outp = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=300, env=env)
+        outp = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=120, env=env)
         res = json.loads(outp.stdout.strip().splitlines()[-1])
         return {"value": res["value"], "unit": "Mrays/s", "ms_per_step": res["ms_per_step"], "library": res["library"], "what": VARIANT_NOTES.get(tag)}
     except Exception as ex:
