@@ -46,13 +46,16 @@ namespace rtb {
 // Device scene layout (built by rt_scene.cu from the reference-layout arrays of rt_scene_desc)
 //
 //   nodes   "fat" BVH2 nodes, 64 B = 4 x float4, one per INTERIOR node of a reference BVH / TLAS:
-//             n0 = (L.min.x, L.min.y, L.min.z, L.max.x)
-//             n1 = (L.max.y, L.max.z, R.min.x, R.min.y)
-//             n2 = (R.min.z, R.max.x, R.max.y, R.max.z)
+//             n0 = (L.min.x, L.min.y | L.max.x, L.max.y)
+//             n1 = (R.min.x, R.min.y | R.max.x, R.max.y)
+//             n2 = (L.min.z, L.max.z | R.min.z, R.max.z)
 //             n3 = (int left_ref, int right_ref, -, -)
 //           Both child boxes travel in one 64-byte, 64-byte-aligned record (two sectors), so an
 //           interior visit costs one node fetch instead of the reference's parent + 2 children.
 //           The boxes are bit copies of the reference's, the test order is the reference's.
+//           The component order pairs the values that meet the same ray constants - (x, y) planes with
+//           (O.x, O.y) / (rD.x, rD.y), z planes with (O.z, O.z) / (rD.z, rD.z) - so that the 24 subtractions and
+//           multiplications of the two slab tests are 12 packed FADD2 / FMUL2 instructions (slab_both below).
 //   ref     >= 0: index of a fat node.   < 0: leaf, payload = ~ref:
 //             payload == SENTINEL            stack marker: leave the current instance
 //             payload & INSTANCE_BIT         TLAS leaf: instance id = payload & ~INSTANCE_BIT
@@ -72,12 +75,13 @@ constexpr int INSTANCE_BIT = 0x40000000;
 constexpr int LAST_BIT = (int)0x80000000u;
 constexpr int STACK_SIZE = 64; // the reference's own limit: BVHNode* stack[64] (bvh.cpp:227)
 
-struct DMaterial {
+struct __align__(16) DMaterial { // rt_material padded to 48 B: one material = three 128-bit loads
     float reflectivity, refractivity;
     float absorption[3];
     float albedo[3];
     int is_light;
     int texture;
+    int pad[2];
 };
 
 struct DTexture {
@@ -203,6 +207,90 @@ __device__ __forceinline__ float slab(float3 O, float3 rD, float rayT, bool exac
     return (tmax >= tmin && tmin < rayT && tmax > 0) ? tmin : 1e30f;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2, PTX add/sub/mul.rn.f32x2).  Each half is an independent IEEE-754
+// operation, round-to-nearest, denormals kept: the same bits as the scalar instruction, at half the issue slots.
+// ------------------------------------------------------------------------------------------------
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 f2pack(float lo, float hi) { u64 d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi)); return d; }
+__device__ __forceinline__ void f2unpack(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 f2sub(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 f2mul(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+// the ray constants of the slab test, paired the way the node layout pairs the box planes
+struct RaySlab {
+    u64 Oxy, Ozz, Rxy, Rzz;
+};
+__device__ __forceinline__ RaySlab make_ray_slab(float3 O, float3 rD)
+{
+    RaySlab r;
+    r.Oxy = f2pack(O.x, O.y), r.Ozz = f2pack(O.z, O.z), r.Rxy = f2pack(rD.x, rD.y), r.Rzz = f2pack(rD.z, rD.z);
+    return r;
+}
+
+struct FatNode {
+    ulonglong2 a, b, c; // n0, n1, n2 as pairs of packed halves
+    int left, right;
+};
+__device__ __forceinline__ FatNode load_node(const float4* __restrict__ nodes, int cur)
+{
+    const ulonglong2* nd = (const ulonglong2*)(nodes + 4 * (size_t)cur);
+    FatNode n;
+    n.a = __ldg(nd), n.b = __ldg(nd + 1), n.c = __ldg(nd + 2);
+    const int2 ch = __ldg((const int2*)(nd + 3));
+    n.left = ch.x, n.right = ch.y;
+    return n;
+}
+
+// min / max and the hit decision of one box from its six plane distances (second half of slab() above)
+template <bool EXACT>
+__device__ __forceinline__ float slab_finish(float tx1, float tx2, float ty1, float ty2, float tz1, float tz2, float rayT)
+{
+    float tmin, tmax;
+    if (!EXACT)
+    {
+        tmin = fminf(tx1, tx2), tmax = fmaxf(tx1, tx2);
+        tmin = fmaxf(tmin, fminf(ty1, ty2)), tmax = fminf(tmax, fmaxf(ty1, ty2));
+        tmin = fmaxf(tmin, fminf(tz1, tz2)), tmax = fminf(tmax, fmaxf(tz1, tz2));
+    }
+    else
+    {
+        tmin = smin(tx1, tx2), tmax = smax(tx1, tx2);
+        tmin = smax(tmin, smin(ty1, ty2)), tmax = smin(tmax, smax(ty1, ty2));
+        tmin = smax(tmin, smin(tz1, tz2)), tmax = smin(tmax, smax(tz1, tz2));
+    }
+    // (tmax >= tmin && tmin < rayT && tmax > 0) ? tmin : 1e30f as one predicate chain + one select (the compiler's own
+    // translation is a chain of three selects per box); comparisons with a NaN are false, as in C
+    float d;
+    asm("{ .reg .pred p;\n\t"
+        "setp.ge.f32 p, %2, %1;\n\t"
+        "setp.lt.and.f32 p, %1, %3, p;\n\t"
+        "setp.gt.and.f32 p, %2, 0f00000000, p;\n\t"
+        "selp.f32 %0, %1, 0f7149F2CA, p; }" // 0f7149F2CA = 1e30f
+        : "=f"(d) : "f"(tmin), "f"(tmax), "f"(rayT));
+    return d;
+}
+
+// both slab tests of a fat node (bvh.cpp:244-247 calls IntersectAABB on child1, then child2): d1 = left, d2 = right
+template <bool EXACT>
+__device__ __forceinline__ void slab_both(const RaySlab& r, const float rayT, const FatNode& n, float& d1, float& d2)
+{
+    float ltx1, lty1, ltx2, lty2, rtx1, rty1, rtx2, rty2, ltz1, ltz2, rtz1, rtz2;
+    f2unpack(f2mul(f2sub(n.a.x, r.Oxy), r.Rxy), ltx1, lty1);
+    f2unpack(f2mul(f2sub(n.a.y, r.Oxy), r.Rxy), ltx2, lty2);
+    f2unpack(f2mul(f2sub(n.b.x, r.Oxy), r.Rxy), rtx1, rty1);
+    f2unpack(f2mul(f2sub(n.b.y, r.Oxy), r.Rxy), rtx2, rty2);
+    f2unpack(f2mul(f2sub(n.c.x, r.Ozz), r.Rzz), ltz1, ltz2);
+    f2unpack(f2mul(f2sub(n.c.y, r.Ozz), r.Rzz), rtz1, rtz2);
+    d1 = slab_finish<EXACT>(ltx1, ltx2, lty1, lty2, ltz1, ltz2, rayT);
+    d2 = slab_finish<EXACT>(rtx1, rtx2, rty1, rty2, rtz1, rtz2, rayT);
+}
+__device__ __forceinline__ void slab_both(const RaySlab& r, const float rayT, const bool exact, const FatNode& n, float& d1, float& d2)
+{
+    if (exact) slab_both<true>(r, rayT, n, d1, d2);
+    else slab_both<false>(r, rayT, n, d1, d2);
+}
+
 // Moeller-Trumbore: bvh.cpp:203-222 / blas_bvh.cpp:281-300.  Returns true when the hit was accepted.
 __device__ __forceinline__ bool intersect_tri(float3 O, float3 D, float3 v0, float3 edge1, float3 edge2,
     float& rayT, float& outU, float& outV)
@@ -239,8 +327,9 @@ __device__ __forceinline__ bool intersect_tri(float3 O, float3 D, float3 v0, flo
 template <bool ANYHIT, bool COUNTERS>
 __device__ __forceinline__ void traverse(const DScene& s, const float3 wO, const float3 wD, HitRec& hit)
 {
-    float3 O = wO, D = wD, rD = recip(wD);
+    float3 O = wO, D = wD;
     bool exact = needs_exact_slab(O, D);
+    RaySlab rs = make_ray_slab(O, recip(D));
     int instObj = s.flat_obj_idx;
     int stack[STACK_SIZE];
     int sp = 0;
@@ -252,12 +341,10 @@ __device__ __forceinline__ void traverse(const DScene& s, const float3 wO, const
         if (cur >= 0)
         {
             if (COUNTERS) hit.traversed++;
-            const float4* n = nodes + 4 * (size_t)cur;
-            const float4 n0 = __ldg(n), n1 = __ldg(n + 1), n2 = __ldg(n + 2);
-            const int4 n3 = __ldg((const int4*)(n + 3));
-            float d1 = slab(O, rD, hit.t, exact, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y);
-            float d2 = slab(O, rD, hit.t, exact, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w);
-            int c1 = n3.x, c2 = n3.y;
+            const FatNode n = load_node(nodes, cur);
+            float d1, d2;
+            slab_both(rs, hit.t, exact, n, d1, d2);
+            int c1 = n.left, c2 = n.right;
             if (d1 > d2) { const float tf = d1; d1 = d2; d2 = tf; const int tc = c1; c1 = c2; c2 = tc; }
             if (d1 == 1e30f)
             {
@@ -275,8 +362,9 @@ __device__ __forceinline__ void traverse(const DScene& s, const float3 wO, const
         if (payload == SENTINEL_PAYLOAD)
         {
             // leave the instance: blas_bvh.cpp:385-388 restores O, D, rD
-            O = wO, D = wD, rD = recip(wD);
+            O = wO, D = wD;
             exact = needs_exact_slab(O, D);
+            rs = make_ray_slab(O, recip(D));
         }
         else if (payload & INSTANCE_BIT)
         {
@@ -292,8 +380,8 @@ __device__ __forceinline__ void traverse(const DScene& s, const float3 wO, const
             D = f3((wD.x * r0.x + wD.y * r0.y) + wD.z * r0.z,
                    (wD.x * r1.x + wD.y * r1.y) + wD.z * r1.z,
                    (wD.x * r2.x + wD.y * r2.y) + wD.z * r2.z);
-            rD = recip(D);
             exact = needs_exact_slab(O, D);
+            rs = make_ray_slab(O, recip(D));
             instObj = meta.y;
             stack[sp++] = ~SENTINEL_PAYLOAD;
             cur = meta.x;
@@ -375,7 +463,8 @@ __device__ __forceinline__ void trace_queue(const DScene& s, Src& src, const int
     const float4* __restrict__ tris = s.tris;
     int stack[STACK_SIZE];
     int sp = 0, cur = 0, rayIdx = -1, instObj = s.flat_obj_idx;
-    float3 O = f3(0, 0, 0), D = f3(0, 0, 0), rD = f3(0, 0, 0);
+    float3 O = f3(0, 0, 0), D = f3(0, 0, 0);
+    RaySlab rs = make_ray_slab(O, O);
     bool exact = false, has = false, queueEmpty = false;
     HitRec hit;
     hit.t = 0, hit.u = 0, hit.v = 0, hit.obj = -1, hit.tri = -1, hit.traversed = 0, hit.tested = 0;
@@ -417,7 +506,7 @@ __device__ __forceinline__ void trace_queue(const DScene& s, Src& src, const int
                     if (done) { src.store(rayIdx, hit); has = false; }
                     else
                     {
-                        rD = recip(D), exact = needs_exact_slab(O, D);
+                        rs = make_ray_slab(O, recip(D)), exact = needs_exact_slab(O, D);
                         sp = 0, cur = s.root_ref, instObj = s.flat_obj_idx;
                     }
                 }
@@ -430,12 +519,10 @@ __device__ __forceinline__ void trace_queue(const DScene& s, Src& src, const int
         if (cur >= 0)
         {
             if (COUNTERS) hit.traversed++;
-            const float4* nd = nodes + 4 * (size_t)cur;
-            const float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2);
-            const int4 n3 = __ldg((const int4*)(nd + 3));
-            float d1 = slab(O, rD, hit.t, exact, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y);
-            float d2 = slab(O, rD, hit.t, exact, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w);
-            int c1 = n3.x, c2 = n3.y;
+            const FatNode nd = load_node(nodes, cur);
+            float d1, d2;
+            slab_both(rs, hit.t, exact, nd, d1, d2);
+            int c1 = nd.left, c2 = nd.right;
             if (d1 > d2) { const float tf = d1; d1 = d2; d2 = tf; const int tc = c1; c1 = c2; c2 = tc; }
             if (d1 == 1e30f) pop = true;
             else
@@ -451,7 +538,7 @@ __device__ __forceinline__ void trace_queue(const DScene& s, Src& src, const int
             if (payload == SENTINEL_PAYLOAD)
             {
                 src.world(rayIdx, O, D); // blas_bvh.cpp:385-388
-                rD = recip(D), exact = needs_exact_slab(O, D);
+                rs = make_ray_slab(O, recip(D)), exact = needs_exact_slab(O, D);
             }
             else if (payload & INSTANCE_BIT)
             {
@@ -466,7 +553,7 @@ __device__ __forceinline__ void trace_queue(const DScene& s, Src& src, const int
                 D = f3((wD.x * r0.x + wD.y * r0.y) + wD.z * r0.z,
                        (wD.x * r1.x + wD.y * r1.y) + wD.z * r1.z,
                        (wD.x * r2.x + wD.y * r2.y) + wD.z * r2.z);
-                rD = recip(D), exact = needs_exact_slab(O, D);
+                rs = make_ray_slab(O, recip(D)), exact = needs_exact_slab(O, D);
                 instObj = meta.y;
                 stack[sp++] = ~SENTINEL_PAYLOAD;
                 cur = meta.x;
@@ -769,14 +856,15 @@ struct GridCursor {
 template <class Blas>
 struct TlasCursor {
     Blas blas;
-    float3 Ol, Dl, rDw;
+    float3 Ol, Dl;
+    RaySlab rsW;
     bool exactW, inBlas;
     int cur, sp;
     int stack[STACK_SIZE];
 
     __device__ __forceinline__ bool start(const DScene& s, const float3 O, const float3 D, const HitRec&, int, int)
     {
-        rDw = recip(D), exactW = needs_exact_slab(O, D), cur = s.root_ref, sp = 0, inBlas = false;
+        rsW = make_ray_slab(O, recip(D)), exactW = needs_exact_slab(O, D), cur = s.root_ref, sp = 0, inBlas = false;
         blas.runCount = 0;
         return false;
     }
@@ -801,12 +889,10 @@ struct TlasCursor {
         if (cur >= 0)
         {
             if (COUNTERS) hit.traversed++;
-            const float4* n = s.nodes + 4 * (size_t)cur;
-            const float4 n0 = __ldg(n), n1 = __ldg(n + 1), n2 = __ldg(n + 2);
-            const int4 n3 = __ldg((const int4*)(n + 3));
-            float d1 = slab(O, rDw, hit.t, exactW, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y);
-            float d2 = slab(O, rDw, hit.t, exactW, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w);
-            int c1 = n3.x, c2 = n3.y;
+            const FatNode n = load_node(s.nodes, cur);
+            float d1, d2;
+            slab_both(rsW, hit.t, exactW, n, d1, d2);
+            int c1 = n.left, c2 = n.right;
             if (d1 > d2) { const float tf = d1; d1 = d2; d2 = tf; const int tc = c1; c1 = c2; c2 = tc; }
             if (d1 == 1e30f) return pop_tlas();
             cur = c1;
@@ -855,17 +941,15 @@ __device__ __forceinline__ void accel_traverse(const DScene& s, const float3 O, 
 // One interior-node visit of the ordered traversal (bvh.cpp:242-257) on register state: both child boxes from one
 // 64-byte record, near child first, left on ties, far child pushed only when hit; selects instead of branches.
 template <bool EXACT>
-__device__ __forceinline__ void node_step(const float4* __restrict__ nodes, const float3 O, const float3 rD, const float ht,
+__device__ __forceinline__ void node_step(const float4* __restrict__ nodes, const RaySlab& rs, const float ht,
     int* stack, int& sp, int& cur, bool& end)
 {
-    const float4* nd = nodes + 4 * (size_t)cur;
-    const float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2);
-    const int4 n3 = __ldg((const int4*)(nd + 3));
-    const float a1 = slab(O, rD, ht, EXACT, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y);
-    const float a2 = slab(O, rD, ht, EXACT, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w);
+    const FatNode n = load_node(nodes, cur);
+    float a1, a2;
+    slab_both<EXACT>(rs, ht, n, a1, a2);
     const bool swp = a1 > a2;
     const float d1 = swp ? a2 : a1, d2 = swp ? a1 : a2;
-    const int c1 = swp ? n3.y : n3.x, c2 = swp ? n3.x : n3.y;
+    const int c1 = swp ? n.right : n.left, c2 = swp ? n.left : n.right;
     const bool miss = d1 == 1e30f, both = !miss && d2 != 1e30f;
     const int top = stack[sp > 0 ? sp - 1 : 0];
     if (both) stack[sp] = c2;
@@ -887,7 +971,8 @@ __device__ __forceinline__ void trace_queue_voted(const DScene& s, Src& src, con
     const float4* __restrict__ tris = s.tris;
     int stack[STACK_SIZE];
     int sp = 0, cur = 0, rayIdx = -1, instObj = s.flat_obj_idx;
-    float3 O = f3(0, 0, 0), D = f3(0, 0, 0), rD = f3(0, 0, 0);
+    float3 O = f3(0, 0, 0), D = f3(0, 0, 0);
+    RaySlab rs = make_ray_slab(O, O);
     bool exact = false, has = false, queueEmpty = false;
     HitRec hit;
     hit.t = 0, hit.u = 0, hit.v = 0, hit.obj = -1, hit.tri = -1, hit.traversed = 0, hit.tested = 0;
@@ -929,7 +1014,7 @@ __device__ __forceinline__ void trace_queue_voted(const DScene& s, Src& src, con
                     if (done) { src.store(rayIdx, hit); has = false; }
                     else
                     {
-                        rD = recip(D), exact = needs_exact_slab(O, D);
+                        rs = make_ray_slab(O, recip(D)), exact = needs_exact_slab(O, D);
                         sp = 0, cur = s.root_ref, instObj = s.flat_obj_idx;
                     }
                 }
@@ -948,8 +1033,8 @@ __device__ __forceinline__ void trace_queue_voted(const DScene& s, Src& src, con
                 {
                     if (COUNTERS) hit.traversed++;
                     bool end;
-                    if (anyExact) node_step<true>(nodes, O, rD, hit.t, stack, sp, cur, end);
-                    else node_step<false>(nodes, O, rD, hit.t, stack, sp, cur, end);
+                    if (anyExact) node_step<true>(nodes, rs, hit.t, stack, sp, cur, end);
+                    else node_step<false>(nodes, rs, hit.t, stack, sp, cur, end);
                     if (end) src.store(rayIdx, hit), has = false;
                     inNode = !end && cur >= 0;
                 }
@@ -962,7 +1047,7 @@ __device__ __forceinline__ void trace_queue_voted(const DScene& s, Src& src, con
             if (payload == SENTINEL_PAYLOAD)
             {
                 src.world(rayIdx, O, D); // blas_bvh.cpp:385-388
-                rD = recip(D), exact = needs_exact_slab(O, D);
+                rs = make_ray_slab(O, recip(D)), exact = needs_exact_slab(O, D);
             }
             else if (payload & INSTANCE_BIT)
             {
@@ -977,7 +1062,7 @@ __device__ __forceinline__ void trace_queue_voted(const DScene& s, Src& src, con
                 D = f3((wD.x * r0.x + wD.y * r0.y) + wD.z * r0.z,
                        (wD.x * r1.x + wD.y * r1.y) + wD.z * r1.z,
                        (wD.x * r2.x + wD.y * r2.y) + wD.z * r2.z);
-                rD = recip(D), exact = needs_exact_slab(O, D);
+                rs = make_ray_slab(O, recip(D)), exact = needs_exact_slab(O, D);
                 instObj = meta.y;
                 stack[sp++] = ~SENTINEL_PAYLOAD;
                 cur = meta.x;
@@ -1191,6 +1276,17 @@ __device__ __forceinline__ void sky_texel_exact(const DTexture& T, float3 D, int
     float fx, fy;
     texture_texel(T, phi * RT_INV2PI, theta * RT_INVPI, x, y, fx, fy);
 }
+// The same, out of line: ~2 % of the sky lookups get here, and inlined the two restated glibc routines (IEEE divisions, a square root,
+// fdlibm's branch trees) cost the hot kernels 7 KB of SASS and registers on every path (round-1 A/B: +5 ms of 68 on the bench job,
+// profiles/r2_libm_ab_*).  Returns x | y << 16.
+static __device__ __noinline__ int sky_texel_exact_cold(int width, int height, float dx, float dy, float dz)
+{
+    DTexture T;
+    T.pixels = nullptr, T.width = width, T.height = height;
+    int x, y;
+    sky_texel_exact(T, f3(dx, dy, dz), x, y);
+    return x | (y << 16);
+}
 
 __device__ __forceinline__ bool sky_texel_filtered(const DTexture& T, float3 D, int& x, int& y)
 {
@@ -1209,12 +1305,29 @@ __device__ __forceinline__ float3 sky_color(const DScene& s, float3 D)
     if (T.width * T.height == 0) return f3(0, 0, 0);
     int x, y;
 #if RT_B200_GLIBC_SKY
-    if (!sky_texel_filtered(T, D, x, y)) sky_texel_exact(T, D, x, y);
+    if (!sky_texel_filtered(T, D, x, y))
+    {
+        if (T.width < 65536 && T.height < 32768)
+        {
+            const int xy = sky_texel_exact_cold(T.width, T.height, D.x, D.y, D.z);
+            x = xy & 0xffff, y = xy >> 16;
+        }
+        else sky_texel_exact(T, D, x, y);
+    }
 #else
     sky_texel_filtered(T, D, x, y); // CUDA's atan2f / acosf only (<= 2 ulp away: a lookup on a texel border can flip)
 #endif
     return texture_fetch(T, x, y);
 }
+
+// Beer's law factors exp(-absorption * t) (3. PathTracer/renderer.cpp:76-80, 2. WhittedStyle/renderer.cpp:81-88).  The restated glibc
+// expf works in double precision; only rays that travelled inside glass get here, so it is kept out of line and the shading code
+// of the hot kernels carries no FP64 instructions.
+#if RT_B200_GLIBC_EXPF
+static __device__ __noinline__ float3 beer_scale(float ax, float ay, float az) { return f3(rt_expf(ax), rt_expf(ay), rt_expf(az)); }
+#else
+__device__ __forceinline__ float3 beer_scale(float ax, float ay, float az) { return f3(rt_expf(ax), rt_expf(ay), rt_expf(az)); }
+#endif
 
 struct ShadeHit {
     float3 N, albedo, absorption;

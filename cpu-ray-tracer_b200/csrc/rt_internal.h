@@ -50,6 +50,7 @@ struct rt_scene {
     rtb::DTexture* textures = nullptr;
     uint32_t* tex_pixels = nullptr;
     size_t node_count = 0, tri_count = 0, inst_count = 0;
+    int stack_entries = 0; // most far children one ray can have pending (bound from the tree depths, rt_scene_create)
     size_t bytes_geometry = 0, bytes_textures = 0;
     // scratch for the host-buffer entry points (rt_find_nearest / rt_is_occluded)
     std::mutex scratch_mutex;

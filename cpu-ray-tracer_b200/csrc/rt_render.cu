@@ -213,7 +213,7 @@ __device__ __forceinline__ int pt_surface(const DScene& s, const int depthLimit,
     if (inside)
     {
         const float3 a = h.absorption * -t; // renderer.cpp:76-80
-        medium_scale = f3(rt_expf(a.x), rt_expf(a.y), rt_expf(a.z));
+        medium_scale = beer_scale(a.x, a.y, a.z);
     }
     const float r = random_float(seed);
     nInside = false;
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(128) k_pt_pilot(const PTState p, const DScene 
     }
 }
 
-// Stream kernel, version 2: per-lane state machine with warp-level action voting.
+// Stream kernels: per-lane state machine with warp-level action voting.
 //
 // ncu on version 1 (profiles/r1_v3_k_pt_streams_v1_ncu_full.txt): issue slots 69 % busy but only 7.9 of
 // 32 lanes active per instruction, because a warp waits for its slowest ray before it shades and lanes
@@ -402,192 +402,8 @@ __global__ void __launch_bounds__(128) k_pt_pilot(const PTState p, const DScene 
 // and each loop iteration the warp executes the ONE action most lanes are waiting for (ballot / popc),
 // so the lanes that take part in an instruction are a majority instead of the leftovers.  Per lane the
 // order of node visits, triangle tests, RNG draws and bounces is unchanged.
+// (Version 2, the first voted kernel, was removed in round 2: profiles/r1_stream_kernel_* keep its numbers.)
 enum { ST_DEAD = 0, ST_NODE = 1, ST_LEAF = 2, ST_SHADE = 3 };
-
-template <bool TLAS>
-__global__ void __launch_bounds__(128) k_pt_streams2(const PTState p, const DScene s, const DCamera cam,
-    const int* __restrict__ tileOrder, const int frames, int* __restrict__ streamCounter)
-{
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int total = p.slots;
-    const float4* __restrict__ nodes = s.nodes;
-    const float4* __restrict__ tris = s.tris;
-    bool poolEmpty = false;
-    int state = ST_DEAD;
-    // stream
-    int tile = 0, pix = 0, depth = 0;
-    bool inside = false;
-    uint32_t seed = 0;
-    float3 wO = f3(0, 0, 0), wD = f3(0, 0, 0); // the ray in world space
-    float3 wst[STREAM_MAX_DEPTH];
-    // traversal
-    float3 O = f3(0, 0, 0), D = f3(0, 0, 0), rD = f3(0, 0, 0); // the ray in the space being traversed
-    bool exact = false;
-    int stack[STACK_SIZE];
-    int sp = 0, cur = 0, instObj = -1;
-    float ht = 0, hu = 0, hv = 0;
-    int hobj = -1, htri = -1;
-    unsigned long long rays = 0;
-
-    // FindNearest prologue for the ray (wO, wD): light quad, floor plane (file_scene.cpp:172-173), then the BVH
-#define RT_START_RAY()                                                                         \
-    {                                                                                          \
-        ht = 1e34f, hu = 0, hv = 0, hobj = -1, htri = -1;                                      \
-        float tq;                                                                              \
-        if (quad_test(s, wO, wD, ht, tq)) ht = tq, hobj = 0;                                   \
-        const float3 fn = f3(s.floor_n[0], s.floor_n[1], s.floor_n[2]);                        \
-        const float tp = -(dot(wO, fn) + s.floor_d) / (dot(wD, fn));                           \
-        if (tp < ht && tp > 0) ht = tp, hobj = 1;                                              \
-        O = wO, D = wD, rD = recip(wD), exact = needs_exact_slab(wO, wD);                      \
-        sp = 0, cur = s.root_ref, instObj = s.flat_obj_idx;                                    \
-        state = cur >= 0 ? ST_NODE : ST_LEAF;                                                  \
-        rays++;                                                                                \
-    }
-
-    while (true)
-    {
-        const unsigned mDead = __ballot_sync(FULL, state == ST_DEAD);
-        if (mDead && !poolEmpty)
-        {
-            const int nIdle = __popc(mDead);
-            const int leader = __ffs(mDead) - 1;
-            int base = 0;
-            if (lane == leader) base = atomicAdd(streamCounter, nIdle);
-            base = __shfl_sync(FULL, base, leader);
-            if (base + nIdle >= total) poolEmpty = true;
-            const int stream = base + __popc(mDead & ((1u << lane) - 1));
-            if (state == ST_DEAD && stream < total)
-            {
-                const int k = stream / frames, frame = stream - k * frames;
-                tile = p.tileBegin + (tileOrder ? tileOrder[k] : k) * p.tileStep;
-                seed = pt_seed(p, tile, p.firstSpp + frame * p.stride);
-                pix = 0, depth = 0, inside = false;
-                const int tx = tile % p.tilesX, ty = tile / p.tilesX;
-                const float jy = random_float(seed), jx = random_float(seed);
-                wD = primary_dir(cam, (float)(tx * 16) + jx, (float)(ty * 16) + jy);
-                wO = cam.pos;
-                RT_START_RAY();
-            }
-        }
-        const unsigned mNode = __ballot_sync(FULL, state == ST_NODE);
-        const unsigned mLeaf = __ballot_sync(FULL, state == ST_LEAF);
-        const unsigned mShade = __ballot_sync(FULL, state == ST_SHADE);
-        if ((mNode | mLeaf | mShade) == 0) break;
-        const int nN = __popc(mNode), nL = __popc(mLeaf), nS = __popc(mShade);
-        if (nN >= nL && nN >= nS)
-        {
-            if (state == ST_NODE)
-            {
-                const float4* nd = nodes + 4 * (size_t)cur;
-                const float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2);
-                const int4 n3 = __ldg((const int4*)(nd + 3));
-                float d1 = slab(O, rD, ht, exact, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y);
-                float d2 = slab(O, rD, ht, exact, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w);
-                int c1 = n3.x, c2 = n3.y;
-                if (d1 > d2) { const float tf = d1; d1 = d2; d2 = tf; const int tc = c1; c1 = c2; c2 = tc; }
-                if (d1 == 1e30f)
-                {
-                    if (sp == 0) state = ST_SHADE;
-                    else cur = stack[--sp], state = cur >= 0 ? ST_NODE : ST_LEAF;
-                }
-                else
-                {
-                    cur = c1, state = c1 >= 0 ? ST_NODE : ST_LEAF;
-                    if (d2 != 1e30f) stack[sp++] = c2;
-                }
-            }
-        }
-        else if (nL >= nS)
-        {
-            if (state == ST_LEAF)
-            {
-                const int payload = ~cur;
-                bool pop = true;
-                if (TLAS && payload == SENTINEL_PAYLOAD)
-                {
-                    O = wO, D = wD, rD = recip(wD), exact = needs_exact_slab(wO, wD); // blas_bvh.cpp:385-388
-                }
-                else if (TLAS && (payload & INSTANCE_BIT))
-                {
-                    const float4* I = s.inst + 4 * (size_t)(payload & ~INSTANCE_BIT);
-                    const float4 r0 = __ldg(I), r1 = __ldg(I + 1), r2 = __ldg(I + 2);
-                    const int4 meta = __ldg((const int4*)(I + 3));
-                    O = f3((wO.x * r0.x + wO.y * r0.y) + (wO.z * r0.z + r0.w),
-                           (wO.x * r1.x + wO.y * r1.y) + (wO.z * r1.z + r1.w),
-                           (wO.x * r2.x + wO.y * r2.y) + (wO.z * r2.z + r2.w));
-                    D = f3((wD.x * r0.x + wD.y * r0.y) + wD.z * r0.z,
-                           (wD.x * r1.x + wD.y * r1.y) + wD.z * r1.z,
-                           (wD.x * r2.x + wD.y * r2.y) + wD.z * r2.z);
-                    rD = recip(D), exact = needs_exact_slab(O, D);
-                    instObj = meta.y;
-                    stack[sp++] = ~SENTINEL_PAYLOAD;
-                    cur = meta.x, state = cur >= 0 ? ST_NODE : ST_LEAF;
-                    pop = false;
-                }
-                else
-                {
-                    int slot = payload;
-                    while (true)
-                    {
-                        const float4* T = tris + 3 * (size_t)slot;
-                        const float4 t0 = __ldg(T), t1 = __ldg(T + 1), t2 = __ldg(T + 2);
-                        const int tag = __float_as_int(t0.w);
-                        if (intersect_tri(O, D, f3(t0.x, t0.y, t0.z), f3(t1.x, t1.y, t1.z), f3(t2.x, t2.y, t2.z), ht, hu, hv))
-                        {
-                            htri = tag & ~LAST_BIT;
-                            hobj = instObj >= 0 ? instObj : __float_as_int(t1.w);
-                        }
-                        if (tag & LAST_BIT) break;
-                        slot++;
-                    }
-                }
-                if (pop)
-                {
-                    if (sp == 0) state = ST_SHADE;
-                    else cur = stack[--sp], state = cur >= 0 ? ST_NODE : ST_LEAF;
-                }
-            }
-        }
-        else
-        {
-            if (state == ST_SHADE)
-            {
-                float3 L, w, nO, nD;
-                bool nInside;
-                if (!pt_bounce(s, p.eps, p.depthLimit, wO, wD, inside, depth, ht, hu, hv, hobj, htri, seed, L, w, nO, nD, nInside))
-                {
-                    wst[depth] = w;
-                    depth++, wO = nO, wD = nD, inside = nInside;
-                    RT_START_RAY();
-                }
-                else
-                {
-                    for (int d = depth - 1; d >= 0; d--) L = wst[d] * L;
-                    const int tx = tile % p.tilesX, ty = tile / p.tilesX;
-                    const int px = pix / p.passes; // pix counts samples: `passes` consecutive ones per pixel
-                    const int x = tx * 16 + (px & 15), y = ty * 16 + (px >> 4);
-                    float* a = (float*)(p.accum + (x + (size_t)y * p.W));
-                    atomicAdd(a + 0, L.x), atomicAdd(a + 1, L.y), atomicAdd(a + 2, L.z);
-                    pix++;
-                    if (pix < 256 * p.passes)
-                    {
-                        const int npx = pix / p.passes;
-                        const int nx = tx * 16 + (npx & 15), ny = ty * 16 + (npx >> 4);
-                        const float jy = random_float(seed), jx = random_float(seed);
-                        wD = primary_dir(cam, (float)nx + jx, (float)ny + jy);
-                        wO = cam.pos, depth = 0, inside = false;
-                        RT_START_RAY();
-                    }
-                    else state = ST_DEAD;
-                }
-            }
-        }
-    }
-#undef RT_START_RAY
-    for (int off = 16; off; off >>= 1) rays += __shfl_xor_sync(FULL, rays, off);
-    if (lane == 0) atomicAdd(p.counters, rays);
-}
 
 // Stream kernel for FileScene's other accelerators (KD-tree, uniform grid): the same schedule as version 2 - one
 // (tile, frame) RNG stream per lane, path state in registers, lanes pull the next stream when theirs ends - with
@@ -615,6 +431,7 @@ __global__ void __launch_bounds__(128) k_pt_streams_alt(const PTState p, const D
     HitRec hit;
     hit.t = 0, hit.u = 0, hit.v = 0, hit.obj = -1, hit.tri = -1, hit.traversed = 0, hit.tested = 0;
     unsigned long long rays = 0;
+    int frameIdx = 0; // frame of the launch this lane's stream belongs to (its samples go to that frame's images)
 
     // FindNearest prologue for the ray (wO, wD): light quad, floor plane (file_scene.cpp:172-173), then the accelerator
 #define RT_START_RAY()                                                                         \
@@ -646,7 +463,7 @@ __global__ void __launch_bounds__(128) k_pt_streams_alt(const PTState p, const D
                 const int k = stream / frames, frame = stream - k * frames;
                 tile = p.tileBegin + (tileOrder ? tileOrder[k] : k) * p.tileStep;
                 seed = pt_seed(p, tile, p.firstSpp + frame * p.stride);
-                pix = 0, depth = 0, inside = false;
+                pix = 0, depth = 0, inside = false, frameIdx = frame;
                 const int tx = tile % p.tilesX, ty = tile / p.tilesX;
                 const float jy = random_float(seed), jx = random_float(seed);
                 wD = primary_dir(cam, (float)(tx * 16) + jx, (float)(ty * 16) + jy);
@@ -699,8 +516,13 @@ __global__ void __launch_bounds__(128) k_pt_streams_alt(const PTState p, const D
                 const int tx = tile % p.tilesX, ty = tile / p.tilesX;
                 const int px = pix / p.passes; // pix counts samples: `passes` consecutive ones per pixel
                 const int x = tx * 16 + (px & 15), y = ty * 16 + (px >> 4);
-                float* a = (float*)(p.accum + (x + (size_t)y * p.W));
-                atomicAdd(a + 0, L.x), atomicAdd(a + 1, L.y), atomicAdd(a + 2, L.z);
+                if (p.frameBuf) // the sample's own (frame, pass) image: added to the accumulator in order by k_sum_frames
+                    p.frameBuf[(size_t)(frameIdx * p.passes + pix % p.passes) * ((size_t)p.W * p.H) + (x + (size_t)y * p.W)] = make_float4(L.x, L.y, L.z, 0);
+                else
+                {
+                    float* a = (float*)(p.accum + (x + (size_t)y * p.W));
+                    atomicAdd(a + 0, L.x), atomicAdd(a + 1, L.y), atomicAdd(a + 2, L.z);
+                }
                 pix++;
                 if (pix < 256 * p.passes)
                 {
@@ -759,7 +581,8 @@ __global__ void __launch_bounds__(128, MINB) k_pt_streams5(const PTState p, cons
     float3 wO = f3(0, 0, 0), wD = f3(0, 0, 0); // the ray in world space
     float3 wst[STREAM_MAX_DEPTH];
     // traversal
-    float3 O = f3(0, 0, 0), D = f3(0, 0, 0), rD = f3(0, 0, 0); // the ray in the space being traversed (TLAS only; flat: wO, wD)
+    float3 O = f3(0, 0, 0), D = f3(0, 0, 0); // the ray in the space being traversed (TLAS only; flat: wO, wD)
+    RaySlab rs = make_ray_slab(wO, wO);
     bool exact = false;
     int stack[STACK_SIZE];
     int sp = 0, cur = 0, instObj = -1;
@@ -824,14 +647,14 @@ __global__ void __launch_bounds__(128, MINB) k_pt_streams5(const PTState p, cons
                 {
                     do
                     {
-                        if (inNode) node_step<true>(nodes, TO, rD, ht, stack, sp, cur, end), inNode = !end && cur >= 0;
+                        if (inNode) node_step<true>(nodes, rs, ht, stack, sp, cur, end), inNode = !end && cur >= 0;
                     } while (__popc(__ballot_sync(FULL, inNode)) >= keep);
                 }
                 else
                 {
                     do
                     {
-                        if (inNode) node_step<false>(nodes, TO, rD, ht, stack, sp, cur, end), inNode = !end && cur >= 0;
+                        if (inNode) node_step<false>(nodes, rs, ht, stack, sp, cur, end), inNode = !end && cur >= 0;
                     } while (__popc(__ballot_sync(FULL, inNode)) >= keep);
                 }
                 if (state == ST_NODE) state = end ? (hobj == -1 ? ST_MISS : ST_SHADE) : (cur >= 0 ? ST_NODE : ST_LEAF);
@@ -844,7 +667,7 @@ __global__ void __launch_bounds__(128, MINB) k_pt_streams5(const PTState p, cons
                     bool pop = true;
                     if (TLAS && payload == SENTINEL_PAYLOAD)
                     {
-                        O = wO, D = wD, rD = recip(wD), exact = needs_exact_slab(wO, wD); // blas_bvh.cpp:385-388
+                        O = wO, D = wD, rs = make_ray_slab(wO, recip(wD)), exact = needs_exact_slab(wO, wD); // blas_bvh.cpp:385-388
                     }
                     else if (TLAS && (payload & INSTANCE_BIT))
                     {
@@ -857,7 +680,7 @@ __global__ void __launch_bounds__(128, MINB) k_pt_streams5(const PTState p, cons
                         D = f3((wD.x * r0.x + wD.y * r0.y) + wD.z * r0.z,
                                (wD.x * r1.x + wD.y * r1.y) + wD.z * r1.z,
                                (wD.x * r2.x + wD.y * r2.y) + wD.z * r2.z);
-                        rD = recip(D), exact = needs_exact_slab(O, D);
+                        rs = make_ray_slab(O, recip(D)), exact = needs_exact_slab(O, D);
                         instObj = meta.y;
                         stack[sp++] = ~SENTINEL_PAYLOAD;
                         cur = meta.x, state = cur >= 0 ? ST_NODE : ST_LEAF;
@@ -955,7 +778,7 @@ __global__ void __launch_bounds__(128, MINB) k_pt_streams5(const PTState p, cons
             const float tp = -(dot(wO, fn) + s.floor_d) / (dot(wD, fn));
             if (tp < ht && tp > 0) ht = tp, hobj = 1;
             if (TLAS) O = wO, D = wD;
-            rD = recip(wD), exact = needs_exact_slab(wO, wD);
+            rs = make_ray_slab(wO, recip(wD)), exact = needs_exact_slab(wO, wD);
             sp = 0, cur = s.root_ref, instObj = s.flat_obj_idx;
             state = cur >= 0 ? ST_NODE : ST_LEAF;
             rays++;
@@ -966,6 +789,12 @@ __global__ void __launch_bounds__(128, MINB) k_pt_streams5(const PTState p, cons
     for (int off = 16; off; off >>= 1) rays += __shfl_xor_sync(FULL, rays, off);
     if (lane == 0) atomicAdd(p.counters, (unsigned long long)rays);
 }
+
+} // namespace rtb
+
+#include "rt_streams8.cuh"
+
+namespace rtb {
 
 // ---------------------------------------------------------------------------------------------
 // Whitted wavefront
@@ -1114,7 +943,7 @@ __global__ void __launch_bounds__(128) k_wh_shade(const WhState p, const DScene 
                 {
                     float3 medium_scale = f3(1, 1, 1);
                     if (inside) // renderer.cpp:81-88
-                        medium_scale = f3(rt_expf(h.absorption.x * -t), rt_expf(h.absorption.y * -t), rt_expf(h.absorption.z * -t));
+                        medium_scale = beer_scale(h.absorption.x * -t, h.absorption.y * -t, h.absorption.z * -t);
                     const float3 wm = w * medium_scale;
                     const float reflectivity = h.reflectivity, refractivity = h.refractivity;
                     const float diffuseness = 1 - (reflectivity + refractivity);
@@ -1293,9 +1122,16 @@ struct rt_renderer {
     bool useStreams = true;
     int passes = 1;   // Renderer::passes (3. PathTracer/renderer.h:50), changeable between frames like the UI slider does
     int streamCtasPerSm = 8;
-    int streamKernel = 5; // 5 = current; 2 = the previous version, kept for A/B profiling (RT_B200_STREAM_KERNEL)
+    int streamKernel = 8; // 8 = current (rt_streams8.cuh); 5 = the round-1 kernel, kept for A/B profiling (RT_B200_STREAM_KERNEL)
     bool streamMeasuredLpt = true;
-    int streamMinB = 7, streamKeepShift = 2;
+    int streamMinB = 7, streamKeepShift = 1;
+    bool streamFastNode = true; // version 8: skip the full vote while interior-node lanes are the majority
+    int streamSmemSlots = 0;  // version 8: stack slots per thread in shared memory (0 = local-memory stack), from the scene's tree depths
+    // ordered accumulation: every sample of a launch goes to its own (frame, pass) image, k_sum_frames adds them in order
+    bool orderedFrames = true;
+    float4* dImages = nullptr;
+    size_t imagesCapacity = 0;            // in images (W x H float4 each)
+    size_t imageBudgetBytes = 4ull << 30; // frames per launch = budget / bytes per frame (RT_B200_IMAGE_BUDGET_MB)
     // look-ahead (rt_render_params.lookahead_frames): frames rendered ahead of the Tick sequence
     float4* dFrameBuf = nullptr;
     int aheadCapacity = 0, aheadBase = 0, aheadStride = 1, aheadReady = 0;
@@ -1372,6 +1208,30 @@ static Streams5Fn streams5_kernel_for(bool tlas, int minb)
 static Streams5Fn streams5_kernel(bool tlas, int minb, bool perPixel = false)
 {
     return perPixel ? streams5_kernel_for<true>(tlas, minb) : streams5_kernel_for<false>(tlas, minb);
+}
+
+// stream kernel version 8: dispatch on (TLAS, min CTAs per SM, seed mode, shared-memory stack slots)
+template <bool TLAS, bool PERPIXEL>
+static Streams5Fn streams8_kernel_for(int minb, int slots)
+{
+    if (PERPIXEL) return slots >= 32 ? k_pt_streams8<TLAS, 7, PERPIXEL, 32> : k_pt_streams8<TLAS, 7, PERPIXEL, 0>;
+    if (minb >= 8) return slots >= 32 ? k_pt_streams8<TLAS, 8, PERPIXEL, 32> : slots >= 24 ? k_pt_streams8<TLAS, 8, PERPIXEL, 24> : k_pt_streams8<TLAS, 8, PERPIXEL, 0>;
+    return slots >= 32 ? k_pt_streams8<TLAS, 7, PERPIXEL, 32> : slots >= 24 ? k_pt_streams8<TLAS, 7, PERPIXEL, 24> : k_pt_streams8<TLAS, 7, PERPIXEL, 0>;
+}
+static Streams5Fn streams8_kernel(bool tlas, int minb, bool perPixel, int slots)
+{
+    if (tlas) return perPixel ? streams8_kernel_for<true, true>(minb, slots) : streams8_kernel_for<true, false>(minb, slots);
+    return perPixel ? streams8_kernel_for<false, true>(minb, slots) : streams8_kernel_for<false, false>(minb, slots);
+}
+// shared-memory stack slots for a scene: its deepest possible stack + the CUR_END slot, rounded up to a compiled size; 0 = local memory
+static int streams8_slots(const rt_scene* sc, bool perPixel)
+{
+    const int need = sc->stack_entries + 1;
+    if (const char* e = getenv("RT_B200_STREAM_SMEM_SLOTS")) { const int v = atoi(e); if (v == 0 || (v >= need && (v == 24 || v == 32))) return (perPixel && v == 24) ? 32 : v; }
+    // default: the local-memory stack.  Same-box A/B (profiles/r2_stream_kernel_sweeps.txt): shared-memory columns are 1-4 % slower -
+    // the carve-out (12-16 KB per CTA) comes out of L1, whose hit rate falls from 84 % to 75 % on the bench scene.
+    (void)perPixel;
+    return 0;
 }
 
 template <class T>
@@ -1456,24 +1316,30 @@ rt_status rt_renderer_create(rt_scene* scene, const rt_render_params* params, rt
         if ((e = getenv("RT_B200_PT_SCHEDULE")) != nullptr) r->useStreams = strcmp(e, "wavefront") != 0;
         const bool altAccel = is_alt_kind(scene->d.kind);
         if ((e = getenv("RT_B200_STREAM_KERNEL")) != nullptr && atoi(e) > 0) r->streamKernel = atoi(e);
-        if (altAccel) r->streamKernel = 0; // k_pt_streams_alt: versions 2 / 5 are state machines over the BVH layout
+        if (altAccel) r->streamKernel = 0; // k_pt_streams_alt: versions 5 / 8 are state machines over the BVH layout
         if ((e = getenv("RT_B200_STREAM_LPT")) != nullptr) r->streamLpt = atoi(e) != 0;
         int occ = 0;
         cudaError_t oe;
         if ((e = getenv("RT_B200_STREAM_MEASURED_LPT")) != nullptr) r->streamMeasuredLpt = atoi(e) != 0;
-        if (r->streamKernel == 5)
+        if ((e = getenv("RT_B200_ORDERED_FRAMES")) != nullptr) r->orderedFrames = atoi(e) != 0;
+        if ((e = getenv("RT_B200_IMAGE_BUDGET_MB")) != nullptr && atoll(e) > 0) r->imageBudgetBytes = (size_t)atoll(e) << 20;
+        if (r->streamKernel != 5 && r->streamKernel != 8 && !altAccel) r->streamKernel = 8;
+        if (r->streamKernel == 5 || r->streamKernel == 8)
         {
             if ((e = getenv("RT_B200_STREAM_MINB")) != nullptr && atoi(e) > 0) r->streamMinB = atoi(e);
             if ((e = getenv("RT_B200_STREAM_KEEPSHIFT")) != nullptr && atoi(e) > 0) r->streamKeepShift = atoi(e);
             if ((e = getenv("RT_B200_STREAM_LANECAP")) != nullptr) r->streamLaneCap = atoi(e) != 0;
-            oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, streams5_kernel(scene->d.kind == RT_SCENE_TLAS, r->streamMinB), 128, 0);
+            if ((e = getenv("RT_B200_STREAM_FASTNODE")) != nullptr) r->streamFastNode = atoi(e) != 0;
+            if (r->streamKernel == 5 && !getenv("RT_B200_STREAM_KEEPSHIFT")) r->streamKeepShift = 2; // version 5's tuned value
+            const bool perPixel = params->seed_mode == RT_SEED_PER_PIXEL;
+            r->streamSmemSlots = streams8_slots(scene, perPixel);
+            oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, r->streamKernel == 8 ? streams8_kernel(scene->d.kind == RT_SCENE_TLAS, r->streamMinB, perPixel, r->streamSmemSlots)
+                                                                                           : streams5_kernel(scene->d.kind == RT_SCENE_TLAS, r->streamMinB, perPixel), 128, 0);
         }
         else if (scene->d.kind == RT_SCENE_FLAT_KDTREE) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams_alt<ACCEL_KD>, 128, 0);
         else if (scene->d.kind == RT_SCENE_FLAT_GRID) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams_alt<ACCEL_GRID>, 128, 0);
         else if (scene->d.kind == RT_SCENE_TLAS_KDTREE) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams_alt<ACCEL_TLAS_KD>, 128, 0);
-        else if (scene->d.kind == RT_SCENE_TLAS_GRID) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams_alt<ACCEL_TLAS_GRID>, 128, 0);
-        else if (scene->d.kind == RT_SCENE_TLAS) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams2<true>, 128, 0);
-        else oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams2<false>, 128, 0);
+        else oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams_alt<ACCEL_TLAS_GRID>, 128, 0);
         if (oe == cudaSuccess && occ > 0) r->streamCtasPerSm = occ;
         if ((e = getenv("RT_B200_STREAM_CTAS")) != nullptr && atoi(e) > 0) r->streamCtasPerSm = atoi(e);
     }
@@ -1655,10 +1521,10 @@ static rt_status render_pt_streams(rt_renderer* r, int first_spp, int count, int
     }
     // time the streams of this launch only while the tile order still comes from the pilot
     // (the BVH kernel only: on the KD-tree / grid kernel the measured order was no better than the pilot's, profiles/r1_kdtree_grid_*)
-    unsigned long long* clk = (order && r->tileOrderSource == 1 && r->streamMeasuredLpt && r->streamKernel == 5) ? r->dTileClock : nullptr;
+    unsigned long long* clk = (order && r->tileOrderSource == 1 && r->streamMeasuredLpt && r->streamKernel != 0) ? r->dTileClock : nullptr;
     if (clk) RT_CUDA(cudaMemsetAsync(clk, 0, (size_t)nTiles * 8, r->stream));
     r->prof_begin();
-    if (r->streamKernel == 5)
+    if (r->streamKernel != 0)
     {
         // small jobs: spread the streams over all resident warps instead of filling the first warps completely
         const long long warps = (long long)r->sms * r->streamCtasPerSm * 4;
@@ -1666,18 +1532,81 @@ static rt_status render_pt_streams(rt_renderer* r, int first_spp, int count, int
         if (perWarp < 1) perWarp = 1;
         if (perWarp > 32 || !r->streamLaneCap) perWarp = 32;
         const unsigned laneMask = perWarp >= 32 ? 0xffffffffu : ((1u << perWarp) - 1);
-        streams5_kernel(r->scene->d.kind == RT_SCENE_TLAS, r->streamMinB, perPixel)<<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6, clk, r->streamKeepShift, laneMask);
+        const Streams5Fn fn = r->streamKernel == 8 ? streams8_kernel(r->scene->d.kind == RT_SCENE_TLAS, r->streamMinB, perPixel, r->streamSmemSlots)
+                                                   : streams5_kernel(r->scene->d.kind == RT_SCENE_TLAS, r->streamMinB, perPixel);
+        const int ks = r->streamKeepShift | (r->streamKernel == 8 && r->streamFastNode ? 256 : 0);
+        fn<<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6, clk, ks, laneMask);
     }
     else if (r->scene->d.kind == RT_SCENE_FLAT_KDTREE) k_pt_streams_alt<ACCEL_KD><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
     else if (r->scene->d.kind == RT_SCENE_FLAT_GRID) k_pt_streams_alt<ACCEL_GRID><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
     else if (r->scene->d.kind == RT_SCENE_TLAS_KDTREE) k_pt_streams_alt<ACCEL_TLAS_KD><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
-    else if (r->scene->d.kind == RT_SCENE_TLAS_GRID) k_pt_streams_alt<ACCEL_TLAS_GRID><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
-    else if (r->scene->d.kind == RT_SCENE_TLAS) k_pt_streams2<true><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
-    else k_pt_streams2<false><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
+    else k_pt_streams_alt<ACCEL_TLAS_GRID><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
     r->prof_end(RT_STAGE_EXTEND);
     if (clk) r->tileClockRecorded = true, r->lastStreamFrames = count;
     r->paths += (uint64_t)nTiles * count * 256 * r->passes;
     RT_CUDA(cudaGetLastError());
+    return RT_OK;
+}
+
+// Grows the per-sample image buffer to `images` W x H float4 images; on an allocation failure the request is halved until one
+// frame's images fit (the caller then renders fewer frames per launch).  Returns the number of images available, 0 = none.
+static size_t ensure_images(rt_renderer* r, size_t images, size_t atLeast)
+{
+    if (images <= r->imagesCapacity) return images;
+    const size_t px = (size_t)r->params.width * r->params.height;
+    if (r->dImages)
+    {
+        cudaStreamSynchronize(r->stream);
+        for (size_t i = 0; i < r->allocations.size(); i++)
+            if (r->allocations[i] == r->dImages) { r->allocations.erase(r->allocations.begin() + i); break; }
+        cudaFree(r->dImages);
+        r->dImages = nullptr, r->imagesCapacity = 0;
+    }
+    while (true)
+    {
+        void* p = nullptr;
+        if (cudaMalloc(&p, images * px * 16) == cudaSuccess)
+        {
+            r->dImages = (float4*)p, r->imagesCapacity = images;
+            r->allocations.push_back(p);
+            return images;
+        }
+        cudaGetLastError();
+        if (images <= atLeast) return 0;
+        images = images / 2 < atLeast ? atLeast : images / 2;
+    }
+}
+
+// A job of `count` frames with the accumulator updated the way the reference's Tick sequence updates it (renderer.cpp:124:
+// accumulator[pixel] += sample, frame after frame, pass after pass): the frames of a launch write their samples to separate
+// images, k_sum_frames adds the images in order.  The result does not depend on how the launch was scheduled: it is bit-identical
+// to `count` single-frame calls and to the reference (tests/test_gpu_parity.py).  Launches hold as many frames as fit the image
+// budget (1080p: 33 MB per image, 64 frames = 2.1 GB; the sum pass reads them once: < 1 ms of HBM time).
+static rt_status render_pt_streams_ordered(rt_renderer* r, int first_spp, int count, int stride)
+{
+    const rt_render_params& P = r->params;
+    const bool kernelWritesImages = r->streamKernel == 8 || r->streamKernel == 0 || r->passes == 1; // version 5 indexes images by frame only
+    if (!r->orderedFrames || !kernelWritesImages) return render_pt_streams(r, first_spp, count, stride);
+    const size_t px = (size_t)P.width * P.height;
+    const size_t perFrame = (size_t)r->passes;
+    size_t framesPerLaunch = r->imageBudgetBytes / (px * 16 * perFrame);
+    if (framesPerLaunch < 1) framesPerLaunch = 1;
+    if (framesPerLaunch > (size_t)count) framesPerLaunch = (size_t)count;
+    const size_t got = ensure_images(r, framesPerLaunch * perFrame, perFrame);
+    if (got == 0) { set_error("rt_renderer_render: no device memory for one frame's sample images"); return RT_ERR_CUDA; }
+    framesPerLaunch = got / perFrame;
+    const int nTiles = num_tiles(P);
+    for (int done = 0; done < count; done += (int)framesPerLaunch)
+    {
+        const int frames = count - done < (int)framesPerLaunch ? count - done : (int)framesPerLaunch;
+        rt_status st = render_pt_streams(r, first_spp + done * stride, frames, stride, r->dImages);
+        if (st != RT_OK) return st;
+        r->prof_begin();
+        k_sum_frames<<<nTiles < r->sms * 8 ? nTiles : r->sms * 8, 256, 0, r->stream>>>(r->accum, r->dImages, frames * (int)perFrame, P.width, P.height, P.width / 16,
+            P.tile_begin, P.tile_step > 0 ? P.tile_step : 1, nTiles);
+        r->prof_end(RT_STAGE_SHADE);
+        RT_CUDA(cudaGetLastError());
+    }
     return RT_OK;
 }
 
@@ -1687,13 +1616,13 @@ static rt_status render_pt(rt_renderer* r, int first_spp, int count, int stride)
     const int nTiles = num_tiles(P);
     if (nTiles == 0 || count <= 0) return RT_OK;
     const long long streamsPerFrame = (long long)nTiles * (P.seed_mode == RT_SEED_PER_PIXEL ? 256 : 1);
-    if (r->useStreams && (P.seed_mode == RT_SEED_REFERENCE_TILE || r->streamKernel == 5) && P.depth_limit <= STREAM_MAX_DEPTH
+    if (r->useStreams && (P.seed_mode == RT_SEED_REFERENCE_TILE || r->streamKernel != 0) && P.depth_limit <= STREAM_MAX_DEPTH
         && streamsPerFrame * count < (1ll << 30))
     {
         const int L = P.lookahead_frames;
         // (with passes > 1 a frame image would hold the SUM of a pixel's samples, which the accumulator then receives in
         // one add instead of `passes` adds: not the Tick sequence bit for bit, so look-ahead serves passes == 1 only)
-        if (count == 1 && L > 1 && r->streamKernel == 5 && r->passes == 1 && streamsPerFrame * L < (1ll << 30))
+        if (count == 1 && L > 1 && r->streamKernel != 0 && r->passes == 1 && streamsPerFrame * L < (1ll << 30))
         {
             // one Tick per call: serve the frame from the images rendered ahead, rendering L more when it is not there
             const size_t px = (size_t)P.width * P.height;
@@ -1719,7 +1648,7 @@ static rt_status render_pt(rt_renderer* r, int first_spp, int count, int stride)
             RT_CUDA(cudaGetLastError());
             return RT_OK;
         }
-        return render_pt_streams(r, first_spp, count, stride);
+        return render_pt_streams_ordered(r, first_spp, count, stride);
     }
     // wavefront: slots per frame = tiles (reference RNG: a slot walks its tile) or pixels (one stream per pixel)
     const bool wfPerPixel = P.seed_mode == RT_SEED_PER_PIXEL;

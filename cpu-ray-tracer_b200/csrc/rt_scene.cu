@@ -173,6 +173,7 @@ static int grid_for(size_t n, int block, int device)
 struct Builder {
     std::vector<float4> nodes, tris, inst, shade, inst_shade;
     std::string error;
+    int lastDepth = 0; // levels of the tree the last add_bvh / add_tlas call laid out (a single leaf = 1)
 
     static float4 f4(float x, float y, float z, float w) { return make_float4(x, y, z, w); }
     static float asf(int i) { float f; memcpy(&f, &i, 4); return f; }
@@ -183,18 +184,26 @@ struct Builder {
         if (b.tri_count == 0 || b.node_count == 0) { error = "empty BLAS"; return 0; }
         const rt_bvh_node* N = b.nodes;
         auto leaf_ref = [&](const rt_bvh_node& n) { return ~(triSlotBase + (int)n.left_first); };
-        if (N[0].tri_count > 0) return leaf_ref(N[0]);
-        struct Item { uint32_t node; int fat; };
+        lastDepth = 1;
+        if (N[0].tri_count > 0)
+        {
+            if ((uint64_t)N[0].left_first + N[0].tri_count > b.tri_count) { error = "leaf range out of bounds"; return 0; }
+            return leaf_ref(N[0]);
+        }
+        struct Item { uint32_t node; int fat; int depth; };
         std::vector<Item> todo;
         const int rootFat = (int)(nodes.size() / 4);
         nodes.resize(nodes.size() + 4);
-        todo.push_back({ 0u, rootFat });
+        todo.push_back({ 0u, rootFat, 1 });
+        size_t visited = 0;
         while (!todo.empty())
         {
+            if (++visited > (size_t)b.node_count) { error = "BVH is not a tree"; return 0; }
             const Item it = todo.back();
             todo.pop_back();
+            if (it.depth + 1 > lastDepth) lastDepth = it.depth + 1; // its children are one level down
             const rt_bvh_node& p = N[it.node];
-            if (p.left_first + 1 >= b.node_count) { error = "BVH child index out of range"; return 0; }
+            if ((uint64_t)p.left_first + 1 >= b.node_count) { error = "BVH child index out of range"; return 0; }
             const rt_bvh_node& L = N[p.left_first];
             const rt_bvh_node& R = N[p.left_first + 1];
             int refs[2];
@@ -211,14 +220,15 @@ struct Builder {
                 {
                     refs[k] = (int)(nodes.size() / 4);
                     nodes.resize(nodes.size() + 4);
-                    todo.push_back({ p.left_first + (uint32_t)k, refs[k] });
+                    todo.push_back({ p.left_first + (uint32_t)k, refs[k], it.depth + 1 });
                 }
             }
             // DFS pre-order wants the left child processed first: it was pushed last, so it pops first
             float4* f = &nodes[4 * (size_t)it.fat];
-            f[0] = f4(L.aabb_min[0], L.aabb_min[1], L.aabb_min[2], L.aabb_max[0]);
-            f[1] = f4(L.aabb_max[1], L.aabb_max[2], R.aabb_min[0], R.aabb_min[1]);
-            f[2] = f4(R.aabb_min[2], R.aabb_max[0], R.aabb_max[1], R.aabb_max[2]);
+            // component order of rt_device.cuh (x / y planes paired per box, z planes of both boxes together)
+            f[0] = f4(L.aabb_min[0], L.aabb_min[1], L.aabb_max[0], L.aabb_max[1]);
+            f[1] = f4(R.aabb_min[0], R.aabb_min[1], R.aabb_max[0], R.aabb_max[1]);
+            f[2] = f4(L.aabb_min[2], L.aabb_max[2], R.aabb_min[2], R.aabb_max[2]);
             f[3] = f4(asf(refs[0]), asf(refs[1]), 0, 0);
         }
         return rootFat;
@@ -261,18 +271,24 @@ struct Builder {
     {
         const rt_tlas_node* N = d.tlas_nodes;
         auto leaf_ref = [&](const rt_tlas_node& n) { return ~(INSTANCE_BIT | (int)n.blas); };
-        if (N[0].left_right == 0) return leaf_ref(N[0]);
-        struct Item { uint32_t node; int fat; };
+        lastDepth = 1;
+        if (N[0].left_right == 0)
+        {
+            if (N[0].blas >= d.blas_count) { error = "TLAS leaf BLAS index out of range"; return 0; }
+            return leaf_ref(N[0]);
+        }
+        struct Item { uint32_t node; int fat; int depth; };
         std::vector<Item> todo;
         const int rootFat = (int)(nodes.size() / 4);
         nodes.resize(nodes.size() + 4);
-        todo.push_back({ 0u, rootFat });
+        todo.push_back({ 0u, rootFat, 1 });
         size_t guard = 0;
         while (!todo.empty())
         {
             if (++guard > 4ull * d.tlas_node_count + 16) { error = "TLAS is not a tree"; return 0; }
             const Item it = todo.back();
             todo.pop_back();
+            if (it.depth + 1 > lastDepth) lastDepth = it.depth + 1;
             const rt_tlas_node& p = N[it.node];
             const uint32_t li = p.left_right & 0xffff, ri = p.left_right >> 16;
             if (li >= d.tlas_node_count || ri >= d.tlas_node_count) { error = "TLAS child index out of range"; return 0; }
@@ -290,15 +306,16 @@ struct Builder {
                 {
                     refs[k] = (int)(nodes.size() / 4);
                     nodes.resize(nodes.size() + 4);
-                    todo.push_back({ idx[k], refs[k] });
+                    todo.push_back({ idx[k], refs[k], it.depth + 1 });
                 }
             }
             const rt_tlas_node& L = *ch[0];
             const rt_tlas_node& R = *ch[1];
             float4* f = &nodes[4 * (size_t)it.fat];
-            f[0] = f4(L.aabb_min[0], L.aabb_min[1], L.aabb_min[2], L.aabb_max[0]);
-            f[1] = f4(L.aabb_max[1], L.aabb_max[2], R.aabb_min[0], R.aabb_min[1]);
-            f[2] = f4(R.aabb_min[2], R.aabb_max[0], R.aabb_max[1], R.aabb_max[2]);
+            // component order of rt_device.cuh (x / y planes paired per box, z planes of both boxes together)
+            f[0] = f4(L.aabb_min[0], L.aabb_min[1], L.aabb_max[0], L.aabb_max[1]);
+            f[1] = f4(R.aabb_min[0], R.aabb_min[1], R.aabb_max[0], R.aabb_max[1]);
+            f[2] = f4(L.aabb_min[2], L.aabb_max[2], R.aabb_min[2], R.aabb_max[2]);
             f[3] = f4(asf(refs[0]), asf(refs[1]), 0, 0);
         }
         return rootFat;
@@ -454,6 +471,7 @@ rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags,
     if (rt_device_count() <= device || device < 0) { set_error("rt_scene_create: no such CUDA device (there is no CPU fallback)"); return RT_ERR_NO_DEVICE; }
 
     Builder B;
+    int maxBlasDepth = 0, tlasDepth = 0;
     std::vector<float4> kdNodes, gridParams;
     std::vector<int2> gridCells;
     std::vector<int> rootRefs(desc->blas_count);
@@ -514,6 +532,7 @@ rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags,
         {
             triBase[i] = (int)(B.tris.size() / 3);
             rootRefs[i] = B.add_bvh(b, triBase[i]);
+            if (B.lastDepth > maxBlasDepth) maxBlasDepth = B.lastDepth;
             if (B.error.empty()) B.add_tris(b);
             if (!B.error.empty()) { set_error("rt_scene_create: " + B.error); return RT_ERR_INVALID; }
             if (firstOfGeometry.size() < 64) firstOfGeometry.push_back(i);
@@ -534,15 +553,49 @@ rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags,
     if (anyTlas)
     {
         rootRef = B.add_tlas(*desc);
+        tlasDepth = B.lastDepth;
         if (!B.error.empty()) { set_error("rt_scene_create: " + B.error); return RT_ERR_INVALID; }
+        if (desc->blas_count > 0x3fffff00u) { set_error("rt_scene_create: more than 2^30 instances"); return RT_ERR_UNSUPPORTED; }
         // GetHitInfo indexes blas[objIdx - 2] (tlas_file_scene.cpp:237): objIdx must be i + 2
         for (uint32_t i = 0; i < desc->blas_count; i++)
             if (desc->blas[i].obj_idx != (int)i + 2) { set_error("rt_scene_create: TLAS scenes need blas[i].obj_idx == i + 2"); return RT_ERR_INVALID; }
     }
 
+    // The traversal kernels keep the pending far children of ONE ray on one stack: at most one entry per level above the node
+    // being visited, plus (TLAS) the instance-exit marker.  The reference uses BVHNode* stack[64] per level (bvh.cpp:227,
+    // tlas_bvh.cpp:86) and overflows silently on a deeper tree; here a scene that could overflow STACK_SIZE entries is refused.
+    const int stackEntries = anyTlas ? (tlasDepth - 1) + (desc->kind == RT_SCENE_TLAS ? 1 + (maxBlasDepth > 0 ? maxBlasDepth - 1 : 0) : 0)
+                                     : (maxBlasDepth > 0 ? maxBlasDepth - 1 : 0);
+    if (stackEntries > STACK_SIZE)
+    {
+        set_error("rt_scene_create: BVH / TLAS too deep for the traversal stack (" + std::to_string(stackEntries) + " pending entries possible, " + std::to_string(STACK_SIZE) + " supported)");
+        return RT_ERR_UNSUPPORTED;
+    }
+    // shading indices (GetHitInfo, file_scene.cpp:189-214 / tlas_file_scene.cpp:220-260): objects -> materials -> textures
+    {
+        const int nObj = (int)desc->obj_count, nMat = (int)desc->material_count, nTex = (int)desc->texture_count;
+        if ((nObj && !desc->obj_material) || (nMat && !desc->materials) || (nTex && !desc->textures)) { set_error("rt_scene_create: null material / texture tables"); return RT_ERR_INVALID; }
+        for (int i = 0; i < nObj; i++)
+            if (desc->obj_material[i] < 0 || desc->obj_material[i] >= nMat) { set_error("rt_scene_create: obj_material entry out of range"); return RT_ERR_INVALID; }
+        for (int i = 0; i < nMat; i++)
+            if (desc->materials[i].texture >= nTex) { set_error("rt_scene_create: material texture id out of range"); return RT_ERR_INVALID; }
+        if (desc->skydome_texture >= nTex || desc->floor_texture >= nTex) { set_error("rt_scene_create: skydome / floor texture id out of range"); return RT_ERR_INVALID; }
+        if (anyTlas)
+        {
+            if ((int)desc->blas_count > nObj) { set_error("rt_scene_create: fewer objects than BLAS instances"); return RT_ERR_INVALID; }
+        }
+        else
+        {
+            const rt_blas_desc& b = desc->blas[0]; // hits take Tri::objIdx (bvh.cpp:219): every triangle needs a valid object
+            for (uint32_t j = 0; j < b.tri_count; j++)
+                if (b.tris[j].obj_idx < 2 || b.tris[j].obj_idx - 2 >= nObj) { set_error("rt_scene_create: triangle obj_idx out of range"); return RT_ERR_INVALID; }
+        }
+    }
+
     RT_CUDA(cudaSetDevice(device));
     rt_scene* s = new rt_scene();
     s->device = device, s->flags = flags;
+    s->stack_entries = stackEntries;
     rt_status st = RT_OK;
     auto fail = [&](rt_status e) { rt_scene_destroy(s); return e; };
     if ((st = upload(&s->nodes, B.nodes.data(), B.nodes.size() * 16)) != RT_OK) return fail(st);
@@ -559,8 +612,16 @@ rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags,
     if (desc->kind == RT_SCENE_FLAT_KDTREE || desc->kind == RT_SCENE_TLAS_KDTREE) s->node_count += kdNodes.size() / 2;
     if (desc->kind == RT_SCENE_FLAT_GRID || desc->kind == RT_SCENE_TLAS_GRID) s->node_count += gridCells.size();
 
-    static_assert(sizeof(DMaterial) == sizeof(rt_material), "material layout");
-    if ((st = upload(&s->materials, desc->materials, desc->material_count * sizeof(rt_material))) != RT_OK) return fail(st);
+    {
+        static_assert(sizeof(DMaterial) == 48 && sizeof(rt_material) == 40, "material layout");
+        std::vector<DMaterial> mats(desc->material_count);
+        for (uint32_t i = 0; i < desc->material_count; i++)
+        {
+            memset(&mats[i], 0, sizeof(DMaterial));
+            memcpy(&mats[i], &desc->materials[i], sizeof(rt_material)); // same field order, padded to 48 B
+        }
+        if ((st = upload(&s->materials, mats.data(), mats.size() * sizeof(DMaterial))) != RT_OK) return fail(st);
+    }
     size_t texels = 0;
     for (uint32_t i = 0; i < desc->texture_count; i++) texels += (size_t)desc->textures[i].width * desc->textures[i].height;
     if ((st = upload(&s->tex_pixels, nullptr, texels * 4)) != RT_OK) return fail(st);
