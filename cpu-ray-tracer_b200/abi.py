@@ -11,7 +11,8 @@ RT_SCENE_FLAG_COUNTERS = 1
 RT_INTEGRATOR_WHITTED, RT_INTEGRATOR_PATH = 0, 1
 RT_SEED_REFERENCE_TILE, RT_SEED_PER_PIXEL = 0, 1
 RT_SCHEDULE_AUTO, RT_SCHEDULE_WAVEFRONT, RT_SCHEDULE_STREAMS = 0, 1, 2
-RT_MATH_EXPF, RT_MATH_ACOSF, RT_MATH_ATAN2F, RT_MATH_SKY_TEXEL, RT_MATH_EXPF_FF = 0, 1, 2, 3, 4
+RT_MATH_EXPF, RT_MATH_ACOSF, RT_MATH_ATAN2F, RT_MATH_SKY_TEXEL = 0, 1, 2, 3
+RT_IPC_HANDLE_BYTES = 64
 
 f3 = C.c_float * 3
 f16 = C.c_float * 16
@@ -77,10 +78,10 @@ class rt_counters(C.Structure):
 
 
 class rt_stage_times(C.Structure):
-    _fields_ = [("ms", C.c_double * 4), ("launches", C.c_uint64 * 4)]
+    _fields_ = [("ms", C.c_double * 5), ("launches", C.c_uint64 * 5)]
 
 
-STAGES = ("generate", "extend", "shade", "connect")
+STAGES = ("generate", "extend", "shade", "connect", "accumulate")
 
 # numpy record layouts of the POD arrays (same bytes as the reference's structs)
 NODE_DTYPE = np.dtype([("aabb_min", "<f4", 3), ("aabb_max", "<f4", 3), ("left_first", "<u4"), ("tri_count", "<u4")])

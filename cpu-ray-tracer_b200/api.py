@@ -33,6 +33,11 @@ EXPORTS = [
     "rt_renderer_get_counters", "rt_renderer_reset_counters",
     "rt_renderer_set_profiling", "rt_renderer_get_stage_times", "rt_renderer_get_launch_spans",
     "rt_renderer_get_queue_history", "rt_measure_gather_bandwidth", "rt_build_bvh", "rt_eval_shading_math",
+    "rt_measure_l2_stream_bandwidth", "rt_renderer_export_accumulator", "rt_renderer_import_accumulator",
+    "rt_multi_renderer_create", "rt_multi_renderer_destroy", "rt_multi_renderer_device_count", "rt_multi_renderer_set_camera",
+    "rt_multi_renderer_set_passes", "rt_multi_renderer_clear", "rt_multi_renderer_render", "rt_multi_renderer_sync",
+    "rt_multi_renderer_read_accumulator", "rt_multi_renderer_read_pixels", "rt_multi_renderer_get_counters",
+    "rt_multi_renderer_reset_counters",
 ]
 
 
@@ -92,6 +97,22 @@ def lib():
     L.rt_measure_gather_bandwidth.argtypes = [i32, sz, i32, C.POINTER(C.c_double)]
     L.rt_build_bvh.argtypes = [i32, vp, C.c_uint32, vp, vp, C.POINTER(C.c_uint32), C.POINTER(C.c_double)]
     L.rt_eval_shading_math.argtypes = [i32, i32, vp, vp, vp, sz]
+    L.rt_measure_l2_stream_bandwidth.argtypes = [i32, sz, C.POINTER(C.c_double)]
+    L.rt_renderer_export_accumulator.argtypes = [vp, vp]
+    L.rt_renderer_import_accumulator.argtypes = [vp, vp]
+    L.rt_multi_renderer_create.argtypes = [C.POINTER(abi.rt_scene_desc), C.c_uint32, C.POINTER(i32), i32, C.POINTER(abi.rt_render_params), C.POINTER(vp)]
+    L.rt_multi_renderer_destroy.argtypes = [vp]
+    L.rt_multi_renderer_destroy.restype = None
+    L.rt_multi_renderer_device_count.argtypes = [vp]
+    L.rt_multi_renderer_set_camera.argtypes = [vp, C.POINTER(abi.rt_camera)]
+    L.rt_multi_renderer_set_passes.argtypes = [vp, i32]
+    L.rt_multi_renderer_clear.argtypes = [vp]
+    L.rt_multi_renderer_render.argtypes = [vp, i32, i32, i32]
+    L.rt_multi_renderer_sync.argtypes = [vp]
+    L.rt_multi_renderer_read_accumulator.argtypes = [vp, vp]
+    L.rt_multi_renderer_read_pixels.argtypes = [vp, C.c_float, vp]
+    L.rt_multi_renderer_get_counters.argtypes = [vp, C.POINTER(abi.rt_counters)]
+    L.rt_multi_renderer_reset_counters.argtypes = [vp]
     _lib = L
     return L
 
@@ -120,6 +141,13 @@ def measure_gather_bandwidth(working_set_bytes, bypass_l1=True, device=0):
     """GB/s of random 64-byte gathers over a working set (L2 roofline denominator for L2-resident scenes)"""
     out = C.c_double()
     _check(lib().rt_measure_gather_bandwidth(device, working_set_bytes, 1 if bypass_l1 else 0, C.byref(out)))
+    return out.value
+
+
+def measure_l2_stream_bandwidth(working_set_bytes=48 << 20, device=0):
+    """GB/s of coalesced streaming reads of an L2-resident buffer, L1 bypassed (the L2 peak of the roofline)"""
+    out = C.c_double()
+    _check(lib().rt_measure_l2_stream_bandwidth(device, working_set_bytes, C.byref(out)))
     return out.value
 
 
@@ -325,6 +353,24 @@ class GpuRenderer:
         self._need()
         return lib().rt_renderer_device_accumulator(self.handle)
 
+    def read_accumulator_into(self, host_ptr):
+        """rt_renderer_read_accumulator into a caller-owned host buffer of width * height float4 (e.g. pinned memory)"""
+        self._need()
+        _check(lib().rt_renderer_read_accumulator(self.handle, host_ptr))
+
+    def export_accumulator(self):
+        """CUDA IPC handle (bytes) of this renderer's accumulator, for the tile shards of other processes"""
+        self._need()
+        buf = C.create_string_buffer(abi.RT_IPC_HANDLE_BYTES)
+        _check(lib().rt_renderer_export_accumulator(self.handle, buf))
+        return buf.raw
+
+    def import_accumulator(self, handle_bytes):
+        """accumulate into another process' accumulator (peer-mapped over NVLink) from now on"""
+        self._need()
+        buf = C.create_string_buffer(bytes(handle_bytes), abi.RT_IPC_HANDLE_BYTES)
+        _check(lib().rt_renderer_import_accumulator(self.handle, buf))
+
     def screen_pixels(self, scale=None):
         """screen->pixels as the reference displays them: accumulator * 1/(spp+passes) through RGBF32_to_RGB8
         (renderer.cpp:119,127-129); note that `spp` here is the value BEFORE the last Tick's increment."""
@@ -371,3 +417,72 @@ class GpuRenderer:
         t = abi.rt_stage_times()
         _check(lib().rt_renderer_get_stage_times(self.handle, C.byref(t)))
         return {name: (float(t.ms[i]), int(t.launches[i])) for i, name in enumerate(abi.STAGES)}
+
+
+class MultiGpuRenderer:
+    """Renderer::Tick (3. PathTracer/renderer.cpp:144-168) on several GPUs of this process: rt_multi_renderer.  The scene is
+    replicated, device k renders the interleaved tiles k, k + n, ... and every device accumulates into ONE image on devices[0]
+    through peer-mapped memory; the accumulator is bit-identical to a one-GPU GpuRenderer's."""
+
+    def __init__(self, flat, integrator, width, height, devices, depthLimit=5, seed_mode=abi.RT_SEED_REFERENCE_TILE,
+                 schedule=abi.RT_SCHEDULE_AUTO, lookahead_frames=0, counters=False):
+        if isinstance(flat, (str, os.PathLike)):
+            flat = FlatScene.load(flat)
+        self.flat, self.integrator, self.width, self.height = flat, integrator, width, height
+        self.devices = [int(d) for d in devices]
+        self.camera = Camera(width, height)
+        self.spp, self.passes = 1, 1
+        self.params = abi.rt_render_params()
+        lib().rt_render_params_default(C.byref(self.params), integrator, width, height)
+        self.params.depth_limit, self.params.seed_mode = depthLimit, seed_mode
+        self.params.schedule, self.params.lookahead_frames = schedule, lookahead_frames
+        self.handle = C.c_void_p()
+        desc = flat.desc()
+        dev = (C.c_int * len(self.devices))(*self.devices)
+        _check(lib().rt_multi_renderer_create(C.byref(desc), abi.RT_SCENE_FLAG_COUNTERS if counters else 0, dev, len(self.devices),
+                                              C.byref(self.params), C.byref(self.handle)))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib().rt_multi_renderer_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def ClearAccumulator(self):
+        _check(lib().rt_multi_renderer_clear(self.handle))
+
+    def Tick(self, deltaTime=0.0):
+        self.render(1)
+
+    def render(self, frames, first_spp=None, stride=None):
+        _check(lib().rt_multi_renderer_set_camera(self.handle, C.byref(self.camera.c)))
+        _check(lib().rt_multi_renderer_set_passes(self.handle, int(self.passes)))
+        first = self.spp if first_spp is None else first_spp
+        _check(lib().rt_multi_renderer_render(self.handle, first, frames, self.passes if stride is None else stride))
+        if first_spp is None:
+            self.spp += frames * self.passes
+
+    def sync(self):
+        _check(lib().rt_multi_renderer_sync(self.handle))
+
+    @property
+    def accumulator(self):
+        out = np.empty((self.height, self.width, 4), np.float32)
+        _check(lib().rt_multi_renderer_read_accumulator(self.handle, out.ctypes.data))
+        return out
+
+    def read_accumulator_into(self, host_ptr):
+        _check(lib().rt_multi_renderer_read_accumulator(self.handle, host_ptr))
+
+    def counters(self):
+        c = abi.rt_counters()
+        _check(lib().rt_multi_renderer_get_counters(self.handle, C.byref(c)))
+        return {k: int(getattr(c, k)) for k, _ in abi.rt_counters._fields_}
+
+    def reset_counters(self):
+        _check(lib().rt_multi_renderer_reset_counters(self.handle))

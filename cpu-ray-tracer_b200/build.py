@@ -11,12 +11,12 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librt_b200.so")
-SOURCES = ["rt_scene.cu", "rt_render.cu", "rt_build.cu"]
-HEADERS = ["rt_device.cuh", "rt_glibc_math.cuh", "rt_internal.h", os.path.join("..", "..", "include", "rt_b200.h")]
+SOURCES = ["rt_scene.cu", "rt_render.cu", "rt_build.cu", "rt_multi.cu"]
+HEADERS = ["rt_device.cuh", "rt_streams8.cuh", "rt_glibc_math.cuh", "rt_internal.h", os.path.join("..", "..", "include", "rt_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
-              "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-shared", "-cudart", "shared"]
+              "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-shared", "-cudart", "shared", "--threads", "0"]
 
 
 def nvcc():
@@ -61,15 +61,12 @@ def build(force=False, verbose=False, extra=()):
     return LIB
 
 
-# Build variants of the same library (same ABI, selected with RT_B200_LIB).  bench.py times each of them beside the default build in a
-# child process ("libm.variants" of the bench line); nothing else loads them and the tests run against the default build only.
+# Build variant of the same library (same ABI, selected with RT_B200_LIB).  bench.py times it beside the default build in a child
+# process ("libm.variants" of the bench line); nothing else loads it and the tests run against the default build only.
 #   cudamath   CUDA's expf / atan2f / acosf: radiance within the tolerance of tests/test_gpu_parity.py instead of bit-identical
-#   glibcexpf  glibc expf + CUDA's sky routines        } the two halves of the default build separately:
-#   glibcsky   CUDA's expf + glibc sky routines        } which one carries the cost (profiles/r1_glibc_math.txt)
-#   ffexpf     the default build with expf evaluated in float-float arithmetic (rt_glibc_expf_ff: same bits, double routine only
-#              near rounding boundaries) - experimental
-VARIANTS = {"cudamath": ["-DRT_B200_GLIBC_MATH=0"], "glibcexpf": ["-DRT_B200_GLIBC_SKY=0"], "glibcsky": ["-DRT_B200_GLIBC_EXPF=0"],
-            "ffexpf": ["-DRT_B200_EXPF_FF=1"]}
+# (Round 1 also built the two halves separately and a float-float expf; round 2 moved the exact routines out of line, which
+# removed their cost - profiles/r2_libm_ab.txt - and the experiments with them.)
+VARIANTS = {"cudamath": ["-DRT_B200_GLIBC_MATH=0"]}
 
 
 def variant_path(tag):

@@ -541,8 +541,17 @@ extern "C" rt_status rt_build_bvh(int device, const rt_tri* tris, uint32_t n, rt
     auto gridFor = [&](size_t items) { const size_t g = (items + block - 1) / block; return (int)(g < (size_t)grid ? (g ? g : 1) : grid); };
 
     RT_CUDA(cudaMemcpy(dTris, tris, (size_t)n * sizeof(rt_tri), cudaMemcpyHostToDevice));
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0), cudaEventCreate(&e1);
+    struct Events {
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        ~Events() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
+    } ev;
+    struct Bins { // grown per level, released on every exit path
+        float* b = nullptr;
+        int* c = nullptr;
+        ~Bins() { cudaFree(b), cudaFree(c); }
+    } bins;
+    cudaEventCreate(&ev.e0), cudaEventCreate(&ev.e1);
+    cudaEvent_t e0 = ev.e0, e1 = ev.e1;
     cudaEventRecord(e0);
     k_build_node_init<<<1, 32>>>(nodes, 0, 1, 0u, n);
     k_build_init<<<grid, block>>>(dTris, N, cen, tmin, tmax, idxA, posNode, nodes);
@@ -555,15 +564,17 @@ extern "C" rt_status rt_build_bvh(int device, const rt_tri* tris, uint32_t n, rt
         if ((size_t)count > binCapacity)
         {
             // (re)allocate the bins for this level; levels first grow, then shrink
-            if (binB) { cudaFree(binB), cudaFree(binC); }
+            cudaFree(bins.b), cudaFree(bins.c);
+            bins.b = nullptr, bins.c = nullptr;
             binCapacity = (size_t)count * 2;
-            if (cudaMalloc((void**)&binB, binCapacity * 3 * BINS * 6 * sizeof(float)) != cudaSuccess ||
-                cudaMalloc((void**)&binC, binCapacity * 3 * BINS * sizeof(int)) != cudaSuccess)
+            if (cudaMalloc((void**)&bins.b, binCapacity * 3 * BINS * 6 * sizeof(float)) != cudaSuccess ||
+                cudaMalloc((void**)&bins.c, binCapacity * 3 * BINS * sizeof(int)) != cudaSuccess)
             {
                 cudaGetLastError();
                 set_error("rt_build_bvh: out of device memory (bins)");
                 return RT_ERR_CUDA;
             }
+            binB = bins.b, binC = bins.c;
         }
         k_build_level_reset<<<gridFor((size_t)count * 3 * BINS), block>>>(nodes, first, count, binB, binC);
         k_build_centroid_bounds<<<grid, BUILD_BLOCK>>>(N, chunk, first, posNode, idx, cen, nodes);
@@ -602,8 +613,6 @@ extern "C" rt_status rt_build_bvh(int device, const rt_tri* tris, uint32_t n, rt
     cudaError_t err = cudaEventSynchronize(e1);
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0), cudaEventDestroy(e1);
-    if (binB) cudaFree(binB), cudaFree(binC);
     if (!cuda_ok(err, "rt_build_bvh kernels") || !cuda_ok(cudaGetLastError(), "rt_build_bvh kernels")) return RT_ERR_CUDA;
     RT_CUDA(cudaMemcpy(nodes_out, dOut, (size_t)total * sizeof(rt_bvh_node), cudaMemcpyDeviceToHost));
     RT_CUDA(cudaMemcpy(tri_indices_out, idx, (size_t)n * 4, cudaMemcpyDeviceToHost));

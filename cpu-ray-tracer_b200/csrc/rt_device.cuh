@@ -21,13 +21,7 @@
 #define RT_B200_GLIBC_SKY RT_B200_GLIBC_MATH
 #endif
 #include "rt_glibc_math.cuh"
-// RT_B200_EXPF_FF (default 0, experimental): the same bits through float-float arithmetic, double routine only near rounding boundaries
-#ifndef RT_B200_EXPF_FF
-#define RT_B200_EXPF_FF 0
-#endif
-#if RT_B200_GLIBC_EXPF && RT_B200_EXPF_FF
-#define rt_expf rt_glibc_expf_ff
-#elif RT_B200_GLIBC_EXPF
+#if RT_B200_GLIBC_EXPF
 #define rt_expf rt_glibc_expf
 #else
 #define rt_expf expf

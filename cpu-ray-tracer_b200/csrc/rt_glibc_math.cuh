@@ -89,80 +89,6 @@ RT_GM_FN float rt_glibc_expf(float x)
     return (float)y;
 }
 
-// The same bits as rt_glibc_expf WITHOUT double arithmetic for almost every argument (experimental build variant
-// RT_B200_EXPF_FF, see DESIGN.md section 9: the double-precision routine is the prime suspect for the cost of the exact build).
-// exp(x) is evaluated in float-float arithmetic (error-free products with fmaf, ~2^-40 relative), rounded to float, and the result
-// is ACCEPTED only when the float-float value is further from a rounding boundary than glibc's double evaluation and this one can
-// disagree (RT_GM_EXPF_FF_MARGIN of an ulp); everything else - subnormal results, overflow, NaN, the ~2 % of arguments near a
-// boundary - goes to rt_glibc_expf.  Not an analytical claim: tests/tools/glibc_math_check.c compares it with libm on all 2^32
-// arguments, which is the whole domain.
-RT_GM_TABLE uint32_t rt_gm_exp2f_ff_tab[32][2] = { // 2^(i/32) = hi + lo
-    {0x3f800000u, 0x00000000u}, {0x3f82cd87u, 0xb34ea7a9u}, {0x3f85aac3u, 0x334f9891u}, {0x3f88980fu, 0xb37eda4bu},
-    {0x3f8b95c2u, 0xb260aba1u}, {0x3f8ea43au, 0xb3697465u}, {0x3f91c3d3u, 0x33675624u}, {0x3f94f4f0u, 0xb32e0212u},
-    {0x3f9837f0u, 0x33231b71u}, {0x3f9b8d3au, 0xb30c5563u}, {0x3f9ef532u, 0x33412342u}, {0x3fa27043u, 0x30c3125au},
-    {0x3fa5fed7u, 0xb32c9d5eu}, {0x3fa9a15bu, 0xb3162b08u}, {0x3fad583fu, 0xb22deaf6u}, {0x3fb123f6u, 0xb37c5aa8u},
-    {0x3fb504f3u, 0x32cfe77au}, {0x3fb8fbafu, 0x330ec5f7u}, {0x3fbd08a4u, 0xb3414fe8u}, {0x3fc12c4du, 0xb2d6663eu},
-    {0x3fc5672au, 0x320aa837u}, {0x3fc9b9beu, 0xb37323a2u}, {0x3fce248cu, 0x3228fc24u}, {0x3fd2a81eu, 0xb35c1daau},
-    {0x3fd744fdu, 0xb2d4a58au}, {0x3fdbfbb8u, 0xb3504a1cu}, {0x3fe0ccdfu, 0xb21eab59u}, {0x3fe5b907u, 0xb2441be6u},
-    {0x3feac0c7u, 0xb24116deu}, {0x3fefe4bau, 0xb348464au}, {0x3ff5257du, 0x32292436u}, {0x3ffa83b3u, 0xb2923758u}};
-#ifndef RT_GM_EXPF_FF_MARGIN
-#define RT_GM_EXPF_FF_MARGIN 0.0078125f // 2^-7 of an ulp on either side of a rounding boundary is left to the double routine
-#endif
-
-RT_GM_FN float rt_glibc_expf_ff_impl(float x, int* accepted)
-{
-    *accepted = 0;
-    if (x > -87.0f && x < 88.0f) // else: subnormal results, overflow, NaN
-    {
-    // k = round(x * 32 / ln 2), r = x - k * ln2 / 32 as a float-float (rh, rl); ln2 / 32 = C1 (11 bits: k * C1 is exact) + C2 + C3
-    const float C1 = rt_gm_u2f(0x3cb16000u), C2 = rt_gm_u2f(0x3710bfbfu), C3 = rt_gm_u2f(0xaae30865u);
-    const float magic = 12582912.0f; // 1.5 * 2^23
-    const float t = rt_gm_fmaf(x, rt_gm_u2f(0x4238aa3bu), magic);
-    const int32_t k = (int32_t)rt_gm_f2u(t) - 0x4b400000;
-    const float kf = t - magic;
-    const float r0 = rt_gm_fmaf(-kf, C1, x);          // exact
-    const float p2 = kf * C2, p2e = rt_gm_fmaf(kf, C2, -p2); // kf * C2 = p2 + p2e
-    const float s = r0 - p2;
-    const float bb = s - r0;
-    const float se = (r0 - (s - bb)) + (-p2 - bb);    // r0 - p2 = s + se
-    const float lo = (se - p2e) - kf * C3;
-    const float rh = s + lo, rl = lo - (rh - s);
-    // e^r - 1 = r + q, q = r^2 (1/2 + r (1/6 + r (1/24 + r (1/120 + r / 720)))) in plain float (|q| < 6e-5)
-    float q = rt_gm_fmaf(rh, 1.0f / 720.0f, 1.0f / 120.0f);
-    q = rt_gm_fmaf(rh, q, 1.0f / 24.0f);
-    q = rt_gm_fmaf(rh, q, 1.0f / 6.0f);
-    q = rt_gm_fmaf(rh, q, 0.5f);
-    q = rt_gm_fmaf(rh * rh, q, rh * rl);
-    const float u = rl + q;
-    const float ph = rh + u;
-    const float pb = ph - rh;
-    const float pl = (rh - (ph - pb)) + (u - pb);     // e^r - 1 = ph + pl
-    // 2^(i/32) (Th + Tl) * (1 + ph + pl) = Th + [a + ae + Tl + Th pl + Tl ph]
-    const float Th = rt_gm_u2f(rt_gm_exp2f_ff_tab[k & 31][0]), Tl = rt_gm_u2f(rt_gm_exp2f_ff_tab[k & 31][1]);
-    const float a = Th * ph, ae = rt_gm_fmaf(Th, ph, -a);
-    const float tail = ((Tl + ae) + Th * pl) + Tl * ph;
-    const float s1 = Th + a;
-    const float e1 = a - (s1 - Th);                   // Th + a = s1 + e1 (|Th| > |a|)
-    const float w = e1 + tail;
-    const float c = s1 + w;
-    const float res = (s1 - c) + w;                   // value - c
-    const float ulp = rt_gm_u2f((rt_gm_f2u(c) & 0x7f800000u) - (23u << 23));
-    const float ares = res < 0.0f ? -res : res;
-    if (ares < (0.5f - RT_GM_EXPF_FF_MARGIN) * ulp)
-    {
-        *accepted = 1;
-        return rt_gm_u2f(rt_gm_f2u(c) + ((uint32_t)(k >> 5) << 23));
-    }
-    }
-    return rt_glibc_expf(x); // the one call of the double routine
-}
-
-RT_GM_FN float rt_glibc_expf_ff(float x)
-{
-    int accepted;
-    return rt_glibc_expf_ff_impl(x, &accepted);
-}
-
 // acosf / atanf / atan2f below keep glibc's arithmetic (each result is produced by the same sequence of float operations
 // as in e_acosf.c / s_atanf.c / e_atan2f.c) but the range cases of the C sources are folded into selects around ONE
 // polynomial and ONE division, so that the lanes of a warp that look up the sky in different octants do not serialise

@@ -50,6 +50,9 @@ struct rt_scene {
     rtb::DTexture* textures = nullptr;
     uint32_t* tex_pixels = nullptr;
     size_t node_count = 0, tri_count = 0, inst_count = 0;
+    // renderers created on this scene: rt_scene_destroy while some exist only marks the scene, the last rt_renderer_destroy frees it
+    std::atomic<int> renderers{0};
+    std::atomic<bool> destroy_requested{false};
     int stack_entries = 0; // most far children one ray can have pending (bound from the tree depths, rt_scene_create)
     size_t bytes_geometry = 0, bytes_textures = 0;
     // scratch for the host-buffer entry points (rt_find_nearest / rt_is_occluded)

@@ -314,8 +314,13 @@ __global__ void __launch_bounds__(128) k_pt_shade(const PTState p, const DScene 
                 {
                     const int tx = tile % p.tilesX, ty = tile / p.tilesX;
                     const int x = tx * 16 + ((pix - 1) & 15), y = ty * 16 + ((pix - 1) >> 4);
-                    float* a = (float*)(p.accum + (x + (size_t)y * p.W)); // renderer.cpp:124: accumulator += float4(sample, 0)
-                    atomicAdd(a + 0, L.x), atomicAdd(a + 1, L.y), atomicAdd(a + 2, L.z);
+                    if (p.frameBuf) // the sample's own (frame, pass) image: added to the accumulator in order by k_sum_frames
+                        p.frameBuf[(size_t)(frame * p.passes + (smp - 1) % p.passes) * ((size_t)p.W * p.H) + (x + (size_t)y * p.W)] = make_float4(L.x, L.y, L.z, 0);
+                    else
+                    {
+                        float* a = (float*)(p.accum + (x + (size_t)y * p.W)); // renderer.cpp:124: accumulator += float4(sample, 0)
+                        atomicAdd(a + 0, L.x), atomicAdd(a + 1, L.y), atomicAdd(a + 2, L.z);
+                    }
                 }
                 // the slot's last sample: the tile's 256 x passes-th, or (one slot per pixel) the pixel's passes-th
                 if (smp < (p.seedMode == RT_SEED_PER_PIXEL ? (px0 + 1) * p.passes : 256 * p.passes))
@@ -1073,19 +1078,6 @@ __global__ void __launch_bounds__(128) k_wh_connect_persistent(const WhState p, 
     if (blockIdx.x == 0 && threadIdx.x == 0) p.counters[1] += (unsigned long long)n;
 }
 
-// look-ahead mode: accumulator += the image of one frame (renderer.cpp:124, one float add per channel per frame,
-// in spp order like the reference's Tick sequence)
-__global__ void k_add_frame(float4* __restrict__ accum, const float4* __restrict__ frame, int n)
-{
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    {
-        float4 a = accum[i];
-        const float4 f = frame[i];
-        a.x += f.x, a.y += f.y, a.z += f.z;
-        accum[i] = a;
-    }
-}
-
 // screen->pixels: RGBF32_to_RGB8 (template/precomp.h:325-341, scalar branch) of accumulator * scale
 __global__ void k_to_rgb8(const float4* __restrict__ accum, uint32_t* __restrict__ out, int n, float scale)
 {
@@ -1113,6 +1105,7 @@ struct rt_renderer {
     cudaStream_t ownStream = nullptr, stream = nullptr;
     float4* ownAccum = nullptr;
     float4* accum = nullptr;
+    void* importedAccum = nullptr; // another process' accumulator opened through CUDA IPC (rt_renderer_import_accumulator)
     int sms = 148;
     // path tracer
     PTState pt = {};
@@ -1154,6 +1147,8 @@ struct rt_renderer {
     cudaGraphExec_t whGraphExec = nullptr;
     float4* whGraphAccum = nullptr;
     int whGraphLaunches = 0;
+    DCamera whLastCam = {};      // camera of the last Whitted frame (an overflowed frame is rendered again by rt_renderer_sync)
+    bool whFramePending = false; // a Whitted frame has been launched and its overflow flag not yet checked
     // counters
     unsigned long long* dCounters = nullptr; // 4
     int* dCount = nullptr;                   // 4
@@ -1243,6 +1238,37 @@ static rt_status ralloc(rt_renderer* r, T** p, size_t bytes)
     return RT_OK;
 }
 
+static void rfree(rt_renderer* r, void* p)
+{
+    if (!p) return;
+    for (size_t i = 0; i < r->allocations.size(); i++)
+        if (r->allocations[i] == p) { r->allocations.erase(r->allocations.begin() + i); break; }
+    cudaFree(p);
+}
+
+// (re)allocates the Whitted ray / hit / shadow queues for `capacity` entries; the frame graph captured for the old buffers is dropped
+static rt_status whitted_alloc_queues(rt_renderer* r, size_t capacity)
+{
+    WhState& w = r->wh;
+    if (capacity > (size_t)0x7fffffff) capacity = 0x7fffffff;
+    if (r->stream) cudaStreamSynchronize(r->stream);
+    if (r->whGraphExec) { cudaGraphExecDestroy(r->whGraphExec); r->whGraphExec = nullptr; }
+    rt_status st;
+    for (int k = 0; k < 2; k++)
+    {
+        rfree(r, w.rayO[k]), rfree(r, w.rayD[k]), rfree(r, w.rayW[k]);
+        if ((st = ralloc(r, &w.rayO[k], capacity * 16)) != RT_OK) return st;
+        if ((st = ralloc(r, &w.rayD[k], capacity * 16)) != RT_OK) return st;
+        if ((st = ralloc(r, &w.rayW[k], capacity * 16)) != RT_OK) return st;
+    }
+    rfree(r, w.hit), rfree(r, w.hitTri), rfree(r, w.shadow);
+    if ((st = ralloc(r, &w.hit, capacity * 16)) != RT_OK) return st;
+    if ((st = ralloc(r, &w.hitTri, capacity * 4)) != RT_OK) return st;
+    if ((st = ralloc(r, &w.shadow, capacity * 80)) != RT_OK) return st;
+    w.capacity = (int)capacity;
+    return RT_OK;
+}
+
 static DCamera make_camera(const rt_camera& c, int W, int H)
 {
     DCamera d;
@@ -1287,8 +1313,10 @@ rt_status rt_renderer_create(rt_scene* scene, const rt_render_params* params, rt
         return RT_ERR_INVALID;
     }
     RT_CUDA(cudaSetDevice(scene->device));
+    if (scene->destroy_requested.load()) { set_error("rt_renderer_create: the scene has been destroyed"); return RT_ERR_INVALID; }
     rt_renderer* r = new rt_renderer();
     r->scene = scene, r->params = *params;
+    scene->renderers.fetch_add(1);
     r->passes = params->passes > 0 ? params->passes : 1;
     if (r->passes > 8) { set_error("rt_renderer_create: passes > 8 (the reference's slider stops at 4)"); delete r; return RT_ERR_UNSUPPORTED; }
     cudaDeviceGetAttribute(&r->sms, cudaDevAttrMultiProcessorCount, scene->device);
@@ -1349,16 +1377,9 @@ rt_status rt_renderer_create(rt_scene* scene, const rt_render_params* params, rt
     if (params->integrator == RT_INTEGRATOR_WHITTED)
     {
         WhState& w = r->wh;
-        w.capacity = (int)(4 * px);
-        for (int k = 0; k < 2; k++)
-        {
-            if ((st = ralloc(r, &w.rayO[k], (size_t)w.capacity * 16)) != RT_OK) return fail(st);
-            if ((st = ralloc(r, &w.rayD[k], (size_t)w.capacity * 16)) != RT_OK) return fail(st);
-            if ((st = ralloc(r, &w.rayW[k], (size_t)w.capacity * 16)) != RT_OK) return fail(st);
-        }
-        if ((st = ralloc(r, &w.hit, (size_t)w.capacity * 16)) != RT_OK) return fail(st);
-        if ((st = ralloc(r, &w.hitTri, (size_t)w.capacity * 4)) != RT_OK) return fail(st);
-        if ((st = ralloc(r, &w.shadow, (size_t)w.capacity * 80)) != RT_OK) return fail(st);
+        size_t cap = 4 * px;
+        if (const char* e = getenv("RT_B200_WHITTED_QUEUE_PER_PIXEL")) { if (atof(e) > 0) cap = (size_t)(atof(e) * px) + 1; } // tests: force the overflow path
+        if ((st = whitted_alloc_queues(r, cap)) != RT_OK) return fail(st);
         w.count = r->dCount, w.counters = r->dCounters;
         if ((st = ralloc(r, &r->dCam, sizeof(DCamera))) != RT_OK) return fail(st);
         { const char* e = getenv("RT_B200_WHITTED_GRAPH"); if (e) r->whGraphEnabled = atoi(e) != 0; }
@@ -1373,12 +1394,15 @@ void rt_renderer_destroy(rt_renderer* r)
     if (!r) return;
     cudaSetDevice(r->scene->device);
     if (r->stream) cudaStreamSynchronize(r->stream);
+    if (r->importedAccum) cudaIpcCloseMemHandle(r->importedAccum);
     for (void* p : r->allocations) cudaFree(p);
     for (cudaEvent_t e : r->evPool) cudaEventDestroy(e);
     if (r->hCount) cudaFreeHost(r->hCount);
     if (r->whGraphExec) cudaGraphExecDestroy(r->whGraphExec);
     if (r->ownStream) cudaStreamDestroy(r->ownStream);
+    rt_scene* scene = r->scene;
     delete r;
+    if (scene->renderers.fetch_sub(1) == 1 && scene->destroy_requested.load()) rt_scene_destroy(scene);
 }
 
 rt_status rt_renderer_set_stream(rt_renderer* r, void* stream)
@@ -1418,7 +1442,44 @@ rt_status rt_renderer_clear(rt_renderer* r)
 {
     if (!r) return RT_ERR_INVALID;
     RT_CUDA(cudaSetDevice(r->scene->device));
-    RT_CUDA(cudaMemsetAsync(r->accum, 0, (size_t)r->params.width * r->params.height * 16, r->stream));
+    const rt_render_params& P = r->params;
+    const int all = (P.width / 16) * (P.height / 16), mine = num_tiles(P);
+    if (P.integrator == RT_INTEGRATOR_PATH && mine < all && mine > 0)
+    {
+        // a tile shard clears its own tiles only: the accumulator may be shared with the other shards (peer-mapped)
+        k_clear_tiles<<<mine < r->sms * 8 ? mine : r->sms * 8, 256, 0, r->stream>>>(r->accum, P.width, P.width / 16, P.tile_begin, P.tile_step > 0 ? P.tile_step : 1, mine);
+        r->launches++;
+        RT_CUDA(cudaGetLastError());
+        return RT_OK;
+    }
+    RT_CUDA(cudaMemsetAsync(r->accum, 0, (size_t)P.width * P.height * 16, r->stream));
+    return RT_OK;
+}
+
+rt_status rt_renderer_export_accumulator(rt_renderer* r, void* handle_out)
+{
+    if (!r || !handle_out) { set_error("rt_renderer_export_accumulator: null argument"); return RT_ERR_INVALID; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == RT_IPC_HANDLE_BYTES, "IPC handle size");
+    if (r->accum != r->ownAccum) { set_error("rt_renderer_export_accumulator: only the renderer's own accumulator can be exported"); return RT_ERR_INVALID; }
+    RT_CUDA(cudaSetDevice(r->scene->device));
+    cudaIpcMemHandle_t h;
+    RT_CUDA(cudaIpcGetMemHandle(&h, r->ownAccum));
+    memcpy(handle_out, &h, sizeof h);
+    return RT_OK;
+}
+
+rt_status rt_renderer_import_accumulator(rt_renderer* r, const void* handle)
+{
+    if (!r || !handle) { set_error("rt_renderer_import_accumulator: null argument"); return RT_ERR_INVALID; }
+    RT_CUDA(cudaSetDevice(r->scene->device));
+    RT_CUDA(cudaStreamSynchronize(r->stream));
+    if (r->importedAccum) { cudaIpcCloseMemHandle(r->importedAccum); r->importedAccum = nullptr; r->accum = r->ownAccum; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    void* p = nullptr;
+    RT_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    r->importedAccum = p, r->accum = (float4*)p;
+    r->aheadValid = false;
     return RT_OK;
 }
 
@@ -1604,7 +1665,7 @@ static rt_status render_pt_streams_ordered(rt_renderer* r, int first_spp, int co
         r->prof_begin();
         k_sum_frames<<<nTiles < r->sms * 8 ? nTiles : r->sms * 8, 256, 0, r->stream>>>(r->accum, r->dImages, frames * (int)perFrame, P.width, P.height, P.width / 16,
             P.tile_begin, P.tile_step > 0 ? P.tile_step : 1, nTiles);
-        r->prof_end(RT_STAGE_SHADE);
+        r->prof_end(RT_STAGE_ACCUMULATE);
         RT_CUDA(cudaGetLastError());
     }
     return RT_OK;
@@ -1643,8 +1704,11 @@ static rt_status render_pt(rt_renderer* r, int first_spp, int count, int stride)
                 r->aheadValid = true, r->aheadBase = first_spp, r->aheadStride = stride, r->aheadReady = L;
             }
             const int k = (first_spp - r->aheadBase) / stride;
-            k_add_frame<<<r->sms * 4, 256, 0, r->stream>>>(r->accum, r->dFrameBuf + (size_t)k * px, (int)px);
-            r->launches++;
+            // (the shard's own tiles only: the accumulator may be shared with other tile shards)
+            r->prof_begin();
+            k_sum_frames<<<nTiles < r->sms * 8 ? nTiles : r->sms * 8, 256, 0, r->stream>>>(r->accum, r->dFrameBuf + (size_t)k * px, 1, P.width, P.height, P.width / 16,
+                P.tile_begin, P.tile_step > 0 ? P.tile_step : 1, nTiles);
+            r->prof_end(RT_STAGE_ACCUMULATE);
             RT_CUDA(cudaGetLastError());
             return RT_OK;
         }
@@ -1656,10 +1720,23 @@ static rt_status render_pt(rt_renderer* r, int first_spp, int count, int stride)
     int inFlight = P.max_frames_in_flight > 0 ? P.max_frames_in_flight : (wfPerPixel ? 8 << 20 : 1 << 20) / slotsPerFrame;
     if (inFlight < 1) inFlight = 1;
     if (inFlight > count) inFlight = count;
+    // ordered accumulation as for the stream schedule: the frames in flight write their samples to (frame, pass) images
+    float4* images = nullptr;
+    if (r->orderedFrames)
+    {
+        const size_t px = (size_t)P.width * P.height;
+        size_t fit = r->imageBudgetBytes / (px * 16 * (size_t)r->passes);
+        if (fit < 1) fit = 1;
+        if ((size_t)inFlight > fit) inFlight = (int)fit;
+        const size_t got = ensure_images(r, (size_t)inFlight * r->passes, (size_t)r->passes);
+        if (got == 0) { set_error("rt_renderer_render: no device memory for one frame's sample images"); return RT_ERR_CUDA; }
+        inFlight = (int)(got / r->passes);
+        images = r->dImages;
+    }
     rt_status st = pt_ensure_slots(r, slotsPerFrame * inFlight);
     if (st != RT_OK) return st;
     PTState& p = r->pt;
-    p.count = r->dCount, p.counters = r->dCounters, p.accum = r->accum;
+    p.count = r->dCount, p.counters = r->dCounters, p.accum = r->accum, p.frameBuf = images;
     p.nTiles = nTiles, p.tilesX = P.width / 16, p.tileBegin = P.tile_begin, p.tileStep = P.tile_step > 0 ? P.tile_step : 1;
     p.W = P.width, p.H = P.height, p.depthLimit = P.depth_limit, p.seedMode = P.seed_mode, p.eps = P.epsilon, p.passes = r->passes;
     p.stride = stride;
@@ -1695,6 +1772,13 @@ static rt_status render_pt(rt_renderer* r, int first_spp, int count, int stride)
                 RT_CUDA(cudaStreamSynchronize(r->stream));
                 if (r->hCount[0] == 0) break;
             }
+        }
+        if (images)
+        {
+            r->prof_begin();
+            k_sum_frames<<<nTiles < r->sms * 8 ? nTiles : r->sms * 8, 256, 0, r->stream>>>(r->accum, images, frames * r->passes, P.width, P.height, P.width / 16,
+                P.tile_begin, P.tile_step > 0 ? P.tile_step : 1, nTiles);
+            r->prof_end(RT_STAGE_ACCUMULATE);
         }
         r->paths += (uint64_t)nTiles * frames * 256 * r->passes;
     }
@@ -1768,6 +1852,7 @@ static rt_status render_whitted(rt_renderer* r)
     }
     else whitted_frame_launches(r);
     r->paths += (size_t)P.width * P.height;
+    r->whLastCam = r->cam, r->whFramePending = true;
     RT_CUDA(cudaGetLastError());
     return RT_OK;
 }
@@ -1785,10 +1870,34 @@ rt_status rt_renderer_sync(rt_renderer* r)
     if (!r) return RT_ERR_INVALID;
     RT_CUDA(cudaSetDevice(r->scene->device));
     RT_CUDA(cudaStreamSynchronize(r->stream));
-    if (r->params.integrator == RT_INTEGRATOR_WHITTED)
+    if (r->params.integrator == RT_INTEGRATOR_WHITTED && r->whFramePending)
     {
-        RT_CUDA(cudaMemcpy(r->hCount, r->dCount, 8 * sizeof(int), cudaMemcpyDeviceToHost));
-        if (r->hCount[3]) { set_error("Whitted ray queue overflow (more than 4 rays per pixel alive at one depth)"); return RT_ERR_UNSUPPORTED; }
+        // a frame whose ray queues overflowed dropped rays: grow the queues and render it again (Tick overwrites the accumulator,
+        // so the repeat is the frame), up to 2^depth_limit rays per pixel - the most a dielectric ray tree can hold at one depth
+        for (int attempt = 0; attempt < 8; attempt++)
+        {
+            RT_CUDA(cudaMemcpy(r->hCount, r->dCount, 8 * sizeof(int), cudaMemcpyDeviceToHost));
+            if (!r->hCount[3]) break;
+            RT_CUDA(cudaMemset(r->dCount + 3, 0, sizeof(int))); // never sticky: later frames start clean
+            const size_t px = (size_t)r->params.width * r->params.height;
+            const size_t most = px << (r->params.depth_limit < 6 ? r->params.depth_limit : 6);
+            if ((size_t)r->wh.capacity >= most || attempt == 7)
+            {
+                set_error("Whitted ray queue overflow: more rays alive at one depth than the queues can grow to");
+                r->whFramePending = false;
+                return RT_ERR_UNSUPPORTED;
+            }
+            rt_status st = whitted_alloc_queues(r, (size_t)r->wh.capacity * 2 < most ? (size_t)r->wh.capacity * 2 : most);
+            if (st != RT_OK) return st;
+            const DCamera now = r->cam;
+            r->cam = r->whLastCam;
+            st = render_whitted(r);
+            r->cam = now;
+            if (st != RT_OK) return st;
+            r->paths -= px; // the repeat is not another frame
+            RT_CUDA(cudaStreamSynchronize(r->stream));
+        }
+        r->whFramePending = false;
     }
     return RT_OK;
 }

@@ -115,8 +115,6 @@ __global__ void __launch_bounds__(256) k_eval_shading_math(int fn, const float* 
             sky_texel_exact(T, D, xe, ye);
             out[i] = !accepted ? 0.0f : (x == xe && y == ye) ? 1.0f : -1.0f;
         }
-        else if (fn == RT_MATH_EXPF_FF)
-            out[i] = rt_glibc_expf_ff(a[i]);
         else
             out[i] = fn == RT_MATH_EXPF ? rt_expf(a[i]) : fn == RT_MATH_ACOSF ? rt_acosf(a[i]) : rt_atan2f(a[i], b[i]);
     }
@@ -152,6 +150,28 @@ __global__ void __launch_bounds__(256) k_gather64(const float4* __restrict__ dat
                 acc += v.x + v.w;
             }
         }
+    }
+    if (acc == 123.456f) *sink = acc; // keep the loads alive
+}
+
+// Roofline denominator, streaming form (SURVEY 8d asks for the L2 peak): every SM reads an L2-resident buffer with coalesced
+// 128-bit loads (one warp instruction = 512 contiguous bytes), L1 bypassed (ld.global.cg), 8 independent loads in flight per thread.
+__global__ void __launch_bounds__(256) k_stream_l2(const float4* __restrict__ data, const size_t n4, const int reps, float* __restrict__ sink)
+{
+    float acc = 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (int rep = 0; rep < reps; rep++)
+    {
+        size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        for (; i + 7 * stride < n4; i += 8 * stride)
+        {
+            float4 v[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) v[q] = __ldcg(data + i + q * stride);
+#pragma unroll
+            for (int q = 0; q < 8; q++) acc += v[q].x + v[q].w;
+        }
+        for (; i < n4; i += stride) { const float4 v = __ldcg(data + i); acc += v.x + v.w; }
     }
     if (acc == 123.456f) *sink = acc; // keep the loads alive
 }
@@ -665,6 +685,9 @@ rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags,
 void rt_scene_destroy(rt_scene* s)
 {
     if (!s) return;
+    // renderers keep a pointer to their scene: while some exist the scene is only marked, and the last
+    // rt_renderer_destroy comes back here (closing a scene before its renderers is not a use-after-free)
+    if (s->renderers.load() > 0) { s->destroy_requested.store(true); return; }
     cudaSetDevice(s->device);
     cudaFree(s->nodes), cudaFree(s->tris), cudaFree(s->inst), cudaFree(s->shade), cudaFree(s->inst_shade);
     cudaFree(s->kd_nodes), cudaFree(s->grid_cells), cudaFree(s->grid_params);
@@ -817,9 +840,47 @@ rt_status rt_measure_gather_bandwidth(int device, size_t working_set_bytes, int 
     return RT_OK;
 }
 
+rt_status rt_measure_l2_stream_bandwidth(int device, size_t working_set_bytes, double* gb_per_s)
+{
+    if (!gb_per_s || working_set_bytes < (1u << 20)) { set_error("rt_measure_l2_stream_bandwidth: bad argument"); return RT_ERR_INVALID; }
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) { set_error("no such CUDA device (there is no CPU fallback)"); return RT_ERR_NO_DEVICE; }
+    RT_CUDA(cudaSetDevice(device));
+    const size_t n4 = working_set_bytes / 16;
+    float4* data = nullptr;
+    float* sink = nullptr;
+    RT_CUDA(cudaMalloc((void**)&data, n4 * 16));
+    if (cudaMalloc((void**)&sink, 4) != cudaSuccess) { cudaFree(data); set_error("rt_measure_l2_stream_bandwidth: out of device memory"); return RT_ERR_CUDA; }
+    cudaMemset(data, 0, n4 * 16);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const int grid = sms * 8, block = 256;
+    int reps = (int)((8ull << 30) / (n4 * 16)); // ~8 GB of reads per timed launch
+    if (reps < 4) reps = 4;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a), cudaEventCreate(&b);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++)
+    {
+        cudaEventRecord(a);
+        k_stream_l2<<<grid, block>>>(data, n4, reps, sink);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        if (rep > 0 && ms < best) best = ms; // the first launch warms the set into L2
+    }
+    cudaEventDestroy(a), cudaEventDestroy(b);
+    cudaError_t e = cudaGetLastError();
+    cudaFree(data), cudaFree(sink);
+    if (!cuda_ok(e, "k_stream_l2")) return RT_ERR_CUDA;
+    *gb_per_s = (double)n4 * 16 * reps / (best * 1e-3) / 1e9;
+    return RT_OK;
+}
+
 rt_status rt_eval_shading_math(int device, int fn, const float* a, const float* b, float* out, size_t n)
 {
-    if (fn < RT_MATH_EXPF || fn > RT_MATH_EXPF_FF || (n && (!a || !out || ((fn == RT_MATH_ATAN2F || fn == RT_MATH_SKY_TEXEL) && !b)))) { set_error("rt_eval_shading_math: bad argument"); return RT_ERR_INVALID; }
+    if (fn < RT_MATH_EXPF || fn > RT_MATH_SKY_TEXEL || (n && (!a || !out || ((fn == RT_MATH_ATAN2F || fn == RT_MATH_SKY_TEXEL) && !b)))) { set_error("rt_eval_shading_math: bad argument"); return RT_ERR_INVALID; }
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) { set_error("no such CUDA device (there is no CPU fallback)"); return RT_ERR_NO_DEVICE; }
     if (n == 0) return RT_OK;

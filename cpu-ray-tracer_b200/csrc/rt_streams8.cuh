@@ -338,4 +338,15 @@ __global__ void __launch_bounds__(256) k_sum_frames(float4* __restrict__ accum, 
     }
 }
 
+// Renderer::ClearAccumulator for the tiles of one shard (rt_renderer_clear of a tile-sharded renderer)
+__global__ void __launch_bounds__(256) k_clear_tiles(float4* __restrict__ accum, const int W, const int tilesX, const int tileBegin, const int tileStep, const int nTiles)
+{
+    for (int k = blockIdx.x; k < nTiles; k += gridDim.x)
+    {
+        const int tile = tileBegin + k * tileStep;
+        const int x = (tile % tilesX) * 16 + (threadIdx.x & 15), y = (tile / tilesX) * 16 + (threadIdx.x >> 4);
+        accum[x + (size_t)y * W] = make_float4(0, 0, 0, 0);
+    }
+}
+
 } // namespace rtb

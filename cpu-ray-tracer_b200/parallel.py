@@ -11,6 +11,12 @@ data-path exchange; the only collective is one reduce of the float4 accumulators
       or a contiguous range of it
 
 Both give, after the sum over ranks, the single-process image up to float reassociation.
+
+  shared accumulator (round 2, what bench.py --gpus N uses): with interleaved tile shards the ranks touch disjoint
+      pixels, so they can all accumulate into ONE image: rank 0 exports its accumulator as a CUDA IPC handle
+      (share_accumulator), the others map it (peer memory over NVLink) and their frame-ordered sums write their tiles
+      straight into it.  No reduce, no gather; after a barrier the image on rank 0 is bit-identical to a one-GPU render.
+
 This module is host logic only (no CUDA): the caller supplies the per-rank render function.
 """
 from dataclasses import dataclass
@@ -96,3 +102,16 @@ def render_sharded(render_frames, acc, first_spp, frames, mode="frames", width=N
     else:
         raise ValueError(mode)
     return reduce_accumulator(acc)
+
+
+def share_accumulator(renderer, rank, world, src=0):
+    """Rank `src` exports its renderer's accumulator (renderer.export_accumulator() -> bytes), every other rank maps it with
+    renderer.import_accumulator(bytes).  The handle travels through torch.distributed's object broadcast (host side, once)."""
+    import torch.distributed as dist
+    if world <= 1:
+        return None
+    box = [renderer.export_accumulator() if rank == src else None]
+    dist.broadcast_object_list(box, src=src)
+    if rank != src:
+        renderer.import_accumulator(box[0])
+    return box[0]

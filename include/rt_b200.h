@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RT_B200_ABI_VERSION 3
+#define RT_B200_ABI_VERSION 4
 
 typedef int rt_status;
 enum {
@@ -322,15 +322,50 @@ rt_status rt_renderer_read_accumulator(rt_renderer* r, float* host_rgba);
  * (template/precomp.h:325-341; scale = 1/(spp+passes) for the path tracer, 1 for Whitted). */
 rt_status rt_renderer_read_pixels(rt_renderer* r, float scale, uint32_t* host_rgb8);
 void* rt_renderer_device_accumulator(rt_renderer* r);
+
+/* Tile-sharded rendering by several PROCESSES (one per GPU, e.g. torchrun): the process that owns the image exports its
+ * accumulator as a CUDA IPC handle (RT_IPC_HANDLE_BYTES opaque bytes, sent to the other ranks by any means); the others
+ * import it, after which their renderers accumulate straight into that memory over NVLink (peer-mapped stores of the
+ * frame-ordered sum, k_sum_frames) - the image is complete after a barrier, no reduce / gather, and bit-identical to a
+ * one-GPU render because interleaved tile shards (tile_begin = rank, tile_step = ranks) touch disjoint pixels.
+ * rt_renderer_clear of a tile-sharded renderer clears only its own tiles.  ABI v4. */
+#define RT_IPC_HANDLE_BYTES 64
+rt_status rt_renderer_export_accumulator(rt_renderer* r, void* handle_out);
+rt_status rt_renderer_import_accumulator(rt_renderer* r, const void* handle);
 rt_status rt_renderer_get_counters(rt_renderer* r, rt_counters* out);
 rt_status rt_renderer_reset_counters(rt_renderer* r);
+
+/* ---- Renderer::Tick on several GPUs of ONE process ---------------------------------------------------------
+ * The tile jobs of a frame are independent (3. PathTracer/renderer.cpp:144-168 hands them to a job pool); here the pool is
+ * the GPUs of the box: the scene is replicated on `n` devices, device k renders tiles k, k + n, ... of every frame
+ * (interleaved shards balance the cost that varies across the image) and its frame-ordered sum writes them straight
+ * into the accumulator on devices[0] through peer-mapped memory over NVLink.  No reduce, no gather; the accumulator is
+ * bit-identical to a one-GPU render of the same frames.  Path tracer only (a Whitted frame is 0.2 ms on one GPU).
+ * Calls are asynchronous on every device like rt_renderer_render; rt_multi_renderer_sync / _read_accumulator wait for all.
+ * Needs peer access between devices[0] and the others (NVLink / NVSwitch boxes): RT_ERR_UNSUPPORTED otherwise.  ABI v4. */
+typedef struct rt_multi_renderer rt_multi_renderer;
+rt_status rt_multi_renderer_create(const rt_scene_desc* desc, uint32_t scene_flags, const int* devices, int n,
+                                   const rt_render_params* params, rt_multi_renderer** out);
+void rt_multi_renderer_destroy(rt_multi_renderer* m);
+int rt_multi_renderer_device_count(const rt_multi_renderer* m);
+rt_status rt_multi_renderer_set_camera(rt_multi_renderer* m, const rt_camera* cam);
+rt_status rt_multi_renderer_set_passes(rt_multi_renderer* m, int passes);
+rt_status rt_multi_renderer_clear(rt_multi_renderer* m);
+rt_status rt_multi_renderer_render(rt_multi_renderer* m, int first_spp, int count, int stride);
+rt_status rt_multi_renderer_sync(rt_multi_renderer* m);
+rt_status rt_multi_renderer_read_accumulator(rt_multi_renderer* m, float* host_rgba);
+rt_status rt_multi_renderer_read_pixels(rt_multi_renderer* m, float scale, uint32_t* host_rgb8);
+/* counters summed over the devices */
+rt_status rt_multi_renderer_get_counters(rt_multi_renderer* m, rt_counters* out);
+rt_status rt_multi_renderer_reset_counters(rt_multi_renderer* m);
 
 /* Per-stage device time (the reference's own instrumentation is a Timer around the pixel loop,
  * template/precomp.h:146-157, and per-ray traversed/tested counters).  With profiling enabled every
  * kernel launch is bracketed by CUDA events on the renderer's stream; rt_renderer_get_stage_times
  * synchronises, sums the spans per stage, returns them and resets.  Costs ~2 event records per launch,
  * so throughput numbers are taken with profiling off. */
-enum { RT_STAGE_GENERATE = 0, RT_STAGE_EXTEND = 1, RT_STAGE_SHADE = 2, RT_STAGE_CONNECT = 3, RT_STAGE_COUNT = 4 };
+/* RT_STAGE_ACCUMULATE: the frame-ordered sum of a multi-frame launch's sample images into the accumulator (k_sum_frames / k_add_frame) */
+enum { RT_STAGE_GENERATE = 0, RT_STAGE_EXTEND = 1, RT_STAGE_SHADE = 2, RT_STAGE_CONNECT = 3, RT_STAGE_ACCUMULATE = 4, RT_STAGE_COUNT = 5 };
 typedef struct rt_stage_times {
     double ms[RT_STAGE_COUNT];
     uint64_t launches[RT_STAGE_COUNT];
@@ -361,6 +396,10 @@ rt_status rt_build_bvh(int device, const rt_tri* tris, uint32_t n, rt_bvh_node* 
  * scenes whose geometry is L2-resident (SURVEY.md section 8d asks for a measured L2 peak).  bypass_l1 != 0
  * uses ld.global.cg.  No reference equivalent (the reference has no memory-hierarchy instrumentation). */
 rt_status rt_measure_gather_bandwidth(int device, size_t working_set_bytes, int bypass_l1, double* gb_per_s);
+/* Measured bandwidth of STREAMING reads of an L2-resident buffer (every SM, coalesced 128-bit loads, L1 bypassed, 8 loads in
+ * flight per thread): the L2 peak the roofline of the L2-resident scenes is quoted against (bench.py `roofline.peak`).
+ * working_set_bytes: 32-64 MB keeps the set inside the 126 MB L2.  ABI v4. */
+rt_status rt_measure_l2_stream_bandwidth(int device, size_t working_set_bytes, double* gb_per_s);
 
 /* Evaluates, ON THE DEVICE, the transcendental routines the shading kernels use, over host arrays of n arguments:
  * fn = RT_MATH_EXPF: out[i] = expf(a[i])   (Beer's law, renderer.cpp:76-80; b is ignored and may be NULL)
@@ -376,9 +415,6 @@ rt_status rt_measure_gather_bandwidth(int device, size_t working_set_bytes, int 
  * routines give, 0 when the lookup was too close to a texel border and was handed to the glibc routines, -1 when the fast lookup
  * accepted a different texel (the parity tests require that this never happens). */
 #define RT_MATH_SKY_TEXEL 3
-/* fn = RT_MATH_EXPF_FF: out[i] = expf(a[i]) through the float-float evaluation of csrc/rt_glibc_math.cuh (experimental build variant
- * RT_B200_EXPF_FF: same bits as glibc's expf, double arithmetic only near rounding boundaries); b is ignored. */
-#define RT_MATH_EXPF_FF 4
 rt_status rt_eval_shading_math(int device, int fn, const float* a, const float* b, float* out, size_t n);
 
 #ifdef __cplusplus

@@ -168,14 +168,15 @@ def _main(argv):
         # warmup x frames untimed, then steps x frames timed; JSON on stdout
         import json
         integrator, kind, scene, W, H, frames, warmup, steps = argv[1], argv[2], argv[3], int(argv[4]), int(argv[5]), int(argv[6]), int(argv[7]), int(argv[8])
-        r = RefRenderer(integrator, kind, scene, W, H)
+        fast = len(argv) > 9 and argv[9] == "1"
+        r = RefRenderer(integrator, kind, scene, W, H, fast=fast)
         for _ in range(warmup):
             r.tick(frames)
         secs = 0.0
         for _ in range(steps):
             secs += r.tick(frames)
-        print(json.dumps({"seconds": secs, "threads": r.threads(), "frames": frames,
-                          "flags": "reference Renderer::Tick built headless with g++ -O2 -fopenmp -ffp-contract=off"}))
+        print(json.dumps({"seconds": secs, "threads": r.threads(), "frames": frames, "fast": fast,
+                          "flags": "reference Renderer::Tick built headless with g++ " + ("-O3 -mavx2 -mfma -ffast-math" if fast else "-O2 -fopenmp -ffp-contract=off")}))
     elif cmd == "flatten":
         integrator, kind, scene, out = argv[1], argv[2], argv[3], os.path.abspath(argv[4])
         r = RefRenderer(integrator, kind, scene, 64, 64)

@@ -15,11 +15,8 @@ import bench  # noqa: E402
 
 
 def test_profile_readers_return_numbers():
-    traffic, src = bench.ncu_dram_traffic()
-    assert src is None or os.path.exists(os.path.join(ROOT, src))
-    assert traffic is None or traffic > 0
-    issue = bench.ncu_issue_figures()
-    assert issue is None or isinstance(issue, dict)
+    prof = bench.kernel_profile()
+    assert prof is None or (os.path.exists(os.path.join(ROOT, prof["source"])) and prof.get("warp_instructions_per_launch", 1) > 0)
     peaks, kind = bench.measured_peaks()
     assert peaks["hbm_gbs"] > 1000 and isinstance(kind, str)
 
@@ -27,10 +24,16 @@ def test_profile_readers_return_numbers():
 def test_algorithmic_bytes_per_ray_from_oracle_counters(flat_scenes):
     """64 I + 52 T + 64 B + 48 bytes per ray, I / T / B from the oracle's traversal counters"""
     w = bench.oracle_work_per_ray(flat_scenes("golden_file"), 64, 36, frames=1)
-    assert w["I"] > 0 and w["T"] > 0 and w["B"] == 0
-    assert abs(w["bytes_per_ray"] - (64 * w["I"] + 52 * w["T"] + 64 * w["B"] + 48)) < 1e-6
+    assert w["interior_visits"] > 0 and w["tri_tests"] > 0 and w["blas_entries"] == 0
+    assert abs(w["bytes_per_ray"] - (64 * w["interior_visits"] + 52 * w["tri_tests"] + 64 * w["blas_entries"] + 48)) < 1e-6
     w = bench.oracle_work_per_ray(flat_scenes("golden_tlas"), 64, 36, frames=1)
-    assert w["B"] > 0
+    assert w["blas_entries"] > 0
+
+
+def test_both_arms_describe_the_job_with_the_same_config_keys():
+    a = bench.config_block("w", 1920, 1080, 64, 1)
+    b = bench.config_block("w", 1920, 1080, 64, 8)
+    assert set(a) == set(b) and a["total_spp"] == 64 and b["total_spp"] == 512 and "tiles" in b["sharding"]
 
 
 def test_alt_build_child_failure_is_reported_not_raised(monkeypatch, tmp_path):
@@ -41,7 +44,6 @@ def test_alt_build_child_failure_is_reported_not_raised(monkeypatch, tmp_path):
     assert res is None or res["value"] is not None or "failed" in res["note"]  # (a GPU box returns the timed line)
     monkeypatch.setenv("RT_B200_LIB", "/nonexistent.so")
     assert bench.alt_build_line(args) is None  # never recurses when a library override is already active
-    assert bench.alt_build_lines(args) is None
 
 
 def test_reference_arm_prints_the_contract_line():
@@ -52,3 +54,6 @@ def test_reference_arm_prints_the_contract_line():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "Mrays/s"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] in ("reference", "port")
+    assert set(line["config"]) == set(bench.config_block("w", 64, 36, 64, 1))  # the GPU arm's keys
+    if line["cpu_baseline"]["kind"] == "reference":
+        assert "strict" in line["cpu_baseline"]["builds"]  # both builds of the reference are reported

@@ -22,7 +22,6 @@ static uint64_t rng(uint64_t* s) { *s ^= *s << 13; *s ^= *s >> 7; *s ^= *s << 17
         } \
         return bad; }
 CHECK1(expf, rt_glibc_expf, expf)
-CHECK1(expf_ff, rt_glibc_expf_ff, expf)
 CHECK1(acosf, rt_glibc_acosf, acosf)
 CHECK1(atanf, rt_glibc_atanf, atanf)
 
@@ -34,33 +33,14 @@ static long pair(float y, float x)
     return 1;
 }
 
-// how often the float-float expf decides by itself: over the arguments with a normal result, and over the Beer's-law range
-static void expf_ff_acceptance(uint64_t stride)
-{
-    long all = 0, fast = 0, shade = 0, shade_fast = 0;
-    #pragma omp parallel for reduction(+:all, fast, shade, shade_fast) schedule(static)
-    for (uint64_t i = 0; i < (1ull << 32); i += stride)
-    {
-        const float x = rt_gm_u2f((uint32_t)i);
-        if (!(x > -87.0f && x < 88.0f)) continue;
-        int acc;
-        rt_glibc_expf_ff_impl(x, &acc);
-        all++, fast += acc;
-        if (x < -1e-4f && x > -40.0f) shade++, shade_fast += acc;
-    }
-    printf("expfff decides itself for %.3f %% of the arguments in (-87, 88), %.3f %% of those in (-40, -1e-4)\n", 100.0 * fast / all, 100.0 * shade_fast / shade);
-}
-
 int main(int argc, char** argv)
 {
     const uint64_t stride = argc > 1 ? strtoull(argv[1], 0, 10) : 4099;
     const long pairs = argc > 2 ? atol(argv[2]) : 2000000;
     long total = 0, bad;
     bad = check_expf(stride), total += bad, printf("expf   stride %llu mismatches %ld\n", (unsigned long long)stride, bad);
-    bad = check_expf_ff(stride), total += bad, printf("expfff stride %llu mismatches %ld\n", (unsigned long long)stride, bad);
     bad = check_acosf(stride), total += bad, printf("acosf  stride %llu mismatches %ld\n", (unsigned long long)stride, bad);
     bad = check_atanf(stride), total += bad, printf("atanf  stride %llu mismatches %ld\n", (unsigned long long)stride, bad);
-    expf_ff_acceptance(stride);
     static const uint32_t special[] = { 0x00000000u, 0x80000000u, 0x00000001u, 0x80000001u, 0x007fffffu, 0x00800000u, 0x3f800000u, 0xbf800000u,
         0x3f000000u, 0x3effffffu, 0x3ee00000u, 0x3f300000u, 0x3f980000u, 0x401c0000u, 0x4c000000u, 0x4bffffffu, 0x31000000u, 0x30ffffffu,
         0x7f7fffffu, 0xff7fffffu, 0x7f800000u, 0xff800000u, 0x7fc00000u, 0xffc00000u, 0x5e800000u, 0xde800000u, 0x4c000001u, 0x30800000u, 0xb0800000u, 0x3e000000u, 0xbf000000u, 0x40000000u, 0xc0400000u, 0x21000000u, 0x40490fdbu, 0x3fc90fdbu };
@@ -96,5 +76,5 @@ void libm_eval(int fn, const float* a, const float* b, float* out, size_t n)
 }
 void restated_eval(int fn, const float* a, const float* b, float* out, size_t n)
 {
-    for (size_t i = 0; i < n; i++) out[i] = fn == 0 ? rt_glibc_expf(a[i]) : fn == 1 ? rt_glibc_acosf(a[i]) : fn == 4 ? rt_glibc_expf_ff(a[i]) : rt_glibc_atan2f(a[i], b[i]);
+    for (size_t i = 0; i < n; i++) out[i] = fn == 0 ? rt_glibc_expf(a[i]) : fn == 1 ? rt_glibc_acosf(a[i]) : rt_glibc_atan2f(a[i], b[i]);
 }
