@@ -13,6 +13,7 @@ RT_SEED_REFERENCE_TILE, RT_SEED_PER_PIXEL = 0, 1
 RT_SCHEDULE_AUTO, RT_SCHEDULE_WAVEFRONT, RT_SCHEDULE_STREAMS = 0, 1, 2
 RT_MATH_EXPF, RT_MATH_ACOSF, RT_MATH_ATAN2F, RT_MATH_SKY_TEXEL = 0, 1, 2, 3
 RT_IPC_HANDLE_BYTES = 64
+RT_REFIT_ALL_NODES, RT_REFIT_REBUILD_TLAS = 1, 2
 
 f3 = C.c_float * 3
 f16 = C.c_float * 16
@@ -58,7 +59,8 @@ class rt_scene_desc(C.Structure):
                 ("kd_nodes", C.c_void_p), ("kd_node_count", C.c_uint32),
                 ("kd_tri_indices", C.c_void_p), ("kd_tri_index_count", C.c_uint32),
                 ("grid", C.POINTER(rt_grid_desc)),
-                ("blas_accel", C.POINTER(rt_blas_accel))]
+                ("blas_accel", C.POINTER(rt_blas_accel)),
+                ("tlas_nodes32", C.c_void_p), ("tlas_node32_count", C.c_uint32)]
 
 
 class rt_camera(C.Structure):
@@ -90,6 +92,7 @@ TRI_DTYPE = np.dtype([("v0", "<f4", 3), ("v1", "<f4", 3), ("v2", "<f4", 3),
                       ("uv0", "<f4", 2), ("uv1", "<f4", 2), ("uv2", "<f4", 2),
                       ("centroid", "<f4", 3), ("obj_idx", "<i4")])
 TLAS_NODE_DTYPE = np.dtype([("aabb_min", "<f4", 3), ("left_right", "<u4"), ("aabb_max", "<f4", 3), ("blas", "<u4")])
+TLAS_NODE32_DTYPE = np.dtype([("aabb_min", "<f4", 3), ("left", "<u4"), ("aabb_max", "<f4", 3), ("right", "<u4")])
 KD_NODE_DTYPE = np.dtype([("aabb_min", "<f4", 3), ("left", "<i4"), ("aabb_max", "<f4", 3), ("right", "<i4"),
                           ("split_axis", "<i4"), ("split_distance", "<f4"), ("tri_start", "<u4"), ("tri_count", "<u4")])
 GRID_HEADER_DTYPE = np.dtype([("resolution", "<i4", 3), ("cell_size", "<f4", 3), ("bounds_min", "<f4", 3), ("bounds_max", "<f4", 3)])
@@ -102,5 +105,6 @@ RAY_DTYPE = np.dtype([("O", "<f4", 3), ("tmax", "<f4"), ("D", "<f4", 3), ("insid
 HIT_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("obj_idx", "<i4"), ("tri_idx", "<i4"),
                       ("traversed", "<i4"), ("tested", "<i4"), ("reserved", "<i4")])
 assert NODE_DTYPE.itemsize == 32 and TRI_DTYPE.itemsize == 112 and TLAS_NODE_DTYPE.itemsize == 32
+assert TLAS_NODE32_DTYPE.itemsize == 32
 assert KD_NODE_DTYPE.itemsize == 48 and GRID_HEADER_DTYPE.itemsize == 48
 assert MATERIAL_DTYPE.itemsize == 40 and RAY_DTYPE.itemsize == 32 and HIT_DTYPE.itemsize == 32

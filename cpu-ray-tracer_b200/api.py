@@ -38,6 +38,7 @@ EXPORTS = [
     "rt_multi_renderer_set_passes", "rt_multi_renderer_clear", "rt_multi_renderer_render", "rt_multi_renderer_sync",
     "rt_multi_renderer_read_accumulator", "rt_multi_renderer_read_pixels", "rt_multi_renderer_get_counters",
     "rt_multi_renderer_reset_counters",
+    "rt_build_tlas", "rt_scene_refit", "rt_scene_download_bvh",
 ]
 
 
@@ -113,6 +114,9 @@ def lib():
     L.rt_multi_renderer_read_pixels.argtypes = [vp, C.c_float, vp]
     L.rt_multi_renderer_get_counters.argtypes = [vp, C.POINTER(abi.rt_counters)]
     L.rt_multi_renderer_reset_counters.argtypes = [vp]
+    L.rt_build_tlas.argtypes = [i32, vp, C.c_uint32, vp, C.POINTER(C.c_uint32), C.POINTER(C.c_double)]
+    L.rt_scene_refit.argtypes = [vp, C.c_uint32, vp, C.c_uint32, C.c_uint32]
+    L.rt_scene_download_bvh.argtypes = [vp, C.c_uint32, vp, vp, C.POINTER(C.c_uint32)]
     _lib = L
     return L
 
@@ -158,6 +162,17 @@ def eval_shading_math(fn, a, b=None, device=0):
     out = np.empty_like(a)
     _check(lib().rt_eval_shading_math(device, fn, a.ctypes.data, None if b is None else b.ctypes.data, out.ctypes.data, a.size))
     return out
+
+
+def build_tlas_gpu(bounds, device=0, return_ms=False):
+    """TLASBVH::Build (tlas_bvh.cpp:17-70) on the GPU over an (n, 6) array of world bounds: rt_build_tlas.
+    Returns the 2n nodes in the reference's order with 32-bit children (abi.TLAS_NODE32_DTYPE)."""
+    bounds = np.ascontiguousarray(bounds, np.float32).reshape(-1, 6)
+    n = len(bounds)
+    out = np.zeros(2 * n, abi.TLAS_NODE32_DTYPE)
+    used, ms = C.c_uint32(), C.c_double()
+    _check(lib().rt_build_tlas(device, bounds.ctypes.data, n, out.ctypes.data, C.byref(used), C.byref(ms)))
+    return (out[:used.value], ms.value) if return_ms else out[:used.value]
 
 
 class Camera:
@@ -241,6 +256,21 @@ class GpuScene:
 
     def GetTriangleCount(self):
         return self.flat.triangle_count
+
+    # -- scene construction steps on the device -----------------------------------
+    def Refit(self, blas_index, tris, all_nodes=False, rebuild_tlas=False):
+        """BVH::Refit / BLASBVH::Refit (bvh.cpp:26-43) for the mesh of BLAS `blas_index` after its triangles moved:
+        rt_scene_refit.  `tris`: the mesh's TRI_DTYPE array in its own order (same count)."""
+        tris = np.ascontiguousarray(tris, abi.TRI_DTYPE)
+        flags = (abi.RT_REFIT_ALL_NODES if all_nodes else 0) | (abi.RT_REFIT_REBUILD_TLAS if rebuild_tlas else 0)
+        _check(lib().rt_scene_refit(self.handle, blas_index, tris.ctypes.data, len(tris), flags))
+
+    def download_bvh(self, blas_index=0):
+        """the device's traversal layout of one mesh read back as the reference's arrays: (nodes[:nodesUsed], tri_indices)"""
+        n = int(self.flat.blas_table[blas_index]["tri_count"])
+        nodes, idx, used = np.zeros(2 * n - 1, abi.NODE_DTYPE), np.zeros(n, np.uint32), C.c_uint32()
+        _check(lib().rt_scene_download_bvh(self.handle, blas_index, nodes.ctypes.data, idx.ctypes.data, C.byref(used)))
+        return nodes[:used.value], idx
 
 
 class GpuFileScene(GpuScene):

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librt_b200.so")
-SOURCES = ["rt_scene.cu", "rt_render.cu", "rt_build.cu", "rt_multi.cu"]
+SOURCES = ["rt_scene.cu", "rt_render.cu", "rt_build.cu", "rt_construct.cu", "rt_multi.cu"]
 HEADERS = ["rt_device.cuh", "rt_streams8.cuh", "rt_glibc_math.cuh", "rt_internal.h", os.path.join("..", "..", "include", "rt_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -488,16 +488,29 @@ struct DevBuf {
         ptrs.push_back(*p);
         return true;
     }
+    void keep(void* p) // hand an allocation over to the caller
+    {
+        for (void*& q : ptrs) if (q == p) q = nullptr;
+    }
 };
 
 } // namespace rtb
 
 using namespace rtb;
 
-extern "C" rt_status rt_build_bvh(int device, const rt_tri* tris, uint32_t n, rt_bvh_node* nodes_out, uint32_t* tri_indices_out,
-    uint32_t* nodes_used, double* device_ms)
+namespace rtb {
+
+void DeviceBvh::release()
 {
-    if (!tris || !nodes_out || !tri_indices_out || n == 0 || n > (1u << 30)) { set_error("rt_build_bvh: bad argument"); return RT_ERR_INVALID; }
+    cudaFree(tris), cudaFree(nodes), cudaFree(idx);
+    tris = nullptr, nodes = nullptr, idx = nullptr;
+}
+
+// The build proper: host triangles in, the reference-layout arrays left in device memory (rt_internal.h DeviceBvh).
+// rt_build_bvh downloads them; rt_scene_create lays them out for traversal without leaving the device (rt_construct.cu).
+rt_status build_bvh_on_device(int device, const rt_tri* tris, uint32_t n, DeviceBvh& result)
+{
+    if (!tris || n == 0 || n > (1u << 30)) { set_error("rt_build_bvh: bad argument"); return RT_ERR_INVALID; }
     int devices = 0;
     if (cudaGetDeviceCount(&devices) != cudaSuccess || device < 0 || device >= devices)
     {
@@ -614,9 +627,25 @@ extern "C" rt_status rt_build_bvh(int device, const rt_tri* tris, uint32_t n, rt
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     if (!cuda_ok(err, "rt_build_bvh kernels") || !cuda_ok(cudaGetLastError(), "rt_build_bvh kernels")) return RT_ERR_CUDA;
-    RT_CUDA(cudaMemcpy(nodes_out, dOut, (size_t)total * sizeof(rt_bvh_node), cudaMemcpyDeviceToHost));
-    RT_CUDA(cudaMemcpy(tri_indices_out, idx, (size_t)n * 4, cudaMemcpyDeviceToHost));
-    if (nodes_used) *nodes_used = (uint32_t)total;
-    if (device_ms) *device_ms = ms;
+    // the three result arrays outlive the scratch buffers
+    B.keep(dTris), B.keep(dOut), B.keep(idx);
+    result.tris = dTris, result.nodes = dOut, result.idx = idx;
+    result.n = n, result.total = (uint32_t)total, result.depth = (int)levels.size(), result.ms = ms;
+    return RT_OK;
+}
+
+} // namespace rtb
+
+extern "C" rt_status rt_build_bvh(int device, const rt_tri* tris, uint32_t n, rt_bvh_node* nodes_out, uint32_t* tri_indices_out,
+    uint32_t* nodes_used, double* device_ms)
+{
+    if (!tris || !nodes_out || !tri_indices_out || n == 0 || n > (1u << 30)) { set_error("rt_build_bvh: bad argument"); return RT_ERR_INVALID; }
+    struct Holder { DeviceBvh b; ~Holder() { b.release(); } } h;
+    const rt_status st = build_bvh_on_device(device, tris, n, h.b);
+    if (st != RT_OK) return st;
+    RT_CUDA(cudaMemcpy(nodes_out, h.b.nodes, (size_t)h.b.total * sizeof(rt_bvh_node), cudaMemcpyDeviceToHost));
+    RT_CUDA(cudaMemcpy(tri_indices_out, h.b.idx, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    if (nodes_used) *nodes_used = h.b.total;
+    if (device_ms) *device_ms = h.b.ms;
     return RT_OK;
 }

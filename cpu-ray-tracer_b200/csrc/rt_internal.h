@@ -19,6 +19,33 @@ bool cuda_ok(cudaError_t e, const char* what);
         if (!rtb::cuda_ok((call), #call)) return RT_ERR_CUDA;    \
     } while (0)
 
+// Result of the device SAH build (rt_build.cu): the reference-layout arrays, left in device memory
+struct DeviceBvh {
+    rt_tri* tris = nullptr;        // the uploaded 112-byte triangles
+    rt_bvh_node* nodes = nullptr;  // `total` nodes, reference numbering
+    uint32_t* idx = nullptr;       // triangleIndices
+    uint32_t n = 0, total = 0;
+    int depth = 0;                 // levels of the tree (a single leaf = 1)
+    double ms = 0;
+    void release();
+};
+rt_status build_bvh_on_device(int device, const rt_tri* host_tris, uint32_t n, DeviceBvh& out);
+
+// One mesh of a BVH-kind scene on the device (several BLAS instances may share it): where its fat nodes, triangle records and
+// shading records live.  rt_scene_refit works on these ranges.
+struct Geometry {
+    int fatBase = 0, fatCount = 0;   // interior nodes: nodes[4 * fatBase .. 4 * (fatBase + fatCount))
+    int triBase = 0;                 // first triangle slot = first shading record
+    uint32_t triCount = 0;
+    int rootRef = 0;
+};
+
+// rt_construct.cu: scene construction steps that run on the device
+rt_status layout_built_bvh(const DeviceBvh& b, int fatBase, int triBase, float4* nodes, float4* tris, float4* shade, cudaStream_t stream);
+rt_status build_tlas_on_device(int device, const float* d_world_bounds, uint32_t n, rt_tlas_node32* d_out, int* d_depth, cudaStream_t stream);
+rt_status layout_built_tlas(const rt_tlas_node32* d_tlas, uint32_t n, int fatBase, float4* nodes, cudaStream_t stream);
+void world_bounds_of(const float* root_min, const float* root_max, const float* T, float* out6);
+
 } // namespace rtb
 
 // Runs CALL with `A` = the accelerator id the scene kind selects (kernel template argument).
@@ -53,6 +80,12 @@ struct rt_scene {
     // renderers created on this scene: rt_scene_destroy while some exist only marks the scene, the last rt_renderer_destroy frees it
     std::atomic<int> renderers{0};
     std::atomic<bool> destroy_requested{false};
+    // BVH kinds: the meshes and which one every BLAS instance uses (rt_scene_refit); TLAS: where its fat nodes live
+    std::vector<rtb::Geometry> geometries;
+    std::vector<int> blas_geometry;
+    std::vector<float> blas_T;          // 16 floats per instance (world bounds after a refit)
+    int tlas_fat_base = 0, tlas_fat_count = 0;
+    int max_blas_depth = 0;
     int stack_entries = 0; // most far children one ray can have pending (bound from the tree depths, rt_scene_create)
     size_t bytes_geometry = 0, bytes_textures = 0;
     // scratch for the host-buffer entry points (rt_find_nearest / rt_is_occluded)

@@ -287,14 +287,24 @@ struct Builder {
         }
     }
 
-    int add_tlas(const rt_scene_desc& d)
+    // children / leaf payload of the two TLAS node formats (reference 2 x 16 bit, ABI v5 2 x 32 bit)
+    static bool tlas_is_leaf(const rt_tlas_node& n) { return n.left_right == 0; }
+    static uint32_t tlas_left(const rt_tlas_node& n) { return n.left_right & 0xffff; }
+    static uint32_t tlas_right(const rt_tlas_node& n) { return n.left_right >> 16; }
+    static uint32_t tlas_blas(const rt_tlas_node& n) { return n.blas; }
+    static bool tlas_is_leaf(const rt_tlas_node32& n) { return n.left == 0; }
+    static uint32_t tlas_left(const rt_tlas_node32& n) { return n.left; }
+    static uint32_t tlas_right(const rt_tlas_node32& n) { return n.right; }
+    static uint32_t tlas_blas(const rt_tlas_node32& n) { return n.right; }
+
+    template <class TNode>
+    int add_tlas(const TNode* N, const uint32_t nodeCount, const uint32_t blasCount)
     {
-        const rt_tlas_node* N = d.tlas_nodes;
-        auto leaf_ref = [&](const rt_tlas_node& n) { return ~(INSTANCE_BIT | (int)n.blas); };
+        auto leaf_ref = [&](const TNode& n) { return ~(INSTANCE_BIT | (int)tlas_blas(n)); };
         lastDepth = 1;
-        if (N[0].left_right == 0)
+        if (tlas_is_leaf(N[0]))
         {
-            if (N[0].blas >= d.blas_count) { error = "TLAS leaf BLAS index out of range"; return 0; }
+            if (tlas_blas(N[0]) >= blasCount) { error = "TLAS leaf BLAS index out of range"; return 0; }
             return leaf_ref(N[0]);
         }
         struct Item { uint32_t node; int fat; int depth; };
@@ -305,21 +315,21 @@ struct Builder {
         size_t guard = 0;
         while (!todo.empty())
         {
-            if (++guard > 4ull * d.tlas_node_count + 16) { error = "TLAS is not a tree"; return 0; }
+            if (++guard > 4ull * nodeCount + 16) { error = "TLAS is not a tree"; return 0; }
             const Item it = todo.back();
             todo.pop_back();
             if (it.depth + 1 > lastDepth) lastDepth = it.depth + 1;
-            const rt_tlas_node& p = N[it.node];
-            const uint32_t li = p.left_right & 0xffff, ri = p.left_right >> 16;
-            if (li >= d.tlas_node_count || ri >= d.tlas_node_count) { error = "TLAS child index out of range"; return 0; }
-            const rt_tlas_node* ch[2] = { &N[li], &N[ri] };
+            const TNode& p = N[it.node];
+            const uint32_t li = tlas_left(p), ri = tlas_right(p);
+            if (li >= nodeCount || ri >= nodeCount) { error = "TLAS child index out of range"; return 0; }
+            const TNode* ch[2] = { &N[li], &N[ri] };
             const uint32_t idx[2] = { li, ri };
             int refs[2];
             for (int k = 1; k >= 0; k--)
             {
-                if (ch[k]->left_right == 0)
+                if (tlas_is_leaf(*ch[k]))
                 {
-                    if (ch[k]->blas >= d.blas_count) { error = "TLAS leaf BLAS index out of range"; return 0; }
+                    if (tlas_blas(*ch[k]) >= blasCount) { error = "TLAS leaf BLAS index out of range"; return 0; }
                     refs[k] = leaf_ref(*ch[k]);
                 }
                 else
@@ -329,8 +339,8 @@ struct Builder {
                     todo.push_back({ idx[k], refs[k], it.depth + 1 });
                 }
             }
-            const rt_tlas_node& L = *ch[0];
-            const rt_tlas_node& R = *ch[1];
+            const TNode& L = *ch[0];
+            const TNode& R = *ch[1];
             float4* f = &nodes[4 * (size_t)it.fat];
             // component order of rt_device.cuh (x / y planes paired per box, z planes of both boxes together)
             f[0] = f4(L.aabb_min[0], L.aabb_min[1], L.aabb_max[0], L.aabb_max[1]);
@@ -448,13 +458,15 @@ static bool build_grid(const rt_grid_desc* gp, const rt_blas_desc& b, std::vecto
     return true;
 }
 
+// allocates max(bytes, total) and copies the `bytes` the host laid out to its start (the rest is filled on the device)
 template <class T>
-static rt_status upload(T** dst, const void* src, size_t bytes)
+static rt_status upload(T** dst, const void* src, size_t bytes, size_t total = 0)
 {
     *dst = nullptr;
-    if (bytes == 0) bytes = 16; // keep pointers valid
-    RT_CUDA(cudaMalloc((void**)dst, bytes));
-    if (src) RT_CUDA(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+    if (total < bytes) total = bytes;
+    if (total == 0) total = 16; // keep pointers valid
+    RT_CUDA(cudaMalloc((void**)dst, total));
+    if (src && bytes) RT_CUDA(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
     return RT_OK;
 }
 
@@ -480,7 +492,10 @@ rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags,
     *out = nullptr;
     if (desc->blas_count == 0 || !desc->blas) { set_error("rt_scene_create: no BLAS"); return RT_ERR_INVALID; }
     if (desc->kind == RT_SCENE_FLAT && desc->blas_count != 1) { set_error("rt_scene_create: a flat scene has exactly one BVH"); return RT_ERR_INVALID; }
-    if (desc->kind == RT_SCENE_TLAS && (!desc->tlas_nodes || desc->tlas_node_count == 0)) { set_error("rt_scene_create: TLAS scene without TLAS nodes"); return RT_ERR_INVALID; }
+    // RT_SCENE_TLAS: reference-format nodes, 32-bit nodes (ABI v5), or neither = TLASBVH::Build on the device
+    const bool tlas32 = desc->kind == RT_SCENE_TLAS && !desc->tlas_nodes && desc->tlas_nodes32;
+    const bool tlasOnDevice = desc->kind == RT_SCENE_TLAS && !desc->tlas_nodes && !desc->tlas_nodes32;
+    if (desc->kind == RT_SCENE_TLAS && ((desc->tlas_nodes && desc->tlas_node_count == 0) || (tlas32 && desc->tlas_node32_count == 0))) { set_error("rt_scene_create: TLAS scene without TLAS nodes"); return RT_ERR_INVALID; }
     const bool alt = desc->kind == RT_SCENE_FLAT_KDTREE || desc->kind == RT_SCENE_FLAT_GRID;
     const bool tlasAlt = desc->kind == RT_SCENE_TLAS_KDTREE || desc->kind == RT_SCENE_TLAS_GRID;
     const bool anyTlas = desc->kind == RT_SCENE_TLAS || tlasAlt;
@@ -490,6 +505,7 @@ rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags,
     if (tlasAlt && (!desc->tlas_nodes || desc->tlas_node_count == 0)) { set_error("rt_scene_create: TLAS scene without TLAS nodes"); return RT_ERR_INVALID; }
     if (rt_device_count() <= device || device < 0) { set_error("rt_scene_create: no such CUDA device (there is no CPU fallback)"); return RT_ERR_NO_DEVICE; }
 
+    RT_CUDA(cudaSetDevice(device));
     Builder B;
     int maxBlasDepth = 0, tlasDepth = 0;
     std::vector<float4> kdNodes, gridParams;
@@ -497,6 +513,13 @@ rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags,
     std::vector<int> rootRefs(desc->blas_count);
     std::vector<int> triBase(desc->blas_count);
     std::vector<uint32_t> firstOfGeometry; // distinct meshes seen so far (bounded: scenes share a handful)
+    // BVH kinds: the distinct meshes (rt_scene_refit works per mesh), the mesh of every BLAS, and the meshes whose BVH is
+    // built on the device (blas.nodes == NULL): their fat nodes / records are appended after everything the host lays out
+    std::vector<Geometry> geoms;
+    std::vector<int> blasGeom(desc->blas_count, -1);
+    std::vector<float> rootBoxes; // 6 floats per mesh: the BVH root's box (SetTransform -> world bounds)
+    struct Pending { uint32_t blas; int geom; DeviceBvh bvh; };
+    struct PendingList { std::vector<Pending> v; ~PendingList() { for (Pending& p : v) p.bvh.release(); } } pending;
     for (uint32_t i = 0; i < desc->blas_count; i++)
     {
         const rt_blas_desc& b = desc->blas[i];
@@ -540,23 +563,37 @@ rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags,
         }
         else
         {
-        if (!b.nodes || !b.tris || !b.tri_indices) { set_error("rt_scene_create: BLAS with null arrays"); return RT_ERR_INVALID; }
+        const bool onDevice = !b.nodes && !b.tri_indices; // ABI v5: SAH build + layout on the device
+        if (!b.tris || b.tri_count == 0 || (!onDevice && (!b.nodes || !b.tri_indices))) { set_error("rt_scene_create: BLAS with null arrays"); return RT_ERR_INVALID; }
         // true instancing: BLAS descriptors that point at the same reference arrays share
         // one device copy of nodes / triangles / shading records; only the 2 x 64-byte instance records differ
         int shared = -1;
         for (uint32_t j : firstOfGeometry)
             if (desc->blas[j].nodes == b.nodes && desc->blas[j].tris == b.tris && desc->blas[j].tri_indices == b.tri_indices &&
-                desc->blas[j].node_count == b.node_count && desc->blas[j].tri_count == b.tri_count) { shared = (int)j; break; }
-        if (shared >= 0) triBase[i] = triBase[shared], rootRefs[i] = rootRefs[shared];
+                (onDevice || desc->blas[j].node_count == b.node_count) && desc->blas[j].tri_count == b.tri_count) { shared = (int)j; break; }
+        if (shared >= 0) blasGeom[i] = blasGeom[shared];
         else
         {
-            triBase[i] = (int)(B.tris.size() / 3);
-            rootRefs[i] = B.add_bvh(b, triBase[i]);
-            if (B.lastDepth > maxBlasDepth) maxBlasDepth = B.lastDepth;
-            if (B.error.empty()) B.add_tris(b);
-            if (!B.error.empty()) { set_error("rt_scene_create: " + B.error); return RT_ERR_INVALID; }
+            Geometry g;
+            g.triCount = b.tri_count;
+            blasGeom[i] = (int)geoms.size();
+            if (onDevice) pending.v.push_back({ i, blasGeom[i], DeviceBvh() });
+            else
+            {
+                g.triBase = (int)(B.tris.size() / 3), g.fatBase = (int)(B.nodes.size() / 4);
+                g.rootRef = B.add_bvh(b, g.triBase);
+                g.fatCount = (int)(B.nodes.size() / 4) - g.fatBase;
+                if (B.lastDepth > maxBlasDepth) maxBlasDepth = B.lastDepth;
+                if (B.error.empty()) B.add_tris(b);
+                if (!B.error.empty()) { set_error("rt_scene_create: " + B.error); return RT_ERR_INVALID; }
+                rootBoxes.resize(6 * geoms.size() + 6);
+                memcpy(&rootBoxes[6 * geoms.size()], b.nodes[0].aabb_min, 12), memcpy(&rootBoxes[6 * geoms.size() + 3], b.nodes[0].aabb_max, 12);
+            }
+            geoms.push_back(g);
+            rootBoxes.resize(6 * geoms.size());
             if (firstOfGeometry.size() < 64) firstOfGeometry.push_back(i);
         }
+        continue; // instance records: below, once the device-built meshes have their places
         }
         const float* M = b.inv_T;
         B.inst.push_back(Builder::f4(M[0], M[1], M[2], M[3]));
@@ -569,16 +606,86 @@ rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags,
         B.inst_shade.push_back(Builder::f4(T[8], T[9], T[10], T[11]));
         B.inst_shade.push_back(Builder::f4(Builder::asf(triBase[i]), 0, 0, 0));
     }
-    int rootRef = rootRefs[0];
-    if (anyTlas)
+    const bool bvhKind = desc->kind == RT_SCENE_FLAT || desc->kind == RT_SCENE_TLAS;
+    // device SAH builds (the arrays stay in device memory until they are laid out below)
+    for (Pending& p : pending.v)
     {
-        rootRef = B.add_tlas(*desc);
+        const rt_blas_desc& b = desc->blas[p.blas];
+        const rt_status bst = build_bvh_on_device(device, b.tris, b.tri_count, p.bvh);
+        if (bst != RT_OK) return bst;
+        if (p.bvh.depth > maxBlasDepth) maxBlasDepth = p.bvh.depth;
+        rt_bvh_node root;
+        RT_CUDA(cudaMemcpy(&root, p.bvh.nodes, sizeof(root), cudaMemcpyDeviceToHost));
+        memcpy(&rootBoxes[6 * (size_t)p.geom], root.aabb_min, 12), memcpy(&rootBoxes[6 * (size_t)p.geom + 3], root.aabb_max, 12);
+    }
+    int rootRef = rootRefs[0];
+    // the TLAS the host brought is laid out by the host (appended to the host part of the node array)
+    if (anyTlas && !tlasOnDevice)
+    {
+        rootRef = tlas32 ? B.add_tlas(desc->tlas_nodes32, desc->tlas_node32_count, desc->blas_count)
+                         : B.add_tlas(desc->tlas_nodes, desc->tlas_node_count, desc->blas_count);
         tlasDepth = B.lastDepth;
         if (!B.error.empty()) { set_error("rt_scene_create: " + B.error); return RT_ERR_INVALID; }
+    }
+    if (anyTlas)
+    {
         if (desc->blas_count > 0x3fffff00u) { set_error("rt_scene_create: more than 2^30 instances"); return RT_ERR_UNSUPPORTED; }
         // GetHitInfo indexes blas[objIdx - 2] (tlas_file_scene.cpp:237): objIdx must be i + 2
         for (uint32_t i = 0; i < desc->blas_count; i++)
             if (desc->blas[i].obj_idx != (int)i + 2) { set_error("rt_scene_create: TLAS scenes need blas[i].obj_idx == i + 2"); return RT_ERR_INVALID; }
+    }
+    // places of the device-built meshes: after the host part, in BLAS order
+    const size_t hostFat = B.nodes.size() / 4, hostTris = B.tris.size() / 3;
+    size_t totalFat = hostFat, totalTris = hostTris;
+    for (Pending& p : pending.v)
+    {
+        Geometry& g = geoms[p.geom];
+        g.fatBase = (int)totalFat, g.fatCount = (int)((p.bvh.total - 1) / 2), g.triBase = (int)totalTris;
+        g.rootRef = p.bvh.total == 1 ? ~g.triBase : g.fatBase; // a mesh of <= 2 triangles is a single leaf
+        totalFat += (size_t)g.fatCount, totalTris += g.triCount;
+    }
+    const int tlasFatBase = tlasOnDevice ? (int)totalFat : (anyTlas && rootRef >= 0 ? rootRef : 0);
+    const int tlasFatCount = anyTlas ? (int)desc->blas_count - 1 : 0;
+    if (tlasOnDevice) totalFat += (size_t)tlasFatCount;
+    if (totalFat >= 0x7fffff00u || totalTris >= 0x3fffff00u) { set_error("rt_scene_create: scene too large for 32-bit references"); return RT_ERR_UNSUPPORTED; }
+    // TLASBVH::Build on the device: world bounds per instance (SetTransform), then the clustering; laid out after the allocation
+    struct TlasBuild { rt_tlas_node32* nodes = nullptr; float* bounds = nullptr; int* depth = nullptr; ~TlasBuild() { cudaFree(nodes), cudaFree(bounds), cudaFree(depth); } } tb;
+    if (tlasOnDevice)
+    {
+        const uint32_t n = desc->blas_count;
+        std::vector<float> wb(6 * (size_t)n);
+        for (uint32_t i = 0; i < n; i++)
+        {
+            const float* r = &rootBoxes[6 * (size_t)blasGeom[i]];
+            world_bounds_of(r, r + 3, desc->blas[i].T, &wb[6 * (size_t)i]);
+        }
+        RT_CUDA(cudaMalloc((void**)&tb.bounds, (size_t)n * 24));
+        RT_CUDA(cudaMalloc((void**)&tb.nodes, 2 * (size_t)n * sizeof(rt_tlas_node32)));
+        RT_CUDA(cudaMalloc((void**)&tb.depth, 4));
+        RT_CUDA(cudaMemcpy(tb.bounds, wb.data(), (size_t)n * 24, cudaMemcpyHostToDevice));
+        const rt_status tst = build_tlas_on_device(device, tb.bounds, n, tb.nodes, tb.depth, nullptr);
+        if (tst != RT_OK) return tst;
+        RT_CUDA(cudaMemcpy(&tlasDepth, tb.depth, 4, cudaMemcpyDeviceToHost));
+        rootRef = n == 1 ? ~(INSTANCE_BIT | 0) : tlasFatBase;
+    }
+    if (bvhKind)
+    {
+        if (!anyTlas) rootRef = geoms[blasGeom[0]].rootRef;
+        for (uint32_t i = 0; i < desc->blas_count; i++)
+        {
+            const rt_blas_desc& b = desc->blas[i];
+            const Geometry& g = geoms[blasGeom[i]];
+            const float* M = b.inv_T;
+            B.inst.push_back(Builder::f4(M[0], M[1], M[2], M[3]));
+            B.inst.push_back(Builder::f4(M[4], M[5], M[6], M[7]));
+            B.inst.push_back(Builder::f4(M[8], M[9], M[10], M[11]));
+            B.inst.push_back(Builder::f4(Builder::asf(g.rootRef), Builder::asf(b.obj_idx), 0, 0));
+            const float* T = b.T;
+            B.inst_shade.push_back(Builder::f4(T[0], T[1], T[2], T[3]));
+            B.inst_shade.push_back(Builder::f4(T[4], T[5], T[6], T[7]));
+            B.inst_shade.push_back(Builder::f4(T[8], T[9], T[10], T[11]));
+            B.inst_shade.push_back(Builder::f4(Builder::asf(g.triBase), 0, 0, 0));
+        }
     }
 
     // The traversal kernels keep the pending far children of ONE ray on one stack: at most one entry per level above the node
@@ -618,17 +725,33 @@ rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags,
     s->stack_entries = stackEntries;
     rt_status st = RT_OK;
     auto fail = [&](rt_status e) { rt_scene_destroy(s); return e; };
-    if ((st = upload(&s->nodes, B.nodes.data(), B.nodes.size() * 16)) != RT_OK) return fail(st);
-    if ((st = upload(&s->tris, B.tris.data(), B.tris.size() * 16)) != RT_OK) return fail(st);
+    if ((st = upload(&s->nodes, B.nodes.data(), B.nodes.size() * 16, totalFat * 64)) != RT_OK) return fail(st);
+    if ((st = upload(&s->tris, B.tris.data(), B.tris.size() * 16, totalTris * 48)) != RT_OK) return fail(st);
     if ((st = upload(&s->inst, B.inst.data(), B.inst.size() * 16)) != RT_OK) return fail(st);
-    if ((st = upload(&s->shade, B.shade.data(), B.shade.size() * 16)) != RT_OK) return fail(st);
+    if ((st = upload(&s->shade, B.shade.data(), B.shade.size() * 16, bvhKind ? totalTris * 64 : 0)) != RT_OK) return fail(st);
+    // device-built meshes and TLAS: reference-layout arrays (still in device memory) -> traversal layout, in place
+    for (Pending& p : pending.v)
+    {
+        const Geometry& g = geoms[p.geom];
+        if ((st = layout_built_bvh(p.bvh, g.fatBase, g.triBase, s->nodes, s->tris, s->shade, nullptr)) != RT_OK) return fail(st);
+        p.bvh.release();
+    }
+    if (tlasOnDevice && (st = layout_built_tlas(tb.nodes, desc->blas_count, tlasFatBase, s->nodes, nullptr)) != RT_OK) return fail(st);
+    if (bvhKind)
+    {
+        s->geometries = geoms, s->blas_geometry = blasGeom;
+        s->tlas_fat_base = tlasFatBase, s->tlas_fat_count = tlasFatCount, s->max_blas_depth = maxBlasDepth;
+        s->blas_T.resize(16 * (size_t)desc->blas_count);
+        for (uint32_t i = 0; i < desc->blas_count; i++) memcpy(&s->blas_T[16 * (size_t)i], desc->blas[i].T, 64);
+    }
     if ((st = upload(&s->inst_shade, B.inst_shade.data(), B.inst_shade.size() * 16)) != RT_OK) return fail(st);
     if ((st = upload(&s->obj_material, desc->obj_material, desc->obj_count * sizeof(int))) != RT_OK) return fail(st);
     if ((st = upload(&s->kd_nodes, kdNodes.data(), kdNodes.size() * 16)) != RT_OK) return fail(st);
     if ((st = upload(&s->grid_cells, gridCells.data(), gridCells.size() * sizeof(int2))) != RT_OK) return fail(st);
     if ((st = upload(&s->grid_params, gridParams.data(), gridParams.size() * 16)) != RT_OK) return fail(st);
-    s->node_count = B.nodes.size() / 4, s->tri_count = B.tris.size() / 3, s->inst_count = desc->blas_count;
-    s->bytes_geometry = (B.nodes.size() + B.tris.size() + B.inst.size() + B.shade.size() + B.inst_shade.size() + kdNodes.size()) * 16 + gridCells.size() * sizeof(int2);
+    s->node_count = totalFat, s->tri_count = totalTris, s->inst_count = desc->blas_count;
+    s->bytes_geometry = (B.inst.size() + B.inst_shade.size() + kdNodes.size()) * 16 + gridCells.size() * sizeof(int2) + totalFat * 64 + totalTris * 48 +
+                        (bvhKind ? totalTris * 64 : B.shade.size() * 16);
     if (desc->kind == RT_SCENE_FLAT_KDTREE || desc->kind == RT_SCENE_TLAS_KDTREE) s->node_count += kdNodes.size() / 2;
     if (desc->kind == RT_SCENE_FLAT_GRID || desc->kind == RT_SCENE_TLAS_GRID) s->node_count += gridCells.size();
 

@@ -381,12 +381,23 @@ void rtb_invert_rigid(const float* M, float* r)
     r[11] = -(M[3] * r[8] + M[7] * r[9] + M[11] * r[10]);
 }
 
+} // extern "C"
+
 // world_bounds: n x 6 floats.  out: 2n entries (node 0 = copy of the root, leaves 1..n in BLAS order).
-int rtb_build_tlas(const float* world_bounds, uint32_t n, rt_tlas_node* out, uint32_t* nodes_used)
+// One clustering loop for both node formats: the reference's TLASBVHNode (children 2 x 16 bit, tlas_bvh.h:10) and the
+// ABI v5 node with 32-bit children (no 32 767-instance cap).
+struct Tlas16 {
+    static void leaf(rt_tlas_node& n, uint32_t blas) { n.blas = blas, n.left_right = 0; }
+    static void join(rt_tlas_node& n, uint32_t a, uint32_t b) { n.left_right = a + (b << 16); }
+};
+struct Tlas32 {
+    static void leaf(rt_tlas_node32& n, uint32_t blas) { n.left = 0, n.right = blas; }
+    static void join(rt_tlas_node32& n, uint32_t a, uint32_t b) { n.left = a, n.right = b; }
+};
+template <class TNode, class F>
+static int build_tlas_any(const float* world_bounds, uint32_t n, TNode* out, uint32_t* nodes_used)
 {
-    if (!world_bounds || !out || n == 0) return RT_ERR_INVALID;
-    if (2 * (uint64_t)n > 65535) return RT_ERR_UNSUPPORTED; // children are packed 2 x 16 bit (tlas_bvh.h:10)
-    memset(out, 0, sizeof(rt_tlas_node) * 2 * (size_t)n);
+    memset(out, 0, sizeof(TNode) * 2 * (size_t)n);
     std::vector<int> nodeIdx(n);
     int nodeIndices = (int)n;
     uint32_t used = 1;
@@ -395,17 +406,17 @@ int rtb_build_tlas(const float* world_bounds, uint32_t n, rt_tlas_node* out, uin
         nodeIdx[i] = (int)used;
         memcpy(out[used].aabb_min, world_bounds + 6 * (size_t)i, 12);
         memcpy(out[used].aabb_max, world_bounds + 6 * (size_t)i + 3, 12);
-        out[used].blas = i, out[used].left_right = 0;
+        F::leaf(out[used], i);
         used++;
     }
     auto best_match = [&](int N, int A) { // FindBestMatch tlas_bvh.cpp:57-70
         float smallest = 1e30f;
         int bestB = -1;
-        const rt_tlas_node& a = out[nodeIdx[A]];
+        const TNode& a = out[nodeIdx[A]];
         for (int B = 0; B < N; B++)
             if (B != A)
             {
-                const rt_tlas_node& b = out[nodeIdx[B]];
+                const TNode& b = out[nodeIdx[B]];
                 const float ex = maxf(a.aabb_max[0], b.aabb_max[0]) - minf(a.aabb_min[0], b.aabb_min[0]);
                 const float ey = maxf(a.aabb_max[1], b.aabb_max[1]) - minf(a.aabb_min[1], b.aabb_min[1]);
                 const float ez = maxf(a.aabb_max[2], b.aabb_max[2]) - minf(a.aabb_min[2], b.aabb_min[2]);
@@ -421,8 +432,8 @@ int rtb_build_tlas(const float* world_bounds, uint32_t n, rt_tlas_node* out, uin
         if (A == Cc)
         {
             const int ia = nodeIdx[A], ib = nodeIdx[B];
-            rt_tlas_node& nn = out[used];
-            nn.left_right = (uint32_t)ia + ((uint32_t)ib << 16);
+            TNode& nn = out[used];
+            F::join(nn, (uint32_t)ia, (uint32_t)ib);
             for (int k = 0; k < 3; k++)
                 nn.aabb_min[k] = minf(out[ia].aabb_min[k], out[ib].aabb_min[k]), nn.aabb_max[k] = maxf(out[ia].aabb_max[k], out[ib].aabb_max[k]);
             nodeIdx[A] = (int)used++;
@@ -434,6 +445,21 @@ int rtb_build_tlas(const float* world_bounds, uint32_t n, rt_tlas_node* out, uin
     out[0] = out[nodeIdx[A]];
     if (nodes_used) *nodes_used = used;
     return RT_OK;
+}
+
+extern "C" {
+
+int rtb_build_tlas(const float* world_bounds, uint32_t n, rt_tlas_node* out, uint32_t* nodes_used)
+{
+    if (!world_bounds || !out || n == 0) return RT_ERR_INVALID;
+    if (2 * (uint64_t)n > 65535) return RT_ERR_UNSUPPORTED; // children are packed 2 x 16 bit (tlas_bvh.h:10): use rtb_build_tlas32
+    return build_tlas_any<rt_tlas_node, Tlas16>(world_bounds, n, out, nodes_used);
+}
+
+int rtb_build_tlas32(const float* world_bounds, uint32_t n, rt_tlas_node32* out, uint32_t* nodes_used)
+{
+    if (!world_bounds || !out || n == 0) return RT_ERR_INVALID;
+    return build_tlas_any<rt_tlas_node32, Tlas32>(world_bounds, n, out, nodes_used);
 }
 
 } // extern "C"

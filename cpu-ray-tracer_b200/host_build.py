@@ -33,6 +33,7 @@ def lib():
         L.rtb_world_bounds.argtypes = [vp, vp, vp, vp]
         L.rtb_invert_rigid.argtypes = [vp, vp]
         L.rtb_build_tlas.argtypes = [vp, C.c_uint32, vp, C.POINTER(C.c_uint32)]
+        L.rtb_build_tlas32.argtypes = [vp, C.c_uint32, vp, C.POINTER(C.c_uint32)]
         u32p = C.POINTER(C.c_uint32)
         L.rtb_kd_build.argtypes, L.rtb_kd_build.restype = [vp, C.c_uint32], vp
         L.rtb_kd_sizes.argtypes, L.rtb_kd_sizes.restype = [vp, u32p, u32p, u32p], None
@@ -184,6 +185,18 @@ def build_tlas(bounds):
     return out[:used.value].copy()
 
 
+def build_tlas32(bounds):
+    """the same clustering with 32-bit children (rt_tlas_node32): no 32 767-instance cap"""
+    bounds = np.ascontiguousarray(bounds, np.float32).reshape(-1, 6)
+    n = len(bounds)
+    out = np.zeros(2 * n, abi.TLAS_NODE32_DTYPE)
+    used = C.c_uint32()
+    rc = lib().rtb_build_tlas32(bounds.ctypes.data, n, out.ctypes.data, C.byref(used))
+    if rc != 0:
+        raise ValueError(f"rtb_build_tlas32 failed: {rc}")
+    return out[:used.value].copy()
+
+
 def make_tris(v0, v1, v2, obj_idx=2, normals=None, uvs=None):
     """Tri records as the reference's loaders fill them (model.cpp:60-79): centroid = (v0 + v1 + v2) * 0.3333f"""
     n = len(v0)
@@ -283,7 +296,7 @@ def terrain_mesh(n_tris, seed=1, size=None, height=0.8):
     return make_tris(v0, v1, v2, obj_idx=2)
 
 
-def instanced_grid(mesh_tris, n_instances, seed=0x12345678, spacing=None, like=None):
+def instanced_grid(mesh_tris, n_instances, seed=0x12345678, spacing=None, like=None, tlas="host"):
     """TLASFileScene equivalent with TRUE instancing: every instance references the same BLAS arrays.
     Rigid transforms: rotation about Y by a xorshift32 angle, translation on a jittered 3-D grid."""
     tris = np.ascontiguousarray(mesh_tris, abi.TRI_DTYPE).copy()
@@ -317,6 +330,16 @@ def instanced_grid(mesh_tris, n_instances, seed=0x12345678, spacing=None, like=N
     tt = np.zeros(1, TEX_TABLE_DTYPE)
     tt[0]["width"], tt[0]["height"] = w, h
     mats = _materials([(0.0, 0.0, (0.8, 0.6, 0.4)), (0.9, 0.0, (0.9, 0.9, 0.9)), (0.1, 0.8, (0.9, 0.95, 1.0))])
-    return FlatScene({"header": _header(abi.RT_SCENE_TLAS, like=like, sky=0), "blas_table": bt, "nodes": nodes, "tris": tris,
-                      "tri_indices": idx, "tlas_nodes": build_tlas(bounds), "obj_material": (np.arange(n_instances) % 3).astype(np.int32),
-                      "materials": mats, "tex_table": tt, "tex_pixels": sky})
+    # tlas: "host" = the reference's node format (<= 32 767 instances), "host32" = 32-bit children, "none" = left to the device
+    chunks = {"header": _header(abi.RT_SCENE_TLAS, like=like, sky=0), "blas_table": bt, "nodes": nodes, "tris": tris,
+              "tri_indices": idx, "obj_material": (np.arange(n_instances) % 3).astype(np.int32),
+              "materials": mats, "tex_table": tt, "tex_pixels": sky}
+    if tlas == "host":
+        chunks["tlas_nodes"] = build_tlas(bounds)
+    elif tlas == "host32":
+        chunks["tlas_nodes32"] = build_tlas32(bounds)
+    fs = FlatScene(chunks)
+    fs.instance_bounds = bounds
+    if tlas == "none":
+        fs.device_tlas = True
+    return fs

@@ -9,6 +9,7 @@ constructors ran (file_scene.cpp:4-62, tlas_file_scene.cpp:4-93), in the referen
     tris         Tri[]       (112 B, helper.h:6-26)
     tri_indices  uint[]      (per-BLAS local indices)
     tlas_nodes   TLASBVHNode[] (32 B, tlas_bvh.h:7-14)      TLAS scenes only
+    tlas_nodes32 rt_tlas_node32[] (32 B)                    TLAS scenes with more than 32 767 instances: 32-bit children
     obj_material int[]       material index of object (objIdx - 2)
     materials    rt_material[]
     tex_table    per texture: offset into tex_pixels, width, height
@@ -48,8 +49,9 @@ _CHUNK_DTYPES = {
     "kd_nodes": abi.KD_NODE_DTYPE, "kd_tri_indices": np.dtype("<u4"),
     "grid_header": abi.GRID_HEADER_DTYPE, "grid_cell_start": np.dtype("<u4"), "grid_tri_indices": np.dtype("<u4"),
     "blas_kd_table": abi.BLAS_KD_TABLE_DTYPE, "blas_grid_table": abi.BLAS_GRID_TABLE_DTYPE,
+    "tlas_nodes32": abi.TLAS_NODE32_DTYPE,
 }
-_OPTIONAL = ("kd_nodes", "kd_tri_indices", "grid_header", "grid_cell_start", "grid_tri_indices", "blas_kd_table", "blas_grid_table")
+_OPTIONAL = ("tlas_nodes32", "kd_nodes", "kd_tri_indices", "grid_header", "grid_cell_start", "grid_tri_indices", "blas_kd_table", "blas_grid_table")
 
 
 class FlatScene:
@@ -69,6 +71,9 @@ class FlatScene:
         for name in _OPTIONAL:
             setattr(self, name, chunks.get(name))
         self._keep = None
+        # ABI v5 construction on the device (not stored in files): desc() then hands over triangles only
+        self.device_build = False   # blas.nodes = blas.tri_indices = NULL: SAH build + layout on the GPU
+        self.device_tlas = False    # tlas_nodes = tlas_nodes32 = NULL: TLASBVH::Build on the GPU
 
     def copy(self):
         """deep copy of the arrays (not of the ctypes tables a previous desc() call left behind)"""
@@ -145,12 +150,19 @@ class FlatScene:
         h = self.header[0]
         nb = len(self.blas_table)
         blas = (abi.rt_blas_desc * nb)()
+        bvh_kind = int(h["kind"]) in (abi.RT_SCENE_FLAT, abi.RT_SCENE_TLAS)
+        on_device = self.device_build and bvh_kind
         for i, b in enumerate(self.blas_table):
-            blas[i].nodes = self.nodes.ctypes.data + int(b["node_offset"]) * 32
-            blas[i].node_count = int(b["node_count"])
-            blas[i].tris = self.tris.ctypes.data + int(b["tri_offset"]) * 112
-            blas[i].tri_indices = self.tri_indices.ctypes.data + int(b["tri_offset"]) * 4
-            blas[i].tri_count = int(b["tri_count"])
+            no, nc, to, tc = int(b["node_offset"]), int(b["node_count"]), int(b["tri_offset"]), int(b["tri_count"])
+            # offsets come from a file: never turn them into pointers unchecked
+            if to + tc > len(self.tris) or (bvh_kind and not on_device and (no + nc > len(self.nodes) or to + tc > len(self.tri_indices))):
+                raise ValueError(f"BLAS {i}: node / triangle range outside the scene's arrays")
+            if not on_device:
+                blas[i].nodes = self.nodes.ctypes.data + no * 32
+                blas[i].node_count = nc
+                blas[i].tri_indices = self.tri_indices.ctypes.data + to * 4
+            blas[i].tris = self.tris.ctypes.data + to * 112
+            blas[i].tri_count = tc
             blas[i].T = abi.f16(*b["T"].tolist())
             blas[i].inv_T = abi.f16(*b["inv_T"].tolist())
             blas[i].obj_idx = int(b["obj_idx"])
@@ -158,14 +170,19 @@ class FlatScene:
         nt = len(self.tex_table)
         tex = (abi.rt_texture * max(nt, 1))()
         for i, t in enumerate(self.tex_table):
+            if int(t["pixel_offset"]) + int(t["width"]) * int(t["height"]) > len(self.tex_pixels) or int(t["width"]) < 0 or int(t["height"]) < 0:
+                raise ValueError(f"texture {i}: texel range outside tex_pixels")
             tex[i].pixels = self.tex_pixels.ctypes.data + int(t["pixel_offset"]) * 4
             tex[i].width, tex[i].height = int(t["width"]), int(t["height"])
         d = abi.rt_scene_desc()
         d.kind = int(h["kind"])
         d.blas = C.cast(blas, C.POINTER(abi.rt_blas_desc))
         d.blas_count = nb
-        d.tlas_nodes = self.tlas_nodes.ctypes.data if len(self.tlas_nodes) else None
-        d.tlas_node_count = len(self.tlas_nodes)
+        if not self.device_tlas:
+            d.tlas_nodes = self.tlas_nodes.ctypes.data if len(self.tlas_nodes) else None
+            d.tlas_node_count = len(self.tlas_nodes)
+            if self.tlas_nodes32 is not None and not len(self.tlas_nodes):
+                d.tlas_nodes32, d.tlas_node32_count = self.tlas_nodes32.ctypes.data, len(self.tlas_nodes32)
         d.obj_material = self.obj_material.ctypes.data
         d.obj_count = len(self.obj_material)
         d.materials = self.materials.ctypes.data

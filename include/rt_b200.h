@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RT_B200_ABI_VERSION 4
+#define RT_B200_ABI_VERSION 5
 
 typedef int rt_status;
 enum {
@@ -65,11 +65,25 @@ typedef struct rt_tlas_node {
     uint32_t blas;
 } rt_tlas_node;
 
+/* The same node with 32-bit child indices (ABI v5): the reference packs both children into one 32-bit word, which caps a
+ * scene at 32 767 instances (tlas_bvh.h:10; its builder also keeps `int nodeIdx[256]`, tlas_bvh.cpp:21 - README "known
+ * issues").  left == 0 => leaf holding BLAS `right`; else children are nodes[left] and nodes[right].  Node 0 = root.
+ * Produced by rt_build_tlas; accepted by rt_scene_create through rt_scene_desc.tlas_nodes32. */
+typedef struct rt_tlas_node32 {
+    float aabb_min[3];
+    uint32_t left;
+    float aabb_max[3];
+    uint32_t right;
+} rt_tlas_node32;
+
 /* One bottom-level BVH: BVH (infra/bvh.h:38-41, FileScene::acc) or BLASBVH (infra/blas_bvh.h:44-53).
  * T / inv_T are row-major mat4::cell arrays (identity for the flat FileScene BVH).
  * obj_idx: the BLAS' objIdx written into hits (blas_bvh.cpp:299); -1 for the flat BVH, where the hit
  * takes tri.obj_idx instead (bvh.cpp:220). */
 typedef struct rt_blas_desc {
+    /* nodes == NULL && tri_indices == NULL (ABI v5): the BVH is built ON THE DEVICE from `tris` (rt_build_bvh's builder:
+     * the reference's binned SAH, bit-identical arrays) and laid out for traversal there, without a round trip through
+     * host memory; node_count is ignored.  Descriptors with the same `tris` pointer and tri_count share one build. */
     const rt_bvh_node* nodes;
     uint32_t node_count;            /* nodesUsed */
     const rt_tri* tris;
@@ -180,6 +194,12 @@ typedef struct rt_scene_desc {
     /* RT_SCENE_TLAS_KDTREE / RT_SCENE_TLAS_GRID: blas_count entries, parallel to blas[] (which then carries tris /
      * tri_count / T / inv_T / obj_idx / mat_idx; nodes and tri_indices are ignored) */
     const rt_blas_accel* blas_accel;
+    /* ABI v5, RT_SCENE_TLAS: a TLAS with 32-bit child indices (more than 32 767 instances); used instead of tlas_nodes
+     * when not NULL.  With tlas_nodes == NULL and tlas_nodes32 == NULL the TLAS is built ON THE DEVICE: world bounds of
+     * every instance as BLASBVH::SetTransform computes them (blas_bvh.cpp:369-373), then the reference's agglomerative
+     * clustering (TLASBVH::Build, tlas_bvh.cpp:17-70) - the same tree, node for node, without the 256 / 32 767 caps. */
+    const rt_tlas_node32* tlas_nodes32;
+    uint32_t tlas_node32_count;
 } rt_scene_desc;
 
 /* ---- rays and hits (Ray, template/ray.h:6-41, as plain records) ------------------------------ */
@@ -388,6 +408,30 @@ rt_status rt_renderer_get_queue_history(rt_renderer* r, int32_t* rays_per_iterat
  * device_ms (optional) receives the kernel time without the host<->device copies. */
 rt_status rt_build_bvh(int device, const rt_tri* tris, uint32_t n, rt_bvh_node* nodes_out, uint32_t* tri_indices_out,
                        uint32_t* nodes_used, double* device_ms);
+
+/* TLASBVH::Build (tlas_bvh.cpp:17-70: agglomerative clustering, FindBestMatch = smallest surface area of the union,
+ * first candidate wins ties) on the GPU.  world_bounds: n x 6 floats (min.xyz, max.xyz per instance, BLAS order); out: 2n
+ * entries in the reference's node order (node 0 = copy of the root, leaves 1..n, merged nodes in creation order) with
+ * 32-bit children.  The tree is the reference's, node for node; n is bounded by memory only.  Host buffers. */
+rt_status rt_build_tlas(int device, const float* world_bounds, uint32_t n, rt_tlas_node32* out, uint32_t* nodes_used, double* device_ms);
+
+/* BVH::Refit / BLASBVH::Refit (bvh.cpp:26-43 = blas_bvh.cpp:104-121) for the mesh of BLAS `blas_index` after its triangles
+ * moved: `tris` (host, tri_count entries, the mesh's own triangle order) replaces positions, normals and uvs; topology
+ * (tree, triangleIndices) is kept, every leaf box is recomputed from its triangles (UpdateNodeBounds) and every interior box
+ * from its children, bottom up, on the device.  Instances that share the mesh all see the change.
+ * flags: 0 reproduces the reference exactly, including its skipped node: the loop `for (i = nodesUsed - 1; i >= 0; i--)
+ * if (i != 1)` never updates node 1, the root's LEFT child (nodesUsed starts at 1 here, bvh.h:41), whose box stays stale.
+ * RT_REFIT_ALL_NODES also updates node 1.  RT_REFIT_REBUILD_TLAS (TLAS scenes): afterwards recompute the world bounds of
+ * every instance (SetTransform, blas_bvh.cpp:369-373) and rebuild the TLAS on the device (TLASBVH::Build); without it
+ * the TLAS keeps its boxes, as in the reference, where nothing calls SetTransform again.
+ * Renderers of the scene must be idle (rt_renderer_sync) while this runs.  BVH kinds only (RT_SCENE_FLAT / RT_SCENE_TLAS). */
+enum { RT_REFIT_ALL_NODES = 1, RT_REFIT_REBUILD_TLAS = 2 };
+rt_status rt_scene_refit(rt_scene* scene, uint32_t blas_index, const rt_tri* tris, uint32_t tri_count, uint32_t flags);
+
+/* Reads the traversal layout of one mesh back as reference-layout arrays (parity tests of the device build / refit):
+ * nodes_out 2 * tri_count - 1 entries, tri_indices_out tri_count entries.  Node boxes, numbering and triangle order are
+ * those of BVH::Build; the root's own box is not stored on the device and is returned as the union of its children. */
+rt_status rt_scene_download_bvh(rt_scene* scene, uint32_t blas_index, rt_bvh_node* nodes_out, uint32_t* tri_indices_out, uint32_t* nodes_used);
 
 /* ---- diagnostics ------------------------------------------------------------------------------ */
 

@@ -45,6 +45,7 @@ class PortOracle:
         L.orc_to_rgb8.argtypes = [vp, C.c_size_t, C.c_float, vp]
         L.orc_camera_default.argtypes = [vp, C.c_int, C.c_int]
         L.orc_camera_look_at.argtypes = [vp, vp, vp, C.c_int, C.c_int]
+        L.orc_refit_bvh.argtypes = [vp, C.c_uint32, vp, vp, C.c_int]
         assert L.orc_sizeof_stats() == 8 * len(STATS_FIELDS)
 
     @staticmethod
@@ -108,6 +109,17 @@ class PortOracle:
         out = np.zeros(acc.shape[:-1], np.uint32)
         self.lib.orc_to_rgb8(acc.ctypes.data, out.size, scale, out.ctypes.data)
         return out
+
+
+def refit_bvh(nodes, tris, tri_indices, all_nodes=False):
+    """BVH::Refit (bvh.cpp:26-43) restated (orc_refit_bvh): returns the refitted copy of `nodes`"""
+    L = C.CDLL(build())
+    L.orc_refit_bvh.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
+    out = np.array(nodes, abi.NODE_DTYPE, copy=True)
+    tris = np.ascontiguousarray(tris, abi.TRI_DTYPE)
+    idx = np.ascontiguousarray(tri_indices, np.uint32)
+    L.orc_refit_bvh(out.ctypes.data, len(out), tris.ctypes.data, idx.ctypes.data, 1 if all_nodes else 0)
+    return out
 
 
 def default_params(integrator, w, h, seed_mode=abi.RT_SEED_REFERENCE_TILE, depth_limit=5, passes=1):

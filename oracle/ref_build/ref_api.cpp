@@ -443,6 +443,35 @@ int ref_flatten( const char* out_path )
 	return 0;
 }
 
+// Moves the vertices of one acceleration structure's triangles (v9: 9 floats per triangle, the structure's own triangle
+// order) and calls the reference's own Refit() on it (bvh.cpp:26-43 / blas_bvh.cpp:104-121).  BVH builds only.
+// A following ref_flatten dumps the refitted nodes: that is what pins oracle/rt_oracle.c orc_refit_bvh.
+int ref_refit( int blas, int n, const float* v9 )
+{
+#if defined(REF_SCENE_FILE) && !defined(USE_KDTree) && !defined(USE_Grid)
+	auto& acc = g_renderer->scene.acc;
+	(void)blas;
+#elif !defined(REF_SCENE_FILE) && !defined(TLAS_USE_KDTree) && !defined(TLAS_USE_Grid)
+	if (blas < 0 || blas >= (int)g_renderer->scene.tlas.blas.size()) return -1;
+	auto& acc = *g_renderer->scene.tlas.blas[blas];
+#endif
+#if (defined(REF_SCENE_FILE) && !defined(USE_KDTree) && !defined(USE_Grid)) || (!defined(REF_SCENE_FILE) && !defined(TLAS_USE_KDTree) && !defined(TLAS_USE_Grid))
+	if (n != (int)acc.triangles.size()) return -1;
+	for (int i = 0; i < n; i++)
+	{
+		const float* v = v9 + 9 * (size_t)i;
+		acc.triangles[i].vertex0 = float3( v[0], v[1], v[2] );
+		acc.triangles[i].vertex1 = float3( v[3], v[4], v[5] );
+		acc.triangles[i].vertex2 = float3( v[6], v[7], v[8] );
+	}
+	acc.Refit();
+	return 0;
+#else
+	(void)blas, (void)n, (void)v9;
+	return -2;
+#endif
+}
+
 int ref_sizeof_tri() { return (int)sizeof( Tri ); }
 int ref_sizeof_node() { return (int)sizeof( BVHNode ); }
 

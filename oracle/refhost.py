@@ -52,6 +52,7 @@ class RefRenderer:
         L.ref_set_depth_limit.argtypes = [C.c_int]
         L.ref_energy.restype = C.c_float
         L.ref_flatten.argtypes = [C.c_char_p]
+        L.ref_refit.argtypes = [C.c_int, C.c_int, f32p]
         self.width, self.height = width, height
         # scene files are addressed the way the reference does: "../assets/scenes/x.xml" from work/run
         if not scene_xml.startswith("../") and not os.path.isabs(scene_xml):
@@ -134,6 +135,13 @@ class RefRenderer:
         n = self.width * self.height
         return np.ctypeslib.as_array(self.lib.ref_screen(), (n,)).reshape(self.height, self.width).copy()
 
+    def refit(self, blas, verts9):
+        """overwrite the triangle vertices of one acceleration structure and call the reference's Refit() on it"""
+        v = np.ascontiguousarray(verts9, np.float32).reshape(-1, 9)
+        rc = self.lib.ref_refit(blas, len(v), v)
+        if rc != 0:
+            raise RuntimeError(f"ref_refit failed: {rc}")
+
     def flatten(self, path):
         rc = self.lib.ref_flatten(os.path.abspath(path).encode())
         if rc != 0:
@@ -177,6 +185,13 @@ def _main(argv):
             secs += r.tick(frames)
         print(json.dumps({"seconds": secs, "threads": r.threads(), "frames": frames, "fast": fast,
                           "flags": "reference Renderer::Tick built headless with g++ " + ("-O3 -mavx2 -mfma -ffast-math" if fast else "-O2 -fopenmp -ffp-contract=off")}))
+    elif cmd == "refit_flatten":
+        # refit_flatten <integrator> <kind> <scene.xml> <verts.npy: (n, 9) float32> <blas> <out.rtscene>
+        integrator, kind, scene, verts, blas, out = argv[1], argv[2], argv[3], argv[4], int(argv[5]), os.path.abspath(argv[6])
+        v = np.load(os.path.abspath(verts))
+        r = RefRenderer(integrator, kind, scene, 64, 64)
+        r.refit(blas, v)
+        r.flatten(out)
     elif cmd == "flatten":
         integrator, kind, scene, out = argv[1], argv[2], argv[3], os.path.abspath(argv[4])
         r = RefRenderer(integrator, kind, scene, 64, 64)

@@ -120,3 +120,18 @@ def random_rays(flat, n, seed):
     nrm = np.linalg.norm(D, axis=1, keepdims=True)
     D = (D / np.where(nrm > 0, nrm, 1)).astype(np.float32)
     return api.make_rays(O, D)
+
+
+def displaced(tris, amp, seed):
+    """the same mesh with every vertex moved by a smooth deterministic field (topology kept): what an animated model hands to
+    Refit.  numpy fp32, only used as test INPUT (the golden refit vectors store the moved vertices themselves)."""
+    rng = np.random.default_rng(seed)
+    t = np.array(tris, copy=True)
+    for v in ("v0", "v1", "v2"):
+        t[v] = (t[v] + (amp * np.sin(7.0 * t[v][:, ::-1] + rng.uniform(0, 6.28, 3))).astype(np.float32)).astype(np.float32)
+    t["centroid"] = ((t["v0"] + t["v1"] + t["v2"]) * np.float32(0.3333)).astype(np.float32)
+    return t
+
+
+def verts9(tris):
+    return np.concatenate([tris["v0"], tris["v1"], tris["v2"]], 1).astype(np.float32)

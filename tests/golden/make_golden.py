@@ -13,6 +13,9 @@ FileScene+USE_KDTree as shipped / FileScene+USE_Grid / TLASFileScene+TLAS_USE_KD
       info_N / info_uv / info_albedo   GetHitInfo + GetAlbedo / GetSkyColor for camera-0 primary hits
       whitted<c>       Whitted accumulator (Renderer::Tick once)
       pt<c>            path-tracer accumulator after FRAMES Ticks from spp = 1
+`make_golden.py refit` writes tests/golden/golden_refit.npz: for the `file` and `tlas` scenes, the moved vertices handed to the
+reference's own BVH::Refit / BLASBVH::Refit (bvh.cpp:26-43, through oracle/ref_build/ref_api.cpp ref_refit) and the node
+array it left behind (file_verts / file_nodes; tlas_blas, tlas_verts / tlas_nodes): pins oracle orc_refit_bvh.
 The scene (scenes/golden_scene.xml) uses tiny generated textures so the fixtures stay small.
 """
 import os
@@ -28,7 +31,37 @@ W, H, FRAMES = 128, 80, 3
 LOOK_AT = ((1.6, 0.9, -1.4), (0.0, -0.4, 1.0))
 
 
+def refit_golden():
+    """the reference's Refit on moved vertices; one subprocess per scene class (the reference keeps global state)"""
+    import subprocess
+    import tempfile
+    import cpu_ray_tracer_b200 as rtb
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import displaced, verts9
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for kind in ("file", "tlas"):
+            fs = rtb.FlatScene.load(os.path.join(HERE, f"golden_{kind}.rtscene.gz"))
+            blas = int(np.argmax(fs.blas_table["tri_count"]))
+            b = fs.blas_table[blas]
+            to, tc = int(b["tri_offset"]), int(b["tri_count"])
+            v = verts9(displaced(fs.tris[to:to + tc], 0.04, seed=11))
+            np.save(os.path.join(tmp, "v.npy"), v)
+            dst = os.path.join(tmp, f"{kind}.rtscene")
+            subprocess.run([sys.executable, "-m", "oracle.refhost", "refit_flatten", "pt", kind, "golden_scene.xml",
+                            os.path.join(tmp, "v.npy"), str(blas), dst], check=True, cwd=ROOT)
+            ref = rtb.FlatScene.load(dst)
+            rb = ref.blas_table[blas]
+            no, nc = int(rb["node_offset"]), int(rb["node_count"])
+            assert np.array_equal(ref.tri_indices, fs.tri_indices) and nc == int(b["node_count"])
+            out[f"{kind}_blas"], out[f"{kind}_verts"], out[f"{kind}_nodes"] = np.int32(blas), v, ref.nodes[no:no + nc]
+            print("refit", kind, "blas", blas, "nodes", nc)
+    np.savez_compressed(os.path.join(HERE, "golden_refit.npz"), **out)
+
+
 def main():
+    if sys.argv[1:] == ["refit"]:
+        return refit_golden()
     from oracle.refhost import RefRenderer
     import cpu_ray_tracer_b200 as rtb
     from cpu_ray_tracer_b200 import api

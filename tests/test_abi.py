@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared_functions():
         assert hasattr(L, name), f"librt_b200.so does not export {name}"
     assert set(api.EXPORTS) == set(declared_functions())
-    assert L.rt_abi_version() == 4
+    assert L.rt_abi_version() == 5
 
 
 def test_struct_sizes_match_header(tmp_path):

@@ -210,3 +210,54 @@ def test_with_accelerator_on_tlas_scenes(accel, kind, flat_scenes):
     W, H = 64, 40
     hits, st = po.find_nearest(po.primary_rays(po.camera_default(W, H), W, H))
     assert (hits["obj_idx"] >= 2).any() and st["blas_entries"] > 0
+
+
+# ---- ABI v5: 32-bit TLAS nodes, Refit restatement ---------------------------------------------------------------------
+def test_tlas32_builder_is_the_same_clustering():
+    """rtb_build_tlas32 (no 32 767-instance cap) builds the tree of rtb_build_tlas, and the oracle walks both alike"""
+    from cpu_ray_tracer_b200 import host_build
+    from oracle import porthost
+    mesh = host_build.terrain_mesh(300, seed=4, size=0.8, height=0.5)
+    a = host_build.instanced_grid(mesh, 150, tlas="host")
+    b = host_build.instanced_grid(mesh, 150, tlas="host32")
+    inner = a.tlas_nodes["left_right"] != 0
+    assert np.array_equal(a.tlas_nodes["left_right"][inner] & 0xffff, b.tlas_nodes32["left"][inner])
+    assert np.array_equal(a.tlas_nodes["left_right"][inner] >> 16, b.tlas_nodes32["right"][inner])
+    assert np.array_equal(a.tlas_nodes["blas"][~inner], b.tlas_nodes32["right"][~inner])
+    assert np.array_equal(a.tlas_nodes["aabb_min"].view(np.uint32), b.tlas_nodes32["aabb_min"].view(np.uint32))
+    pa, pb = porthost.PortOracle(a), porthost.PortOracle(b)
+    rays = pa.primary_rays(pa.camera_default(160, 96), 160, 96)
+    ha, sa = pa.find_nearest(rays)
+    hb, sb = pb.find_nearest(rays)
+    assert ha.tobytes() == hb.tobytes() and sa == sb and sa["blas_entries"] > 0
+
+
+def test_refit_restatement_properties():
+    """orc_refit_bvh (BVH::Refit, bvh.cpp:26-43): refitting unmoved triangles reproduces the builder's boxes; after a move every
+    leaf box is the bounds of its triangles, every interior box the union of its children - except node 1, which the reference's
+    loop skips (`if (i != 1)`), unless the repaired variant is asked for"""
+    from cpu_ray_tracer_b200 import host_build
+    from oracle import porthost
+    tris = host_build.terrain_mesh(5000, seed=2)
+    nodes, idx, _ = host_build.build_bvh(tris)
+    same = porthost.refit_bvh(nodes, tris, idx)
+    assert same.tobytes() == nodes.tobytes()
+    moved = np.array(tris, copy=True)
+    for v in ("v0", "v1", "v2"):
+        moved[v] = (moved[v] * np.float32(1.25) + np.float32(0.1)).astype(np.float32)
+    for all_nodes in (False, True):
+        out = porthost.refit_bvh(nodes, moved, idx, all_nodes=all_nodes)
+        assert np.array_equal(out["left_first"], nodes["left_first"]) and np.array_equal(out["tri_count"], nodes["tri_count"])
+        for i in range(len(out)):
+            if i == 1 and not all_nodes:
+                assert out[1].tobytes() == nodes[1].tobytes()       # stale: the reference never refits it
+                continue
+            n = out[i]
+            if n["tri_count"] > 0:
+                t = moved[idx[n["left_first"]:n["left_first"] + n["tri_count"]]]
+                v = np.concatenate([t["v0"], t["v1"], t["v2"]])
+                assert np.array_equal(n["aabb_min"], v.min(0)) and np.array_equal(n["aabb_max"], v.max(0))
+            else:
+                l, r = out[n["left_first"]], out[n["left_first"] + 1]
+                assert np.array_equal(n["aabb_min"], np.minimum(l["aabb_min"], r["aabb_min"]))
+                assert np.array_equal(n["aabb_max"], np.maximum(l["aabb_max"], r["aabb_max"]))

@@ -81,6 +81,27 @@ def test_oracle_pt_frame_split_is_exact(oracles):
     assert biteq(a, b)
 
 
+@pytest.mark.parametrize("kind", ["file", "tlas"])
+def test_oracle_refit_vs_golden(flat_scenes, kind):
+    """orc_refit_bvh == what the reference's own BVH::Refit / BLASBVH::Refit left behind on the same moved vertices
+    (tests/golden/golden_refit.npz, written by make_golden.py refit through ref_api.cpp ref_refit), node 1 stale included"""
+    from oracle import porthost
+    g = np.load(os.path.join(GOLDEN, "golden_refit.npz"))
+    fs = flat_scenes(f"golden_{kind}")
+    blas = int(g[f"{kind}_blas"])
+    b = fs.blas_table[blas]
+    no, nc, to, tc = int(b["node_offset"]), int(b["node_count"]), int(b["tri_offset"]), int(b["tri_count"])
+    tris = np.array(fs.tris[to:to + tc], copy=True)
+    v = g[f"{kind}_verts"]
+    tris["v0"], tris["v1"], tris["v2"] = v[:, 0:3], v[:, 3:6], v[:, 6:9]
+    got = porthost.refit_bvh(fs.nodes[no:no + nc], tris, fs.tri_indices[to:to + tc])
+    want = g[f"{kind}_nodes"]
+    assert got.tobytes() == want.tobytes()
+    assert got[1].tobytes() == fs.nodes[no + 1].tobytes() and got[2].tobytes() != fs.nodes[no + 2].tobytes()  # bvh.cpp:28 skips node 1
+    fixed = porthost.refit_bvh(fs.nodes[no:no + nc], tris, fs.tri_indices[to:to + tc], all_nodes=True)
+    assert fixed[1].tobytes() != got[1].tobytes() and fixed[3:].tobytes() == got[3:].tobytes()
+
+
 # ---- live reference (only where oracle/_ref was built, i.e. where /root/reference is mounted) ----
 def _ref_available():
     from oracle import refhost

@@ -1,5 +1,5 @@
 """Per-source-line hot spots of one kernel from an .ncu-rep captured with --import-source on (-lineinfo build).
-usage: python tools/ncu_source_hot.py report.ncu-rep [top]"""
+usage: python tools/ncu_source_hot.py report.ncu-rep [top [all_lines.csv]]"""
 import csv, subprocess, sys
 def main(rep, top=45):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
@@ -21,5 +21,11 @@ def main(rep, top=45):
     print(f"{'file:line':24s} {'%inst':>6s} {'%smpl':>6s} {'lanes':>5s}  source")
     for a in sorted(agg, key=lambda a: -a[4])[:int(top)]:
         print(f"{a[0][:16]+':'+str(a[1]):24s} {100*a[4]/ti:6.2f} {100*a[3]/ts:6.2f} {a[5]/max(a[4],1):5.1f}  {a[2]}")
+    if len(sys.argv) > 3:
+        # every line, for offline aggregation by phase (tools/ncu_phase_share.py)
+        with open(sys.argv[3], "w") as f:
+            f.write("file,line,samples,warp_inst,thread_inst\n")
+            for a in sorted(agg, key=lambda a: (a[0], a[1])):
+                f.write(f"{a[0]},{a[1]},{a[3]},{a[4]},{a[5]}\n")
 if __name__ == "__main__":
-    main(*sys.argv[1:])
+    main(*sys.argv[1:3])
