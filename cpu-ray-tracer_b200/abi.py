@@ -79,6 +79,11 @@ class rt_counters(C.Structure):
                 ("wavefront_iterations", C.c_uint64), ("kernel_launches", C.c_uint64)]
 
 
+class rt_scene_info(C.Structure):
+    _fields_ = [("fat_nodes", C.c_uint64), ("triangle_slots", C.c_uint64), ("instances", C.c_uint64), ("meshes", C.c_uint64),
+                ("bytes_geometry", C.c_uint64), ("bytes_textures", C.c_uint64), ("stack_entries", C.c_int32), ("max_blas_depth", C.c_int32)]
+
+
 class rt_stage_times(C.Structure):
     _fields_ = [("ms", C.c_double * 5), ("launches", C.c_uint64 * 5)]
 

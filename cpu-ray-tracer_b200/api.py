@@ -38,7 +38,7 @@ EXPORTS = [
     "rt_multi_renderer_set_passes", "rt_multi_renderer_clear", "rt_multi_renderer_render", "rt_multi_renderer_sync",
     "rt_multi_renderer_read_accumulator", "rt_multi_renderer_read_pixels", "rt_multi_renderer_get_counters",
     "rt_multi_renderer_reset_counters",
-    "rt_build_tlas", "rt_scene_refit", "rt_scene_download_bvh",
+    "rt_build_tlas", "rt_scene_refit", "rt_scene_download_bvh", "rt_scene_get_info", "rt_scene_validate",
 ]
 
 
@@ -117,6 +117,8 @@ def lib():
     L.rt_build_tlas.argtypes = [i32, vp, C.c_uint32, vp, C.POINTER(C.c_uint32), C.POINTER(C.c_double)]
     L.rt_scene_refit.argtypes = [vp, C.c_uint32, vp, C.c_uint32, C.c_uint32]
     L.rt_scene_download_bvh.argtypes = [vp, C.c_uint32, vp, vp, C.POINTER(C.c_uint32)]
+    L.rt_scene_get_info.argtypes = [vp, C.POINTER(abi.rt_scene_info)]
+    L.rt_scene_validate.argtypes = [vp]
     _lib = L
     return L
 
@@ -256,6 +258,16 @@ class GpuScene:
 
     def GetTriangleCount(self):
         return self.flat.triangle_count
+
+    def info(self):
+        """what the scene occupies on the device (rt_scene_get_info): meshes < instances = shared geometry"""
+        i = abi.rt_scene_info()
+        _check(lib().rt_scene_get_info(self.handle, C.byref(i)))
+        return {k: int(getattr(i, k)) for k, _ in abi.rt_scene_info._fields_}
+
+    def validate(self):
+        """rt_scene_validate: structural check of the traversal data read back from device memory (raises RtError)"""
+        _check(lib().rt_scene_validate(self.handle))
 
     # -- scene construction steps on the device (SURVEY 8f rank 1) -----------------------------------
     def Refit(self, blas_index, tris, all_nodes=False, rebuild_tlas=False):

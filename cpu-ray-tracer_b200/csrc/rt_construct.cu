@@ -8,6 +8,7 @@
 // Arithmetic: min / max by comparison-select exactly as the reference's float3 fminf / fmaxf (tmplmath.h:122-123, 256-257),
 // surface areas with the reference's operation order; compiled with -fmad=false like the rest of the library.
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include "rt_internal.h"
@@ -501,6 +502,115 @@ rt_status rt_scene_refit(rt_scene* s, uint32_t blas_index, const rt_tri* tris, u
         if ((st = layout_built_tlas(dt, n, s->tlas_fat_base, s->nodes, s->stream)) != RT_OK) return st;
         s->stack_entries = entries;
     }
+    return RT_OK;
+}
+
+rt_status rt_scene_validate(rt_scene* s)
+{
+    if (!s) { set_error("rt_scene_validate: null argument"); return RT_ERR_INVALID; }
+    if (s->d.kind != RT_SCENE_FLAT && s->d.kind != RT_SCENE_TLAS) { set_error("rt_scene_validate: BVH scenes only"); return RT_ERR_UNSUPPORTED; }
+    RT_CUDA(cudaSetDevice(s->device));
+    const size_t nFat = s->node_count, nSlots = s->tri_count, nInst = s->inst_count;
+    std::vector<float4> fat(4 * nFat), recs(3 * nSlots), inst(4 * nInst);
+    if (nFat) RT_CUDA(cudaMemcpy(fat.data(), s->nodes, fat.size() * 16, cudaMemcpyDeviceToHost));
+    if (nSlots) RT_CUDA(cudaMemcpy(recs.data(), s->tris, recs.size() * 16, cudaMemcpyDeviceToHost));
+    if (nInst) RT_CUDA(cudaMemcpy(inst.data(), s->inst, inst.size() * 16, cudaMemcpyDeviceToHost));
+    auto asi = [](float f) { int i; memcpy(&i, &f, 4); return i; };
+    auto bad = [&](const std::string& what) { set_error("rt_scene_validate: " + what); return RT_ERR_INVALID; };
+    // mesh of every triangle slot (tags index the mesh's own shading records)
+    std::vector<int> meshOfSlot(nSlots, -1);
+    for (size_t gi = 0; gi < s->geometries.size(); gi++)
+    {
+        const Geometry& g = s->geometries[gi];
+        if ((size_t)g.triBase + g.triCount > nSlots || (size_t)g.fatBase + g.fatCount > nFat) return bad("mesh " + std::to_string(gi) + " lies outside the device arrays");
+        for (uint32_t j = 0; j < g.triCount; j++)
+        {
+            if (meshOfSlot[g.triBase + j] != -1) return bad("meshes overlap in the triangle array");
+            meshOfSlot[g.triBase + j] = (int)gi;
+            const uint32_t triIdx = (uint32_t)(asi(recs[3 * (size_t)(g.triBase + j)].w) & ~LAST_BIT);
+            if (triIdx >= g.triCount) return bad("triangle tag " + std::to_string(triIdx) + " outside its mesh (" + std::to_string(g.triCount) + " triangles)");
+        }
+        if (g.triCount && !(asi(recs[3 * (size_t)(g.triBase + g.triCount - 1)].w) & LAST_BIT)) return bad("the last triangle of mesh " + std::to_string(gi) + " does not end a leaf");
+    }
+    std::vector<uint8_t> seen(nFat, 0);
+    // depth-first walk of one tree: returns its depth in levels (a single leaf = 1), -1 on a violation (error set)
+    auto walk = [&](int rootRef, bool tlasLevel, int lo, int hi, const char* what) -> int {
+        struct Item { int ref; int depth; };
+        std::vector<Item> todo;
+        todo.push_back({ rootRef, 1 });
+        int depth = 0;
+        while (!todo.empty())
+        {
+            const Item it = todo.back();
+            todo.pop_back();
+            if (it.depth > depth) depth = it.depth;
+            if (it.ref >= 0)
+            {
+                if (it.ref < lo || it.ref >= hi) { bad(std::string(what) + ": node reference " + std::to_string(it.ref) + " outside [" + std::to_string(lo) + ", " + std::to_string(hi) + ")"); return -1; }
+                if (seen[it.ref]) { bad(std::string(what) + ": node " + std::to_string(it.ref) + " is reached twice (not a tree)"); return -1; }
+                seen[it.ref] = 1;
+                todo.push_back({ asi(fat[4 * (size_t)it.ref + 3].x), it.depth + 1 });
+                todo.push_back({ asi(fat[4 * (size_t)it.ref + 3].y), it.depth + 1 });
+                continue;
+            }
+            const int payload = ~it.ref;
+            if (payload == SENTINEL_PAYLOAD) { bad(std::string(what) + ": the stack marker appears as a child"); return -1; }
+            if (tlasLevel)
+            {
+                if (!(payload & INSTANCE_BIT) || (size_t)(payload & ~INSTANCE_BIT) >= nInst) { bad(std::string(what) + ": TLAS leaf without a valid instance"); return -1; }
+            }
+            else
+            {
+                if ((payload & INSTANCE_BIT) || (size_t)payload >= nSlots) { bad(std::string(what) + ": leaf slot " + std::to_string(payload) + " outside the triangle array"); return -1; }
+                size_t j = (size_t)payload;
+                const int mesh = meshOfSlot[j];
+                while (!(asi(recs[3 * j].w) & LAST_BIT))
+                    if (++j >= nSlots || meshOfSlot[j] != mesh) { bad(std::string(what) + ": a leaf's triangle run does not end inside its mesh"); return -1; }
+            }
+        }
+        return depth;
+    };
+    int maxBlas = 0;
+    for (size_t gi = 0; gi < s->geometries.size(); gi++)
+    {
+        const Geometry& g = s->geometries[gi];
+        const int d = walk(g.rootRef, false, g.fatBase, g.fatBase + g.fatCount, "mesh BVH");
+        if (d < 0) return RT_ERR_INVALID;
+        if (d > maxBlas) maxBlas = d;
+        for (int f = g.fatBase; f < g.fatBase + g.fatCount; f++)
+            if (!seen[f]) return bad("mesh " + std::to_string(gi) + ": fat node " + std::to_string(f) + " is unreachable");
+    }
+    int entries = maxBlas > 0 ? maxBlas - 1 : 0;
+    if (s->d.kind == RT_SCENE_TLAS)
+    {
+        for (size_t i = 0; i < nInst; i++)
+        {
+            const int root = asi(inst[4 * i + 3].x);
+            const Geometry& g = s->geometries[s->blas_geometry[i]];
+            if (root != g.rootRef) return bad("instance " + std::to_string(i) + " does not point at the root of its mesh");
+        }
+        const int d = walk(s->d.root_ref, true, s->tlas_fat_base, s->tlas_fat_base + s->tlas_fat_count, "TLAS");
+        if (d < 0) return RT_ERR_INVALID;
+        std::vector<uint8_t> used(nInst, 0);
+        for (int f = s->tlas_fat_base; f < s->tlas_fat_base + s->tlas_fat_count; f++)
+        {
+            if (!seen[f]) return bad("TLAS fat node " + std::to_string(f) + " is unreachable");
+            for (int k = 0; k < 2; k++)
+            {
+                const int ref = asi(k ? fat[4 * (size_t)f + 3].y : fat[4 * (size_t)f + 3].x);
+                if (ref < 0)
+                {
+                    uint8_t& u = used[~ref & ~INSTANCE_BIT];
+                    if (u) return bad("an instance hangs under two TLAS leaves");
+                    u = 1;
+                }
+            }
+        }
+        entries = (d - 1) + 1 + (maxBlas > 0 ? maxBlas - 1 : 0);
+    }
+    else if (s->d.root_ref != s->geometries[s->blas_geometry[0]].rootRef) return bad("the scene root is not the root of its BVH");
+    if (entries > STACK_SIZE) return bad("a ray can have " + std::to_string(entries) + " entries pending: more than the traversal stack holds");
+    if (entries > s->stack_entries) return bad("the trees are deeper (" + std::to_string(entries) + " pending entries) than the scene recorded (" + std::to_string(s->stack_entries) + "): the stream kernel sizes its stack from that");
     return RT_OK;
 }
 

@@ -76,7 +76,7 @@ struct rt_scene {
     rtb::DMaterial* materials = nullptr;
     rtb::DTexture* textures = nullptr;
     uint32_t* tex_pixels = nullptr;
-    size_t node_count = 0, tri_count = 0, inst_count = 0;
+    size_t node_count = 0, tri_count = 0, inst_count = 0, mesh_count = 0;
     // renderers created on this scene: rt_scene_destroy while some exist only marks the scene, the last rt_renderer_destroy frees it
     std::atomic<int> renderers{0};
     std::atomic<bool> destroy_requested{false};
@@ -100,5 +100,10 @@ struct rt_scene {
     int* fetch_counters = nullptr;
     std::atomic<unsigned> fetch_next{0};
     bool persistent = true, voted = false;
+    // north_star (b) "L2-resident top levels": bytes of the L2 set aside for the fat-node array (access-policy window on the
+    // streams that traverse; RT_B200_L2_PERSIST_MB, 0 = off).  Node fetches then keep their lines against the streaming ray /
+    // hit / frame-image traffic; for node arrays larger than the set-aside the window persists that fraction of the lines.
+    size_t l2_persist_bytes = 0;
+    void apply_l2_policy(cudaStream_t stream) const;
     int* next_fetch_counter() { return fetch_counters + (fetch_next.fetch_add(1) % FETCH_RING); }
 };

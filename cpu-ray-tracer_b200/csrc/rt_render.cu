@@ -1327,6 +1327,7 @@ rt_status rt_renderer_create(rt_scene* scene, const rt_render_params* params, rt
     auto fail = [&](rt_status e) { rt_renderer_destroy(r); return e; };
     if (cudaStreamCreateWithFlags(&r->ownStream, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream create failed"); return fail(RT_ERR_CUDA); }
     r->stream = r->ownStream;
+    scene->apply_l2_policy(r->stream); // fat nodes persisting in L2 against the streaming frame images (RT_B200_L2_PERSIST_MB)
     const size_t px = (size_t)params->width * params->height;
     if ((st = ralloc(r, &r->ownAccum, px * 16)) != RT_OK) return fail(st);
     r->accum = r->ownAccum;

@@ -8,6 +8,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <tuple>
 
 #include "rt_internal.h"
 
@@ -175,6 +177,26 @@ __global__ void __launch_bounds__(256) k_stream_l2(const float4* __restrict__ da
     }
     if (acc == 123.456f) *sink = acc; // keep the loads alive
 }
+
+} // namespace rtb
+
+void rt_scene::apply_l2_policy(cudaStream_t stream) const
+{
+    if (l2_persist_bytes == 0 || node_count == 0) return;
+    cudaStreamAttrValue a = {};
+    size_t bytes = node_count * 64;
+    int maxWindow = 0;
+    cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, device);
+    if (maxWindow > 0 && bytes > (size_t)maxWindow) bytes = (size_t)maxWindow;
+    a.accessPolicyWindow.base_ptr = (void*)nodes;
+    a.accessPolicyWindow.num_bytes = bytes;
+    a.accessPolicyWindow.hitRatio = bytes <= l2_persist_bytes ? 1.0f : (float)((double)l2_persist_bytes / (double)bytes);
+    a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &a) != cudaSuccess) cudaGetLastError(); // a hint: never an error
+}
+
+namespace rtb {
 
 static int grid_for(size_t n, int block, int device)
 {
@@ -512,7 +534,9 @@ rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags,
     std::vector<int2> gridCells;
     std::vector<int> rootRefs(desc->blas_count);
     std::vector<int> triBase(desc->blas_count);
-    std::vector<uint32_t> firstOfGeometry; // distinct meshes seen so far (bounded: scenes share a handful)
+    // distinct meshes seen so far, by the identity of the arrays a descriptor points at -> first BLAS that brought them
+    typedef std::tuple<const void*, const void*, const void*, uint32_t, uint32_t> MeshKey;
+    std::map<MeshKey, uint32_t> meshOf;
     // BVH kinds: the distinct meshes (rt_scene_refit works per mesh), the mesh of every BLAS, and the meshes whose BVH is
     // built on the device (blas.nodes == NULL): their fat nodes / records are appended after everything the host lays out
     std::vector<Geometry> geoms;
@@ -542,13 +566,10 @@ rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags,
             // descriptors that point at the same arrays share one device copy (true instancing, as for the BVH kind)
             if (!b.tris || b.tri_count == 0) { set_error("rt_scene_create: BLAS without triangles"); return RT_ERR_INVALID; }
             const rt_blas_accel& a = desc->blas_accel[i];
-            int shared = -1;
-            for (uint32_t j : firstOfGeometry)
-            {
-                const rt_blas_accel& o = desc->blas_accel[j];
-                if (desc->blas[j].tris == b.tris && desc->blas[j].tri_count == b.tri_count &&
-                    (desc->kind == RT_SCENE_TLAS_KDTREE ? (o.kd_nodes == a.kd_nodes && o.kd_tri_indices == a.kd_tri_indices) : (o.grid == a.grid))) { shared = (int)j; break; }
-            }
+            const MeshKey key = desc->kind == RT_SCENE_TLAS_KDTREE ? MeshKey{ b.tris, a.kd_nodes, a.kd_tri_indices, a.kd_node_count, b.tri_count }
+                                                                   : MeshKey{ b.tris, a.grid, nullptr, 0u, b.tri_count };
+            const auto found = meshOf.find(key);
+            const int shared = found == meshOf.end() ? -1 : (int)found->second;
             if (shared >= 0) triBase[i] = triBase[shared], rootRefs[i] = rootRefs[shared];
             else
             {
@@ -558,7 +579,7 @@ rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags,
                                                                    : build_grid(a.grid, b, gridCells, gridParams, B.tris, rootRefs[i], B.error);
                 if (!ok) { set_error("rt_scene_create: " + B.error); return RT_ERR_INVALID; }
                 push_shade_records(B.shade, b);
-                if (firstOfGeometry.size() < 64) firstOfGeometry.push_back(i);
+                meshOf[key] = i;
             }
         }
         else
@@ -567,10 +588,9 @@ rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags,
         if (!b.tris || b.tri_count == 0 || (!onDevice && (!b.nodes || !b.tri_indices))) { set_error("rt_scene_create: BLAS with null arrays"); return RT_ERR_INVALID; }
         // true instancing: BLAS descriptors that point at the same reference arrays share
         // one device copy of nodes / triangles / shading records; only the 2 x 64-byte instance records differ
-        int shared = -1;
-        for (uint32_t j : firstOfGeometry)
-            if (desc->blas[j].nodes == b.nodes && desc->blas[j].tris == b.tris && desc->blas[j].tri_indices == b.tri_indices &&
-                (onDevice || desc->blas[j].node_count == b.node_count) && desc->blas[j].tri_count == b.tri_count) { shared = (int)j; break; }
+        const MeshKey key = { b.tris, b.nodes, b.tri_indices, onDevice ? 0u : b.node_count, b.tri_count };
+        const auto found = meshOf.find(key);
+        const int shared = found == meshOf.end() ? -1 : (int)found->second;
         if (shared >= 0) blasGeom[i] = blasGeom[shared];
         else
         {
@@ -591,7 +611,7 @@ rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags,
             }
             geoms.push_back(g);
             rootBoxes.resize(6 * geoms.size());
-            if (firstOfGeometry.size() < 64) firstOfGeometry.push_back(i);
+            meshOf[key] = i;
         }
         continue; // instance records: below, once the device-built meshes have their places
         }
@@ -750,6 +770,7 @@ rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags,
     if ((st = upload(&s->grid_cells, gridCells.data(), gridCells.size() * sizeof(int2))) != RT_OK) return fail(st);
     if ((st = upload(&s->grid_params, gridParams.data(), gridParams.size() * 16)) != RT_OK) return fail(st);
     s->node_count = totalFat, s->tri_count = totalTris, s->inst_count = desc->blas_count;
+    s->mesh_count = bvhKind ? geoms.size() : (alt ? 1 : meshOf.size());
     s->bytes_geometry = (B.inst.size() + B.inst_shade.size() + kdNodes.size()) * 16 + gridCells.size() * sizeof(int2) + totalFat * 64 + totalTris * 48 +
                         (bvhKind ? totalTris * 64 : B.shade.size() * 16);
     if (desc->kind == RT_SCENE_FLAT_KDTREE || desc->kind == RT_SCENE_TLAS_KDTREE) s->node_count += kdNodes.size() / 2;
@@ -786,6 +807,20 @@ rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags,
     if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream create failed"); return fail(RT_ERR_CUDA); }
     if ((st = upload(&s->fetch_counters, nullptr, rt_scene::FETCH_RING * sizeof(int))) != RT_OK) return fail(st);
     {
+        const char* e = getenv("RT_B200_L2_PERSIST_MB");
+        const long mb = e ? atol(e) : 0;
+        if (mb > 0)
+        {
+            int maxPersist = 0;
+            cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, device);
+            size_t want = (size_t)mb << 20;
+            if (maxPersist > 0 && want > (size_t)maxPersist) want = (size_t)maxPersist;
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) s->l2_persist_bytes = want;
+            else cudaGetLastError();
+            s->apply_l2_policy(s->stream);
+        }
+    }
+    {
         const char* e = getenv("RT_B200_TRAVERSAL");
         s->persistent = !(e && strcmp(e, "simple") == 0);
         s->voted = e && strcmp(e, "voted") == 0; // RT_B200_TRAVERSAL=voted: the queue traversal with the stream kernel's action vote (A/B)
@@ -820,11 +855,22 @@ void rt_scene_destroy(rt_scene* s)
     delete s;
 }
 
+rt_status rt_scene_get_info(const rt_scene* s, rt_scene_info* out)
+{
+    if (!s || !out) { set_error("rt_scene_get_info: null argument"); return RT_ERR_INVALID; }
+    out->fat_nodes = s->node_count, out->triangle_slots = s->tri_count, out->instances = s->inst_count;
+    out->meshes = s->geometries.empty() ? s->mesh_count : s->geometries.size();
+    out->bytes_geometry = s->bytes_geometry, out->bytes_textures = s->bytes_textures;
+    out->stack_entries = s->stack_entries, out->max_blas_depth = s->max_blas_depth;
+    return RT_OK;
+}
+
 rt_status rt_find_nearest_device(rt_scene* s, const rt_ray* d_rays, rt_hit* d_hits, size_t n, void* stream)
 {
     if (!s || (n && (!d_rays || !d_hits))) { set_error("rt_find_nearest_device: null argument"); return RT_ERR_INVALID; }
     if (n == 0) return RT_OK;
     RT_CUDA(cudaSetDevice(s->device));
+    s->apply_l2_policy((cudaStream_t)stream);
     const int grid = grid_for(n, 128, s->device);
     const bool counters = s->flags & RT_SCENE_FLAG_COUNTERS;
     if (s->persistent)
@@ -856,6 +902,7 @@ rt_status rt_is_occluded_device(rt_scene* s, const rt_ray* d_rays, uint8_t* d_ou
     if (!s || (n && (!d_rays || !d_out))) { set_error("rt_is_occluded_device: null argument"); return RT_ERR_INVALID; }
     if (n == 0) return RT_OK;
     RT_CUDA(cudaSetDevice(s->device));
+    s->apply_l2_policy((cudaStream_t)stream);
     const int grid = grid_for(n, 128, s->device);
     if (s->persistent)
     {

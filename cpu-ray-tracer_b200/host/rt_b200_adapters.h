@@ -28,6 +28,7 @@
 // tlas_bvh.h:27 — add an accessor or a friend), to Texture::pixels and, for USE_Grid, to Grid::resolution /
 // cellSize / gridCells (private at grid.h:25-30).
 #pragma once
+#include <cstddef>
 #include <cstdint>
 #include <cstring>
 #include <stdexcept>
@@ -224,23 +225,58 @@ inline void Flatten( Tmpl8::FileScene& scene, FlattenedScene& f )
 #endif
 
 #ifdef TLAS_USE_BVH
-// TLASFileScene: one BLASBVH per <object> (tlas_file_scene.cpp:41-55) under the agglomerative TLAS
-inline void Flatten( Tmpl8::TLASFileScene& scene, FlattenedScene& f )
+// Content hash of one BLASBVH's geometry: vertices / normals / uvs / centroids of every triangle (not Tri::objIdx, which the
+// loader stamps per object, blas_bvh.cpp:64-80), the node array and the index array.
+inline uint64_t MeshHash( const Tmpl8::BLASBVH& b )
+{
+	uint64_t h = 1469598103934665603ull;
+	auto mix = [&]( const void* p, size_t n ) { const unsigned char* c = (const unsigned char*)p; for (size_t i = 0; i < n; i++) h = (h ^ c[i]) * 1099511628211ull; };
+	for (const Tri& t : b.triangles) mix( &t, offsetof( rt_tri, obj_idx ) );
+	mix( b.bvhNodes.data(), (size_t)b.nodesUsed * sizeof( rt_bvh_node ) );
+	mix( b.triangleIndices.data(), b.triangleIndices.size() * sizeof( uint32_t ) );
+	return h;
+}
+inline bool SameMesh( const Tmpl8::BLASBVH& a, const Tmpl8::BLASBVH& b )
+{
+	if (a.nodesUsed != b.nodesUsed || a.triangles.size() != b.triangles.size()) return false;
+	for (size_t i = 0; i < a.triangles.size(); i++)
+		if (memcmp( &a.triangles[i], &b.triangles[i], offsetof( rt_tri, obj_idx ) ) != 0) return false;
+	return memcmp( a.bvhNodes.data(), b.bvhNodes.data(), (size_t)a.nodesUsed * sizeof( rt_bvh_node ) ) == 0 &&
+	       memcmp( a.triangleIndices.data(), b.triangleIndices.data(), a.triangleIndices.size() * sizeof( uint32_t ) ) == 0;
+}
+
+// TLASFileScene: one BLASBVH per <object> (tlas_file_scene.cpp:41-55) under the agglomerative TLAS.
+// True instancing (README "known issues"): the reference loads and builds every <object> separately, also
+// when several use the same OBJ at the same scale.  Objects whose BLAS turned out IDENTICAL (same triangles, nodes, indices:
+// hash, then full compare) are handed over with the arrays of the first of them, and rt_scene_create keeps ONE device copy
+// per distinct array set; the instances differ only in (T, invT, objIdx, matIdx).  Hits are unchanged: in a TLAS scene the
+// hit's objIdx is the BLAS' own (blas_bvh.cpp:297), not the triangle's.
+// deviceTlas: leave TLASBVH::Build to the device (32-bit children: no 32 767-instance cap) instead of taking the host's nodes.
+inline void Flatten( Tmpl8::TLASFileScene& scene, FlattenedScene& f, bool deviceTlas = false )
 {
 	f.desc.kind = RT_SCENE_TLAS;
+	std::vector<std::pair<uint64_t, Tmpl8::BLASBVH*>> distinct;
 	for (Tmpl8::BLASBVH* blas : scene.tlas.blas)
 	{
+		const uint64_t h = MeshHash( *blas );
+		Tmpl8::BLASBVH* src = blas;
+		for (auto& d : distinct)
+			if (d.first == h && SameMesh( *d.second, *blas )) { src = d.second; break; }
+		if (src == blas) distinct.push_back( { h, blas } );
 		rt_blas_desc b = {};
-		b.nodes = (const rt_bvh_node*)blas->bvhNodes.data(), b.node_count = blas->nodesUsed;
-		b.tris = (const rt_tri*)blas->triangles.data(), b.tri_count = (uint32_t)blas->triangles.size();
-		b.tri_indices = (const uint32_t*)blas->triangleIndices.data();
+		b.nodes = (const rt_bvh_node*)src->bvhNodes.data(), b.node_count = src->nodesUsed;
+		b.tris = (const rt_tri*)src->triangles.data(), b.tri_count = (uint32_t)src->triangles.size();
+		b.tri_indices = (const uint32_t*)src->triangleIndices.data();
 		memcpy( b.T, blas->T.cell, 64 ), memcpy( b.inv_T, blas->invT.cell, 64 );
 		b.obj_idx = blas->objIdx, b.mat_idx = blas->matIdx;
 		f.blas.push_back( b );
 		f.objMaterial.push_back( blas->matIdx );
 	}
-	f.desc.tlas_nodes = (const rt_tlas_node*)scene.tlas.tlasNode;
-	f.desc.tlas_node_count = scene.tlas.nodesUsed;
+	if (!deviceTlas)
+	{
+		f.desc.tlas_nodes = (const rt_tlas_node*)scene.tlas.tlasNode;
+		f.desc.tlas_node_count = scene.tlas.nodesUsed;
+	}
 	FlattenCommon( scene, f );
 	FinishDesc( f );
 }
@@ -309,9 +345,8 @@ template <class HostScene> class GpuScene : public Tmpl8::BaseScene
 public:
 	explicit GpuScene( const std::string& filePath, int device = 0 ) : host( filePath )
 	{
-		FlattenedScene f;
-		Flatten( host, f );
-		check( rt_scene_create( &f.desc, device, 0, &dev ), "rt_scene_create" );
+		Flatten( host, flat );
+		check( rt_scene_create( &flat.desc, device, 0, &dev ), "rt_scene_create" );
 	}
 	GpuScene( const GpuScene& ) = delete;
 	GpuScene& operator=( const GpuScene& ) = delete;
@@ -354,9 +389,13 @@ public:
 		check( rt_is_occluded( dev, in.data(), occluded, n ), "rt_is_occluded" );
 	}
 	rt_scene* Handle() const { return dev; }
+	// the tables handed to rt_scene_create (they point into `host`'s containers): a multi-GPU renderer replicates the scene from them
+	const rt_scene_desc& Desc() const { return flat.desc; }
+	rt_scene_info Info() const { rt_scene_info i = {}; check( rt_scene_get_info( dev, &i ), "rt_scene_get_info" ); return i; }
 public:
 	HostScene host;
 private:
+	FlattenedScene flat;
 	static void Pack( const Tmpl8::Ray& r, rt_ray& p )
 	{
 		p.O[0] = r.O.x, p.O[1] = r.O.y, p.O[2] = r.O.z, p.tmax = r.t;
@@ -371,10 +410,15 @@ private:
 template <class HostScene, int INTEGRATOR> class GpuRenderer : public TheApp
 {
 public:
-	explicit GpuRenderer( const std::string& scenePath, int device = 0 ) : scene( scenePath, device ) {}
+	// devices: the GPUs that render.  One device = rt_renderer on it.  Several (path tracer) = rt_multi_renderer: the tile jobs
+	// of Renderer::Tick (3. PathTracer/renderer.cpp:144-168) are dealt to the GPUs, tile k to device k mod n, and every GPU
+	// writes its tiles into ONE accumulator on devices[0] through peer-mapped memory - the image is bit-identical to one GPU's.
+	explicit GpuRenderer( const std::string& scenePath, int device = 0 ) : scene( scenePath, device ), devices( 1, device ) {}
+	GpuRenderer( const std::string& scenePath, const std::vector<int>& gpus ) : scene( scenePath, gpus.empty() ? 0 : gpus[0] ), devices( gpus.empty() ? std::vector<int>( 1, 0 ) : gpus ) {}
 	~GpuRenderer()
 	{
 		if (dev) rt_renderer_destroy( dev );
+		if (multi) rt_multi_renderer_destroy( multi );
 		if (accumulator) FREE64( accumulator );
 	}
 	// Renderer::Init (renderer.cpp:8-13)
@@ -387,35 +431,31 @@ public:
 		p.depth_limit = depthLimit, p.epsilon = EPSILON;
 		// one Tick per frame is how the reference runs: render `lookahead` frames per launch, reveal one per Tick
 		p.lookahead_frames = INTEGRATOR == RT_INTEGRATOR_PATH ? lookahead : 0;
-		check( rt_renderer_create( scene.Handle(), &p, &dev ), "rt_renderer_create" );
+		if (INTEGRATOR == RT_INTEGRATOR_PATH && devices.size() > 1)
+			check( rt_multi_renderer_create( &scene.Desc(), 0, devices.data(), (int)devices.size(), &p, &multi ), "rt_multi_renderer_create" );
+		else check( rt_renderer_create( scene.Handle(), &p, &dev ), "rt_renderer_create" );
 		createdDepthLimit = depthLimit;
 	}
 	// Renderer::ClearAccumulator (3. PathTracer/renderer.cpp:15-18)
 	void ClearAccumulator()
 	{
 		memset( accumulator, 0, (size_t)SCRWIDTH * SCRHEIGHT * 16 );
-		check( rt_renderer_clear( dev ), "rt_renderer_clear" );
+		check( multi ? rt_multi_renderer_clear( multi ) : rt_renderer_clear( dev ), "rt_renderer_clear" );
 	}
 	// Renderer::Tick (3. PathTracer/renderer.cpp:144-168, 2. WhittedStyle/renderer.cpp:131-190)
 	void Tick( float deltaTime ) override
 	{
 		if (depthLimit != createdDepthLimit) // the UI may change depthLimit between frames
 		{
-			rt_renderer_destroy( dev ), dev = nullptr;
+			if (dev) rt_renderer_destroy( dev ), dev = nullptr;
+			if (multi) rt_multi_renderer_destroy( multi ), multi = nullptr;
 			FREE64( accumulator );
 			Init();
 		}
-		// the UI's "spp" slider changes `passes` between frames (renderer.cpp:182): samples per pixel per Tick
-		if (INTEGRATOR == RT_INTEGRATOR_PATH) check( rt_renderer_set_passes( dev, passes ), "rt_renderer_set_passes" );
 		if (animating) scene.SetTime( anim_time += deltaTime * 0.002f ), ClearAccumulator();
-		rt_camera c;
-		Store( c.pos, camera.camPos ), Store( c.top_left, camera.topLeft );
-		Store( c.top_right, camera.topRight ), Store( c.bottom_left, camera.bottomLeft );
-		check( rt_renderer_set_camera( dev, &c ), "rt_renderer_set_camera" );
-		check( rt_renderer_render( dev, spp, 1, passes ), "rt_renderer_render" );
-		check( rt_renderer_read_accumulator( dev, (float*)accumulator ), "rt_renderer_read_accumulator" );
+		Submit( 1 );
 		const float scale = INTEGRATOR == RT_INTEGRATOR_PATH ? 1.0f / (spp + passes) : 1.0f; // renderer.cpp:119
-		if (screen) check( rt_renderer_read_pixels( dev, scale, (uint32_t*)screen->pixels ), "rt_renderer_read_pixels" );
+		if (screen) check( multi ? rt_multi_renderer_read_pixels( multi, scale, (uint32_t*)screen->pixels ) : rt_renderer_read_pixels( dev, scale, (uint32_t*)screen->pixels ), "rt_renderer_read_pixels" );
 		if (INTEGRATOR == RT_INTEGRATOR_PATH)
 		{
 			if (camera.HandleInput( deltaTime )) ClearAccumulator();
@@ -423,19 +463,15 @@ public:
 		}
 		else camera.HandleInput( deltaTime );
 	}
-	// `frames` Ticks in one call: all (tile, frame) RNG streams are in flight together on the GPU
+	// `frames` Ticks in one call: all (tile, frame) RNG streams are in flight together on the GPU(s)
 	void Render( int frames )
 	{
-		rt_camera c;
-		Store( c.pos, camera.camPos ), Store( c.top_left, camera.topLeft );
-		Store( c.top_right, camera.topRight ), Store( c.bottom_left, camera.bottomLeft );
-		check( rt_renderer_set_camera( dev, &c ), "rt_renderer_set_camera" );
-		if (INTEGRATOR == RT_INTEGRATOR_PATH) check( rt_renderer_set_passes( dev, passes ), "rt_renderer_set_passes" );
-		check( rt_renderer_render( dev, spp, frames, passes ), "rt_renderer_render" );
-		check( rt_renderer_read_accumulator( dev, (float*)accumulator ), "rt_renderer_read_accumulator" );
+		Submit( frames );
 		if (INTEGRATOR == RT_INTEGRATOR_PATH) spp += frames * passes;
 	}
 	rt_renderer* Handle() const { return dev; }
+	rt_multi_renderer* MultiHandle() const { return multi; }
+	int DeviceCount() const { return (int)devices.size(); }
 	// data members, as in the reference's Renderer
 	int2 mousePos;
 	float4* accumulator = nullptr;
@@ -448,7 +484,29 @@ public:
 	int lookahead = 32; // frames rendered ahead of the Tick sequence (set before Init; 0 = off)
 private:
 	static void Store( float* p, const float3& v ) { p[0] = v.x, p[1] = v.y, p[2] = v.z; }
+	// camera + passes + `frames` frames from spp + accumulator back to the host copy the reference's callers read
+	void Submit( int frames )
+	{
+		rt_camera c;
+		Store( c.pos, camera.camPos ), Store( c.top_left, camera.topLeft );
+		Store( c.top_right, camera.topRight ), Store( c.bottom_left, camera.bottomLeft );
+		if (multi)
+		{
+			// the UI's "spp" slider changes `passes` between frames (renderer.cpp:182): samples per pixel per Tick
+			check( rt_multi_renderer_set_passes( multi, passes ), "rt_multi_renderer_set_passes" );
+			check( rt_multi_renderer_set_camera( multi, &c ), "rt_multi_renderer_set_camera" );
+			check( rt_multi_renderer_render( multi, spp, frames, passes ), "rt_multi_renderer_render" );
+			check( rt_multi_renderer_read_accumulator( multi, (float*)accumulator ), "rt_multi_renderer_read_accumulator" );
+			return;
+		}
+		if (INTEGRATOR == RT_INTEGRATOR_PATH) check( rt_renderer_set_passes( dev, passes ), "rt_renderer_set_passes" );
+		check( rt_renderer_set_camera( dev, &c ), "rt_renderer_set_camera" );
+		check( rt_renderer_render( dev, spp, frames, passes ), "rt_renderer_render" );
+		check( rt_renderer_read_accumulator( dev, (float*)accumulator ), "rt_renderer_read_accumulator" );
+	}
+	std::vector<int> devices;
 	rt_renderer* dev = nullptr;
+	rt_multi_renderer* multi = nullptr;
 	int createdDepthLimit = -1;
 };
 

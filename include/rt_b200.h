@@ -236,6 +236,28 @@ int rt_device_count(void);
 rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags, rt_scene** out);
 void rt_scene_destroy(rt_scene* scene);
 
+/* What the scene occupies on the device (BaseScene::GetTriangleCount is the reference's only such query, base_scene.h:31).
+ * meshes < instances means BLAS instances share geometry (true instancing, README "known issues").  ABI v5. */
+typedef struct rt_scene_info {
+    uint64_t fat_nodes;        /* 64-byte interior-node records (BLAS + TLAS) */
+    uint64_t triangle_slots;   /* 48-byte leaf-ordered triangle records */
+    uint64_t instances;        /* BLAS instances (1 for a flat scene) */
+    uint64_t meshes;           /* distinct meshes resident on the device */
+    uint64_t bytes_geometry, bytes_textures;
+    int32_t stack_entries;     /* most pending far children one ray can have (<= 64) */
+    int32_t max_blas_depth;
+} rt_scene_info;
+rt_status rt_scene_get_info(const rt_scene* scene, rt_scene_info* out);
+
+/* Structural check of the traversal data AS IT LIES IN DEVICE MEMORY (read back): every child reference of every fat node is
+ * in range and reached exactly once from its root (a tree), every leaf's triangle run ends inside the triangle array, every
+ * triangle tag indexes a shading record of its own mesh, every instance points at a valid root, and the deepest path keeps
+ * the traversal stack within its 64 entries.  With these invariants no traversal kernel can read outside the scene's
+ * arrays or overflow its stack (the reference's `BVHNode* stack[64]`, bvh.cpp:227, is unchecked).  Meant for tests and for
+ * callers that build or refit on the device; compute-sanitizer is the other tool, where the platform allows it.
+ * BVH kinds (RT_SCENE_FLAT / RT_SCENE_TLAS).  RT_ERR_INVALID + rt_last_error() names the first violation.  ABI v5. */
+rt_status rt_scene_validate(rt_scene* scene);
+
 /* Batched BaseScene::FindNearest (file_scene.cpp:170-175 / tlas_file_scene.cpp:201-206):
  * light quad, floor plane, then the accelerator: BVH (bvh.cpp:224-288), TLAS (tlas_bvh.cpp:83-111), KD-tree
  * (kdtree.cpp:144-210) or grid (grid.cpp:94-161).  Host buffers; H2D + kernel + D2H inside the call. */

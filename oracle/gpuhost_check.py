@@ -1,6 +1,6 @@
 """Drop-in check of the C++ adapters (TEST INFRASTRUCTURE ONLY; run as a subprocess by tests/test_cpp_adapters.py).
 
-    python -m oracle.gpuhost_check <whitted|pt> <file|tlas> <scene.xml> <W> <H> <frames>
+    python -m oracle.gpuhost_check <whitted|pt> <file|tlas> <scene.xml> <W> <H> <frames> [devices, e.g. 0,1]
 
 Loads oracle/_ref/libgpuhost_<integrator>_<kind>.so, which holds BOTH the reference's own Renderer
 (ref_* entry points, CPU) and rtb200::GpuRenderer (gh_* entry points: the reference's loaders and
@@ -27,8 +27,9 @@ def available(integrator, kind):
     return os.path.exists(lib_path(integrator, kind)) and os.path.isdir(os.path.join(refhost.WORK, "assets"))
 
 
-def main(integrator, kind, xml, W, H, frames):
+def main(integrator, kind, xml, W, H, frames, devices=""):
     W, H, frames = int(W), int(H), int(frames)
+    devices = [int(d) for d in devices.split(",") if d != ""]
     L = C.CDLL(lib_path(integrator, kind))
     L.gh_last_error.restype = C.c_char_p
     L.gh_create.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int]
@@ -48,9 +49,19 @@ def main(integrator, kind, xml, W, H, frames):
     run = os.path.join(refhost.WORK, "run").encode()
     if L.ref_create(path, run, W, H) != 0:
         raise SystemExit("ref_create failed")
-    if L.gh_create(path, run, W, H, 0) != 0:
+    if len(devices) > 1:
+        # GpuRenderer over several GPUs of this process (tile jobs dealt to the devices, one peer-mapped accumulator)
+        L.gh_create_multi.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]
+        rc = L.gh_create_multi(path, run, W, H, (C.c_int * len(devices))(*devices), len(devices))
+    else:
+        rc = L.gh_create(path, run, W, H, devices[0] if devices else 0)
+    if rc != 0:
         raise SystemExit("gh_create failed: " + L.gh_last_error().decode())
     out = {"triangles": L.gh_triangle_count()}
+    info = (C.c_ulonglong * 6)()
+    if L.gh_scene_info(info) != 0:
+        raise SystemExit(L.gh_last_error().decode())
+    out["scene_info"] = dict(zip(("instances", "meshes", "fat_nodes", "triangle_slots", "bytes_geometry", "multi_devices"), (int(x) for x in info)))
     n = W * H
     res = {}
     for cam in (None, ((1.6, 0.9, -1.4), (0.0, -0.4, 1.0))):
@@ -117,4 +128,4 @@ def main(integrator, kind, xml, W, H, frames):
 
 
 if __name__ == "__main__":
-    main(*sys.argv[1:7])
+    main(*sys.argv[1:8])

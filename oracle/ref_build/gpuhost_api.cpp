@@ -40,7 +40,39 @@ int gh_create( const char* scene_xml, const char* workdir, int width, int height
 	}
 }
 
+// the same on several GPUs of this process (path tracer: rt_multi_renderer behind GpuRenderer::Tick)
+int gh_create_multi( const char* scene_xml, const char* workdir, int width, int height, const int* devices, int n )
+{
+	try
+	{
+		if (workdir && workdir[0] && chdir( workdir ) != 0) return -2;
+		g_ref_scrwidth = width, g_ref_scrheight = height;
+		g_gh = new GhRenderer( scene_xml, std::vector<int>( devices, devices + n ) );
+		g_gh->screen = new Surface( width, height );
+		g_gh->Init();
+		return 0;
+	}
+	catch (const std::exception& e)
+	{
+		g_gh_error = e.what();
+		return -1;
+	}
+}
+
 void gh_destroy() { delete g_gh; g_gh = nullptr; }
+
+// out: instances, meshes resident on the device, fat nodes, triangle slots, geometry bytes, devices rendering
+int gh_scene_info( unsigned long long* out )
+{
+	try
+	{
+		const rt_scene_info i = g_gh->scene.Info();
+		out[0] = i.instances, out[1] = i.meshes, out[2] = i.fat_nodes, out[3] = i.triangle_slots, out[4] = i.bytes_geometry;
+		out[5] = (unsigned long long)g_gh->DeviceCount() * (g_gh->MultiHandle() ? 1 : 0);
+		return 0;
+	}
+	catch (const std::exception& e) { g_gh_error = e.what(); return -1; }
+}
 
 void gh_set_camera( const float* pos, const float* target )
 {

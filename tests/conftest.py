@@ -72,6 +72,8 @@ def gpu_scenes(flat_scenes):
         key = (name, counters)
         if key not in cache:
             cache[key] = api.open_scene(flat_scenes(name), counters=counters)
+            if flat_scenes(name).kind in (0, 1):
+                cache[key].validate()   # every reference in the device arrays in range, trees, stack depth (rt_scene_validate)
         return cache[key]
     yield get
     for s in cache.values():

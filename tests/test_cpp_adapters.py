@@ -61,3 +61,32 @@ def test_cpp_adapter_matches_reference(integ, kind, xml):
             assert t["rmse"] < 2e-3, (tag, t)
         # screen->pixels (RGBF32_to_RGB8 of accumulator * scale): at most one 8-bit step apart
         assert t["screen_max_channel_diff"] <= 1 or t["screen_pixels_differing"] <= 4, (tag, t)
+    info = r["scene_info"]
+    if xml == "instanced_scene.xml" and kind == "tlas":
+        # true instancing from the XML: the reference builds one BLASBVH per <object>; the adapter hands identical ones over once
+        # (2 x watch-tower and 4 x log_fence at equal scale -> 6 meshes for 10 instances)
+        assert info["instances"] == 10 and info["meshes"] < info["instances"], info
+
+
+@pytest.mark.gpu
+def test_cpp_adapter_tick_on_all_gpus_of_the_box():
+    """rtb200::GpuRenderer constructed with a device list: Renderer::Tick's tile jobs are dealt to the GPUs (rt_multi_renderer),
+    the accumulator the reference's callers read is the same image"""
+    from cpu_ray_tracer_b200 import api
+    from oracle import gpuhost_check
+    if not gpuhost_check.available("pt", "tlas"):
+        pytest.skip("oracle/_ref/libgpuhost_* not built (needs /root/reference at build time)")
+    n = api.device_count()
+    if n < 2:
+        pytest.skip("one GPU on this box: the device-list form is covered by tests/test_gpu_multi.py through the C-ABI")
+    W, H, frames = 192, 112, 2
+    outs = []
+    for devices in ("0", ",".join(str(d) for d in range(n))):
+        p = subprocess.run([sys.executable, "-m", "oracle.gpuhost_check", "pt", "tlas", "inside_scene.xml", str(W), str(H), str(frames), devices],
+                           cwd=ROOT, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:] + p.stdout[-500:]
+        outs.append(json.loads(p.stdout.strip().splitlines()[-1]))
+    one, many = outs
+    assert many["scene_info"]["multi_devices"] == n and one["scene_info"]["multi_devices"] == 0
+    for tag in one["tick"]:
+        assert one["tick"][tag] == many["tick"][tag], (tag, one["tick"][tag], many["tick"][tag])   # same statistics against the reference, digit for digit

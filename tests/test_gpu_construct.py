@@ -39,6 +39,9 @@ def test_device_built_scene_equals_host_built(name, flat_scenes, oracles):
     from oracle import porthost
     flat, po = flat_scenes(name), oracles(name)
     sc = api.open_scene(device_built(flat, tlas=flat.kind == abi.RT_SCENE_TLAS), counters=True)
+    sc.validate()
+    info = sc.info()
+    assert info["instances"] == len(flat.blas_table) and info["triangle_slots"] == len(flat.tris) and info["stack_entries"] <= 64
     for i, b in enumerate(flat.blas_table):
         no, nc, to, tc = int(b["node_offset"]), int(b["node_count"]), int(b["tri_offset"]), int(b["tri_count"])
         nodes, idx = sc.download_bvh(i)
@@ -77,6 +80,8 @@ def test_device_built_large_mesh_and_instancing():
     sc.close()
     inst = host_build.instanced_grid(host_build.terrain_mesh(1200, seed=9, size=0.8, height=0.5), 343)
     sc = api.open_scene(device_built(inst, tlas=True), counters=True)
+    sc.validate()
+    assert sc.info()["meshes"] == 1 and sc.info()["instances"] == 343 and sc.info()["triangle_slots"] == len(inst.tris)
     po = porthost.PortOracle(inst)
     rays = po.primary_rays(po.camera_default(320, 192), 320, 192)
     ref, st = po.find_nearest(rays)
@@ -131,6 +136,7 @@ def test_more_instances_than_the_reference_can_hold():
     dev.device_build, dev.device_tlas, dev.tlas_nodes32 = True, True, None
     for flat, what in ((host, "32-bit TLAS from the host"), (dev, "mesh + TLAS built on the device")):
         sc = api.open_scene(flat, counters=True)
+        sc.validate()
         assert_hits_equal(sc.FindNearest(rays), ref, f"{n} instances, {what}")
         sc.close()
 
@@ -146,6 +152,7 @@ def test_refit_equals_the_reference_refit(name, all_nodes, flat_scenes):
     no, nc, to, tc = int(b["node_offset"]), int(b["node_count"]), int(b["tri_offset"]), int(b["tri_count"])
     new = displaced(flat.tris[to:to + tc], 0.04, seed=11)
     sc.Refit(blas, new, all_nodes=all_nodes)
+    sc.validate()
     want = porthost.refit_bvh(flat.nodes[no:no + nc], new, flat.tri_indices[to:to + tc], all_nodes=all_nodes)
     got, idx = sc.download_bvh(blas)
     nodes_equal(got, want, f"{name} refit")
@@ -179,6 +186,7 @@ def test_refit_with_tlas_rebuild():
     sc = api.open_scene(flat, counters=True)
     new = displaced(flat.tris, 0.15, seed=2)
     sc.Refit(0, new, rebuild_tlas=True)
+    sc.validate()
     nodes = porthost.refit_bvh(flat.nodes, new, flat.tri_indices)
     bounds = np.stack([host_build.world_bounds(nodes[0]["aabb_min"], nodes[0]["aabb_max"], b["T"]) for b in flat.blas_table])
     flat.tris[:], flat.nodes[:] = new, nodes
