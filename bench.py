@@ -248,6 +248,8 @@ def alt_build_line(args, tag="cudamath"):
         env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
         env["RT_B200_LIB"] = alt
         outp = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=120, env=env)
+        if outp.returncode != 0 or not outp.stdout.strip():
+            return {"value": None, "note": f"child run failed (rc {outp.returncode}): {outp.stderr.strip()[-300:]}"}
         res = json.loads(outp.stdout.strip().splitlines()[-1])
         return {"value": res["value"], "unit": "Mrays/s", "ms_per_step": res["ms_per_step"], "library": res["library"],
                 "what": "CUDA's expf / atan2f / acosf (radiance within the tolerance of tests/test_gpu_parity.py instead of bit-identical)"}

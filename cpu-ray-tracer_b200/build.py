@@ -106,3 +106,5 @@ if __name__ == "__main__":
     else:
         extra = ["-Xptxas", "-v"] if "-v" in sys.argv else []
         print(build(force=True, verbose=True, extra=extra))
+        if "--no-variants" not in sys.argv:
+            print(build_variants(verbose=True))  # a stale variant lacks newer exports and cannot be loaded
