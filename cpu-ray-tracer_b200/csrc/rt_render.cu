@@ -42,7 +42,11 @@ struct PTState {
     int* history;      // queued rays per iteration of the current batch
     int iteration;
     float4* accum;
-    float4* frameBuf;  // optional: one W x H float4 image per frame of the launch (look-ahead mode), else nullptr
+    float4* frameBuf;  // optional: one float4 image per sample of the launch (ordered accumulation / look-ahead mode), else nullptr
+    // layout of an image in frameBuf: 0 = W x H pixels; 1 = compact, only the job's own tiles: (k-th tile of the job) * 256 + pixel of the
+    // tile (k_pt_streams8 + k_sum_frames: a tile shard of N ranks needs 1 / N of the memory, and a tile's samples are contiguous)
+    int frameCompact;
+    float invTileStep; // 1 / tileStep (exact tile -> k for the job's tiles: the quotient is an integer below 2^22)
     int slots, nTiles, tilesX, tileBegin, tileStep; // the job's k-th tile is tileBegin + k * tileStep
     int firstSpp, stride;
     int W, H, depthLimit, seedMode;
@@ -1123,8 +1127,8 @@ struct rt_renderer {
     // ordered accumulation: every sample of a launch goes to its own (frame, pass) image, k_sum_frames adds them in order
     bool orderedFrames = true;
     float4* dImages = nullptr;
-    size_t imagesCapacity = 0;            // in images (W x H float4 each)
-    size_t imageBudgetBytes = 4ull << 30; // frames per launch = budget / bytes per frame (RT_B200_IMAGE_BUDGET_MB)
+    size_t imagesCapacity = 0;            // in pixels (float4 each)
+    size_t imageBudgetBytes = 8ull << 30; // frames per launch = budget / bytes per frame (RT_B200_IMAGE_BUDGET_MB)
     // look-ahead (rt_render_params.lookahead_frames): frames rendered ahead of the Tick sequence
     float4* dFrameBuf = nullptr;
     int aheadCapacity = 0, aheadBase = 0, aheadStride = 1, aheadReady = 0;
@@ -1561,13 +1565,15 @@ static rt_status pt_tile_order(rt_renderer* r, const PTState& p)
     return RT_OK;
 }
 
-static rt_status render_pt_streams(rt_renderer* r, int first_spp, int count, int stride, float4* frameBuf = nullptr)
+static rt_status render_pt_streams(rt_renderer* r, int first_spp, int count, int stride, float4* frameBuf = nullptr, bool compactImages = false)
 {
     const rt_render_params& P = r->params;
     const int nTiles = num_tiles(P);
     PTState p = {};
     p.counters = r->dCounters, p.accum = r->accum, p.frameBuf = frameBuf;
+    p.frameCompact = frameBuf && compactImages ? 1 : 0;
     p.nTiles = nTiles, p.tilesX = P.width / 16, p.tileBegin = P.tile_begin, p.tileStep = P.tile_step > 0 ? P.tile_step : 1;
+    p.invTileStep = 1.0f / (float)p.tileStep;
     p.W = P.width, p.H = P.height, p.depthLimit = P.depth_limit, p.seedMode = P.seed_mode, p.eps = P.epsilon, p.passes = r->passes;
     p.stride = stride, p.firstSpp = first_spp;
     // all frames of the call form one pool of nTiles x count streams (x 256 with one stream per pixel; int range checked by the caller)
@@ -1593,6 +1599,7 @@ static rt_status render_pt_streams(rt_renderer* r, int first_spp, int count, int
         long long perWarp = ((long long)p.slots + warps - 1) / warps;
         if (perWarp < 1) perWarp = 1;
         if (perWarp > 32 || !r->streamLaneCap) perWarp = 32;
+        if (const char* e = getenv("RT_B200_STREAM_FORCE_LANES")) { const int v = atoi(e); if (v >= 1 && v <= 32) perWarp = v; } // experiments: streams per warp
         const unsigned laneMask = perWarp >= 32 ? 0xffffffffu : ((1u << perWarp) - 1);
         const Streams5Fn fn = r->streamKernel == 8 ? streams8_kernel(r->scene->d.kind == RT_SCENE_TLAS, r->streamMinB, perPixel, r->streamSmemSlots)
                                                    : streams5_kernel(r->scene->d.kind == RT_SCENE_TLAS, r->streamMinB, perPixel);
@@ -1612,10 +1619,10 @@ static rt_status render_pt_streams(rt_renderer* r, int first_spp, int count, int
 
 // Grows the per-sample image buffer to `images` W x H float4 images; on an allocation failure the request is halved until one
 // frame's images fit (the caller then renders fewer frames per launch).  Returns the number of images available, 0 = none.
-static size_t ensure_images(rt_renderer* r, size_t images, size_t atLeast)
+static size_t ensure_images(rt_renderer* r, size_t images, size_t atLeast, size_t pixelsPerImage = 0)
 {
-    if (images <= r->imagesCapacity) return images;
-    const size_t px = (size_t)r->params.width * r->params.height;
+    const size_t px = pixelsPerImage ? pixelsPerImage : (size_t)r->params.width * r->params.height;
+    if (images * px <= r->imagesCapacity) return images;
     if (r->dImages)
     {
         cudaStreamSynchronize(r->stream);
@@ -1629,7 +1636,7 @@ static size_t ensure_images(rt_renderer* r, size_t images, size_t atLeast)
         void* p = nullptr;
         if (cudaMalloc(&p, images * px * 16) == cudaSuccess)
         {
-            r->dImages = (float4*)p, r->imagesCapacity = images;
+            r->dImages = (float4*)p, r->imagesCapacity = images * px;
             r->allocations.push_back(p);
             return images;
         }
@@ -1649,23 +1656,25 @@ static rt_status render_pt_streams_ordered(rt_renderer* r, int first_spp, int co
     const rt_render_params& P = r->params;
     const bool kernelWritesImages = r->streamKernel == 8 || r->streamKernel == 0 || r->passes == 1; // version 5 indexes images by frame only
     if (!r->orderedFrames || !kernelWritesImages) return render_pt_streams(r, first_spp, count, stride);
-    const size_t px = (size_t)P.width * P.height;
+    const int nTiles = num_tiles(P);
+    // version 8 writes compact images (the job's own tiles only): a tile shard of N ranks holds N times as many frames per launch
+    const bool compact = r->streamKernel == 8;
+    const size_t px = compact ? (size_t)nTiles * 256 : (size_t)P.width * P.height;
     const size_t perFrame = (size_t)r->passes;
     size_t framesPerLaunch = r->imageBudgetBytes / (px * 16 * perFrame);
     if (framesPerLaunch < 1) framesPerLaunch = 1;
     if (framesPerLaunch > (size_t)count) framesPerLaunch = (size_t)count;
-    const size_t got = ensure_images(r, framesPerLaunch * perFrame, perFrame);
+    const size_t got = ensure_images(r, framesPerLaunch * perFrame, perFrame, px);
     if (got == 0) { set_error("rt_renderer_render: no device memory for one frame's sample images"); return RT_ERR_CUDA; }
     framesPerLaunch = got / perFrame;
-    const int nTiles = num_tiles(P);
     for (int done = 0; done < count; done += (int)framesPerLaunch)
     {
         const int frames = count - done < (int)framesPerLaunch ? count - done : (int)framesPerLaunch;
-        rt_status st = render_pt_streams(r, first_spp + done * stride, frames, stride, r->dImages);
+        rt_status st = render_pt_streams(r, first_spp + done * stride, frames, stride, r->dImages, compact);
         if (st != RT_OK) return st;
         r->prof_begin();
         k_sum_frames<<<nTiles < r->sms * 8 ? nTiles : r->sms * 8, 256, 0, r->stream>>>(r->accum, r->dImages, frames * (int)perFrame, P.width, P.height, P.width / 16,
-            P.tile_begin, P.tile_step > 0 ? P.tile_step : 1, nTiles);
+            P.tile_begin, P.tile_step > 0 ? P.tile_step : 1, nTiles, compact ? 1 : 0);
         r->prof_end(RT_STAGE_ACCUMULATE);
         RT_CUDA(cudaGetLastError());
     }
@@ -1708,7 +1717,7 @@ static rt_status render_pt(rt_renderer* r, int first_spp, int count, int stride)
             // (the shard's own tiles only: the accumulator may be shared with other tile shards)
             r->prof_begin();
             k_sum_frames<<<nTiles < r->sms * 8 ? nTiles : r->sms * 8, 256, 0, r->stream>>>(r->accum, r->dFrameBuf + (size_t)k * px, 1, P.width, P.height, P.width / 16,
-                P.tile_begin, P.tile_step > 0 ? P.tile_step : 1, nTiles);
+                P.tile_begin, P.tile_step > 0 ? P.tile_step : 1, nTiles, 0);
             r->prof_end(RT_STAGE_ACCUMULATE);
             RT_CUDA(cudaGetLastError());
             return RT_OK;
@@ -1778,7 +1787,7 @@ static rt_status render_pt(rt_renderer* r, int first_spp, int count, int stride)
         {
             r->prof_begin();
             k_sum_frames<<<nTiles < r->sms * 8 ? nTiles : r->sms * 8, 256, 0, r->stream>>>(r->accum, images, frames * r->passes, P.width, P.height, P.width / 16,
-                P.tile_begin, P.tile_step > 0 ? P.tile_step : 1, nTiles);
+                P.tile_begin, P.tile_step > 0 ? P.tile_step : 1, nTiles, 0);
             r->prof_end(RT_STAGE_ACCUMULATE);
         }
         r->paths += (uint64_t)nTiles * frames * 256 * r->passes;

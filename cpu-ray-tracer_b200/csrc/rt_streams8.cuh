@@ -259,7 +259,13 @@ __global__ void __launch_bounds__(128, MINB) k_pt_streams8(const PTState p, cons
                     int px = pix & 511, pass = (pix >> PIX_PASS_SHIFT) & 15; // `passes` consecutive samples per pixel (renderer.cpp:123)
                     const int frame = pix >> PIX_FRAME_SHIFT;
                     const size_t pixel = (x0 + (px & 15)) + (size_t)(y0 + (px >> 4)) * p.W;
-                    if (p.frameBuf) p.frameBuf[(size_t)(frame * p.passes + pass) * imagePixels + pixel] = make_float4(L.x, L.y, L.z, 0); // the sample's own image
+                    if (p.frameCompact)
+                    {
+                        // the sample's own image, compact layout: (k-th tile of the job) * 256 + pixel of the tile
+                        const int k = __float2int_rn((float)((y0 >> 4) * p.tilesX + (x0 >> 4) - p.tileBegin) * p.invTileStep);
+                        p.frameBuf[((size_t)(frame * p.passes + pass) * p.nTiles + k) * 256 + px] = make_float4(L.x, L.y, L.z, 0);
+                    }
+                    else if (p.frameBuf) p.frameBuf[(size_t)(frame * p.passes + pass) * imagePixels + pixel] = make_float4(L.x, L.y, L.z, 0); // W x H images (look-ahead)
                     else
                     {
                         float* a = (float*)(p.accum + pixel); // renderer.cpp:124, in completion order (callers that asked for no images)
@@ -308,16 +314,17 @@ __global__ void __launch_bounds__(128, MINB) k_pt_streams8(const PTState p, cons
 // channel per sample, frame after frame, pass after pass - the order of the reference's Tick sequence).  One CTA = one 16 x 16 tile.
 // `accum` may live on another GPU (peer-mapped: tile-sharded multi-GPU renders write their tiles straight into rank 0's image).
 __global__ void __launch_bounds__(256) k_sum_frames(float4* __restrict__ accum, const float4* __restrict__ images, const int nImages,
-    const int W, const int H, const int tilesX, const int tileBegin, const int tileStep, const int nTiles)
+    const int W, const int H, const int tilesX, const int tileBegin, const int tileStep, const int nTiles, const int compact)
 {
-    const size_t imagePixels = (size_t)W * H;
+    // image stride and this thread's pixel inside an image: W x H images, or compact ones holding the job's tiles only
+    const size_t imagePixels = compact ? (size_t)nTiles * 256 : (size_t)W * H;
     for (int k = blockIdx.x; k < nTiles; k += gridDim.x)
     {
         const int tile = tileBegin + k * tileStep;
         const int x = (tile % tilesX) * 16 + (threadIdx.x & 15), y = (tile / tilesX) * 16 + (threadIdx.x >> 4);
         const size_t pixel = x + (size_t)y * W;
         float4 a = accum[pixel];
-        const float4* f = images + pixel;
+        const float4* f = images + (compact ? (size_t)k * 256 + threadIdx.x : pixel);
         int i = 0;
         for (; i + 4 <= nImages; i += 4)
         {
