@@ -87,7 +87,7 @@ struct AbiSrc {
 // resident CTAs per SM the closest-hit queue kernel is compiled for (register cap): the scattered 10 M-triangle ray set is bound by
 // memory LATENCY (ncu: long-scoreboard stall 14 cycles per issue, DRAM at 24 % of its peak), so resident warps are what hides it
 #ifndef RT_FN_MINB
-#define RT_FN_MINB 9
+#define RT_FN_MINB 10
 #endif
 template <bool COUNTERS, int ACCEL, bool VOTED>
 __global__ void __launch_bounds__(128, RT_FN_MINB) k_find_nearest_persistent(const DScene s, const rt_ray* rays, rt_hit* hits, int n, int* fetch)

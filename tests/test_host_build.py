@@ -261,3 +261,21 @@ def test_refit_restatement_properties():
                 l, r = out[n["left_first"]], out[n["left_first"] + 1]
                 assert np.array_equal(n["aabb_min"], np.minimum(l["aabb_min"], r["aabb_min"]))
                 assert np.array_equal(n["aabb_max"], np.maximum(l["aabb_max"], r["aabb_max"]))
+
+
+def test_scene_file_offsets_are_checked_before_they_become_pointers(flat_scenes):
+    """a .rtscene whose tables point outside its arrays must not reach the C-ABI as wild pointers (FlatScene.desc)"""
+    for name, field, value in (("golden_file", "tri_count", 10 ** 8), ("golden_tlas", "node_offset", 10 ** 8), ("golden_tlas", "tri_offset", 2 ** 31)):
+        fs = flat_scenes(name).copy()
+        fs.blas_table[len(fs.blas_table) - 1][field] = value
+        with pytest.raises(ValueError):
+            fs.desc()
+    fs = flat_scenes("golden_file").copy()
+    fs.tex_table[0]["pixel_offset"] = len(fs.tex_pixels)
+    with pytest.raises(ValueError):
+        fs.desc()
+    # device-built scenes carry no nodes / indices: only the triangle range is checked
+    fs = flat_scenes("golden_file").copy()
+    fs.device_build = True
+    d = fs.desc()
+    assert not d.blas[0].nodes and not d.blas[0].tri_indices and d.blas[0].tris
