@@ -365,6 +365,45 @@ def extra_c3(torch, stream, l2_peak):
     return out
 
 
+def extra_c4(torch, stream, l2_peak):
+    """BASELINE configs[3], bounded for one GPU: bunny instanced to ~100 M triangles under a TLAS, 3840 x 2160; 16 of the 256 spp here
+    (the full job sharded over 8 GPUs: tools/c4_multi.py, profiles/r2_multi_gpu.txt).  Mesh BVH and TLAS are built on the device."""
+    import cpu_ray_tracer_b200 as rtb
+    from cpu_ray_tracer_b200 import abi, api, host_build
+    if not os.path.exists(baked("bunny_flat")):
+        return {"skipped": "oracle/_ref/scenes/bunny_flat.rtscene.gz not baked"}
+    mesh = rtb.FlatScene.load(baked("bunny_flat")).tris.copy()
+    c = (mesh["v0"].min(0) + mesh["v0"].max(0)) / 2
+    for f in ("v0", "v1", "v2"):
+        mesh[f] = (mesh[f] - c).astype(np.float32)
+    mesh["centroid"] = ((mesh["v0"] + mesh["v1"]).astype(np.float32) + mesh["v2"]).astype(np.float32) * np.float32(0.3333)
+    n_inst, W, H, spp = 20129, 3840, 2160, 16
+    t0 = time.time()
+    fs = host_build.instanced_grid(mesh, n_inst, tlas="none")   # transforms only: the TLAS is left to the device
+    fs.device_build = True
+    host_s = time.time() - t0
+    t0 = time.time()
+    sc = api.GpuTLASFileScene(fs)
+    create_s = time.time() - t0
+    sc.validate()
+    info = sc.info()
+    r = api.GpuRenderer(sc, abi.RT_INTEGRATOR_PATH, W, H).Init()
+    r.set_stream(stream.cuda_stream)
+    side = int(np.ceil(n_inst ** (1 / 3)))
+    r.camera.SetCameraState((0.0, side * 0.9, -side * 1.2), (0.0, side * 0.3, side * 0.8))
+    r.render(2, first_spp=1)
+    ms, cnt = timed_render(torch, stream, r, spp, 1)
+    rays = cnt["extension_rays"]
+    out = {"workload": f"BASELINE configs[3]: {n_inst} instances of bunny.obj = {n_inst * len(mesh)} triangles under a TLAS (ONE device copy of the mesh), "
+                       f"{W}x{H}, {spp} of the 256 spp on one GPU; mesh BVH + TLAS built on the device",
+           "ms_per_step": ms, "value": rays / ms / 1e3, "unit": "Mrays/s", "rays_per_step": rays, "rays_per_path": rays / cnt["paths"],
+           "rt_scene_create_s": create_s, "host_transforms_s": host_s,
+           "scene": {k: info[k] for k in ("instances", "meshes", "fat_nodes", "triangle_slots", "bytes_geometry", "stack_entries")},
+           "eight_gpus": "256 spp in 1.40 s = 6.69 Grays/s, 7.9x one GPU (profiles/r2_multi_gpu.txt)"}
+    r.close(), sc.close()
+    return out
+
+
 def abi_mod():
     from cpu_ray_tracer_b200 import abi
     return abi
@@ -654,6 +693,7 @@ def bench_ours(args):
                 extras = {}
                 for key, fn in (("C1_whitted_bunny_640x360", lambda: extra_c1(torch, stream, l2_stream)),
                                 ("C3_tlas_1080p_256spp", lambda: extra_c3(torch, stream, l2_stream)),
+                                ("C4_instanced_100M_triangles_4k", lambda: extra_c4(torch, stream, l2_stream)),
                                 ("C5_ray_microbench_10M_triangles", lambda: extra_c5(torch, stream, peaks))):
                     t0 = time.time()
                     try:
