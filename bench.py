@@ -45,7 +45,7 @@ WORKLOAD = ("BASELINE configs[1]: path tracer, FileScene BVH-SAH, wok+teapot sce
             "1920x1080, 64 spp, reference tile RNG")
 DATA = ("synthetic: scene authored for this repo from the reference's wok / teapot OBJ assets (scenes/wok_teapot_scene.xml), generated "
         "stand-in skydome, default camera; no dataset - the samples come from the reference's deterministic per-tile RNG streams")
-KERNEL_PROFILE_GLOB = "r2_*_k_pt_streams8_ncu_full.txt"
+KERNEL_PROFILE_GLOB = "r2_*_default_k_pt_streams8_ncu_full.txt"  # the capture of the DEFAULT build on the bench scene (not the TLAS one)
 
 
 def baked(name):

@@ -366,6 +366,7 @@ __global__ void __launch_bounds__(256) k_refit_up(float4* __restrict__ nodes, co
             // wait for the interior children: the last of them to arrive carries on
             __threadfence();
             if (atomicAdd(&arrived[f0], 2 - interior) + (2 - interior) < 2) continue;
+            __threadfence();
         }
         // this node is final: propagate
         int cur = f0;
@@ -381,6 +382,7 @@ __global__ void __launch_bounds__(256) k_refit_up(float4* __restrict__ nodes, co
             if (!(skipNode1 && pf == 0 && k == 0)) store_child_box(nodes + 4 * (size_t)(fatBase + pf), k, mn, mx);
             __threadfence();
             if (atomicAdd(&arrived[pf], 1) + 1 < 2) break;
+            __threadfence(); // the sibling's stores to pf's record happened before its arrival: order this thread's reads after ours
             cur = pf;
         }
     }
@@ -459,19 +461,20 @@ rt_status rt_scene_refit(rt_scene* s, uint32_t blas_index, const rt_tri* tris, u
             float* r = &roots[6 * gi];
             if (gg.fatCount == 0)
             {
-                // a single leaf: bounds of its triangles; only the refitted mesh can have changed, the others are recomputed from their records' v0 / edges
-                // (exact only for the refitted mesh, which is read from `tris`; single-leaf meshes are <= 2 triangles)
+                // a mesh of <= 2 triangles is a single leaf with no fat node: its root box is kept on the host (rt_scene_create) and
+                // follows a refit here (UpdateNodeBounds of the root leaf, bvh.cpp:45-61)
                 if (&gg == &g)
                 {
-                    for (int a = 0; a < 3; a++) r[a] = 1e30f, r[3 + a] = -1e30f;
+                    float* rb = &s->root_boxes[6 * gi];
+                    for (int a = 0; a < 3; a++) rb[a] = 1e30f, rb[3 + a] = -1e30f;
                     for (uint32_t j = 0; j < gg.triCount; j++)
                         for (int a = 0; a < 3; a++)
                         {
                             const float v[3] = { tris[j].v0[a], tris[j].v1[a], tris[j].v2[a] };
-                            for (int q = 0; q < 3; q++) r[a] = r[a] < v[q] ? r[a] : v[q], r[3 + a] = r[3 + a] > v[q] ? r[3 + a] : v[q];
+                            for (int q = 0; q < 3; q++) rb[a] = rb[a] < v[q] ? rb[a] : v[q], rb[3 + a] = rb[3 + a] > v[q] ? rb[3 + a] : v[q];
                         }
                 }
-                else { set_error("rt_scene_refit: RT_REFIT_REBUILD_TLAS needs meshes of more than two triangles"); return RT_ERR_UNSUPPORTED; }
+                memcpy(r, &s->root_boxes[6 * gi], 24);
                 continue;
             }
             float4 f[3];

@@ -84,6 +84,7 @@ struct rt_scene {
     std::vector<rtb::Geometry> geometries;
     std::vector<int> blas_geometry;
     std::vector<float> blas_T;          // 16 floats per instance (world bounds after a refit)
+    std::vector<float> root_boxes;      // 6 floats per mesh: the box of its BVH root as the builder left it (single-leaf meshes have no fat node)
     int tlas_fat_base = 0, tlas_fat_count = 0;
     int max_blas_depth = 0;
     int stack_entries = 0; // most far children one ray can have pending (bound from the tree depths, rt_scene_create)

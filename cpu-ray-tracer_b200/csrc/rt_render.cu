@@ -1601,7 +1601,9 @@ static rt_status render_pt_streams(rt_renderer* r, int first_spp, int count, int
         if (perWarp > 32 || !r->streamLaneCap) perWarp = 32;
         if (const char* e = getenv("RT_B200_STREAM_FORCE_LANES")) { const int v = atoi(e); if (v >= 1 && v <= 32) perWarp = v; } // experiments: streams per warp
         const unsigned laneMask = perWarp >= 32 ? 0xffffffffu : ((1u << perWarp) - 1);
-        const Streams5Fn fn = r->streamKernel == 8 ? streams8_kernel(r->scene->d.kind == RT_SCENE_TLAS, r->streamMinB, perPixel, r->streamSmemSlots)
+        // (a refit with a TLAS rebuild can deepen the scene after the renderer chose its shared-memory stack: fall back to the local one)
+        const int smemSlots = r->streamSmemSlots > r->scene->stack_entries ? r->streamSmemSlots : 0;
+        const Streams5Fn fn = r->streamKernel == 8 ? streams8_kernel(r->scene->d.kind == RT_SCENE_TLAS, r->streamMinB, perPixel, smemSlots)
                                                    : streams5_kernel(r->scene->d.kind == RT_SCENE_TLAS, r->streamMinB, perPixel);
         const int ks = r->streamKeepShift | (r->streamKernel == 8 && r->streamFastNode ? 256 : 0);
         fn<<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6, clk, ks, laneMask);

@@ -764,7 +764,7 @@ rt_status rt_scene_create(const rt_scene_desc* desc, int device, uint32_t flags,
     if (tlasOnDevice && (st = layout_built_tlas(tb.nodes, desc->blas_count, tlasFatBase, s->nodes, nullptr)) != RT_OK) return fail(st);
     if (bvhKind)
     {
-        s->geometries = geoms, s->blas_geometry = blasGeom;
+        s->geometries = geoms, s->blas_geometry = blasGeom, s->root_boxes = rootBoxes;
         s->tlas_fat_base = tlasFatBase, s->tlas_fat_count = tlasFatCount, s->max_blas_depth = maxBlasDepth;
         s->blas_T.resize(16 * (size_t)desc->blas_count);
         for (uint32_t i = 0; i < desc->blas_count; i++) memcpy(&s->blas_T[16 * (size_t)i], desc->blas[i].T, 64);

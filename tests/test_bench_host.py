@@ -57,3 +57,14 @@ def test_reference_arm_prints_the_contract_line():
     assert set(line["config"]) == set(bench.config_block("w", 64, 36, 64, 1))  # the GPU arm's keys
     if line["cpu_baseline"]["kind"] == "reference":
         assert "strict" in line["cpu_baseline"]["builds"]  # both builds of the reference are reported
+
+
+def test_roofline_issue_figures_come_from_the_default_build_capture():
+    """profiles/ holds ncu captures of several instances of the stream kernel (flat default build, TLAS): bench.py's roofline.issue must
+    read the one of the timed configuration (flat scene, default build)"""
+    import bench
+    prof = bench.kernel_profile()
+    assert prof is not None and "default" in prof["source"]
+    assert prof["kernel"].startswith("void k_pt_streams8<0,")            # TLAS = 0
+    assert 2e10 < prof["warp_instructions_per_launch"] < 6e10              # 64 spp of the bench scene: ~143 warp instructions per ray
+    assert prof["dram_bytes_per_launch"] and prof["dram_bytes_per_launch"] < 1e10
