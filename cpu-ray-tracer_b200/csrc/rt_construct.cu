@@ -7,6 +7,8 @@
 //   * rt_scene_download_bvh the traversal layout read back as reference arrays (parity tests).
 // Arithmetic: min / max by comparison-select exactly as the reference's float3 fminf / fmaxf (tmplmath.h:122-123, 256-257),
 // surface areas with the reference's operation order; compiled with -fmad=false like the rest of the library.
+#include <cooperative_groups.h>
+
 #include <cstring>
 #include <string>
 #include <vector>
@@ -226,23 +228,201 @@ __global__ void __launch_bounds__(TLAS_THREADS, 1) k_build_tlas(const float* __r
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The same build on a THREAD-BLOCK CLUSTER with the live cluster boxes in DISTRIBUTED SHARED MEMORY.
+// The single-CTA kernel above streams all live boxes (32 B each) through one SM for every FindBestMatch: 20 129 instances =
+// 640 KB per call, more than that SM's L1 - 5 us per call, bound by one SM's L2 port.  Here TLAS_CLUSTER CTAs (one per SM) each
+// keep an interleaved slice of the slot array (slot s lives in CTA s % TLAS_CLUSTER at index s / TLAS_CLUSTER) in their own
+// shared memory, scan it in ~3 boxes per thread, and exchange the per-CTA (area, slot) minima through DSMEM: one
+// cluster barrier per FindBestMatch, no global-memory traffic inside the loop.  Every CTA computes the same argmin from the same
+// partials, so all stay in lock step on A / B / C without a broadcast.  Slot updates of a merge are made by the CTAs that own the
+// slots.  Same tree, node for node (the scan order and the tie rule are those of the reference: smaller slot index first).
+// Capacity: TLAS_CLUSTER x (shared memory / 32 B) slots = ~56 000 instances; larger scenes use the single-CTA kernel.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace cg = cooperative_groups;
+constexpr int TLAS_CLUSTER = 8; // portable cluster size
+
+struct TlasPartial { float area; int slot; };
+
+__device__ __forceinline__ int tlas_cluster_best_match(cg::cluster_group& cluster, const float4* __restrict__ bmin, const float4* __restrict__ bmax,
+    const int N, const int A, const int rank, float* sArea, int* sIdx, TlasPartial* part, int& parity)
+{
+    // box A from the CTA that owns slot A
+    const float4* rmin = cluster.map_shared_rank(bmin, A % TLAS_CLUSTER);
+    const float4* rmax = cluster.map_shared_rank(bmax, A % TLAS_CLUSTER);
+    const float4 amin = rmin[A / TLAS_CLUSTER], amax = rmax[A / TLAS_CLUSTER];
+    float best = 1e30f;
+    int bestB = 0x7fffffff;
+    for (int l = threadIdx.x; l * TLAS_CLUSTER + rank < N; l += (int)blockDim.x)
+    {
+        const int B = l * TLAS_CLUSTER + rank;
+        if (B == A) continue;
+        const float4 bmn = bmin[l], bmx = bmax[l];
+        // tlas_bvh.cpp:62-66
+        const float ex = tfmaxf(amax.x, bmx.x) - tfminf(amin.x, bmn.x);
+        const float ey = tfmaxf(amax.y, bmx.y) - tfminf(amin.y, bmn.y);
+        const float ez = tfmaxf(amax.z, bmx.z) - tfminf(amin.z, bmn.z);
+        const float area = ex * ey + ey * ez + ez * ex;
+        if (area < best) best = area, bestB = B; // ascending B per thread: strict < keeps the first
+    }
+    for (int off = 16; off; off >>= 1)
+    {
+        const float oa = __shfl_xor_sync(0xffffffffu, best, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, bestB, off);
+        best_of(best, bestB, oa, oi);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) sArea[warp] = best, sIdx[warp] = bestB;
+    __syncthreads();
+    if (warp == 0)
+    {
+        const int warps = (int)blockDim.x >> 5;
+        best = lane < warps ? sArea[lane] : 1e30f, bestB = lane < warps ? sIdx[lane] : 0x7fffffff;
+        for (int off = 16; off; off >>= 1)
+        {
+            const float oa = __shfl_xor_sync(0xffffffffu, best, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bestB, off);
+            best_of(best, bestB, oa, oi);
+        }
+        if (lane == 0) part[parity].area = best, part[parity].slot = bestB;
+    }
+    cluster.sync(); // every CTA's partial of this call is in its shared memory (and the previous call's reads are over)
+    best = 1e30f, bestB = 0x7fffffff;
+#pragma unroll
+    for (int r = 0; r < TLAS_CLUSTER; r++)
+    {
+        const TlasPartial* q = cluster.map_shared_rank(part, r);
+        best_of(best, bestB, q[parity].area, q[parity].slot);
+    }
+    parity ^= 1; // the next call writes the other buffer: a fast CTA cannot overwrite what a slow one still reads
+    return best < 1e30f ? bestB : -1;
+}
+
+__global__ void __launch_bounds__(1024, 1) k_build_tlas_cluster(const float* __restrict__ worldBounds, const int n, rt_tlas_node32* __restrict__ out,
+    int* __restrict__ depthOf, int* __restrict__ depthOut)
+{
+    extern __shared__ float4 sBoxes[]; // [slice] mins, then [slice] maxs; .w of a min = node index of the slot (the reference's nodeIdx[])
+    __shared__ float sArea[32];
+    __shared__ int sIdx[32];
+    __shared__ TlasPartial part[2];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int slice = (n + TLAS_CLUSTER - 1) / TLAS_CLUSTER;
+    float4* bmin = sBoxes;
+    float4* bmax = sBoxes + slice;
+    // tlas_bvh.cpp:22-30: a leaf per BLAS, nodes 1..n; this CTA's slots
+    for (int l = threadIdx.x; l * TLAS_CLUSTER + rank < n; l += (int)blockDim.x)
+    {
+        const int i = l * TLAS_CLUSTER + rank;
+        const float* w = worldBounds + 6 * (size_t)i;
+        rt_tlas_node32 leaf;
+        leaf.aabb_min[0] = w[0], leaf.aabb_min[1] = w[1], leaf.aabb_min[2] = w[2];
+        leaf.aabb_max[0] = w[3], leaf.aabb_max[1] = w[4], leaf.aabb_max[2] = w[5];
+        leaf.left = 0, leaf.right = (uint32_t)i;
+        out[1 + i] = leaf;
+        bmin[l] = make_float4(w[0], w[1], w[2], __int_as_float(1 + i));
+        bmax[l] = make_float4(w[3], w[4], w[5], 0);
+        depthOf[1 + i] = 1;
+    }
+    __threadfence();
+    cluster.sync();
+    int parity = 0;
+    int nodeIndices = n, used = 1 + n;
+    int A = 0, B = n > 1 ? tlas_cluster_best_match(cluster, bmin, bmax, nodeIndices, A, rank, sArea, sIdx, part, parity) : -1;
+    while (nodeIndices > 1)
+    {
+        const int C = tlas_cluster_best_match(cluster, bmin, bmax, nodeIndices, B, rank, sArea, sIdx, part, parity);
+        if (A == C)
+        {
+            // everyone reads the two boxes (and the last slot) before their owners overwrite them
+            const int last = nodeIndices - 1;
+            const float4 amin = cluster.map_shared_rank(bmin, A % TLAS_CLUSTER)[A / TLAS_CLUSTER], amax = cluster.map_shared_rank(bmax, A % TLAS_CLUSTER)[A / TLAS_CLUSTER];
+            const float4 bmn = cluster.map_shared_rank(bmin, B % TLAS_CLUSTER)[B / TLAS_CLUSTER], bmx = cluster.map_shared_rank(bmax, B % TLAS_CLUSTER)[B / TLAS_CLUSTER];
+            const float4 lmin = cluster.map_shared_rank(bmin, last % TLAS_CLUSTER)[last / TLAS_CLUSTER], lmax = cluster.map_shared_rank(bmax, last % TLAS_CLUSTER)[last / TLAS_CLUSTER];
+            const int ia = __float_as_int(amin.w), ib = __float_as_int(bmn.w);
+            const float4 nmin = make_float4(tfminf(amin.x, bmn.x), tfminf(amin.y, bmn.y), tfminf(amin.z, bmn.z), __int_as_float(used));
+            const float4 nmax = make_float4(tfmaxf(amax.x, bmx.x), tfmaxf(amax.y, bmx.y), tfmaxf(amax.z, bmx.z), 0);
+            cluster.sync();
+            if (threadIdx.x == 0)
+            {
+                if (rank == 0)
+                {
+                    rt_tlas_node32 nn;
+                    nn.left = (uint32_t)ia, nn.right = (uint32_t)ib;
+                    nn.aabb_min[0] = nmin.x, nn.aabb_min[1] = nmin.y, nn.aabb_min[2] = nmin.z;
+                    nn.aabb_max[0] = nmax.x, nn.aabb_max[1] = nmax.y, nn.aabb_max[2] = nmax.z;
+                    out[used] = nn;
+                    const int da = depthOf[ia], db = depthOf[ib];
+                    depthOf[used] = 1 + (da > db ? da : db);
+                }
+                // nodeIdx[A] = nodesUsed++;  nodeIdx[B] = nodeIdx[nodeIndices - 1]  (tlas_bvh.cpp:46-47; when the last slot IS A, B receives the new node)
+                if (A % TLAS_CLUSTER == rank) bmin[A / TLAS_CLUSTER] = nmin, bmax[A / TLAS_CLUSTER] = nmax;
+                if (B % TLAS_CLUSTER == rank) bmin[B / TLAS_CLUSTER] = last == A ? nmin : lmin, bmax[B / TLAS_CLUSTER] = last == A ? nmax : lmax;
+            }
+            used++, nodeIndices--;
+            // (the next call's first cluster barrier comes too late for these writes: it would let a CTA scan before the owners wrote)
+            cluster.sync();
+            B = tlas_cluster_best_match(cluster, bmin, bmax, nodeIndices, A, rank, sArea, sIdx, part, parity);
+        }
+        else A = B, B = C;
+    }
+    if (rank == 0 && threadIdx.x == 0)
+    {
+        __threadfence();
+        const int root = __float_as_int(cluster.map_shared_rank(bmin, A % TLAS_CLUSTER)[A / TLAS_CLUSTER].w);
+        out[0] = out[root]; // tlas_bvh.cpp:52 (merged nodes were written by this thread; a leaf root is slot 0's, written by this CTA)
+        *depthOut = depthOf[root];
+    }
+    cluster.sync(); // no CTA may exit while another still reads its shared memory
+}
+
 // d_out: 2n entries; d_depth: one int (levels of the tree, a single leaf = 1)
 rt_status build_tlas_on_device(int device, const float* d_world_bounds, uint32_t n, rt_tlas_node32* d_out, int* d_depth, cudaStream_t stream)
 {
-    (void)device;
     float4 *boxMin = nullptr, *boxMax = nullptr;
     int* depthOf = nullptr;
-    if (cudaMalloc((void**)&boxMin, (size_t)n * 16) != cudaSuccess || cudaMalloc((void**)&boxMax, (size_t)n * 16) != cudaSuccess ||
-        cudaMalloc((void**)&depthOf, 2 * (size_t)n * 4) != cudaSuccess)
+    struct Free { float4*& a; float4*& b; int*& c; ~Free() { cudaFree(a), cudaFree(b), cudaFree(c); } } guard{ boxMin, boxMax, depthOf };
+    if (cudaMalloc((void**)&depthOf, 2 * (size_t)n * 4) != cudaSuccess) { cudaGetLastError(); set_error("rt_build_tlas: out of device memory"); return RT_ERR_CUDA; }
+    // cluster + distributed shared memory when the live boxes fit the cluster's shared memory (RT_B200_TLAS_BUILD=single forces the other)
+    const size_t slice = ((size_t)n + TLAS_CLUSTER - 1) / TLAS_CLUSTER, smem = slice * 32;
+    int maxSmem = 0;
+    cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    // measured (profiles/r2_tlas_build.txt): below ~8 000 instances the single CTA wins (a call costs ~2 us of cluster barrier + DSMEM
+    // latency however few boxes there are); RT_B200_TLAS_BUILD=cluster / single forces one of them (cluster needs n >= 64)
+    const char* mode = getenv("RT_B200_TLAS_BUILD");
+    const bool force = mode && strcmp(mode, "cluster") == 0;
+    bool useCluster = n >= (force ? 64u : 8192u) && smem + 1024 <= (size_t)maxSmem && !(mode && strcmp(mode, "single") == 0);
+    if (useCluster)
     {
-        cudaGetLastError();
-        cudaFree(boxMin), cudaFree(boxMax), cudaFree(depthOf);
-        set_error("rt_build_tlas: out of device memory");
-        return RT_ERR_CUDA;
+        cudaLaunchConfig_t cfg = {};
+        // the loop is a chain of cluster barriers: a barrier of 8 x 256 threads completes sooner than one of 8 x 1024, and 256 threads
+        // still scan a 20 000-instance scene in ~10 boxes each (RT_B200_TLAS_THREADS for experiments)
+        int threads = 256;
+        if (const char* e = getenv("RT_B200_TLAS_THREADS")) { const int v = atoi(e); if (v == 128 || v == 256 || v == 512 || v == 1024) threads = v; }
+        cfg.gridDim = dim3(TLAS_CLUSTER), cfg.blockDim = dim3(threads), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = TLAS_CLUSTER, attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr, cfg.numAttrs = 1;
+        const int ni = (int)n;
+        if (cudaFuncSetAttribute(k_build_tlas_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+            cudaLaunchKernelEx(&cfg, k_build_tlas_cluster, d_world_bounds, ni, d_out, depthOf, d_depth) != cudaSuccess)
+        {
+            cudaGetLastError(); // no cluster of this shape on this device / partition: the single-CTA kernel builds the same tree
+            useCluster = false;
+        }
     }
-    k_build_tlas<<<1, TLAS_THREADS, 0, stream>>>(d_world_bounds, (int)n, d_out, boxMin, boxMax, depthOf, d_depth);
+    if (!useCluster)
+    {
+        if (cudaMalloc((void**)&boxMin, (size_t)n * 16) != cudaSuccess || cudaMalloc((void**)&boxMax, (size_t)n * 16) != cudaSuccess)
+        {
+            cudaGetLastError();
+            set_error("rt_build_tlas: out of device memory");
+            return RT_ERR_CUDA;
+        }
+        k_build_tlas<<<1, TLAS_THREADS, 0, stream>>>(d_world_bounds, (int)n, d_out, boxMin, boxMax, depthOf, d_depth);
+    }
     const cudaError_t e = cudaStreamSynchronize(stream);
-    cudaFree(boxMin), cudaFree(boxMax), cudaFree(depthOf);
     if (!cuda_ok(e, "rt_build_tlas kernel") || !cuda_ok(cudaGetLastError(), "rt_build_tlas kernel")) return RT_ERR_CUDA;
     return RT_OK;
 }

@@ -90,10 +90,13 @@ def test_device_built_large_mesh_and_instancing():
     sc.close()
 
 
-@pytest.mark.parametrize("n", [1, 2, 3, 7, 257, 5000])
-def test_gpu_tlas_builder_equals_the_reference_clustering(n):
+@pytest.mark.parametrize("mode", ["cluster", "single"])
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 63, 64, 65, 257, 1000, 5000])
+def test_gpu_tlas_builder_equals_the_reference_clustering(n, mode, monkeypatch):
     """random boxes plus lattice-aligned ones (equal union areas: FindBestMatch keeps the FIRST best candidate)"""
     from cpu_ray_tracer_b200 import api, host_build
+    # two kernels build the same tree: a thread-block cluster with the live boxes in distributed shared memory (n >= 64), and one CTA
+    monkeypatch.setenv("RT_B200_TLAS_BUILD", mode)
     rng = np.random.default_rng(n)
     lo = rng.uniform(-20, 20, (n, 3)).astype(np.float32)
     lo[: n // 2] = np.round(lo[: n // 2])                      # ties
@@ -123,10 +126,14 @@ def test_more_instances_than_the_reference_can_hold():
     host = host_build.instanced_grid(mesh, n, tlas="host32")
     with pytest.raises(ValueError):
         host_build.build_tlas(host.instance_bounds)            # the reference's format cannot hold it
-    got, ms = api.build_tlas_gpu(host.instance_bounds, return_ms=True)
-    assert np.array_equal(got["left"], host.tlas_nodes32["left"]) and np.array_equal(got["right"], host.tlas_nodes32["right"])
-    assert biteq(got["aabb_min"], host.tlas_nodes32["aabb_min"]) and biteq(got["aabb_max"], host.tlas_nodes32["aabb_max"])
-    print(f"rt_build_tlas: {n} instances in {ms:.1f} ms on the device")
+    import os
+    for mode in ("cluster", "single"):
+        os.environ["RT_B200_TLAS_BUILD"] = mode
+        got, ms = api.build_tlas_gpu(host.instance_bounds, return_ms=True)
+        assert np.array_equal(got["left"], host.tlas_nodes32["left"]) and np.array_equal(got["right"], host.tlas_nodes32["right"])
+        assert biteq(got["aabb_min"], host.tlas_nodes32["aabb_min"]) and biteq(got["aabb_max"], host.tlas_nodes32["aabb_max"])
+        print(f"rt_build_tlas [{mode}]: {n} instances in {ms:.1f} ms on the device")
+    del os.environ["RT_B200_TLAS_BUILD"]
     po = porthost.PortOracle(host)
     W, H = 256, 128
     rays = po.primary_rays(po.camera_look_at((0.0, 9.0, 40.0), (0.0, 6.0, 20.0), W, H), W, H)   # from behind: the last instances are in front
@@ -218,3 +225,57 @@ def test_refit_argument_errors(flat_scenes):
         kd.Refit(0, flat_scenes("golden_kd").tris)
     assert e.value.status == abi.RT_ERR_UNSUPPORTED
     kd.close()
+
+
+@pytest.mark.parametrize("n_tris", [1, 2, 3, 5, 17])
+def test_device_build_of_tiny_meshes(n_tris):
+    """edge cases of the device build + layout: a mesh of <= 2 triangles is a single leaf (no fat node at all), 3 triangles give one
+    split; flat scene and the same mesh under a device-built TLAS of 1 and 3 instances; refit of the single leaf included"""
+    from cpu_ray_tracer_b200 import api, host_build
+    from oracle import porthost
+    rng = np.random.default_rng(n_tris)
+    c = rng.uniform(-0.6, 0.6, (n_tris, 3)).astype(np.float32) + np.array([0, 0.2, 1.5], np.float32)
+    v0 = c
+    v1 = (c + rng.uniform(0.2, 0.5, (n_tris, 3)).astype(np.float32) * np.array([1, 0, 0], np.float32)).astype(np.float32)
+    v2 = (c + rng.uniform(0.2, 0.5, (n_tris, 3)).astype(np.float32) * np.array([0, 1, 0], np.float32)).astype(np.float32)
+    tris = host_build.make_tris(v0, v1, v2)
+    flat = host_build.flat_scene_from_tris(tris)
+    po = porthost.PortOracle(flat)
+    W, H = 192, 112
+    rays = po.primary_rays(po.camera_default(W, H), W, H)
+    ref, _ = po.find_nearest(rays)
+    assert (ref["obj_idx"] >= 2).any()
+    sc = api.open_scene(device_built(flat), counters=True)
+    sc.validate()
+    nodes, idx = sc.download_bvh(0)
+    want = flat.nodes[:int(flat.blas_table[0]["node_count"])]
+    nodes_equal(nodes, want, f"{n_tris} triangles")
+    assert np.array_equal(idx, flat.tri_indices)
+    assert_hits_equal(sc.FindNearest(rays), ref, f"{n_tris} triangles, device-built")
+    # move the triangles: Refit on a mesh that may be a single leaf
+    moved = displaced(tris, 0.05, seed=3)
+    sc.Refit(0, moved, all_nodes=True)
+    sc.validate()
+    flat2 = flat.copy()
+    flat2.tris[:] = moved
+    flat2.nodes[:len(want)] = porthost.refit_bvh(want, moved, flat.tri_indices, all_nodes=True)
+    po2 = porthost.PortOracle(flat2)
+    assert_hits_equal(sc.FindNearest(rays), po2.find_nearest(rays)[0], f"{n_tris} triangles after Refit")
+    sc.close()
+    for n_inst in (1, 3):
+        inst = host_build.instanced_grid(tris, n_inst, spacing=1.4)
+        poi = porthost.PortOracle(inst)
+        r = poi.primary_rays(poi.camera_default(W, H), W, H)
+        sci = api.open_scene(device_built(inst, tlas=True), counters=True)
+        sci.validate()
+        assert_hits_equal(sci.FindNearest(r), poi.find_nearest(r)[0], f"{n_tris} triangles x {n_inst} instances, all built on the device")
+        if n_inst == 3:
+            sci.Refit(0, moved, rebuild_tlas=True)   # single-leaf meshes keep their root box on the host
+            sci.validate()
+            nodes2 = porthost.refit_bvh(inst.nodes, moved, inst.tri_indices)
+            inst.tris[:], inst.nodes[:] = moved, nodes2
+            bounds = np.stack([host_build.world_bounds(nodes2[0]["aabb_min"], nodes2[0]["aabb_max"], b["T"]) for b in inst.blas_table])
+            inst.tlas_nodes = host_build.build_tlas(bounds)
+            poj = porthost.PortOracle(inst)
+            assert_hits_equal(sci.FindNearest(r), poj.find_nearest(r)[0], f"{n_tris} triangles x 3 instances after Refit + TLAS rebuild")
+        sci.close()
