@@ -458,7 +458,8 @@ def extra_c5(torch, stream, peaks):
             ms = ray_bench.time_batch(lambda: sc.IsOccludedDevice(d_rays.data_ptr(), res.data_ptr(), m, stream.cuda_stream), 3)
         else:
             res = torch.empty((m, 32), dtype=torch.uint8, device="cuda")
-            ms = ray_bench.time_batch(lambda: sc.FindNearestDevice(d_rays.data_ptr(), res.data_ptr(), m, stream.cuda_stream), 3)
+            incoherent = not label.startswith("primary")   # what the caller knows about its batch (rt_find_nearest_device_ex hint)
+            ms = ray_bench.time_batch(lambda: sc.FindNearestDevice(d_rays.data_ptr(), res.data_ptr(), m, stream.cuda_stream, incoherent=incoherent), 3)
         sub = r[rng.choice(m, 1 << 15, replace=False)]
         exact = None
         if occl:

@@ -14,6 +14,7 @@ RT_SCHEDULE_AUTO, RT_SCHEDULE_WAVEFRONT, RT_SCHEDULE_STREAMS = 0, 1, 2
 RT_MATH_EXPF, RT_MATH_ACOSF, RT_MATH_ATAN2F, RT_MATH_SKY_TEXEL = 0, 1, 2, 3
 RT_IPC_HANDLE_BYTES = 64
 RT_REFIT_ALL_NODES, RT_REFIT_REBUILD_TLAS = 1, 2
+RT_RAYS_DEFAULT, RT_RAYS_INCOHERENT = 0, 1
 
 f3 = C.c_float * 3
 f16 = C.c_float * 16

@@ -38,7 +38,7 @@ EXPORTS = [
     "rt_multi_renderer_set_passes", "rt_multi_renderer_clear", "rt_multi_renderer_render", "rt_multi_renderer_sync",
     "rt_multi_renderer_read_accumulator", "rt_multi_renderer_read_pixels", "rt_multi_renderer_get_counters",
     "rt_multi_renderer_reset_counters",
-    "rt_build_tlas", "rt_scene_refit", "rt_scene_download_bvh", "rt_scene_get_info", "rt_scene_validate",
+    "rt_build_tlas", "rt_scene_refit", "rt_scene_download_bvh", "rt_scene_get_info", "rt_scene_validate", "rt_find_nearest_device_ex",
 ]
 
 
@@ -69,6 +69,7 @@ def lib():
     L.rt_is_occluded.argtypes = [vp, vp, vp, sz]
     L.rt_find_nearest_device.argtypes = [vp, vp, vp, sz, vp]
     L.rt_is_occluded_device.argtypes = [vp, vp, vp, sz, vp]
+    L.rt_find_nearest_device_ex.argtypes = [vp, vp, vp, sz, vp, C.c_uint32]
     L.rt_camera_default.argtypes = [C.POINTER(abi.rt_camera), i32, i32]
     L.rt_camera_default.restype = None
     L.rt_camera_look_at.argtypes = [C.POINTER(abi.rt_camera), C.POINTER(C.c_float), C.POINTER(C.c_float), i32, i32]
@@ -243,9 +244,10 @@ class GpuScene:
         _check(lib().rt_is_occluded(self.handle, rays.ctypes.data, out.ctypes.data, len(rays)))
         return out
 
-    def FindNearestDevice(self, d_rays_ptr, d_hits_ptr, n, stream=None):
-        """Buffers already in HBM (e.g. torch tensors' data_ptr()); asynchronous on `stream`."""
-        _check(lib().rt_find_nearest_device(self.handle, d_rays_ptr, d_hits_ptr, n, stream))
+    def FindNearestDevice(self, d_rays_ptr, d_hits_ptr, n, stream=None, incoherent=False):
+        """Buffers already in HBM (e.g. torch tensors' data_ptr()); asynchronous on `stream`.  incoherent=True: the batch is
+        bounce rays, not camera rays (RT_RAYS_INCOHERENT: same hits, the traversal kernel that suits them)."""
+        _check(lib().rt_find_nearest_device_ex(self.handle, d_rays_ptr, d_hits_ptr, n, stream, abi.RT_RAYS_INCOHERENT if incoherent else 0))
 
     def IsOccludedDevice(self, d_rays_ptr, d_out_ptr, n, stream=None):
         _check(lib().rt_is_occluded_device(self.handle, d_rays_ptr, d_out_ptr, n, stream))

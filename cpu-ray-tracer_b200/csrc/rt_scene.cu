@@ -872,7 +872,15 @@ rt_status rt_scene_get_info(const rt_scene* s, rt_scene_info* out)
 
 rt_status rt_find_nearest_device(rt_scene* s, const rt_ray* d_rays, rt_hit* d_hits, size_t n, void* stream)
 {
+    return rt_find_nearest_device_ex(s, d_rays, d_hits, n, stream, RT_RAYS_DEFAULT);
+}
+
+rt_status rt_find_nearest_device_ex(rt_scene* s, const rt_ray* d_rays, rt_hit* d_hits, size_t n, void* stream, uint32_t ray_flags)
+{
     if (!s || (n && (!d_rays || !d_hits))) { set_error("rt_find_nearest_device: null argument"); return RT_ERR_INVALID; }
+    // the caller knows what the library would have to guess: incoherent closest-hit queues run the voted traversal (one action per
+    // warp iteration, like the stream kernel), coherent ones the plain one (profiles/r1_ray_queue_voted_vs_plain.txt)
+    const bool voted = s->voted || (ray_flags & RT_RAYS_INCOHERENT) != 0;
     if (n == 0) return RT_OK;
     RT_CUDA(cudaSetDevice(s->device));
     s->apply_l2_policy((cudaStream_t)stream);
@@ -887,7 +895,7 @@ rt_status rt_find_nearest_device(rt_scene* s, const rt_ray* d_rays, rt_hit* d_hi
             int* fetch = s->next_fetch_counter();
             RT_CUDA(cudaMemsetAsync(fetch, 0, sizeof(int), (cudaStream_t)stream));
             void (*k)(const DScene, const rt_ray*, rt_hit*, int, int*) = nullptr;
-            if (s->voted) { RT_FOR_ACCEL(s->d.kind, (k = counters ? k_find_nearest_persistent<true, A, true> : k_find_nearest_persistent<false, A, true>)); }
+            if (voted) { RT_FOR_ACCEL(s->d.kind, (k = counters ? k_find_nearest_persistent<true, A, true> : k_find_nearest_persistent<false, A, true>)); }
             else { RT_FOR_ACCEL(s->d.kind, (k = counters ? k_find_nearest_persistent<true, A, false> : k_find_nearest_persistent<false, A, false>)); }
             k<<<grid, 128, 0, (cudaStream_t)stream>>>(s->d, d_rays + off, d_hits + off, m, fetch);
         }

@@ -267,6 +267,11 @@ rt_status rt_is_occluded(rt_scene* scene, const rt_ray* rays, uint8_t* occluded,
 /* Same, buffers already resident on the scene's device; `stream` is a cudaStream_t (NULL = default). */
 rt_status rt_find_nearest_device(rt_scene* scene, const rt_ray* d_rays, rt_hit* d_hits, size_t n, void* stream);
 rt_status rt_is_occluded_device(rt_scene* scene, const rt_ray* d_rays, uint8_t* d_occluded, size_t n, void* stream);
+/* rt_find_nearest_device with a hint about the batch (ABI v5).  The reference's callers know what they trace - primary rays from
+ * the camera (Renderer::Tick) or bounce rays (Sample / Trace recursion) - and the two want different kernels: RT_RAYS_INCOHERENT runs
+ * the traversal that votes one action per warp iteration (+3..13 % on bounce rays, slower on camera rays).  Results are identical. */
+enum { RT_RAYS_DEFAULT = 0, RT_RAYS_INCOHERENT = 1 };
+rt_status rt_find_nearest_device_ex(rt_scene* scene, const rt_ray* d_rays, rt_hit* d_hits, size_t n, void* stream, uint32_t ray_flags);
 
 /* ---- camera (template/camera.h) -------------------------------------------------------------- */
 

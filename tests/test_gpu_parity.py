@@ -161,10 +161,10 @@ def test_error_behaviour_kdtree_and_grid_inputs(flat_scenes):
     assert L.rt_scene_create(C.byref(d), 0, 0, C.byref(h)) == abi.RT_ERR_INVALID
 
 
-def test_device_pointer_entry_points(oracles, gpu_scenes, flat_scenes):
-    """rt_find_nearest_device / rt_is_occluded_device on buffers owned by torch"""
+@pytest.mark.parametrize("name", ["golden_file", "golden_tlas", "golden_kd"])
+def test_device_pointer_entry_points(name, oracles, gpu_scenes, flat_scenes):
+    """rt_find_nearest_device(_ex) / rt_is_occluded_device on buffers owned by torch; the coherence hint changes the kernel, not the hits"""
     import torch
-    name = "golden_file"
     po, sc = oracles(name), gpu_scenes(name)
     rays = random_rays(flat_scenes(name), 10000, seed=5)
     ref, _ = po.find_nearest(rays)
@@ -174,6 +174,9 @@ def test_device_pointer_entry_points(oracles, gpu_scenes, flat_scenes):
     sc.FindNearestDevice(d_rays.data_ptr(), d_hits.data_ptr(), len(rays), stream)
     got = d_hits.cpu().numpy().reshape(-1).view(abi.HIT_DTYPE)
     assert_hits_equal(got, ref, "device pointers")
+    d_hits.zero_()
+    sc.FindNearestDevice(d_rays.data_ptr(), d_hits.data_ptr(), len(rays), stream, incoherent=True)   # RT_RAYS_INCOHERENT
+    assert_hits_equal(d_hits.cpu().numpy().reshape(-1).view(abi.HIT_DTYPE), ref, "device pointers, incoherent hint")
     d_occ = torch.empty(len(rays), dtype=torch.uint8, device="cuda")
     sc.IsOccludedDevice(d_rays.data_ptr(), d_occ.data_ptr(), len(rays), stream)
     occ, _ = po.is_occluded(rays)

@@ -45,6 +45,8 @@ def child(n_tris):
         else:
             res = torch.empty((m, 32), dtype=torch.uint8, device="cuda")
             ms = ray_bench.time_batch(lambda: sc.FindNearestDevice(d_rays.data_ptr(), res.data_ptr(), m, stream.cuda_stream), 5)
+            ms2 = ray_bench.time_batch(lambda: sc.FindNearestDevice(d_rays.data_ptr(), res.data_ptr(), m, stream.cuda_stream, incoherent=True), 5)
+            out[label + "_hint_incoherent_Mrays"] = round(m / ms2 / 1e3, 1)
         out[label + "_Mrays"] = round(m / ms / 1e3, 1)
         del d_rays, res
     print(json.dumps(out))
