@@ -114,15 +114,11 @@ void world_bounds_of(const float* root_min, const float* root_max, const float* 
 // TLASBVH::Build on the device
 // ---------------------------------------------------------------------------------------------------------------------
 // The clustering is a serial chain of FindBestMatch calls (each an argmin over the live clusters: O(n) work, first candidate
-// wins ties), so the parallelism is INSIDE a call.  One CTA of 1024 threads runs the whole build: live cluster boxes are kept
-// compact in a (min, max) float4 pair array indexed like the reference's nodeIdx[], every thread scans a strided part,
-// the block reduces (area, index) with warp shuffles + one shared-memory stage.  ~2 block reductions per clustering step.
+// wins ties), so the parallelism is INSIDE a call.  Two kernels build the same tree (build_tlas_on_device picks by size):
+// k_build_tlas, one CTA of 1024 threads: live cluster boxes compact in a (min, max) float4 pair array in global memory, indexed like the
+// reference's nodeIdx[] (.w of a min = the slot's node index); every thread scans a strided part, the block reduces (area, index) with
+// warp shuffles + one shared-memory stage.  k_build_tlas_cluster (below): a thread-block cluster with the boxes in distributed shared memory.
 constexpr int TLAS_THREADS = 1024;
-
-struct TlasWork {
-    float4* boxMin; // per live cluster slot: (min.xyz, as_float(node index))
-    float4* boxMax;
-};
 
 __device__ __forceinline__ void best_of(float& area, int& idx, const float oa, const int oi)
 {
