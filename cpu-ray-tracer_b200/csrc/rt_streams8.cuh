@@ -16,7 +16,10 @@
 //   * every sample is written to its own (frame, pass) image and the images are added to the accumulator in frame order by
 //     k_sum_frames: a multi-frame call leaves the accumulator bit-identical to the reference's Tick sequence
 //     (3. PathTracer/renderer.cpp:117-131) instead of float atomics in completion order;
-//   * the glibc-exact expf / atan2f / acosf paths are out of line (rt_device.cuh beer_scale, sky_texel_exact_cold).
+//   * the glibc-exact expf / atan2f / acosf paths are out of line (rt_device.cuh beer_scale, sky_texel_exact_cold);
+//   * ONE expansion of the NODE action for both ways into it (fast path and full vote): the kernel's hot code is larger than the
+//     instruction cache and every KB shows (profiles/r2_code_footprint.txt: -3.5 % time on the flat scene; moving the NaN-exact
+//     loop out of line or into a per-lane branch of the node step, also measured there, costs more than its 1 KB).
 // Per lane the order of node visits, triangle tests, RNG draws and bounces is the reference's, as before.
 #pragma once
 
@@ -86,8 +89,9 @@ __global__ void __launch_bounds__(128, MINB) k_pt_streams8(const PTState p, cons
 #define TO (TLAS ? O : wO)
 #define TD (TLAS ? D : wD)
     // NODE action: interior-node visits, repeated without a new vote while >= (1 - 2^-keepShift) of the lanes that entered are still
-    // on interior nodes.  The NaN-exact slab variant is chosen per ACTION, not per lane and box: if any lane of this action holds a
-    // degenerate ray everyone takes the select-based min / max (same values for ordinary rays).
+    // on interior nodes.  ONE expansion serves both ways into it (fast path and full vote).
+    // The NaN-exact slab variant is chosen per ACTION, not per lane and box: if any lane of this action holds a degenerate ray
+    // everyone takes the select-based min / max (same values for ordinary rays).
 #define RT_S8_NODE_ACTION(NN)                                                                            \
     {                                                                                                    \
         const int keep = (NN) - ((NN) >> keepShift);                                                     \
@@ -114,180 +118,175 @@ __global__ void __launch_bounds__(128, MINB) k_pt_streams8(const PTState p, cons
     while (true)
     {
         const unsigned mNode = __ballot_sync(FULL, cur >= 0);
-        {
-            // fast path: interior-node lanes are at least half of the lanes that were live at the last full vote, so NODE wins any vote.
-            // Skips the other three ballots, the counts and the refill test (dead lanes wait for the next full vote, which comes as
-            // soon as NODE stops being the majority).
-            const int nN = __popc(mNode);
-            if (fastNode && 2 * nN >= nLive && nN > 0)
-            {
-                RT_S8_NODE_ACTION(nN);
-                continue;
-            }
-        }
-        const unsigned mLeaf = __ballot_sync(FULL, (unsigned)cur > (unsigned)CUR_DEAD);
-        const unsigned mShade = __ballot_sync(FULL, cur == CUR_SHADE);
-        const unsigned mMiss = __ballot_sync(FULL, cur == CUR_MISS);
-        const unsigned mLive = mNode | mLeaf | mShade | mMiss;
+        const int nNodes = __popc(mNode);
+        // fast path: interior-node lanes are at least half of the lanes that were live at the last full vote, so NODE wins any vote.
+        // Skips the other three ballots, the counts and the refill test (dead lanes wait for the next full vote, which comes as
+        // soon as NODE stops being the majority).
+        bool nodeAction = fastNode && 2 * nNodes >= nLive && nNodes > 0;
         bool start = false;
-        // (per-pixel streams end after every path: refill in batches of >= 8 lanes so that refills do not alternate with actions)
-        if ((~mLive & laneMask) != 0 && !poolEmpty && (!PERPIXEL || mLive == 0 || __popc(~mLive & laneMask) >= 8))
+        if (!nodeAction)
         {
-            // refill the dead lanes from the stream pool: one atomic per warp.  laneMask caps the streams per warp
-            // for small jobs (fewer streams than lanes): a chain runs faster the fewer neighbours it waits for
-            const unsigned mDead = ~mLive & laneMask;
-            const int nIdle = __popc(mDead);
-            const int leader = __ffs(mDead) - 1;
-            int base = 0;
-            if (lane == leader) base = atomicAdd(streamCounter, nIdle);
-            base = __shfl_sync(FULL, base, leader);
-            if (base + nIdle >= total) poolEmpty = true;
-            const int stream = base + __popc(mDead & ((1u << lane) - 1));
-            if (cur == CUR_DEAD && ((laneMask >> lane) & 1) && stream < total)
+            const unsigned mLeaf = __ballot_sync(FULL, (unsigned)cur > (unsigned)CUR_DEAD);
+            const unsigned mShade = __ballot_sync(FULL, cur == CUR_SHADE);
+            const unsigned mMiss = __ballot_sync(FULL, cur == CUR_MISS);
+            const unsigned mLive = mNode | mLeaf | mShade | mMiss;
+            // (per-pixel streams end after every path: refill in batches of >= 8 lanes so that refills do not alternate with actions)
+            if ((~mLive & laneMask) != 0 && !poolEmpty && (!PERPIXEL || mLive == 0 || __popc(~mLive & laneMask) >= 8))
             {
-                // RT_SEED_REFERENCE_TILE: a stream is a (tile, frame) pair and runs the tile's 256 pixels; RT_SEED_PER_PIXEL:
-                // a stream is ONE pixel of a (tile, frame) pair (32 consecutive streams = two pixel rows of one tile)
-                const int unit = PERPIXEL ? stream >> 8 : stream, px0 = PERPIXEL ? stream & 255 : 0;
-                const int k = unit / frames, frame = unit - k * frames;
-                const int tile = p.tileBegin + (tileOrder ? tileOrder[k] : k) * p.tileStep;
-                const int tx = tile % p.tilesX, ty = tile / p.tilesX;
-                const int x = tx * 16 + (px0 & 15), y = ty * 16 + (px0 >> 4);
-                seed = PERPIXEL ? pt_pixel_seed(p, x, y, p.firstSpp + frame * p.stride) : pt_seed(p, tile, p.firstSpp + frame * p.stride);
-                tileXY = (tx * 16) | ((ty * 16) << 16);
-                pix = px0 | (frame << PIX_FRAME_SHIFT), depth = 0, inside = false;
-                const float jy = random_float(seed), jx = random_float(seed);
-                wD = primary_dir(cam, (float)x + jx, (float)y + jy);
-                wO = cam.pos;
-                t0 = (unsigned int)clock();
-                start = true;
-            }
-        }
-        else
-        {
-            if (mLive == 0) break;
-            const int nN = __popc(mNode), nL = __popc(mLeaf), nS = __popc(mShade), nM = __popc(mMiss);
-            nLive = nN + nL + nS + nM;
-            if (nN >= nL && nN >= nS && nN >= nM)
-            {
-                RT_S8_NODE_ACTION(nN);
-            }
-            else if (nL >= nS && nL >= nM)
-            {
-                if ((unsigned)cur > (unsigned)CUR_DEAD)
+                // refill the dead lanes from the stream pool: one atomic per warp.  laneMask caps the streams per warp
+                // for small jobs (fewer streams than lanes): a chain runs faster the fewer neighbours it waits for
+                const unsigned mDead = ~mLive & laneMask;
+                const int nIdle = __popc(mDead);
+                const int leader = __ffs(mDead) - 1;
+                int base = 0;
+                if (lane == leader) base = atomicAdd(streamCounter, nIdle);
+                base = __shfl_sync(FULL, base, leader);
+                if (base + nIdle >= total) poolEmpty = true;
+                const int stream = base + __popc(mDead & ((1u << lane) - 1));
+                if (cur == CUR_DEAD && ((laneMask >> lane) & 1) && stream < total)
                 {
-                    const int payload = ~cur;
-                    bool pop = true;
-                    if (TLAS && cur == CUR_EXIT)
-                    {
-                        O = wO, D = wD, rs = make_ray_slab(wO, recip(wD)), exact = needs_exact_slab(wO, wD); // blas_bvh.cpp:385-388
-                    }
-                    else if (TLAS && (payload & INSTANCE_BIT))
-                    {
-                        // TLAS leaf -> BLASBVH::Intersect (blas_bvh.cpp:376-389), SSE lane-sum order of TransformPosition_SSE /
-                        // TransformVector_SSE (tmplmath.cpp:170-191)
-                        const float4* I = s.inst + 4 * (size_t)(payload & ~INSTANCE_BIT);
-                        const float4 r0 = __ldg(I), r1 = __ldg(I + 1), r2 = __ldg(I + 2);
-                        const int4 meta = __ldg((const int4*)(I + 3));
-                        O = f3((wO.x * r0.x + wO.y * r0.y) + (wO.z * r0.z + r0.w),
-                               (wO.x * r1.x + wO.y * r1.y) + (wO.z * r1.z + r1.w),
-                               (wO.x * r2.x + wO.y * r2.y) + (wO.z * r2.z + r2.w));
-                        D = f3((wD.x * r0.x + wD.y * r0.y) + wD.z * r0.z,
-                               (wD.x * r1.x + wD.y * r1.y) + wD.z * r1.z,
-                               (wD.x * r2.x + wD.y * r2.y) + wD.z * r2.z);
-                        rs = make_ray_slab(O, recip(D)), exact = needs_exact_slab(O, D);
-                        instObj = meta.y;
-                        *sp = CUR_EXIT, sp += STRIDE;
-                        cur = meta.x;
-                        pop = false;
-                    }
-                    else
-                    {
-                        // triangle leaf: bvh.cpp:232-241
-                        int slot = payload;
-                        while (true)
-                        {
-                            const float4* T = tris + 3 * (size_t)slot;
-                            const float4 t0_ = __ldg(T), t1 = __ldg(T + 1), t2 = __ldg(T + 2);
-                            const int tag = __float_as_int(t0_.w);
-                            if (intersect_tri(TO, TD, f3(t0_.x, t0_.y, t0_.z), f3(t1.x, t1.y, t1.z), f3(t2.x, t2.y, t2.z), ht, hu, hv))
-                            {
-                                htri = tag & ~LAST_BIT;
-                                const int own = TLAS ? instObj : s.flat_obj_idx; // BLAS' objIdx (blas_bvh.cpp:297) / Tri::objIdx (bvh.cpp:219)
-                                hobj = own >= 0 ? own : __float_as_int(t1.w);
-                            }
-                            if (tag & LAST_BIT) break;
-                            slot++;
-                        }
-                    }
-                    if (pop) sp -= STRIDE, cur = *sp;
-                    if (cur == CUR_END) cur = hobj == -1 ? CUR_MISS : CUR_SHADE;
+                    // RT_SEED_REFERENCE_TILE: a stream is a (tile, frame) pair and runs the tile's 256 pixels; RT_SEED_PER_PIXEL:
+                    // a stream is ONE pixel of a (tile, frame) pair (32 consecutive streams = two pixel rows of one tile)
+                    const int unit = PERPIXEL ? stream >> 8 : stream, px0 = PERPIXEL ? stream & 255 : 0;
+                    const int k = unit / frames, frame = unit - k * frames;
+                    const int tile = p.tileBegin + (tileOrder ? tileOrder[k] : k) * p.tileStep;
+                    const int tx = tile % p.tilesX, ty = tile / p.tilesX;
+                    const int x = tx * 16 + (px0 & 15), y = ty * 16 + (px0 >> 4);
+                    seed = PERPIXEL ? pt_pixel_seed(p, x, y, p.firstSpp + frame * p.stride) : pt_seed(p, tile, p.firstSpp + frame * p.stride);
+                    tileXY = (tx * 16) | ((ty * 16) << 16);
+                    pix = px0 | (frame << PIX_FRAME_SHIFT), depth = 0, inside = false;
+                    const float jy = random_float(seed), jx = random_float(seed);
+                    wD = primary_dir(cam, (float)x + jx, (float)y + jy);
+                    wO = cam.pos;
+                    t0 = (unsigned int)clock();
+                    start = true;
                 }
             }
             else
             {
-                // MISS (sky, renderer.cpp:54) or surface shading, whichever more lanes wait for; then ONE copy
-                // of "sample finished -> write it, next pixel" for the lanes whose path ended
-                const bool doMiss = nM >= nS;
-                bool fin = false;
-                float3 L = f3(0, 0, 0);
-                if (doMiss)
+                if (mLive == 0) break;
+                const int nN = nNodes, nL = __popc(mLeaf), nS = __popc(mShade), nM = __popc(mMiss);
+                nLive = nN + nL + nS + nM;
+                if (nN >= nL && nN >= nS && nN >= nM) nodeAction = true;
+                else if (nL >= nS && nL >= nM)
                 {
-                    if (cur == CUR_MISS) L = sky_color(s, wD), fin = true;
-                }
-                else if (cur == CUR_SHADE)
-                {
-                    float3 w, I, N, nD;
-                    bool nInside;
-                    const int k = pt_surface(s, p.depthLimit, wO, wD, inside, depth, ht, hu, hv, hobj, htri, seed, L, w, I, N, nD, nInside);
-                    if (k == PT_END) fin = true;
-                    else
+                    if ((unsigned)cur > (unsigned)CUR_DEAD)
                     {
-                        if (k == PT_DIFF)
+                        const int payload = ~cur;
+                        bool pop = true;
+                        if (TLAS && cur == CUR_EXIT)
                         {
-                            nD = diffuse_reflection(N, seed);
-                            w = w * dot(nD, N);
+                            O = wO, D = wD, rs = make_ray_slab(wO, recip(wD)), exact = needs_exact_slab(wO, wD); // blas_bvh.cpp:385-388
                         }
-                        wst[depth] = w;
-                        depth++, wO = I + nD * p.eps, wD = nD, inside = nInside;
-                        start = true;
+                        else if (TLAS && (payload & INSTANCE_BIT))
+                        {
+                            // TLAS leaf -> BLASBVH::Intersect (blas_bvh.cpp:376-389), SSE lane-sum order of TransformPosition_SSE /
+                            // TransformVector_SSE (tmplmath.cpp:170-191)
+                            const float4* I = s.inst + 4 * (size_t)(payload & ~INSTANCE_BIT);
+                            const float4 r0 = __ldg(I), r1 = __ldg(I + 1), r2 = __ldg(I + 2);
+                            const int4 meta = __ldg((const int4*)(I + 3));
+                            O = f3((wO.x * r0.x + wO.y * r0.y) + (wO.z * r0.z + r0.w),
+                                   (wO.x * r1.x + wO.y * r1.y) + (wO.z * r1.z + r1.w),
+                                   (wO.x * r2.x + wO.y * r2.y) + (wO.z * r2.z + r2.w));
+                            D = f3((wD.x * r0.x + wD.y * r0.y) + wD.z * r0.z,
+                                   (wD.x * r1.x + wD.y * r1.y) + wD.z * r1.z,
+                                   (wD.x * r2.x + wD.y * r2.y) + wD.z * r2.z);
+                            rs = make_ray_slab(O, recip(D)), exact = needs_exact_slab(O, D);
+                            instObj = meta.y;
+                            *sp = CUR_EXIT, sp += STRIDE;
+                            cur = meta.x;
+                            pop = false;
+                        }
+                        else
+                        {
+                            // triangle leaf: bvh.cpp:232-241
+                            int slot = payload;
+                            while (true)
+                            {
+                                const float4* T = tris + 3 * (size_t)slot;
+                                const float4 t0_ = __ldg(T), t1 = __ldg(T + 1), t2 = __ldg(T + 2);
+                                const int tag = __float_as_int(t0_.w);
+                                if (intersect_tri(TO, TD, f3(t0_.x, t0_.y, t0_.z), f3(t1.x, t1.y, t1.z), f3(t2.x, t2.y, t2.z), ht, hu, hv))
+                                {
+                                    htri = tag & ~LAST_BIT;
+                                    const int own = TLAS ? instObj : s.flat_obj_idx; // BLAS' objIdx (blas_bvh.cpp:297) / Tri::objIdx (bvh.cpp:219)
+                                    hobj = own >= 0 ? own : __float_as_int(t1.w);
+                                }
+                                if (tag & LAST_BIT) break;
+                                slot++;
+                            }
+                        }
+                        if (pop) sp -= STRIDE, cur = *sp;
+                        if (cur == CUR_END) cur = hobj == -1 ? CUR_MISS : CUR_SHADE;
                     }
                 }
-                if (fin)
+                else
                 {
-                    for (int d = depth - 1; d >= 0; d--) L = wst[d] * L;
-                    const int x0 = tileXY & 0xffff, y0 = tileXY >> 16;
-                    int px = pix & 511, pass = (pix >> PIX_PASS_SHIFT) & 15; // `passes` consecutive samples per pixel (renderer.cpp:123)
-                    const int frame = pix >> PIX_FRAME_SHIFT;
-                    const size_t pixel = (x0 + (px & 15)) + (size_t)(y0 + (px >> 4)) * p.W;
-                    if (p.frameCompact)
+                    // MISS (sky, renderer.cpp:54) or surface shading, whichever more lanes wait for; then ONE copy
+                    // of "sample finished -> write it, next pixel" for the lanes whose path ended
+                    const bool doMiss = nM >= nS;
+                    bool fin = false;
+                    float3 L = f3(0, 0, 0);
+                    if (doMiss)
                     {
-                        // the sample's own image, compact layout: (k-th tile of the job) * 256 + pixel of the tile
-                        const int k = __float2int_rn((float)((y0 >> 4) * p.tilesX + (x0 >> 4) - p.tileBegin) * p.invTileStep);
-                        p.frameBuf[((size_t)(frame * p.passes + pass) * p.nTiles + k) * 256 + px] = make_float4(L.x, L.y, L.z, 0);
+                        if (cur == CUR_MISS) L = sky_color(s, wD), fin = true;
                     }
-                    else if (p.frameBuf) p.frameBuf[(size_t)(frame * p.passes + pass) * imagePixels + pixel] = make_float4(L.x, L.y, L.z, 0); // W x H images (look-ahead)
-                    else
+                    else if (cur == CUR_SHADE)
                     {
-                        float* a = (float*)(p.accum + pixel); // renderer.cpp:124, in completion order (callers that asked for no images)
-                        atomicAdd(a + 0, L.x), atomicAdd(a + 1, L.y), atomicAdd(a + 2, L.z);
+                        float3 w, I, N, nD;
+                        bool nInside;
+                        const int k = pt_surface(s, p.depthLimit, wO, wD, inside, depth, ht, hu, hv, hobj, htri, seed, L, w, I, N, nD, nInside);
+                        if (k == PT_END) fin = true;
+                        else
+                        {
+                            if (k == PT_DIFF)
+                            {
+                                nD = diffuse_reflection(N, seed);
+                                w = w * dot(nD, N);
+                            }
+                            wst[depth] = w;
+                            depth++, wO = I + nD * p.eps, wD = nD, inside = nInside;
+                            start = true;
+                        }
                     }
-                    if (++pass == p.passes) pass = 0, px++;
-                    pix = px | (pass << PIX_PASS_SHIFT) | (frame << PIX_FRAME_SHIFT);
-                    if (PERPIXEL ? pass != 0 : px < 256)
+                    if (fin)
                     {
-                        const float jy = random_float(seed), jx = random_float(seed);
-                        wD = primary_dir(cam, (float)(x0 + (px & 15)) + jx, (float)(y0 + (px >> 4)) + jy);
-                        wO = cam.pos, depth = 0, inside = false;
-                        start = true;
-                    }
-                    else
-                    {
-                        cur = CUR_DEAD;
-                        if (tileCost) atomicAdd(&tileCost[((y0 >> 4) * p.tilesX + (x0 >> 4) - p.tileBegin) / p.tileStep], (unsigned long long)((unsigned int)clock() - t0));
+                        for (int d = depth - 1; d >= 0; d--) L = wst[d] * L;
+                        const int x0 = tileXY & 0xffff, y0 = tileXY >> 16;
+                        int px = pix & 511, pass = (pix >> PIX_PASS_SHIFT) & 15; // `passes` consecutive samples per pixel (renderer.cpp:123)
+                        const int frame = pix >> PIX_FRAME_SHIFT;
+                        const size_t pixel = (x0 + (px & 15)) + (size_t)(y0 + (px >> 4)) * p.W;
+                        if (p.frameCompact)
+                        {
+                            // the sample's own image, compact layout: (k-th tile of the job) * 256 + pixel of the tile
+                            const int k = __float2int_rn((float)((y0 >> 4) * p.tilesX + (x0 >> 4) - p.tileBegin) * p.invTileStep);
+                            p.frameBuf[((size_t)(frame * p.passes + pass) * p.nTiles + k) * 256 + px] = make_float4(L.x, L.y, L.z, 0);
+                        }
+                        else if (p.frameBuf) p.frameBuf[(size_t)(frame * p.passes + pass) * imagePixels + pixel] = make_float4(L.x, L.y, L.z, 0); // W x H images (look-ahead)
+                        else
+                        {
+                            float* a = (float*)(p.accum + pixel); // renderer.cpp:124, in completion order (callers that asked for no images)
+                            atomicAdd(a + 0, L.x), atomicAdd(a + 1, L.y), atomicAdd(a + 2, L.z);
+                        }
+                        if (++pass == p.passes) pass = 0, px++;
+                        pix = px | (pass << PIX_PASS_SHIFT) | (frame << PIX_FRAME_SHIFT);
+                        if (PERPIXEL ? pass != 0 : px < 256)
+                        {
+                            const float jy = random_float(seed), jx = random_float(seed);
+                            wD = primary_dir(cam, (float)(x0 + (px & 15)) + jx, (float)(y0 + (px >> 4)) + jy);
+                            wO = cam.pos, depth = 0, inside = false;
+                            start = true;
+                        }
+                        else
+                        {
+                            cur = CUR_DEAD;
+                            if (tileCost) atomicAdd(&tileCost[((y0 >> 4) * p.tilesX + (x0 >> 4) - p.tileBegin) / p.tileStep], (unsigned long long)((unsigned int)clock() - t0));
+                        }
                     }
                 }
             }
         }
+        if (nodeAction) RT_S8_NODE_ACTION(nNodes);
         if (start)
         {
             // FindNearest prologue for the ray (wO, wD): light quad, floor plane (file_scene.cpp:172-173), then the BVH
