@@ -1272,14 +1272,14 @@ __device__ __forceinline__ void sky_texel_exact(const DTexture& T, float3 D, int
 }
 // The same, out of line: ~2 % of the sky lookups get here, and inlined the two restated glibc routines (IEEE divisions, a square root,
 // fdlibm's branch trees) cost the hot kernels 7 KB of SASS and registers on every path (round-1 A/B: +5 ms of 68 on the bench job,
-// profiles/r2_libm_ab_*).  Returns x | y << 16.
-static __device__ __noinline__ int sky_texel_exact_cold(int width, int height, float dx, float dy, float dz)
+// profiles/r2_libm_ab_*).  Returns x | y << 32.
+static __device__ __noinline__ unsigned long long sky_texel_exact_cold(int width, int height, float dx, float dy, float dz)
 {
     DTexture T;
     T.pixels = nullptr, T.width = width, T.height = height;
     int x, y;
     sky_texel_exact(T, f3(dx, dy, dz), x, y);
-    return x | (y << 16);
+    return (unsigned long long)(unsigned)x | ((unsigned long long)(unsigned)y << 32);
 }
 
 __device__ __forceinline__ bool sky_texel_filtered(const DTexture& T, float3 D, int& x, int& y)
@@ -1301,12 +1301,8 @@ __device__ __forceinline__ float3 sky_color(const DScene& s, float3 D)
 #if RT_B200_GLIBC_SKY
     if (!sky_texel_filtered(T, D, x, y))
     {
-        if (T.width < 65536 && T.height < 32768)
-        {
-            const int xy = sky_texel_exact_cold(T.width, T.height, D.x, D.y, D.z);
-            x = xy & 0xffff, y = xy >> 16;
-        }
-        else sky_texel_exact(T, D, x, y);
+        const unsigned long long xy = sky_texel_exact_cold(T.width, T.height, D.x, D.y, D.z);
+        x = (int)(unsigned)xy, y = (int)(xy >> 32);
     }
 #else
     sky_texel_filtered(T, D, x, y); // CUDA's atan2f / acosf only (<= 2 ulp away: a lookup on a texel border can flip)
