@@ -7,10 +7,11 @@
 // sectors going to the 64-entry local-memory stack.
 //   * node step 96 -> ~60 instructions: the two slab tests use packed FADD2 / FMUL2 (rt_device.cuh slab_both, node layout
 //     re-ordered so that box planes meet their ray constants pairwise); near / far by FMNMX instead of selects;
-//   * the node stack lives in SHARED memory, one column of SMEM_SLOTS entries per thread (bank = lane: conflict-free), and is
-//     addressed through a running pointer: push = one predicated STS, top-of-stack = one LDS, no index arithmetic.  Its bottom
-//     slot holds CUR_END, so the pop that empties the stack needs no `sp == 0` test: the lane simply finds CUR_END in `cur`.
-//     Scenes whose trees are deeper than SMEM_SLOTS - 1 run the SMEM_SLOTS = 0 instance (same code, 65-entry local array);
+//   * the node stack is addressed through a running pointer: push = one predicated store, top-of-stack = one load, no index
+//     arithmetic.  Its bottom slot holds CUR_END, so the pop that empties the stack needs no `sp == 0` test: the lane simply finds
+//     CUR_END in `cur`.  Two placements of the same code: SMEM_SLOTS = 0, a 65-entry local-memory array (the DEFAULT: L1-resident,
+//     and measured 1-4 % faster than the carve-out, profiles/r2_stream_kernel_sweeps.txt), or SMEM_SLOTS = 24 / 32, one column per
+//     thread in shared memory (bank = lane: conflict-free; RT_B200_STREAM_SMEM_SLOTS, for trees that fit);
 //   * `cur` is the whole traversal state (>= 0 interior node, leaf / instance references, CUR_* markers): the node loop
 //     carries two registers (cur, sp) instead of packed bool flags;
 //   * every sample is written to its own (frame, pass) image and the images are added to the accumulator in frame order by
