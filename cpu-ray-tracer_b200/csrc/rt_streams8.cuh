@@ -23,6 +23,11 @@
 //     loop out of line or into a per-lane branch of the node step, also measured there, costs more than its 1 KB).
 // Per lane the order of node visits, triangle tests, RNG draws and bounces is the reference's, as before.
 #pragma once
+// 1: a TLAS ray's world-space slab constants are parked in local memory while it is inside an instance (-1 % time on the TLAS scenes,
+// profiles/r2_stream_kernel_sweeps.txt block 6); 0: recomputed when the ray leaves the instance
+#ifndef RT_S8_PARK_WORLD
+#define RT_S8_PARK_WORLD 1
+#endif
 
 namespace rtb {
 
@@ -66,8 +71,11 @@ __global__ void __launch_bounds__(128, MINB) k_pt_streams8(const PTState p, cons
     const float4* __restrict__ tris = s.tris;
     constexpr int STRIDE = SMEM_SLOTS > 0 ? 128 : 1;
     __shared__ int smemStack[SMEM_SLOTS > 0 ? SMEM_SLOTS * 128 : 1];
-    int localStack[SMEM_SLOTS > 0 ? 1 : STACK_SIZE + 1];
-    int* const stackBase = SMEM_SLOTS > 0 ? smemStack + threadIdx.x : localStack;
+    // local-memory placement: 4 ints in front of the stack park the world-space reciprocal direction + degenerate-ray flag of a
+    // TLAS ray while it is inside an instance (leaving the instance reloads them: no divisions, no re-test)
+    constexpr bool PARK = RT_S8_PARK_WORLD && TLAS && SMEM_SLOTS == 0;
+    __align__(16) int localStack[SMEM_SLOTS > 0 ? 1 : STACK_SIZE + 1 + (PARK ? 4 : 0)];
+    int* const stackBase = SMEM_SLOTS > 0 ? smemStack + threadIdx.x : localStack + (PARK ? 4 : 0);
     stackBase[0] = CUR_END;
     int* sp = stackBase + STRIDE;
     bool poolEmpty = false;
@@ -177,7 +185,14 @@ __global__ void __launch_bounds__(128, MINB) k_pt_streams8(const PTState p, cons
                         bool pop = true;
                         if (TLAS && cur == CUR_EXIT)
                         {
-                            O = wO, D = wD, rs = make_ray_slab(wO, recip(wD)), exact = needs_exact_slab(wO, wD); // blas_bvh.cpp:385-388
+                            // blas_bvh.cpp:385-388
+                            O = wO, D = wD;
+                            if (PARK)
+                            {
+                                const int4 pk = *(const int4*)localStack;
+                                rs = make_ray_slab(wO, f3(__int_as_float(pk.x), __int_as_float(pk.y), __int_as_float(pk.z))), exact = pk.w != 0;
+                            }
+                            else rs = make_ray_slab(wO, recip(wD)), exact = needs_exact_slab(wO, wD);
                         }
                         else if (TLAS && (payload & INSTANCE_BIT))
                         {
@@ -298,7 +313,9 @@ __global__ void __launch_bounds__(128, MINB) k_pt_streams8(const PTState p, cons
             const float tp = -(dot(wO, fn) + s.floor_d) / (dot(wD, fn));
             if (tp < ht && tp > 0) ht = tp, hobj = 1;
             if (TLAS) O = wO, D = wD;
-            rs = make_ray_slab(wO, recip(wD)), exact = needs_exact_slab(wO, wD);
+            const float3 wrD = recip(wD);
+            rs = make_ray_slab(wO, wrD), exact = needs_exact_slab(wO, wD);
+            if (PARK) *(int4*)localStack = make_int4(__float_as_int(wrD.x), __float_as_int(wrD.y), __float_as_int(wrD.z), exact ? 1 : 0);
             sp = stackBase + STRIDE, cur = s.root_ref;
             rays++;
         }
