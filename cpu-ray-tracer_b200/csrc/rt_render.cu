@@ -1567,6 +1567,19 @@ static rt_status pt_tile_order(rt_renderer* r, const PTState& p)
 
 static rt_status render_pt_streams(rt_renderer* r, int first_spp, int count, int stride, float4* frameBuf = nullptr, bool compactImages = false)
 {
+    // the stream kernels keep the frame of a launch in 18 bits of a lane's sample counter (rt_streams8.cuh PIX_FRAME_MASK)
+    constexpr int MAX_FRAMES_PER_LAUNCH = 1 << 17;
+    if (count > MAX_FRAMES_PER_LAUNCH)
+    {
+        if (frameBuf) { set_error("rt_renderer_render: more than 131 072 frames in one launch with sample images"); return RT_ERR_UNSUPPORTED; }
+        for (int done = 0; done < count; done += MAX_FRAMES_PER_LAUNCH)
+        {
+            const int frames = count - done < MAX_FRAMES_PER_LAUNCH ? count - done : MAX_FRAMES_PER_LAUNCH;
+            const rt_status st = render_pt_streams(r, first_spp + done * stride, frames, stride);
+            if (st != RT_OK) return st;
+        }
+        return RT_OK;
+    }
     const rt_render_params& P = r->params;
     const int nTiles = num_tiles(P);
     PTState p = {};
@@ -1666,6 +1679,7 @@ static rt_status render_pt_streams_ordered(rt_renderer* r, int first_spp, int co
     size_t framesPerLaunch = r->imageBudgetBytes / (px * 16 * perFrame);
     if (framesPerLaunch < 1) framesPerLaunch = 1;
     if (framesPerLaunch > (size_t)count) framesPerLaunch = (size_t)count;
+    if (framesPerLaunch > (1u << 17)) framesPerLaunch = 1u << 17; // render_pt_streams: MAX_FRAMES_PER_LAUNCH
     const size_t got = ensure_images(r, framesPerLaunch * perFrame, perFrame, px);
     if (got == 0) { set_error("rt_renderer_render: no device memory for one frame's sample images"); return RT_ERR_CUDA; }
     framesPerLaunch = got / perFrame;

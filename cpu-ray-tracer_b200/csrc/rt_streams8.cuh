@@ -23,6 +23,9 @@
 //     loop out of line or into a per-lane branch of the node step, also measured there, costs more than its 1 KB).
 // Per lane the order of node visits, triangle tests, RNG draws and bounces is the reference's, as before.
 #pragma once
+#ifndef RT_S8_LIVE_BALLOT
+#define RT_S8_LIVE_BALLOT 1
+#endif
 // 1: a TLAS ray's world-space slab constants are parked in local memory while it is inside an instance (-1 % time on the TLAS scenes,
 // profiles/r2_stream_kernel_sweeps.txt block 6); 0: recomputed when the ray leaves the instance
 #ifndef RT_S8_PARK_WORLD
@@ -39,8 +42,10 @@ constexpr int CUR_EXIT = (int)0x80000005u;  // stack marker: leave the current i
 // leaf / instance references are ~payload with payload < 0x7ffffffa (rt_scene_create bounds the instance count), i.e. > CUR_EXIT
 // as unsigned numbers; a lane is in LEAF state iff (unsigned)cur > (unsigned)CUR_DEAD
 
-// sample counter of a stream: pixel of the tile (0..256) | pass << 9 | frame of the launch << 13
+// sample counter of a stream: pixel of the tile (0..256) | pass << 9 | frame of the launch << 13 | PIX_POOL_EMPTY (warp-uniform flag kept in
+// every lane's counter: as a variable of its own it cost the TLAS instance of the kernel a local-memory load in front of every full vote)
 constexpr int PIX_PASS_SHIFT = 9, PIX_FRAME_SHIFT = 13;
+constexpr int PIX_POOL_EMPTY = (int)0x80000000u, PIX_FRAME_MASK = 0x3ffff; // frames of one launch < 2^18 (rt_renderer_render bounds them)
 
 // One interior-node visit (bvh.cpp:242-257): both child boxes from one 64-byte record, near child first, left on ties, far
 // child pushed only when hit, 1e30f compared with == like the reference.  STRIDE = distance between two stack slots of a lane.
@@ -78,7 +83,6 @@ __global__ void __launch_bounds__(128, MINB) k_pt_streams8(const PTState p, cons
     int* const stackBase = SMEM_SLOTS > 0 ? smemStack + threadIdx.x : localStack + (PARK ? 4 : 0);
     stackBase[0] = CUR_END;
     int* sp = stackBase + STRIDE;
-    bool poolEmpty = false;
     // stream
     int tileXY = 0, pix = 0, depth = 0;
     bool inside = false;
@@ -121,7 +125,9 @@ __global__ void __launch_bounds__(128, MINB) k_pt_streams8(const PTState p, cons
         if (cur == CUR_END) cur = hobj == -1 ? CUR_MISS : CUR_SHADE;                                     \
     }
 
+#if !RT_S8_LIVE_BALLOT
     int nLive = 32; // live lanes at the last full vote (warp-uniform)
+#endif
     const bool fastNode = (keepShiftAndFlags & 256) != 0;
     const int keepShift = keepShiftAndFlags & 255;
     while (true)
@@ -131,16 +137,26 @@ __global__ void __launch_bounds__(128, MINB) k_pt_streams8(const PTState p, cons
         // fast path: interior-node lanes are at least half of the lanes that were live at the last full vote, so NODE wins any vote.
         // Skips the other three ballots, the counts and the refill test (dead lanes wait for the next full vote, which comes as
         // soon as NODE stops being the majority).
+#if RT_S8_LIVE_BALLOT
+        // (the live lanes are counted with a second ballot here rather than remembered from the last full vote: a register less, and
+        // in the TLAS instance of the kernel ptxas kept that count in local memory - a load in front of every decision)
+        const unsigned mLiveNow = __ballot_sync(FULL, cur != CUR_DEAD);
+        const int nLive = __popc(mLiveNow);
+#endif
         bool nodeAction = fastNode && 2 * nNodes >= nLive && nNodes > 0;
         bool start = false;
         if (!nodeAction)
         {
             const unsigned mLeaf = __ballot_sync(FULL, (unsigned)cur > (unsigned)CUR_DEAD);
             const unsigned mShade = __ballot_sync(FULL, cur == CUR_SHADE);
+#if RT_S8_LIVE_BALLOT
+            const unsigned mLive = mLiveNow, mMiss = mLive & ~(mNode | mLeaf | mShade); // a live lane is in exactly one of the four states
+#else
             const unsigned mMiss = __ballot_sync(FULL, cur == CUR_MISS);
             const unsigned mLive = mNode | mLeaf | mShade | mMiss;
+#endif
             // (per-pixel streams end after every path: refill in batches of >= 8 lanes so that refills do not alternate with actions)
-            if ((~mLive & laneMask) != 0 && !poolEmpty && (!PERPIXEL || mLive == 0 || __popc(~mLive & laneMask) >= 8))
+            if ((~mLive & laneMask) != 0 && pix >= 0 && (!PERPIXEL || mLive == 0 || __popc(~mLive & laneMask) >= 8))
             {
                 // refill the dead lanes from the stream pool: one atomic per warp.  laneMask caps the streams per warp
                 // for small jobs (fewer streams than lanes): a chain runs faster the fewer neighbours it waits for
@@ -150,7 +166,7 @@ __global__ void __launch_bounds__(128, MINB) k_pt_streams8(const PTState p, cons
                 int base = 0;
                 if (lane == leader) base = atomicAdd(streamCounter, nIdle);
                 base = __shfl_sync(FULL, base, leader);
-                if (base + nIdle >= total) poolEmpty = true;
+                if (base + nIdle >= total) pix |= PIX_POOL_EMPTY;
                 const int stream = base + __popc(mDead & ((1u << lane) - 1));
                 if (cur == CUR_DEAD && ((laneMask >> lane) & 1) && stream < total)
                 {
@@ -163,7 +179,7 @@ __global__ void __launch_bounds__(128, MINB) k_pt_streams8(const PTState p, cons
                     const int x = tx * 16 + (px0 & 15), y = ty * 16 + (px0 >> 4);
                     seed = PERPIXEL ? pt_pixel_seed(p, x, y, p.firstSpp + frame * p.stride) : pt_seed(p, tile, p.firstSpp + frame * p.stride);
                     tileXY = (tx * 16) | ((ty * 16) << 16);
-                    pix = px0 | (frame << PIX_FRAME_SHIFT), depth = 0, inside = false;
+                    pix = (pix & PIX_POOL_EMPTY) | px0 | (frame << PIX_FRAME_SHIFT), depth = 0, inside = false;
                     const float jy = random_float(seed), jx = random_float(seed);
                     wD = primary_dir(cam, (float)x + jx, (float)y + jy);
                     wO = cam.pos;
@@ -175,7 +191,9 @@ __global__ void __launch_bounds__(128, MINB) k_pt_streams8(const PTState p, cons
             {
                 if (mLive == 0) break;
                 const int nN = nNodes, nL = __popc(mLeaf), nS = __popc(mShade), nM = __popc(mMiss);
+#if !RT_S8_LIVE_BALLOT
                 nLive = nN + nL + nS + nM;
+#endif
                 if (nN >= nL && nN >= nS && nN >= nM) nodeAction = true;
                 else if (nL >= nS && nL >= nM)
                 {
@@ -270,7 +288,7 @@ __global__ void __launch_bounds__(128, MINB) k_pt_streams8(const PTState p, cons
                         for (int d = depth - 1; d >= 0; d--) L = wst[d] * L;
                         const int x0 = tileXY & 0xffff, y0 = tileXY >> 16;
                         int px = pix & 511, pass = (pix >> PIX_PASS_SHIFT) & 15; // `passes` consecutive samples per pixel (renderer.cpp:123)
-                        const int frame = pix >> PIX_FRAME_SHIFT;
+                        const int frame = (pix >> PIX_FRAME_SHIFT) & PIX_FRAME_MASK;
                         const size_t pixel = (x0 + (px & 15)) + (size_t)(y0 + (px >> 4)) * p.W;
                         if (p.frameCompact)
                         {
@@ -285,7 +303,7 @@ __global__ void __launch_bounds__(128, MINB) k_pt_streams8(const PTState p, cons
                             atomicAdd(a + 0, L.x), atomicAdd(a + 1, L.y), atomicAdd(a + 2, L.z);
                         }
                         if (++pass == p.passes) pass = 0, px++;
-                        pix = px | (pass << PIX_PASS_SHIFT) | (frame << PIX_FRAME_SHIFT);
+                        pix = (pix & PIX_POOL_EMPTY) | px | (pass << PIX_PASS_SHIFT) | (frame << PIX_FRAME_SHIFT);
                         if (PERPIXEL ? pass != 0 : px < 256)
                         {
                             const float jy = random_float(seed), jx = random_float(seed);
