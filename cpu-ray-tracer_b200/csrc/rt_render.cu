@@ -1122,6 +1122,10 @@ struct rt_renderer {
     int streamKernel = 8; // 8 = current (rt_streams8.cuh); 5 = the round-1 kernel, kept for A/B profiling (RT_B200_STREAM_KERNEL)
     bool streamMeasuredLpt = true;
     int streamMinB = 7, streamKeepShift = 1;
+    // version 8 without RT_B200_STREAM_MINB: 8 CTAs/SM (64 registers, shading code spills) for throughput-bound jobs - TLAS scenes, or
+    // >= 8 streams per resident lane - and 7 (72 registers) where the longest chain bounds the job (profiles/r2_stream_kernel_sweeps.txt block 8)
+    bool streamMinBAuto = false;
+    int streamCtasPerSm8 = 8;
     bool streamFastNode = true; // version 8: skip the full vote while interior-node lanes are the majority
     int streamSmemSlots = 0;  // version 8: stack slots per thread in shared memory (0 = local-memory stack), from the scene's tree depths
     // ordered accumulation: every sample of a launch goes to its own (frame, pass) image, k_sum_frames adds them in order
@@ -1368,6 +1372,13 @@ rt_status rt_renderer_create(rt_scene* scene, const rt_render_params* params, rt
             r->streamSmemSlots = streams8_slots(scene, perPixel);
             oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, r->streamKernel == 8 ? streams8_kernel(scene->d.kind == RT_SCENE_TLAS, r->streamMinB, perPixel, r->streamSmemSlots)
                                                                                            : streams5_kernel(scene->d.kind == RT_SCENE_TLAS, r->streamMinB, perPixel), 128, 0);
+            if (r->streamKernel == 8 && !perPixel && !getenv("RT_B200_STREAM_MINB") && !getenv("RT_B200_STREAM_CTAS"))
+            {
+                int occ8 = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ8, streams8_kernel(scene->d.kind == RT_SCENE_TLAS, 8, perPixel, r->streamSmemSlots), 128, 0) == cudaSuccess && occ8 > 0)
+                    r->streamMinBAuto = true, r->streamCtasPerSm8 = occ8;
+                else cudaGetLastError();
+            }
         }
         else if (scene->d.kind == RT_SCENE_FLAT_KDTREE) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams_alt<ACCEL_KD>, 128, 0);
         else if (scene->d.kind == RT_SCENE_FLAT_GRID) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pt_streams_alt<ACCEL_GRID>, 128, 0);
@@ -1608,7 +1619,9 @@ static rt_status render_pt_streams(rt_renderer* r, int first_spp, int count, int
     if (r->streamKernel != 0)
     {
         // small jobs: spread the streams over all resident warps instead of filling the first warps completely
-        const long long warps = (long long)r->sms * r->streamCtasPerSm * 4;
+        int minb = r->streamMinB, ctasPerSm = r->streamCtasPerSm;
+        if (r->streamMinBAuto && (r->scene->d.kind == RT_SCENE_TLAS || (long long)p.slots >= 8ll * r->sms * r->streamCtasPerSm8 * 128)) minb = 8, ctasPerSm = r->streamCtasPerSm8;
+        const long long warps = (long long)r->sms * ctasPerSm * 4;
         long long perWarp = ((long long)p.slots + warps - 1) / warps;
         if (perWarp < 1) perWarp = 1;
         if (perWarp > 32 || !r->streamLaneCap) perWarp = 32;
@@ -1616,10 +1629,10 @@ static rt_status render_pt_streams(rt_renderer* r, int first_spp, int count, int
         const unsigned laneMask = perWarp >= 32 ? 0xffffffffu : ((1u << perWarp) - 1);
         // (a refit with a TLAS rebuild can deepen the scene after the renderer chose its shared-memory stack: fall back to the local one)
         const int smemSlots = r->streamSmemSlots > r->scene->stack_entries ? r->streamSmemSlots : 0;
-        const Streams5Fn fn = r->streamKernel == 8 ? streams8_kernel(r->scene->d.kind == RT_SCENE_TLAS, r->streamMinB, perPixel, smemSlots)
-                                                   : streams5_kernel(r->scene->d.kind == RT_SCENE_TLAS, r->streamMinB, perPixel);
+        const Streams5Fn fn = r->streamKernel == 8 ? streams8_kernel(r->scene->d.kind == RT_SCENE_TLAS, minb, perPixel, smemSlots)
+                                                   : streams5_kernel(r->scene->d.kind == RT_SCENE_TLAS, minb, perPixel);
         const int ks = r->streamKeepShift | (r->streamKernel == 8 && r->streamFastNode ? 256 : 0);
-        fn<<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6, clk, ks, laneMask);
+        fn<<<r->sms * ctasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6, clk, ks, laneMask);
     }
     else if (r->scene->d.kind == RT_SCENE_FLAT_KDTREE) k_pt_streams_alt<ACCEL_KD><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
     else if (r->scene->d.kind == RT_SCENE_FLAT_GRID) k_pt_streams_alt<ACCEL_GRID><<<r->sms * r->streamCtasPerSm, 128, 0, r->stream>>>(p, r->scene->d, r->cam, order, count, r->dCount + 6);
